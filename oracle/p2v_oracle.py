@@ -1,0 +1,264 @@
+"""ctypes front-end of the CPU oracle (TEST INFRASTRUCTURE -- see p2v_oracle.c).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs
+may import this module.  Nothing under ``phylo2vec_b200/`` does.
+
+Every function restates one reference function (paths relative to
+/root/reference); the citation is in the docstring and in p2v_oracle.c.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libp2v_oracle.so")
+_SRC = os.path.join(_HERE, "p2v_oracle.c")
+
+EBADINPUT = -2
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/p2v_oracle.c with oracle/Makefile (gcc, OpenMP)."""
+    stale = (not os.path.exists(_SO)) or os.path.getmtime(_SO) < os.path.getmtime(_SRC)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_SO)
+        i64 = ctypes.c_int64
+        p = ctypes.c_void_p
+        _lib.p2vo_check_v.restype = i64
+        _lib.p2vo_check_v.argtypes = [p, i64]
+        _lib.p2vo_is_unordered.restype = ctypes.c_int
+        _lib.p2vo_is_unordered.argtypes = [p, i64, p]
+        for name in ("p2vo_to_pairs", "p2vo_to_pairs_avl", "p2vo_to_pairs_loop", "p2vo_to_pairs_list",
+                     "p2vo_to_ancestry", "p2vo_to_edges", "p2vo_build_vector", "p2vo_from_pairs",
+                     "p2vo_from_ancestry", "p2vo_from_edges"):
+            f = getattr(_lib, name)
+            f.restype = ctypes.c_int
+            f.argtypes = [p, i64, p]
+        _lib.p2vo_order_cherries.restype = ctypes.c_int
+        _lib.p2vo_order_cherries.argtypes = [p, i64]
+        _lib.p2vo_cophenetic_literal.restype = ctypes.c_int
+        _lib.p2vo_cophenetic_literal.argtypes = [p, p, i64, ctypes.c_int, p]
+        _lib.p2vo_cophenetic_rows.restype = ctypes.c_int
+        _lib.p2vo_cophenetic_rows.argtypes = [p, p, i64, ctypes.c_int, i64, i64, p]
+        _lib.p2vo_cophenetic_matrix_literal.restype = ctypes.c_int
+        _lib.p2vo_cophenetic_matrix_literal.argtypes = [p, i64, ctypes.c_int, p]
+        _lib.p2vo_to_newick.restype = i64
+        _lib.p2vo_to_newick.argtypes = [p, i64, ctypes.c_char_p, i64]
+        _lib.p2vo_num_threads.restype = ctypes.c_int
+        _lib.p2vo_batch.restype = ctypes.c_int
+        _lib.p2vo_batch.argtypes = [ctypes.c_int, p, i64, i64, p, p, ctypes.c_int]
+        _lib.p2vo_cophenetic_batch.restype = ctypes.c_int
+        _lib.p2vo_cophenetic_batch.argtypes = [p, p, i64, i64, ctypes.c_int, p, ctypes.c_int]
+    return _lib
+
+
+def _i64(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int64))
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class InvalidVector(AssertionError):
+    """Raised where the reference panics in check_max (vector/base.rs:60-67)."""
+
+
+def _raise(rc: int, v: np.ndarray):
+    if rc > 0:
+        i = rc - 1
+        raise InvalidVector(
+            f"Validation failed: v[{i}] = {int(v[i])} is out of bounds (max = {2 * i})")
+    if rc < 0:
+        raise ValueError(f"oracle: malformed input (code {rc})")
+
+
+def check_v(v) -> None:
+    """vector/base.rs:50-54"""
+    v = _i64(v)
+    _raise(int(lib().p2vo_check_v(_ptr(v), v.size)), v)
+
+
+def is_unordered(v) -> bool:
+    """vector/base.rs:92-101"""
+    v = _i64(v)
+    bad = ctypes.c_int64(0)
+    r = lib().p2vo_is_unordered(_ptr(v), v.size, ctypes.byref(bad))
+    _raise(int(bad.value), v)
+    return bool(r)
+
+
+def _decode(fn: str, v, cols: int, rows_per_k: int = 1) -> np.ndarray:
+    v = _i64(v)
+    k = v.size
+    out = np.zeros((rows_per_k * k, cols), dtype=np.int64)
+    _raise(int(getattr(lib(), fn)(_ptr(v), k, _ptr(out))), v)
+    return out
+
+
+def to_pairs(v) -> np.ndarray:
+    """vector/convert.rs:103-109 -> (k,2)"""
+    return _decode("p2vo_to_pairs", v, 2)
+
+
+def to_pairs_avl(v) -> np.ndarray:
+    """vector/convert.rs:83-87 + vector/avl.rs:35-52,193-211"""
+    return _decode("p2vo_to_pairs_avl", v, 2)
+
+
+def to_pairs_loop(v) -> np.ndarray:
+    """vector/convert.rs:39-76"""
+    return _decode("p2vo_to_pairs_loop", v, 2)
+
+
+def to_pairs_list(v) -> np.ndarray:
+    """naive list-insert form of vector/avl.rs:35-52"""
+    return _decode("p2vo_to_pairs_list", v, 2)
+
+
+def to_ancestry(v) -> np.ndarray:
+    """vector/convert.rs:167-188 -> (k,3)"""
+    return _decode("p2vo_to_ancestry", v, 3)
+
+
+def to_edges(v) -> np.ndarray:
+    """vector/convert.rs:227-248 -> (2k,2)"""
+    return _decode("p2vo_to_edges", v, 2, rows_per_k=2)
+
+
+def _encode(fn: str, a, cols: int) -> np.ndarray:
+    a = _i64(a).reshape(-1, cols)
+    k = a.shape[0]
+    out = np.zeros(k, dtype=np.int64)
+    rc = int(getattr(lib(), fn)(_ptr(a), k, _ptr(out)))
+    if rc:
+        raise ValueError(f"oracle: malformed input (code {rc})")
+    return out
+
+
+def build_vector(cherries) -> np.ndarray:
+    """vector/convert.rs:320-337"""
+    return _encode("p2vo_build_vector", cherries, 3)
+
+
+def from_pairs(pairs) -> np.ndarray:
+    """vector/convert.rs:23-30"""
+    return _encode("p2vo_from_pairs", pairs, 2)
+
+
+def from_ancestry(anc) -> np.ndarray:
+    """vector/convert.rs:129-136"""
+    return _encode("p2vo_from_ancestry", anc, 3)
+
+
+def from_edges(edges) -> np.ndarray:
+    """vector/convert.rs:201-213"""
+    e = _i64(edges).reshape(-1, 2)
+    out = np.zeros(e.shape[0] // 2, dtype=np.int64)
+    rc = int(lib().p2vo_from_edges(_ptr(e), e.shape[0], _ptr(out)))
+    if rc:
+        raise ValueError(f"oracle: malformed input (code {rc})")
+    return out
+
+
+def order_cherries(anc) -> np.ndarray:
+    """vector/convert.rs:449-477 (returns the reordered, normalised cherries)"""
+    a = _i64(anc).reshape(-1, 3).copy()
+    rc = int(lib().p2vo_order_cherries(_ptr(a), a.shape[0]))
+    if rc:
+        raise ValueError(f"oracle: malformed input (code {rc})")
+    return a
+
+
+def _split_tree(tree):
+    """PyTree dispatch of py-phylo2vec/src/lib.rs:20-24,144-156."""
+    t = np.asarray(tree)
+    if t.ndim == 2:
+        m = np.ascontiguousarray(t, dtype=np.float64)
+        v = m[:, 0].astype(np.int64)  # matrix/base.rs:108-121 (`as usize`)
+        bls = np.ascontiguousarray(m[:, 1:3])
+        return v, bls
+    if t.ndim == 1:
+        return _i64(t), None
+    raise TypeError("tree must be a 1-D vector or a 2-D matrix")
+
+
+def cophenetic_distances(tree, unrooted: bool = False) -> np.ndarray:
+    """Literal vector/graph.rs:20-90 (+ matrix/graph.rs:23-26). (n,n) float64."""
+    v, bls = _split_tree(tree)
+    k = v.size
+    out = np.zeros((k + 1, k + 1), dtype=np.float64)
+    _raise(int(lib().p2vo_cophenetic_literal(_ptr(v), _ptr(bls), k, int(unrooted), _ptr(out))), v)
+    return out
+
+
+def cophenetic_rows(tree, unrooted: bool, row_begin: int, row_end: int) -> np.ndarray:
+    """Closed-form rows (long-double path sums) for sizes where the literal
+    (2k+1)^2 scratch does not fit; pinned against the literal form in tests."""
+    v, bls = _split_tree(tree)
+    k = v.size
+    out = np.zeros((row_end - row_begin, k + 1), dtype=np.float64)
+    _raise(int(lib().p2vo_cophenetic_rows(_ptr(v), _ptr(bls), k, int(unrooted), row_begin, row_end,
+                                          _ptr(out))), v)
+    return out
+
+
+def to_newick(v) -> str:
+    """vector/convert.rs:394-397 (host only)"""
+    v = _i64(v)
+    n = int(lib().p2vo_to_newick(_ptr(v), v.size, None, 0))
+    if n < 0:
+        raise ValueError(f"oracle: to_newick failed ({n})")
+    buf = ctypes.create_string_buffer(n + 2)
+    lib().p2vo_to_newick(_ptr(v), v.size, buf, n + 2)
+    return buf.value.decode()
+
+
+# ---- batch drivers (CPU baseline) -----------------------------------------
+OPS = {"to_pairs": 0, "to_ancestry": 1, "to_edges": 2, "from_pairs": 3, "from_ancestry": 4,
+       "from_edges": 5}
+
+
+def num_threads() -> int:
+    return int(lib().p2vo_num_threads())
+
+
+def batch(op: str, x: np.ndarray, k: int, nthreads: int = 0, out: Optional[np.ndarray] = None):
+    """Run one reference call per tree, OpenMP parallel-for over trees."""
+    x = _i64(x)
+    B = x.shape[0]
+    shape = {0: (B, k, 2), 1: (B, k, 3), 2: (B, 2 * k, 2), 3: (B, k), 4: (B, k), 5: (B, k)}[OPS[op]]
+    if out is None:
+        out = np.empty(shape, dtype=np.int64)
+    status = np.zeros(B, dtype=np.int32)
+    lib().p2vo_batch(OPS[op], _ptr(x), B, k, _ptr(out), _ptr(status), nthreads)
+    return out, status
+
+
+def cophenetic_batch(v: np.ndarray, bls: Optional[np.ndarray], unrooted: bool = False,
+                     nthreads: int = 0) -> np.ndarray:
+    v = _i64(v)
+    B, k = v.shape
+    if bls is not None:
+        bls = np.ascontiguousarray(bls, dtype=np.float64)
+    out = np.empty((B, k + 1, k + 1), dtype=np.float64)
+    lib().p2vo_cophenetic_batch(_ptr(v), _ptr(bls), B, k, int(unrooted), _ptr(out), nthreads)
+    return out

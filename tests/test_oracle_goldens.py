@@ -1,0 +1,89 @@
+"""Pins the CPU oracle against the reference's own golden vectors
+(tests/golden/reference_goldens.json, transcribed from the reference's rstest
+tables, doctests and docs notebook -- see make_reference_goldens.py)."""
+
+import numpy as np
+import pytest
+
+from oracle import p2v_oracle as O
+
+
+def test_to_pairs(goldens):
+    for g in goldens["to_pairs"]:
+        exp = np.array(g["pairs"])
+        for fn in (O.to_pairs, O.to_pairs_avl, O.to_pairs_list):
+            assert np.array_equal(fn(g["v"]), exp), (fn.__name__, g["src"])
+
+
+def test_to_ancestry(goldens):
+    for g in goldens["to_ancestry"]:
+        assert np.array_equal(O.to_ancestry(g["v"]), np.array(g["ancestry"])), g["src"]
+
+
+def test_to_edges(goldens):
+    for g in goldens["to_edges"]:
+        assert np.array_equal(O.to_edges(g["v"]), np.array(g["edges"])), g["src"]
+
+
+def test_to_newick(goldens):
+    for g in goldens["to_newick"]:
+        assert O.to_newick(g["v"]) == g["newick"], g["src"]
+
+
+def test_encode(goldens):
+    for g in goldens["from_pairs"]:
+        assert np.array_equal(O.from_pairs(g["pairs"]), g["v"]), g["src"]
+    for g in goldens["from_ancestry"]:
+        assert np.array_equal(O.from_ancestry(g["ancestry"]), g["v"]), g["src"]
+    for g in goldens["from_edges"]:
+        assert np.array_equal(O.from_edges(g["edges"]), g["v"]), g["src"]
+    for g in goldens["build_vector"]:
+        assert np.array_equal(O.build_vector(g["cherries"]), g["v"]), g["src"]
+    for g in goldens["order_cherries"]:
+        assert np.array_equal(O.order_cherries(g["in"]), np.array(g["out"])), g["src"]
+
+
+def test_validation(goldens):
+    for v in goldens["check_v"]["ok"]:
+        O.check_v(v)
+    for v in goldens["check_v"]["panic"]:
+        with pytest.raises(AssertionError, match="out of bounds"):
+            O.check_v(v)
+    for g in goldens["is_unordered"]:
+        if g["expected"] == "panic":
+            with pytest.raises(AssertionError):
+                O.is_unordered(g["v"])
+        else:
+            assert O.is_unordered(g["v"]) == g["expected"], g["src"]
+
+
+def test_check_v_message():
+    # phylo2vec/src/vector/base.rs:60-67
+    with pytest.raises(AssertionError) as e:
+        O.check_v([0, 0, 9, 1])
+    assert str(e.value) == "Validation failed: v[2] = 9 is out of bounds (max = 4)"
+
+
+def test_cophenetic_vector(goldens):
+    for g in goldens["cophenetic_vector"]:
+        got = O.cophenetic_distances(np.array(g["v"], dtype=np.int64), g["unrooted"])
+        exp = np.array(g["d"], dtype=np.float64)
+        assert got.dtype == np.float64 and got.shape == exp.shape
+        assert np.array_equal(got, exp), g["src"]      # exact: reference uses assert_eq
+        n = exp.shape[0]
+        rows = O.cophenetic_rows(np.array(g["v"], dtype=np.int64), g["unrooted"], 0, n)
+        assert np.array_equal(rows, exp), g["src"]
+
+
+def test_cophenetic_matrix(goldens):
+    for g in goldens["cophenetic_matrix"]:
+        m = np.array(g["m"], dtype=np.float64)
+        got = O.cophenetic_distances(m, g["unrooted"])
+        exp = np.array(g["d"], dtype=np.float64)
+        if "round" in g:
+            assert np.array_equal(got.round(g["round"]), exp), g["src"]
+        else:
+            # the reference's own tolerance: matrix/graph.rs:99-109
+            assert np.allclose(got, exp, rtol=1e-5, atol=1e-8), g["src"]
+        rows = O.cophenetic_rows(m, g["unrooted"], 0, exp.shape[0])
+        assert np.allclose(rows, got, rtol=1e-14, atol=0), g["src"]
