@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (BASELINE.json): batched to_ancestry at n=1000, batch 1M,
+plus the cophenetic row kernel at n=65536.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A step = one pass of to_ancestry over one batch of synthetic vectors (1M trees per
+GPU, int64, inputs resident in HBM and larger than L2).  Prints ONE JSON line (rank 0).
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_LEAVES = 1000
+K = N_LEAVES - 1
+BATCH = 1_000_000
+METRIC = "trees/s to_ancestry @n=1k batch 1M; cophenetic matrix HBM GB/s @n=64k"
+WORKLOAD = "to_ancestry: batch of 1M random trees n=1000, int64 (BASELINE.json configs[1]); v ~ UniformInt{0..2i}"
+COPH_N = 65536
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synth_vectors_device(torch, B, k, seed, device):
+    g = torch.Generator(device=device).manual_seed(seed)
+    hi = (2 * torch.arange(k, device=device) + 1).to(torch.float64)
+    out = torch.empty((B, k), dtype=torch.int64, device=device)
+    step = 1 << 17
+    for b0 in range(0, B, step):
+        b1 = min(B, b0 + step)
+        out[b0:b1] = (torch.rand((b1 - b0, k), generator=g, device=device, dtype=torch.float64) * hi).to(torch.int64)
+    return out
+
+
+def synth_vectors_host(np, B, k, seed):
+    rng = np.random.Generator(np.random.Philox(seed))
+    hi = 2 * np.arange(k, dtype=np.int64) + 1
+    return (rng.random((B, k)) * hi).astype(np.int64)
+
+
+# --------------------------------------------------------------------------- reference arm
+def cpu_baseline(np, sample_trees, nthreads=0, repeats=1):
+    """The reference's CPU algorithm (oracle port: AVL decode + relabel pass,
+    phylo2vec/src/vector/avl.rs, convert.rs:167-188), one reference call per tree,
+    OpenMP parallel-for over trees on the host cores."""
+    from oracle import p2v_oracle as O
+    V = synth_vectors_host(np, sample_trees, K, seed=1)
+    out = np.empty((sample_trees, K, 3), dtype=np.int64)
+    O.batch("to_ancestry", V[:256], K, nthreads=nthreads)      # warm up threads / pages
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        O.batch("to_ancestry", V, K, nthreads=nthreads, out=out)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    cores = O.num_threads() if nthreads <= 0 else nthreads
+    return sample_trees / best, cores, best
+
+
+def run_reference(args):
+    import numpy as np
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 65536
+    rates = []
+    for _ in range(args.warmup):
+        cpu_baseline(np, 4096)
+    t_all = 0.0
+    cores = 0
+    for _ in range(args.steps):
+        r, cores, dt = cpu_baseline(np, sample)
+        rates.append(r)
+        t_all += dt
+    value = sample * len(rates) / t_all
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "trees/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, len(rates)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": f"{sample} trees per step"},
+        "cpu_baseline": {"value": value, "unit": "trees/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} trees of n=1000 per step, all host threads (OpenMP over trees)"},
+        "e2e": {"value": value, "unit": "trees/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from phylo2vec_b200 import _capi, batch as pb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    lib = _capi.load()
+    peaks, peak_src = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B = args.batch
+    V = synth_vectors_device(torch, B, K, seed=1234 + rank, device=device)
+    out = torch.empty((B, K, 3), dtype=torch.int64, device=device)
+    status = torch.empty(B, dtype=torch.int32, device=device)
+    stream = torch.cuda.current_stream(device)
+
+    def step():
+        rc = lib.p2v_to_ancestry_batch(V.data_ptr(), 8, B, K, out.data_ptr(), status.data_ptr(), None, 0,
+                                       stream.cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"p2v_to_ancestry_batch failed: {lib.p2v_last_error()}")
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _capi.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = _capi.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if int(status.count_nonzero()) != 0:
+        raise RuntimeError("decode reported invalid vectors on synthetic input")
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * B / (ms_step * 1e-3)
+    alg_bytes = 4 * K * 8 * B                       # 4*k*w per tree, w = 8
+    achieved = alg_bytes / (ms_total / args.steps * 1e-3) / 1e9
+    peak = float(peaks["hbm_gbs"])
+
+    # ---- parity spot check on the timed buffers (never timed) -----------------------------
+    parity = None
+    if rank == 0:
+        from oracle import p2v_oracle as O
+        idx = torch.arange(0, B, max(1, B // 32), device=device)[:32]
+        ref, _ = O.batch("to_ancestry", V[idx].cpu().numpy(), K)
+        parity = bool(np.array_equal(out[idx].cpu().numpy(), ref))
+
+    # ---- end to end: host buffers through the C ABI (H2D + kernels + D2H in the timed region)
+    Be = args.e2e_batch if args.e2e_batch > 0 else (B if world == 1 else B // 4)
+    hV = torch.empty((Be, K), dtype=torch.int64).pin_memory()
+    hV.copy_(V[:Be])
+    hOut = torch.empty((Be, K, 3), dtype=torch.int64).pin_memory()
+    hSt = torch.empty(Be, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        rc = lib.p2v_to_ancestry_host(hV.data_ptr(), 8, Be, K, hOut.data_ptr(), hSt.data_ptr())
+        if rc != 0:
+            raise RuntimeError(f"p2v_to_ancestry_host failed: {lib.p2v_last_error()}")
+
+    e2e_step()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * Be * e2e_steps / float(te.item())
+    e2e_ok = bool(torch.equal(hOut[:1024], out[:1024].cpu())) and int(hSt.count_nonzero()) == 0
+    del hV, hOut, hSt
+
+    # ---- second half of the metric: cophenetic rows at n = 65536 (row block of this rank) ----
+    coph = None
+    try:
+        coph = bench_cophenetic(torch, lib, device, rank, world, peak, args)
+    except Exception as exc:  # keep the headline line even if this part fails
+        coph = {"error": repr(exc)}
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, coph)
+        if rank == 0 and all(isinstance(g, dict) and "rows_ms" in g for g in gathered):
+            worst = max(g["rows_ms"] for g in gathered)
+            coph["rows_ms_max_over_ranks"] = worst
+            coph["aggregate_gbs"] = sum(g["bytes"] for g in gathered) / (worst * 1e-3) / 1e9
+
+    if rank == 0:
+        cb_rate, cb_cores, cb_dt = cpu_baseline(np, 65536)
+        line = {
+            "metric": METRIC, "value": value, "unit": "trees/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "n_leaves": N_LEAVES, "idx_bytes": 8,
+                       "sharding": "tree-batch index, no collective",
+                       "l2": "inputs (8 GB) and outputs (24 GB) per step exceed the 126 MB L2"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "decode_small_kernel<int64, ancestry>",
+                         "algorithmic_bytes_per_tree": 4 * K * 8,
+                         "note": "issue/latency-bound integer kernel (SURVEY 7 hard part 1); HBM fraction reported as required"},
+            "cpu_baseline": {"value": cb_rate, "unit": "trees/s", "cores": cb_cores, "kind": "port",
+                             "sample": f"65536 trees of n=1000, {cb_dt:.2f} s, OpenMP over trees"},
+            "e2e": {"value": e2e_value, "unit": "trees/s", "h2d_bytes_per_step": Be * K * 8,
+                    "d2h_bytes_per_step": Be * K * 24 + Be * 4, "batch_per_gpu": Be, "steps": e2e_steps,
+                    "api": "p2v_to_ancestry_host (C ABI, pinned host buffers)", "matches_device_path": e2e_ok},
+            "gpu_launches": launches, "clocks": clocks, "parity_spot_check": parity,
+            "cophenetic": coph,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_cophenetic(torch, lib, device, rank, world, peak, args):
+    """One tree, n = 65536, float64 branch lengths; this rank writes its row block
+    [n*rank/world, n*(rank+1)/world).  Times the row kernel alone (prepared tables)."""
+    n = COPH_N
+    k = n - 1
+    g = torch.Generator(device=device).manual_seed(7)            # same tree on every rank
+    hi = (2 * torch.arange(k, device=device) + 1).to(torch.float64)
+    v = (torch.rand((1, k), generator=g, device=device, dtype=torch.float64) * hi).to(torch.int64)
+    bls = torch.rand((1, k, 2), generator=g, device=device, dtype=torch.float64)
+    r0, r1 = n * rank // world, n * (rank + 1) // world
+    rows = r1 - r0
+    out = torch.empty((rows, n), dtype=torch.float64, device=device)
+    need = lib.p2v_cophenetic_workspace_bytes(1, k)
+    ws = torch.empty(need, dtype=torch.uint8, device=device)
+    stream = torch.cuda.current_stream(device)
+    res = {"n_leaves": n, "rows": [r0, r1], "bytes": rows * n * 8}
+    for label, weighted, blp in (("fp64_branch_lengths", 1, bls.data_ptr()), ("topological", 0, 0)):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        rc = lib.p2v_cophenetic_prepare_batch(v.data_ptr(), 8, blp, 1, k, 0, None, ws.data_ptr(), need, stream.cuda_stream)
+        assert rc == 0, lib.p2v_last_error()
+        for _ in range(2):
+            rc = lib.p2v_cophenetic_rows_batch(ws.data_ptr(), need, 1, k, weighted, r0, r1, out.data_ptr(), stream.cuda_stream)
+            assert rc == 0, lib.p2v_last_error()
+        torch.cuda.synchronize()
+        e[0].record(stream)
+        rc = lib.p2v_cophenetic_prepare_batch(v.data_ptr(), 8, blp, 1, k, 0, None, ws.data_ptr(), need, stream.cuda_stream)
+        e[1].record(stream)
+        reps = 5
+        e[2].record(stream)
+        for _ in range(reps):
+            lib.p2v_cophenetic_rows_batch(ws.data_ptr(), need, 1, k, weighted, r0, r1, out.data_ptr(), stream.cuda_stream)
+        e[3].record(stream)
+        torch.cuda.synchronize()
+        prep_ms = e[0].elapsed_time(e[1])
+        rows_ms = e[2].elapsed_time(e[3]) / reps
+        gbs = rows * n * 8 / (rows_ms * 1e-3) / 1e9
+        res[label] = {"prepare_ms": prep_ms, "rows_ms": rows_ms, "achieved_gbs": gbs, "frac_of_peak": gbs / peak}
+        if weighted:
+            res["rows_ms"] = rows_ms
+    # write-only ceiling: a plain 128-bit streaming fill of the same bytes
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lib.p2v_fill_f64(out.data_ptr(), rows * n, 1.0, stream.cuda_stream)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(5):
+        lib.p2v_fill_f64(out.data_ptr(), rows * n, 1.0, stream.cuda_stream)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    fill_ms = e0.elapsed_time(e1) / 5
+    res["fill_ceiling_gbs"] = rows * n * 8 / (fill_ms * 1e-3) / 1e9
+    res["roofline"] = {"bound": "hbm", "achieved": res["fp64_branch_lengths"]["achieved_gbs"], "peak": peak,
+                       "unit": "GB/s", "frac": res["fp64_branch_lengths"]["achieved_gbs"] / peak,
+                       "kernel": "rows_kernel<fp64>", "algorithmic_bytes": rows * n * 8}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="trees per GPU per step")
+    ap.add_argument("--e2e-batch", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

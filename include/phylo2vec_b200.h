@@ -1,0 +1,141 @@
+/*
+ * phylo2vec_b200.h -- C ABI of the B200 (sm_100a) implementation of phylo2vec's
+ * batched decode / encode / cophenetic-distance path.
+ *
+ * This is the drop-in boundary: a Rust FFI crate next to the phylo2vec core
+ * (see INTEGRATION.md), a ctypes loader (phylo2vec_b200/_capi.py) or any other
+ * host binds exactly these symbols.  Plain pointers and sizes only.
+ *
+ * Conventions
+ *  - k = number of vector entries = n_leaves - 1.  Nodes: leaves 0..k,
+ *    internal k+1..2k, root 2k  (reference: phylo2vec/src/vector/convert.rs:138-154).
+ *  - idx_bytes selects the integer width of every index buffer of the call:
+ *    8 = int64 (the reference's usize / numpy int64 layout, py-phylo2vec/src/lib.rs:108-136)
+ *    4 = int32 (what the R binding uses, r-phylo2vec/src/rust/src/lib.rs:36-44).
+ *  - *_batch functions take DEVICE pointers, never allocate, are asynchronous on
+ *    `stream` (a cudaStream_t) and re-entrant.  All arrays are dense, row-major,
+ *    batch-major:  v (B,k); pairs (B,k,2); ancestry (B,k,3); edges (B,2k,2);
+ *    bls (B,k,2) f64; matrix (B,k,3) f64; distances (B,rows,n) f64.
+ *  - status (B int32, may be NULL) receives per tree: 0 = ok; i+1 = v[i] is out of
+ *    bounds (the reference panics with "Validation failed: v[i] = .. is out of
+ *    bounds", vector/base.rs:60-67); P2V_TREE_MALFORMED for encode input that is
+ *    not a tree in the reference's format.  Output of a failed tree is unspecified.
+ *  - *_host functions take HOST pointers, copy in, run and copy out on an
+ *    internal stream and return after completion (what a single-tree drop-in of
+ *    the reference's functions calls).
+ *  - Return value: P2V_OK or a negative error code; p2v_last_error() gives text.
+ *    Nothing throws, nothing aborts.
+ */
+#ifndef PHYLO2VEC_B200_H
+#define PHYLO2VEC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P2V_OK 0
+#define P2V_ERR_INVALID_ARG (-1)
+#define P2V_ERR_CUDA (-2)
+#define P2V_ERR_UNSUPPORTED (-3)
+#define P2V_ERR_WORKSPACE (-4)
+
+#define P2V_TREE_MALFORMED (-2)
+
+typedef void *p2v_stream_t; /* cudaStream_t */
+
+int p2v_version(void);
+const char *p2v_last_error(void);
+/* number of kernels this library has launched in the calling process */
+int64_t p2v_launch_count(void);
+
+/* ---- decode: v -> pairs / ancestry / edges -------------------------------
+ * replaces vector::convert::to_pairs (convert.rs:103-109, avl.rs:35-211),
+ * to_ancestry (convert.rs:167-188), to_edges (convert.rs:227-248), i.e. the
+ * PyO3 entry points get_pairs / get_ancestry / get_edges
+ * (py-phylo2vec/src/lib.rs:108-131), batched.
+ * Trees with k <= 1024 need no workspace; larger trees need
+ * p2v_decode_workspace_bytes(B,k) bytes of device scratch. */
+size_t p2v_decode_workspace_bytes(int64_t B, int64_t k);
+int p2v_to_pairs_batch(const void *v, int idx_bytes, int64_t B, int64_t k, void *pairs,
+                       int32_t *status, void *workspace, size_t workspace_bytes,
+                       p2v_stream_t stream);
+int p2v_to_ancestry_batch(const void *v, int idx_bytes, int64_t B, int64_t k, void *ancestry,
+                          int32_t *status, void *workspace, size_t workspace_bytes,
+                          p2v_stream_t stream);
+int p2v_to_edges_batch(const void *v, int idx_bytes, int64_t B, int64_t k, void *edges,
+                       int32_t *status, void *workspace, size_t workspace_bytes,
+                       p2v_stream_t stream);
+
+/* ---- encode: pairs / ancestry / edges -> v -------------------------------
+ * replaces vector::convert::from_pairs (convert.rs:23-30), from_ancestry
+ * (:129-136, build_cherries :399-440), from_edges (:201-213, order_cherries
+ * :449-477) and build_vector (:320-337, Fenwick :286-316); PyO3 entry points
+ * from_pairs / from_ancestry / from_edges (py-phylo2vec/src/lib.rs:113-136). */
+size_t p2v_encode_workspace_bytes(int64_t B, int64_t k);
+int p2v_from_pairs_batch(const void *pairs, int idx_bytes, int64_t B, int64_t k, void *v,
+                         int32_t *status, void *workspace, size_t workspace_bytes,
+                         p2v_stream_t stream);
+int p2v_from_ancestry_batch(const void *ancestry, int idx_bytes, int64_t B, int64_t k, void *v,
+                            int32_t *status, void *workspace, size_t workspace_bytes,
+                            p2v_stream_t stream);
+int p2v_from_edges_batch(const void *edges, int idx_bytes, int64_t B, int64_t k, void *v,
+                         int32_t *status, void *workspace, size_t workspace_bytes,
+                         p2v_stream_t stream);
+
+/* ---- validation: vector::base::check_v (base.rs:50-67) ------------------- */
+int p2v_check_v_batch(const void *v, int idx_bytes, int64_t B, int64_t k, int32_t *status,
+                      p2v_stream_t stream);
+
+/* ---- cophenetic distances ------------------------------------------------
+ * replaces vector::graph::_cophenetic_distances (vector/graph.rs:20-90) and
+ * matrix::graph::cophenetic_distances (matrix/graph.rs:23-26, parse_matrix
+ * matrix/base.rs:108-121); PyO3 entry point cophenetic_distances
+ * (py-phylo2vec/src/lib.rs:144-156).
+ * Writes rows [row_begin,row_end) of every tree's n x n float64 matrix
+ * (n = k+1) to out (B, row_end-row_begin, n).  bls == NULL: topological
+ * (unit lengths).  Row blocks are how one very large tree is sharded over GPUs. */
+size_t p2v_cophenetic_workspace_bytes(int64_t B, int64_t k);
+int p2v_cophenetic_batch(const void *v, int idx_bytes, const double *bls, int64_t B, int64_t k,
+                         int unrooted, int64_t row_begin, int64_t row_end, double *out,
+                         int32_t *status, void *workspace, size_t workspace_bytes,
+                         p2v_stream_t stream);
+/* same with the reference's (k,3) float64 matrix input [v, bl1, bl2] */
+int p2v_cophenetic_matrix_batch(const double *matrix, int64_t B, int64_t k, int unrooted,
+                                int64_t row_begin, int64_t row_end, double *out, int32_t *status,
+                                void *workspace, size_t workspace_bytes, p2v_stream_t stream);
+
+/* Two-phase form of the same computation: prepare once (decode + per-tree tables kept
+ * in `workspace`), then emit any number of row blocks from the prepared workspace
+ * (e.g. to stream a 34 GB matrix in pieces).  weighted = 0 for topological input
+ * (v without bls), 1 for branch lengths (bls or matrix input). */
+int p2v_cophenetic_prepare_batch(const void *v_or_matrix, int idx_bytes /* 0 = (k,3) f64 matrix */,
+                                 const double *bls, int64_t B, int64_t k, int unrooted, int32_t *status,
+                                 void *workspace, size_t workspace_bytes, p2v_stream_t stream);
+int p2v_cophenetic_rows_batch(const void *workspace, size_t workspace_bytes, int64_t B, int64_t k,
+                              int weighted, int64_t row_begin, int64_t row_end, double *out,
+                              p2v_stream_t stream);
+
+/* ---- host-buffer entry points (H2D + kernels + D2H inside the call) ------ */
+int p2v_to_pairs_host(const void *v, int idx_bytes, int64_t B, int64_t k, void *pairs, int32_t *status);
+int p2v_to_ancestry_host(const void *v, int idx_bytes, int64_t B, int64_t k, void *ancestry, int32_t *status);
+int p2v_to_edges_host(const void *v, int idx_bytes, int64_t B, int64_t k, void *edges, int32_t *status);
+int p2v_from_pairs_host(const void *pairs, int idx_bytes, int64_t B, int64_t k, void *v, int32_t *status);
+int p2v_from_ancestry_host(const void *ancestry, int idx_bytes, int64_t B, int64_t k, void *v, int32_t *status);
+int p2v_from_edges_host(const void *edges, int idx_bytes, int64_t B, int64_t k, void *v, int32_t *status);
+int p2v_check_v_host(const void *v, int idx_bytes, int64_t B, int64_t k, int32_t *status);
+int p2v_cophenetic_host(const void *v, int idx_bytes, const double *bls, int64_t B, int64_t k,
+                        int unrooted, int64_t row_begin, int64_t row_end, double *out, int32_t *status);
+int p2v_cophenetic_matrix_host(const double *matrix, int64_t B, int64_t k, int unrooted,
+                               int64_t row_begin, int64_t row_end, double *out, int32_t *status);
+
+/* ---- measurement helper: a plain 128-bit streaming fill of `bytes` bytes, the
+ * write-only ceiling the distance kernel is compared with in bench.py -------- */
+int p2v_fill_f64(double *out, int64_t count, double value, p2v_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHYLO2VEC_B200_H */

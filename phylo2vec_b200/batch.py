@@ -1,0 +1,244 @@
+"""Batched device API: torch tensors (or any DLPack producer) in, torch tensors out.
+
+These are additions next to the reference's single-tree functions
+(SURVEY section 8b): ``(B,k)`` vectors -> ``(B,k,3)`` ancestry etc.  Tensors
+stay on the device; hand-off is zero-copy (DLPack), the kernels run on torch's
+current stream through the C ABI in include/phylo2vec_b200.h.  torch is plumbing
+here (device memory, streams); there is no eager/PyTorch implementation of the
+path and no CPU fallback.
+"""
+
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _capi
+
+_DECODE = {"to_pairs": 2, "to_ancestry": 3, "to_edges": 4}
+_ENCODE = {"from_pairs": 2, "from_ancestry": 3, "from_edges": 4}
+
+
+def as_tensor(x) -> torch.Tensor:
+    """torch tensor from a tensor or any object exposing ``__dlpack__`` (zero copy)."""
+    if isinstance(x, torch.Tensor):
+        return x
+    if hasattr(x, "__dlpack__"):
+        return torch.from_dlpack(x)
+    raise TypeError("expected a torch.Tensor or a DLPack-capable object on a CUDA device")
+
+
+def _idx_tensor(x, ndim: int, what: str) -> torch.Tensor:
+    t = as_tensor(x)
+    if not t.is_cuda:
+        raise ValueError(f"{what}: tensor must live on a CUDA device (use the *_host functions for host data)")
+    if t.dtype not in (torch.int64, torch.int32):
+        raise TypeError(f"{what}: dtype must be int64 or int32, got {t.dtype}")
+    if t.dim() != ndim:
+        raise ValueError(f"{what}: expected {ndim} dimensions, got {t.dim()}")
+    return t.contiguous()
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ws(nbytes: int, device) -> Tuple[Optional[torch.Tensor], int]:
+    if nbytes == 0:
+        return None, 0
+    t = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return t, t.data_ptr()
+
+
+def raise_for_status(status: torch.Tensor, v: Optional[torch.Tensor] = None) -> None:
+    """Raise like the reference for the first failed tree of a batch.
+
+    Invalid vectors: AssertionError with check_max's message
+    (phylo2vec/src/vector/base.rs:60-67)."""
+    bad = torch.nonzero(status)
+    if bad.numel() == 0:
+        return
+    b = int(bad[0, 0])
+    code = int(status[b])
+    if code > 0:
+        i = code - 1
+        val = int(v[b, i]) if v is not None else "?"
+        raise AssertionError(
+            f"Validation failed: v[{i}] = {val} is out of bounds (max = {2 * i})" +
+            (f" [tree {b} of the batch]" if status.numel() > 1 else ""))
+    raise ValueError(f"malformed tree input (tree {b} of the batch, code {code})")
+
+
+def _decode(name: str, V, out=None, status=None, check: bool = True) -> torch.Tensor:
+    cols = _DECODE[name]
+    V = _idx_tensor(V, 2, name)
+    B, k = V.shape
+    shape = {"to_pairs": (B, k, 2), "to_ancestry": (B, k, 3), "to_edges": (B, 2 * k, 2)}[name]
+    if out is None:
+        out = torch.empty(shape, dtype=V.dtype, device=V.device)
+    else:
+        out = as_tensor(out)
+        if tuple(out.shape) != shape or out.dtype != V.dtype or not out.is_contiguous() or out.device != V.device:
+            raise ValueError(f"{name}: out must be a contiguous {shape} {V.dtype} tensor on {V.device}")
+    if status is None:
+        status = torch.empty(B, dtype=torch.int32, device=V.device)
+    lib = _capi.load()
+    with torch.cuda.device(V.device):
+        ws_t, ws_p = _ws(lib.p2v_decode_workspace_bytes(B, k), V.device)
+        rc = getattr(lib, f"p2v_{name}_batch")(V.data_ptr(), V.element_size(), B, k, out.data_ptr(),
+                                              status.data_ptr(), ws_p, 0 if ws_t is None else ws_t.numel(),
+                                              _stream_ptr(V.device))
+    _capi.check(rc, name)
+    del cols
+    if check:
+        raise_for_status(status, V)
+    return out
+
+
+def to_pairs_batch(V, out=None, status=None, check=True):
+    """(B,k) int vectors -> (B,k,2) pairs (branch, leaf).  Batched to_pairs
+    (phylo2vec/src/vector/convert.rs:103-109)."""
+    return _decode("to_pairs", V, out, status, check)
+
+
+def to_ancestry_batch(V, out=None, status=None, check=True):
+    """(B,k) -> (B,k,3) rows [child1, child2, parent].  Batched to_ancestry
+    (phylo2vec/src/vector/convert.rs:167-188)."""
+    return _decode("to_ancestry", V, out, status, check)
+
+
+def to_edges_batch(V, out=None, status=None, check=True):
+    """(B,k) -> (B,2k,2) edges (child, parent).  Batched to_edges
+    (phylo2vec/src/vector/convert.rs:227-248)."""
+    return _decode("to_edges", V, out, status, check)
+
+
+def _encode(name: str, X, out=None, status=None, check: bool = True) -> torch.Tensor:
+    cols = _ENCODE[name]
+    X = _idx_tensor(X, 3, name)
+    B = X.shape[0]
+    if name == "from_edges":
+        if X.shape[1] % 2 != 0:  # phylo2vec/src/vector/convert.rs:202
+            raise AssertionError("The number of edges must be even")
+        k = X.shape[1] // 2
+        ok = X.shape[2] == 2
+    else:
+        k = X.shape[1]
+        ok = X.shape[2] == cols
+    if not ok:
+        raise ValueError(f"{name}: bad trailing dimension {tuple(X.shape)}")
+    if out is None:
+        out = torch.empty((B, k), dtype=X.dtype, device=X.device)
+    else:
+        out = as_tensor(out)
+        if tuple(out.shape) != (B, k) or out.dtype != X.dtype or not out.is_contiguous() or out.device != X.device:
+            raise ValueError(f"{name}: out must be a contiguous {(B, k)} {X.dtype} tensor on {X.device}")
+    if status is None:
+        status = torch.empty(B, dtype=torch.int32, device=X.device)
+    lib = _capi.load()
+    with torch.cuda.device(X.device):
+        ws_t, ws_p = _ws(lib.p2v_encode_workspace_bytes(B, k), X.device)
+        rc = getattr(lib, f"p2v_{name}_batch")(X.data_ptr(), X.element_size(), B, k, out.data_ptr(),
+                                              status.data_ptr(), ws_p, 0 if ws_t is None else ws_t.numel(),
+                                              _stream_ptr(X.device))
+    _capi.check(rc, name)
+    if check:
+        raise_for_status(status)
+    return out
+
+
+def from_pairs_batch(P, out=None, status=None, check=True):
+    """(B,k,2) -> (B,k).  Batched from_pairs (phylo2vec/src/vector/convert.rs:23-30)."""
+    return _encode("from_pairs", P, out, status, check)
+
+
+def from_ancestry_batch(A, out=None, status=None, check=True):
+    """(B,k,3) -> (B,k).  Batched from_ancestry (phylo2vec/src/vector/convert.rs:129-136)."""
+    return _encode("from_ancestry", A, out, status, check)
+
+
+def from_edges_batch(E, out=None, status=None, check=True):
+    """(B,2k,2) -> (B,k).  Batched from_edges (phylo2vec/src/vector/convert.rs:201-213)."""
+    return _encode("from_edges", E, out, status, check)
+
+
+def check_v_batch(V) -> torch.Tensor:
+    """Per-tree status of check_v (phylo2vec/src/vector/base.rs:50-67): 0 or bad index + 1."""
+    V = _idx_tensor(V, 2, "check_v")
+    B, k = V.shape
+    status = torch.empty(B, dtype=torch.int32, device=V.device)
+    with torch.cuda.device(V.device):
+        rc = _capi.load().p2v_check_v_batch(V.data_ptr(), V.element_size(), B, k, status.data_ptr(),
+                                            _stream_ptr(V.device))
+    _capi.check(rc, "check_v")
+    return status
+
+
+def cophenetic_workspace_bytes(B: int, k: int) -> int:
+    return int(_capi.load().p2v_cophenetic_workspace_bytes(B, k))
+
+
+def cophenetic_distances_batch(trees, unrooted: bool = False, rows: Optional[Tuple[int, int]] = None,
+                               out=None, bls=None, status=None, check: bool = True,
+                               workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Distance matrices of a batch of trees, float64 ``(B, rows, n)``.
+
+    trees: int ``(B,k)`` vectors (topological unless ``bls`` ``(B,k,2)`` float64 is
+    given) or float64 ``(B,k,3)`` matrices ``[v, bl1, bl2]`` -- the PyTree dispatch of
+    py-phylo2vec/src/lib.rs:20-24,144-156 lifted to batches.  ``rows=(r0,r1)`` selects a
+    row block of every matrix (how one huge tree is sharded over GPUs).
+    Replaces vector::graph::_cophenetic_distances (phylo2vec/src/vector/graph.rs:20-90)."""
+    T = as_tensor(trees)
+    if not T.is_cuda:
+        raise ValueError("cophenetic_distances_batch: tensor must live on a CUDA device")
+    lib = _capi.load()
+    if T.dim() == 3:
+        if T.dtype != torch.float64 or T.shape[2] != 3:
+            raise TypeError("matrix input must be float64 with shape (B,k,3)")
+        if bls is not None:
+            raise ValueError("bls given together with matrix input")
+        T = T.contiguous()
+        B, k = T.shape[0], T.shape[1]
+        is_matrix = True
+    elif T.dim() == 2:
+        T = _idx_tensor(T, 2, "cophenetic_distances")
+        B, k = T.shape
+        is_matrix = False
+        if bls is not None:
+            bls = as_tensor(bls)
+            if bls.dtype != torch.float64 or tuple(bls.shape) != (B, k, 2) or bls.device != T.device:
+                raise TypeError("bls must be float64 (B,k,2) on the same device")
+            bls = bls.contiguous()
+    else:
+        raise TypeError("trees must be (B,k) integer vectors or (B,k,3) float64 matrices")
+    n = k + 1
+    r0, r1 = (0, n) if rows is None else (int(rows[0]), int(rows[1]))
+    if not (0 <= r0 <= r1 <= n):
+        raise ValueError(f"rows {rows} outside [0, {n}]")
+    shape = (B, r1 - r0, n)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float64, device=T.device)
+    else:
+        out = as_tensor(out)
+        if tuple(out.shape) != shape or out.dtype != torch.float64 or not out.is_contiguous() or out.device != T.device:
+            raise ValueError(f"out must be a contiguous float64 {shape} tensor on {T.device}")
+    if status is None:
+        status = torch.empty(B, dtype=torch.int32, device=T.device)
+    need = lib.p2v_cophenetic_workspace_bytes(B, k)
+    with torch.cuda.device(T.device):
+        if workspace is None or workspace.numel() * workspace.element_size() < need:
+            workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=T.device)
+        wsb = workspace.numel() * workspace.element_size()
+        if is_matrix:
+            rc = lib.p2v_cophenetic_matrix_batch(T.data_ptr(), B, k, int(bool(unrooted)), r0, r1, out.data_ptr(),
+                                                 status.data_ptr(), workspace.data_ptr(), wsb,
+                                                 _stream_ptr(T.device))
+        else:
+            rc = lib.p2v_cophenetic_batch(T.data_ptr(), T.element_size(), 0 if bls is None else bls.data_ptr(),
+                                          B, k, int(bool(unrooted)), r0, r1, out.data_ptr(), status.data_ptr(),
+                                          workspace.data_ptr(), wsb, _stream_ptr(T.device))
+    _capi.check(rc, "cophenetic_distances")
+    if check and bool(status.any()):
+        raise_for_status(status, T[..., 0].to(torch.int64) if is_matrix else T)
+    return out

@@ -1,0 +1,348 @@
+// C ABI of the library (declared in include/phylo2vec_b200.h).
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/phylo2vec_b200.h"
+#include "p2v_internal.h"
+
+namespace p2v {
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count() {
+    static thread_local int cached_dev = -1;
+    static thread_local int cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached = v; cached_dev = dev;
+    }
+    return cached;
+}
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    g_err = what;
+    if (e != cudaSuccess) { g_err += ": "; g_err += cudaGetErrorString(e); }
+    return code;
+}
+
+static int from_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return P2V_OK;
+    if (e == cudaErrorNotSupported) return fail(P2V_ERR_UNSUPPORTED, what, e);
+    if (e == cudaErrorInvalidValue) return fail(P2V_ERR_INVALID_ARG, what, e);
+    return fail(P2V_ERR_CUDA, what, e);
+}
+
+static int check_common(const void* in, const void* out, int idx_bytes, int64_t B, int64_t k) {
+    if (B < 0 || k < 0) return fail(P2V_ERR_INVALID_ARG, "negative batch or length");
+    if (idx_bytes != 4 && idx_bytes != 8) return fail(P2V_ERR_INVALID_ARG, "idx_bytes must be 4 or 8");
+    if (B > 0 && k > 0 && (!in || !out)) return fail(P2V_ERR_INVALID_ARG, "null buffer");
+    if (k > LARGE_K_MAX) return fail(P2V_ERR_UNSUPPORTED, "k above the supported maximum (2^19)");
+    return P2V_OK;
+}
+
+static int decode_entry(int mode, const void* v, int idx_bytes, int64_t B, int64_t k, void* out,
+                        int32_t* status, void* ws, size_t ws_bytes, p2v_stream_t stream) {
+    int rc = check_common(v, out, idx_bytes, B, k);
+    if (rc) return rc;
+    if (ws_bytes < decode_workspace_bytes(B, k)) return fail(P2V_ERR_WORKSPACE, "decode workspace too small");
+    return from_cuda(launch_decode(mode, v, idx_bytes, B, k, out, status, ws, ws_bytes, (cudaStream_t)stream),
+                     "decode launch");
+}
+
+static int encode_entry(int mode, const void* in, int idx_bytes, int64_t B, int64_t k, void* v,
+                        int32_t* status, void* ws, size_t ws_bytes, p2v_stream_t stream) {
+    int rc = check_common(in, v, idx_bytes, B, k);
+    if (rc) return rc;
+    if (ws_bytes < encode_workspace_bytes(B, k)) return fail(P2V_ERR_WORKSPACE, "encode workspace too small");
+    return from_cuda(launch_encode(mode, in, idx_bytes, B, k, v, status, ws, ws_bytes, (cudaStream_t)stream),
+                     "encode launch");
+}
+
+// ---- host-buffer plumbing --------------------------------------------------------------
+// Chunks the batch so that the device footprint stays bounded, and alternates two
+// streams so that (with pinned host memory) H2D, kernels and D2H of neighbouring chunks overlap.
+struct HostRun {
+    cudaStream_t st[2] = {nullptr, nullptr};
+    void* din[2] = {nullptr, nullptr};
+    void* dout[2] = {nullptr, nullptr};
+    void* dws[2] = {nullptr, nullptr};
+    int32_t* dstat[2] = {nullptr, nullptr};
+    cudaError_t err = cudaSuccess;
+    ~HostRun() {
+        for (int i = 0; i < 2; ++i) {
+            if (st[i]) cudaStreamSynchronize(st[i]);
+            if (din[i]) cudaFree(din[i]);
+            if (dout[i]) cudaFree(dout[i]);
+            if (dws[i]) cudaFree(dws[i]);
+            if (dstat[i]) cudaFree(dstat[i]);
+            if (st[i]) cudaStreamDestroy(st[i]);
+        }
+    }
+};
+
+template <typename Launch, typename WsBytes>
+static int host_chunked(const void* in, size_t in_tree_bytes, void* out, size_t out_tree_bytes,
+                        int32_t* status, int64_t B, WsBytes ws_bytes_of, Launch launch) {
+    if (B <= 0) return P2V_OK;
+    const size_t budget = (size_t)3 << 30;  // device bytes per chunk (in + out)
+    size_t per = in_tree_bytes + out_tree_bytes;
+    if (per == 0) per = 1;
+    int64_t chunk = (int64_t)(budget / per);
+    if (chunk < 1) chunk = 1;
+    if (chunk > B) chunk = B;
+    const int nstreams = (chunk < B) ? 2 : 1;
+    HostRun H;
+    const size_t wsb = ws_bytes_of(chunk);
+    for (int i = 0; i < nstreams; ++i) {
+        cudaError_t e = cudaStreamCreateWithFlags(&H.st[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess && in_tree_bytes) e = cudaMalloc(&H.din[i], in_tree_bytes * chunk);
+        if (e == cudaSuccess && out_tree_bytes) e = cudaMalloc(&H.dout[i], out_tree_bytes * chunk);
+        if (e == cudaSuccess && wsb) e = cudaMalloc(&H.dws[i], wsb);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&H.dstat[i], sizeof(int32_t) * chunk);
+        if (e != cudaSuccess) return from_cuda(e, "host entry: device allocation");
+    }
+    int c = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk, ++c) {
+        const int s = c % nstreams;
+        const int64_t nb = (B - b0 < chunk) ? (B - b0) : chunk;
+        cudaError_t e = cudaSuccess;
+        if (in_tree_bytes)
+            e = cudaMemcpyAsync(H.din[s], (const char*)in + (size_t)b0 * in_tree_bytes, in_tree_bytes * nb,
+                                cudaMemcpyHostToDevice, H.st[s]);
+        if (e == cudaSuccess) e = launch(H.din[s], H.dout[s], H.dstat[s], nb, H.dws[s], wsb, H.st[s]);
+        if (e == cudaSuccess && out_tree_bytes)
+            e = cudaMemcpyAsync((char*)out + (size_t)b0 * out_tree_bytes, H.dout[s], out_tree_bytes * nb,
+                                cudaMemcpyDeviceToHost, H.st[s]);
+        if (e == cudaSuccess && status)
+            e = cudaMemcpyAsync(status + b0, H.dstat[s], sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, H.st[s]);
+        if (e != cudaSuccess) return from_cuda(e, "host entry: chunk");
+    }
+    for (int i = 0; i < nstreams; ++i) {
+        cudaError_t e = cudaStreamSynchronize(H.st[i]);
+        if (e != cudaSuccess) return from_cuda(e, "host entry: synchronize");
+    }
+    return P2V_OK;
+}
+
+static int decode_host(int mode, int cols, const void* v, int idx_bytes, int64_t B, int64_t k, void* out,
+                       int32_t* status) {
+    int rc = check_common(v, out, idx_bytes, B, k);
+    if (rc) return rc;
+    if (k == 0) { if (status && B > 0) memset(status, 0, sizeof(int32_t) * B); return P2V_OK; }
+    return host_chunked(
+        v, (size_t)k * idx_bytes, out, (size_t)k * cols * idx_bytes, status, B,
+        [&](int64_t nb) { return decode_workspace_bytes(nb, k); },
+        [&](void* din, void* dout, int32_t* dst, int64_t nb, void* ws, size_t wsb, cudaStream_t st) {
+            return launch_decode(mode, din, idx_bytes, nb, k, dout, dst, ws, wsb, st);
+        });
+}
+
+static int encode_host(int mode, int cols, const void* in, int idx_bytes, int64_t B, int64_t k, void* v,
+                       int32_t* status) {
+    int rc = check_common(in, v, idx_bytes, B, k);
+    if (rc) return rc;
+    if (k == 0) { if (status && B > 0) memset(status, 0, sizeof(int32_t) * B); return P2V_OK; }
+    return host_chunked(
+        in, (size_t)k * cols * idx_bytes, v, (size_t)k * idx_bytes, status, B,
+        [&](int64_t nb) { return encode_workspace_bytes(nb, k); },
+        [&](void* din, void* dout, int32_t* dst, int64_t nb, void* ws, size_t wsb, cudaStream_t st) {
+            return launch_encode(mode, din, idx_bytes, nb, k, dout, dst, ws, wsb, st);
+        });
+}
+
+static int coph_check(const void* in, const double* out, int64_t B, int64_t k, int64_t rb, int64_t re) {
+    if (B < 0 || k < 0) return fail(P2V_ERR_INVALID_ARG, "negative batch or length");
+    if (rb < 0 || re > k + 1 || rb > re) return fail(P2V_ERR_INVALID_ARG, "row block outside [0, n]");
+    if (B > 0 && (!out || (k > 0 && !in))) return fail(P2V_ERR_INVALID_ARG, "null buffer");
+    if (k > LARGE_K_MAX) return fail(P2V_ERR_UNSUPPORTED, "k above the supported maximum (2^19)");
+    return P2V_OK;
+}
+
+// Host entry for distances.  in_a: v (idx_bytes 4/8) or the (k,3) matrix (idx_bytes 0); bls optional.
+static int coph_host(const void* in_a, int idx_bytes, const double* bls, int64_t B, int64_t k, int unrooted,
+                     int64_t rb, int64_t re, double* out, int32_t* status) {
+    int rc = coph_check(in_a, out, B, k, rb, re);
+    if (rc) return rc;
+    if (B == 0 || re == rb) return P2V_OK;
+    const size_t a_bytes = (idx_bytes == 0) ? (size_t)k * 3 * sizeof(double) : (size_t)k * idx_bytes;
+    const size_t b_bytes = bls ? (size_t)k * 2 * sizeof(double) : 0;
+    const size_t out_tree = (size_t)(re - rb) * (size_t)(k + 1) * sizeof(double);
+    // one packed input record per tree: [a | bls]
+    const size_t in_tree = a_bytes + b_bytes;
+    // pack on the fly only when bls is present and separate; otherwise pass through
+    if (!bls) {
+        return host_chunked(
+            in_a, a_bytes, out, out_tree, status, B,
+            [&](int64_t nb) { return cophenetic_workspace_bytes(nb, k); },
+            [&](void* din, void* dout, int32_t* dst, int64_t nb, void* ws, size_t wsb, cudaStream_t st) {
+                return launch_cophenetic(din, idx_bytes, nullptr, nb, k, unrooted, rb, re, (double*)dout, dst,
+                                         ws, wsb, st);
+            });
+    }
+    // v and bls are separate host arrays: copy bls per chunk inside the launch lambda
+    (void)in_tree;
+    int64_t done = 0;  // trees consumed so far (chunks are issued in order)
+    double* dbl[2] = {nullptr, nullptr};
+    int flip = 0;
+    int64_t cap_chunk = 0;
+    auto cleanup = [&]() { for (int i = 0; i < 2; ++i) if (dbl[i]) cudaFree(dbl[i]); };
+    int r = host_chunked(
+        in_a, a_bytes, out, out_tree, status, B,
+        [&](int64_t nb) { cap_chunk = nb; return cophenetic_workspace_bytes(nb, k); },
+        [&](void* din, void* dout, int32_t* dst, int64_t nb, void* ws, size_t wsb, cudaStream_t st) {
+            cudaError_t e = cudaSuccess;
+            const int s = flip; flip ^= 1;
+            if (!dbl[s]) e = cudaMalloc((void**)&dbl[s], b_bytes * (size_t)cap_chunk);
+            if (e != cudaSuccess) return e;
+            e = cudaMemcpyAsync(dbl[s], (const char*)bls + (size_t)done * b_bytes, b_bytes * nb,
+                                cudaMemcpyHostToDevice, st);
+            done += nb;
+            if (e != cudaSuccess) return e;
+            return launch_cophenetic(din, idx_bytes, dbl[s], nb, k, unrooted, rb, re, (double*)dout, dst, ws,
+                                     wsb, st);
+        });
+    cudaDeviceSynchronize();
+    cleanup();
+    return r;
+}
+
+}  // namespace p2v
+
+using namespace p2v;
+
+extern "C" {
+
+int p2v_version(void) { return 100; }
+const char* p2v_last_error(void) { return g_err.c_str(); }
+int64_t p2v_launch_count(void) { return g_launches.load(); }
+
+size_t p2v_decode_workspace_bytes(int64_t B, int64_t k) { return decode_workspace_bytes(B, k); }
+size_t p2v_encode_workspace_bytes(int64_t B, int64_t k) { return encode_workspace_bytes(B, k); }
+size_t p2v_cophenetic_workspace_bytes(int64_t B, int64_t k) { return cophenetic_workspace_bytes(B, k); }
+
+int p2v_to_pairs_batch(const void* v, int idx_bytes, int64_t B, int64_t k, void* pairs, int32_t* status,
+                       void* ws, size_t ws_bytes, p2v_stream_t stream) {
+    return decode_entry(MODE_PAIRS, v, idx_bytes, B, k, pairs, status, ws, ws_bytes, stream);
+}
+int p2v_to_ancestry_batch(const void* v, int idx_bytes, int64_t B, int64_t k, void* anc, int32_t* status,
+                          void* ws, size_t ws_bytes, p2v_stream_t stream) {
+    return decode_entry(MODE_ANCESTRY, v, idx_bytes, B, k, anc, status, ws, ws_bytes, stream);
+}
+int p2v_to_edges_batch(const void* v, int idx_bytes, int64_t B, int64_t k, void* edges, int32_t* status,
+                       void* ws, size_t ws_bytes, p2v_stream_t stream) {
+    return decode_entry(MODE_EDGES, v, idx_bytes, B, k, edges, status, ws, ws_bytes, stream);
+}
+int p2v_from_pairs_batch(const void* pairs, int idx_bytes, int64_t B, int64_t k, void* v, int32_t* status,
+                         void* ws, size_t ws_bytes, p2v_stream_t stream) {
+    return encode_entry(FROM_PAIRS, pairs, idx_bytes, B, k, v, status, ws, ws_bytes, stream);
+}
+int p2v_from_ancestry_batch(const void* anc, int idx_bytes, int64_t B, int64_t k, void* v, int32_t* status,
+                            void* ws, size_t ws_bytes, p2v_stream_t stream) {
+    return encode_entry(FROM_ANCESTRY, anc, idx_bytes, B, k, v, status, ws, ws_bytes, stream);
+}
+int p2v_from_edges_batch(const void* edges, int idx_bytes, int64_t B, int64_t k, void* v, int32_t* status,
+                         void* ws, size_t ws_bytes, p2v_stream_t stream) {
+    return encode_entry(FROM_EDGES, edges, idx_bytes, B, k, v, status, ws, ws_bytes, stream);
+}
+
+int p2v_check_v_batch(const void* v, int idx_bytes, int64_t B, int64_t k, int32_t* status, p2v_stream_t stream) {
+    if (!status) return fail(P2V_ERR_INVALID_ARG, "status is required");
+    int rc = check_common(v, status, idx_bytes, B, k);
+    if (rc) return rc;
+    if (k == 0) return from_cuda(cudaMemsetAsync(status, 0, sizeof(int32_t) * B, (cudaStream_t)stream), "memset");
+    return from_cuda(launch_check_v(v, idx_bytes, B, k, status, (cudaStream_t)stream), "check_v launch");
+}
+
+int p2v_cophenetic_batch(const void* v, int idx_bytes, const double* bls, int64_t B, int64_t k, int unrooted,
+                         int64_t row_begin, int64_t row_end, double* out, int32_t* status, void* ws,
+                         size_t ws_bytes, p2v_stream_t stream) {
+    if (idx_bytes != 4 && idx_bytes != 8) return fail(P2V_ERR_INVALID_ARG, "idx_bytes must be 4 or 8");
+    int rc = coph_check(v, out, B, k, row_begin, row_end);
+    if (rc) return rc;
+    if (ws_bytes < cophenetic_workspace_bytes(B, k)) return fail(P2V_ERR_WORKSPACE, "cophenetic workspace too small");
+    return from_cuda(launch_cophenetic(v, idx_bytes, bls, B, k, unrooted, row_begin, row_end, out, status, ws,
+                                       ws_bytes, (cudaStream_t)stream), "cophenetic launch");
+}
+
+int p2v_cophenetic_matrix_batch(const double* m, int64_t B, int64_t k, int unrooted, int64_t row_begin,
+                                int64_t row_end, double* out, int32_t* status, void* ws, size_t ws_bytes,
+                                p2v_stream_t stream) {
+    int rc = coph_check(m, out, B, k, row_begin, row_end);
+    if (rc) return rc;
+    if (ws_bytes < cophenetic_workspace_bytes(B, k)) return fail(P2V_ERR_WORKSPACE, "cophenetic workspace too small");
+    return from_cuda(launch_cophenetic(m, 0, nullptr, B, k, unrooted, row_begin, row_end, out, status, ws,
+                                       ws_bytes, (cudaStream_t)stream), "cophenetic launch");
+}
+
+int p2v_cophenetic_prepare_batch(const void* v_or_matrix, int idx_bytes, const double* bls, int64_t B, int64_t k,
+                                 int unrooted, int32_t* status, void* ws, size_t ws_bytes, p2v_stream_t stream) {
+    if (idx_bytes != 0 && idx_bytes != 4 && idx_bytes != 8) return fail(P2V_ERR_INVALID_ARG, "idx_bytes must be 0, 4 or 8");
+    if (B < 0 || k < 0) return fail(P2V_ERR_INVALID_ARG, "negative batch or length");
+    if (B > 0 && k > 0 && !v_or_matrix) return fail(P2V_ERR_INVALID_ARG, "null buffer");
+    if (k > LARGE_K_MAX) return fail(P2V_ERR_UNSUPPORTED, "k above the supported maximum (2^19)");
+    if (ws_bytes < cophenetic_workspace_bytes(B, k)) return fail(P2V_ERR_WORKSPACE, "cophenetic workspace too small");
+    return from_cuda(launch_cophenetic_prepare(v_or_matrix, idx_bytes, bls, B, k, unrooted, status, ws, ws_bytes,
+                                               (cudaStream_t)stream), "cophenetic prepare");
+}
+int p2v_cophenetic_rows_batch(const void* ws, size_t ws_bytes, int64_t B, int64_t k, int weighted,
+                              int64_t row_begin, int64_t row_end, double* out, p2v_stream_t stream) {
+    int rc = coph_check(ws, out, B, k, row_begin, row_end);
+    if (rc) return rc;
+    if (ws_bytes < cophenetic_workspace_bytes(B, k)) return fail(P2V_ERR_WORKSPACE, "cophenetic workspace too small");
+    return from_cuda(launch_cophenetic_rows(ws, ws_bytes, B, k, weighted, row_begin, row_end, out,
+                                            (cudaStream_t)stream), "cophenetic rows");
+}
+
+int p2v_to_pairs_host(const void* v, int idx_bytes, int64_t B, int64_t k, void* out, int32_t* status) {
+    return decode_host(MODE_PAIRS, 2, v, idx_bytes, B, k, out, status);
+}
+int p2v_to_ancestry_host(const void* v, int idx_bytes, int64_t B, int64_t k, void* out, int32_t* status) {
+    return decode_host(MODE_ANCESTRY, 3, v, idx_bytes, B, k, out, status);
+}
+int p2v_to_edges_host(const void* v, int idx_bytes, int64_t B, int64_t k, void* out, int32_t* status) {
+    return decode_host(MODE_EDGES, 4, v, idx_bytes, B, k, out, status);
+}
+int p2v_from_pairs_host(const void* in, int idx_bytes, int64_t B, int64_t k, void* v, int32_t* status) {
+    return encode_host(FROM_PAIRS, 2, in, idx_bytes, B, k, v, status);
+}
+int p2v_from_ancestry_host(const void* in, int idx_bytes, int64_t B, int64_t k, void* v, int32_t* status) {
+    return encode_host(FROM_ANCESTRY, 3, in, idx_bytes, B, k, v, status);
+}
+int p2v_from_edges_host(const void* in, int idx_bytes, int64_t B, int64_t k, void* v, int32_t* status) {
+    return encode_host(FROM_EDGES, 4, in, idx_bytes, B, k, v, status);
+}
+int p2v_check_v_host(const void* v, int idx_bytes, int64_t B, int64_t k, int32_t* status) {
+    if (!status) return fail(P2V_ERR_INVALID_ARG, "status is required");
+    int rc = check_common(v, status, idx_bytes, B, k);
+    if (rc) return rc;
+    if (k == 0 || B == 0) { if (B > 0) memset(status, 0, sizeof(int32_t) * B); return P2V_OK; }
+    return host_chunked(
+        v, (size_t)k * idx_bytes, nullptr, 0, status, B, [&](int64_t) { return (size_t)0; },
+        [&](void* din, void*, int32_t* dst, int64_t nb, void*, size_t, cudaStream_t st) {
+            return launch_check_v(din, idx_bytes, nb, k, dst, st);
+        });
+}
+int p2v_cophenetic_host(const void* v, int idx_bytes, const double* bls, int64_t B, int64_t k, int unrooted,
+                        int64_t row_begin, int64_t row_end, double* out, int32_t* status) {
+    if (idx_bytes != 4 && idx_bytes != 8) return fail(P2V_ERR_INVALID_ARG, "idx_bytes must be 4 or 8");
+    return coph_host(v, idx_bytes, bls, B, k, unrooted, row_begin, row_end, out, status);
+}
+int p2v_cophenetic_matrix_host(const double* m, int64_t B, int64_t k, int unrooted, int64_t row_begin,
+                               int64_t row_end, double* out, int32_t* status) {
+    return coph_host(m, 0, nullptr, B, k, unrooted, row_begin, row_end, out, status);
+}
+
+int p2v_fill_f64(double* out, int64_t count, double value, p2v_stream_t stream) {
+    if (count > 0 && !out) return fail(P2V_ERR_INVALID_ARG, "null buffer");
+    return from_cuda(launch_fill_f64(out, count, value, (cudaStream_t)stream), "fill launch");
+}
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+// Shared device helpers for the phylo2vec B200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace p2v {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr uint32_t NONE16 = 0xFFFFu;
+constexpr uint32_t NONE32 = 0xFFFFFFFFu;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// lanes strictly above / at-or-below `lane`
+__device__ __forceinline__ uint32_t lanes_gt(int lane) { return ~((2u << lane) - 1u); }
+__device__ __forceinline__ uint32_t lanes_le(int lane) { return (2u << lane) - 1u; }
+__device__ __forceinline__ uint32_t lanes_lt(int lane) { return (1u << lane) - 1u; }
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t x, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(FULL, x, d);
+        if (lane >= d) x += y;
+    }
+    return x;
+}
+
+// position of the r-th (0-based) set bit of wd; r < popc(wd)
+__device__ __forceinline__ uint32_t nth_set_bit(uint32_t wd, uint32_t r) {
+    uint32_t pos = 0, c;
+    c = __popc(wd & 0xFFFFu);          if (r >= c) { r -= c; pos = 16; }
+    c = __popc((wd >> pos) & 0xFFu);   if (r >= c) { r -= c; pos += 8; }
+    c = __popc((wd >> pos) & 0xFu);    if (r >= c) { r -= c; pos += 4; }
+    c = __popc((wd >> pos) & 0x3u);    if (r >= c) { r -= c; pos += 2; }
+    c = (wd >> pos) & 1u;              if (r >= c) { pos += 1; }
+    return pos;
+}
+
+// One step of the in-batch rank scan: lane i looks at lane i+d (if it exists)
+// and bumps R when that later element was inserted at or before R.
+// SHFL.DOWN delivers the "source lane in range" predicate for free.
+__device__ __forceinline__ void rank_step(uint32_t& R, uint32_t ins, int d) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 x;\n\t"
+        "shfl.sync.down.b32 x|p, %1, %2, 31, 0xffffffff;\n\t"
+        "setp.le.and.u32 p, x, %0, p;\n\t"
+        "@p add.u32 %0, %0, 1;\n\t"
+        "}\n"
+        : "+r"(R)
+        : "r"(ins), "r"(d));
+}
+
+// lane i counts earlier lanes (i-d) whose value is smaller (order-free count)
+__device__ __forceinline__ void count_smaller_step(uint32_t& cnt, uint32_t mine, int d) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 x;\n\t"
+        "shfl.sync.up.b32 x|p, %1, %2, 0, 0xffffffff;\n\t"
+        "setp.lt.and.u32 p, x, %1, p;\n\t"
+        "@p add.u32 %0, %0, 1;\n\t"
+        "}\n"
+        : "+r"(cnt)
+        : "r"(mine), "r"(d));
+}
+
+// ---- double-double helpers (fp64 branch-length depths) --------------------
+struct dd { double hi, lo; };
+
+__device__ __forceinline__ dd two_sum(double a, double b) {
+    double s = __dadd_rn(a, b);
+    double bb = __dadd_rn(s, -a);
+    double e = __dadd_rn(__dadd_rn(a, -__dadd_rn(s, -bb)), __dadd_rn(b, -bb));
+    return {s, e};
+}
+__device__ __forceinline__ dd quick_two_sum(double a, double b) {
+    double s = __dadd_rn(a, b);
+    double e = __dadd_rn(b, -__dadd_rn(s, -a));
+    return {s, e};
+}
+__device__ __forceinline__ dd dd_add(dd a, dd b) {
+    dd s = two_sum(a.hi, b.hi);
+    dd t = two_sum(a.lo, b.lo);
+    s.lo = __dadd_rn(s.lo, t.hi);
+    s = quick_two_sum(s.hi, s.lo);
+    s.lo = __dadd_rn(s.lo, t.lo);
+    return quick_two_sum(s.hi, s.lo);
+}
+__device__ __forceinline__ dd dd_neg2(dd a) { return {-2.0 * a.hi, -2.0 * a.lo}; }
+
+}  // namespace p2v

@@ -1,0 +1,452 @@
+// Batched encode pairs / ancestry / edges -> v for sm_100a.
+//
+// Replaces (reference, paths relative to /root/reference):
+//   vector::convert::from_pairs      phylo2vec/src/vector/convert.rs:23-30
+//   vector::convert::from_ancestry   :129-136   + build_cherries :399-440
+//   vector::convert::from_edges      :201-213   + order_cherries :449-477
+//   vector::convert::build_vector    :320-337   + Fenwick :286-316
+//
+// Formulation (validated on the CPU by tests/parallel_model.py):
+//  * build_vector: for the cherry whose c_max is c, idx = number of EARLIER rows
+//    with a smaller c_max.  Walking the values c upwards in batches of 32, idx is
+//    a prefix-popcount on the "rows already seen" bit mask (state at batch
+//    start) plus an in-batch count of lower lanes with a smaller row.
+//  * build_cherries (min-descendant relabel) keeps the reference's row-order
+//    semantics but runs as a wavefront: 32 rows at a time, a row fires as soon
+//    as the rows defining its internal children have fired.
+#include "p2v_common.cuh"
+#include "p2v_internal.h"
+
+namespace p2v {
+
+constexpr int ENC_SMALL_WARPS = 4;
+constexpr int ENC_LARGE_THREADS = 256;
+constexpr int ENC_LARGE_WARPS = ENC_LARGE_THREADS / 32;
+
+// status codes written per tree
+constexpr int32_t TREE_OK = 0;
+constexpr int32_t TREE_MALFORMED = -2;
+
+// ---- generic per-tree body, parameterised on the storage type of the scratch
+//      arrays (uint16 in shared memory for k<=1024, uint32 in global above) ----
+template <typename IdxT, int MODE>
+__device__ __forceinline__ bool load_row(const IdxT* __restrict__ in, int s, int k, uint32_t& c1,
+                                         uint32_t& c2, uint32_t& p) {
+    long long a, b, c;
+    if (MODE == FROM_PAIRS) {
+        a = (long long)__ldg(in + 2 * (size_t)s);
+        b = (long long)__ldg(in + 2 * (size_t)s + 1);
+        c = 0;
+        if (a < 0 || a > k || b < 0 || b > k) return false;
+    } else if (MODE == FROM_ANCESTRY) {
+        a = (long long)__ldg(in + 3 * (size_t)s);
+        b = (long long)__ldg(in + 3 * (size_t)s + 1);
+        c = (long long)__ldg(in + 3 * (size_t)s + 2);
+        const long long top = 2LL * k + 1;
+        if (a < 0 || a > top || b < 0 || b > top || c < 0 || c > top) return false;
+    } else {  // FROM_EDGES: edges[2s] = (c1, p), edges[2s+1] = (c2, .)   convert.rs:206-208
+        a = (long long)__ldg(in + 4 * (size_t)s);
+        c = (long long)__ldg(in + 4 * (size_t)s + 1);
+        b = (long long)__ldg(in + 4 * (size_t)s + 2);
+        const long long top = 2LL * k + 1;
+        if (a < 0 || a > top || b < 0 || b > top || c < 0 || c > top) return false;
+    }
+    c1 = (uint32_t)a; c2 = (uint32_t)b; p = (uint32_t)c;
+    return true;
+}
+
+// --------------------------------------------------------------------------
+// k <= 1024: one warp per tree, shared memory.
+// --------------------------------------------------------------------------
+template <typename IdxT, int MODE>
+__global__ void __launch_bounds__(ENC_SMALL_WARPS * 32)
+encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restrict__ vout,
+                    int32_t* __restrict__ status, int K) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int KA = K + 32;
+    const int KL = 2 * K + 64;  // label-indexed arrays (labels 0..2k+1)
+    const bool has_par = (MODE != FROM_PAIRS);
+    const size_t per_warp = (size_t)3 * KA + (has_par ? 2 * (size_t)KL : 0) + 64;
+    uint16_t* base = reinterpret_cast<uint16_t*>(smem_raw) + warp * per_warp;
+    uint16_t* sc1 = base;
+    uint16_t* sc2 = sc1 + KA;
+    uint16_t* spr = sc2 + KA;       // parent label by row; later row_of[value]
+    uint16_t* sdef = spr + KA;      // defining row of an internal label      [has_par]
+    uint16_t* smd = sdef + KL;      // min descendant of an internal label    [has_par]
+    uint32_t* smask = reinterpret_cast<uint32_t*>(base + per_warp - 64);
+    const int nb = K >> 5;
+    const int in_cols = (MODE == FROM_PAIRS) ? 2 : (MODE == FROM_ANCESTRY ? 3 : 4);
+
+    for (int64_t tree = (int64_t)blockIdx.x * ENC_SMALL_WARPS + warp; tree < B;
+         tree += (int64_t)gridDim.x * ENC_SMALL_WARPS) {
+        const IdxT* it = in + tree * ((int64_t)k * in_cols);
+        bool bad = false;
+        // ---- E1: load rows ----------------------------------------------------------
+        if (has_par) {
+            for (int i = lane; i < KL; i += 32) { sdef[i] = (uint16_t)NONE16; smd[i] = (uint16_t)NONE16; }
+        }
+        smask[lane] = 0;
+        __syncwarp();
+        if (MODE == FROM_EDGES) {
+            // order_cherries (convert.rs:449-477): row -> index parent - k - offset
+            uint32_t mx = 0;
+            for (int b = 0; b < nb; ++b) {
+                const int s = b * 32 + lane;
+                uint32_t c1 = 0, c2 = 0, p = 0;
+                if (s < k && !load_row<IdxT, MODE>(it, s, k, c1, c2, p)) bad = true;
+                mx = max(mx, p);
+            }
+#pragma unroll
+            for (int d = 16; d; d >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, d));
+            bad = __any_sync(FULL, bad);
+            const long long offset = (long long)mx - 2LL * k + 1;
+            if (!bad) {
+                for (int b = 0; b < nb; ++b) {
+                    const int s = b * 32 + lane;
+                    if (s < k) {
+                        uint32_t c1, c2, p;
+                        load_row<IdxT, MODE>(it, s, k, c1, c2, p);
+                        const long long idx = (long long)p - k - offset;
+                        if (idx < 0 || idx >= k) bad = true;
+                        else {
+                            const uint32_t old = atomicOr(&smask[idx >> 5], 1u << (idx & 31));
+                            if (old & (1u << (idx & 31))) bad = true;  // two rows, one parent
+                            sc1[idx] = (uint16_t)c1; sc2[idx] = (uint16_t)c2; spr[idx] = (uint16_t)p;
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int b = 0; b < nb; ++b) {
+                const int s = b * 32 + lane;
+                if (s < k) {
+                    uint32_t c1 = 0, c2 = 0, p = 0;
+                    if (!load_row<IdxT, MODE>(it, s, k, c1, c2, p)) bad = true;
+                    sc1[s] = (uint16_t)c1; sc2[s] = (uint16_t)c2; spr[s] = (uint16_t)p;
+                }
+            }
+        }
+        bad = __any_sync(FULL, bad);
+        __syncwarp();
+        smask[lane] = 0;
+        // ---- E2: min-descendant relabel (build_cherries) as a wavefront ---------------
+        if (has_par && !bad) {
+            for (int b = 0; b < nb; ++b) {
+                const int s = b * 32 + lane;
+                if (s < k) sdef[spr[s]] = (uint16_t)s;
+            }
+            __syncwarp();
+            for (int b = 0; b < nb; ++b) {
+                const int base_row = b * 32;
+                const int s = base_row + lane;
+                const bool act = s < k;
+                uint32_t c1 = 0, c2 = 0, p = 0, d1 = NONE16, d2 = NONE16;
+                if (act) {
+                    c1 = sc1[s]; c2 = sc2[s]; p = spr[s];
+                    d1 = sdef[c1]; d2 = sdef[c2];
+                    if (d1 != NONE16 && d1 >= (uint32_t)s) d1 = NONE16;  // defined later: a leaf, as in the reference
+                    if (d2 != NONE16 && d2 >= (uint32_t)s) d2 = NONE16;
+                }
+                uint32_t done = __ballot_sync(FULL, !act);
+                while (done != FULL) {
+                    bool ready = false;
+                    if (!((done >> lane) & 1u)) {
+                        const bool w1 = d1 != NONE16 && d1 >= (uint32_t)base_row && !((done >> (d1 - base_row)) & 1u);
+                        const bool w2 = d2 != NONE16 && d2 >= (uint32_t)base_row && !((done >> (d2 - base_row)) & 1u);
+                        ready = !w1 && !w2;
+                        if (ready) {
+                            const uint32_t m1 = (d1 != NONE16) ? (uint32_t)smd[c1] : c1;
+                            const uint32_t m2 = (d2 != NONE16) ? (uint32_t)smd[c2] : c2;
+                            smd[p] = (uint16_t)min(m1, m2);
+                            sc1[s] = (uint16_t)m1; sc2[s] = (uint16_t)m2;
+                        }
+                    }
+                    __syncwarp();
+                    done |= __ballot_sync(FULL, ready);
+                }
+            }
+            __syncwarp();
+        }
+        // ---- E3: row_of[c_max], c_max must be a permutation of 1..k ---------------------
+        if (!bad) {
+            for (int b = 0; b < nb; ++b) {
+                const int s = b * 32 + lane;
+                if (s < k) {
+                    const uint32_t cm = max((uint32_t)sc1[s], (uint32_t)sc2[s]);
+                    if (cm < 1 || cm > (uint32_t)k) bad = true;
+                    else {
+                        const uint32_t bit = 1u << ((cm - 1) & 31);
+                        if (atomicOr(&smask[(cm - 1) >> 5], bit) & bit) bad = true;
+                        spr[cm] = (uint16_t)s;
+                    }
+                }
+            }
+            bad = __any_sync(FULL, bad);
+        }
+        __syncwarp();
+        if (bad) {
+            if (lane == 0 && status) status[tree] = TREE_MALFORMED;
+            continue;
+        }
+        if (lane == 0 && status) status[tree] = TREE_OK;
+        smask[lane] = 0;
+        __syncwarp();
+        // ---- E4: build_vector, values ascending ------------------------------------------
+        IdxT* vo = vout + tree * k;
+        uint32_t word = 0;  // rows already seen (rows of smaller values), word `lane`
+        for (int b = 0; b < nb; ++b) {
+            const int c = b * 32 + lane + 1;
+            const bool act = c <= k;
+            const uint32_t r = act ? (uint32_t)spr[c] : 0u;
+            const uint32_t cnt = __popc(word);
+            const uint32_t excl = warp_incl_scan(cnt, lane) - cnt;
+            const uint32_t wd = __shfl_sync(FULL, word, r >> 5);
+            uint32_t idx = __shfl_sync(FULL, excl, r >> 5) + __popc(wd & ((1u << (r & 31)) - 1u));
+            const uint32_t mine = act ? r : 0xFFFFFFFFu;
+#pragma unroll
+            for (int d = 1; d < 32; ++d) count_smaller_step(idx, mine, d);
+            if (act) {
+                const uint32_t lo = min((uint32_t)sc1[r], (uint32_t)sc2[r]);
+                vo[c - 1] = (IdxT)(idx == 0 ? lo : (uint32_t)(c - 1) + idx);
+                atomicOr(&smask[r >> 5], 1u << (r & 31));
+            }
+            __syncwarp();
+            word = smask[lane];
+        }
+        __syncwarp();
+    }
+}
+
+// --------------------------------------------------------------------------
+// k > 1024: one CTA per tree, scratch in a global workspace, bit mask + Fenwick
+// tree in shared memory.
+// --------------------------------------------------------------------------
+template <typename IdxT, int MODE>
+__global__ void __launch_bounds__(ENC_LARGE_THREADS)
+encode_large_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restrict__ vout,
+                    int32_t* __restrict__ status, uint32_t* __restrict__ ws, size_t ws_stride) {
+    extern __shared__ __align__(16) uint32_t sm32[];
+    __shared__ int s_bad;
+    __shared__ uint32_t s_max;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nw = (k + 31) >> 5;
+    const int KA = ((k + 1 + 31) & ~31) + 32;
+    const int KL = ((2 * k + 2 + 31) & ~31) + 32;
+    uint32_t* bits = sm32;
+    uint32_t* fen = bits + nw;      // fen[1..nw]
+    uint32_t* wc1 = ws + (size_t)blockIdx.x * ws_stride;
+    uint32_t* wc2 = wc1 + KA;
+    uint32_t* wpr = wc2 + KA;       // parent by row; later row_of[value]
+    uint32_t* wcnt = wpr + KA;      // in-batch counts (by value-1)
+    uint32_t* wdef = wcnt + KA;
+    uint32_t* wmd = wdef + KL;
+    const bool has_par = (MODE != FROM_PAIRS);
+    const int in_cols = (MODE == FROM_PAIRS) ? 2 : (MODE == FROM_ANCESTRY ? 3 : 4);
+
+    for (int64_t tree = blockIdx.x; tree < B; tree += gridDim.x) {
+        const IdxT* it = in + tree * ((int64_t)k * in_cols);
+        if (tid == 0) { s_bad = 0; s_max = 0; }
+        for (int w = tid; w < nw; w += ENC_LARGE_THREADS) bits[w] = 0;
+        for (int i = tid; i <= nw; i += ENC_LARGE_THREADS) fen[i] = 0;
+        if (has_par)
+            for (int i = tid; i < KL; i += ENC_LARGE_THREADS) { wdef[i] = NONE32; wmd[i] = NONE32; }
+        __syncthreads();
+        // ---- E1 ---------------------------------------------------------------------
+        if (MODE == FROM_EDGES) {
+            uint32_t mx = 0;
+            for (int s = tid; s < k; s += ENC_LARGE_THREADS) {
+                uint32_t c1 = 0, c2 = 0, p = 0;
+                if (!load_row<IdxT, MODE>(it, s, k, c1, c2, p)) s_bad = 1;
+                mx = max(mx, p);
+            }
+            atomicMax(&s_max, mx);
+            __syncthreads();
+            const long long offset = (long long)s_max - 2LL * k + 1;
+            if (!s_bad) {
+                for (int s = tid; s < k; s += ENC_LARGE_THREADS) {
+                    uint32_t c1, c2, p;
+                    load_row<IdxT, MODE>(it, s, k, c1, c2, p);
+                    const long long idx = (long long)p - k - offset;
+                    if (idx < 0 || idx >= k) s_bad = 1;
+                    else {
+                        const uint32_t bit = 1u << (idx & 31);
+                        if (atomicOr(&bits[idx >> 5], bit) & bit) s_bad = 1;
+                        wc1[idx] = c1; wc2[idx] = c2; wpr[idx] = p;
+                    }
+                }
+            }
+            __syncthreads();
+            for (int w = tid; w < nw; w += ENC_LARGE_THREADS) bits[w] = 0;
+        } else {
+            for (int s = tid; s < k; s += ENC_LARGE_THREADS) {
+                uint32_t c1 = 0, c2 = 0, p = 0;
+                if (!load_row<IdxT, MODE>(it, s, k, c1, c2, p)) s_bad = 1;
+                wc1[s] = c1; wc2[s] = c2; wpr[s] = p;
+            }
+        }
+        __syncthreads();
+        // ---- E2: wavefront over 32-row batches, one warp (rows depend on earlier rows) ----
+        if (has_par && !s_bad) {
+            for (int s = tid; s < k; s += ENC_LARGE_THREADS) wdef[wpr[s]] = (uint32_t)s;
+            __syncthreads();
+            if (warp == 0) {
+                for (int b = 0; b < nw; ++b) {
+                    const int base_row = b * 32;
+                    const int s = base_row + lane;
+                    const bool act = s < k;
+                    uint32_t c1 = 0, c2 = 0, p = 0, d1 = NONE32, d2 = NONE32;
+                    if (act) {
+                        c1 = wc1[s]; c2 = wc2[s]; p = wpr[s];
+                        d1 = wdef[c1]; d2 = wdef[c2];
+                        if (d1 != NONE32 && d1 >= (uint32_t)s) d1 = NONE32;
+                        if (d2 != NONE32 && d2 >= (uint32_t)s) d2 = NONE32;
+                    }
+                    uint32_t done = __ballot_sync(FULL, !act);
+                    while (done != FULL) {
+                        bool ready = false;
+                        if (!((done >> lane) & 1u)) {
+                            const bool w1 = d1 != NONE32 && d1 >= (uint32_t)base_row && !((done >> (d1 - base_row)) & 1u);
+                            const bool w2 = d2 != NONE32 && d2 >= (uint32_t)base_row && !((done >> (d2 - base_row)) & 1u);
+                            ready = !w1 && !w2;
+                            if (ready) {
+                                const uint32_t m1 = (d1 != NONE32) ? wmd[c1] : c1;
+                                const uint32_t m2 = (d2 != NONE32) ? wmd[c2] : c2;
+                                wmd[p] = min(m1, m2);
+                                wc1[s] = m1; wc2[s] = m2;
+                            }
+                        }
+                        __syncwarp();
+                        done |= __ballot_sync(FULL, ready);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- E3 ---------------------------------------------------------------------
+        if (!s_bad) {
+            for (int s = tid; s < k; s += ENC_LARGE_THREADS) {
+                const uint32_t cm = max(wc1[s], wc2[s]);
+                if (cm < 1 || cm > (uint32_t)k) s_bad = 1;
+                else {
+                    const uint32_t bit = 1u << ((cm - 1) & 31);
+                    if (atomicOr(&bits[(cm - 1) >> 5], bit) & bit) s_bad = 1;
+                    wpr[cm] = (uint32_t)s;
+                }
+            }
+        }
+        __syncthreads();
+        if (s_bad) {
+            if (tid == 0 && status) status[tree] = TREE_MALFORMED;
+            __syncthreads();
+            continue;
+        }
+        if (tid == 0 && status) status[tree] = TREE_OK;
+        for (int w = tid; w < nw; w += ENC_LARGE_THREADS) bits[w] = 0;
+        // ---- E4a: in-batch counts, all warps --------------------------------------------
+        for (int b = warp; b < nw; b += ENC_LARGE_WARPS) {
+            const int c = b * 32 + lane + 1;
+            const bool act = c <= k;
+            const uint32_t mine = act ? wpr[c] : 0xFFFFFFFFu;
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int d = 1; d < 32; ++d) count_smaller_step(cnt, mine, d);
+            if (act) wcnt[c - 1] = cnt;
+        }
+        __syncthreads();
+        // ---- E4b: prefix counts on the seen-rows mask, serial over value batches ------------
+        if (warp == 0) {
+            IdxT* vo = vout + tree * k;
+            for (int b = 0; b < nw; ++b) {
+                const int c = b * 32 + lane + 1;
+                const bool act = c <= k;
+                uint32_t r = 0;
+                if (act) {
+                    r = wpr[c];
+                    const int w = (int)(r >> 5);
+                    uint32_t idx = wcnt[c - 1] + __popc(bits[w] & ((1u << (r & 31)) - 1u));
+                    for (int i = w; i > 0; i -= i & -i) idx += fen[i];
+                    const uint32_t lo = min(wc1[r], wc2[r]);
+                    vo[c - 1] = (IdxT)(idx == 0 ? lo : (uint32_t)(c - 1) + idx);
+                }
+                __syncwarp();
+                if (act) {
+                    const int w = (int)(r >> 5);
+                    atomicOr(&bits[w], 1u << (r & 31));
+                    for (int i = w + 1; i <= nw; i += i & -i) atomicAdd(&fen[i], 1u);
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// --------------------------------------------------------------------------
+static size_t enc_large_stride(int64_t k) {
+    const size_t KA = (((size_t)k + 1 + 31) & ~(size_t)31) + 32;
+    const size_t KL = ((2 * (size_t)k + 2 + 31) & ~(size_t)31) + 32;
+    return 4 * KA + 2 * KL;
+}
+static int enc_large_grid(int64_t B) {
+    const int64_t cap = (int64_t)sm_count() * 4;
+    return (int)(B < cap ? B : cap);
+}
+
+size_t encode_workspace_bytes(int64_t B, int64_t k) {
+    if (k <= SMALL_K_MAX || B <= 0) return 0;
+    return (size_t)enc_large_grid(B) * enc_large_stride(k) * sizeof(uint32_t);
+}
+
+template <typename IdxT, int MODE>
+static cudaError_t launch_encode_t(const void* in, int64_t B, int64_t k, void* v, int32_t* status,
+                                   void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (k <= SMALL_K_MAX) {
+        const int K = (int)((k + 31) & ~31);
+        const size_t per_warp = (size_t)3 * (K + 32) + (MODE != FROM_PAIRS ? 2 * (size_t)(2 * K + 64) : 0) + 64;
+        const size_t smem = ENC_SMALL_WARPS * per_warp * sizeof(uint16_t);
+        auto kern = encode_small_kernel<IdxT, MODE>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ENC_SMALL_WARPS * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        int64_t want = (B + ENC_SMALL_WARPS - 1) / ENC_SMALL_WARPS;
+        int64_t cap = (int64_t)sm_count() * per_sm;
+        const int grid = (int)(want < cap ? want : cap);
+        kern<<<grid, ENC_SMALL_WARPS * 32, smem, stream>>>((const IdxT*)in, B, (int)k, (IdxT*)v, status, K);
+    } else {
+        const size_t stride = enc_large_stride(k);
+        const int grid = enc_large_grid(B);
+        if (!ws || ws_bytes < (size_t)grid * stride * sizeof(uint32_t)) return cudaErrorInvalidValue;
+        const int nw = (int)((k + 31) >> 5);
+        const size_t smem = ((size_t)2 * nw + 8) * sizeof(uint32_t);
+        auto kern = encode_large_kernel<IdxT, MODE>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, ENC_LARGE_THREADS, smem, stream>>>((const IdxT*)in, B, (int)k, (IdxT*)v, status,
+                                                       (uint32_t*)ws, stride);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_encode(int mode, const void* in, int idx_bytes, int64_t B, int64_t k, void* v,
+                          int32_t* status, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (B <= 0 || k <= 0) return cudaSuccess;
+#define P2V_DISPATCH(T)                                                                             \
+    switch (mode) {                                                                                 \
+    case FROM_PAIRS: return launch_encode_t<T, FROM_PAIRS>(in, B, k, v, status, ws, ws_bytes, stream);       \
+    case FROM_ANCESTRY: return launch_encode_t<T, FROM_ANCESTRY>(in, B, k, v, status, ws, ws_bytes, stream); \
+    case FROM_EDGES: return launch_encode_t<T, FROM_EDGES>(in, B, k, v, status, ws, ws_bytes, stream);       \
+    default: return cudaErrorInvalidValue;                                                          \
+    }
+    if (idx_bytes == 8) { P2V_DISPATCH(long long) }
+    if (idx_bytes == 4) { P2V_DISPATCH(int) }
+#undef P2V_DISPATCH
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace p2v

@@ -1,0 +1,46 @@
+// Internal launcher interface between the C ABI (p2v_capi.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace p2v {
+
+enum DecodeMode { MODE_PAIRS = 0, MODE_ANCESTRY = 1, MODE_EDGES = 2 };
+enum EncodeMode { FROM_PAIRS = 0, FROM_ANCESTRY = 1, FROM_EDGES = 2 };
+
+constexpr int SMALL_K_MAX = 1024;      // warp-per-tree kernels, everything in shared memory
+constexpr int LARGE_K_MAX = 1 << 19;   // CTA-per-tree kernels (bit mask + Fenwick in shared memory)
+
+int sm_count();
+void count_launch(int n = 1);
+
+// decode: v -> pairs / ancestry / edges
+size_t decode_workspace_bytes(int64_t B, int64_t k);
+// out_stride: elements between consecutive trees' outputs (0 = dense)
+cudaError_t launch_decode(int mode, const void* v, int idx_bytes, int64_t B, int64_t k, void* out,
+                          int32_t* status, void* ws, size_t ws_bytes, cudaStream_t stream,
+                          int64_t out_stride = 0);
+cudaError_t launch_check_v(const void* v, int idx_bytes, int64_t B, int64_t k, int32_t* status,
+                           cudaStream_t stream);
+
+// encode: pairs / ancestry / edges -> v
+size_t encode_workspace_bytes(int64_t B, int64_t k);
+cudaError_t launch_encode(int mode, const void* in, int idx_bytes, int64_t B, int64_t k, void* v,
+                          int32_t* status, void* ws, size_t ws_bytes, cudaStream_t stream);
+
+// cophenetic distances
+size_t cophenetic_workspace_bytes(int64_t B, int64_t k);
+// v_or_matrix: index vector (idx_bytes 4/8) with optional bls, or (k,3) f64 matrix when idx_bytes == 0
+cudaError_t launch_cophenetic(const void* v_or_matrix, int idx_bytes, const double* bls, int64_t B,
+                              int64_t k, int unrooted, int64_t row_begin, int64_t row_end,
+                              double* out, int32_t* status, void* ws, size_t ws_bytes,
+                              cudaStream_t stream);
+cudaError_t launch_cophenetic_prepare(const void* v_or_matrix, int idx_bytes, const double* bls, int64_t B,
+                                      int64_t k, int unrooted, int32_t* status, void* ws, size_t ws_bytes,
+                                      cudaStream_t stream);
+cudaError_t launch_cophenetic_rows(const void* ws, size_t ws_bytes, int64_t B, int64_t k, int weighted,
+                                   int64_t row_begin, int64_t row_end, double* out, cudaStream_t stream);
+cudaError_t launch_fill_f64(double* out, int64_t count, double value, cudaStream_t stream);
+
+}  // namespace p2v

@@ -1,0 +1,4 @@
+"""Same module layout as py-phylo2vec/phylo2vec/stats (nodewise part only)."""
+from .nodewise import cophenetic_distances, pairwise_distances
+
+__all__ = ["cophenetic_distances", "pairwise_distances"]

@@ -1,0 +1,294 @@
+"""Executable model of the data-parallel algorithms the CUDA kernels implement.
+
+Pure Python/numpy, no CUDA: it exists so that the *derivations* behind the
+kernels (DESIGN.md "Decode", "Encode", "Distance rows") are checked against the
+oracle on the CPU, where there is no GPU.  tests/test_parallel_model.py runs it.
+It mirrors the kernel phases one to one (same batch size, same formulas) but is
+not used by the product.
+"""
+
+import numpy as np
+
+W = 32  # batch width == warp width
+
+
+# --------------------------------------------------------------------------
+# Decode: v -> slot order -> pairs / ancestry / edges
+# --------------------------------------------------------------------------
+def slot_assignment(v):
+    """slot_of[t] for every element t (element t <-> leaf t+1, pair (., t+1)).
+
+    Insertion rank ins_t = 0 if v[t] <= t else v[t]-t (avl.rs:41-47: rank 0, or
+    index+1 = v[t]-(t+1)+1).  Going backwards in time, element t ends up in the
+    ins_t-th slot that later elements left free.  Batched: for a batch of W
+    consecutive times [a, a+W) the rank R_t of element t among elements
+    [0, a+W) follows from a forward scan inside the batch
+    (R = ins_t; for j in t+1..a+W-1: R += ins_j <= R); all W selects then run
+    against the same free mask."""
+    k = len(v)
+    ins = np.where(v <= np.arange(k), 0, v - np.arange(k))
+    free = np.ones(k, dtype=bool)
+    slot_of = np.full(k, -1, dtype=np.int64)
+    nb = (k + W - 1) // W
+    for b in range(nb - 1, -1, -1):
+        a, e = b * W, min(k, b * W + W)
+        R = ins[a:e].copy()
+        for lane in range(e - a):           # lanes run this in lock step with shfl.down
+            for d in range(1, e - a - lane):
+                if ins[a + lane + d] <= R[lane]:
+                    R[lane] += 1
+        free_idx = np.flatnonzero(free)      # rank-select on the mask
+        assert len(free_idx) == e
+        s = free_idx[R]
+        assert len(set(s.tolist())) == e - a
+        slot_of[a:e] = s
+        free[s] = False
+    return slot_of, ins
+
+
+def decode_model(v):
+    v = np.asarray(v, dtype=np.int64)
+    k = len(v)
+    if k == 0:
+        z = np.zeros((0, 2), dtype=np.int64)
+        return z, np.zeros((0, 3), dtype=np.int64), z
+    slot_of, ins = slot_assignment(v)
+    time_at = np.empty(k, dtype=np.int64)
+    time_at[slot_of] = np.arange(k)
+    is_root_t = ins == 0                     # inserted at rank 0 with its own label v[t]
+    # pairs: label of a slot = v[time] of the nearest root slot at or left of it
+    root_slot = np.where(is_root_t[time_at], np.arange(k), -1)
+    seg_root = np.maximum.accumulate(root_slot)       # segmented broadcast (max-scan)
+    assert seg_root[0] == 0
+    label = v[time_at[seg_root]]
+    pairs = np.stack([label, time_at + 1], axis=1)
+
+    # ancestry without the sequential parents[] pass (convert.rs:174-185):
+    #  * roots appear in slot order by DEcreasing time, so the segment of root j
+    #    ends right before the slot of the previous root in time.
+    #  * c1 of a non-root row is the previous row's parent (same label, same segment).
+    #  * c1 of a root row with label L: last earlier row carrying L == last row of the
+    #    segment of the next root in time with the same v value, else leaf L.
+    #  * c2 = leaf t+1: last earlier row carrying it == last row of the segment of
+    #    the first root j (in time) with v[j] == t+1, else leaf t+1.
+    roots_t = np.flatnonzero(is_root_t)
+    prev_root = np.full(k, -1, dtype=np.int64)
+    prev_root[roots_t[1:]] = roots_t[:-1]
+    seg_end_node = np.full(k, -1, dtype=np.int64)     # by root time j: k+1+(last slot of its segment)
+    for j in roots_t:
+        end = k - 1 if prev_root[j] < 0 else slot_of[prev_root[j]] - 1
+        seg_end_node[j] = k + 1 + end
+    next_occ = np.full(k, -1, dtype=np.int64)         # next root time with the same v value
+    first_root = np.full(k + 1, -1, dtype=np.int64)   # by value
+    for t in range(k - 1, -1, -1):
+        if is_root_t[t]:
+            next_occ[t] = first_root[v[t]]
+            first_root[v[t]] = t
+    anc = np.empty((k, 3), dtype=np.int64)
+    for s in range(k):
+        t = time_at[s]
+        if is_root_t[t]:
+            j = next_occ[t]
+            c1p = seg_end_node[j] if j >= 0 else v[t]
+        else:
+            c1p = k + s
+        j = first_root[t + 1] if t + 1 <= k else -1
+        c2p = seg_end_node[j] if j >= 0 else t + 1
+        anc[s] = (c1p, c2p, k + 1 + s)
+    edges = np.empty((2 * k, 2), dtype=np.int64)
+    edges[0::2, 0] = anc[:, 0]
+    edges[1::2, 0] = anc[:, 1]
+    edges[0::2, 1] = anc[:, 2]
+    edges[1::2, 1] = anc[:, 2]
+    return pairs, anc, edges
+
+
+# --------------------------------------------------------------------------
+# Encode: cherries [c1,c2,cmax] (row order) -> v    (convert.rs:320-337)
+# --------------------------------------------------------------------------
+def build_vector_model(cherries):
+    ch = np.asarray(cherries, dtype=np.int64).reshape(-1, 3)
+    k = len(ch)
+    row_of = np.full(k + 1, -1, dtype=np.int64)
+    row_of[ch[:, 2]] = np.arange(k)
+    assert (row_of[1:] >= 0).all(), "c_max must be a permutation of 1..k"
+    seen = np.zeros(k, dtype=bool)          # rows whose value is < current batch
+    v = np.zeros(k, dtype=np.int64)
+    for a in range(1, k + 1, W):
+        e = min(k + 1, a + W)
+        rows = row_of[a:e]
+        idx = np.array([seen[:r].sum() for r in rows])           # rank query on the mask
+        for lane in range(e - a):                                 # in-batch pairs
+            idx[lane] += sum(1 for l2 in range(lane) if rows[l2] < rows[lane])
+        for lane, c in enumerate(range(a, e)):
+            r = rows[lane]
+            v[c - 1] = min(ch[r, 0], ch[r, 1]) if idx[lane] == 0 else c - 1 + idx[lane]
+        seen[rows] = True
+    return v
+
+
+def min_desc_cherries_model(anc):
+    """build_cherries (convert.rs:399-440): sequential semantics."""
+    anc = np.asarray(anc, dtype=np.int64).reshape(-1, 3)
+    k = len(anc)
+    md = np.full(2 * k + 2, -1, dtype=np.int64)
+    out = np.empty_like(anc)
+    for r in range(k):
+        c1, c2, p = anc[r]
+        m1 = md[c1] if md[c1] >= 0 else c1
+        m2 = md[c2] if md[c2] >= 0 else c2
+        md[p] = min(m1, m2)
+        out[r] = (m1, m2, max(m1, m2))
+    return out
+
+
+# --------------------------------------------------------------------------
+# Distance rows: tables + blocked range-minimum scheme of the row kernel
+# --------------------------------------------------------------------------
+def tree_tables(v, bls, unrooted):
+    """Everything the row kernel reads, for one tree with k >= 2.
+
+    DFS order = the leaf order of the reference's Newick string (each row
+    appends the absorbed leaf's whole sequence to the label's sequence,
+    convert.rs:361-381).  sep[r] (r = 1..n-1) is the internal node that
+    separates DFS leaves r-1 and r: it is the absorbing row of the leaf at DFS
+    position r.  LCA(a,b) is then the shallowest sep in (a,b]."""
+    v = np.asarray(v, dtype=np.int64)
+    k = len(v)
+    n = k + 1
+    pairs, anc, _ = decode_model(v)
+    N = 2 * k + 1
+    par = np.full(N, -1, dtype=np.int64)
+    wlen = np.zeros(N)
+    for r in range(k):
+        c1, c2, p = anc[r]
+        par[c1] = par[c2] = p
+        wlen[c1] = 1.0 if bls is None else bls[r][0]
+        wlen[c2] = 1.0 if bls is None else bls[r][1]
+    wint = np.ones(N, dtype=np.int64)
+    wint[2 * k] = 0
+    if unrooted:
+        wlen[2 * k - 1] = 0.0
+        wint[2 * k - 1] = 0
+    # root-path sums by pointer jumping (log rounds)
+    depth_i = wint.copy()
+    depth_f = wlen.astype(np.longdouble)      # stands in for the kernel's double-double
+    anc_ptr = par.copy()
+    while (anc_ptr >= 0).any():
+        has = anc_ptr >= 0
+        ni, nf, na = depth_i.copy(), depth_f.copy(), anc_ptr.copy()
+        ni[has] += depth_i[anc_ptr[has]]
+        nf[has] += depth_f[anc_ptr[has]]
+        na[has] = anc_ptr[anc_ptr[has]]
+        depth_i, depth_f, anc_ptr = ni, nf, na
+    # leaf order: linked list of leaves, then ranking
+    nxt = np.full(n, -1, dtype=np.int64)
+    tail = np.arange(n)                       # current tail of each label's sequence
+    for s in range(k):
+        c1, c2 = pairs[s]
+        nxt[tail[c1]] = c2
+        tail[c1] = tail[c2]
+    order = []
+    x = 0
+    while x >= 0:
+        order.append(x)
+        x = nxt[x]
+    leaf_at = np.array(order)
+    assert len(leaf_at) == n
+    pos = np.empty(n, dtype=np.int64)
+    pos[leaf_at] = np.arange(n)
+    # absorbing row of leaf L>=1 is the slot of element L-1 -> node k+1+slot
+    slot_of, _ = slot_assignment(v)
+    sep_node = np.full(n, -1, dtype=np.int64)          # indexed by DFS position r>=1
+    sep_node[pos[1:]] = k + 1 + slot_of
+    return dict(n=n, k=k, pos=pos, leaf_at=leaf_at, depth_i=depth_i, depth_f=depth_f,
+                sep_node=sep_node, anc=anc)
+
+
+def distance_rows_model(v, bls, unrooted, R=8, rows=None):
+    """Blocked RMQ evaluation used by the row kernel.  Returns (n,n) float64
+    (only `rows` filled if given).  key = topological depth of the separator;
+    the LCA of DFS positions a<b is the separator with the smallest key in
+    (a,b]; that minimum is assembled from
+       row part   : suffix/prefix minimum inside the row's DFS block
+       column part: min(prefix/suffix minimum inside the column's block,
+                        minimum over the whole blocks in between)
+    and an R x R table for columns inside the row's own block."""
+    T = tree_tables(v, bls, unrooted)
+    n, pos, leaf_at = T["n"], T["pos"], T["leaf_at"]
+    BIG = 1 << 40
+    topo = bls is None
+    dep = T["depth_i"] if topo else T["depth_f"]
+    key = np.full(n + 1, BIG, dtype=np.int64)           # key[r], r=1..n-1; key[0], key[n] = +inf
+    key[1:n] = T["depth_i"][T["sep_node"][1:n]]
+    kval = np.zeros(n + 1, dtype=dep.dtype)
+    kval[1:n] = dep[T["sep_node"][1:n]]
+    nb = (n + R - 1) // R
+    # per-position within-block prefix / suffix minima (static tables)
+    pre_k = np.full(n, BIG, dtype=np.int64); pre_v = np.zeros(n, dtype=dep.dtype)
+    suf_k = np.full(n, BIG, dtype=np.int64); suf_v = np.zeros(n, dtype=dep.dtype)
+    blk_k = np.full(nb, BIG, dtype=np.int64); blk_v = np.zeros(nb, dtype=dep.dtype)
+    for b in range(nb):
+        lo, hi = b * R, min(n, b * R + R)
+        # prefix: min key[lo..p];   suffix: min key[p+1..hi-1]
+        bk, bv = BIG, 0
+        for p in range(lo, hi):
+            if key[p] < bk:
+                bk, bv = key[p], kval[p]
+            pre_k[p], pre_v[p] = bk, bv
+        blk_k[b], blk_v[b] = bk, bv
+        bk, bv = BIG, 0
+        for p in range(hi - 1, lo - 1, -1):
+            suf_k[p], suf_v[p] = bk, bv
+            if key[p] < bk:
+                bk, bv = key[p], kval[p]
+    out = np.zeros((n, n))
+    for I in range(nb):
+        lo, hi = I * R, min(n, I * R + R)
+        # per tile: minima over whole blocks strictly between I and J
+        mid_k = np.full(nb, BIG, dtype=np.int64); mid_v = np.zeros(nb, dtype=dep.dtype)
+        bk, bv = BIG, 0
+        for J in range(I + 1, nb):
+            mid_k[J], mid_v[J] = bk, bv
+            if blk_k[J] < bk:
+                bk, bv = blk_k[J], blk_v[J]
+        bk, bv = BIG, 0
+        for J in range(I - 1, -1, -1):
+            mid_k[J], mid_v[J] = bk, bv
+            if blk_k[J] < bk:
+                bk, bv = blk_k[J], blk_v[J]
+        for j in range(n):                      # column setup, once per tile
+            p = pos[j]
+            J = p // R
+            if J == I:
+                continue
+            if J > I:                           # column right of the tile: key[JR..p]
+                ck, cv = pre_k[p], pre_v[p]
+            else:                               # column left of the tile: key[p+1..(J+1)R-1]
+                ck, cv = suf_k[p], suf_v[p]
+            if mid_k[J] < ck:
+                ck, cv = mid_k[J], mid_v[J]
+            dj = dep[j]
+            for q in range(lo, hi):             # the streamed part
+                i = leaf_at[q]
+                if rows is not None and i not in rows:
+                    continue
+                if J > I:
+                    rk, rv = suf_k[q], suf_v[q]     # key[q+1..hi-1]
+                else:
+                    rk, rv = pre_k[q], pre_v[q]     # key[lo..q]
+                lv = cv if ck < rk else rv
+                out[i, j] = float((dep[i] - lv) + (dj - lv))
+        # columns inside the tile's own block: direct minima
+        for q in range(lo, hi):
+            i = leaf_at[q]
+            if rows is not None and i not in rows:
+                continue
+            for p in range(lo, hi):
+                if p == q:
+                    continue
+                a, b = min(p, q), max(p, q)
+                r = a + 1 + int(np.argmin(key[a + 1:b + 1]))
+                j = leaf_at[p]
+                out[i, j] = float((dep[i] - kval[r]) + (dep[j] - kval[r]))
+    return out

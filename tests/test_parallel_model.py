@@ -1,0 +1,43 @@
+"""Checks the data-parallel formulations used by the CUDA kernels (modelled in
+tests/parallel_model.py) against the oracle, on the CPU."""
+
+import numpy as np
+import pytest
+
+from oracle import p2v_oracle as O
+from tests import parallel_model as M
+from tests.helpers import adversarial_vectors, sample_bls, sample_vectors, to_matrix_input
+
+
+@pytest.mark.parametrize("n_leaves", [2, 3, 4, 5, 9, 32, 33, 34, 64, 65, 100, 257])
+def test_decode_model(n_leaves):
+    vs = list(sample_vectors(6, n_leaves, seed=n_leaves)) + \
+        list(sample_vectors(2, n_leaves, seed=n_leaves, ordered=True)) + \
+        list(adversarial_vectors(n_leaves).values())
+    for v in vs:
+        pairs, anc, edges = M.decode_model(v)
+        assert np.array_equal(pairs, O.to_pairs(v))
+        assert np.array_equal(anc, O.to_ancestry(v))
+        assert np.array_equal(edges, O.to_edges(v))
+
+
+@pytest.mark.parametrize("n_leaves", [2, 3, 5, 33, 34, 100, 200])
+def test_encode_model(n_leaves):
+    for v in list(sample_vectors(4, n_leaves, seed=n_leaves + 1)) + list(adversarial_vectors(n_leaves).values()):
+        pairs = O.to_pairs(v)
+        ch = np.concatenate([pairs, pairs.max(axis=1, keepdims=True)], axis=1)
+        assert np.array_equal(M.build_vector_model(ch), v)
+        assert np.array_equal(M.build_vector_model(M.min_desc_cherries_model(O.to_ancestry(v))), v)
+
+
+@pytest.mark.parametrize("n_leaves", [3, 4, 5, 8, 9, 17, 40, 70])
+@pytest.mark.parametrize("unrooted", [False, True])
+@pytest.mark.parametrize("R", [4, 8])
+def test_distance_rows_model(n_leaves, unrooted, R):
+    for s, v in enumerate(list(sample_vectors(3, n_leaves, seed=n_leaves)) + list(adversarial_vectors(n_leaves).values())):
+        d = M.distance_rows_model(v, None, unrooted, R=R)
+        assert np.array_equal(d, O.cophenetic_distances(v, unrooted))
+        bls = sample_bls(1, n_leaves, seed=s)[0]
+        d = M.distance_rows_model(v, bls, unrooted, R=R)
+        ref = O.cophenetic_distances(to_matrix_input(v, bls), unrooted)
+        assert np.allclose(d, ref, rtol=1e-13, atol=0)
