@@ -161,7 +161,7 @@ static int encode_host(int mode, int cols, const void* in, int idx_bytes, int64_
 static int coph_check(const void* in, const double* out, int64_t B, int64_t k, int64_t rb, int64_t re) {
     if (B < 0 || k < 0) return fail(P2V_ERR_INVALID_ARG, "negative batch or length");
     if (rb < 0 || re > k + 1 || rb > re) return fail(P2V_ERR_INVALID_ARG, "row block outside [0, n]");
-    if (B > 0 && (!out || (k > 0 && !in))) return fail(P2V_ERR_INVALID_ARG, "null buffer");
+    if (B > 0 && ((re > rb && !out) || (k > 0 && !in))) return fail(P2V_ERR_INVALID_ARG, "null buffer");
     if (k > LARGE_K_MAX) return fail(P2V_ERR_UNSUPPORTED, "k above the supported maximum (2^19)");
     return P2V_OK;
 }

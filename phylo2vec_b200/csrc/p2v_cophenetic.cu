@@ -584,9 +584,11 @@ cudaError_t launch_cophenetic_prepare(const void* v_or_matrix, int idx_bytes, co
             count_launch();
         }
         vin = v32; vin_bytes = 4;
-    } else if (idx_bytes == 8 && k > 0) {
-        narrow_v_kernel<<<grid1d, 256, 0, stream>>>(static_cast<const long long*>(v_or_matrix), B * k, v32);
-        count_launch();
+    } else if (idx_bytes == 8) {
+        if (k > 0) {
+            narrow_v_kernel<<<grid1d, 256, 0, stream>>>(static_cast<const long long*>(v_or_matrix), B * k, v32);
+            count_launch();
+        }
         vin = v32; vin_bytes = 4;
     } else if (idx_bytes != 4) {
         return cudaErrorInvalidValue;

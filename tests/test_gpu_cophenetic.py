@@ -33,6 +33,17 @@ def rel_err(a, b):
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))) if a.size else 0.0
 
 
+def assert_symmetric(d, exact):
+    """Topological matrices are bit-symmetric.  fp64 matrices are symmetric to the
+    last bits only: D[i][j] and D[j][i] may combine the same three double-double
+    depths in a different order (DESIGN.md "fp64 parity")."""
+    dt = np.swapaxes(d, -1, -2)
+    if exact:
+        assert np.array_equal(d, dt)
+    else:
+        assert rel_err(d, dt) <= 1e-15
+
+
 def test_goldens_single_tree(p2v, goldens):
     for g in goldens["cophenetic_vector"]:
         got = p2v.cophenetic_distances(np.array(g["v"], dtype=np.int64), unrooted=g["unrooted"])
@@ -92,7 +103,8 @@ def test_batch_parity(p2v, n_leaves, unrooted):
     M = to_matrix_input(V, bls)
     got_m = p2v.cophenetic_distances_batch(dev(M), unrooted=unrooted).cpu().numpy()
     assert np.array_equal(got_m, got)
-    assert np.array_equal(got, np.transpose(got, (0, 2, 1)))
+    assert_symmetric(got, exact=False)
+    assert_symmetric(p2v.cophenetic_distances_batch(dev(V), unrooted=unrooted).cpu().numpy(), exact=True)
     assert not np.diagonal(got, axis1=1, axis2=2).any()
 
 
@@ -139,7 +151,7 @@ def test_config_c3_sample(p2v):
         got = p2v.cophenetic_distances_batch(dev(V), unrooted=unrooted, bls=dev(bls)).cpu().numpy()
         ref = O.cophenetic_batch(V[:4], bls[:4], unrooted)
         assert rel_err(got[:4], ref) <= RTOL
-        assert np.array_equal(got, np.transpose(got, (0, 2, 1)))
+        assert_symmetric(got, exact=False)
 
 
 @pytest.mark.parametrize("n_leaves", [16384, 65536])
@@ -163,11 +175,13 @@ def test_single_large_tree(p2v, n_leaves):
     blk = n_leaves // G
     a = p2v.cophenetic_distances_batch(dev(M), rows=(0, blk))[0]            # rows [0,blk)
     b = p2v.cophenetic_distances_batch(dev(M), rows=(blk, 2 * blk))[0]      # rows [blk,2blk)
-    assert torch.equal(a[:, blk:2 * blk], b[:, :blk].T)
-    assert torch.equal(a[:, :blk], a[:, :blk].T)
+    assert rel_err(a[:, blk:2 * blk].cpu().numpy(), b[:, :blk].T.cpu().numpy()) <= 1e-15
+    assert_symmetric(a[:, :blk].cpu().numpy(), exact=False)
     assert not bool(torch.diagonal(a[:, :blk]).any())
     assert bool((a >= 0).all())
     t = p2v.cophenetic_distances_batch(dev(V), rows=(0, blk))[0]
+    t2 = p2v.cophenetic_distances_batch(dev(V), rows=(blk, 2 * blk))[0]
+    assert torch.equal(t[:, blk:2 * blk], t2[:, :blk].T) and torch.equal(t[:, :blk], t[:, :blk].T)
     assert torch.equal(t, t.round()) and float(t.max()) < 2 * n_leaves
 
 
