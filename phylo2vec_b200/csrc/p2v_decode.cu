@@ -58,6 +58,25 @@ __device__ __forceinline__ void store_row(IdxT* tree_out, int s, IdxT c1p, IdxT 
 // --------------------------------------------------------------------------
 // k <= 1024: one warp per tree, all state in shared memory (uint16).
 // --------------------------------------------------------------------------
+
+// Rank of element t = 32b+lane among the elements [0, 32b+32) at the end of its batch.
+// Lane i scans the later lanes i+1.. in time order; SHFL.DOWN past lane 31 hands back the
+// lane's own value, which always compares <= R, so the `lane` wrapped steps are taken off
+// at the end (they all come after the real ones).  The 31 shuffles do not depend on R and
+// are issued back to back; only the compare/add chain is serial.
+__device__ __forceinline__ uint32_t batch_rank(const uint16_t* __restrict__ sv, int b, int k, int lane) {
+    const int t = b * 32 + lane;
+    const uint32_t x = sv[t];
+    const uint32_t ins = (t < k) ? (x <= (uint32_t)t ? 0u : x - (uint32_t)t) : BIG;
+    uint32_t R = ins;
+#pragma unroll
+    for (int d = 1; d < 32; ++d) {
+        const uint32_t y = __shfl_down_sync(FULL, ins, d);
+        R += (y <= R) ? 1u : 0u;
+    }
+    return R - (uint32_t)lane;
+}
+
 template <typename IdxT, int MODE>
 __global__ void __launch_bounds__(SMALL_WARPS * 32)
 decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restrict__ out,
@@ -66,31 +85,39 @@ decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int KA = K + 32;
-    const int narr = (MODE == MODE_PAIRS) ? 2 : 5;
+    const int narr = (MODE == MODE_PAIRS) ? 2 : 3;
     uint16_t* base = reinterpret_cast<uint16_t*>(smem_raw) + (size_t)warp * (narr * KA + 64);
-    uint16_t* sv = base;            // v[t]                          (by time)
-    uint16_t* stime = sv + KA;      // element at slot s             (by slot)
-    uint16_t* slast = stime + KA;   // first root with value x       (by value)   [!PAIRS]
-    uint16_t* snext = slast + KA;   // next root with the same value (by time)    [!PAIRS]
-    uint16_t* sseg = snext + KA;    // k+1+last slot of root's segment (by time)  [!PAIRS]
+    uint16_t* sv = base;            // v[t]                                   (by time)
+    uint16_t* stime = sv + KA;      // element at slot s                      (by slot)
+    uint16_t* stbl = stime + KA;    // last row so far whose label is x       (by label)  [!PAIRS]
     uint32_t* smask = reinterpret_cast<uint32_t*>(base + narr * KA);  // 32 words of free-slot bits
     const int nb = K >> 5;
 
     for (int64_t tree = (int64_t)blockIdx.x * SMALL_WARPS + warp; tree < B;
          tree += (int64_t)gridDim.x * SMALL_WARPS) {
         const IdxT* vt = v + tree * k;
-        // ---- A: load, validate (check_v), narrow --------------------------------
+        // ---- A: load (8 loads in flight per lane), validate (check_v), narrow ----------
         int bad = -1;
-        for (int b = 0; b < nb; ++b) {
-            const int i = b * 32 + lane;
-            long long x = (i < k) ? (long long)__ldg(vt + i) : 0;
-            const bool ok = (i >= k) || (x >= 0 && x <= 2LL * i);
-            const unsigned bm = __ballot_sync(FULL, !ok);
-            if (bm && bad < 0) bad = b * 32 + __ffs(bm) - 1;
-            sv[i] = (uint16_t)x;
-            if (MODE != MODE_PAIRS) slast[i] = (uint16_t)NONE16;
+        for (int b0 = 0; b0 < nb; b0 += 8) {
+            long long xs[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = (b0 + j) * 32 + lane;
+                xs[j] = (i < k) ? (long long)__ldg(vt + i) : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = (b0 + j) * 32 + lane;
+                if (b0 + j < nb) {
+                    const bool ok = (i >= k) || (xs[j] >= 0 && xs[j] <= 2LL * i);
+                    const unsigned bm = __ballot_sync(FULL, !ok);
+                    if (bm && bad < 0) bad = (b0 + j) * 32 + __ffs(bm) - 1;
+                    sv[i] = (uint16_t)xs[j];
+                    if (MODE != MODE_PAIRS) stbl[i] = (uint16_t)NONE16;
+                }
+            }
         }
-        if (MODE != MODE_PAIRS) slast[K + lane] = (uint16_t)NONE16;
+        if (MODE != MODE_PAIRS) stbl[K + lane] = (uint16_t)NONE16;
         if (bad >= 0) {
             if (lane == 0 && status) status[tree] = bad + 1;
             __syncwarp();
@@ -103,15 +130,14 @@ decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
         smask[lane] = word;
         __syncwarp();
 
-        // ---- B: slot assignment, walking time backwards ---------------------------
+        // ---- B: slot assignment, walking time backwards; the rank scan of the next batch
+        //         is independent of the placement of the current one --------------------------
+        uint32_t Rnext = batch_rank(sv, nb - 1, k, lane);
         for (int b = nb - 1; b >= 0; --b) {
             const int t = b * 32 + lane;
             const bool act = t < k;
-            const uint32_t x = sv[t];
-            const uint32_t ins = act ? (x <= (uint32_t)t ? 0u : x - (uint32_t)t) : BIG;
-            uint32_t R = ins;
-#pragma unroll
-            for (int d = 1; d < 32; ++d) rank_step(R, ins, d);
+            const uint32_t R = Rnext;
+            if (b > 0) Rnext = batch_rank(sv, b - 1, k, lane);
             // rank-select R among the free slots
             const uint32_t cnt = __popc(word);
             const uint32_t incl = warp_incl_scan(cnt, lane);
@@ -119,7 +145,7 @@ decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
 #pragma unroll
             for (int step = 16; step >= 1; step >>= 1) {
                 const uint32_t y = __shfl_sync(FULL, incl, (w + step - 1) & 31);
-                if (y <= R && w + step <= 32) w += step;
+                if (y <= R) w += step;
             }
             w &= 31;
             const uint32_t wd = __shfl_sync(FULL, word, w);
@@ -129,73 +155,44 @@ decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
                 stime[w * 32 + pos] = (uint16_t)t;
                 atomicAnd(&smask[w], ~(1u << pos));
             }
-            if (MODE != MODE_PAIRS) {
-                // tables over root values, filled in the same backward sweep
-                const bool root = act && x <= (uint32_t)t;
-                const uint32_t key = root ? x : (0x10000u + lane);
-                const uint32_t peers = __match_any_sync(FULL, key);
-                const uint32_t higher = peers & lanes_gt(lane);
-                uint32_t nxt = NONE16;
-                if (root) nxt = higher ? (uint32_t)(b * 32 + __ffs(higher) - 1) : slast[x];
-                __syncwarp();
-                if (root) {
-                    snext[t] = (uint16_t)nxt;
-                    if ((peers & lanes_lt(lane)) == 0) slast[x] = (uint16_t)t;
-                }
-            }
             __syncwarp();
             word = smask[lane];
         }
 
+        // ---- D: forward sweep over the slots, 32 rows at a time -------------------------------
+        // label of a row = v[t] of the nearest root (rank-0 insertion) at or left of it.
+        // Ancestry / edges: the reference's parents[] pass (convert.rs:174-185) only ever looks
+        // up the last earlier row with a given label; stbl keeps that row per label, same-batch
+        // occurrences are resolved with MATCH.ANY.
         IdxT* ot = out + tree * out_stride;
-        if (MODE == MODE_PAIRS) {
-            // ---- D(pairs): label = v[root of the segment], second = time+1 -------
-            uint32_t carry = 0;
-            for (int b = 0; b < nb; ++b) {
-                const int s = b * 32 + lane;
-                const bool act = s < k;
-                const uint32_t t = act ? stime[s] : 0u;
-                const uint32_t x = sv[t];
-                const bool root = act && x <= t;
-                const uint32_t m = __ballot_sync(FULL, root) & lanes_le(lane);
-                const int src = m ? 31 - __clz(m) : 0;
-                uint32_t lab = __shfl_sync(FULL, x, src);
-                if (!m) lab = carry;
-                carry = __shfl_sync(FULL, lab, 31);
+        uint32_t lab_carry = 0;
+        for (int b = 0; b < nb; ++b) {
+            const int s = b * 32 + lane;
+            const bool act = s < k;
+            const uint32_t t = act ? stime[s] : 0u;
+            const uint32_t x = sv[t];
+            const bool root = act && x <= t;
+            const uint32_t m = __ballot_sync(FULL, root) & lanes_le(lane);
+            const int src = m ? 31 - __clz(m) : 0;
+            uint32_t lab = __shfl_sync(FULL, x, src);
+            if (!m) lab = lab_carry;
+            lab_carry = __shfl_sync(FULL, lab, 31);
+            if (MODE == MODE_PAIRS) {
                 if (act) store_pair<IdxT>(ot + 2 * (size_t)s, (IdxT)lab, (IdxT)(t + 1));
-            }
-        } else {
-            // ---- C: end of every root's segment (roots sit in slot order by
-            //         decreasing time; a segment ends before the next root slot) ----
-            int carry = k;
-            for (int b = nb - 1; b >= 0; --b) {
-                const int s = b * 32 + lane;
-                const bool act = s < k;
-                const uint32_t t = act ? stime[s] : 0u;
-                const uint32_t x = sv[t];
-                const bool root = act && x <= t;
-                const uint32_t rm = __ballot_sync(FULL, root);
-                const uint32_t higher = rm & lanes_gt(lane);
-                const int nr = higher ? b * 32 + __ffs(higher) - 1 : carry;
-                if (root) sseg[t] = (uint16_t)(k + nr);  // k+1 + (nr-1)
-                if (rm) carry = b * 32 + __ffs(rm) - 1;
-            }
-            __syncwarp();
-            // ---- D: rows [parents[c1], parents[c2], k+1+s] without the serial pass --
-            for (int b = 0; b < nb; ++b) {
-                const int s = b * 32 + lane;
-                if (s < k) {
-                    const uint32_t t = stime[s];
-                    const uint32_t x = sv[t];
-                    const uint32_t j2 = slast[t + 1];
-                    const uint32_t c2p = (j2 != NONE16) ? (uint32_t)sseg[j2] : t + 1;
-                    uint32_t c1p;
-                    if (x <= t) {
-                        const uint32_t j1 = snext[t];
-                        c1p = (j1 != NONE16) ? (uint32_t)sseg[j1] : x;
-                    } else {
-                        c1p = (uint32_t)(k + s);
-                    }
+            } else {
+                const uint32_t peers = __match_any_sync(FULL, act ? lab : (0x10000u + lane));
+                uint32_t c1p = (uint32_t)(k + s);            // non-root: the previous row's parent
+                if (root) {
+                    const uint32_t lower = peers & lanes_lt(lane);
+                    const uint32_t cand = lower ? (uint32_t)(b * 32 + 31 - __clz(lower)) : (uint32_t)stbl[lab];
+                    c1p = (cand != NONE16) ? (uint32_t)(k + 1) + cand : lab;
+                }
+                __syncwarp();
+                if (act && (peers & lanes_gt(lane)) == 0) stbl[lab] = (uint16_t)s;
+                __syncwarp();
+                if (act) {
+                    const uint32_t q = stbl[t + 1];
+                    const uint32_t c2p = (q != NONE16) ? (uint32_t)(k + 1) + q : t + 1;
                     store_row<IdxT, MODE>(ot, s, (IdxT)c1p, (IdxT)c2p, (IdxT)(k + 1 + s));
                 }
             }
@@ -463,7 +460,7 @@ static cudaError_t launch_decode_t(const void* v, int64_t B, int64_t k, void* ou
     if (out_stride <= 0) out_stride = k * (MODE == MODE_PAIRS ? 2 : (MODE == MODE_ANCESTRY ? 3 : 4));
     if (k <= SMALL_K_MAX) {
         const int K = (int)((k + 31) & ~31);
-        const int narr = (MODE == MODE_PAIRS) ? 2 : 5;
+        const int narr = (MODE == MODE_PAIRS) ? 2 : 3;
         const size_t smem = (size_t)SMALL_WARPS * ((size_t)narr * (K + 32) + 64) * sizeof(uint16_t);
         auto kern = decode_small_kernel<IdxT, MODE>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
