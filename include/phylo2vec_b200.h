@@ -110,11 +110,12 @@ int p2v_cophenetic_matrix_batch(const double *matrix, int64_t B, int64_t k, int 
 /* Two-phase form of the same computation: prepare once (decode + per-tree tables kept
  * in `workspace`), then emit any number of row blocks from the prepared workspace
  * (e.g. to stream a 34 GB matrix in pieces).  weighted = 0 for topological input
- * (v without bls), 1 for branch lengths (bls or matrix input). */
+ * (v without bls), 1 for branch lengths (bls or matrix input).  The rows call keeps its
+ * per-row-block tables in the same workspace: one call at a time per workspace. */
 int p2v_cophenetic_prepare_batch(const void *v_or_matrix, int idx_bytes /* 0 = (k,3) f64 matrix */,
                                  const double *bls, int64_t B, int64_t k, int unrooted, int32_t *status,
                                  void *workspace, size_t workspace_bytes, p2v_stream_t stream);
-int p2v_cophenetic_rows_batch(const void *workspace, size_t workspace_bytes, int64_t B, int64_t k,
+int p2v_cophenetic_rows_batch(void *workspace, size_t workspace_bytes, int64_t B, int64_t k,
                               int weighted, int64_t row_begin, int64_t row_end, double *out,
                               p2v_stream_t stream);
 

@@ -292,7 +292,7 @@ int p2v_cophenetic_prepare_batch(const void* v_or_matrix, int idx_bytes, const d
     return from_cuda(launch_cophenetic_prepare(v_or_matrix, idx_bytes, bls, B, k, unrooted, status, ws, ws_bytes,
                                                (cudaStream_t)stream), "cophenetic prepare");
 }
-int p2v_cophenetic_rows_batch(const void* ws, size_t ws_bytes, int64_t B, int64_t k, int weighted,
+int p2v_cophenetic_rows_batch(void* ws, size_t ws_bytes, int64_t B, int64_t k, int weighted,
                               int64_t row_begin, int64_t row_end, double* out, p2v_stream_t stream) {
     int rc = coph_check(ws, out, B, k, row_begin, row_end);
     if (rc) return rc;

@@ -14,40 +14,49 @@
 // the write order at :72-79), k = 0 and k = 1 are the special cases at :28-42.
 //
 // Pipeline per tree (k >= 2):
-//   1. decode v -> ancestry (p2v_decode.cu)
-//   2. tables_kernel: parent pointers; root-path sums (topological depth and
-//      double-double branch-length depth) by pointer jumping; Euler tour of the
-//      tree ranked by pointer jumping -> DFS position of every leaf and, for
-//      every DFS position r, the internal node sep[r] that separates leaves
-//      r-1 and r.  LCA(a,b) for DFS positions a<b is the shallowest sep in (a,b].
-//      Per DFS block of R positions: prefix / suffix minima and the block minimum.
-//   3. rows_kernel: one CTA = (DFS block of R rows) x (chunk of columns in
-//      label order).  The range minimum splits into a per-row part (inside the
-//      row's block), a per-column part (inside the column's block, combined once
-//      per CTA with the minimum over the whole blocks in between), so the
-//      streamed inner loop is a compare, a select and an add per element.
-//      Columns whose leaf lies inside the row block are patched afterwards from
-//      the running minima of that block.
-// fp64 branch lengths: depths are kept as double-double and the two candidates
-// (row part wins / column part wins) are pre-combined so that each element costs
-// three DADD and is rounded once (DESIGN.md "fp64 parity").
+//   prepare (independent of the requested rows)
+//     1. decode v -> ancestry (p2v_decode.cu)
+//     2. tables_kernel: parent pointers; root-path sums (topological depth and
+//        double-double branch-length depth) by pointer jumping; Euler tour of the
+//        tree ranked by pointer jumping -> DFS position of every leaf and, for
+//        every DFS position r, the internal node sep[r] that separates leaves
+//        r-1 and r.  LCA(a,b) for DFS positions a<b is the shallowest sep in (a,b].
+//   rows [row_begin,row_end)
+//     3. blocks_kernel: the DFS positions are cut into blocks that hold at most
+//        ROW_R requested rows and at most ROW_PMAX positions; per block: prefix /
+//        suffix minima of sep and the block minimum.
+//     4. rows_kernel: one CTA = (block with its <= ROW_R requested rows) x (chunk of
+//        1024 columns in label order).  With rl = the row's candidate inside its own
+//        block and cl = the column's candidate (inside its block, combined once per
+//        CTA with the minimum over the whole blocks in between), the LCA is the
+//        shallower of the two and both lie on one root path, so
+//            D = (d_i - d_rl) + (d_j - d_cl) + |d_rl - d_cl|
+//        -- three non-negative terms, no compare/select on the hot path, and for
+//        fp64 no cancellation: the first two are rounded once per row / column, the
+//        third is a double-double difference (DESIGN.md "fp64 parity").
+//        Columns whose leaf lies inside the row block are patched afterwards by the
+//        same CTA from a sparse table over the block's separators.
 #include "p2v_common.cuh"
 #include "p2v_internal.h"
 
 namespace p2v {
 
-constexpr int TAB_THREADS = 512;
+constexpr int TAB_THREADS = 1024;
+constexpr int BLK_THREADS = 1024;
 constexpr int ROW_THREADS = 256;
-constexpr int ROW_R = 64;                  // DFS positions (matrix rows) per CTA
+constexpr int ROW_R = 64;                  // requested rows per CTA (tile)
+constexpr int ROW_PMAX = 512;              // DFS positions per block at most
+constexpr int ROW_LEVELS = 10;             // sparse-table levels for ROW_PMAX
 constexpr int ROW_CPT = 4;                 // columns per thread (two 16-byte stores per row)
 constexpr int ROW_CHUNK = ROW_THREADS * ROW_CPT;   // 1024 columns per CTA
 constexpr int KEY_INF = 0x3FFFFFFF;
 
 struct CophLayout {
     // byte offsets inside one tree's table area
-    size_t anc, jA, jDI, jDH, jDL, tn, tc, pos, leaf_at, sepk, sephi, seplo, prek, sufk, prehi,
-        prelo, sufhi, suflo, blkk, blkhi, blklo, total;
-    int n, N, A, nb;
+    size_t anc, jA, jDI, jDH, jDL, tn, tc, pos, leaf_at, sepk, sephi, seplo;     // prepare
+    size_t blk_of, rowlist, prek, prea, sufk, sufa, bstart, bend, rowoff, cend, blkk, blka, hdr;  // rows call
+    size_t total;
+    int n, N, A, nbmax;
 };
 
 __host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -55,7 +64,7 @@ __host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15
 __host__ __device__ inline CophLayout coph_layout(int64_t k) {
     CophLayout L;
     L.n = (int)(k + 1); L.N = (int)(2 * k + 1); L.A = (int)(4 * k);
-    L.nb = (L.n + ROW_R - 1) / ROW_R;
+    L.nbmax = L.n / ROW_PMAX + L.n / ROW_R + 3;
     size_t o = 0;
     L.anc = o; o = al16(o + 4 * 3 * (size_t)k);
     L.jA = o; o = al16(o + 4 * 2 * (size_t)L.N);
@@ -69,15 +78,19 @@ __host__ __device__ inline CophLayout coph_layout(int64_t k) {
     L.sepk = o; o = al16(o + 4 * (size_t)(L.n + 1));
     L.sephi = o; o = al16(o + 8 * (size_t)(L.n + 1));
     L.seplo = o; o = al16(o + 8 * (size_t)(L.n + 1));
+    L.blk_of = o; o = al16(o + 4 * (size_t)L.n);
+    L.rowlist = o; o = al16(o + 4 * (size_t)L.n);
     L.prek = o; o = al16(o + 4 * (size_t)L.n);
+    L.prea = o; o = al16(o + 4 * (size_t)L.n);
     L.sufk = o; o = al16(o + 4 * (size_t)L.n);
-    L.prehi = o; o = al16(o + 8 * (size_t)L.n);
-    L.prelo = o; o = al16(o + 8 * (size_t)L.n);
-    L.sufhi = o; o = al16(o + 8 * (size_t)L.n);
-    L.suflo = o; o = al16(o + 8 * (size_t)L.n);
-    L.blkk = o; o = al16(o + 4 * (size_t)L.nb);
-    L.blkhi = o; o = al16(o + 8 * (size_t)L.nb);
-    L.blklo = o; o = al16(o + 8 * (size_t)L.nb);
+    L.sufa = o; o = al16(o + 4 * (size_t)L.n);
+    L.bstart = o; o = al16(o + 4 * (size_t)L.nbmax);
+    L.bend = o; o = al16(o + 4 * (size_t)L.nbmax);
+    L.rowoff = o; o = al16(o + 4 * (size_t)L.nbmax);
+    L.cend = o; o = al16(o + 4 * (size_t)L.nbmax);
+    L.blkk = o; o = al16(o + 4 * (size_t)L.nbmax);
+    L.blka = o; o = al16(o + 4 * (size_t)L.nbmax);
+    L.hdr = o; o = al16(o + 64);
     L.total = al16(o + 64);
     return L;
 }
@@ -242,39 +255,120 @@ tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* 
             sepk[r] = jDI[u]; sephi[r] = jDH[u]; seplo[r] = jDL[u];
         }
         __syncthreads();
-        // per-block prefix / suffix minima over the separators (by DFS position)
-        {
-            int* prek = reinterpret_cast<int*>(T + L.prek);
-            int* sufk = reinterpret_cast<int*>(T + L.sufk);
-            double* prehi = reinterpret_cast<double*>(T + L.prehi);
-            double* prelo = reinterpret_cast<double*>(T + L.prelo);
-            double* sufhi = reinterpret_cast<double*>(T + L.sufhi);
-            double* suflo = reinterpret_cast<double*>(T + L.suflo);
-            int* blkk = reinterpret_cast<int*>(T + L.blkk);
-            double* blkhi = reinterpret_cast<double*>(T + L.blkhi);
-            double* blklo = reinterpret_cast<double*>(T + L.blklo);
-            for (int b = tid; b < L.nb; b += TAB_THREADS) {
-                const int lo = b * ROW_R, hi = min(n, lo + ROW_R);
-                int bk = KEY_INF; double bh = 0.0, bl_ = 0.0;
-                for (int p = lo; p < hi; ++p) {          // pre[p] = min sep[lo..p]
-                    const int kk = sepk[p];
-                    if (kk < bk) { bk = kk; bh = sephi[p]; bl_ = seplo[p]; }
-                    prek[p] = bk; prehi[p] = bh; prelo[p] = bl_;
-                }
-                blkk[b] = bk; blkhi[b] = bh; blklo[b] = bl_;
-                bk = KEY_INF; bh = 0.0; bl_ = 0.0;
-                for (int p = hi - 1; p >= lo; --p) {     // suf[p] = min sep[p+1..hi-1]
-                    sufk[p] = bk; sufhi[p] = bh; suflo[p] = bl_;
-                    const int kk = sepk[p];
-                    if (kk < bk) { bk = kk; bh = sephi[p]; bl_ = seplo[p]; }
-                }
-            }
-        }
-        __syncthreads();
     }
 }
 
-// ---- 3. rows --------------------------------------------------------------------------------
+// ---- 3. blocks for the requested rows ----------------------------------------------------------
+// Block id of DFS position p:  p / ROW_PMAX + max(0, c(p) - 1) / ROW_R,  c(p) = number of requested
+// rows at positions <= p.  Hence every block holds <= ROW_R requested rows and <= ROW_PMAX positions
+// (ids that no position maps to stay empty).  hdr[0] = number of ids.
+__device__ __forceinline__ unsigned long long pack_key(int key, int p) {
+    return ((unsigned long long)(unsigned)key << 32) | (unsigned)p;
+}
+
+__global__ void __launch_bounds__(BLK_THREADS)
+blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int k, int64_t row_begin,
+              int64_t row_end, const int32_t* __restrict__ status) {
+    __shared__ int s_part[BLK_THREADS / 32];
+    const CophLayout L = coph_layout(k);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = L.n;
+    for (int64_t tree = blockIdx.x; tree < B; tree += gridDim.x) {
+        if (status && status[tree] != 0) continue;
+        unsigned char* T = tab + (size_t)tree * tab_stride;
+        const int* leaf_at = reinterpret_cast<const int*>(T + L.leaf_at);
+        const int* sepk = reinterpret_cast<const int*>(T + L.sepk);
+        int* blk_of = reinterpret_cast<int*>(T + L.blk_of);
+        int* rowlist = reinterpret_cast<int*>(T + L.rowlist);
+        int* prek = reinterpret_cast<int*>(T + L.prek);
+        int* prea = reinterpret_cast<int*>(T + L.prea);
+        int* sufk = reinterpret_cast<int*>(T + L.sufk);
+        int* sufa = reinterpret_cast<int*>(T + L.sufa);
+        int* bstart = reinterpret_cast<int*>(T + L.bstart);
+        int* bend = reinterpret_cast<int*>(T + L.bend);
+        int* rowoff = reinterpret_cast<int*>(T + L.rowoff);
+        int* cend = reinterpret_cast<int*>(T + L.cend);
+        int* blkk = reinterpret_cast<int*>(T + L.blkk);
+        int* blka = reinterpret_cast<int*>(T + L.blka);
+        int* hdr = reinterpret_cast<int*>(T + L.hdr);
+
+        __syncthreads();   // s_part of the previous tree is no longer read
+        for (int i = tid; i < L.nbmax; i += BLK_THREADS) {
+            bstart[i] = -1; bend[i] = -1; rowoff[i] = 0; cend[i] = 0; blkk[i] = KEY_INF; blka[i] = -1;
+        }
+        // counts of requested rows per contiguous chunk of positions, block-wide exclusive scan
+        const int CH = (n + BLK_THREADS - 1) / BLK_THREADS;
+        const int p0 = min(n, tid * CH), p1 = min(n, p0 + CH);
+        int cnt = 0;
+        for (int p = p0; p < p1; ++p) {
+            const int lab = leaf_at[p];
+            cnt += (lab >= row_begin && lab < row_end);
+        }
+        const int incl = (int)warp_incl_scan((uint32_t)cnt, lane);
+        if (lane == 31) s_part[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int v = s_part[lane];
+            const int sc = (int)warp_incl_scan((uint32_t)v, lane);
+            s_part[lane] = sc - v;
+        }
+        __syncthreads();
+        int c = s_part[warp] + incl - cnt;           // requested rows at positions < p0
+        int prev_id = (p0 > 0) ? (p0 - 1) / ROW_PMAX + max(0, c - 1) / ROW_R : -1;
+        for (int p = p0; p < p1; ++p) {
+            const int lab = leaf_at[p];
+            const int own = (lab >= row_begin && lab < row_end);
+            c += own;
+            const int id = p / ROW_PMAX + max(0, c - 1) / ROW_R;
+            blk_of[p] = id;
+            if (own) rowlist[c - 1] = p;
+            if (id != prev_id) {
+                bstart[id] = p; rowoff[id] = c - own;
+                if (prev_id >= 0) { bend[prev_id] = p; cend[prev_id] = c - own; }
+            }
+            prev_id = id;
+            if (p == n - 1) { bend[id] = n; cend[id] = c; hdr[0] = id + 1; }
+        }
+        __syncthreads();
+        // prefix / suffix minima of sep inside every block, one warp per block
+        const int nid = hdr[0];
+        for (int id = warp; id < nid; id += BLK_THREADS / 32) {
+            const int lo = bstart[id], hi = bend[id];
+            if (lo < 0) continue;
+            unsigned long long carry = pack_key(KEY_INF, 0);
+            for (int base = lo; base < hi; base += 32) {       // pre[p] = min sep[lo..p]
+                const int p = base + lane;
+                unsigned long long m = (p < hi) ? pack_key(sepk[p], p) : pack_key(KEY_INF, 0);
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned long long y = __shfl_up_sync(FULL, m, d);
+                    if (lane >= d) m = min(m, y);
+                }
+                m = min(m, carry);
+                if (p < hi) { prek[p] = (int)(m >> 32); prea[p] = (int)(m & 0xFFFFFFFFu); }
+                carry = __shfl_sync(FULL, m, 31);
+            }
+            if (lane == 0) { blkk[id] = (int)(carry >> 32); blka[id] = (int)(carry & 0xFFFFFFFFu); }
+            carry = pack_key(KEY_INF, 0);
+            for (int base = lo + ((hi - lo - 1) / 32) * 32; base >= lo; base -= 32) {   // suf[p] = min sep[p+1..hi-1]
+                const int p = base + lane;
+                unsigned long long m = (p < hi) ? pack_key(sepk[p], p) : pack_key(KEY_INF, 0);
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned long long y = __shfl_down_sync(FULL, m, d);
+                    if (lane + d < 32) m = min(m, y);
+                }
+                unsigned long long ex = __shfl_down_sync(FULL, m, 1);
+                if (lane == 31) ex = pack_key(KEY_INF, 0);
+                ex = min(ex, carry);
+                if (p < hi) { sufk[p] = (int)(ex >> 32); sufa[p] = (int)(ex & 0xFFFFFFFFu); }
+                carry = min(carry, __shfl_sync(FULL, m, 0));
+            }
+        }
+    }
+}
+
+// ---- 4. rows --------------------------------------------------------------------------------
 __device__ __forceinline__ double int_to_f64(int v) {
     // exact for |v| < 2^31 : one DADD instead of an I2F.F64 on the slow pipe
     return __hiloint2double(0x43300000, (int)(0x80000000u ^ (unsigned)v)) - 4503601774854144.0;  // 2^52 + 2^31
@@ -290,34 +384,43 @@ __device__ __forceinline__ void store2(double* p, double a, double b) {
     }
 }
 
+// double-double a - b, rounded to one double
+__device__ __forceinline__ double dd_diff_round(dd a, dd b) {
+    return __dadd_rn(__dadd_rn(a.hi, -b.hi), __dadd_rn(a.lo, -b.lo));
+}
+
 struct RowShared {
-    int label[ROW_R];
-    int bk[2][ROW_R];        // [0]: prefix key (columns left of the tile)  [1]: suffix key (columns right)
-    int di[ROW_R];           // topological depth of the row leaf
-    int fi[2][ROW_R];        // di - 2 * row-part depth                       (topological)
+    int label[ROW_R];          // leaf label of the row
+    int qpos[ROW_R];           // its DFS position
+    int ai[2][ROW_R];          // topological depth of the row candidate  [0]: columns left  [1]: right
+    int ui[2][ROW_R];          // d_i - that depth
+    int di[ROW_R];
+    double ahi[2][ROW_R], alo[2][ROW_R];   // double-double depth of the row candidate
+    double uf[2][ROW_R];                   // d_i - d_rl, rounded once
     double dhi[ROW_R], dlo[ROW_R];
-    double fhi[2][ROW_R], flo[2][ROW_R];
-    int sk[ROW_R + 1];       // separators of the tile (for the in-tile patch)
-    double shi[ROW_R + 1], slo[ROW_R + 1];
+    int kblk[ROW_PMAX];                    // separators of the block (patch)
+    unsigned short st[ROW_LEVELS][ROW_PMAX];   // sparse table of argmin offsets
+    int inlist[ROW_PMAX];                  // positions of in-block leaves whose column is in this chunk
+    int incount;
 };
 
 template <bool TOPO, bool VEC2>
-__global__ void __launch_bounds__(ROW_THREADS)
+__global__ void __launch_bounds__(ROW_THREADS, 3)
 rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int k,
             int64_t row_begin, int64_t row_end, double* __restrict__ out,
             const int32_t* __restrict__ status, int chunks_per_tree) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ RowShared S;
     const CophLayout L = coph_layout(k);
-    const int n = L.n, nb = L.nb;
-    int* midk = reinterpret_cast<int*>(dyn);          // nb
-    int* mida = midk + nb;                            // nb
-    unsigned long long* scanR = reinterpret_cast<unsigned long long*>(dyn + (((size_t)8 * nb + 15) & ~(size_t)15));
+    const int n = L.n, nbmax = L.nbmax;
+    int* midk = reinterpret_cast<int*>(dyn);          // nbmax
+    int* mida = midk + nbmax;                         // nbmax
+    unsigned long long* scanR = reinterpret_cast<unsigned long long*>(dyn + (((size_t)8 * nbmax + 15) & ~(size_t)15));
     unsigned long long* scanL = scanR + ROW_THREADS;
     const int tid = threadIdx.x;
     const int64_t rows = row_end - row_begin;
 
-    const int64_t tiles_per_tree = (int64_t)nb * chunks_per_tree;
+    const int64_t tiles_per_tree = (int64_t)nbmax * chunks_per_tree;
     for (int64_t work = blockIdx.x; work < B * tiles_per_tree; work += gridDim.x) {
         const int64_t tree = work / tiles_per_tree;
         const int rem = (int)(work % tiles_per_tree);
@@ -325,6 +428,18 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
         const int chunk = rem % chunks_per_tree;
         if (status && status[tree] != 0) continue;
         const unsigned char* T = tab + (size_t)tree * tab_stride;
+        const int* hdr = reinterpret_cast<const int*>(T + L.hdr);
+        const int nb = hdr[0];
+        if (I >= nb) continue;
+        const int* bstart = reinterpret_cast<const int*>(T + L.bstart);
+        const int lo = bstart[I];
+        if (lo < 0) continue;
+        const int* rowoff = reinterpret_cast<const int*>(T + L.rowoff);
+        const int* cend = reinterpret_cast<const int*>(T + L.cend);
+        const int roff = rowoff[I];
+        const int nrow = cend[I] - roff;
+        if (nrow <= 0) continue;                      // all conditions above are uniform per CTA
+        const int hi = reinterpret_cast<const int*>(T + L.bend)[I];
         const int* jDI = reinterpret_cast<const int*>(T + L.jDI);
         const double* jDH = reinterpret_cast<const double*>(T + L.jDH);
         const double* jDL = reinterpret_cast<const double*>(T + L.jDL);
@@ -333,60 +448,57 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
         const int* sepk = reinterpret_cast<const int*>(T + L.sepk);
         const double* sephi = reinterpret_cast<const double*>(T + L.sephi);
         const double* seplo = reinterpret_cast<const double*>(T + L.seplo);
+        const int* blk_of = reinterpret_cast<const int*>(T + L.blk_of);
+        const int* rowlist = reinterpret_cast<const int*>(T + L.rowlist);
         const int* prek = reinterpret_cast<const int*>(T + L.prek);
+        const int* prea = reinterpret_cast<const int*>(T + L.prea);
         const int* sufk = reinterpret_cast<const int*>(T + L.sufk);
-        const double* prehi = reinterpret_cast<const double*>(T + L.prehi);
-        const double* prelo = reinterpret_cast<const double*>(T + L.prelo);
-        const double* sufhi = reinterpret_cast<const double*>(T + L.sufhi);
-        const double* suflo = reinterpret_cast<const double*>(T + L.suflo);
+        const int* sufa = reinterpret_cast<const int*>(T + L.sufa);
         const int* blkk = reinterpret_cast<const int*>(T + L.blkk);
-        const double* blkhi = reinterpret_cast<const double*>(T + L.blkhi);
-        const double* blklo = reinterpret_cast<const double*>(T + L.blklo);
-        const int lo = I * ROW_R, hi = min(n, lo + ROW_R), nrow = hi - lo;
+        const int* blka = reinterpret_cast<const int*>(T + L.blka);
+        const int cbase = chunk * ROW_CHUNK;
         __syncthreads();   // previous iteration's readers of S / dyn are done
 
         // ---- row side of the tile -------------------------------------------------------
-        bool any_row = false;
         if (tid < nrow) {
-            const int q = lo + tid;
+            const int q = rowlist[roff + tid];
             const int i = leaf_at[q];
-            S.label[tid] = i;
-            const int pk = prek[q], sk = sufk[q];
-            S.bk[0][tid] = pk; S.bk[1][tid] = sk;
+            S.label[tid] = i; S.qpos[tid] = q;
             const int di = jDI[i];
             S.di[tid] = di;
-            if (TOPO) {
-                S.fi[0][tid] = di - 2 * pk;     // key == topological depth of the candidate
-                S.fi[1][tid] = di - 2 * sk;
-            } else {
-                const dd d = {jDH[i], jDL[i]};
-                S.dhi[tid] = d.hi; S.dlo[tid] = d.lo;
-                const dd f0 = dd_add(d, dd_neg2(dd{prehi[q], prelo[q]}));
-                const dd f1 = dd_add(d, dd_neg2(dd{sufhi[q], suflo[q]}));
-                S.fhi[0][tid] = f0.hi; S.flo[0][tid] = f0.lo;
-                S.fhi[1][tid] = f1.hi; S.flo[1][tid] = f1.lo;
+            const dd d = {jDH[i], jDL[i]};
+            if (!TOPO) { S.dhi[tid] = d.hi; S.dlo[tid] = d.lo; }
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const int ck = side ? sufk[q] : prek[q];
+                const int ca = side ? sufa[q] : prea[q];
+                const bool none = ck >= KEY_INF;         // no separator on that side inside the block
+                if (TOPO) {
+                    const int a = none ? di : ck;        // key == topological depth of the candidate
+                    S.ai[side][tid] = a; S.ui[side][tid] = di - a;
+                } else {
+                    const dd a = none ? d : dd{sephi[ca], seplo[ca]};
+                    S.ahi[side][tid] = a.hi; S.alo[side][tid] = a.lo;
+                    S.uf[side][tid] = none ? 0.0 : dd_diff_round(d, a);
+                }
             }
-            any_row = (i >= row_begin && i < row_end);
         }
-        if (tid <= nrow) {
-            const int r = lo + tid;
-            S.sk[tid] = (tid == 0) ? KEY_INF : sepk[min(r, n)];
-            if (!TOPO) { S.shi[tid] = sephi[min(r, n)]; S.slo[tid] = seplo[min(r, n)]; }
+        if (tid == 0) S.incount = 0;
+        // separators of the block for the in-block patch
+        for (int x = tid; x < hi - lo; x += ROW_THREADS) {
+            S.kblk[x] = sepk[lo + x];
+            S.st[0][x] = (unsigned short)x;
         }
-        if (!__syncthreads_or(any_row)) continue;    // none of this tile's rows is in [row_begin,row_end)
 
         // ---- minima over the whole blocks between the tile and every other block --------
-        // midk[J] / mida[J] = min / argmin of blkk over the blocks strictly between I and J.
-        // Each thread owns a contiguous segment of blocks; segment minima are combined with
-        // a block-wide prefix (right of I) and suffix (left of I) min-scan on packed
-        // (key << 32 | block) words, then every thread walks its own segment.
+        // midk[J] / mida[J] = min / arg position of sep over the blocks strictly between I and J.
         {
             const int SEG = (nb + ROW_THREADS - 1) / ROW_THREADS;
-            const int s0 = tid * SEG, s1 = min(nb, s0 + SEG);
+            const int s0 = min(nb, tid * SEG), s1 = min(nb, s0 + SEG);
             const unsigned long long INF64 = ((unsigned long long)KEY_INF << 32);
             unsigned long long pr = INF64, pl = INF64;      // this segment's minimum right / left of I
             for (int J = s0; J < s1; ++J) {
-                const unsigned long long e = ((unsigned long long)(unsigned)blkk[J] << 32) | (unsigned)J;
+                const unsigned long long e = ((unsigned long long)(unsigned)blkk[J] << 32) | (unsigned)blka[J];
                 if (J > I) pr = min(pr, e);
                 if (J < I) pl = min(pl, e);
             }
@@ -404,14 +516,14 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
             for (int J = s0; J < s1; ++J) {
                 if (J > I) {
                     midk[J] = (int)(run >> 32); mida[J] = (int)(run & 0xFFFFFFFFu);
-                    run = min(run, ((unsigned long long)(unsigned)blkk[J] << 32) | (unsigned)J);
+                    run = min(run, ((unsigned long long)(unsigned)blkk[J] << 32) | (unsigned)blka[J]);
                 }
             }
             run = (tid + 1 < ROW_THREADS) ? scanL[tid + 1] : INF64;            // blocks left of I, right of my segment
             for (int J = s1 - 1; J >= s0; --J) {
                 if (J < I) {
                     midk[J] = (int)(run >> 32); mida[J] = (int)(run & 0xFFFFFFFFu);
-                    run = min(run, ((unsigned long long)(unsigned)blkk[J] << 32) | (unsigned)J);
+                    run = min(run, ((unsigned long long)(unsigned)blkk[J] << 32) | (unsigned)blka[J]);
                 }
                 if (J == I) { midk[J] = KEY_INF; mida[J] = 0; }
             }
@@ -419,73 +531,66 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
         __syncthreads();
 
         // ---- column side: 4 columns per thread (two adjacent pairs) ----------------------
-        const int cbase = chunk * ROW_CHUNK;
-        int col[ROW_CPT];
-        int ak[ROW_CPT], side[ROW_CPT];
-        int ei[ROW_CPT], dji[ROW_CPT];
-        double ehi[ROW_CPT], elo[ROW_CPT], djh[ROW_CPT], djl[ROW_CPT];
+        int col[ROW_CPT], side[ROW_CPT];
+        int bi[ROW_CPT], uji[ROW_CPT];
+        double bhi[ROW_CPT], blo[ROW_CPT], ujf[ROW_CPT];
 #pragma unroll
         for (int c = 0; c < ROW_CPT; ++c) {
             const int j = cbase + (c >> 1) * (ROW_THREADS * 2) + 2 * tid + (c & 1);
             col[c] = j;
-            ak[c] = KEY_INF; side[c] = 0; ei[c] = 0; dji[c] = 0;
-            ehi[c] = elo[c] = djh[c] = djl[c] = 0.0;
+            side[c] = 0; bi[c] = 0; uji[c] = 0; bhi[c] = blo[c] = ujf[c] = 0.0;
             if (j < n) {
                 const int p = pos[j];
-                const int J = p / ROW_R;
+                const int J = blk_of[p];
                 const bool right = J > I;
                 side[c] = right ? 1 : 0;
                 int ck = right ? prek[p] : sufk[p];
-                dd cv = {0.0, 0.0};
-                if (!TOPO) cv = right ? dd{prehi[p], prelo[p]} : dd{sufhi[p], suflo[p]};
+                int ca = right ? prea[p] : sufa[p];
                 const int mk = midk[J];
-                if (mk < ck) {
-                    ck = mk;
-                    if (!TOPO) { const int a = mida[J]; cv = dd{blkhi[a], blklo[a]}; }
+                if (mk < ck) { ck = mk; ca = mida[J]; }
+                const bool none = ck >= KEY_INF;
+                const int dj = jDI[j];
+                if (J == I) {                      // patched after the streamed part
+                    const int slot = atomicAdd(&S.incount, 1);
+                    S.inlist[slot] = p;
                 }
-                if (J == I) ck = KEY_INF;      // patched after the streamed part
-                ak[c] = ck;
-                dji[c] = jDI[j];
                 if (TOPO) {
-                    ei[c] = dji[c] - 2 * ck;
+                    bi[c] = none ? dj : ck;
+                    uji[c] = dj - bi[c];
                 } else {
-                    const dd dj = {jDH[j], jDL[j]};
-                    djh[c] = dj.hi; djl[c] = dj.lo;
-                    const dd e = dd_add(dj, dd_neg2(cv));
-                    ehi[c] = e.hi; elo[c] = e.lo;
+                    const dd d = {jDH[j], jDL[j]};
+                    const dd b = none ? d : dd{sephi[ca], seplo[ca]};
+                    bhi[c] = b.hi; blo[c] = b.lo;
+                    ujf[c] = none ? 0.0 : dd_diff_round(d, b);
                 }
             }
         }
 
-        // ---- streamed part: R rows x 4 columns per thread ----------------------------------
+        // ---- streamed part: requested rows x 4 columns per thread -----------------------------
         double* obase = out + (size_t)tree * rows * n;
+#pragma unroll 2
         for (int r = 0; r < nrow; ++r) {
             const int i = S.label[r];
-            if (i < row_begin || i >= row_end) continue;
             double* orow = obase + (size_t)(i - row_begin) * n;
             double val[ROW_CPT];
             if (TOPO) {
-                const int b0 = S.bk[0][r], b1 = S.bk[1][r], f0 = S.fi[0][r], f1 = S.fi[1][r], di = S.di[r];
+                const int a0 = S.ai[0][r], a1 = S.ai[1][r], u0 = S.ui[0][r], u1 = S.ui[1][r];
 #pragma unroll
                 for (int c = 0; c < ROW_CPT; ++c) {
-                    const int rk = side[c] ? b1 : b0;
-                    const int f = side[c] ? f1 : f0;
-                    const int x = (ak[c] < rk) ? (di + ei[c]) : (f + dji[c]);
-                    val[c] = int_to_f64(x);
+                    const int a = side[c] ? a1 : a0;
+                    const int u = side[c] ? u1 : u0;
+                    val[c] = int_to_f64(u + uji[c] + abs(a - bi[c]));
                 }
             } else {
-                const int b0 = S.bk[0][r], b1 = S.bk[1][r];
-                const double dh = S.dhi[r], dl = S.dlo[r];
-                const double f0h = S.fhi[0][r], f0l = S.flo[0][r], f1h = S.fhi[1][r], f1l = S.flo[1][r];
+                const double a0h = S.ahi[0][r], a0l = S.alo[0][r], a1h = S.ahi[1][r], a1l = S.alo[1][r];
+                const double u0 = S.uf[0][r], u1 = S.uf[1][r];
 #pragma unroll
                 for (int c = 0; c < ROW_CPT; ++c) {
-                    const int rk = side[c] ? b1 : b0;
-                    const double fh = side[c] ? f1h : f0h;
-                    const double fl = side[c] ? f1l : f0l;
-                    const bool colwin = ak[c] < rk;
-                    const double xh = colwin ? dh : fh, xl = colwin ? dl : fl;
-                    const double yh = colwin ? ehi[c] : djh[c], yl = colwin ? elo[c] : djl[c];
-                    val[c] = __dadd_rn(__dadd_rn(xh, yh), __dadd_rn(xl, yl));
+                    const double ah = side[c] ? a1h : a0h;
+                    const double al = side[c] ? a1l : a0l;
+                    const double u = side[c] ? u1 : u0;
+                    const double m = __dadd_rn(__dadd_rn(ah, -bhi[c]), __dadd_rn(al, -blo[c]));
+                    val[c] = __dadd_rn(__dadd_rn(u, ujf[c]), fabs(m));
                 }
             }
 #pragma unroll
@@ -494,36 +599,41 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
                 else if (col[c] < n) __stcs(orow + col[c], val[c]);
             }
         }
-        __syncthreads();   // streamed stores of this CTA are ordered before the patch below
 
-        // ---- patch: columns whose leaf sits inside the tile (incl. the zero diagonal) ------
-        // thread a walks b = a+1.. with the running minimum of sep(a, b]
-        if (tid < nrow) {
-            const int a = tid;
-            const int ia = S.label[a];
-            const bool ia_row = ia >= row_begin && ia < row_end;
-            const bool ia_col = ia >= cbase && ia < cbase + ROW_CHUNK;
-            if (ia_row && ia_col) obase[(size_t)(ia - row_begin) * n + ia] = 0.0;
-            int bk = KEY_INF; dd bv = {0.0, 0.0};
-            for (int b = a + 1; b < nrow; ++b) {
-                if (S.sk[b] < bk) { bk = S.sk[b]; if (!TOPO) bv = dd{S.shi[b], S.slo[b]}; }
-                const int ib = S.label[b];
-                const bool ib_row = ib >= row_begin && ib < row_end;
-                const bool ib_col = ib >= cbase && ib < cbase + ROW_CHUNK;
-                if (!((ia_row && ib_col) || (ib_row && ia_col))) continue;
-                double d;
+        // ---- patch: columns whose leaf sits inside the block (incl. the zero diagonal) --------
+        // sparse table of argmin offsets over the block's separators
+        const int bs = hi - lo;
+        for (int lev = 1; (1 << lev) <= bs; ++lev) {
+            __syncthreads();
+            const int half = 1 << (lev - 1);
+            for (int x = tid; x + (1 << lev) <= bs; x += ROW_THREADS) {
+                const int a = S.st[lev - 1][x], b = S.st[lev - 1][x + half];
+                S.st[lev][x] = (unsigned short)(S.kblk[a] <= S.kblk[b] ? a : b);
+            }
+        }
+        __syncthreads();   // also orders the streamed stores of this CTA before the patch stores
+        const int nin = S.incount;
+        for (int w = tid; w < nin * nrow; w += ROW_THREADS) {
+            const int r = w / nin, e = w - r * nin;
+            const int q = S.qpos[r], p = S.inlist[e];
+            const int i = S.label[r], j = leaf_at[p];
+            double d = 0.0;
+            if (p != q) {
+                const int a = min(p, q) + 1 - lo, b = max(p, q) - lo;     // sep offsets a..b
+                const int lev = 31 - __clz(b - a + 1);
+                const int x = S.st[lev][a], y = S.st[lev][b - (1 << lev) + 1];
+                const int arg = (S.kblk[x] <= S.kblk[y]) ? x : y;
                 if (TOPO) {
-                    d = int_to_f64(S.di[a] + S.di[b] - 2 * bk);
+                    d = int_to_f64(S.di[r] + jDI[j] - 2 * S.kblk[arg]);
                 } else {
-                    // (d_a - lca) + (d_b - lca), each difference in double-double
-                    const dd m = dd{-bv.hi, -bv.lo};
-                    const dd xa = dd_add(dd{S.dhi[a], S.dlo[a]}, m);
-                    const dd xb = dd_add(dd{S.dhi[b], S.dlo[b]}, m);
+                    const dd l = {sephi[lo + arg], seplo[lo + arg]};
+                    const dd m = dd{-l.hi, -l.lo};
+                    const dd xa = dd_add(dd{S.dhi[r], S.dlo[r]}, m);
+                    const dd xb = dd_add(dd{jDH[j], jDL[j]}, m);
                     d = __dadd_rn(__dadd_rn(xa.hi, xb.hi), __dadd_rn(xa.lo, xb.lo));
                 }
-                if (ia_row && ib_col) obase[(size_t)(ia - row_begin) * n + ib] = d;
-                if (ib_row && ia_col) obase[(size_t)(ib - row_begin) * n + ia] = d;
             }
+            obase[(size_t)(i - row_begin) * n + j] = d;
         }
     }
 }
@@ -611,7 +721,7 @@ cudaError_t launch_cophenetic_prepare(const void* v_or_matrix, int idx_bytes, co
         e = launch_decode(MODE_ANCESTRY, vin, vin_bytes, B, k, tab + L.anc, st, wsb + W.dec, W.tab - W.dec,
                           stream, (int64_t)(L.total / sizeof(int)));
         if (e != cudaSuccess) return e;
-        const int64_t cap = (int64_t)sm_count() * 4;
+        const int64_t cap = (int64_t)sm_count() * 2;
         const int grid = (int)(B < cap ? B : cap);
         tables_kernel<<<grid, TAB_THREADS, 0, stream>>>(tab, L.total, bl, bl_stride, bl_tree_stride, B,
                                                        (int)k, unrooted, st);
@@ -626,8 +736,8 @@ cudaError_t launch_cophenetic_prepare(const void* v_or_matrix, int idx_bytes, co
     return cudaGetLastError();
 }
 
-// Phase 3: rows [row_begin,row_end) of every prepared tree.
-cudaError_t launch_cophenetic_rows(const void* ws, size_t ws_bytes, int64_t B, int64_t k, int weighted,
+// Phase 3+4: rows [row_begin,row_end) of every prepared tree.
+cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t k, int weighted,
                                    int64_t row_begin, int64_t row_end, double* out, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
     const int64_t n = k + 1;
@@ -635,7 +745,7 @@ cudaError_t launch_cophenetic_rows(const void* ws, size_t ws_bytes, int64_t B, i
     if (row_begin == row_end) return cudaSuccess;
     const CophWs W = coph_ws(B, k);
     if (!ws || ws_bytes < W.total) return cudaErrorInvalidValue;
-    const unsigned char* wsb = static_cast<const unsigned char*>(ws);
+    unsigned char* wsb = static_cast<unsigned char*>(ws);
     const int32_t* st = reinterpret_cast<const int32_t*>(wsb + W.status);
     cudaError_t e;
     if (k < 2) {
@@ -645,13 +755,21 @@ cudaError_t launch_cophenetic_rows(const void* ws, size_t ws_bytes, int64_t B, i
         return cudaGetLastError();
     }
     const CophLayout L = coph_layout(k);
-    const unsigned char* tab = wsb + W.tab;
+    unsigned char* tab = wsb + W.tab;
+    {
+        const int64_t cap = (int64_t)sm_count() * 2;
+        const int grid = (int)(B < cap ? B : cap);
+        blocks_kernel<<<grid, BLK_THREADS, 0, stream>>>(tab, L.total, B, (int)k, row_begin, row_end, st);
+        count_launch();
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
     const int chunks = (int)((n + ROW_CHUNK - 1) / ROW_CHUNK);
-    const int64_t work = B * (int64_t)L.nb * chunks;
-    const size_t smem = (((size_t)8 * L.nb + 15) & ~(size_t)15) + 2 * ROW_THREADS * sizeof(unsigned long long);
+    const int64_t work = B * (int64_t)L.nbmax * chunks;
+    const size_t smem = (((size_t)8 * L.nbmax + 15) & ~(size_t)15) + 2 * ROW_THREADS * sizeof(unsigned long long);
     const bool topo = !weighted;
     const bool vec2 = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    const int64_t cap = (int64_t)sm_count() * 64;
+    const int64_t cap = (int64_t)sm_count() * 96;
     const int grid = (int)(work < cap ? work : cap);
 #define P2V_ROWS(T_, V_)                                                                              \
     do {                                                                                              \

@@ -39,7 +39,7 @@ cudaError_t launch_cophenetic(const void* v_or_matrix, int idx_bytes, const doub
 cudaError_t launch_cophenetic_prepare(const void* v_or_matrix, int idx_bytes, const double* bls, int64_t B,
                                       int64_t k, int unrooted, int32_t* status, void* ws, size_t ws_bytes,
                                       cudaStream_t stream);
-cudaError_t launch_cophenetic_rows(const void* ws, size_t ws_bytes, int64_t B, int64_t k, int weighted,
+cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t k, int weighted,
                                    int64_t row_begin, int64_t row_end, double* out, cudaStream_t stream);
 cudaError_t launch_fill_f64(double* out, int64_t count, double value, cudaStream_t stream);
 

@@ -292,3 +292,94 @@ def distance_rows_model(v, bls, unrooted, R=8, rows=None):
                 j = leaf_at[p]
                 out[i, j] = float((dep[i] - kval[r]) + (dep[j] - kval[r]))
     return out
+
+
+# --------------------------------------------------------------------------
+# Row kernel, current formulation: blocks sized by the REQUESTED rows, and
+#   D = (d_i - d_rl) + (d_j - d_cl) + |d_rl - d_cl|
+# with rl / cl the row's / column's own candidate (see p2v_cophenetic.cu).
+# --------------------------------------------------------------------------
+def distance_rows_model_v2(v, bls, unrooted, row_begin, row_end, R=4, PMAX=16):
+    T = tree_tables(v, bls, unrooted)
+    n, pos, leaf_at = T["n"], T["pos"], T["leaf_at"]
+    INF = 1 << 40
+    topo = bls is None
+    dep = T["depth_i"] if topo else T["depth_f"]
+    key = np.full(n + 1, INF, dtype=np.int64)
+    key[1:n] = T["depth_i"][T["sep_node"][1:n]]
+    val = np.zeros(n + 1, dtype=dep.dtype)
+    val[1:n] = dep[T["sep_node"][1:n]]
+    own = np.array([(row_begin <= leaf_at[p] < row_end) for p in range(n)], dtype=np.int64)
+    c = np.cumsum(own)
+    blk_of = np.arange(n) // PMAX + np.maximum(0, c - 1) // R
+    nb = int(blk_of[-1]) + 1
+    rowlist = np.flatnonzero(own)
+    bstart = np.full(nb, -1); bend = np.full(nb, -1)
+    for p in range(n):
+        b = blk_of[p]
+        if bstart[b] < 0:
+            bstart[b] = p
+        bend[b] = p + 1
+    pre = [None] * n; suf = [None] * n; blk = [(INF, -1)] * nb
+    for b in range(nb):
+        if bstart[b] < 0:
+            continue
+        lo, hi = bstart[b], bend[b]
+        assert hi - lo <= PMAX and own[lo:hi].sum() <= R
+        best = (INF, -1)
+        for p in range(lo, hi):
+            best = min(best, (key[p], p))
+            pre[p] = best
+        blk[b] = best
+        best = (INF, -1)
+        for p in range(hi - 1, lo - 1, -1):
+            suf[p] = best
+            best = min(best, (key[p], p))
+    out = np.full((row_end - row_begin, n), np.nan)
+    for I in range(nb):
+        if bstart[I] < 0:
+            continue
+        rows_q = [q for q in rowlist if blk_of[q] == I]
+        if not rows_q:
+            continue
+        mid = [(INF, -1)] * nb
+        best = (INF, -1)
+        for J in range(I + 1, nb):
+            mid[J] = best
+            best = min(best, blk[J])
+        best = (INF, -1)
+        for J in range(I - 1, -1, -1):
+            mid[J] = best
+            best = min(best, blk[J])
+        for q in rows_q:
+            i = leaf_at[q]
+            cand = {}
+            for side, (ck, ca) in ((0, pre[q]), (1, suf[q])):
+                if ck >= INF:
+                    cand[side] = (dep[i], dep[i] - dep[i])      # candidate = the leaf itself
+                else:
+                    cand[side] = (val[ca], dep[i] - val[ca])
+            for j in range(n):
+                p = pos[j]
+                J = blk_of[p]
+                if J == I:                                       # in-block: direct range minimum
+                    if p == q:
+                        d = 0.0
+                    else:
+                        a, b = min(p, q), max(p, q)
+                        r = a + 1 + int(np.argmin(key[a + 1:b + 1]))
+                        d = float((dep[i] - val[r]) + (dep[j] - val[r]))
+                else:
+                    right = J > I
+                    ck, ca = pre[p] if right else suf[p]
+                    if mid[J][0] < ck:
+                        ck, ca = mid[J]
+                    if ck >= INF:
+                        B, uj = dep[j], dep[j] - dep[j]
+                    else:
+                        B, uj = val[ca], dep[j] - val[ca]
+                    A, ui = cand[1 if right else 0]
+                    d = float(ui + uj + abs(A - B))
+                out[i - row_begin, j] = d
+    assert not np.isnan(out).any()
+    return out

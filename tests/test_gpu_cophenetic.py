@@ -110,21 +110,30 @@ def test_batch_parity(p2v, n_leaves, unrooted):
 
 @pytest.mark.parametrize("n_leaves", [70, 1000, 3000])
 def test_row_blocks(p2v, n_leaves):
+    """Row blocks (how one tree is sharded over GPUs).  Topological rows are bit-identical
+    to the full matrix; fp64 rows agree to the last bits only, because the DFS blocks -- and
+    with them the order in which the three path pieces are summed -- follow the requested
+    rows (DESIGN.md "fp64 parity")."""
     V = sample_vectors(3, n_leaves, seed=5)
     bls = sample_bls(3, n_leaves, seed=5)
     full_t = p2v.cophenetic_distances_batch(dev(V))
     full_b = p2v.cophenetic_distances_batch(dev(V), bls=dev(bls))
-    for r0, r1 in ((0, 1), (n_leaves // 3, n_leaves // 3 + 17), (n_leaves - 5, n_leaves), (7, 7)):
+    ref_b = O.cophenetic_batch(V[:1], bls[:1])
+    for r0, r1 in ((0, 1), (n_leaves // 3, n_leaves // 3 + 17), (n_leaves - 5, n_leaves), (7, 7),
+                   (0, n_leaves // 8), (n_leaves // 2, n_leaves)):
         part = p2v.cophenetic_distances_batch(dev(V), rows=(r0, r1))
         assert tuple(part.shape) == (3, r1 - r0, n_leaves)
         assert torch.equal(part, full_t[:, r0:r1])
         part = p2v.cophenetic_distances_batch(dev(V), rows=(r0, r1), bls=dev(bls))
-        assert torch.equal(part, full_b[:, r0:r1])
+        assert rel_err(part.cpu().numpy(), full_b[:, r0:r1].cpu().numpy()) <= 1e-15
+        assert rel_err(part[0].cpu().numpy(), ref_b[0, r0:r1]) <= RTOL
     # shards of a row partition reassemble the matrix (what the multi-GPU path does)
     G = 4
     cuts = [n_leaves * g // G for g in range(G + 1)]
+    parts = [p2v.cophenetic_distances_batch(dev(V), rows=(cuts[g], cuts[g + 1])) for g in range(G)]
+    assert torch.equal(torch.cat(parts, dim=1), full_t)
     parts = [p2v.cophenetic_distances_batch(dev(V), rows=(cuts[g], cuts[g + 1]), bls=dev(bls)) for g in range(G)]
-    assert torch.equal(torch.cat(parts, dim=1), full_b)
+    assert rel_err(torch.cat(parts, dim=1).cpu().numpy(), full_b.cpu().numpy()) <= 1e-15
 
 
 def test_invalid_tree_in_batch(p2v):

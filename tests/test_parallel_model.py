@@ -41,3 +41,19 @@ def test_distance_rows_model(n_leaves, unrooted, R):
         d = M.distance_rows_model(v, bls, unrooted, R=R)
         ref = O.cophenetic_distances(to_matrix_input(v, bls), unrooted)
         assert np.allclose(d, ref, rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("n_leaves", [3, 4, 5, 9, 17, 40, 70])
+@pytest.mark.parametrize("unrooted", [False, True])
+def test_distance_rows_model_v2(n_leaves, unrooted):
+    """Blocks sized by the requested rows + the three-term form used by rows_kernel."""
+    for s, v in enumerate(list(sample_vectors(2, n_leaves, seed=n_leaves)) + list(adversarial_vectors(n_leaves).values())):
+        ref_t = O.cophenetic_distances(v, unrooted)
+        bls = sample_bls(1, n_leaves, seed=s)[0]
+        ref_b = O.cophenetic_distances(to_matrix_input(v, bls), unrooted)
+        for (r0, r1) in ((0, n_leaves), (n_leaves // 3, n_leaves // 3 + max(1, n_leaves // 4)), (n_leaves - 1, n_leaves)):
+            for R, PMAX in ((4, 16), (2, 3), (64, 512)):
+                d = M.distance_rows_model_v2(v, None, unrooted, r0, r1, R=R, PMAX=PMAX)
+                assert np.array_equal(d, ref_t[r0:r1])
+                d = M.distance_rows_model_v2(v, bls, unrooted, r0, r1, R=R, PMAX=PMAX)
+                assert np.allclose(d, ref_b[r0:r1], rtol=1e-13, atol=0)
