@@ -43,18 +43,33 @@ namespace p2v {
 
 constexpr int TAB_THREADS = 1024;
 constexpr int BLK_THREADS = 1024;
-constexpr int ROW_THREADS = 256;
-constexpr int ROW_R = 64;                  // requested rows per CTA (tile)
-constexpr int ROW_PMAX = 512;              // DFS positions per block at most
-constexpr int ROW_LEVELS = 10;             // sparse-table levels for ROW_PMAX
+#ifndef P2V_ROW_R
+#define P2V_ROW_R 64
+#endif
+constexpr int ROW_R = P2V_ROW_R;           // requested rows per CTA (tile)
+constexpr int ROW_PMAX_LARGE = 1024;       // capacity: DFS positions per block at most (n > 512)
+constexpr int ROW_PMAX_SMALL = 64;         //                                            (n <= 512)
+constexpr int ilog2c(int x) { return x <= 1 ? 0 : 1 + ilog2c(x >> 1); }
 constexpr int ROW_CPT = 4;                 // columns per thread (two 16-byte stores per row)
-constexpr int ROW_CHUNK = ROW_THREADS * ROW_CPT;   // 1024 columns per CTA
+// Position cap of a block for a call that asks for m of the n rows: blocks are cut every ROW_R
+// requested rows, which span about ROW_R*n/m positions; the cap sits 25% above that so that it
+// rarely cuts a second time, within the capacity of the in-block sparse table.
+inline int coph_pmax(int64_t n, int64_t m) {
+    if (n <= 512) return ROW_PMAX_SMALL;
+    int64_t want = (5 * (int64_t)ROW_R * n) / (4 * (m > 0 ? m : 1));
+    want = (want + 31) & ~(int64_t)31;
+    if (want < ROW_R) want = ROW_R;
+    if (want > ROW_PMAX_LARGE) want = ROW_PMAX_LARGE;
+    return (int)want;
+}
+// threads per rows-CTA: 4 columns per thread, so small trees get small CTAs
+inline int coph_row_threads(int n) { return n <= 128 ? 32 : (n <= 256 ? 64 : (n <= 512 ? 128 : 256)); }
 constexpr int KEY_INF = 0x3FFFFFFF;
 
 struct CophLayout {
     // byte offsets inside one tree's table area
     size_t anc, jA, jDI, jDH, jDL, tn, tc, pos, leaf_at, sepk, sephi, seplo;     // prepare
-    size_t blk_of, rowlist, prek, prea, sufk, sufa, bstart, bend, rowoff, cend, blkk, blka, hdr;  // rows call
+    size_t blk_of, rowlist, prek, prea, sufk, sufa, bstart, bend, rowoff, cend, blkk, blka, tilelist, hdr;  // rows call
     size_t total;
     int n, N, A, nbmax;
 };
@@ -64,7 +79,7 @@ __host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15
 __host__ __device__ inline CophLayout coph_layout(int64_t k) {
     CophLayout L;
     L.n = (int)(k + 1); L.N = (int)(2 * k + 1); L.A = (int)(4 * k);
-    L.nbmax = L.n / ROW_PMAX + L.n / ROW_R + 3;
+    L.nbmax = 2 * (L.n / ROW_R) + 3;      // position cap >= ROW_R, row cap == ROW_R
     size_t o = 0;
     L.anc = o; o = al16(o + 4 * 3 * (size_t)k);
     L.jA = o; o = al16(o + 4 * 2 * (size_t)L.N);
@@ -90,6 +105,7 @@ __host__ __device__ inline CophLayout coph_layout(int64_t k) {
     L.cend = o; o = al16(o + 4 * (size_t)L.nbmax);
     L.blkk = o; o = al16(o + 4 * (size_t)L.nbmax);
     L.blka = o; o = al16(o + 4 * (size_t)L.nbmax);
+    L.tilelist = o; o = al16(o + 4 * (size_t)L.nbmax);
     L.hdr = o; o = al16(o + 64);
     L.total = al16(o + 64);
     return L;
@@ -259,31 +275,29 @@ tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* 
 }
 
 // ---- 3. blocks for the requested rows ----------------------------------------------------------
-// Block id of DFS position p:  p / ROW_PMAX + max(0, c(p) - 1) / ROW_R,  c(p) = number of requested
-// rows at positions <= p.  Hence every block holds <= ROW_R requested rows and <= ROW_PMAX positions
-// (ids that no position maps to stay empty).  hdr[0] = number of ids.
+// Block id of DFS position p:  p / pmax + max(0, c(p) - 1) / ROW_R  (pmax: coph_pmax),  c(p) = number of requested
+// rows at positions <= p.  Hence every block holds <= ROW_R requested rows and <= pmax positions
+// (ids that no position maps to stay empty).  hdr[0] = number of ids, hdr[1] = number of tiles
+// (blocks that hold requested rows), listed in tilelist.
 __device__ __forceinline__ unsigned long long pack_key(int key, int p) {
     return ((unsigned long long)(unsigned)key << 32) | (unsigned)p;
 }
 
 __global__ void __launch_bounds__(BLK_THREADS)
 blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int k, int64_t row_begin,
-              int64_t row_end, const int32_t* __restrict__ status) {
+              int64_t row_end, int pmax, const int32_t* __restrict__ status) {
     __shared__ int s_part[BLK_THREADS / 32];
+    __shared__ int s_total;
     const CophLayout L = coph_layout(k);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = BLK_THREADS / 32;
     const int n = L.n;
     for (int64_t tree = blockIdx.x; tree < B; tree += gridDim.x) {
         if (status && status[tree] != 0) continue;
         unsigned char* T = tab + (size_t)tree * tab_stride;
         const int* leaf_at = reinterpret_cast<const int*>(T + L.leaf_at);
-        const int* sepk = reinterpret_cast<const int*>(T + L.sepk);
         int* blk_of = reinterpret_cast<int*>(T + L.blk_of);
         int* rowlist = reinterpret_cast<int*>(T + L.rowlist);
-        int* prek = reinterpret_cast<int*>(T + L.prek);
-        int* prea = reinterpret_cast<int*>(T + L.prea);
-        int* sufk = reinterpret_cast<int*>(T + L.sufk);
-        int* sufa = reinterpret_cast<int*>(T + L.sufa);
         int* bstart = reinterpret_cast<int*>(T + L.bstart);
         int* bend = reinterpret_cast<int*>(T + L.bend);
         int* rowoff = reinterpret_cast<int*>(T + L.rowoff);
@@ -292,20 +306,20 @@ blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int
         int* blka = reinterpret_cast<int*>(T + L.blka);
         int* hdr = reinterpret_cast<int*>(T + L.hdr);
 
-        __syncthreads();   // s_part of the previous tree is no longer read
+        __syncthreads();   // shared scratch of the previous tree is no longer read
         for (int i = tid; i < L.nbmax; i += BLK_THREADS) {
             bstart[i] = -1; bend[i] = -1; rowoff[i] = 0; cend[i] = 0; blkk[i] = KEY_INF; blka[i] = -1;
         }
-        // counts of requested rows per contiguous chunk of positions, block-wide exclusive scan
-        const int CH = (n + BLK_THREADS - 1) / BLK_THREADS;
-        const int p0 = min(n, tid * CH), p1 = min(n, p0 + CH);
+        // every warp owns a contiguous range of positions and reads it with coalesced loads
+        const int per_warp = (((n + NW - 1) / NW) + 31) & ~31;
+        const int w0 = min(n, warp * per_warp), w1 = min(n, w0 + per_warp);
         int cnt = 0;
-        for (int p = p0; p < p1; ++p) {
-            const int lab = leaf_at[p];
-            cnt += (lab >= row_begin && lab < row_end);
+        for (int base = w0; base < w1; base += 32) {
+            const int p = base + lane;
+            const int lab = (p < w1) ? leaf_at[p] : -1;
+            cnt += __popc(__ballot_sync(FULL, lab >= row_begin && lab < row_end));
         }
-        const int incl = (int)warp_incl_scan((uint32_t)cnt, lane);
-        if (lane == 31) s_part[warp] = incl;
+        if (lane == 0) s_part[warp] = cnt;
         __syncthreads();
         if (warp == 0) {
             const int v = s_part[lane];
@@ -313,28 +327,85 @@ blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int
             s_part[lane] = sc - v;
         }
         __syncthreads();
-        int c = s_part[warp] + incl - cnt;           // requested rows at positions < p0
-        int prev_id = (p0 > 0) ? (p0 - 1) / ROW_PMAX + max(0, c - 1) / ROW_R : -1;
-        for (int p = p0; p < p1; ++p) {
-            const int lab = leaf_at[p];
-            const int own = (lab >= row_begin && lab < row_end);
-            c += own;
-            const int id = p / ROW_PMAX + max(0, c - 1) / ROW_R;
-            blk_of[p] = id;
-            if (own) rowlist[c - 1] = p;
-            if (id != prev_id) {
-                bstart[id] = p; rowoff[id] = c - own;
-                if (prev_id >= 0) { bend[prev_id] = p; cend[prev_id] = c - own; }
+        int c0 = s_part[warp];                       // requested rows at positions < w0
+        int prev_last = (w0 > 0) ? (w0 - 1) / pmax + max(0, c0 - 1) / ROW_R : -1;   // id of position w0-1
+        for (int base = w0; base < w1; base += 32) {
+            const int p = base + lane;
+            const bool in = p < w1;
+            const int lab = in ? leaf_at[p] : -1;
+            const bool own = lab >= row_begin && lab < row_end;
+            const unsigned bm = __ballot_sync(FULL, own);
+            const int c = c0 + __popc(bm & lanes_le(lane));          // requested rows at positions <= p
+            const int id = in ? p / pmax + max(0, c - 1) / ROW_R : -1;
+            int prev_id = __shfl_up_sync(FULL, id, 1);
+            if (lane == 0) prev_id = prev_last;
+            if (in) {
+                blk_of[p] = id;
+                if (own) rowlist[c - 1] = p;
+                if (id != prev_id) {
+                    bstart[id] = p; rowoff[id] = c - (own ? 1 : 0);
+                    if (prev_id >= 0) { bend[prev_id] = p; cend[prev_id] = c - (own ? 1 : 0); }
+                }
+                if (p == n - 1) { bend[id] = n; cend[id] = c; hdr[0] = id + 1; }
             }
-            prev_id = id;
-            if (p == n - 1) { bend[id] = n; cend[id] = c; hdr[0] = id + 1; }
+            c0 += __popc(bm);
+            const int last = __shfl_sync(FULL, id, 31);
+            if (last >= 0) prev_last = last;
         }
         __syncthreads();
-        // prefix / suffix minima of sep inside every block, one warp per block
-        const int nid = hdr[0];
-        for (int id = warp; id < nid; id += BLK_THREADS / 32) {
-            const int lo = bstart[id], hi = bend[id];
-            if (lo < 0) continue;
+        // compact the blocks that hold requested rows into tilelist
+        {
+            int* tilelist = reinterpret_cast<int*>(T + L.tilelist);
+            const int nid = hdr[0];
+            int base_count = 0;
+            for (int id0 = 0; id0 < nid; id0 += BLK_THREADS) {
+                const int id = id0 + tid;
+                const int has = (id < nid && bstart[id] >= 0 && cend[id] - rowoff[id] > 0) ? 1 : 0;
+                const int inc = (int)warp_incl_scan((uint32_t)has, lane);
+                __syncthreads();
+                if (lane == 31) s_part[warp] = inc;
+                __syncthreads();
+                if (warp == 0) {
+                    const int v = s_part[lane];
+                    const int sc = (int)warp_incl_scan((uint32_t)v, lane);
+                    s_part[lane] = sc - v;
+                    if (lane == 31) s_total = sc;
+                }
+                __syncthreads();
+                if (has) tilelist[base_count + s_part[warp] + inc - 1] = id;
+                base_count += s_total;
+            }
+            if (tid == 0) hdr[1] = base_count;
+        }
+    }
+}
+
+// prefix / suffix minima of sep inside every block: one warp per (tree, block), whole grid
+__global__ void __launch_bounds__(256)
+block_minima_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int k,
+                    const int32_t* __restrict__ status) {
+    const CophLayout L = coph_layout(k);
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = gwarp; w < B * L.nbmax; w += nwarps) {
+        const int64_t tree = w / L.nbmax;
+        const int id = (int)(w % L.nbmax);
+        if (status && status[tree] != 0) continue;
+        unsigned char* T = tab + (size_t)tree * tab_stride;
+        const int* hdr = reinterpret_cast<const int*>(T + L.hdr);
+        if (id >= hdr[0]) continue;
+        const int* sepk = reinterpret_cast<const int*>(T + L.sepk);
+        int* prek = reinterpret_cast<int*>(T + L.prek);
+        int* prea = reinterpret_cast<int*>(T + L.prea);
+        int* sufk = reinterpret_cast<int*>(T + L.sufk);
+        int* sufa = reinterpret_cast<int*>(T + L.sufa);
+        int* blkk = reinterpret_cast<int*>(T + L.blkk);
+        int* blka = reinterpret_cast<int*>(T + L.blka);
+        const int lo = reinterpret_cast<const int*>(T + L.bstart)[id];
+        const int hi = reinterpret_cast<const int*>(T + L.bend)[id];
+        if (lo < 0) continue;
+        {
             unsigned long long carry = pack_key(KEY_INF, 0);
             for (int base = lo; base < hi; base += 32) {       // pre[p] = min sep[lo..p]
                 const int p = base + lane;
@@ -389,7 +460,9 @@ __device__ __forceinline__ double dd_diff_round(dd a, dd b) {
     return __dadd_rn(__dadd_rn(a.hi, -b.hi), __dadd_rn(a.lo, -b.lo));
 }
 
+template <int PMAXT>
 struct RowShared {
+    static constexpr int LEVELS = ilog2c(PMAXT) + 1;
     int label[ROW_R];          // leaf label of the row
     int qpos[ROW_R];           // its DFS position
     int ai[2][ROW_R];          // topological depth of the row candidate  [0]: columns left  [1]: right
@@ -398,48 +471,56 @@ struct RowShared {
     double ahi[2][ROW_R], alo[2][ROW_R];   // double-double depth of the row candidate
     double uf[2][ROW_R];                   // d_i - d_rl, rounded once
     double dhi[ROW_R], dlo[ROW_R];
-    int kblk[ROW_PMAX];                    // separators of the block (patch)
-    unsigned short st[ROW_LEVELS][ROW_PMAX];   // sparse table of argmin offsets
-    int inlist[ROW_PMAX];                  // positions of in-block leaves whose column is in this chunk
+    int kblk[PMAXT];                       // separators of the block (patch)
+    unsigned short st[LEVELS][PMAXT];      // sparse table of argmin offsets
+    int inlist[PMAXT];                     // positions of in-block leaves whose column is in this chunk
+    unsigned long long wtotR[8], wtotL[8]; // per-warp totals of the block scan
     int incount;
 };
 
-template <bool TOPO, bool VEC2>
-__global__ void __launch_bounds__(ROW_THREADS, 3)
+__device__ __forceinline__ unsigned long long shfl_up64(unsigned long long x, int d) {
+    const unsigned lo = __shfl_up_sync(FULL, (unsigned)x, d), hi = __shfl_up_sync(FULL, (unsigned)(x >> 32), d);
+    return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ unsigned long long shfl_down64(unsigned long long x, int d) {
+    const unsigned lo = __shfl_down_sync(FULL, (unsigned)x, d), hi = __shfl_down_sync(FULL, (unsigned)(x >> 32), d);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+constexpr int rows_min_blocks(int threads) { return threads >= 256 ? 3 : (threads == 128 ? 6 : (threads == 64 ? 10 : 16)); }
+
+template <bool TOPO, bool VEC2, int THREADS, int PMAXT>
+__global__ void __launch_bounds__(THREADS, rows_min_blocks(THREADS))
 rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int k,
             int64_t row_begin, int64_t row_end, double* __restrict__ out,
-            const int32_t* __restrict__ status, int chunks_per_tree) {
+            const int32_t* __restrict__ status, int chunks_per_tree, int tiles_bound) {
     extern __shared__ __align__(16) unsigned char dyn[];
-    __shared__ RowShared S;
+    __shared__ RowShared<PMAXT> S;
+    constexpr int CHUNK = THREADS * ROW_CPT;
+    constexpr int NWARP = THREADS / 32;
     const CophLayout L = coph_layout(k);
     const int n = L.n, nbmax = L.nbmax;
     int* midk = reinterpret_cast<int*>(dyn);          // nbmax
     int* mida = midk + nbmax;                         // nbmax
-    unsigned long long* scanR = reinterpret_cast<unsigned long long*>(dyn + (((size_t)8 * nbmax + 15) & ~(size_t)15));
-    unsigned long long* scanL = scanR + ROW_THREADS;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t rows = row_end - row_begin;
 
-    const int64_t tiles_per_tree = (int64_t)nbmax * chunks_per_tree;
+    const int64_t tiles_per_tree = (int64_t)tiles_bound * chunks_per_tree;
     for (int64_t work = blockIdx.x; work < B * tiles_per_tree; work += gridDim.x) {
         const int64_t tree = work / tiles_per_tree;
         const int rem = (int)(work % tiles_per_tree);
-        const int I = rem / chunks_per_tree;
+        const int tix = rem / chunks_per_tree;
         const int chunk = rem % chunks_per_tree;
         if (status && status[tree] != 0) continue;
         const unsigned char* T = tab + (size_t)tree * tab_stride;
         const int* hdr = reinterpret_cast<const int*>(T + L.hdr);
+        if (tix >= hdr[1]) continue;                  // uniform per CTA
         const int nb = hdr[0];
-        if (I >= nb) continue;
-        const int* bstart = reinterpret_cast<const int*>(T + L.bstart);
-        const int lo = bstart[I];
-        if (lo < 0) continue;
-        const int* rowoff = reinterpret_cast<const int*>(T + L.rowoff);
-        const int* cend = reinterpret_cast<const int*>(T + L.cend);
-        const int roff = rowoff[I];
-        const int nrow = cend[I] - roff;
-        if (nrow <= 0) continue;                      // all conditions above are uniform per CTA
+        const int I = reinterpret_cast<const int*>(T + L.tilelist)[tix];
+        const int lo = reinterpret_cast<const int*>(T + L.bstart)[I];
         const int hi = reinterpret_cast<const int*>(T + L.bend)[I];
+        const int roff = reinterpret_cast<const int*>(T + L.rowoff)[I];
+        const int nrow = reinterpret_cast<const int*>(T + L.cend)[I] - roff;
         const int* jDI = reinterpret_cast<const int*>(T + L.jDI);
         const double* jDH = reinterpret_cast<const double*>(T + L.jDH);
         const double* jDL = reinterpret_cast<const double*>(T + L.jDL);
@@ -456,18 +537,18 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
         const int* sufa = reinterpret_cast<const int*>(T + L.sufa);
         const int* blkk = reinterpret_cast<const int*>(T + L.blkk);
         const int* blka = reinterpret_cast<const int*>(T + L.blka);
-        const int cbase = chunk * ROW_CHUNK;
+        const int cbase = chunk * CHUNK;
         __syncthreads();   // previous iteration's readers of S / dyn are done
 
         // ---- row side of the tile -------------------------------------------------------
-        if (tid < nrow) {
-            const int q = rowlist[roff + tid];
+        for (int r = tid; r < nrow; r += THREADS) {
+            const int q = rowlist[roff + r];
             const int i = leaf_at[q];
-            S.label[tid] = i; S.qpos[tid] = q;
+            S.label[r] = i; S.qpos[r] = q;
             const int di = jDI[i];
-            S.di[tid] = di;
+            S.di[r] = di;
             const dd d = {jDH[i], jDL[i]};
-            if (!TOPO) { S.dhi[tid] = d.hi; S.dlo[tid] = d.lo; }
+            if (!TOPO) { S.dhi[r] = d.hi; S.dlo[r] = d.lo; }
 #pragma unroll
             for (int side = 0; side < 2; ++side) {
                 const int ck = side ? sufk[q] : prek[q];
@@ -475,25 +556,27 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
                 const bool none = ck >= KEY_INF;         // no separator on that side inside the block
                 if (TOPO) {
                     const int a = none ? di : ck;        // key == topological depth of the candidate
-                    S.ai[side][tid] = a; S.ui[side][tid] = di - a;
+                    S.ai[side][r] = a; S.ui[side][r] = di - a;
                 } else {
                     const dd a = none ? d : dd{sephi[ca], seplo[ca]};
-                    S.ahi[side][tid] = a.hi; S.alo[side][tid] = a.lo;
-                    S.uf[side][tid] = none ? 0.0 : dd_diff_round(d, a);
+                    S.ahi[side][r] = a.hi; S.alo[side][r] = a.lo;
+                    S.uf[side][r] = none ? 0.0 : dd_diff_round(d, a);
                 }
             }
         }
         if (tid == 0) S.incount = 0;
         // separators of the block for the in-block patch
-        for (int x = tid; x < hi - lo; x += ROW_THREADS) {
+        for (int x = tid; x < hi - lo; x += THREADS) {
             S.kblk[x] = sepk[lo + x];
             S.st[0][x] = (unsigned short)x;
         }
 
         // ---- minima over the whole blocks between the tile and every other block --------
         // midk[J] / mida[J] = min / arg position of sep over the blocks strictly between I and J.
+        // Every thread owns a contiguous segment of blocks; the segment minima go through a
+        // block-wide exclusive prefix-min (blocks right of I) and suffix-min (left of I).
         {
-            const int SEG = (nb + ROW_THREADS - 1) / ROW_THREADS;
+            const int SEG = (nb + THREADS - 1) / THREADS;
             const int s0 = min(nb, tid * SEG), s1 = min(nb, s0 + SEG);
             const unsigned long long INF64 = ((unsigned long long)KEY_INF << 32);
             unsigned long long pr = INF64, pl = INF64;      // this segment's minimum right / left of I
@@ -502,28 +585,35 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
                 if (J > I) pr = min(pr, e);
                 if (J < I) pl = min(pl, e);
             }
-            scanR[tid] = pr; scanL[tid] = pl;
-            __syncthreads();
-            for (int d = 1; d < ROW_THREADS; d <<= 1) {     // inclusive prefix-min (R) / suffix-min (L)
-                unsigned long long a = scanR[tid], b = scanL[tid];
-                if (tid >= d) a = min(a, scanR[tid - d]);
-                if (tid + d < ROW_THREADS) b = min(b, scanL[tid + d]);
-                __syncthreads();
-                scanR[tid] = a; scanL[tid] = b;
-                __syncthreads();
+            unsigned long long ir = pr, il = pl;            // inclusive scans inside the warp
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long y = shfl_up64(ir, d), z = shfl_down64(il, d);
+                if (lane >= d) ir = min(ir, y);
+                if (lane + d < 32) il = min(il, z);
             }
-            unsigned long long run = (tid > 0) ? scanR[tid - 1] : INF64;      // blocks right of I, left of my segment
-            for (int J = s0; J < s1; ++J) {
-                if (J > I) {
-                    midk[J] = (int)(run >> 32); mida[J] = (int)(run & 0xFFFFFFFFu);
-                    run = min(run, ((unsigned long long)(unsigned)blkk[J] << 32) | (unsigned)blka[J]);
+            unsigned long long runR = shfl_up64(ir, 1), runL = shfl_down64(il, 1);
+            if (lane == 0) runR = INF64;
+            if (lane == 31) runL = INF64;
+            if (NWARP > 1) {
+                if (lane == 31) S.wtotR[warp] = ir;
+                if (lane == 0) S.wtotL[warp] = il;
+                __syncthreads();
+                for (int w = 0; w < NWARP; ++w) {
+                    if (w < warp) runR = min(runR, S.wtotR[w]);
+                    if (w > warp) runL = min(runL, S.wtotL[w]);
                 }
             }
-            run = (tid + 1 < ROW_THREADS) ? scanL[tid + 1] : INF64;            // blocks left of I, right of my segment
-            for (int J = s1 - 1; J >= s0; --J) {
+            for (int J = s0; J < s1; ++J) {                  // blocks right of I, walking right
+                if (J > I) {
+                    midk[J] = (int)(runR >> 32); mida[J] = (int)(runR & 0xFFFFFFFFu);
+                    runR = min(runR, ((unsigned long long)(unsigned)blkk[J] << 32) | (unsigned)blka[J]);
+                }
+            }
+            for (int J = s1 - 1; J >= s0; --J) {             // blocks left of I, walking left
                 if (J < I) {
-                    midk[J] = (int)(run >> 32); mida[J] = (int)(run & 0xFFFFFFFFu);
-                    run = min(run, ((unsigned long long)(unsigned)blkk[J] << 32) | (unsigned)blka[J]);
+                    midk[J] = (int)(runL >> 32); mida[J] = (int)(runL & 0xFFFFFFFFu);
+                    runL = min(runL, ((unsigned long long)(unsigned)blkk[J] << 32) | (unsigned)blka[J]);
                 }
                 if (J == I) { midk[J] = KEY_INF; mida[J] = 0; }
             }
@@ -536,7 +626,7 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
         double bhi[ROW_CPT], blo[ROW_CPT], ujf[ROW_CPT];
 #pragma unroll
         for (int c = 0; c < ROW_CPT; ++c) {
-            const int j = cbase + (c >> 1) * (ROW_THREADS * 2) + 2 * tid + (c & 1);
+            const int j = cbase + (c >> 1) * (THREADS * 2) + 2 * tid + (c & 1);
             col[c] = j;
             side[c] = 0; bi[c] = 0; uji[c] = 0; bhi[c] = blo[c] = ujf[c] = 0.0;
             if (j < n) {
@@ -606,14 +696,14 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
         for (int lev = 1; (1 << lev) <= bs; ++lev) {
             __syncthreads();
             const int half = 1 << (lev - 1);
-            for (int x = tid; x + (1 << lev) <= bs; x += ROW_THREADS) {
+            for (int x = tid; x + (1 << lev) <= bs; x += THREADS) {
                 const int a = S.st[lev - 1][x], b = S.st[lev - 1][x + half];
                 S.st[lev][x] = (unsigned short)(S.kblk[a] <= S.kblk[b] ? a : b);
             }
         }
         __syncthreads();   // also orders the streamed stores of this CTA before the patch stores
         const int nin = S.incount;
-        for (int w = tid; w < nin * nrow; w += ROW_THREADS) {
+        for (int w = tid; w < nin * nrow; w += THREADS) {
             const int r = w / nin, e = w - r * nin;
             const int q = S.qpos[r], p = S.inlist[e];
             const int i = S.label[r], j = leaf_at[p];
@@ -756,31 +846,49 @@ cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t
     }
     const CophLayout L = coph_layout(k);
     unsigned char* tab = wsb + W.tab;
+    const int pmax = coph_pmax(n, row_end - row_begin);
     {
         const int64_t cap = (int64_t)sm_count() * 2;
         const int grid = (int)(B < cap ? B : cap);
-        blocks_kernel<<<grid, BLK_THREADS, 0, stream>>>(tab, L.total, B, (int)k, row_begin, row_end, st);
+        blocks_kernel<<<grid, BLK_THREADS, 0, stream>>>(tab, L.total, B, (int)k, row_begin, row_end, pmax, st);
+        count_launch();
+        const int64_t warps = B * (int64_t)L.nbmax;
+        const int64_t want = (warps + 7) / 8, cap2 = (int64_t)sm_count() * 8;
+        block_minima_kernel<<<(int)(want < cap2 ? want : cap2), 256, 0, stream>>>(tab, L.total, B, (int)k, st);
         count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    const int chunks = (int)((n + ROW_CHUNK - 1) / ROW_CHUNK);
-    const int64_t work = B * (int64_t)L.nbmax * chunks;
-    const size_t smem = (((size_t)8 * L.nbmax + 15) & ~(size_t)15) + 2 * ROW_THREADS * sizeof(unsigned long long);
+    const int threads = coph_row_threads((int)n);
+    const int chunk_cols = threads * ROW_CPT;
+    const int chunks = (int)((n + chunk_cols - 1) / chunk_cols);
+    int64_t tiles_bound = (row_end - row_begin) / ROW_R + n / pmax + 2;
+    if (tiles_bound > L.nbmax) tiles_bound = L.nbmax;
+    const int64_t work = B * tiles_bound * chunks;
+    const size_t smem = (((size_t)8 * L.nbmax + 15) & ~(size_t)15);
     const bool topo = !weighted;
     const bool vec2 = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    const int64_t cap = (int64_t)sm_count() * 96;
+    const int64_t cap = (int64_t)sm_count() * 96 * (256 / threads);
     const int grid = (int)(work < cap ? work : cap);
-#define P2V_ROWS(T_, V_)                                                                              \
+#define P2V_ROWS4(T_, V_, TH_, PM_)                                                                   \
     do {                                                                                              \
-        auto kern = rows_kernel<T_, V_>;                                                              \
+        auto kern = rows_kernel<T_, V_, TH_, PM_>;                                                    \
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
         if (e != cudaSuccess) return e;                                                               \
-        kern<<<grid, ROW_THREADS, smem, stream>>>(tab, L.total, B, (int)k, row_begin, row_end, out, st, chunks); \
+        kern<<<grid, TH_, smem, stream>>>(tab, L.total, B, (int)k, row_begin, row_end, out, st, chunks, \
+                                          (int)tiles_bound);                                          \
     } while (0)
-    if (topo) { if (vec2) P2V_ROWS(true, true); else P2V_ROWS(true, false); }
-    else { if (vec2) P2V_ROWS(false, true); else P2V_ROWS(false, false); }
-#undef P2V_ROWS
+#define P2V_ROWS2(T_, V_)                                                                             \
+    do {                                                                                              \
+        if (threads == 256) P2V_ROWS4(T_, V_, 256, ROW_PMAX_LARGE);                                    \
+        else if (threads == 128) P2V_ROWS4(T_, V_, 128, ROW_PMAX_SMALL);                               \
+        else if (threads == 64) P2V_ROWS4(T_, V_, 64, ROW_PMAX_SMALL);                                 \
+        else P2V_ROWS4(T_, V_, 32, ROW_PMAX_SMALL);                                                    \
+    } while (0)
+    if (topo) { if (vec2) P2V_ROWS2(true, true); else P2V_ROWS2(true, false); }
+    else { if (vec2) P2V_ROWS2(false, true); else P2V_ROWS2(false, false); }
+#undef P2V_ROWS2
+#undef P2V_ROWS4
     count_launch();
     return cudaGetLastError();
 }
