@@ -460,9 +460,7 @@ __device__ __forceinline__ double dd_diff_round(dd a, dd b) {
     return __dadd_rn(__dadd_rn(a.hi, -b.hi), __dadd_rn(a.lo, -b.lo));
 }
 
-template <int PMAXT>
 struct RowShared {
-    static constexpr int LEVELS = ilog2c(PMAXT) + 1;
     int label[ROW_R];          // leaf label of the row
     int qpos[ROW_R];           // its DFS position
     int ai[2][ROW_R];          // topological depth of the row candidate  [0]: columns left  [1]: right
@@ -471,12 +469,15 @@ struct RowShared {
     double ahi[2][ROW_R], alo[2][ROW_R];   // double-double depth of the row candidate
     double uf[2][ROW_R];                   // d_i - d_rl, rounded once
     double dhi[ROW_R], dlo[ROW_R];
-    int kblk[PMAXT];                       // separators of the block (patch)
-    unsigned short st[LEVELS][PMAXT];      // sparse table of argmin offsets
-    int inlist[PMAXT];                     // positions of in-block leaves whose column is in this chunk
     unsigned long long wtotR[8], wtotL[8]; // per-warp totals of the block scan
     int incount;
 };
+// dynamic shared memory of rows_kernel: midk[nbmax], mida[nbmax], then (sized by the call's
+// position cap pmax) kblk[pmax], inlist[pmax], st[levels][pmax] (uint16)
+inline size_t rows_dyn_smem(int nbmax, int pmax) {
+    const int levels = ilog2c(pmax) + 1;
+    return (((size_t)8 * nbmax + 15) & ~(size_t)15) + (size_t)8 * pmax + (size_t)2 * levels * pmax + 16;
+}
 
 __device__ __forceinline__ unsigned long long shfl_up64(unsigned long long x, int d) {
     const unsigned lo = __shfl_up_sync(FULL, (unsigned)x, d), hi = __shfl_up_sync(FULL, (unsigned)(x >> 32), d);
@@ -489,19 +490,22 @@ __device__ __forceinline__ unsigned long long shfl_down64(unsigned long long x, 
 
 constexpr int rows_min_blocks(int threads) { return threads >= 256 ? 3 : (threads == 128 ? 6 : (threads == 64 ? 10 : 16)); }
 
-template <bool TOPO, bool VEC2, int THREADS, int PMAXT>
+template <bool TOPO, bool VEC2, int THREADS>
 __global__ void __launch_bounds__(THREADS, rows_min_blocks(THREADS))
 rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int k,
             int64_t row_begin, int64_t row_end, double* __restrict__ out,
-            const int32_t* __restrict__ status, int chunks_per_tree, int tiles_bound) {
+            const int32_t* __restrict__ status, int chunks_per_tree, int tiles_bound, int pmax) {
     extern __shared__ __align__(16) unsigned char dyn[];
-    __shared__ RowShared<PMAXT> S;
+    __shared__ RowShared S;
     constexpr int CHUNK = THREADS * ROW_CPT;
     constexpr int NWARP = THREADS / 32;
     const CophLayout L = coph_layout(k);
     const int n = L.n, nbmax = L.nbmax;
     int* midk = reinterpret_cast<int*>(dyn);          // nbmax
     int* mida = midk + nbmax;                         // nbmax
+    int* s_kblk = reinterpret_cast<int*>(dyn + (((size_t)8 * nbmax + 15) & ~(size_t)15));   // pmax: separators of the block
+    int* s_inlist = s_kblk + pmax;                    // pmax: in-block leaves whose column is in this chunk
+    unsigned short* s_st = reinterpret_cast<unsigned short*>(s_inlist + pmax);   // [levels][pmax] argmin offsets
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t rows = row_end - row_begin;
 
@@ -567,8 +571,8 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
         if (tid == 0) S.incount = 0;
         // separators of the block for the in-block patch
         for (int x = tid; x < hi - lo; x += THREADS) {
-            S.kblk[x] = sepk[lo + x];
-            S.st[0][x] = (unsigned short)x;
+            s_kblk[x] = sepk[lo + x];
+            s_st[x] = (unsigned short)x;
         }
 
         // ---- minima over the whole blocks between the tile and every other block --------
@@ -642,7 +646,7 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
                 const int dj = jDI[j];
                 if (J == I) {                      // patched after the streamed part
                     const int slot = atomicAdd(&S.incount, 1);
-                    S.inlist[slot] = p;
+                    s_inlist[slot] = p;
                 }
                 if (TOPO) {
                     bi[c] = none ? dj : ck;
@@ -697,24 +701,24 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
             __syncthreads();
             const int half = 1 << (lev - 1);
             for (int x = tid; x + (1 << lev) <= bs; x += THREADS) {
-                const int a = S.st[lev - 1][x], b = S.st[lev - 1][x + half];
-                S.st[lev][x] = (unsigned short)(S.kblk[a] <= S.kblk[b] ? a : b);
+                const int a = s_st[(lev - 1) * pmax + x], b = s_st[(lev - 1) * pmax + x + half];
+                s_st[lev * pmax + x] = (unsigned short)(s_kblk[a] <= s_kblk[b] ? a : b);
             }
         }
         __syncthreads();   // also orders the streamed stores of this CTA before the patch stores
         const int nin = S.incount;
         for (int w = tid; w < nin * nrow; w += THREADS) {
             const int r = w / nin, e = w - r * nin;
-            const int q = S.qpos[r], p = S.inlist[e];
+            const int q = S.qpos[r], p = s_inlist[e];
             const int i = S.label[r], j = leaf_at[p];
             double d = 0.0;
             if (p != q) {
                 const int a = min(p, q) + 1 - lo, b = max(p, q) - lo;     // sep offsets a..b
                 const int lev = 31 - __clz(b - a + 1);
-                const int x = S.st[lev][a], y = S.st[lev][b - (1 << lev) + 1];
-                const int arg = (S.kblk[x] <= S.kblk[y]) ? x : y;
+                const int x = s_st[lev * pmax + a], y = s_st[lev * pmax + b - (1 << lev) + 1];
+                const int arg = (s_kblk[x] <= s_kblk[y]) ? x : y;
                 if (TOPO) {
-                    d = int_to_f64(S.di[r] + jDI[j] - 2 * S.kblk[arg]);
+                    d = int_to_f64(S.di[r] + jDI[j] - 2 * s_kblk[arg]);
                 } else {
                     const dd l = {sephi[lo + arg], seplo[lo + arg]};
                     const dd m = dd{-l.hi, -l.lo};
@@ -865,25 +869,25 @@ cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t
     int64_t tiles_bound = (row_end - row_begin) / ROW_R + n / pmax + 2;
     if (tiles_bound > L.nbmax) tiles_bound = L.nbmax;
     const int64_t work = B * tiles_bound * chunks;
-    const size_t smem = (((size_t)8 * L.nbmax + 15) & ~(size_t)15);
+    const size_t smem = rows_dyn_smem(L.nbmax, pmax);
     const bool topo = !weighted;
     const bool vec2 = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     const int64_t cap = (int64_t)sm_count() * 96 * (256 / threads);
     const int grid = (int)(work < cap ? work : cap);
-#define P2V_ROWS4(T_, V_, TH_, PM_)                                                                   \
+#define P2V_ROWS4(T_, V_, TH_)                                                                        \
     do {                                                                                              \
-        auto kern = rows_kernel<T_, V_, TH_, PM_>;                                                    \
+        auto kern = rows_kernel<T_, V_, TH_>;                                                         \
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
         if (e != cudaSuccess) return e;                                                               \
         kern<<<grid, TH_, smem, stream>>>(tab, L.total, B, (int)k, row_begin, row_end, out, st, chunks, \
-                                          (int)tiles_bound);                                          \
+                                          (int)tiles_bound, pmax);                                    \
     } while (0)
 #define P2V_ROWS2(T_, V_)                                                                             \
     do {                                                                                              \
-        if (threads == 256) P2V_ROWS4(T_, V_, 256, ROW_PMAX_LARGE);                                    \
-        else if (threads == 128) P2V_ROWS4(T_, V_, 128, ROW_PMAX_SMALL);                               \
-        else if (threads == 64) P2V_ROWS4(T_, V_, 64, ROW_PMAX_SMALL);                                 \
-        else P2V_ROWS4(T_, V_, 32, ROW_PMAX_SMALL);                                                    \
+        if (threads == 256) P2V_ROWS4(T_, V_, 256);                                                    \
+        else if (threads == 128) P2V_ROWS4(T_, V_, 128);                                               \
+        else if (threads == 64) P2V_ROWS4(T_, V_, 64);                                                 \
+        else P2V_ROWS4(T_, V_, 32);                                                                    \
     } while (0)
     if (topo) { if (vec2) P2V_ROWS2(true, true); else P2V_ROWS2(true, false); }
     else { if (vec2) P2V_ROWS2(false, true); else P2V_ROWS2(false, false); }

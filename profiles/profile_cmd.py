@@ -3,6 +3,7 @@
 
     python profiles/profile_cmd.py decode    # to_ancestry, 131072 trees of n=1000, int64
     python profiles/profile_cmd.py rows      # cophenetic rows, n=65536, rows [0,8192), fp64 + topological
+    python profiles/profile_cmd.py rowsfull  # the same with all 65536 rows (34 GB)
     python profiles/profile_cmd.py encode    # from_ancestry, 131072 trees
 """
 import os
@@ -33,13 +34,14 @@ else:
     hi = (2 * torch.arange(k, device=dev) + 1).to(torch.float64)
     v = (torch.rand((1, k), generator=g, device=dev, dtype=torch.float64) * hi).to(torch.int64)
     bls = torch.rand((1, k, 2), generator=g, device=dev, dtype=torch.float64)
-    out = torch.empty((8192, n), dtype=torch.float64, device=dev)
+    nrows = n if what == "rowsfull" else 8192
+    out = torch.empty((nrows, n), dtype=torch.float64, device=dev)
     need = lib.p2v_cophenetic_workspace_bytes(1, k)
     ws = torch.empty(need, dtype=torch.uint8, device=dev)
     s = torch.cuda.current_stream().cuda_stream
     for weighted, blp in ((1, bls.data_ptr()), (0, 0)):
         lib.p2v_cophenetic_prepare_batch(v.data_ptr(), 8, blp, 1, k, 0, None, ws.data_ptr(), need, s)
         for _ in range(3):
-            lib.p2v_cophenetic_rows_batch(ws.data_ptr(), need, 1, k, weighted, 0, 8192, out.data_ptr(), s)
+            lib.p2v_cophenetic_rows_batch(ws.data_ptr(), need, 1, k, weighted, 0, nrows, out.data_ptr(), s)
 torch.cuda.synchronize()
 print("done", what, _capi.launch_count())
