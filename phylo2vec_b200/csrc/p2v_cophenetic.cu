@@ -36,12 +36,18 @@
 //        third is a double-double difference (DESIGN.md "fp64 parity").
 //        Columns whose leaf lies inside the row block are patched afterwards by the
 //        same CTA from a sparse table over the block's separators.
+#include <cooperative_groups.h>
+
 #include "p2v_common.cuh"
 #include "p2v_internal.h"
+
+namespace cg = cooperative_groups;
 
 namespace p2v {
 
 constexpr int TAB_THREADS = 1024;
+constexpr int TAB_CLUSTER = 16;            // CTAs per tree when there are few, large trees
+constexpr int TAB_FLAGS = 128;             // per-tree convergence flags (one per jumping round)
 constexpr int BLK_THREADS = 1024;
 #ifndef P2V_ROW_R
 #define P2V_ROW_R 64
@@ -69,7 +75,7 @@ constexpr int KEY_INF = 0x3FFFFFFF;
 struct CophLayout {
     // byte offsets inside one tree's table area
     size_t anc, jA, jDI, jDH, jDL, tn, tc, pos, leaf_at, sepk, sephi, seplo;     // prepare
-    size_t blk_of, rowlist, prek, prea, sufk, sufa, bstart, bend, rowoff, cend, blkk, blka, tilelist, hdr;  // rows call
+    size_t blk_of, rowlist, prek, prea, sufk, sufa, bstart, bend, rowoff, cend, blkk, blka, tilelist, hdr, flags;  // rows call (+ flags: prepare)
     size_t total;
     int n, N, A, nbmax;
 };
@@ -107,6 +113,7 @@ __host__ __device__ inline CophLayout coph_layout(int64_t k) {
     L.blka = o; o = al16(o + 4 * (size_t)L.nbmax);
     L.tilelist = o; o = al16(o + 4 * (size_t)L.nbmax);
     L.hdr = o; o = al16(o + 64);
+    L.flags = o; o = al16(o + 4 * (size_t)TAB_FLAGS);
     L.total = al16(o + 64);
     return L;
 }
@@ -152,15 +159,38 @@ __global__ void tiny_kernel(const double* __restrict__ sums, int64_t B, int k, i
 }
 
 // ---- 2. per-tree tables ------------------------------------------------------------------
+// A team of CSIZE CTAs works on one tree: CSIZE = 1 for batches (one CTA per tree), a thread-block
+// cluster of TAB_CLUSTER CTAs when there are only a few large trees (the jumping rounds are then
+// spread over 16 SMs and separated by cluster barriers).
+template <int CSIZE>
+__device__ __forceinline__ void team_sync() {
+    if (CSIZE == 1) __syncthreads();
+    else cg::this_cluster().sync();
+}
+
+// OR of `live` over the whole team; `flag` is a zero-initialised per-round word of the tree
+template <int CSIZE>
+__device__ __forceinline__ int team_any(int live, int* flag) {
+    const int any_cta = __syncthreads_or(live);
+    if (CSIZE == 1) return any_cta;
+    if (threadIdx.x == 0 && any_cta) atomicOr(flag, 1);
+    cg::this_cluster().sync();
+    return *reinterpret_cast<volatile int*>(flag);
+}
+
+template <int CSIZE>
 __global__ void __launch_bounds__(TAB_THREADS)
 tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* __restrict__ bl,
               int bl_stride, int64_t bl_tree_stride, int64_t B, int k, int unrooted,
               const int32_t* __restrict__ status) {
     const CophLayout L = coph_layout(k);
-    const int tid = threadIdx.x;
+    const int crank = (CSIZE == 1) ? 0 : (int)cg::this_cluster().block_rank();
+    const int tid = crank * TAB_THREADS + threadIdx.x;       // thread index inside the team
+    constexpr int TT = CSIZE * TAB_THREADS;                   // threads per team
     const int n = L.n, N = L.N, A = L.A, root = 2 * k;
-    for (int64_t tree = blockIdx.x; tree < B; tree += gridDim.x) {
-        if (status && status[tree] != 0) continue;   // uniform per CTA
+    const int64_t team = blockIdx.x / CSIZE, nteams = gridDim.x / CSIZE;
+    for (int64_t tree = team; tree < B; tree += nteams) {
+        if (status && status[tree] != 0) continue;   // uniform per team
         unsigned char* T = tab + (size_t)tree * tab_stride;
         const int* anc = reinterpret_cast<const int*>(T + L.anc);
         int* jA = reinterpret_cast<int*>(T + L.jA);
@@ -174,11 +204,13 @@ tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* 
         int* sepk = reinterpret_cast<int*>(T + L.sepk);
         double* sephi = reinterpret_cast<double*>(T + L.sephi);
         double* seplo = reinterpret_cast<double*>(T + L.seplo);
+        int* flags = reinterpret_cast<int*>(T + L.flags);
         const double* blt = bl ? bl + tree * bl_tree_stride : nullptr;
 
+        if (tid < TAB_FLAGS) flags[tid] = 0;
         // parents and edge weights (row r of bls: lengths above ancestry[r][0], [r][1];
         // graph.rs:57-58).  jA/jDI/jDH/jDL buffer 0 = initial state of the jumping.
-        for (int r = tid; r < k; r += TAB_THREADS) {
+        for (int r = tid; r < k; r += TT) {
             const int c1 = anc[3 * r], c2 = anc[3 * r + 1], p = k + 1 + r;
             double b1 = 1.0, b2 = 1.0;
             if (blt) { b1 = blt[(size_t)r * bl_stride]; b2 = blt[(size_t)r * bl_stride + 1]; }
@@ -193,9 +225,9 @@ tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* 
             jDL[c1] = 0.0; jDL[c2] = 0.0;
         }
         if (tid == 0) { jA[root] = -1; jDI[root] = 0; jDH[root] = 0.0; jDL[root] = 0.0; }
-        __syncthreads();
+        team_sync<CSIZE>();
         // Euler tour arcs: down(c) = 2c, up(c) = 2c+1 for every non-root node c.
-        for (int c = tid; c < 2 * k; c += TAB_THREADS) {
+        for (int c = tid; c < 2 * k; c += TT) {
             const int p = jA[c];
             int nd, wd;
             if (c <= k) { nd = 2 * c + 1; wd = 1; }                     // leaf: turn around
@@ -207,17 +239,19 @@ tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* 
             tn[2 * c] = nd; tc[2 * c] = wd;
             tn[2 * c + 1] = nu; tc[2 * c + 1] = 0;
         }
-        __syncthreads();
+        team_sync<CSIZE>();
         // root-path sums by pointer jumping; an even number of rounds leaves the result in buffer 0
+        int fround = 0;
         {
             int cur = 0;
-            for (int round = 0;; ++round) {
+            for (;; ++fround) {
                 const int* a_in = jA + cur * N; int* a_out = jA + (cur ^ 1) * N;
                 const int* i_in = jDI + cur * N; int* i_out = jDI + (cur ^ 1) * N;
                 const double* h_in = jDH + cur * N; double* h_out = jDH + (cur ^ 1) * N;
                 const double* l_in = jDL + cur * N; double* l_out = jDL + (cur ^ 1) * N;
                 int live = 0;
-                for (int u = tid; u < N; u += TAB_THREADS) {
+#pragma unroll 2
+                for (int u = tid; u < N; u += TT) {
                     const int a = a_in[u];
                     int di = i_in[u];
                     dd d = {h_in[u], l_in[u]};
@@ -231,18 +265,19 @@ tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* 
                     a_out[u] = na; i_out[u] = di; h_out[u] = d.hi; l_out[u] = d.lo;
                 }
                 cur ^= 1;
-                const int any = __syncthreads_or(live);
-                if (!any && cur == 0) break;
+                const int any = team_any<CSIZE>(live, flags + min(fround, TAB_FLAGS - 1));
+                if (!any && cur == 0) { ++fround; break; }
             }
         }
         // rank the tour: tc[a] becomes the number of leaf arcs from a to the end (inclusive)
         {
             int cur = 0;
-            for (int round = 0;; ++round) {
+            for (;; ++fround) {
                 const int* n_in = tn + cur * A; int* n_out = tn + (cur ^ 1) * A;
                 const int* c_in = tc + cur * A; int* c_out = tc + (cur ^ 1) * A;
                 int live = 0;
-                for (int a = tid; a < A; a += TAB_THREADS) {
+#pragma unroll 4
+                for (int a = tid; a < A; a += TT) {
                     const int nx = n_in[a];
                     int c = c_in[a];
                     int nn = -1;
@@ -254,23 +289,23 @@ tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* 
                     n_out[a] = nn; c_out[a] = c;
                 }
                 cur ^= 1;
-                const int any = __syncthreads_or(live);
+                const int any = team_any<CSIZE>(live, flags + min(fround, TAB_FLAGS - 1));
                 if (!any && cur == 0) break;
             }
         }
         // DFS positions of the leaves; separators by position
-        for (int c = tid; c <= k; c += TAB_THREADS) {
+        for (int c = tid; c <= k; c += TT) {
             const int p = n - tc[2 * c];
             pos[c] = p;
             leaf_at[p] = c;
         }
         if (tid == 0) { sepk[0] = KEY_INF; sephi[0] = 0.0; seplo[0] = 0.0; sepk[n] = KEY_INF; sephi[n] = 0.0; seplo[n] = 0.0; }
-        for (int u = k + 1 + tid; u <= 2 * k; u += TAB_THREADS) {
+        for (int u = k + 1 + tid; u <= 2 * k; u += TT) {
             const int c1 = anc[3 * (u - k - 1) + 1];      // child 1: its first leaf opens the right part
             const int r = n - tc[2 * c1];
             sepk[r] = jDI[u]; sephi[r] = jDH[u]; seplo[r] = jDL[u];
         }
-        __syncthreads();
+        team_sync<CSIZE>();
     }
 }
 
@@ -760,6 +795,37 @@ size_t cophenetic_workspace_bytes(int64_t B, int64_t k) {
     return coph_ws(B, k).total;
 }
 
+template <int CSIZE>
+static bool launch_tables_cluster(unsigned char* tab, size_t tab_stride, const double* bl, int bl_stride,
+                                  int64_t bl_tree_stride, int64_t B, int k, int unrooted, const int32_t* st,
+                                  cudaStream_t stream) {
+    auto kern = tables_kernel<CSIZE>;
+    if (CSIZE > 8 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * CSIZE));
+    cfg.blockDim = dim3(TAB_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CSIZE; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError();
+        return false;
+    }
+    if (cudaLaunchKernelEx(&cfg, kern, tab, tab_stride, bl, bl_stride, bl_tree_stride, B, k, unrooted, st) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return true;
+}
+
 // Phase 1+2: decode and build the per-tree tables inside the workspace.
 cudaError_t launch_cophenetic_prepare(const void* v_or_matrix, int idx_bytes, const double* bls, int64_t B,
                                       int64_t k, int unrooted, int32_t* status, void* ws, size_t ws_bytes,
@@ -816,9 +882,19 @@ cudaError_t launch_cophenetic_prepare(const void* v_or_matrix, int idx_bytes, co
                           stream, (int64_t)(L.total / sizeof(int)));
         if (e != cudaSuccess) return e;
         const int64_t cap = (int64_t)sm_count() * 2;
-        const int grid = (int)(B < cap ? B : cap);
-        tables_kernel<<<grid, TAB_THREADS, 0, stream>>>(tab, L.total, bl, bl_stride, bl_tree_stride, B,
-                                                       (int)k, unrooted, st);
+        bool launched = false;
+        if (B * 8 <= sm_count() && k >= 4096) {
+            // few large trees: a thread-block cluster per tree (16 CTAs, else the portable 8)
+            launched = launch_tables_cluster<TAB_CLUSTER>(tab, L.total, bl, bl_stride, bl_tree_stride, B, (int)k,
+                                                          unrooted, st, stream) ||
+                       launch_tables_cluster<8>(tab, L.total, bl, bl_stride, bl_tree_stride, B, (int)k, unrooted,
+                                                st, stream);
+        }
+        if (!launched) {
+            const int grid = (int)(B < cap ? B : cap);
+            tables_kernel<1><<<grid, TAB_THREADS, 0, stream>>>(tab, L.total, bl, bl_stride, bl_tree_stride, B,
+                                                              (int)k, unrooted, st);
+        }
         count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
