@@ -1,5 +1,6 @@
 // Shared device helpers for the phylo2vec B200 kernels (sm_100a).
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -64,6 +65,26 @@ __device__ __forceinline__ void count_smaller_step(uint32_t& cnt, uint32_t mine,
         "}\n"
         : "+r"(cnt)
         : "r"(mine), "r"(d));
+}
+
+// ---- teams: one CTA, or a thread-block cluster of CSIZE CTAs working on one tree ---------
+template <int CSIZE>
+__device__ __forceinline__ void team_sync() {
+    if (CSIZE == 1) __syncthreads();
+    else cooperative_groups::this_cluster().sync();
+}
+template <int CSIZE>
+__device__ __forceinline__ int team_rank() {
+    return (CSIZE == 1) ? 0 : (int)cooperative_groups::this_cluster().block_rank();
+}
+// OR of `live` over the whole team; `flag` is a zero-initialised word owned by the team
+template <int CSIZE>
+__device__ __forceinline__ int team_any(int live, int* flag) {
+    const int any_cta = __syncthreads_or(live);
+    if (CSIZE == 1) return any_cta;
+    if (threadIdx.x == 0 && any_cta) atomicOr(flag, 1);
+    cooperative_groups::this_cluster().sync();
+    return *reinterpret_cast<volatile int*>(flag);
 }
 
 // ---- double-double helpers (fp64 branch-length depths) --------------------

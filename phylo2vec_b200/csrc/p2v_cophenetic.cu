@@ -163,28 +163,12 @@ __global__ void tiny_kernel(const double* __restrict__ sums, int64_t B, int k, i
 // cluster of TAB_CLUSTER CTAs when there are only a few large trees (the jumping rounds are then
 // spread over 16 SMs and separated by cluster barriers).
 template <int CSIZE>
-__device__ __forceinline__ void team_sync() {
-    if (CSIZE == 1) __syncthreads();
-    else cg::this_cluster().sync();
-}
-
-// OR of `live` over the whole team; `flag` is a zero-initialised per-round word of the tree
-template <int CSIZE>
-__device__ __forceinline__ int team_any(int live, int* flag) {
-    const int any_cta = __syncthreads_or(live);
-    if (CSIZE == 1) return any_cta;
-    if (threadIdx.x == 0 && any_cta) atomicOr(flag, 1);
-    cg::this_cluster().sync();
-    return *reinterpret_cast<volatile int*>(flag);
-}
-
-template <int CSIZE>
 __global__ void __launch_bounds__(TAB_THREADS)
 tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* __restrict__ bl,
               int bl_stride, int64_t bl_tree_stride, int64_t B, int k, int unrooted,
               const int32_t* __restrict__ status) {
     const CophLayout L = coph_layout(k);
-    const int crank = (CSIZE == 1) ? 0 : (int)cg::this_cluster().block_rank();
+    const int crank = team_rank<CSIZE>();
     const int tid = crank * TAB_THREADS + threadIdx.x;       // thread index inside the team
     constexpr int TT = CSIZE * TAB_THREADS;                   // threads per team
     const int n = L.n, N = L.N, A = L.A, root = 2 * k;

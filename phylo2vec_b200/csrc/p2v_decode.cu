@@ -11,8 +11,8 @@
 //    later elements left free.  Batches of 32 consecutive times are resolved
 //    together: a 31-step SHFL.DOWN scan gives each lane its rank R among the
 //    elements of [0, batch end), then all 32 lanes rank-select against the same
-//    free-slot bit mask (one 32-bit word per lane + popc prefix for k <= 1024,
-//    a shared-memory Fenwick tree over word counts above that).
+//    free-slot bit mask (one 32-bit word per lane + popc prefix).  Trees with k > 1024
+//    sort the batches by rank and merge them pairwise instead (see decode_large_kernel).
 //  * Rank-0 insertions ("roots") carry their own label v[t]; every other element
 //    inherits the label of the nearest root on its left, so pair labels are a
 //    segmented broadcast over slots.
@@ -26,8 +26,6 @@
 namespace p2v {
 
 constexpr int SMALL_WARPS = 4;             // warps (= trees in flight) per CTA, small kernel
-constexpr int LARGE_THREADS = 256;
-constexpr int LARGE_WARPS = LARGE_THREADS / 32;
 constexpr uint32_t BIG = 0x7FFFFFFFu;
 
 template <typename IdxT> struct Vec2;
@@ -202,216 +200,217 @@ decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
 }
 
 // --------------------------------------------------------------------------
-// k > 1024: one CTA per tree.  Per-element arrays live in a global workspace
-// (L2 resident), the free-slot mask and its Fenwick tree in shared memory.
+// k > 1024: one team per tree -- a CTA for batches, a thread-block cluster of 16 (8) CTAs when
+// there are only a few large trees.  Per-element arrays live in a global workspace (L2 resident).
+//
+// Slot assignment without any serial pass: level 0 ranks every element inside its 32-element
+// batch (the same SHFL scan as the small kernel) and stores the batch sorted by rank; then blocks
+// are merged pairwise, log2(k/32) levels.  For a pair X (earlier times) | Y (later times), the
+// ranks of Y are already final for the merged block; an X element of rank r moves up by the
+// number of Y elements that land before it, #{l : y_l - l <= r}, and a Y element (index l, rank
+// y) ends up after #{x : r_x < y - l} X elements -- one binary search per element and level.
+// After the last level the array of elements sorted by rank IS the slot order.
+// Labels: segmented broadcast with a per-32 group scan.  Ancestry / edges: the forward relabel
+// sweep of the small kernel, run by one warp with the last-row-per-label table in shared memory.
 // --------------------------------------------------------------------------
-template <typename IdxT, int MODE>
-__global__ void __launch_bounds__(LARGE_THREADS)
+template <typename IdxT, int MODE, int CSIZE, int THREADS, bool SMEMTBL>
+__global__ void __launch_bounds__(THREADS)
 decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restrict__ out,
                     int64_t out_stride, int32_t* __restrict__ status, uint32_t* __restrict__ ws,
                     size_t ws_stride) {
-    extern __shared__ __align__(16) uint32_t sm32[];
-    __shared__ int s_bad;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nw = (k + 31) >> 5;
-    const int KA = ((k + 1 + 31) & ~31) + 32;
-    uint32_t* bits = sm32;            // nw words, 1 = free slot
-    uint32_t* fen = bits + nw;        // fen[1..nw]: Fenwick tree over popc(bits[w])
-    uint32_t* grp = fen + nw + 1;     // nw: per 32-slot group scan scratch
-    uint32_t* wv = ws + (size_t)blockIdx.x * ws_stride;
-    uint32_t* wR = wv + KA;
-    uint32_t* wtime = wR + KA;
-    uint32_t* wlast = wtime + KA;
-    uint32_t* wnext = wlast + KA;
-    uint32_t* wseg = wnext + KA;
-    int hb = 1;
-    while (hb * 2 <= nw) hb *= 2;
+    extern __shared__ __align__(16) uint16_t s_tbl[];        // k+2 entries when SMEMTBL
+    const int crank = team_rank<CSIZE>();
+    const int tid = crank * THREADS + threadIdx.x;            // thread index inside the team
+    constexpr int TT = CSIZE * THREADS;
+    constexpr int NWT = TT / 32;
+    const int lane = threadIdx.x & 31;
+    const int gw = tid >> 5;                                   // warp index inside the team
+    const int K = (k + 31) & ~31;
+    const int nbat = K >> 5;
+    const int64_t team = blockIdx.x / CSIZE, nteams = gridDim.x / CSIZE;
+    uint32_t* wv = ws + (size_t)team * ws_stride;
+    uint32_t* rk0 = wv + K;
+    uint32_t* rk1 = rk0 + K;
+    uint32_t* el0 = rk1 + K;
+    uint32_t* el1 = el0 + K;
+    uint32_t* wlab = el1 + K;
+    uint32_t* grp = wlab + K;                 // nbat + 32
+    uint32_t* gtbl = grp + nbat + 32;         // K + 32 (only without SMEMTBL)
+    int* flags = reinterpret_cast<int*>(gtbl + K + 32);   // 16
 
-    for (int64_t tree = blockIdx.x; tree < B; tree += gridDim.x) {
+    for (int64_t tree = team; tree < B; tree += nteams) {
         const IdxT* vt = v + tree * k;
-        if (tid == 0) s_bad = 0x7FFFFFFF;
-        __syncthreads();
-        // ---- A ---------------------------------------------------------------------
-        for (int i = tid; i < k; i += LARGE_THREADS) {
-            long long x = (long long)__ldg(vt + i);
-            if (x < 0 || x > 2LL * i) { atomicMin(&s_bad, i); x = 0; }
+        if (tid < 16) flags[tid] = 0;
+        // ---- A: load, validate, narrow ---------------------------------------------------
+        int badlocal = 0x7FFFFFFF;
+        for (int i = tid; i < K; i += TT) {
+            long long x = (i < k) ? (long long)__ldg(vt + i) : 0;
+            if (i < k && (x < 0 || x > 2LL * i)) { badlocal = min(badlocal, i); x = 0; }
             wv[i] = (uint32_t)x;
-            wlast[i] = NONE32;
         }
-        if (tid == 0) wlast[k] = NONE32;
-        for (int w = tid; w < nw; w += LARGE_THREADS)
-            bits[w] = (w * 32 + 32 <= k) ? 0xFFFFFFFFu : ((1u << (k - w * 32)) - 1u);
-        for (int i = tid + 1; i <= nw; i += LARGE_THREADS) {
-            const int lo = i - (i & -i);
-            fen[i] = (uint32_t)(min(32 * i, k) - min(32 * lo, k));
-        }
-        __syncthreads();
-        if (s_bad != 0x7FFFFFFF) {
-            if (tid == 0 && status) status[tree] = s_bad + 1;
-            __syncthreads();
+        team_sync<CSIZE>();
+        if (badlocal != 0x7FFFFFFF) atomicMax(&flags[1], K - badlocal);     // K - i >= 1
+        team_sync<CSIZE>();
+        const int badmark = *reinterpret_cast<volatile int*>(&flags[1]);
+        if (badmark) {
+            if (tid == 0 && status) status[tree] = (K - badmark) + 1;
+            team_sync<CSIZE>();
             continue;
         }
         if (tid == 0 && status) status[tree] = 0;
-        // ---- B1: in-batch ranks, all warps ---------------------------------------------
-        for (int b = warp; b < nw; b += LARGE_WARPS) {
+
+        // ---- level 0: rank inside each batch of 32, stored sorted by rank ----------------------
+        for (int b = gw; b < nbat; b += NWT) {
             const int t = b * 32 + lane;
             const bool act = t < k;
-            const uint32_t x = act ? wv[t] : 0u;
+            const uint32_t x = wv[t];
             const uint32_t ins = act ? (x <= (uint32_t)t ? 0u : x - (uint32_t)t) : BIG;
             uint32_t R = ins;
 #pragma unroll
-            for (int d = 1; d < 32; ++d) rank_step(R, ins, d);
-            if (act) wR[t] = R;
+            for (int d = 1; d < 32; ++d) {
+                const uint32_t y = __shfl_down_sync(FULL, ins, d);
+                R += (y <= R) ? 1u : 0u;
+            }
+            R -= (uint32_t)lane;
+            const uint32_t key = act ? R : BIG;
+            uint32_t p = 0;
+#pragma unroll
+            for (int d = 1; d < 32; ++d) {
+                const uint32_t y = __shfl_sync(FULL, key, (lane + d) & 31);
+                p += (y < key) ? 1u : 0u;
+            }
+            if (act) { rk0[b * 32 + p] = R; el0[b * 32 + p] = (uint32_t)t; }
         }
-        __syncthreads();
-        // ---- B2: warp 0 places the batches (serial over batches); warp 1 fills the
-        //          root-value tables concurrently -------------------------------------------
-        if (warp == 0) {
-            for (int b = nw - 1; b >= 0; --b) {
-                const int t = b * 32 + lane;
-                const bool act = t < k;
-                uint32_t rem = act ? wR[t] : 0u;
-                int pos = 0;
-                for (int step = hb; step; step >>= 1) {
-                    const int np = pos + step;
-                    if (np <= nw) {
-                        const uint32_t f = fen[np];
-                        if (f <= rem) { pos = np; rem -= f; }
+        team_sync<CSIZE>();
+
+        // ---- merge levels ----------------------------------------------------------------------
+        int cur = 0;
+        for (int S = 32; S < k; S <<= 1) {
+            const uint32_t* rin = cur ? rk1 : rk0;
+            const uint32_t* ein = cur ? el1 : el0;
+            uint32_t* rout = cur ? rk0 : rk1;
+            uint32_t* eout = cur ? el0 : el1;
+            for (int i = tid; i < k; i += TT) {
+                const int a = (i / (2 * S)) * (2 * S), m = a + S;
+                const uint32_t r = rin[i], e = ein[i];
+                if (m >= k) { rout[i] = r; eout[i] = e; continue; }      // lone block: copy through
+                const int end = min(k, a + 2 * S);
+                if (i < m) {                       // X: how many Y elements land before me
+                    int lo = 0, hi = end - m;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (rin[m + mid] - (uint32_t)mid <= r) lo = mid + 1; else hi = mid;
                     }
+                    rout[i + lo] = r + (uint32_t)lo; eout[i + lo] = e;
+                } else {                           // Y: how many X elements stay before me
+                    const int l = i - m;
+                    const uint32_t z = r - (uint32_t)l;
+                    int lo = 0, hi = S;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (rin[a + mid] < z) lo = mid + 1; else hi = mid;
+                    }
+                    rout[a + l + lo] = r; eout[a + l + lo] = e;
                 }
-                uint32_t bit = 0;
-                if (act) {
-                    bit = nth_set_bit(bits[pos], rem);
-                    wtime[pos * 32 + bit] = (uint32_t)t;
-                }
-                __syncwarp();
-                if (act) {
-                    atomicAnd(&bits[pos], ~(1u << bit));
-                    for (int i = pos + 1; i <= nw; i += i & -i) atomicSub(&fen[i], 1u);
-                }
-                __syncwarp();
             }
-        } else if (warp == 1 && MODE != MODE_PAIRS) {
-            for (int b = nw - 1; b >= 0; --b) {
-                const int t = b * 32 + lane;
-                const bool act = t < k;
-                const uint32_t x = act ? wv[t] : 0u;
-                const bool root = act && x <= (uint32_t)t;
-                // distinct keys for non-roots: values are < 2^20, lanes tag bit 30
-                const uint32_t key = root ? x : (0x40000000u + lane);
-                const uint32_t peers = __match_any_sync(FULL, key);
-                const uint32_t higher = peers & lanes_gt(lane);
-                uint32_t nxt = NONE32;
-                if (root) nxt = higher ? (uint32_t)(b * 32 + __ffs(higher) - 1) : wlast[x];
-                __syncwarp();
-                if (root) {
-                    wnext[t] = nxt;
-                    if ((peers & lanes_lt(lane)) == 0) wlast[x] = (uint32_t)t;
+            cur ^= 1;
+            team_sync<CSIZE>();
+        }
+        const uint32_t* time_at = cur ? el1 : el0;            // element at slot s
+
+        // ---- labels: nearest root (rank-0 insertion) at or left of every slot ------------------
+        for (int g = gw; g < nbat; g += NWT) {
+            const int s = g * 32 + lane;
+            const bool act = s < k;
+            const uint32_t t = act ? time_at[s] : 0u;
+            const uint32_t x = act ? wv[t] : 1u;
+            const uint32_t rm = __ballot_sync(FULL, act && x <= t);
+            if (lane == 0) grp[g] = rm ? (uint32_t)(g * 32 + 31 - __clz(rm)) : 0u;
+        }
+        team_sync<CSIZE>();
+        if (gw == 0) {  // exclusive prefix max over groups (slot 0 is always a root)
+            uint32_t carry = 0;
+            for (int c = 0; c < nbat; c += 32) {
+                const int g = c + lane;
+                const uint32_t val = g < nbat ? grp[g] : 0u;
+                uint32_t m = val;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(FULL, m, d);
+                    if (lane >= d) m = max(m, y);
                 }
-                __syncwarp();
+                uint32_t ex = __shfl_up_sync(FULL, m, 1);
+                if (lane == 0) ex = 0;
+                ex = max(ex, carry);
+                carry = max(carry, __shfl_sync(FULL, m, 31));
+                if (g < nbat) grp[g] = ex;
             }
         }
-        __syncthreads();
+        team_sync<CSIZE>();
         IdxT* ot = out + tree * out_stride;
-        if (MODE == MODE_PAIRS) {
-            // last root slot at or left of every slot: per-group last root, prefix-max
-            for (int g = warp; g < nw; g += LARGE_WARPS) {
-                const int s = g * 32 + lane;
-                const bool act = s < k;
-                const uint32_t t = act ? wtime[s] : 0u;
-                const uint32_t x = act ? wv[t] : 1u;
-                const uint32_t rm = __ballot_sync(FULL, act && x <= t);
-                if (lane == 0) grp[g] = rm ? (uint32_t)(g * 32 + 31 - __clz(rm)) : 0u;
-            }
-            __syncthreads();
-            if (warp == 0) {  // exclusive prefix max over groups (slot 0 is always a root)
-                uint32_t carry = 0;
-                for (int c = 0; c < nw; c += 32) {
-                    const int g = c + lane;
-                    const uint32_t val = g < nw ? grp[g] : 0u;
-                    uint32_t m = val;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t y = __shfl_up_sync(FULL, m, d);
-                        if (lane >= d) m = max(m, y);
-                    }
-                    uint32_t ex = __shfl_up_sync(FULL, m, 1);
-                    if (lane == 0) ex = 0;
-                    ex = max(ex, carry);
-                    carry = max(carry, __shfl_sync(FULL, m, 31));
-                    if (g < nw) grp[g] = ex;
-                }
-            }
-            __syncthreads();
-            for (int g = warp; g < nw; g += LARGE_WARPS) {
-                const int s = g * 32 + lane;
-                const bool act = s < k;
-                const uint32_t t = act ? wtime[s] : 0u;
-                const uint32_t x = act ? wv[t] : 1u;
-                const uint32_t m = __ballot_sync(FULL, act && x <= t) & lanes_le(lane);
-                if (act) {
-                    const uint32_t rs = m ? (uint32_t)(g * 32 + 31 - __clz(m)) : grp[g];
-                    const uint32_t lab = wv[wtime[rs]];
-                    store_pair<IdxT>(ot + 2 * (size_t)s, (IdxT)lab, (IdxT)(t + 1));
-                }
-            }
-        } else {
-            // first root slot right of every slot: per-group first root, suffix-min
-            for (int g = warp; g < nw; g += LARGE_WARPS) {
-                const int s = g * 32 + lane;
-                const bool act = s < k;
-                const uint32_t t = act ? wtime[s] : 0u;
-                const uint32_t x = act ? wv[t] : 1u;
-                const uint32_t rm = __ballot_sync(FULL, act && x <= t);
-                if (lane == 0) grp[g] = rm ? (uint32_t)(g * 32 + __ffs(rm) - 1) : NONE32;
-            }
-            __syncthreads();
-            if (warp == 0) {  // exclusive suffix min over groups, "none" == k
-                uint32_t carry = (uint32_t)k;
-                for (int c = ((nw - 1) / 32) * 32; c >= 0; c -= 32) {
-                    const int g = c + lane;
-                    const uint32_t val = g < nw ? grp[g] : NONE32;
-                    uint32_t m = val;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t y = __shfl_down_sync(FULL, m, d);
-                        if (lane + d < 32) m = min(m, y);
-                    }
-                    uint32_t ex = __shfl_down_sync(FULL, m, 1);
-                    if (lane == 31) ex = NONE32;
-                    ex = min(ex, carry);
-                    carry = min(carry, __shfl_sync(FULL, m, 0));
-                    if (g < nw) grp[g] = ex;
-                }
-            }
-            __syncthreads();
-            for (int g = warp; g < nw; g += LARGE_WARPS) {
-                const int s = g * 32 + lane;
-                const bool act = s < k;
-                const uint32_t t = act ? wtime[s] : 0u;
-                const uint32_t x = act ? wv[t] : 1u;
-                const bool root = act && x <= t;
-                const uint32_t rm = __ballot_sync(FULL, root);
-                const uint32_t higher = rm & lanes_gt(lane);
-                if (root) wseg[t] = (uint32_t)k + (higher ? (uint32_t)(g * 32 + __ffs(higher) - 1) : grp[g]);
-            }
-            __syncthreads();
-            for (int s = tid; s < k; s += LARGE_THREADS) {
-                const uint32_t t = wtime[s];
-                const uint32_t x = wv[t];
-                const uint32_t j2 = wlast[t + 1];
-                const uint32_t c2p = (j2 != NONE32) ? wseg[j2] : t + 1;
-                uint32_t c1p;
-                if (x <= t) {
-                    const uint32_t j1 = wnext[t];
-                    c1p = (j1 != NONE32) ? wseg[j1] : x;
-                } else {
-                    c1p = (uint32_t)(k + s);
-                }
-                store_row<IdxT, MODE>(ot, s, (IdxT)c1p, (IdxT)c2p, (IdxT)(k + 1 + s));
+        for (int g = gw; g < nbat; g += NWT) {
+            const int s = g * 32 + lane;
+            const bool act = s < k;
+            const uint32_t t = act ? time_at[s] : 0u;
+            const uint32_t x = act ? wv[t] : 1u;
+            const bool root = act && x <= t;
+            const uint32_t m = __ballot_sync(FULL, root) & lanes_le(lane);
+            if (act) {
+                const uint32_t rs = m ? (uint32_t)(g * 32 + 31 - __clz(m)) : grp[g];
+                const uint32_t lab = root ? x : wv[time_at[rs]];
+                if (MODE == MODE_PAIRS) store_pair<IdxT>(ot + 2 * (size_t)s, (IdxT)lab, (IdxT)(t + 1));
+                else wlab[s] = lab | (root ? 0x80000000u : 0u);
             }
         }
-        __syncthreads();
+        if (MODE == MODE_PAIRS) { team_sync<CSIZE>(); continue; }
+
+        // ---- ancestry / edges: forward relabel sweep, one warp, table of the last row per label --
+        if (SMEMTBL) {
+            if (crank == 0)
+                for (int i = threadIdx.x; i <= k + 1; i += THREADS) s_tbl[i] = (uint16_t)NONE16;
+        } else {
+            for (int i = tid; i <= k + 1; i += TT) gtbl[i] = NONE32;
+        }
+        team_sync<CSIZE>();
+        if (gw == 0) {
+            uint32_t nlab = (lane < k) ? wlab[lane] : 0u;
+            uint32_t nt = (lane < k) ? time_at[lane] : 0u;
+            for (int b = 0; b < nbat; ++b) {
+                const int s = b * 32 + lane;
+                const bool act = s < k;
+                const uint32_t labr = nlab, t = nt;
+                if (b + 1 < nbat) {                       // prefetch the next batch
+                    const int s2 = s + 32;
+                    nlab = (s2 < k) ? wlab[s2] : 0u;
+                    nt = (s2 < k) ? time_at[s2] : 0u;
+                }
+                const uint32_t lab = labr & 0x7FFFFFFFu;
+                const bool root = act && (labr >> 31);
+                const uint32_t peers = __match_any_sync(FULL, act ? lab : (0x40000000u + lane));
+                uint32_t c1p = (uint32_t)(k + s);
+                if (root) {
+                    const uint32_t lower = peers & lanes_lt(lane);
+                    uint32_t cand;
+                    if (lower) cand = (uint32_t)(b * 32 + 31 - __clz(lower));
+                    else if (SMEMTBL) { const uint32_t q = s_tbl[lab]; cand = (q == NONE16) ? NONE32 : q; }
+                    else cand = gtbl[lab];
+                    c1p = (cand != NONE32) ? (uint32_t)(k + 1) + cand : lab;
+                }
+                __syncwarp();
+                if (act && (peers & lanes_gt(lane)) == 0) {
+                    if (SMEMTBL) s_tbl[lab] = (uint16_t)s; else gtbl[lab] = (uint32_t)s;
+                }
+                __syncwarp();
+                if (act) {
+                    uint32_t q;
+                    if (SMEMTBL) { const uint32_t q16 = s_tbl[t + 1]; q = (q16 == NONE16) ? NONE32 : q16; }
+                    else q = gtbl[t + 1];
+                    const uint32_t c2p = (q != NONE32) ? (uint32_t)(k + 1) + q : t + 1;
+                    store_row<IdxT, MODE>(ot, s, (IdxT)c1p, (IdxT)c2p, (IdxT)(k + 1 + s));
+                }
+            }
+        }
+        team_sync<CSIZE>();
     }
 }
 
@@ -440,18 +439,60 @@ __global__ void check_v_kernel(const IdxT* __restrict__ v, int64_t B, int k, int
 // --------------------------------------------------------------------------
 // launchers
 // --------------------------------------------------------------------------
-static size_t large_ws_stride(int64_t k) {  // uint32 elements per CTA
-    const size_t KA = (((size_t)k + 1 + 31) & ~(size_t)31) + 32;
-    return 6 * KA;
+constexpr int LARGE_THREADS_SINGLE = 512;
+constexpr int LARGE_THREADS_CLUSTER = 1024;
+
+static size_t large_ws_stride(int64_t k) {  // uint32 elements per team
+    const size_t K = ((size_t)k + 31) & ~(size_t)31;
+    return 7 * K + (K >> 5) + 128;
 }
-static int large_grid(int64_t B) {
+static int large_teams(int64_t B) {
     const int64_t cap = (int64_t)sm_count() * 4;
     return (int)(B < cap ? B : cap);
 }
 
 size_t decode_workspace_bytes(int64_t B, int64_t k) {
     if (k <= SMALL_K_MAX || B <= 0) return 0;
-    return (size_t)large_grid(B) * large_ws_stride(k) * sizeof(uint32_t);
+    return (size_t)large_teams(B) * large_ws_stride(k) * sizeof(uint32_t);
+}
+
+template <typename IdxT, int MODE, int CSIZE, int THREADS, bool SMEMTBL>
+static bool launch_large(const void* v, int64_t B, int64_t k, void* out, int64_t out_stride, int32_t* status,
+                         void* ws, size_t stride, int teams, size_t smem, cudaStream_t stream) {
+    auto kern = decode_large_kernel<IdxT, MODE, CSIZE, THREADS, SMEMTBL>;
+    if (smem > 0 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (CSIZE > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(teams * CSIZE));
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CSIZE; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = (CSIZE > 1) ? 1 : 0;
+    if (CSIZE > 1) {
+        int max_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < 1) {
+            cudaGetLastError();
+            return false;
+        }
+    }
+    const IdxT* vp = (const IdxT*)v;
+    IdxT* op = (IdxT*)out;
+    uint32_t* wp = (uint32_t*)ws;
+    const int kk = (int)k;
+    if (cudaLaunchKernelEx(&cfg, kern, vp, B, kk, op, out_stride, status, wp, stride) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return true;
 }
 
 template <typename IdxT, int MODE>
@@ -474,16 +515,22 @@ static cudaError_t launch_decode_t(const void* v, int64_t B, int64_t k, void* ou
         int grid = (int)(want < cap ? want : cap);
         kern<<<grid, SMALL_WARPS * 32, smem, stream>>>((const IdxT*)v, B, (int)k, (IdxT*)out, out_stride, status, K);
     } else {
+        if (k > LARGE_K_MAX) return cudaErrorNotSupported;
         const size_t stride = large_ws_stride(k);
-        const int grid = large_grid(B);
-        if (!ws || ws_bytes < (size_t)grid * stride * sizeof(uint32_t)) return cudaErrorInvalidValue;
-        const int nw = (int)((k + 31) >> 5);
-        const size_t smem = ((size_t)3 * nw + 8) * sizeof(uint32_t);
-        auto kern = decode_large_kernel<IdxT, MODE>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        kern<<<grid, LARGE_THREADS, smem, stream>>>((const IdxT*)v, B, (int)k, (IdxT*)out, out_stride,
-                                                   status, (uint32_t*)ws, stride);
+        const int teams = large_teams(B);
+        if (!ws || ws_bytes < (size_t)teams * stride * sizeof(uint32_t)) return cudaErrorInvalidValue;
+        // last-row-per-label table in shared memory as uint16 while slots fit (k <= 65535)
+        const bool smemtbl = (MODE != MODE_PAIRS) && (k <= 65535);
+        const size_t smem = smemtbl ? ((size_t)k + 2 + 7) / 8 * 8 * sizeof(uint16_t) : 0;
+        bool ok = false;
+        const bool few_large = (B * 8 <= sm_count()) && k >= 8192;
+#define P2V_LARGE(CS_, TH_)                                                                            \
+        (smemtbl ? launch_large<IdxT, MODE, CS_, TH_, (MODE != MODE_PAIRS)>(v, B, k, out, out_stride, status, ws, stride, teams, smem, stream) \
+                 : launch_large<IdxT, MODE, CS_, TH_, false>(v, B, k, out, out_stride, status, ws, stride, teams, smem, stream))
+        if (few_large) ok = P2V_LARGE(16, LARGE_THREADS_CLUSTER) || P2V_LARGE(8, LARGE_THREADS_CLUSTER);
+        if (!ok) ok = P2V_LARGE(1, LARGE_THREADS_SINGLE);
+#undef P2V_LARGE
+        if (!ok) return cudaErrorLaunchFailure;
     }
     count_launch();
     return cudaGetLastError();

@@ -383,3 +383,93 @@ def distance_rows_model_v2(v, bls, unrooted, row_begin, row_end, R=4, PMAX=16):
                 out[i - row_begin, j] = d
     assert not np.isnan(out).any()
     return out
+
+
+# --------------------------------------------------------------------------
+# Decode, large trees: merge-based slot assignment (decode_large_kernel) and the
+# forward relabel sweep used by both decode kernels.
+# --------------------------------------------------------------------------
+def slot_assignment_merge(v):
+    """Level 0: rank inside each batch of W, stored sorted by rank.  Then pairwise merges:
+    for X (earlier times) | Y (later times), Y's ranks are final for the merged block; an X
+    element of rank r gains #{l : y_l - l <= r}; a Y element (index l, rank y) is preceded
+    by #{x : r_x < y - l} X elements."""
+    v = np.asarray(v, dtype=np.int64)
+    k = len(v)
+    ins = np.where(v <= np.arange(k), 0, v - np.arange(k))
+    rk = np.zeros(k, dtype=np.int64)
+    el = np.zeros(k, dtype=np.int64)
+    for a in range(0, k, W):
+        e = min(k, a + W)
+        R = ins[a:e].copy()
+        for lane in range(e - a):
+            for d in range(1, e - a - lane):
+                if ins[a + lane + d] <= R[lane]:
+                    R[lane] += 1
+        order = np.argsort(R, kind="stable")
+        rk[a:e] = R[order]
+        el[a:e] = np.arange(a, e)[order]
+    S = W
+    while S < k:
+        nrk, nel = rk.copy(), el.copy()
+        for a in range(0, k, 2 * S):
+            m = a + S
+            if m >= k:
+                continue
+            e = min(k, a + 2 * S)
+            X, Y = rk[a:m], rk[m:e]
+            z = Y - np.arange(len(Y))
+            for ix in range(len(X)):
+                cnt = int(np.searchsorted(z, X[ix], side="right"))
+                nrk[a + ix + cnt] = X[ix] + cnt
+                nel[a + ix + cnt] = el[a + ix]
+            for l in range(len(Y)):
+                cntx = int(np.searchsorted(X, z[l], side="left"))
+                nrk[a + l + cntx] = Y[l]
+                nel[a + l + cntx] = el[m + l]
+        rk, el = nrk, nel
+        S *= 2
+    assert np.array_equal(rk, np.arange(k))
+    slot_of = np.empty(k, dtype=np.int64)
+    slot_of[el] = np.arange(k)
+    return slot_of
+
+
+def ancestry_forward_model(v):
+    """The reference's parents[] pass (convert.rs:174-185) as a forward sweep over slots, W
+    rows at a time, with one table: the last row so far whose label is x.  Non-root rows point
+    at the previous row; a root row looks its label up (same-batch occurrences first); the
+    absorbed leaf t+1 is looked up after the batch's updates (all rows labelled t+1 lie left)."""
+    v = np.asarray(v, dtype=np.int64)
+    k = len(v)
+    slot_of, _ = slot_assignment(v)
+    time_at = np.empty(k, dtype=np.int64)
+    time_at[slot_of] = np.arange(k)
+    tbl = np.full(k + 2, -1, dtype=np.int64)
+    anc = np.empty((k, 3), dtype=np.int64)
+    carry_label = 0
+    for a in range(0, k, W):
+        e = min(k, a + W)
+        t = time_at[a:e]
+        x = v[t]
+        root = x <= t
+        lab = np.empty(e - a, dtype=np.int64)
+        for l in range(e - a):
+            if root[l]:
+                carry_label = x[l]
+            lab[l] = carry_label
+        pre = tbl[lab].copy()
+        c1 = np.empty(e - a, dtype=np.int64)
+        for l in range(e - a):
+            if root[l]:
+                lower = [l2 for l2 in range(l) if lab[l2] == lab[l]]
+                cand = a + max(lower) if lower else pre[l]
+                c1[l] = k + 1 + cand if cand >= 0 else lab[l]
+            else:
+                c1[l] = k + a + l
+        for l in range(e - a):
+            tbl[lab[l]] = max(tbl[lab[l]], a + l)
+        for l in range(e - a):
+            q = tbl[t[l] + 1]
+            anc[a + l] = (c1[l], k + 1 + q if q >= 0 else t[l] + 1, k + 1 + a + l)
+    return anc

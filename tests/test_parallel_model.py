@@ -57,3 +57,11 @@ def test_distance_rows_model_v2(n_leaves, unrooted):
                 assert np.array_equal(d, ref_t[r0:r1])
                 d = M.distance_rows_model_v2(v, bls, unrooted, r0, r1, R=R, PMAX=PMAX)
                 assert np.allclose(d, ref_b[r0:r1], rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("n_leaves", [2, 3, 5, 33, 34, 64, 65, 100, 257, 1000, 1500])
+def test_merge_slot_assignment_and_forward_sweep(n_leaves):
+    for v in list(sample_vectors(3, n_leaves, seed=n_leaves)) + list(adversarial_vectors(n_leaves).values()):
+        ref, _ = M.slot_assignment(v)
+        assert np.array_equal(M.slot_assignment_merge(v), ref)
+        assert np.array_equal(M.ancestry_forward_model(v), O.to_ancestry(v))
