@@ -110,11 +110,22 @@ def synth_vectors_host(np, B, k, seed):
 
 
 # --------------------------------------------------------------------------- reference arm
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the baseline
+    passes its thread count to OpenMP explicitly)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_baseline(np, sample_trees, nthreads=0, repeats=1):
     """The reference's CPU algorithm (oracle port: AVL decode + relabel pass,
     phylo2vec/src/vector/avl.rs, convert.rs:167-188), one reference call per tree,
     OpenMP parallel-for over trees on the host cores."""
     from oracle import p2v_oracle as O
+    if nthreads <= 0:
+        nthreads = host_threads()
     V = synth_vectors_host(np, sample_trees, K, seed=1)
     out = np.empty((sample_trees, K, 3), dtype=np.int64)
     O.batch("to_ancestry", V[:256], K, nthreads=nthreads)      # warm up threads / pages
@@ -124,7 +135,7 @@ def cpu_baseline(np, sample_trees, nthreads=0, repeats=1):
         O.batch("to_ancestry", V, K, nthreads=nthreads, out=out)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    cores = O.num_threads() if nthreads <= 0 else nthreads
+    cores = nthreads
     return sample_trees / best, cores, best
 
 
@@ -228,6 +239,36 @@ def run_b200(args):
         ref, _ = O.batch("to_ancestry", V[idx].cpu().numpy(), K)
         parity = bool(np.array_equal(out[idx].cpu().numpy(), ref))
 
+    # ---- the other functions of BASELINE config C2, same batch (device resident, event timed) ----
+    c2 = {}
+    if rank == 0:
+        def timed(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        Bs = min(B, 250_000)
+        Vs = V[:Bs]
+        for name, cols in (("to_pairs", 2), ("to_edges", 4)):
+            o = torch.empty((Bs, K * cols), dtype=torch.int64, device=device)
+            fnc = getattr(lib, f"p2v_{name}_batch")
+            ms = timed(lambda: fnc(Vs.data_ptr(), 8, Bs, K, o.data_ptr(), status.data_ptr(), None, 0, stream.cuda_stream))
+            c2[name] = {"trees_per_s": Bs / (ms * 1e-3), "gbs": (1 + cols) * K * 8 * Bs / (ms * 1e-3) / 1e9}
+            del o
+        anc_s = out[:Bs]
+        vb = torch.empty((Bs, K), dtype=torch.int64, device=device)
+        ms = timed(lambda: lib.p2v_from_ancestry_batch(anc_s.data_ptr(), 8, Bs, K, vb.data_ptr(), status.data_ptr(), None, 0,
+                                                       stream.cuda_stream))
+        c2["from_ancestry"] = {"trees_per_s": Bs / (ms * 1e-3), "gbs": 4 * K * 8 * Bs / (ms * 1e-3) / 1e9,
+                               "round_trip_equal": bool(torch.equal(vb, Vs))}
+        c2["batch"] = Bs
+        del vb
+
     # ---- end to end: host buffers through the C ABI (H2D + kernels + D2H in the timed region)
     Be = args.e2e_batch if args.e2e_batch > 0 else (B if world == 1 else B // 4)
     hV = torch.empty((Be, K), dtype=torch.int64).pin_memory()
@@ -289,7 +330,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": Be * K * 24 + Be * 4, "batch_per_gpu": Be, "steps": e2e_steps,
                     "api": "p2v_to_ancestry_host (C ABI, pinned host buffers)", "matches_device_path": e2e_ok},
             "gpu_launches": launches, "clocks": clocks, "parity_spot_check": parity,
-            "cophenetic": coph,
+            "config_c2_other_functions": c2, "cophenetic": coph,
         }
         print(json.dumps(line))
     if world > 1:

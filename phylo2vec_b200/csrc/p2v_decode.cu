@@ -20,6 +20,8 @@
 //    closed forms over two tables filled in the same backward sweep
 //    (first root per label value, next root with the same value) and the end
 //    slot of every root's segment.
+#include <cuda_fp16.h>
+
 #include "p2v_common.cuh"
 #include "p2v_internal.h"
 
@@ -58,21 +60,29 @@ __device__ __forceinline__ void store_row(IdxT* tree_out, int s, IdxT c1p, IdxT 
 // --------------------------------------------------------------------------
 
 // Rank of element t = 32b+lane among the elements [0, 32b+32) at the end of its batch.
-// Lane i scans the later lanes i+1.. in time order; SHFL.DOWN past lane 31 hands back the
-// lane's own value, which always compares <= R, so the `lane` wrapped steps are taken off
-// at the end (they all come after the real ones).  The 31 shuffles do not depend on R and
-// are issued back to back; only the compare/add chain is serial.
-__device__ __forceinline__ uint32_t batch_rank(const uint16_t* __restrict__ sv, int b, int k, int lane) {
-    const int t = b * 32 + lane;
-    const uint32_t x = sv[t];
-    const uint32_t ins = (t < k) ? (x <= (uint32_t)t ? 0u : x - (uint32_t)t) : BIG;
-    uint32_t R = ins;
+// Lane i scans the later lanes i+1.. in time order: R = ins_i; R += (ins_j <= R).  SHFL.DOWN past
+// lane 31 hands back the lane's own value, which always compares <= R, so the `lane` wrapped
+// steps are taken off at the end (they all come after the real ones).
+// Two batches (b and b-1) are scanned at once in the two halves of a half2: all values are
+// integers <= 1024, exact in fp16, so one 32-bit shuffle, one HSET2.LE and one HADD2 advance
+// both scans.  The 31 shuffles do not depend on R and are issued back to back.
+__device__ __forceinline__ void batch_rank_pair(const uint16_t* __restrict__ sv, int b, int k, int lane,
+                                                uint32_t& R_hi, uint32_t& R_lo) {
+    const int t1 = b * 32 + lane, t0 = t1 - 32;            // batch b and batch b-1 (t0 < 0 if b == 0)
+    const uint32_t x1 = sv[t1];
+    const uint32_t x0 = (t0 >= 0) ? (uint32_t)sv[t0] : 0u;
+    const __half inf = __ushort_as_half((unsigned short)0x7C00);
+    const __half i1 = (t1 < k) ? __uint2half_rn(x1 <= (uint32_t)t1 ? 0u : x1 - (uint32_t)t1) : inf;
+    const __half i0 = (t0 >= 0) ? __uint2half_rn(x0 <= (uint32_t)t0 ? 0u : x0 - (uint32_t)t0) : inf;
+    const __half2 ins = __halves2half2(i0, i1);
+    __half2 R = ins;
 #pragma unroll
     for (int d = 1; d < 32; ++d) {
-        const uint32_t y = __shfl_down_sync(FULL, ins, d);
-        R += (y <= R) ? 1u : 0u;
+        const __half2 y = __shfl_down_sync(FULL, ins, d);
+        R = __hadd2(R, __hle2(y, R));
     }
-    return R - (uint32_t)lane;
+    R_lo = (uint32_t)__half2int_rz(__low2half(R)) - (uint32_t)lane;    // garbage for inactive lanes
+    R_hi = (uint32_t)__half2int_rz(__high2half(R)) - (uint32_t)lane;
 }
 
 template <typename IdxT, int MODE>
@@ -128,33 +138,40 @@ decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
         smask[lane] = word;
         __syncwarp();
 
-        // ---- B: slot assignment, walking time backwards; the rank scan of the next batch
-        //         is independent of the placement of the current one --------------------------
-        uint32_t Rnext = batch_rank(sv, nb - 1, k, lane);
-        for (int b = nb - 1; b >= 0; --b) {
-            const int t = b * 32 + lane;
-            const bool act = t < k;
-            const uint32_t R = Rnext;
-            if (b > 0) Rnext = batch_rank(sv, b - 1, k, lane);
-            // rank-select R among the free slots
-            const uint32_t cnt = __popc(word);
-            const uint32_t incl = warp_incl_scan(cnt, lane);
-            uint32_t w = 0;
+        // ---- B: slot assignment, walking time backwards, two batches per rank scan; the scan
+        //         of the next pair is independent of the placement of the current one ------------
+        uint32_t Rn_hi, Rn_lo;
+        batch_rank_pair(sv, nb - 1, k, lane, Rn_hi, Rn_lo);
+        for (int bp = nb - 1; bp >= 0; bp -= 2) {
+            const uint32_t Rpair[2] = {Rn_hi, Rn_lo};
+            if (bp >= 2) batch_rank_pair(sv, bp - 2, k, lane, Rn_hi, Rn_lo);
 #pragma unroll
-            for (int step = 16; step >= 1; step >>= 1) {
-                const uint32_t y = __shfl_sync(FULL, incl, (w + step - 1) & 31);
-                if (y <= R) w += step;
+            for (int h = 0; h < 2; ++h) {
+                const int b = bp - h;
+                if (b < 0) break;
+                const int t = b * 32 + lane;
+                const bool act = t < k;
+                const uint32_t R = Rpair[h];
+                // rank-select R among the free slots
+                const uint32_t cnt = __popc(word);
+                const uint32_t incl = warp_incl_scan(cnt, lane);
+                uint32_t w = 0;
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const uint32_t y = __shfl_sync(FULL, incl, (w + step - 1) & 31);
+                    if (y <= R) w += step;
+                }
+                w &= 31;
+                const uint32_t wd = __shfl_sync(FULL, word, w);
+                const uint32_t ex = __shfl_sync(FULL, incl - cnt, w);
+                const uint32_t pos = nth_set_bit(wd, R - ex);
+                if (act) {
+                    stime[w * 32 + pos] = (uint16_t)t;
+                    atomicAnd(&smask[w], ~(1u << pos));
+                }
+                __syncwarp();
+                word = smask[lane];
             }
-            w &= 31;
-            const uint32_t wd = __shfl_sync(FULL, word, w);
-            const uint32_t ex = __shfl_sync(FULL, incl - cnt, w);
-            const uint32_t pos = nth_set_bit(wd, R - ex);
-            if (act) {
-                stime[w * 32 + pos] = (uint16_t)t;
-                atomicAnd(&smask[w], ~(1u << pos));
-            }
-            __syncwarp();
-            word = smask[lane];
         }
 
         // ---- D: forward sweep over the slots, 32 rows at a time -------------------------------
