@@ -14,6 +14,8 @@
 //  * build_cherries (min-descendant relabel) keeps the reference's row-order
 //    semantics but runs as a wavefront: 32 rows at a time, a row fires as soon
 //    as the rows defining its internal children have fired.
+#include <cuda_fp16.h>
+
 #include "p2v_common.cuh"
 #include "p2v_internal.h"
 
@@ -58,6 +60,24 @@ __device__ __forceinline__ bool load_row(const IdxT* __restrict__ in, int s, int
 // --------------------------------------------------------------------------
 // k <= 1024: one warp per tree, shared memory.
 // --------------------------------------------------------------------------
+
+// For two batches of 32 values at once (halves of a half2; rows are integers < 1024, exact in
+// fp16): number of LOWER lanes of the same batch whose row is smaller.  SHFL.UP below lane 0
+// hands back the lane's own value, which never compares smaller.
+__device__ __forceinline__ void count_smaller_pair(uint32_t r_a, bool act_a, uint32_t r_b, bool act_b,
+                                                   uint32_t& cnt_a, uint32_t& cnt_b) {
+    const __half inf = __ushort_as_half((unsigned short)0x7C00);
+    const __half2 mine = __halves2half2(act_a ? __uint2half_rn(r_a) : inf, act_b ? __uint2half_rn(r_b) : inf);
+    __half2 cnt = __float2half2_rn(0.0f);
+#pragma unroll
+    for (int d = 1; d < 32; ++d) {
+        const __half2 y = __shfl_up_sync(FULL, mine, d);
+        cnt = __hadd2(cnt, __hlt2(y, mine));
+    }
+    cnt_a = (uint32_t)__half2int_rz(__low2half(cnt));
+    cnt_b = (uint32_t)__half2int_rz(__high2half(cnt));
+}
+
 template <typename IdxT, int MODE>
 __global__ void __launch_bounds__(ENC_SMALL_WARPS * 32)
 encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restrict__ vout,
@@ -66,65 +86,74 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int KA = K + 32;
-    const int KL = 2 * K + 64;  // label-indexed arrays (labels 0..2k+1)
     const bool has_par = (MODE != FROM_PAIRS);
-    const size_t per_warp = (size_t)3 * KA + (has_par ? 2 * (size_t)KL : 0) + 64;
+    const size_t per_warp = (size_t)(has_par ? 5 : 3) * KA + 64;
     uint16_t* base = reinterpret_cast<uint16_t*>(smem_raw) + warp * per_warp;
     uint16_t* sc1 = base;
     uint16_t* sc2 = sc1 + KA;
     uint16_t* spr = sc2 + KA;       // parent label by row; later row_of[value]
-    uint16_t* sdef = spr + KA;      // defining row of an internal label      [has_par]
-    uint16_t* smd = sdef + KL;      // min descendant of an internal label    [has_par]
+    uint16_t* sdef = spr + KA;      // defining row of internal label k+1+i      [has_par]
+    uint16_t* smd = sdef + KA;      // min descendant of internal label k+1+i    [has_par]
     uint32_t* smask = reinterpret_cast<uint32_t*>(base + per_warp - 64);
     const int nb = K >> 5;
     const int in_cols = (MODE == FROM_PAIRS) ? 2 : (MODE == FROM_ANCESTRY ? 3 : 4);
+    const uint32_t kint = (uint32_t)k + 1;      // first internal label
 
     for (int64_t tree = (int64_t)blockIdx.x * ENC_SMALL_WARPS + warp; tree < B;
          tree += (int64_t)gridDim.x * ENC_SMALL_WARPS) {
         const IdxT* it = in + tree * ((int64_t)k * in_cols);
         bool bad = false;
-        // ---- E1: load rows ----------------------------------------------------------
+        // ---- E1: load rows (4 batches of loads in flight) -------------------------------------
         if (has_par) {
-            for (int i = lane; i < KL; i += 32) { sdef[i] = (uint16_t)NONE16; smd[i] = (uint16_t)NONE16; }
+            for (int i = lane; i < KA; i += 32) { sdef[i] = (uint16_t)NONE16; smd[i] = (uint16_t)NONE16; }
         }
         smask[lane] = 0;
         __syncwarp();
+        long long offset = 0;
         if (MODE == FROM_EDGES) {
-            // order_cherries (convert.rs:449-477): row -> index parent - k - offset
+            // order_cherries (convert.rs:449-477): row -> index parent - k - offset,
+            // offset = max parent - 2k + 1
             uint32_t mx = 0;
-            for (int b = 0; b < nb; ++b) {
-                const int s = b * 32 + lane;
-                uint32_t c1 = 0, c2 = 0, p = 0;
-                if (s < k && !load_row<IdxT, MODE>(it, s, k, c1, c2, p)) bad = true;
-                mx = max(mx, p);
+            for (int b0 = 0; b0 < nb; b0 += 4) {
+                long long pv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int s = (b0 + j) * 32 + lane;
+                    pv[j] = (s < k) ? (long long)__ldg(it + 4 * (size_t)s + 1) : 0;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (pv[j] < 0 || pv[j] > 2LL * k + 1) bad = true;
+                    else mx = max(mx, (uint32_t)pv[j]);
+                }
             }
 #pragma unroll
             for (int d = 16; d; d >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, d));
-            bad = __any_sync(FULL, bad);
-            const long long offset = (long long)mx - 2LL * k + 1;
-            if (!bad) {
-                for (int b = 0; b < nb; ++b) {
-                    const int s = b * 32 + lane;
-                    if (s < k) {
-                        uint32_t c1, c2, p;
-                        load_row<IdxT, MODE>(it, s, k, c1, c2, p);
-                        const long long idx = (long long)p - k - offset;
-                        if (idx < 0 || idx >= k) bad = true;
-                        else {
-                            const uint32_t old = atomicOr(&smask[idx >> 5], 1u << (idx & 31));
-                            if (old & (1u << (idx & 31))) bad = true;  // two rows, one parent
-                            sc1[idx] = (uint16_t)c1; sc2[idx] = (uint16_t)c2; spr[idx] = (uint16_t)p;
-                        }
-                    }
-                }
+            offset = (long long)mx - 2LL * k + 1;
+        }
+        for (int b0 = 0; b0 < nb; b0 += 4) {
+            uint32_t c1[4], c2[4], pp[4];
+            bool okr[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int s = (b0 + j) * 32 + lane;
+                c1[j] = c2[j] = pp[j] = 0; okr[j] = true;
+                if (s < k) okr[j] = load_row<IdxT, MODE>(it, s, k, c1[j], c2[j], pp[j]);
             }
-        } else {
-            for (int b = 0; b < nb; ++b) {
-                const int s = b * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int s = (b0 + j) * 32 + lane;
                 if (s < k) {
-                    uint32_t c1 = 0, c2 = 0, p = 0;
-                    if (!load_row<IdxT, MODE>(it, s, k, c1, c2, p)) bad = true;
-                    sc1[s] = (uint16_t)c1; sc2[s] = (uint16_t)c2; spr[s] = (uint16_t)p;
+                    if (!okr[j]) { bad = true; continue; }
+                    int dst = s;
+                    if (MODE == FROM_EDGES) {
+                        const long long idx = (long long)pp[j] - k - offset;
+                        if (idx < 0 || idx >= k) { bad = true; continue; }
+                        const uint32_t old = atomicOr(&smask[idx >> 5], 1u << (idx & 31));
+                        if (old & (1u << (idx & 31))) bad = true;      // two rows, one parent
+                        dst = (int)idx;
+                    }
+                    sc1[dst] = (uint16_t)c1[j]; sc2[dst] = (uint16_t)c2[j]; spr[dst] = (uint16_t)pp[j];
                 }
             }
         }
@@ -135,17 +164,25 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
         if (has_par && !bad) {
             for (int b = 0; b < nb; ++b) {
                 const int s = b * 32 + lane;
-                if (s < k) sdef[spr[s]] = (uint16_t)s;
+                if (s < k) {
+                    const uint32_t p = spr[s];
+                    if (p < kint) bad = true;                 // a leaf label as parent: not a tree in this format
+                    else sdef[p - kint] = (uint16_t)s;
+                }
             }
+            bad = __any_sync(FULL, bad);
             __syncwarp();
+        }
+        if (has_par && !bad) {
             for (int b = 0; b < nb; ++b) {
                 const int base_row = b * 32;
                 const int s = base_row + lane;
                 const bool act = s < k;
-                uint32_t c1 = 0, c2 = 0, p = 0, d1 = NONE16, d2 = NONE16;
+                uint32_t c1 = 0, c2 = 0, p = kint, d1 = NONE16, d2 = NONE16;
                 if (act) {
                     c1 = sc1[s]; c2 = sc2[s]; p = spr[s];
-                    d1 = sdef[c1]; d2 = sdef[c2];
+                    if (c1 >= kint) d1 = sdef[c1 - kint];
+                    if (c2 >= kint) d2 = sdef[c2 - kint];
                     if (d1 != NONE16 && d1 >= (uint32_t)s) d1 = NONE16;  // defined later: a leaf, as in the reference
                     if (d2 != NONE16 && d2 >= (uint32_t)s) d2 = NONE16;
                 }
@@ -157,9 +194,9 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                         const bool w2 = d2 != NONE16 && d2 >= (uint32_t)base_row && !((done >> (d2 - base_row)) & 1u);
                         ready = !w1 && !w2;
                         if (ready) {
-                            const uint32_t m1 = (d1 != NONE16) ? (uint32_t)smd[c1] : c1;
-                            const uint32_t m2 = (d2 != NONE16) ? (uint32_t)smd[c2] : c2;
-                            smd[p] = (uint16_t)min(m1, m2);
+                            const uint32_t m1 = (d1 != NONE16) ? (uint32_t)smd[c1 - kint] : c1;
+                            const uint32_t m2 = (d2 != NONE16) ? (uint32_t)smd[c2 - kint] : c2;
+                            smd[p - kint] = (uint16_t)min(m1, m2);
                             sc1[s] = (uint16_t)m1; sc2[s] = (uint16_t)m2;
                         }
                     }
@@ -170,6 +207,7 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
             __syncwarp();
         }
         // ---- E3: row_of[c_max], c_max must be a permutation of 1..k ---------------------
+        __syncwarp();
         if (!bad) {
             for (int b = 0; b < nb; ++b) {
                 const int s = b * 32 + lane;
@@ -193,27 +231,34 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
         if (lane == 0 && status) status[tree] = TREE_OK;
         smask[lane] = 0;
         __syncwarp();
-        // ---- E4: build_vector, values ascending ------------------------------------------
+        // ---- E4: build_vector, values ascending, two batches per in-batch count ----------------
         IdxT* vo = vout + tree * k;
         uint32_t word = 0;  // rows already seen (rows of smaller values), word `lane`
-        for (int b = 0; b < nb; ++b) {
-            const int c = b * 32 + lane + 1;
-            const bool act = c <= k;
-            const uint32_t r = act ? (uint32_t)spr[c] : 0u;
-            const uint32_t cnt = __popc(word);
-            const uint32_t excl = warp_incl_scan(cnt, lane) - cnt;
-            const uint32_t wd = __shfl_sync(FULL, word, r >> 5);
-            uint32_t idx = __shfl_sync(FULL, excl, r >> 5) + __popc(wd & ((1u << (r & 31)) - 1u));
-            const uint32_t mine = act ? r : 0xFFFFFFFFu;
+        for (int bp = 0; bp < nb; bp += 2) {
+            const int ca = bp * 32 + lane + 1, cb = ca + 32;
+            const bool act_a = ca <= k, act_b = cb <= k;
+            const uint32_t ra = act_a ? (uint32_t)spr[ca] : 0u;
+            const uint32_t rb = act_b ? (uint32_t)spr[cb] : 0u;
+            uint32_t inb_a, inb_b;
+            count_smaller_pair(ra, act_a, rb, act_b, inb_a, inb_b);
 #pragma unroll
-            for (int d = 1; d < 32; ++d) count_smaller_step(idx, mine, d);
-            if (act) {
-                const uint32_t lo = min((uint32_t)sc1[r], (uint32_t)sc2[r]);
-                vo[c - 1] = (IdxT)(idx == 0 ? lo : (uint32_t)(c - 1) + idx);
-                atomicOr(&smask[r >> 5], 1u << (r & 31));
+            for (int h = 0; h < 2; ++h) {
+                const int c = h ? cb : ca;
+                const bool act = h ? act_b : act_a;
+                const uint32_t r = h ? rb : ra;
+                const uint32_t cnt = __popc(word);
+                const uint32_t excl = warp_incl_scan(cnt, lane) - cnt;
+                const uint32_t wd = __shfl_sync(FULL, word, r >> 5);
+                const uint32_t idx = __shfl_sync(FULL, excl, r >> 5) + __popc(wd & ((1u << (r & 31)) - 1u)) +
+                                     (h ? inb_b : inb_a);
+                if (act) {
+                    const uint32_t lo = min((uint32_t)sc1[r], (uint32_t)sc2[r]);
+                    vo[c - 1] = (IdxT)(idx == 0 ? lo : (uint32_t)(c - 1) + idx);
+                    atomicOr(&smask[r >> 5], 1u << (r & 31));
+                }
+                __syncwarp();
+                word = smask[lane];
             }
-            __syncwarp();
-            word = smask[lane];
         }
         __syncwarp();
     }
@@ -404,7 +449,7 @@ static cudaError_t launch_encode_t(const void* in, int64_t B, int64_t k, void* v
                                    void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (k <= SMALL_K_MAX) {
         const int K = (int)((k + 31) & ~31);
-        const size_t per_warp = (size_t)3 * (K + 32) + (MODE != FROM_PAIRS ? 2 * (size_t)(2 * K + 64) : 0) + 64;
+        const size_t per_warp = (size_t)(MODE != FROM_PAIRS ? 5 : 3) * (K + 32) + 64;
         const size_t smem = ENC_SMALL_WARPS * per_warp * sizeof(uint16_t);
         auto kern = encode_small_kernel<IdxT, MODE>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
