@@ -20,8 +20,8 @@
  *    bounds (the reference panics with "Validation failed: v[i] = .. is out of
  *    bounds", vector/base.rs:60-67); P2V_TREE_MALFORMED for encode input that is
  *    not a tree in the reference's format.  Output of a failed tree is unspecified.
- *  - *_host functions take HOST pointers, copy in, run and copy out on an
- *    internal stream and return after completion (what a single-tree drop-in of
+ *  - *_host functions take HOST pointers, copy in, run and copy out in chunks on
+ *    internal streams and return after completion (what a single-tree drop-in of
  *    the reference's functions calls).
  *  - Return value: P2V_OK or a negative error code; p2v_last_error() gives text.
  *    Nothing throws, nothing aborts.
@@ -131,6 +131,10 @@ int p2v_cophenetic_host(const void *v, int idx_bytes, const double *bls, int64_t
                         int unrooted, int64_t row_begin, int64_t row_end, double *out, int32_t *status);
 int p2v_cophenetic_matrix_host(const double *matrix, int64_t B, int64_t k, int unrooted,
                                int64_t row_begin, int64_t row_end, double *out, int32_t *status);
+
+/* The *_host entry points cache three streams and their device staging buffers per host
+ * thread (they grow on demand).  This frees the calling thread's cache. */
+void p2v_host_release(void);
 
 /* ---- measurement helper: a plain 128-bit streaming fill of `bytes` bytes, the
  * write-only ceiling the distance kernel is compared with in bench.py -------- */

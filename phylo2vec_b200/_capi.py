@@ -36,6 +36,7 @@ SIGNATURES = {
     "p2v_check_v_host": (_int, [_vp, _int, _i64, _i64, _vp]),
     "p2v_cophenetic_host": (_int, [_vp, _int, _vp, _i64, _i64, _int, _i64, _i64, _vp, _vp]),
     "p2v_cophenetic_matrix_host": (_int, [_vp, _i64, _i64, _int, _i64, _i64, _vp, _vp]),
+    "p2v_host_release": (None, []),
     "p2v_fill_f64": (_int, [_vp, _i64, ctypes.c_double, _vp]),
 }
 for _name in ("to_pairs", "to_ancestry", "to_edges", "from_pairs", "from_ancestry", "from_edges"):

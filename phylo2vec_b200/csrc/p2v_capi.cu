@@ -67,53 +67,89 @@ static int encode_entry(int mode, const void* in, int idx_bytes, int64_t B, int6
 }
 
 // ---- host-buffer plumbing --------------------------------------------------------------
-// Chunks the batch so that the device footprint stays bounded, and alternates two
-// streams so that (with pinned host memory) H2D, kernels and D2H of neighbouring chunks overlap.
-struct HostRun {
-    cudaStream_t st[2] = {nullptr, nullptr};
-    void* din[2] = {nullptr, nullptr};
-    void* dout[2] = {nullptr, nullptr};
-    void* dws[2] = {nullptr, nullptr};
-    int32_t* dstat[2] = {nullptr, nullptr};
-    cudaError_t err = cudaSuccess;
-    ~HostRun() {
-        for (int i = 0; i < 2; ++i) {
+// The batch is cut into chunks that rotate over three streams, so that (with pinned host memory)
+// the H2D copy, the kernels and the D2H copy of neighbouring chunks overlap.  Streams and device
+// staging buffers are cached per host thread and grow on demand; p2v_host_release() frees them.
+constexpr int HOST_STREAMS = 3;
+struct HostCtx {
+    int dev = -1;
+    cudaStream_t st[HOST_STREAMS] = {};
+    void* din[HOST_STREAMS] = {};
+    void* dout[HOST_STREAMS] = {};
+    void* dws[HOST_STREAMS] = {};
+    int32_t* dstat[HOST_STREAMS] = {};
+    size_t cap_in = 0, cap_out = 0, cap_ws = 0, cap_stat = 0;
+    void release() {
+        for (int i = 0; i < HOST_STREAMS; ++i) {
             if (st[i]) cudaStreamSynchronize(st[i]);
             if (din[i]) cudaFree(din[i]);
             if (dout[i]) cudaFree(dout[i]);
             if (dws[i]) cudaFree(dws[i]);
             if (dstat[i]) cudaFree(dstat[i]);
             if (st[i]) cudaStreamDestroy(st[i]);
+            st[i] = nullptr; din[i] = dout[i] = dws[i] = nullptr; dstat[i] = nullptr;
+        }
+        cap_in = cap_out = cap_ws = cap_stat = 0;
+        dev = -1;
+    }
+    ~HostCtx() { /* the CUDA context may already be gone at thread exit: leave it to the driver */ }
+};
+static thread_local HostCtx g_host;
+
+static cudaError_t host_ensure(HostCtx& H, size_t in_b, size_t out_b, size_t ws_b, size_t stat_b) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (H.dev != dev) { if (H.dev >= 0) H.release(); H.dev = dev; }
+    for (int i = 0; i < HOST_STREAMS; ++i) {
+        if (!H.st[i]) { e = cudaStreamCreateWithFlags(&H.st[i], cudaStreamNonBlocking); if (e != cudaSuccess) return e; }
+        if (in_b > H.cap_in || (in_b && !H.din[i])) {
+            if (H.din[i]) cudaFree(H.din[i]);
+            H.din[i] = nullptr;
+            e = cudaMalloc(&H.din[i], in_b); if (e != cudaSuccess) return e;
+        }
+        if (out_b > H.cap_out || (out_b && !H.dout[i])) {
+            if (H.dout[i]) cudaFree(H.dout[i]);
+            H.dout[i] = nullptr;
+            e = cudaMalloc(&H.dout[i], out_b); if (e != cudaSuccess) return e;
+        }
+        if (ws_b > H.cap_ws || (ws_b && !H.dws[i])) {
+            if (H.dws[i]) cudaFree(H.dws[i]);
+            H.dws[i] = nullptr;
+            e = cudaMalloc(&H.dws[i], ws_b); if (e != cudaSuccess) return e;
+        }
+        if (stat_b > H.cap_stat || !H.dstat[i]) {
+            if (H.dstat[i]) cudaFree(H.dstat[i]);
+            H.dstat[i] = nullptr;
+            e = cudaMalloc((void**)&H.dstat[i], stat_b); if (e != cudaSuccess) return e;
         }
     }
-};
+    if (in_b > H.cap_in) H.cap_in = in_b;
+    if (out_b > H.cap_out) H.cap_out = out_b;
+    if (ws_b > H.cap_ws) H.cap_ws = ws_b;
+    if (stat_b > H.cap_stat) H.cap_stat = stat_b;
+    return cudaSuccess;
+}
 
 template <typename Launch, typename WsBytes>
 static int host_chunked(const void* in, size_t in_tree_bytes, void* out, size_t out_tree_bytes,
                         int32_t* status, int64_t B, WsBytes ws_bytes_of, Launch launch) {
     if (B <= 0) return P2V_OK;
-    const size_t budget = (size_t)3 << 30;  // device bytes per chunk (in + out)
+    const size_t budget = (size_t)1 << 30;  // device bytes per chunk (in + out)
     size_t per = in_tree_bytes + out_tree_bytes;
     if (per == 0) per = 1;
     int64_t chunk = (int64_t)(budget / per);
     if (chunk < 1) chunk = 1;
     if (chunk > B) chunk = B;
-    const int nstreams = (chunk < B) ? 2 : 1;
-    HostRun H;
+    HostCtx& H = g_host;
     const size_t wsb = ws_bytes_of(chunk);
-    for (int i = 0; i < nstreams; ++i) {
-        cudaError_t e = cudaStreamCreateWithFlags(&H.st[i], cudaStreamNonBlocking);
-        if (e == cudaSuccess && in_tree_bytes) e = cudaMalloc(&H.din[i], in_tree_bytes * chunk);
-        if (e == cudaSuccess && out_tree_bytes) e = cudaMalloc(&H.dout[i], out_tree_bytes * chunk);
-        if (e == cudaSuccess && wsb) e = cudaMalloc(&H.dws[i], wsb);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&H.dstat[i], sizeof(int32_t) * chunk);
-        if (e != cudaSuccess) return from_cuda(e, "host entry: device allocation");
-    }
+    cudaError_t e = host_ensure(H, in_tree_bytes * chunk, out_tree_bytes * chunk, wsb, sizeof(int32_t) * chunk);
+    if (e != cudaSuccess) { H.release(); return from_cuda(e, "host entry: device allocation"); }
     int c = 0;
     for (int64_t b0 = 0; b0 < B; b0 += chunk, ++c) {
-        const int s = c % nstreams;
+        const int s = c % HOST_STREAMS;
         const int64_t nb = (B - b0 < chunk) ? (B - b0) : chunk;
-        cudaError_t e = cudaSuccess;
+        e = cudaSuccess;
         if (in_tree_bytes)
             e = cudaMemcpyAsync(H.din[s], (const char*)in + (size_t)b0 * in_tree_bytes, in_tree_bytes * nb,
                                 cudaMemcpyHostToDevice, H.st[s]);
@@ -123,10 +159,10 @@ static int host_chunked(const void* in, size_t in_tree_bytes, void* out, size_t 
                                 cudaMemcpyDeviceToHost, H.st[s]);
         if (e == cudaSuccess && status)
             e = cudaMemcpyAsync(status + b0, H.dstat[s], sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, H.st[s]);
-        if (e != cudaSuccess) return from_cuda(e, "host entry: chunk");
+        if (e != cudaSuccess) { for (int i = 0; i < HOST_STREAMS; ++i) cudaStreamSynchronize(H.st[i]); return from_cuda(e, "host entry: chunk"); }
     }
-    for (int i = 0; i < nstreams; ++i) {
-        cudaError_t e = cudaStreamSynchronize(H.st[i]);
+    for (int i = 0; i < HOST_STREAMS; ++i) {
+        e = cudaStreamSynchronize(H.st[i]);
         if (e != cudaSuccess) return from_cuda(e, "host entry: synchronize");
     }
     return P2V_OK;
@@ -190,16 +226,16 @@ static int coph_host(const void* in_a, int idx_bytes, const double* bls, int64_t
     // v and bls are separate host arrays: copy bls per chunk inside the launch lambda
     (void)in_tree;
     int64_t done = 0;  // trees consumed so far (chunks are issued in order)
-    double* dbl[2] = {nullptr, nullptr};
+    double* dbl[HOST_STREAMS] = {};
     int flip = 0;
     int64_t cap_chunk = 0;
-    auto cleanup = [&]() { for (int i = 0; i < 2; ++i) if (dbl[i]) cudaFree(dbl[i]); };
+    auto cleanup = [&]() { for (int i = 0; i < HOST_STREAMS; ++i) if (dbl[i]) cudaFree(dbl[i]); };
     int r = host_chunked(
         in_a, a_bytes, out, out_tree, status, B,
         [&](int64_t nb) { cap_chunk = nb; return cophenetic_workspace_bytes(nb, k); },
         [&](void* din, void* dout, int32_t* dst, int64_t nb, void* ws, size_t wsb, cudaStream_t st) {
             cudaError_t e = cudaSuccess;
-            const int s = flip; flip ^= 1;
+            const int s = flip; flip = (flip + 1) % HOST_STREAMS;
             if (!dbl[s]) e = cudaMalloc((void**)&dbl[s], b_bytes * (size_t)cap_chunk);
             if (e != cudaSuccess) return e;
             e = cudaMemcpyAsync(dbl[s], (const char*)bls + (size_t)done * b_bytes, b_bytes * nb,
@@ -339,6 +375,8 @@ int p2v_cophenetic_matrix_host(const double* m, int64_t B, int64_t k, int unroot
                                int64_t row_end, double* out, int32_t* status) {
     return coph_host(m, 0, nullptr, B, k, unrooted, row_begin, row_end, out, status);
 }
+
+void p2v_host_release(void) { g_host.release(); }
 
 int p2v_fill_f64(double* out, int64_t count, double value, p2v_stream_t stream) {
     if (count > 0 && !out) return fail(P2V_ERR_INVALID_ARG, "null buffer");
