@@ -513,7 +513,8 @@ template <bool TOPO, bool VEC2, int THREADS>
 __global__ void __launch_bounds__(THREADS, rows_min_blocks(THREADS))
 rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int k,
             int64_t row_begin, int64_t row_end, double* __restrict__ out,
-            const int32_t* __restrict__ status, int chunks_per_tree, int tiles_bound, int pmax) {
+            const int32_t* __restrict__ status, int chunks_per_tree, int chunks_per_cta, int tiles_bound,
+            int pmax) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ RowShared S;
     constexpr int CHUNK = THREADS * ROW_CPT;
@@ -528,12 +529,14 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t rows = row_end - row_begin;
 
-    const int64_t tiles_per_tree = (int64_t)tiles_bound * chunks_per_tree;
+    const int groups = (chunks_per_tree + chunks_per_cta - 1) / chunks_per_cta;   // chunk groups per tile
+    const int64_t tiles_per_tree = (int64_t)tiles_bound * groups;
     for (int64_t work = blockIdx.x; work < B * tiles_per_tree; work += gridDim.x) {
         const int64_t tree = work / tiles_per_tree;
         const int rem = (int)(work % tiles_per_tree);
-        const int tix = rem / chunks_per_tree;
-        const int chunk = rem % chunks_per_tree;
+        const int tix = rem / groups;
+        const int chunk_begin = (rem % groups) * chunks_per_cta;
+        const int chunk_end = min(chunks_per_tree, chunk_begin + chunks_per_cta);
         if (status && status[tree] != 0) continue;
         const unsigned char* T = tab + (size_t)tree * tab_stride;
         const int* hdr = reinterpret_cast<const int*>(T + L.hdr);
@@ -560,7 +563,6 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
         const int* sufa = reinterpret_cast<const int*>(T + L.sufa);
         const int* blkk = reinterpret_cast<const int*>(T + L.blkk);
         const int* blka = reinterpret_cast<const int*>(T + L.blka);
-        const int cbase = chunk * CHUNK;
         __syncthreads();   // previous iteration's readers of S / dyn are done
 
         // ---- row side of the tile -------------------------------------------------------
@@ -587,7 +589,6 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
                 }
             }
         }
-        if (tid == 0) S.incount = 0;
         // separators of the block for the in-block patch
         for (int x = tid; x < hi - lo; x += THREADS) {
             s_kblk[x] = sepk[lo + x];
@@ -643,6 +644,22 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
         }
         __syncthreads();
 
+        // sparse table of argmin offsets over the block's separators (for the in-block patch)
+        const int bs = hi - lo;
+        for (int lev = 1; (1 << lev) <= bs; ++lev) {
+            const int half = 1 << (lev - 1);
+            for (int x = tid; x + (1 << lev) <= bs; x += THREADS) {
+                const int a = s_st[(lev - 1) * pmax + x], b = s_st[(lev - 1) * pmax + x + half];
+                s_st[lev * pmax + x] = (unsigned short)(s_kblk[a] <= s_kblk[b] ? a : b);
+            }
+            __syncthreads();
+        }
+        double* obase = out + (size_t)tree * rows * n;
+
+        for (int chunk = chunk_begin; chunk < chunk_end; ++chunk) {
+        const int cbase = chunk * CHUNK;
+        if (tid == 0) S.incount = 0;
+        __syncthreads();
         // ---- column side: 4 columns per thread (two adjacent pairs) ----------------------
         int col[ROW_CPT], side[ROW_CPT];
         int bi[ROW_CPT], uji[ROW_CPT];
@@ -680,7 +697,6 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
         }
 
         // ---- streamed part: requested rows x 4 columns per thread -----------------------------
-        double* obase = out + (size_t)tree * rows * n;
 #pragma unroll 2
         for (int r = 0; r < nrow; ++r) {
             const int i = S.label[r];
@@ -714,16 +730,6 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
         }
 
         // ---- patch: columns whose leaf sits inside the block (incl. the zero diagonal) --------
-        // sparse table of argmin offsets over the block's separators
-        const int bs = hi - lo;
-        for (int lev = 1; (1 << lev) <= bs; ++lev) {
-            __syncthreads();
-            const int half = 1 << (lev - 1);
-            for (int x = tid; x + (1 << lev) <= bs; x += THREADS) {
-                const int a = s_st[(lev - 1) * pmax + x], b = s_st[(lev - 1) * pmax + x + half];
-                s_st[lev * pmax + x] = (unsigned short)(s_kblk[a] <= s_kblk[b] ? a : b);
-            }
-        }
         __syncthreads();   // also orders the streamed stores of this CTA before the patch stores
         const int nin = S.incount;
         for (int w = tid; w < nin * nrow; w += THREADS) {
@@ -748,6 +754,8 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
             }
             obase[(size_t)(i - row_begin) * n + j] = d;
         }
+        __syncthreads();   // the patch has read inlist / incount before the next chunk resets them
+        }  // chunk
     }
 }
 
@@ -928,7 +936,9 @@ cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t
     const int chunks = (int)((n + chunk_cols - 1) / chunk_cols);
     int64_t tiles_bound = (row_end - row_begin) / ROW_R + n / pmax + 2;
     if (tiles_bound > L.nbmax) tiles_bound = L.nbmax;
-    const int64_t work = B * tiles_bound * chunks;
+    // small matrices: one CTA walks all column chunks of its tile (row-side setup done once)
+    const int chunks_per_cta = (chunks <= 4) ? chunks : 1;
+    const int64_t work = B * tiles_bound * ((chunks + chunks_per_cta - 1) / chunks_per_cta);
     const size_t smem = rows_dyn_smem(L.nbmax, pmax);
     const bool topo = !weighted;
     const bool vec2 = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
@@ -940,7 +950,7 @@ cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
         if (e != cudaSuccess) return e;                                                               \
         kern<<<grid, TH_, smem, stream>>>(tab, L.total, B, (int)k, row_begin, row_end, out, st, chunks, \
-                                          (int)tiles_bound, pmax);                                    \
+                                          chunks_per_cta, (int)tiles_bound, pmax);                                    \
     } while (0)
 #define P2V_ROWS2(T_, V_)                                                                             \
     do {                                                                                              \

@@ -230,12 +230,15 @@ decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
 // Labels: segmented broadcast with a per-32 group scan.  Ancestry / edges: the forward relabel
 // sweep of the small kernel, run by one warp with the last-row-per-label table in shared memory.
 // --------------------------------------------------------------------------
-template <typename IdxT, int MODE, int CSIZE, int THREADS, bool SMEMTBL>
+// WT / SMEMARR: work arrays as uint16 in shared memory for mid-size trees (k <= MID_K_MAX),
+// as uint32 in the global workspace above that.
+template <typename IdxT, int MODE, int CSIZE, int THREADS, bool SMEMTBL, typename WT, bool SMEMARR>
 __global__ void __launch_bounds__(THREADS)
 decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restrict__ out,
                     int64_t out_stride, int32_t* __restrict__ status, uint32_t* __restrict__ ws,
                     size_t ws_stride) {
-    extern __shared__ __align__(16) uint16_t s_tbl[];        // k+2 entries when SMEMTBL
+    extern __shared__ __align__(16) uint16_t s_tbl[];        // k+2 entries (rounded to 8) when SMEMTBL
+    constexpr uint32_t ROOTBIT = 1u << (sizeof(WT) * 8 - 1);
     const int crank = team_rank<CSIZE>();
     const int tid = crank * THREADS + threadIdx.x;            // thread index inside the team
     constexpr int TT = CSIZE * THREADS;
@@ -245,15 +248,17 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
     const int K = (k + 31) & ~31;
     const int nbat = K >> 5;
     const int64_t team = blockIdx.x / CSIZE, nteams = gridDim.x / CSIZE;
-    uint32_t* wv = ws + (size_t)team * ws_stride;
-    uint32_t* rk0 = wv + K;
-    uint32_t* rk1 = rk0 + K;
-    uint32_t* el0 = rk1 + K;
-    uint32_t* el1 = el0 + K;
-    uint32_t* wlab = el1 + K;
-    uint32_t* grp = wlab + K;                 // nbat + 32
-    uint32_t* gtbl = grp + nbat + 32;         // K + 32 (only without SMEMTBL)
-    int* flags = reinterpret_cast<int*>(gtbl + K + 32);   // 16
+    const size_t tbl_entries = SMEMTBL ? (((size_t)k + 2 + 7) & ~(size_t)7) : 0;
+    WT* wv = SMEMARR ? reinterpret_cast<WT*>(s_tbl + tbl_entries)
+                     : reinterpret_cast<WT*>(ws + (size_t)team * ws_stride);
+    WT* rk0 = wv + K;
+    WT* rk1 = rk0 + K;
+    WT* el0 = rk1 + K;
+    WT* el1 = el0 + K;
+    WT* wlab = el1 + K;
+    WT* grp = wlab + K;                       // nbat + 32
+    WT* gtbl = grp + nbat + 32;               // K + 32 (only without SMEMTBL)
+    int* flags = reinterpret_cast<int*>(gtbl + (SMEMTBL ? 0 : K + 32) + ((nbat & 1) ? 1 : 0));   // 16, 4-byte aligned
 
     for (int64_t tree = team; tree < B; tree += nteams) {
         const IdxT* vt = v + tree * k;
@@ -263,7 +268,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
         for (int i = tid; i < K; i += TT) {
             long long x = (i < k) ? (long long)__ldg(vt + i) : 0;
             if (i < k && (x < 0 || x > 2LL * i)) { badlocal = min(badlocal, i); x = 0; }
-            wv[i] = (uint32_t)x;
+            wv[i] = (WT)x;
         }
         team_sync<CSIZE>();
         if (badlocal != 0x7FFFFFFF) atomicMax(&flags[1], K - badlocal);     // K - i >= 1
@@ -296,44 +301,44 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
                 const uint32_t y = __shfl_sync(FULL, key, (lane + d) & 31);
                 p += (y < key) ? 1u : 0u;
             }
-            if (act) { rk0[b * 32 + p] = R; el0[b * 32 + p] = (uint32_t)t; }
+            if (act) { rk0[b * 32 + p] = (WT)R; el0[b * 32 + p] = (WT)t; }
         }
         team_sync<CSIZE>();
 
         // ---- merge levels ----------------------------------------------------------------------
         int cur = 0;
         for (int S = 32; S < k; S <<= 1) {
-            const uint32_t* rin = cur ? rk1 : rk0;
-            const uint32_t* ein = cur ? el1 : el0;
-            uint32_t* rout = cur ? rk0 : rk1;
-            uint32_t* eout = cur ? el0 : el1;
+            const WT* rin = cur ? rk1 : rk0;
+            const WT* ein = cur ? el1 : el0;
+            WT* rout = cur ? rk0 : rk1;
+            WT* eout = cur ? el0 : el1;
             for (int i = tid; i < k; i += TT) {
                 const int a = (i / (2 * S)) * (2 * S), m = a + S;
                 const uint32_t r = rin[i], e = ein[i];
-                if (m >= k) { rout[i] = r; eout[i] = e; continue; }      // lone block: copy through
+                if (m >= k) { rout[i] = (WT)r; eout[i] = (WT)e; continue; }      // lone block: copy through
                 const int end = min(k, a + 2 * S);
                 if (i < m) {                       // X: how many Y elements land before me
                     int lo = 0, hi = end - m;
                     while (lo < hi) {
                         const int mid = (lo + hi) >> 1;
-                        if (rin[m + mid] - (uint32_t)mid <= r) lo = mid + 1; else hi = mid;
+                        if ((uint32_t)rin[m + mid] - (uint32_t)mid <= r) lo = mid + 1; else hi = mid;
                     }
-                    rout[i + lo] = r + (uint32_t)lo; eout[i + lo] = e;
+                    rout[i + lo] = (WT)(r + (uint32_t)lo); eout[i + lo] = (WT)e;
                 } else {                           // Y: how many X elements stay before me
                     const int l = i - m;
                     const uint32_t z = r - (uint32_t)l;
                     int lo = 0, hi = S;
                     while (lo < hi) {
                         const int mid = (lo + hi) >> 1;
-                        if (rin[a + mid] < z) lo = mid + 1; else hi = mid;
+                        if ((uint32_t)rin[a + mid] < z) lo = mid + 1; else hi = mid;
                     }
-                    rout[a + l + lo] = r; eout[a + l + lo] = e;
+                    rout[a + l + lo] = (WT)r; eout[a + l + lo] = (WT)e;
                 }
             }
             cur ^= 1;
             team_sync<CSIZE>();
         }
-        const uint32_t* time_at = cur ? el1 : el0;            // element at slot s
+        const WT* time_at = cur ? el1 : el0;                  // element at slot s
 
         // ---- labels: nearest root (rank-0 insertion) at or left of every slot ------------------
         for (int g = gw; g < nbat; g += NWT) {
@@ -342,7 +347,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
             const uint32_t t = act ? time_at[s] : 0u;
             const uint32_t x = act ? wv[t] : 1u;
             const uint32_t rm = __ballot_sync(FULL, act && x <= t);
-            if (lane == 0) grp[g] = rm ? (uint32_t)(g * 32 + 31 - __clz(rm)) : 0u;
+            if (lane == 0) grp[g] = (WT)(rm ? (uint32_t)(g * 32 + 31 - __clz(rm)) : 0u);
         }
         team_sync<CSIZE>();
         if (gw == 0) {  // exclusive prefix max over groups (slot 0 is always a root)
@@ -360,7 +365,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
                 if (lane == 0) ex = 0;
                 ex = max(ex, carry);
                 carry = max(carry, __shfl_sync(FULL, m, 31));
-                if (g < nbat) grp[g] = ex;
+                if (g < nbat) grp[g] = (WT)ex;
             }
         }
         team_sync<CSIZE>();
@@ -376,7 +381,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
                 const uint32_t rs = m ? (uint32_t)(g * 32 + 31 - __clz(m)) : grp[g];
                 const uint32_t lab = root ? x : wv[time_at[rs]];
                 if (MODE == MODE_PAIRS) store_pair<IdxT>(ot + 2 * (size_t)s, (IdxT)lab, (IdxT)(t + 1));
-                else wlab[s] = lab | (root ? 0x80000000u : 0u);
+                else wlab[s] = (WT)(lab | (root ? ROOTBIT : 0u));
             }
         }
         if (MODE == MODE_PAIRS) { team_sync<CSIZE>(); continue; }
@@ -386,7 +391,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
             if (crank == 0)
                 for (int i = threadIdx.x; i <= k + 1; i += THREADS) s_tbl[i] = (uint16_t)NONE16;
         } else {
-            for (int i = tid; i <= k + 1; i += TT) gtbl[i] = NONE32;
+            for (int i = tid; i <= k + 1; i += TT) gtbl[i] = (WT)NONE32;
         }
         team_sync<CSIZE>();
         if (gw == 0) {
@@ -401,8 +406,8 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
                     nlab = (s2 < k) ? wlab[s2] : 0u;
                     nt = (s2 < k) ? time_at[s2] : 0u;
                 }
-                const uint32_t lab = labr & 0x7FFFFFFFu;
-                const bool root = act && (labr >> 31);
+                const uint32_t lab = labr & (ROOTBIT - 1u);
+                const bool root = act && (labr & ROOTBIT);
                 const uint32_t peers = __match_any_sync(FULL, act ? lab : (0x40000000u + lane));
                 uint32_t c1p = (uint32_t)(k + s);
                 if (root) {
@@ -415,7 +420,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
                 }
                 __syncwarp();
                 if (act && (peers & lanes_gt(lane)) == 0) {
-                    if (SMEMTBL) s_tbl[lab] = (uint16_t)s; else gtbl[lab] = (uint32_t)s;
+                    if (SMEMTBL) s_tbl[lab] = (uint16_t)s; else gtbl[lab] = (WT)s;
                 }
                 __syncwarp();
                 if (act) {
@@ -458,6 +463,13 @@ __global__ void check_v_kernel(const IdxT* __restrict__ v, int64_t B, int k, int
 // --------------------------------------------------------------------------
 constexpr int LARGE_THREADS_SINGLE = 512;
 constexpr int LARGE_THREADS_CLUSTER = 1024;
+constexpr int MID_THREADS = 256;
+constexpr int MID_K_MAX = 12287;           // work arrays as uint16 in shared memory up to here
+static size_t mid_smem_bytes(int64_t k) {
+    const size_t K = ((size_t)k + 31) & ~(size_t)31;
+    const size_t tbl = ((size_t)k + 2 + 7) & ~(size_t)7;
+    return (tbl + 6 * K + (K >> 5) + 32 + 2) * sizeof(uint16_t) + 16 * sizeof(int) + 16;
+}
 
 static size_t large_ws_stride(int64_t k) {  // uint32 elements per team
     const size_t K = ((size_t)k + 31) & ~(size_t)31;
@@ -469,14 +481,14 @@ static int large_teams(int64_t B) {
 }
 
 size_t decode_workspace_bytes(int64_t B, int64_t k) {
-    if (k <= SMALL_K_MAX || B <= 0) return 0;
+    if (k <= MID_K_MAX || B <= 0) return 0;
     return (size_t)large_teams(B) * large_ws_stride(k) * sizeof(uint32_t);
 }
 
-template <typename IdxT, int MODE, int CSIZE, int THREADS, bool SMEMTBL>
+template <typename IdxT, int MODE, int CSIZE, int THREADS, bool SMEMTBL, typename WT = uint32_t, bool SMEMARR = false>
 static bool launch_large(const void* v, int64_t B, int64_t k, void* out, int64_t out_stride, int32_t* status,
                          void* ws, size_t stride, int teams, size_t smem, cudaStream_t stream) {
-    auto kern = decode_large_kernel<IdxT, MODE, CSIZE, THREADS, SMEMTBL>;
+    auto kern = decode_large_kernel<IdxT, MODE, CSIZE, THREADS, SMEMTBL, WT, SMEMARR>;
     if (smem > 0 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return false;
@@ -531,6 +543,14 @@ static cudaError_t launch_decode_t(const void* v, int64_t B, int64_t k, void* ou
         int64_t cap = (int64_t)sm_count() * per_sm;
         int grid = (int)(want < cap ? want : cap);
         kern<<<grid, SMALL_WARPS * 32, smem, stream>>>((const IdxT*)v, B, (int)k, (IdxT*)out, out_stride, status, K);
+    } else if (k <= MID_K_MAX) {
+        // mid-size trees: the same merge kernel with uint16 work arrays in shared memory
+        const size_t smem = mid_smem_bytes(k);
+        const int64_t cap = (int64_t)sm_count() * 8;
+        const int teams = (int)(B < cap ? B : cap);
+        if (!launch_large<IdxT, MODE, 1, MID_THREADS, true, uint16_t, true>(v, B, k, out, out_stride, status, nullptr, 0,
+                                                                            teams, smem, stream))
+            return cudaErrorLaunchFailure;
     } else {
         if (k > LARGE_K_MAX) return cudaErrorNotSupported;
         const size_t stride = large_ws_stride(k);
