@@ -85,7 +85,9 @@ __device__ __forceinline__ void batch_rank_pair(const uint16_t* __restrict__ sv,
     R_hi = (uint32_t)__half2int_rz(__high2half(R)) - (uint32_t)lane;
 }
 
-template <typename IdxT, int MODE>
+// WPL = free-mask words per lane: 1 for k <= 1024, 2 for k <= 2016 (the half2 rank scan is exact
+// for integers up to 2048 and overshoots the true rank by at most 31 before the correction).
+template <typename IdxT, int MODE, int WPL>
 __global__ void __launch_bounds__(SMALL_WARPS * 32)
 decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restrict__ out,
                     int64_t out_stride, int32_t* __restrict__ status, int K) {
@@ -94,11 +96,11 @@ decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
     const int warp = threadIdx.x >> 5;
     const int KA = K + 32;
     const int narr = (MODE == MODE_PAIRS) ? 2 : 3;
-    uint16_t* base = reinterpret_cast<uint16_t*>(smem_raw) + (size_t)warp * (narr * KA + 64);
+    uint16_t* base = reinterpret_cast<uint16_t*>(smem_raw) + (size_t)warp * (narr * KA + 64 * WPL);
     uint16_t* sv = base;            // v[t]                                   (by time)
     uint16_t* stime = sv + KA;      // element at slot s                      (by slot)
     uint16_t* stbl = stime + KA;    // last row so far whose label is x       (by label)  [!PAIRS]
-    uint32_t* smask = reinterpret_cast<uint32_t*>(base + narr * KA);  // 32 words of free-slot bits
+    uint32_t* smask = reinterpret_cast<uint32_t*>(base + narr * KA);  // 32*WPL words of free-slot bits
     const int nb = K >> 5;
 
     for (int64_t tree = (int64_t)blockIdx.x * SMALL_WARPS + warp; tree < B;
@@ -132,10 +134,14 @@ decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
             continue;
         }
         if (lane == 0 && status) status[tree] = 0;
-        // free-slot mask: bit i of word w <-> slot 32w+i, 1 = free
-        uint32_t word = (lane * 32 + 32 <= k) ? 0xFFFFFFFFu
-                        : (lane * 32 >= k ? 0u : ((1u << (k - lane * 32)) - 1u));
-        smask[lane] = word;
+        // free-slot mask: bit i of word g <-> slot 32g+i, 1 = free; lane l holds words l*WPL .. l*WPL+WPL-1
+        uint32_t word[WPL];
+#pragma unroll
+        for (int j = 0; j < WPL; ++j) {
+            const int g = lane * WPL + j;
+            word[j] = (g * 32 + 32 <= k) ? 0xFFFFFFFFu : (g * 32 >= k ? 0u : ((1u << (k - g * 32)) - 1u));
+            smask[g] = word[j];
+        }
         __syncwarp();
 
         // ---- B: slot assignment, walking time backwards, two batches per rank scan; the scan
@@ -153,7 +159,9 @@ decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
                 const bool act = t < k;
                 const uint32_t R = Rpair[h];
                 // rank-select R among the free slots
-                const uint32_t cnt = __popc(word);
+                uint32_t cnt = 0;
+#pragma unroll
+                for (int j = 0; j < WPL; ++j) cnt += __popc(word[j]);
                 const uint32_t incl = warp_incl_scan(cnt, lane);
                 uint32_t w = 0;
 #pragma unroll
@@ -162,15 +170,23 @@ decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
                     if (y <= R) w += step;
                 }
                 w &= 31;
-                const uint32_t wd = __shfl_sync(FULL, word, w);
-                const uint32_t ex = __shfl_sync(FULL, incl - cnt, w);
-                const uint32_t pos = nth_set_bit(wd, R - ex);
+                uint32_t rr = R - __shfl_sync(FULL, incl - cnt, w);     // rank inside lane w's words
+                uint32_t wd = __shfl_sync(FULL, word[0], w);
+                uint32_t g = w * WPL;
+#pragma unroll
+                for (int j = 1; j < WPL; ++j) {
+                    const uint32_t nxt = __shfl_sync(FULL, word[j], w);
+                    const uint32_t c = __popc(wd);
+                    if (rr >= c) { rr -= c; wd = nxt; g = w * WPL + j; }
+                }
+                const uint32_t pos = nth_set_bit(wd, rr);
                 if (act) {
-                    stime[w * 32 + pos] = (uint16_t)t;
-                    atomicAnd(&smask[w], ~(1u << pos));
+                    stime[g * 32 + pos] = (uint16_t)t;
+                    atomicAnd(&smask[g], ~(1u << pos));
                 }
                 __syncwarp();
-                word = smask[lane];
+#pragma unroll
+                for (int j = 0; j < WPL; ++j) word[j] = smask[lane * WPL + j];
             }
         }
 
@@ -531,8 +547,9 @@ static cudaError_t launch_decode_t(const void* v, int64_t B, int64_t k, void* ou
     if (k <= SMALL_K_MAX) {
         const int K = (int)((k + 31) & ~31);
         const int narr = (MODE == MODE_PAIRS) ? 2 : 3;
-        const size_t smem = (size_t)SMALL_WARPS * ((size_t)narr * (K + 32) + 64) * sizeof(uint16_t);
-        auto kern = decode_small_kernel<IdxT, MODE>;
+        const int wpl = (k <= 1024) ? 1 : 2;
+        const size_t smem = (size_t)SMALL_WARPS * ((size_t)narr * (K + 32) + 64 * wpl) * sizeof(uint16_t);
+        auto kern = (wpl == 1) ? decode_small_kernel<IdxT, MODE, 1> : decode_small_kernel<IdxT, MODE, 2>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 0;

@@ -440,14 +440,14 @@ static int enc_large_grid(int64_t B) {
 }
 
 size_t encode_workspace_bytes(int64_t B, int64_t k) {
-    if (k <= SMALL_K_MAX || B <= 0) return 0;
+    if (k <= ENC_SMALL_K_MAX || B <= 0) return 0;
     return (size_t)enc_large_grid(B) * enc_large_stride(k) * sizeof(uint32_t);
 }
 
 template <typename IdxT, int MODE>
 static cudaError_t launch_encode_t(const void* in, int64_t B, int64_t k, void* v, int32_t* status,
                                    void* ws, size_t ws_bytes, cudaStream_t stream) {
-    if (k <= SMALL_K_MAX) {
+    if (k <= ENC_SMALL_K_MAX) {
         const int K = (int)((k + 31) & ~31);
         const size_t per_warp = (size_t)(MODE != FROM_PAIRS ? 5 : 3) * (K + 32) + 64;
         const size_t smem = ENC_SMALL_WARPS * per_warp * sizeof(uint16_t);
