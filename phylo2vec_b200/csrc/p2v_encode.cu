@@ -78,7 +78,7 @@ __device__ __forceinline__ void count_smaller_pair(uint32_t r_a, bool act_a, uin
     cnt_b = (uint32_t)__half2int_rz(__high2half(cnt));
 }
 
-template <typename IdxT, int MODE>
+template <typename IdxT, int MODE, int WPL>
 __global__ void __launch_bounds__(ENC_SMALL_WARPS * 32)
 encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restrict__ vout,
                     int32_t* __restrict__ status, int K) {
@@ -87,14 +87,14 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
     const int warp = threadIdx.x >> 5;
     const int KA = K + 32;
     const bool has_par = (MODE != FROM_PAIRS);
-    const size_t per_warp = (size_t)(has_par ? 5 : 3) * KA + 64;
+    const size_t per_warp = (size_t)(has_par ? 5 : 3) * KA + 64 * WPL;
     uint16_t* base = reinterpret_cast<uint16_t*>(smem_raw) + warp * per_warp;
     uint16_t* sc1 = base;
     uint16_t* sc2 = sc1 + KA;
     uint16_t* spr = sc2 + KA;       // parent label by row; later row_of[value]
     uint16_t* sdef = spr + KA;      // defining row of internal label k+1+i      [has_par]
     uint16_t* smd = sdef + KA;      // min descendant of internal label k+1+i    [has_par]
-    uint32_t* smask = reinterpret_cast<uint32_t*>(base + per_warp - 64);
+    uint32_t* smask = reinterpret_cast<uint32_t*>(base + per_warp - 64 * WPL);   // 32*WPL words
     const int nb = K >> 5;
     const int in_cols = (MODE == FROM_PAIRS) ? 2 : (MODE == FROM_ANCESTRY ? 3 : 4);
     const uint32_t kint = (uint32_t)k + 1;      // first internal label
@@ -107,7 +107,8 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
         if (has_par) {
             for (int i = lane; i < KA; i += 32) { sdef[i] = (uint16_t)NONE16; smd[i] = (uint16_t)NONE16; }
         }
-        smask[lane] = 0;
+#pragma unroll
+        for (int j = 0; j < WPL; ++j) smask[lane * WPL + j] = 0;
         __syncwarp();
         long long offset = 0;
         if (MODE == FROM_EDGES) {
@@ -159,7 +160,8 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
         }
         bad = __any_sync(FULL, bad);
         __syncwarp();
-        smask[lane] = 0;
+#pragma unroll
+        for (int j = 0; j < WPL; ++j) smask[lane * WPL + j] = 0;
         // ---- E2: min-descendant relabel (build_cherries) as a wavefront ---------------
         if (has_par && !bad) {
             for (int b = 0; b < nb; ++b) {
@@ -229,11 +231,14 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
             continue;
         }
         if (lane == 0 && status) status[tree] = TREE_OK;
-        smask[lane] = 0;
+#pragma unroll
+        for (int j = 0; j < WPL; ++j) smask[lane * WPL + j] = 0;
         __syncwarp();
         // ---- E4: build_vector, values ascending, two batches per in-batch count ----------------
         IdxT* vo = vout + tree * k;
-        uint32_t word = 0;  // rows already seen (rows of smaller values), word `lane`
+        uint32_t word[WPL];  // rows already seen (rows of smaller values): words lane*WPL .. +WPL-1
+#pragma unroll
+        for (int j = 0; j < WPL; ++j) word[j] = 0;
         for (int bp = 0; bp < nb; bp += 2) {
             const int ca = bp * 32 + lane + 1, cb = ca + 32;
             const bool act_a = ca <= k, act_b = cb <= k;
@@ -246,18 +251,29 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                 const int c = h ? cb : ca;
                 const bool act = h ? act_b : act_a;
                 const uint32_t r = h ? rb : ra;
-                const uint32_t cnt = __popc(word);
+                uint32_t cnt = 0;
+#pragma unroll
+                for (int j = 0; j < WPL; ++j) cnt += __popc(word[j]);
                 const uint32_t excl = warp_incl_scan(cnt, lane) - cnt;
-                const uint32_t wd = __shfl_sync(FULL, word, r >> 5);
-                const uint32_t idx = __shfl_sync(FULL, excl, r >> 5) + __popc(wd & ((1u << (r & 31)) - 1u)) +
-                                     (h ? inb_b : inb_a);
+                const uint32_t g = r >> 5;                       // word that holds row r
+                const uint32_t src = g / WPL;
+                uint32_t idx = __shfl_sync(FULL, excl, src) + (h ? inb_b : inb_a);
+                const uint32_t low = (1u << (r & 31)) - 1u;
+#pragma unroll
+                for (int j = 0; j < WPL; ++j) {
+                    const uint32_t wj = __shfl_sync(FULL, word[j], src);
+                    const uint32_t jj = g - src * WPL;
+                    if ((uint32_t)j < jj) idx += __popc(wj);
+                    else if ((uint32_t)j == jj) idx += __popc(wj & low);
+                }
                 if (act) {
                     const uint32_t lo = min((uint32_t)sc1[r], (uint32_t)sc2[r]);
                     vo[c - 1] = (IdxT)(idx == 0 ? lo : (uint32_t)(c - 1) + idx);
-                    atomicOr(&smask[r >> 5], 1u << (r & 31));
+                    atomicOr(&smask[g], 1u << (r & 31));
                 }
                 __syncwarp();
-                word = smask[lane];
+#pragma unroll
+                for (int j = 0; j < WPL; ++j) word[j] = smask[lane * WPL + j];
             }
         }
         __syncwarp();
@@ -449,9 +465,10 @@ static cudaError_t launch_encode_t(const void* in, int64_t B, int64_t k, void* v
                                    void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (k <= ENC_SMALL_K_MAX) {
         const int K = (int)((k + 31) & ~31);
-        const size_t per_warp = (size_t)(MODE != FROM_PAIRS ? 5 : 3) * (K + 32) + 64;
+        const int wpl = (k <= 1024) ? 1 : 2;
+        const size_t per_warp = (size_t)(MODE != FROM_PAIRS ? 5 : 3) * (K + 32) + 64 * wpl;
         const size_t smem = ENC_SMALL_WARPS * per_warp * sizeof(uint16_t);
-        auto kern = encode_small_kernel<IdxT, MODE>;
+        auto kern = (wpl == 1) ? encode_small_kernel<IdxT, MODE, 1> : encode_small_kernel<IdxT, MODE, 2>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 0;

@@ -10,7 +10,7 @@ enum DecodeMode { MODE_PAIRS = 0, MODE_ANCESTRY = 1, MODE_EDGES = 2 };
 enum EncodeMode { FROM_PAIRS = 0, FROM_ANCESTRY = 1, FROM_EDGES = 2 };
 
 constexpr int SMALL_K_MAX = 2016;      // warp-per-tree decode in shared memory; the half2 rank scan needs K + 30 <= 2048
-constexpr int ENC_SMALL_K_MAX = 1024;  // warp-per-tree encode
+constexpr int ENC_SMALL_K_MAX = 2047;  // warp-per-tree encode (rows exact in fp16)
 constexpr int LARGE_K_MAX = 1 << 19;   // CTA-per-tree kernels (bit mask + Fenwick in shared memory)
 
 int sm_count();

@@ -84,7 +84,7 @@ def test_empty_and_tiny(p2v):
 
 
 # ---------------------------------------------------------------- batched parity vs oracle
-SIZES = [2, 3, 4, 5, 17, 32, 33, 34, 64, 65, 100, 257, 1000, 1024, 1025, 1026, 1500, 2000, 2016, 2017, 2018, 2049, 5000, 12288, 12289, 20000]
+SIZES = [2, 3, 4, 5, 17, 32, 33, 34, 64, 65, 100, 257, 1000, 1024, 1025, 1026, 1500, 2000, 2016, 2017, 2018, 2048, 2049, 5000, 12288, 12289, 20000]
 
 
 @pytest.mark.parametrize("n_leaves", SIZES)
