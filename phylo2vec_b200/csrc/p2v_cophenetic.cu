@@ -76,6 +76,7 @@ struct CophLayout {
     // byte offsets inside one tree's table area
     size_t anc, jA, jDI, jDH, jDL, tn, tc, pos, leaf_at, sepk, sephi, seplo;     // prepare
     size_t blk_of, rowlist, prek, prea, sufk, sufa, bstart, bend, rowoff, cend, blkk, blka, tilelist, hdr, flags;  // rows call (+ flags: prepare)
+    size_t c_blk, c_prek, c_sufk, c_prehi, c_prelo, c_sufhi, c_suflo;      // rows call, by leaf label
     size_t total;
     int n, N, A, nbmax;
 };
@@ -112,6 +113,13 @@ __host__ __device__ inline CophLayout coph_layout(int64_t k) {
     L.blkk = o; o = al16(o + 4 * (size_t)L.nbmax);
     L.blka = o; o = al16(o + 4 * (size_t)L.nbmax);
     L.tilelist = o; o = al16(o + 4 * (size_t)L.nbmax);
+    L.c_blk = o; o = al16(o + 4 * (size_t)L.n);
+    L.c_prek = o; o = al16(o + 4 * (size_t)L.n);
+    L.c_sufk = o; o = al16(o + 4 * (size_t)L.n);
+    L.c_prehi = o; o = al16(o + 8 * (size_t)L.n);
+    L.c_prelo = o; o = al16(o + 8 * (size_t)L.n);
+    L.c_sufhi = o; o = al16(o + 8 * (size_t)L.n);
+    L.c_suflo = o; o = al16(o + 8 * (size_t)L.n);
     L.hdr = o; o = al16(o + 64);
     L.flags = o; o = al16(o + 4 * (size_t)TAB_FLAGS);
     L.total = al16(o + 64);
@@ -458,6 +466,37 @@ block_minima_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t 
     }
 }
 
+// Per-label copies of what rows_kernel needs about a column, so that its column setup is one level
+// of coalesced loads: block of the leaf, and the two in-block candidates (prefix / suffix minimum
+// at the leaf's position) with their double-double depths.
+__global__ void __launch_bounds__(256)
+column_tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int k, int weighted,
+                     const int32_t* __restrict__ status) {
+    const CophLayout L = coph_layout(k);
+    const int n = L.n;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < B * n; w += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t tree = w / n;
+        const int j = (int)(w % n);
+        if (status && status[tree] != 0) continue;
+        unsigned char* T = tab + (size_t)tree * tab_stride;
+        const int p = reinterpret_cast<const int*>(T + L.pos)[j];
+        const int pk = reinterpret_cast<const int*>(T + L.prek)[p], sk = reinterpret_cast<const int*>(T + L.sufk)[p];
+        reinterpret_cast<int*>(T + L.c_blk)[j] = reinterpret_cast<const int*>(T + L.blk_of)[p];
+        reinterpret_cast<int*>(T + L.c_prek)[j] = pk;
+        reinterpret_cast<int*>(T + L.c_sufk)[j] = sk;
+        if (weighted) {
+            const double* sephi = reinterpret_cast<const double*>(T + L.sephi);
+            const double* seplo = reinterpret_cast<const double*>(T + L.seplo);
+            const int pa = reinterpret_cast<const int*>(T + L.prea)[p], sa = reinterpret_cast<const int*>(T + L.sufa)[p];
+            const bool hp = pk < KEY_INF, hs = sk < KEY_INF;
+            reinterpret_cast<double*>(T + L.c_prehi)[j] = hp ? sephi[pa] : 0.0;
+            reinterpret_cast<double*>(T + L.c_prelo)[j] = hp ? seplo[pa] : 0.0;
+            reinterpret_cast<double*>(T + L.c_sufhi)[j] = hs ? sephi[sa] : 0.0;
+            reinterpret_cast<double*>(T + L.c_suflo)[j] = hs ? seplo[sa] : 0.0;
+        }
+    }
+}
+
 // ---- 4. rows --------------------------------------------------------------------------------
 __device__ __forceinline__ double int_to_f64(int v) {
     // exact for |v| < 2^31 : one DADD instead of an I2F.F64 on the slow pipe
@@ -491,11 +530,11 @@ struct RowShared {
     unsigned long long wtotR[8], wtotL[8]; // per-warp totals of the block scan
     int incount;
 };
-// dynamic shared memory of rows_kernel: midk[nbmax], mida[nbmax], then (sized by the call's
-// position cap pmax) kblk[pmax], inlist[pmax], st[levels][pmax] (uint16)
+// dynamic shared memory of rows_kernel: midhi[nbmax], midlo[nbmax] (doubles), midk[nbmax], mida[nbmax],
+// then (sized by the call's position cap pmax) kblk[pmax], inlist[pmax], st[levels][pmax] (uint16)
 inline size_t rows_dyn_smem(int nbmax, int pmax) {
     const int levels = ilog2c(pmax) + 1;
-    return (((size_t)8 * nbmax + 15) & ~(size_t)15) + (size_t)8 * pmax + (size_t)2 * levels * pmax + 16;
+    return (((size_t)24 * nbmax + 15) & ~(size_t)15) + (size_t)8 * pmax + (size_t)2 * levels * pmax + 16;
 }
 
 __device__ __forceinline__ unsigned long long shfl_up64(unsigned long long x, int d) {
@@ -521,9 +560,11 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
     constexpr int NWARP = THREADS / 32;
     const CophLayout L = coph_layout(k);
     const int n = L.n, nbmax = L.nbmax;
-    int* midk = reinterpret_cast<int*>(dyn);          // nbmax
-    int* mida = midk + nbmax;                         // nbmax
-    int* s_kblk = reinterpret_cast<int*>(dyn + (((size_t)8 * nbmax + 15) & ~(size_t)15));   // pmax: separators of the block
+    double* midhi = reinterpret_cast<double*>(dyn);   // nbmax: dd depth of the minimum between the tile and block J
+    double* midlo = midhi + nbmax;
+    int* midk = reinterpret_cast<int*>(midlo + nbmax);   // nbmax: its key
+    int* mida = midk + nbmax;                         // nbmax: its position
+    int* s_kblk = reinterpret_cast<int*>(dyn + (((size_t)24 * nbmax + 15) & ~(size_t)15));   // pmax: separators of the block
     int* s_inlist = s_kblk + pmax;                    // pmax: in-block leaves whose column is in this chunk
     unsigned short* s_st = reinterpret_cast<unsigned short*>(s_inlist + pmax);   // [levels][pmax] argmin offsets
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -563,6 +604,13 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
         const int* sufa = reinterpret_cast<const int*>(T + L.sufa);
         const int* blkk = reinterpret_cast<const int*>(T + L.blkk);
         const int* blka = reinterpret_cast<const int*>(T + L.blka);
+        const int* c_blk = reinterpret_cast<const int*>(T + L.c_blk);
+        const int* c_prek = reinterpret_cast<const int*>(T + L.c_prek);
+        const int* c_sufk = reinterpret_cast<const int*>(T + L.c_sufk);
+        const double* c_prehi = reinterpret_cast<const double*>(T + L.c_prehi);
+        const double* c_prelo = reinterpret_cast<const double*>(T + L.c_prelo);
+        const double* c_sufhi = reinterpret_cast<const double*>(T + L.c_sufhi);
+        const double* c_suflo = reinterpret_cast<const double*>(T + L.c_suflo);
         __syncthreads();   // previous iteration's readers of S / dyn are done
 
         // ---- row side of the tile -------------------------------------------------------
@@ -631,12 +679,14 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
             for (int J = s0; J < s1; ++J) {                  // blocks right of I, walking right
                 if (J > I) {
                     midk[J] = (int)(runR >> 32); mida[J] = (int)(runR & 0xFFFFFFFFu);
+                    if (!TOPO && runR < INF64) { midhi[J] = sephi[mida[J]]; midlo[J] = seplo[mida[J]]; }
                     runR = min(runR, ((unsigned long long)(unsigned)blkk[J] << 32) | (unsigned)blka[J]);
                 }
             }
             for (int J = s1 - 1; J >= s0; --J) {             // blocks left of I, walking left
                 if (J < I) {
                     midk[J] = (int)(runL >> 32); mida[J] = (int)(runL & 0xFFFFFFFFu);
+                    if (!TOPO && runL < INF64) { midhi[J] = sephi[mida[J]]; midlo[J] = seplo[mida[J]]; }
                     runL = min(runL, ((unsigned long long)(unsigned)blkk[J] << 32) | (unsigned)blka[J]);
                 }
                 if (J == I) { midk[J] = KEY_INF; mida[J] = 0; }
@@ -670,26 +720,27 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
             col[c] = j;
             side[c] = 0; bi[c] = 0; uji[c] = 0; bhi[c] = blo[c] = ujf[c] = 0.0;
             if (j < n) {
-                const int p = pos[j];
-                const int J = blk_of[p];
+                const int J = c_blk[j];
                 const bool right = J > I;
                 side[c] = right ? 1 : 0;
-                int ck = right ? prek[p] : sufk[p];
-                int ca = right ? prea[p] : sufa[p];
+                int ck = right ? c_prek[j] : c_sufk[j];
                 const int mk = midk[J];
-                if (mk < ck) { ck = mk; ca = mida[J]; }
+                const bool usemid = mk < ck;
+                if (usemid) ck = mk;
                 const bool none = ck >= KEY_INF;
-                const int dj = jDI[j];
                 if (J == I) {                      // patched after the streamed part
                     const int slot = atomicAdd(&S.incount, 1);
-                    s_inlist[slot] = p;
+                    s_inlist[slot] = pos[j];
                 }
                 if (TOPO) {
+                    const int dj = jDI[j];
                     bi[c] = none ? dj : ck;
                     uji[c] = dj - bi[c];
                 } else {
                     const dd d = {jDH[j], jDL[j]};
-                    const dd b = none ? d : dd{sephi[ca], seplo[ca]};
+                    dd b = right ? dd{c_prehi[j], c_prelo[j]} : dd{c_sufhi[j], c_suflo[j]};
+                    if (usemid) b = dd{midhi[J], midlo[J]};
+                    if (none) b = d;
                     bhi[c] = b.hi; blo[c] = b.lo;
                     ujf[c] = none ? 0.0 : dd_diff_round(d, b);
                 }
@@ -927,6 +978,10 @@ cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t
         const int64_t warps = B * (int64_t)L.nbmax;
         const int64_t want = (warps + 7) / 8, cap2 = (int64_t)sm_count() * 8;
         block_minima_kernel<<<(int)(want < cap2 ? want : cap2), 256, 0, stream>>>(tab, L.total, B, (int)k, st);
+        count_launch();
+        const int64_t want3 = (B * n + 255) / 256;
+        column_tables_kernel<<<(int)(want3 < cap2 * 4 ? want3 : cap2 * 4), 256, 0, stream>>>(tab, L.total, B, (int)k,
+                                                                                           weighted, st);
         count_launch();
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
