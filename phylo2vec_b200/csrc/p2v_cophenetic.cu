@@ -57,16 +57,28 @@ constexpr int ROW_PMAX_LARGE = 1024;       // capacity: DFS positions per block 
 constexpr int ROW_PMAX_SMALL = 64;         //                                            (n <= 512)
 constexpr int ilog2c(int x) { return x <= 1 ? 0 : 1 + ilog2c(x >> 1); }
 constexpr int ROW_CPT = 4;                 // columns per thread (two 16-byte stores per row)
-// Position cap of a block for a call that asks for m of the n rows: blocks are cut every ROW_R
-// requested rows, which span about ROW_R*n/m positions; the cap sits 25% above that so that it
-// rarely cuts a second time, within the capacity of the in-block sparse table.
-inline int coph_pmax(int64_t n, int64_t m) {
-    if (n <= 512) return ROW_PMAX_SMALL;
-    int64_t want = (5 * (int64_t)ROW_R * n) / (4 * (m > 0 ? m : 1));
-    want = (want + 31) & ~(int64_t)31;
-    if (want < ROW_R) want = ROW_R;
-    if (want > ROW_PMAX_LARGE) want = ROW_PMAX_LARGE;
-    return (int)want;
+constexpr int ROW_NINCAP = 64;             // in-block columns per chunk whose values are staged in shared memory
+// Shape of one rows call.  Blocks are cut every `rcap` requested rows and every `pcap` DFS
+// positions; the requested rows of a block span about rcap*n/m positions, and pcap sits 25% above
+// that so that it rarely cuts a second time (no cap at all when every row is requested).  `bsz`
+// bounds the positions in a block (capacity of the in-block tables), `nidb` the number of block ids.
+struct CophCall { int pcap, rcap, bsz, nidb, nincap; };
+inline CophCall coph_call(int64_t n, int64_t m) {
+    CophCall c;
+    c.rcap = (n <= 512) ? 32 : ROW_R;
+    if (m >= n) {
+        c.pcap = 1 << 30; c.bsz = c.rcap;
+    } else {
+        int64_t want = (5 * (int64_t)c.rcap * n) / (4 * (m > 0 ? m : 1));
+        want = (want + 31) & ~(int64_t)31;
+        if (want < c.rcap) want = c.rcap;
+        const int64_t cap = (n <= 512) ? ROW_PMAX_SMALL : ROW_PMAX_LARGE;
+        if (want > cap) want = cap;
+        c.pcap = (int)want; c.bsz = c.pcap;
+    }
+    c.nidb = (int)(n / c.pcap + (m + c.rcap - 1) / c.rcap + 2);
+    c.nincap = c.bsz < ROW_NINCAP ? c.bsz : ROW_NINCAP;
+    return c;
 }
 // threads per rows-CTA: 4 columns per thread, so small trees get small CTAs
 inline int coph_row_threads(int n) { return n <= 128 ? 32 : (n <= 256 ? 64 : (n <= 512 ? 128 : 256)); }
@@ -86,7 +98,7 @@ __host__ __device__ inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15
 __host__ __device__ inline CophLayout coph_layout(int64_t k) {
     CophLayout L;
     L.n = (int)(k + 1); L.N = (int)(2 * k + 1); L.A = (int)(4 * k);
-    L.nbmax = 2 * (L.n / ROW_R) + 3;      // position cap >= ROW_R, row cap == ROW_R
+    L.nbmax = L.n / 32 + L.n / 32 + 4;     // bound on block ids for any call (pcap >= 32, rcap >= 32)
     size_t o = 0;
     L.anc = o; o = al16(o + 4 * 3 * (size_t)k);
     L.jA = o; o = al16(o + 4 * 2 * (size_t)L.N);
@@ -302,8 +314,8 @@ tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* 
 }
 
 // ---- 3. blocks for the requested rows ----------------------------------------------------------
-// Block id of DFS position p:  p / pmax + max(0, c(p) - 1) / ROW_R  (pmax: coph_pmax),  c(p) = number of requested
-// rows at positions <= p.  Hence every block holds <= ROW_R requested rows and <= pmax positions
+// Block id of DFS position p:  p / pcap + max(0, c(p) - 1) / rcap  (coph_call),  c(p) = number of requested
+// rows at positions <= p.  Hence every block holds <= rcap requested rows and <= pcap positions
 // (ids that no position maps to stay empty).  hdr[0] = number of ids, hdr[1] = number of tiles
 // (blocks that hold requested rows), listed in tilelist.
 __device__ __forceinline__ unsigned long long pack_key(int key, int p) {
@@ -312,7 +324,7 @@ __device__ __forceinline__ unsigned long long pack_key(int key, int p) {
 
 __global__ void __launch_bounds__(BLK_THREADS)
 blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int k, int64_t row_begin,
-              int64_t row_end, int pmax, const int32_t* __restrict__ status) {
+              int64_t row_end, int pcap, int rcap, const int32_t* __restrict__ status) {
     __shared__ int s_part[BLK_THREADS / 32];
     __shared__ int s_total;
     const CophLayout L = coph_layout(k);
@@ -355,7 +367,7 @@ blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int
         }
         __syncthreads();
         int c0 = s_part[warp];                       // requested rows at positions < w0
-        int prev_last = (w0 > 0) ? (w0 - 1) / pmax + max(0, c0 - 1) / ROW_R : -1;   // id of position w0-1
+        int prev_last = (w0 > 0) ? (w0 - 1) / pcap + max(0, c0 - 1) / rcap : -1;   // id of position w0-1
         for (int base = w0; base < w1; base += 32) {
             const int p = base + lane;
             const bool in = p < w1;
@@ -363,7 +375,7 @@ blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int
             const bool own = lab >= row_begin && lab < row_end;
             const unsigned bm = __ballot_sync(FULL, own);
             const int c = c0 + __popc(bm & lanes_le(lane));          // requested rows at positions <= p
-            const int id = in ? p / pmax + max(0, c - 1) / ROW_R : -1;
+            const int id = in ? p / pcap + max(0, c - 1) / rcap : -1;
             int prev_id = __shfl_up_sync(FULL, id, 1);
             if (lane == 0) prev_id = prev_last;
             if (in) {
@@ -530,11 +542,12 @@ struct RowShared {
     unsigned long long wtotR[8], wtotL[8]; // per-warp totals of the block scan
     int incount;
 };
-// dynamic shared memory of rows_kernel: midhi[nbmax], midlo[nbmax] (doubles), midk[nbmax], mida[nbmax],
-// then (sized by the call's position cap pmax) kblk[pmax], inlist[pmax], st[levels][pmax] (uint16)
-inline size_t rows_dyn_smem(int nbmax, int pmax) {
-    const int levels = ilog2c(pmax) + 1;
-    return (((size_t)24 * nbmax + 15) & ~(size_t)15) + (size_t)8 * pmax + (size_t)2 * levels * pmax + 16;
+// dynamic shared memory of rows_kernel: midhi[nidb], midlo[nidb] (doubles), midk[nidb], mida[nidb],
+// ptab[rcap * nincap] (doubles), then kblk[bsz], inlist[bsz], st[levels][bsz] (uint16)
+inline size_t rows_dyn_smem(const CophCall& c) {
+    const int levels = ilog2c(c.bsz) + 1;
+    return (((size_t)24 * c.nidb + 15) & ~(size_t)15) + (size_t)8 * c.rcap * c.nincap + (size_t)8 * c.bsz +
+           (size_t)2 * levels * c.bsz + 16;
 }
 
 __device__ __forceinline__ unsigned long long shfl_up64(unsigned long long x, int d) {
@@ -553,18 +566,19 @@ __global__ void __launch_bounds__(THREADS, rows_min_blocks(THREADS))
 rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int k,
             int64_t row_begin, int64_t row_end, double* __restrict__ out,
             const int32_t* __restrict__ status, int chunks_per_tree, int chunks_per_cta, int tiles_bound,
-            int pmax) {
+            int pmax /* block size cap */, int nidb, int rcap, int nincap) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ RowShared S;
     constexpr int CHUNK = THREADS * ROW_CPT;
     constexpr int NWARP = THREADS / 32;
     const CophLayout L = coph_layout(k);
-    const int n = L.n, nbmax = L.nbmax;
-    double* midhi = reinterpret_cast<double*>(dyn);   // nbmax: dd depth of the minimum between the tile and block J
-    double* midlo = midhi + nbmax;
-    int* midk = reinterpret_cast<int*>(midlo + nbmax);   // nbmax: its key
-    int* mida = midk + nbmax;                         // nbmax: its position
-    int* s_kblk = reinterpret_cast<int*>(dyn + (((size_t)24 * nbmax + 15) & ~(size_t)15));   // pmax: separators of the block
+    const int n = L.n;
+    double* midhi = reinterpret_cast<double*>(dyn);   // nidb: dd depth of the minimum between the tile and block J
+    double* midlo = midhi + nidb;
+    int* midk = reinterpret_cast<int*>(midlo + nidb);    // nidb: its key
+    int* mida = midk + nidb;                          // nidb: its position
+    double* s_ptab = reinterpret_cast<double*>(dyn + (((size_t)24 * nidb + 15) & ~(size_t)15));   // rcap*nincap: row x in-block column
+    int* s_kblk = reinterpret_cast<int*>(s_ptab + (size_t)rcap * nincap);                          // pmax: separators of the block
     int* s_inlist = s_kblk + pmax;                    // pmax: in-block leaves whose column is in this chunk
     unsigned short* s_st = reinterpret_cast<unsigned short*>(s_inlist + pmax);   // [levels][pmax] argmin offsets
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -712,6 +726,7 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
         __syncthreads();
         // ---- column side: 4 columns per thread (two adjacent pairs) ----------------------
         int col[ROW_CPT], side[ROW_CPT];
+        unsigned inpack = 0;               // per column: slot + 1 in the in-block list, 0 = outside (8 bits each)
         int bi[ROW_CPT], uji[ROW_CPT];
         double bhi[ROW_CPT], blo[ROW_CPT], ujf[ROW_CPT];
 #pragma unroll
@@ -731,6 +746,7 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
                 if (J == I) {                      // patched after the streamed part
                     const int slot = atomicAdd(&S.incount, 1);
                     s_inlist[slot] = pos[j];
+                    if (slot < nincap) inpack |= (unsigned)(slot + 1) << (8 * c);
                 }
                 if (TOPO) {
                     const int dj = jDI[j];
@@ -746,6 +762,36 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
                 }
             }
         }
+
+        // ---- in-block columns (incl. the zero diagonal): their LCA lies inside the block and comes
+        //      from the sparse table.  Normally (<= ROW_NINCAP of them in this chunk) the values are
+        //      staged in shared memory and merged into the streamed stores; otherwise they are
+        //      written by a patch pass after the streamed part.
+        __syncthreads();
+        const int nin = S.incount;
+        const bool staged = nin <= nincap;
+        auto inblock_value = [&](int r, int e) -> double {
+            const int q = S.qpos[r], p = s_inlist[e];
+            if (p == q) return 0.0;
+            const int a = min(p, q) + 1 - lo, b = max(p, q) - lo;     // sep offsets a..b
+            const int lev = 31 - __clz(b - a + 1);
+            const int x = s_st[lev * pmax + a], y = s_st[lev * pmax + b - (1 << lev) + 1];
+            const int arg = (s_kblk[x] <= s_kblk[y]) ? x : y;
+            const int j = leaf_at[p];
+            if (TOPO) return int_to_f64(S.di[r] + jDI[j] - 2 * s_kblk[arg]);
+            const dd m = dd{-sephi[lo + arg], -seplo[lo + arg]};
+            const dd xa = dd_add(dd{S.dhi[r], S.dlo[r]}, m);
+            const dd xb = dd_add(dd{jDH[j], jDL[j]}, m);
+            return __dadd_rn(__dadd_rn(xa.hi, xb.hi), __dadd_rn(xa.lo, xb.lo));
+        };
+        if (staged) {
+            for (int w = tid; w < nin * nrow; w += THREADS) {
+                const int r = w / nin, e = w - r * nin;
+                s_ptab[r * nincap + e] = inblock_value(r, e);
+            }
+            __syncthreads();
+        }
+        const bool warp_has_in = staged && __any_sync(FULL, inpack != 0);
 
         // ---- streamed part: requested rows x 4 columns per thread -----------------------------
 #pragma unroll 2
@@ -773,6 +819,13 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
                     val[c] = __dadd_rn(__dadd_rn(u, ujf[c]), fabs(m));
                 }
             }
+            if (warp_has_in) {           // warp-uniform
+#pragma unroll
+                for (int c = 0; c < ROW_CPT; ++c) {
+                    const unsigned e = (inpack >> (8 * c)) & 0xFFu;
+                    if (e) val[c] = s_ptab[r * nincap + e - 1];
+                }
+            }
 #pragma unroll
             for (int c = 0; c < ROW_CPT; c += 2) {
                 if (col[c] + 1 < n) store2<VEC2>(orow + col[c], val[c], val[c + 1]);
@@ -780,30 +833,12 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
             }
         }
 
-        // ---- patch: columns whose leaf sits inside the block (incl. the zero diagonal) --------
-        __syncthreads();   // also orders the streamed stores of this CTA before the patch stores
-        const int nin = S.incount;
-        for (int w = tid; w < nin * nrow; w += THREADS) {
-            const int r = w / nin, e = w - r * nin;
-            const int q = S.qpos[r], p = s_inlist[e];
-            const int i = S.label[r], j = leaf_at[p];
-            double d = 0.0;
-            if (p != q) {
-                const int a = min(p, q) + 1 - lo, b = max(p, q) - lo;     // sep offsets a..b
-                const int lev = 31 - __clz(b - a + 1);
-                const int x = s_st[lev * pmax + a], y = s_st[lev * pmax + b - (1 << lev) + 1];
-                const int arg = (s_kblk[x] <= s_kblk[y]) ? x : y;
-                if (TOPO) {
-                    d = int_to_f64(S.di[r] + jDI[j] - 2 * s_kblk[arg]);
-                } else {
-                    const dd l = {sephi[lo + arg], seplo[lo + arg]};
-                    const dd m = dd{-l.hi, -l.lo};
-                    const dd xa = dd_add(dd{S.dhi[r], S.dlo[r]}, m);
-                    const dd xb = dd_add(dd{jDH[j], jDL[j]}, m);
-                    d = __dadd_rn(__dadd_rn(xa.hi, xb.hi), __dadd_rn(xa.lo, xb.lo));
-                }
+        if (!staged) {   // rare: more in-block columns in this chunk than the staging table holds
+            __syncthreads();   // orders the streamed stores of this CTA before the patch stores
+            for (int w = tid; w < nin * nrow; w += THREADS) {
+                const int r = w / nin, e = w - r * nin;
+                obase[(size_t)(S.label[r] - row_begin) * n + leaf_at[s_inlist[e]]] = inblock_value(r, e);
             }
-            obase[(size_t)(i - row_begin) * n + j] = d;
         }
         __syncthreads();   // the patch has read inlist / incount before the next chunk resets them
         }  // chunk
@@ -969,11 +1004,11 @@ cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t
     }
     const CophLayout L = coph_layout(k);
     unsigned char* tab = wsb + W.tab;
-    const int pmax = coph_pmax(n, row_end - row_begin);
+    const CophCall call = coph_call(n, row_end - row_begin);
     {
         const int64_t cap = (int64_t)sm_count() * 2;
         const int grid = (int)(B < cap ? B : cap);
-        blocks_kernel<<<grid, BLK_THREADS, 0, stream>>>(tab, L.total, B, (int)k, row_begin, row_end, pmax, st);
+        blocks_kernel<<<grid, BLK_THREADS, 0, stream>>>(tab, L.total, B, (int)k, row_begin, row_end, call.pcap, call.rcap, st);
         count_launch();
         const int64_t warps = B * (int64_t)L.nbmax;
         const int64_t want = (warps + 7) / 8, cap2 = (int64_t)sm_count() * 8;
@@ -989,12 +1024,12 @@ cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t
     const int threads = coph_row_threads((int)n);
     const int chunk_cols = threads * ROW_CPT;
     const int chunks = (int)((n + chunk_cols - 1) / chunk_cols);
-    int64_t tiles_bound = (row_end - row_begin) / ROW_R + n / pmax + 2;
+    int64_t tiles_bound = call.nidb;
     if (tiles_bound > L.nbmax) tiles_bound = L.nbmax;
     // small matrices: one CTA walks all column chunks of its tile (row-side setup done once)
     const int chunks_per_cta = (chunks <= 4) ? chunks : 1;
     const int64_t work = B * tiles_bound * ((chunks + chunks_per_cta - 1) / chunks_per_cta);
-    const size_t smem = rows_dyn_smem(L.nbmax, pmax);
+    const size_t smem = rows_dyn_smem(call);
     const bool topo = !weighted;
     const bool vec2 = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     const int64_t cap = (int64_t)sm_count() * 96 * (256 / threads);
@@ -1005,7 +1040,8 @@ cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
         if (e != cudaSuccess) return e;                                                               \
         kern<<<grid, TH_, smem, stream>>>(tab, L.total, B, (int)k, row_begin, row_end, out, st, chunks, \
-                                          chunks_per_cta, (int)tiles_bound, pmax);                                    \
+                                          chunks_per_cta, (int)tiles_bound, call.bsz, call.nidb, call.rcap,   \
+                                          call.nincap);                                               \
     } while (0)
 #define P2V_ROWS2(T_, V_)                                                                             \
     do {                                                                                              \
