@@ -543,10 +543,11 @@ struct RowShared {
     int incount;
 };
 // dynamic shared memory of rows_kernel: midhi[nidb], midlo[nidb] (doubles), midk[nidb], mida[nidb],
-// ptab[rcap * nincap] (doubles), then kblk[bsz], inlist[bsz], st[levels][bsz] (uint16)
+// ptab[rcap * nincap], sephi[bsz], seplo[bsz], inhi[bsz], inlo[bsz] (doubles), then kblk[bsz],
+// inlist[bsz], inlab[bsz], indi[bsz] (ints), st[levels][bsz] (uint16)
 inline size_t rows_dyn_smem(const CophCall& c) {
     const int levels = ilog2c(c.bsz) + 1;
-    return (((size_t)24 * c.nidb + 15) & ~(size_t)15) + (size_t)8 * c.rcap * c.nincap + (size_t)8 * c.bsz +
+    return (((size_t)24 * c.nidb + 15) & ~(size_t)15) + (size_t)8 * c.rcap * c.nincap + (size_t)48 * c.bsz +
            (size_t)2 * levels * c.bsz + 16;
 }
 
@@ -578,9 +579,15 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
     int* midk = reinterpret_cast<int*>(midlo + nidb);    // nidb: its key
     int* mida = midk + nidb;                          // nidb: its position
     double* s_ptab = reinterpret_cast<double*>(dyn + (((size_t)24 * nidb + 15) & ~(size_t)15));   // rcap*nincap: row x in-block column
-    int* s_kblk = reinterpret_cast<int*>(s_ptab + (size_t)rcap * nincap);                          // pmax: separators of the block
-    int* s_inlist = s_kblk + pmax;                    // pmax: in-block leaves whose column is in this chunk
-    unsigned short* s_st = reinterpret_cast<unsigned short*>(s_inlist + pmax);   // [levels][pmax] argmin offsets
+    double* s_sephi = s_ptab + (size_t)rcap * nincap; // pmax: dd depth of the block's separators
+    double* s_seplo = s_sephi + pmax;
+    double* s_inhi = s_seplo + pmax;                  // pmax: dd depth of the in-block leaves of this chunk
+    double* s_inlo = s_inhi + pmax;
+    int* s_kblk = reinterpret_cast<int*>(s_inlo + pmax);   // pmax: separator keys of the block
+    int* s_inlist = s_kblk + pmax;                    // pmax: in-block leaves whose column is in this chunk (positions)
+    int* s_inlab = s_inlist + pmax;                   // pmax: their labels
+    int* s_indi = s_inlab + pmax;                     // pmax: their topological depths
+    unsigned short* s_st = reinterpret_cast<unsigned short*>(s_indi + pmax);   // [levels][pmax] argmin offsets
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t rows = row_end - row_begin;
 
@@ -655,6 +662,7 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
         for (int x = tid; x < hi - lo; x += THREADS) {
             s_kblk[x] = sepk[lo + x];
             s_st[x] = (unsigned short)x;
+            if (!TOPO) { s_sephi[x] = sephi[lo + x]; s_seplo[x] = seplo[lo + x]; }
         }
 
         // ---- minima over the whole blocks between the tile and every other block --------
@@ -743,17 +751,20 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
                 const bool usemid = mk < ck;
                 if (usemid) ck = mk;
                 const bool none = ck >= KEY_INF;
-                if (J == I) {                      // patched after the streamed part
-                    const int slot = atomicAdd(&S.incount, 1);
-                    s_inlist[slot] = pos[j];
+                int slot = -1;
+                if (J == I) {                      // its LCA with the rows lies inside the block
+                    slot = atomicAdd(&S.incount, 1);
+                    s_inlist[slot] = pos[j]; s_inlab[slot] = j;
                     if (slot < nincap) inpack |= (unsigned)(slot + 1) << (8 * c);
                 }
                 if (TOPO) {
                     const int dj = jDI[j];
+                    if (slot >= 0) s_indi[slot] = dj;
                     bi[c] = none ? dj : ck;
                     uji[c] = dj - bi[c];
                 } else {
                     const dd d = {jDH[j], jDL[j]};
+                    if (slot >= 0) { s_inhi[slot] = d.hi; s_inlo[slot] = d.lo; }
                     dd b = right ? dd{c_prehi[j], c_prelo[j]} : dd{c_sufhi[j], c_suflo[j]};
                     if (usemid) b = dd{midhi[J], midlo[J]};
                     if (none) b = d;
@@ -777,11 +788,10 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
             const int lev = 31 - __clz(b - a + 1);
             const int x = s_st[lev * pmax + a], y = s_st[lev * pmax + b - (1 << lev) + 1];
             const int arg = (s_kblk[x] <= s_kblk[y]) ? x : y;
-            const int j = leaf_at[p];
-            if (TOPO) return int_to_f64(S.di[r] + jDI[j] - 2 * s_kblk[arg]);
-            const dd m = dd{-sephi[lo + arg], -seplo[lo + arg]};
+            if (TOPO) return int_to_f64(S.di[r] + s_indi[e] - 2 * s_kblk[arg]);
+            const dd m = dd{-s_sephi[arg], -s_seplo[arg]};
             const dd xa = dd_add(dd{S.dhi[r], S.dlo[r]}, m);
-            const dd xb = dd_add(dd{jDH[j], jDL[j]}, m);
+            const dd xb = dd_add(dd{s_inhi[e], s_inlo[e]}, m);
             return __dadd_rn(__dadd_rn(xa.hi, xb.hi), __dadd_rn(xa.lo, xb.lo));
         };
         if (staged) {
@@ -837,7 +847,7 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
             __syncthreads();   // orders the streamed stores of this CTA before the patch stores
             for (int w = tid; w < nin * nrow; w += THREADS) {
                 const int r = w / nin, e = w - r * nin;
-                obase[(size_t)(S.label[r] - row_begin) * n + leaf_at[s_inlist[e]]] = inblock_value(r, e);
+                obase[(size_t)(S.label[r] - row_begin) * n + s_inlab[e]] = inblock_value(r, e);
             }
         }
         __syncthreads();   // the patch has read inlist / incount before the next chunk resets them
