@@ -320,7 +320,11 @@ def run_b200(args):
                        "sharding": "tree-batch index, no collective",
                        "l2": "inputs (8 GB) and outputs (24 GB) per step exceed the 126 MB L2"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_TREE * B,
+                         "traffic_source": "ncu --set full capture profiles/r01_decode_small_v5.summary.txt: "
+                                           "dram read+write 4.1337 GB per launch of 131072 trees = "
+                                           f"{NCU_DRAM_BYTES_PER_TREE} B/tree, scaled to this launch's {B} trees",
+                         "peak_source": peak_src,
                          "kernel": "decode_small_kernel<int64, ancestry>",
                          "algorithmic_bytes_per_tree": 4 * K * 8,
                          "note": "issue/latency-bound integer kernel (SURVEY 7 hard part 1); HBM fraction reported as required"},
@@ -389,8 +393,16 @@ def bench_cophenetic(torch, lib, device, rank, world, peak, args):
     res["fill_ceiling_gbs"] = rows * n * 8 / (fill_ms * 1e-3) / 1e9
     res["roofline"] = {"bound": "hbm", "achieved": res["fp64_branch_lengths"]["achieved_gbs"], "peak": peak,
                        "unit": "GB/s", "frac": res["fp64_branch_lengths"]["achieved_gbs"] / peak,
-                       "kernel": "rows_kernel<fp64>", "algorithmic_bytes": rows * n * 8}
+                       "kernel": "rows_kernel<fp64>", "algorithmic_bytes": rows * n * 8,
+                       "traffic": int(34.317283e9 * rows / n),
+                       "traffic_source": "ncu --set full, profiles/r01_rows_full_fp64_v5.summary.txt: 34.300 GB written "
+                                         "+ 0.017 GB read for all 65536 rows, scaled to this rank's rows"}
     return res
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of decode_small_kernel<int64, ancestry> per tree
+# (profiles/r01_decode_small_v5.summary.txt: (1.048728 + 3.084973) GB / 131072 trees)
+NCU_DRAM_BYTES_PER_TREE = 31538
 
 
 def main():
