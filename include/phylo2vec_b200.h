@@ -119,6 +119,31 @@ int p2v_cophenetic_rows_batch(void *workspace, size_t workspace_bytes, int64_t B
                               int weighted, int64_t row_begin, int64_t row_end, double *out,
                               p2v_stream_t stream);
 
+/* ---- variance-covariance matrix and node depths (the path's first "next" row) ----
+ * vcv replaces vector::graph::_vcv / vcv (vector/graph.rs:211-282) and matrix::graph::vcv
+ * (matrix/graph.rs:61-64); PyO3 entry point vcv (py-phylo2vec/src/lib.rs:166-172), Python
+ * phylo2vec.stats.cov (stats/nodewise.py:55-71).  out[l][r] = depth of the node where leaves l
+ * and r meet, diagonal = depth of the leaf; rows [row_begin,row_end) of every tree's n x n
+ * float64 matrix to out (B, row_end-row_begin, n).  k = 0 is the reference's assert:
+ * P2V_ERR_INVALID_ARG.  Same workspace as the distances (p2v_cophenetic_workspace_bytes);
+ * p2v_vcv_rows_batch emits row blocks from a workspace prepared by
+ * p2v_cophenetic_prepare_batch(unrooted = 0). */
+int p2v_vcv_batch(const void *v, int idx_bytes, const double *bls, int64_t B, int64_t k,
+                  int64_t row_begin, int64_t row_end, double *out, int32_t *status, void *workspace,
+                  size_t workspace_bytes, p2v_stream_t stream);
+int p2v_vcv_matrix_batch(const double *matrix, int64_t B, int64_t k, int64_t row_begin, int64_t row_end,
+                         double *out, int32_t *status, void *workspace, size_t workspace_bytes,
+                         p2v_stream_t stream);
+int p2v_vcv_rows_batch(void *workspace, size_t workspace_bytes, int64_t B, int64_t k, int weighted,
+                       int64_t row_begin, int64_t row_end, double *out, p2v_stream_t stream);
+/* node depths replace vector::ops::_get_node_depths (vector/ops.rs:201-233) and matrix::ops::
+ * get_node_depths (matrix/ops.rs:42-45); PyO3 get_node_depths (py-phylo2vec/src/lib.rs:281-287).
+ * out (B, 2k+1) float64: distance from the root to node i, root (2k) = 0.
+ * idx_bytes 0 = (k,3) float64 matrix input, 4/8 = index vector with optional bls. */
+int p2v_node_depths_batch(const void *v_or_matrix, int idx_bytes, const double *bls, int64_t B, int64_t k,
+                          double *out, int32_t *status, void *workspace, size_t workspace_bytes,
+                          p2v_stream_t stream);
+
 /* ---- host-buffer entry points (H2D + kernels + D2H inside the call) ------ */
 int p2v_to_pairs_host(const void *v, int idx_bytes, int64_t B, int64_t k, void *pairs, int32_t *status);
 int p2v_to_ancestry_host(const void *v, int idx_bytes, int64_t B, int64_t k, void *ancestry, int32_t *status);
@@ -131,6 +156,13 @@ int p2v_cophenetic_host(const void *v, int idx_bytes, const double *bls, int64_t
                         int unrooted, int64_t row_begin, int64_t row_end, double *out, int32_t *status);
 int p2v_cophenetic_matrix_host(const double *matrix, int64_t B, int64_t k, int unrooted,
                                int64_t row_begin, int64_t row_end, double *out, int32_t *status);
+
+int p2v_vcv_host(const void *v, int idx_bytes, const double *bls, int64_t B, int64_t k,
+                 int64_t row_begin, int64_t row_end, double *out, int32_t *status);
+int p2v_vcv_matrix_host(const double *matrix, int64_t B, int64_t k, int64_t row_begin, int64_t row_end,
+                        double *out, int32_t *status);
+int p2v_node_depths_host(const void *v_or_matrix, int idx_bytes, const double *bls, int64_t B, int64_t k,
+                         double *out, int32_t *status);
 
 /* The *_host entry points cache three streams and their device staging buffers per host
  * thread (they grow on demand).  This frees the calling thread's cache. */

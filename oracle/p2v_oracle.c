@@ -29,6 +29,7 @@
 
 #define P2VO_EBADINPUT (-2)
 #define P2VO_ENOMEM (-3)
+#define P2VO_EINVAL (-4)
 
 typedef int64_t i64;
 
@@ -548,6 +549,125 @@ int p2vo_cophenetic_matrix_literal(const double *m, i64 k, int unrooted, double 
     int rc = p2vo_cophenetic_literal(v, bls, k, unrooted, out);
     free(v); free(bls);
     return rc;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Variance-covariance matrix and node depths.             */
+/* ------------------------------------------------------------------------ */
+
+/* Literal restatement of vector/graph.rs:211-258 (_vcv) with
+ * get_descendants_and_edges :171-204: walking the edges from the root down,
+ * root_to_x[child] = root_to_x[parent] + bl (plain f64, that order), and the
+ * two leaf sets under a cherry's children get out[l][r] = out[r][l] =
+ * root_to_x[parent]; the diagonal is root_to_x[leaf].  The leaf sets are kept
+ * as linked lists (a BitSet in the reference; only membership matters).
+ * bls == NULL means unit lengths.  k == 0 is the reference's assert (:214-217)
+ * and returns P2VO_EINVAL.  out is (k+1)x(k+1). */
+int p2vo_vcv_literal(const i64 *v, const double *bls, i64 k, double *out) {
+    if (k <= 0) return P2VO_EINVAL;
+    i64 n = k + 1, N = 2 * k + 1;
+    i64 *edges = (i64 *)malloc(sizeof(i64) * 4 * (size_t)k);
+    i64 *head = (i64 *)malloc(sizeof(i64) * (size_t)N);
+    i64 *tail = (i64 *)malloc(sizeof(i64) * (size_t)N);
+    i64 *next = (i64 *)malloc(sizeof(i64) * (size_t)n);
+    double *root_to_x = (double *)calloc((size_t)N, sizeof(double));
+    if (!edges || !head || !tail || !next || !root_to_x) {
+        free(edges); free(head); free(tail); free(next); free(root_to_x); return P2VO_ENOMEM;
+    }
+    int rc = p2vo_to_edges(v, k, edges);
+    if (rc) { free(edges); free(head); free(tail); free(next); free(root_to_x); return rc; }
+    /* desc[leaf] = {leaf}; desc[parent] = desc[c1] U desc[c2] in cherry order.  The lists are
+     * concatenated destructively, so the sets are rebuilt top-down below from a second copy:
+     * keep, for every node, the [first,last] leaves of its list and cut nothing -- a child's
+     * list is a contiguous run of its parent's list. */
+    for (i64 i = 0; i < n; ++i) { head[i] = i; tail[i] = i; next[i] = -1; }
+    for (i64 r = 0; r < k; ++r) {
+        i64 c1 = edges[4 * r], c2 = edges[4 * r + 2], p = edges[4 * r + 1];
+        next[tail[c1]] = head[c2];
+        head[p] = head[c1]; tail[p] = tail[c2];
+    }
+    for (size_t i = 0; i < (size_t)n * (size_t)n; ++i) out[i] = 0.0;
+    for (i64 i = 2 * k - 1; i >= 0; --i) {          /* graph.rs:236-254 */
+        i64 ci = edges[2 * i], p = edges[2 * i + 1];
+        double var = root_to_x[p];
+        root_to_x[ci] = var + (bls ? bls[i] : 1.0);  /* bls[i/2][i%2] == flat bls[i] */
+        if (i % 2 == 1) {
+            i64 cj = edges[2 * (i - 1)];
+            for (i64 l = head[cj];; l = next[l]) {
+                for (i64 r = head[ci];; r = next[r]) {
+                    out[l * n + r] = var; out[r * n + l] = var;
+                    if (r == tail[ci]) break;
+                }
+                if (l == tail[cj]) break;
+            }
+        }
+    }
+    for (i64 i = 0; i < n; ++i) out[i * n + i] = root_to_x[i];   /* :257 */
+    free(edges); free(head); free(tail); free(next); free(root_to_x);
+    return 0;
+}
+
+/* matrix/graph.rs:61-64 */
+int p2vo_vcv_matrix_literal(const double *m, i64 k, double *out) {
+    if (k <= 0) return P2VO_EINVAL;
+    i64 *v = (i64 *)malloc(sizeof(i64) * (size_t)(k + 1));
+    double *bls = (double *)malloc(sizeof(double) * 2 * (size_t)(k + 1));
+    if (!v || !bls) { free(v); free(bls); return P2VO_ENOMEM; }
+    for (i64 r = 0; r < k; ++r) {
+        double x = m[3 * r];
+        v[r] = (x != x || x <= 0.0) ? 0 : (i64)x;
+        bls[2 * r] = m[3 * r + 1]; bls[2 * r + 1] = m[3 * r + 2];
+    }
+    int rc = p2vo_vcv_literal(v, bls, k, out);
+    free(v); free(bls);
+    return rc;
+}
+
+/* vector/ops.rs:201-233 (_get_node_depths): ancestry walked from the last row up,
+ * depths[child] = depths[parent] + bl.  out has 2k+1 entries. */
+int p2vo_node_depths(const i64 *v, const double *bls, i64 k, double *out) {
+    if (k == 0) { out[0] = 0.0; return 0; }
+    i64 *anc = (i64 *)malloc(sizeof(i64) * 3 * (size_t)k);
+    if (!anc) return P2VO_ENOMEM;
+    int rc = p2vo_to_ancestry(v, k, anc);
+    if (rc) { free(anc); return rc; }
+    for (i64 i = 0; i <= 2 * k; ++i) out[i] = 0.0;
+    for (i64 r = k - 1; r >= 0; --r) {
+        i64 c1 = anc[3 * r], c2 = anc[3 * r + 1], p = anc[3 * r + 2];
+        out[c1] = out[p] + (bls ? bls[2 * r] : 1.0);
+        out[c2] = out[p] + (bls ? bls[2 * r + 1] : 1.0);
+    }
+    free(anc);
+    return 0;
+}
+
+/* Rows [row_begin,row_end) of the vcv matrix for sizes where the full matrix is too large
+ * for the host: out[a][b] = node depth (as p2vo_node_depths) of the LCA of leaves a and b. */
+int p2vo_vcv_rows(const i64 *v, const double *bls, i64 k, i64 row_begin, i64 row_end, double *out) {
+    if (k <= 0) return P2VO_EINVAL;
+    i64 n = k + 1, N = 2 * k + 1;
+    i64 *anc = (i64 *)malloc(sizeof(i64) * 3 * (size_t)k);
+    i64 *par = (i64 *)malloc(sizeof(i64) * (size_t)N);
+    i64 *stamp = (i64 *)malloc(sizeof(i64) * (size_t)N);
+    double *depth = (double *)malloc(sizeof(double) * (size_t)N);
+    if (!anc || !par || !stamp || !depth) { free(anc); free(par); free(stamp); free(depth); return P2VO_ENOMEM; }
+    int rc = p2vo_to_ancestry(v, k, anc);
+    if (!rc) rc = p2vo_node_depths(v, bls, k, depth);
+    if (rc) { free(anc); free(par); free(stamp); free(depth); return rc; }
+    for (i64 r = 0; r < k; ++r) { par[anc[3 * r]] = anc[3 * r + 2]; par[anc[3 * r + 1]] = anc[3 * r + 2]; }
+    par[2 * k] = -1;
+    for (i64 x = 0; x < N; ++x) stamp[x] = -1;
+    for (i64 a = row_begin; a < row_end; ++a) {
+        for (i64 x = a; x >= 0; x = par[x]) stamp[x] = a;
+        double *row = &out[(a - row_begin) * n];
+        for (i64 b = 0; b < n; ++b) {
+            i64 x = b;
+            while (stamp[x] != a) x = par[x];
+            row[b] = depth[x];
+        }
+    }
+    free(anc); free(par); free(stamp); free(depth);
+    return 0;
 }
 
 /* ------------------------------------------------------------------------ */

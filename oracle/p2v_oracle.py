@@ -60,6 +60,12 @@ def lib() -> ctypes.CDLL:
         _lib.p2vo_cophenetic_rows.argtypes = [p, p, i64, ctypes.c_int, i64, i64, p]
         _lib.p2vo_cophenetic_matrix_literal.restype = ctypes.c_int
         _lib.p2vo_cophenetic_matrix_literal.argtypes = [p, i64, ctypes.c_int, p]
+        _lib.p2vo_vcv_literal.restype = ctypes.c_int
+        _lib.p2vo_vcv_literal.argtypes = [p, p, i64, p]
+        _lib.p2vo_vcv_rows.restype = ctypes.c_int
+        _lib.p2vo_vcv_rows.argtypes = [p, p, i64, i64, i64, p]
+        _lib.p2vo_node_depths.restype = ctypes.c_int
+        _lib.p2vo_node_depths.argtypes = [p, p, i64, p]
         _lib.p2vo_to_newick.restype = i64
         _lib.p2vo_to_newick.argtypes = [p, i64, ctypes.c_char_p, i64]
         _lib.p2vo_num_threads.restype = ctypes.c_int
@@ -218,6 +224,36 @@ def cophenetic_rows(tree, unrooted: bool, row_begin: int, row_end: int) -> np.nd
     out = np.zeros((row_end - row_begin, k + 1), dtype=np.float64)
     _raise(int(lib().p2vo_cophenetic_rows(_ptr(v), _ptr(bls), k, int(unrooted), row_begin, row_end,
                                           _ptr(out))), v)
+    return out
+
+
+def vcv(tree) -> np.ndarray:
+    """Literal vector/graph.rs:211-258 (+ matrix/graph.rs:61-64). (n,n) float64; k == 0 is the
+    reference's assert."""
+    v, bls = _split_tree(tree)
+    k = v.size
+    if k == 0:
+        raise AssertionError("Variance-covariance matrix not supported for trees with < 2 leaves.")
+    out = np.zeros((k + 1, k + 1), dtype=np.float64)
+    _raise(int(lib().p2vo_vcv_literal(_ptr(v), _ptr(bls), k, _ptr(out))), v)
+    return out
+
+
+def vcv_rows(tree, row_begin: int, row_end: int) -> np.ndarray:
+    """Rows of the vcv matrix as node depth of the LCA (for sizes where (n,n) is too large)."""
+    v, bls = _split_tree(tree)
+    k = v.size
+    out = np.zeros((row_end - row_begin, k + 1), dtype=np.float64)
+    _raise(int(lib().p2vo_vcv_rows(_ptr(v), _ptr(bls), k, row_begin, row_end, _ptr(out))), v)
+    return out
+
+
+def get_node_depths(tree) -> np.ndarray:
+    """vector/ops.rs:201-233 (+ matrix/ops.rs:42-45). (2k+1,) float64."""
+    v, bls = _split_tree(tree)
+    k = v.size
+    out = np.zeros(2 * k + 1, dtype=np.float64)
+    _raise(int(lib().p2vo_node_depths(_ptr(v), _ptr(bls), k, _ptr(out))), v)
     return out
 
 

@@ -12,18 +12,20 @@ from . import _capi
 from .base.ancestry import from_ancestry, to_ancestry
 from .base.edges import from_edges, to_edges
 from .base.pairs import from_pairs, to_pairs
-from .stats.nodewise import cophenetic_distances, pairwise_distances
-from .utils import check_v
+from .stats.nodewise import cophenetic_distances, cov, pairwise_distances
+from .utils.vector import check_v, get_node_depth, get_node_depths
 
 __all__ = [
     "to_ancestry", "to_pairs", "to_edges", "from_ancestry", "from_pairs", "from_edges",
-    "cophenetic_distances", "pairwise_distances", "check_v",
+    "cophenetic_distances", "pairwise_distances", "check_v", "cov", "get_node_depths", "get_node_depth",
     "to_ancestry_batch", "to_pairs_batch", "to_edges_batch", "from_ancestry_batch",
     "from_pairs_batch", "from_edges_batch", "cophenetic_distances_batch", "check_v_batch",
+    "vcv_batch", "node_depths_batch",
 ]
 
 _BATCH = {"to_ancestry_batch", "to_pairs_batch", "to_edges_batch", "from_ancestry_batch",
-          "from_pairs_batch", "from_edges_batch", "cophenetic_distances_batch", "check_v_batch"}
+          "from_pairs_batch", "from_edges_batch", "cophenetic_distances_batch", "check_v_batch",
+          "vcv_batch", "node_depths_batch"}
 
 
 def __getattr__(name):

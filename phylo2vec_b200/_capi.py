@@ -34,6 +34,13 @@ SIGNATURES = {
     "p2v_cophenetic_prepare_batch": (_int, [_vp, _int, _vp, _i64, _i64, _int, _vp, _vp, _sz, _vp]),
     "p2v_cophenetic_rows_batch": (_int, [_vp, _sz, _i64, _i64, _int, _i64, _i64, _vp, _vp]),
     "p2v_check_v_host": (_int, [_vp, _int, _i64, _i64, _vp]),
+    "p2v_vcv_batch": (_int, [_vp, _int, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "p2v_vcv_matrix_batch": (_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "p2v_vcv_rows_batch": (_int, [_vp, _sz, _i64, _i64, _int, _i64, _i64, _vp, _vp]),
+    "p2v_node_depths_batch": (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "p2v_vcv_host": (_int, [_vp, _int, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "p2v_vcv_matrix_host": (_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "p2v_node_depths_host": (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp]),
     "p2v_cophenetic_host": (_int, [_vp, _int, _vp, _i64, _i64, _int, _i64, _i64, _vp, _vp]),
     "p2v_cophenetic_matrix_host": (_int, [_vp, _i64, _i64, _int, _i64, _i64, _vp, _vp]),
     "p2v_host_release": (None, []),

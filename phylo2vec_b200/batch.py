@@ -179,6 +179,74 @@ def cophenetic_workspace_bytes(B: int, k: int) -> int:
     return int(_capi.load().p2v_cophenetic_workspace_bytes(B, k))
 
 
+def _tree_batch(trees, bls, what: str):
+    """PyTree dispatch of py-phylo2vec/src/lib.rs:20-24 lifted to batches."""
+    T = as_tensor(trees)
+    if not T.is_cuda:
+        raise ValueError(f"{what}: tensor must live on a CUDA device")
+    if T.dim() == 3:
+        if T.dtype != torch.float64 or T.shape[2] != 3:
+            raise TypeError("matrix input must be float64 with shape (B,k,3)")
+        if bls is not None:
+            raise ValueError("bls given together with matrix input")
+        return T.contiguous(), None, True
+    if T.dim() == 2:
+        T = _idx_tensor(T, 2, what)
+        B, k = T.shape
+        if bls is not None:
+            bls = as_tensor(bls)
+            if bls.dtype != torch.float64 or tuple(bls.shape) != (B, k, 2) or bls.device != T.device:
+                raise TypeError("bls must be float64 (B,k,2) on the same device")
+            bls = bls.contiguous()
+        return T, bls, False
+    raise TypeError("trees must be (B,k) integer vectors or (B,k,3) float64 matrices")
+
+
+def _out_f64(out, shape, device):
+    if out is None:
+        return torch.empty(shape, dtype=torch.float64, device=device)
+    out = as_tensor(out)
+    if tuple(out.shape) != shape or out.dtype != torch.float64 or not out.is_contiguous() or out.device != device:
+        raise ValueError(f"out must be a contiguous float64 {shape} tensor on {device}")
+    return out
+
+
+def _rows_call(what, trees, unrooted, rows, out, bls, status, check, workspace):
+    T, bls, is_matrix = _tree_batch(trees, bls, what)
+    lib = _capi.load()
+    B, k = T.shape[0], T.shape[1]
+    n = k + 1
+    if what == "vcv" and k == 0:    # vector/graph.rs:214-217
+        raise AssertionError("Variance-covariance matrix not supported for trees with < 2 leaves.")
+    r0, r1 = (0, n) if rows is None else (int(rows[0]), int(rows[1]))
+    if not (0 <= r0 <= r1 <= n):
+        raise ValueError(f"rows {rows} outside [0, {n}]")
+    out = _out_f64(out, (B, r1 - r0, n), T.device)
+    if status is None:
+        status = torch.empty(B, dtype=torch.int32, device=T.device)
+    need = lib.p2v_cophenetic_workspace_bytes(B, k)
+    with torch.cuda.device(T.device):
+        if workspace is None or workspace.numel() * workspace.element_size() < need:
+            workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=T.device)
+        wsb = workspace.numel() * workspace.element_size()
+        tail = (r0, r1, out.data_ptr(), status.data_ptr(), workspace.data_ptr(), wsb, _stream_ptr(T.device))
+        blp = 0 if bls is None else bls.data_ptr()
+        if what == "vcv":
+            if is_matrix:
+                rc = lib.p2v_vcv_matrix_batch(T.data_ptr(), B, k, *tail)
+            else:
+                rc = lib.p2v_vcv_batch(T.data_ptr(), T.element_size(), blp, B, k, *tail)
+        else:
+            if is_matrix:
+                rc = lib.p2v_cophenetic_matrix_batch(T.data_ptr(), B, k, int(bool(unrooted)), *tail)
+            else:
+                rc = lib.p2v_cophenetic_batch(T.data_ptr(), T.element_size(), blp, B, k, int(bool(unrooted)), *tail)
+    _capi.check(rc, what)
+    if check and bool(status.any()):
+        raise_for_status(status, T[..., 0].to(torch.int64) if is_matrix else T)
+    return out
+
+
 def cophenetic_distances_batch(trees, unrooted: bool = False, rows: Optional[Tuple[int, int]] = None,
                                out=None, bls=None, status=None, check: bool = True,
                                workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -189,40 +257,26 @@ def cophenetic_distances_batch(trees, unrooted: bool = False, rows: Optional[Tup
     py-phylo2vec/src/lib.rs:20-24,144-156 lifted to batches.  ``rows=(r0,r1)`` selects a
     row block of every matrix (how one huge tree is sharded over GPUs).
     Replaces vector::graph::_cophenetic_distances (phylo2vec/src/vector/graph.rs:20-90)."""
-    T = as_tensor(trees)
-    if not T.is_cuda:
-        raise ValueError("cophenetic_distances_batch: tensor must live on a CUDA device")
+    return _rows_call("cophenetic_distances", trees, unrooted, rows, out, bls, status, check, workspace)
+
+
+def vcv_batch(trees, rows: Optional[Tuple[int, int]] = None, out=None, bls=None, status=None,
+              check: bool = True, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Variance-covariance matrices of a batch of trees, float64 ``(B, rows, n)``: entry (l, r) is the
+    depth of the node where leaves l and r meet, the diagonal the depth of the leaf.  Same input
+    conventions as :func:`cophenetic_distances_batch`.
+    Replaces vector::graph::_vcv (phylo2vec/src/vector/graph.rs:211-282, matrix/graph.rs:61-64)."""
+    return _rows_call("vcv", trees, False, rows, out, bls, status, check, workspace)
+
+
+def node_depths_batch(trees, out=None, bls=None, status=None, check: bool = True,
+                      workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Depth (distance from the root) of every node of every tree, float64 ``(B, 2k+1)``.
+    Replaces vector::ops::_get_node_depths (phylo2vec/src/vector/ops.rs:201-233, matrix/ops.rs:42-45)."""
+    T, bls, is_matrix = _tree_batch(trees, bls, "get_node_depths")
     lib = _capi.load()
-    if T.dim() == 3:
-        if T.dtype != torch.float64 or T.shape[2] != 3:
-            raise TypeError("matrix input must be float64 with shape (B,k,3)")
-        if bls is not None:
-            raise ValueError("bls given together with matrix input")
-        T = T.contiguous()
-        B, k = T.shape[0], T.shape[1]
-        is_matrix = True
-    elif T.dim() == 2:
-        T = _idx_tensor(T, 2, "cophenetic_distances")
-        B, k = T.shape
-        is_matrix = False
-        if bls is not None:
-            bls = as_tensor(bls)
-            if bls.dtype != torch.float64 or tuple(bls.shape) != (B, k, 2) or bls.device != T.device:
-                raise TypeError("bls must be float64 (B,k,2) on the same device")
-            bls = bls.contiguous()
-    else:
-        raise TypeError("trees must be (B,k) integer vectors or (B,k,3) float64 matrices")
-    n = k + 1
-    r0, r1 = (0, n) if rows is None else (int(rows[0]), int(rows[1]))
-    if not (0 <= r0 <= r1 <= n):
-        raise ValueError(f"rows {rows} outside [0, {n}]")
-    shape = (B, r1 - r0, n)
-    if out is None:
-        out = torch.empty(shape, dtype=torch.float64, device=T.device)
-    else:
-        out = as_tensor(out)
-        if tuple(out.shape) != shape or out.dtype != torch.float64 or not out.is_contiguous() or out.device != T.device:
-            raise ValueError(f"out must be a contiguous float64 {shape} tensor on {T.device}")
+    B, k = T.shape[0], T.shape[1]
+    out = _out_f64(out, (B, 2 * k + 1), T.device)
     if status is None:
         status = torch.empty(B, dtype=torch.int32, device=T.device)
     need = lib.p2v_cophenetic_workspace_bytes(B, k)
@@ -230,15 +284,10 @@ def cophenetic_distances_batch(trees, unrooted: bool = False, rows: Optional[Tup
         if workspace is None or workspace.numel() * workspace.element_size() < need:
             workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=T.device)
         wsb = workspace.numel() * workspace.element_size()
-        if is_matrix:
-            rc = lib.p2v_cophenetic_matrix_batch(T.data_ptr(), B, k, int(bool(unrooted)), r0, r1, out.data_ptr(),
-                                                 status.data_ptr(), workspace.data_ptr(), wsb,
-                                                 _stream_ptr(T.device))
-        else:
-            rc = lib.p2v_cophenetic_batch(T.data_ptr(), T.element_size(), 0 if bls is None else bls.data_ptr(),
-                                          B, k, int(bool(unrooted)), r0, r1, out.data_ptr(), status.data_ptr(),
-                                          workspace.data_ptr(), wsb, _stream_ptr(T.device))
-    _capi.check(rc, "cophenetic_distances")
+        rc = lib.p2v_node_depths_batch(T.data_ptr(), 0 if is_matrix else T.element_size(),
+                                       0 if bls is None else bls.data_ptr(), B, k, out.data_ptr(),
+                                       status.data_ptr(), workspace.data_ptr(), wsb, _stream_ptr(T.device))
+    _capi.check(rc, "get_node_depths")
     if check and bool(status.any()):
         raise_for_status(status, T[..., 0].to(torch.int64) if is_matrix else T)
     return out

@@ -203,14 +203,21 @@ static int coph_check(const void* in, const double* out, int64_t B, int64_t k, i
 }
 
 // Host entry for distances.  in_a: v (idx_bytes 4/8) or the (k,3) matrix (idx_bytes 0); bls optional.
+// what: 0 distances, 1 variance-covariance, 2 node depths (out (B, 2k+1), rb/re ignored)
 static int coph_host(const void* in_a, int idx_bytes, const double* bls, int64_t B, int64_t k, int unrooted,
-                     int64_t rb, int64_t re, double* out, int32_t* status) {
+                     int64_t rb, int64_t re, double* out, int32_t* status, int what = 0) {
     int rc = coph_check(in_a, out, B, k, rb, re);
     if (rc) return rc;
-    if (B == 0 || re == rb) return P2V_OK;
+    if (B == 0 || (re == rb && what != 2)) return P2V_OK;
     const size_t a_bytes = (idx_bytes == 0) ? (size_t)k * 3 * sizeof(double) : (size_t)k * idx_bytes;
     const size_t b_bytes = bls ? (size_t)k * 2 * sizeof(double) : 0;
-    const size_t out_tree = (size_t)(re - rb) * (size_t)(k + 1) * sizeof(double);
+    const size_t out_tree = (what == 2) ? (size_t)(2 * k + 1) * sizeof(double)
+                                        : (size_t)(re - rb) * (size_t)(k + 1) * sizeof(double);
+    auto run = [&](void* din, const double* dbls, void* dout, int32_t* dst, int64_t nb, void* ws, size_t wsb,
+                   cudaStream_t st) {
+        if (what == 2) return launch_node_depths(din, idx_bytes, dbls, nb, k, (double*)dout, dst, ws, wsb, st);
+        return launch_cophenetic(din, idx_bytes, dbls, nb, k, unrooted, rb, re, (double*)dout, dst, ws, wsb, st, what);
+    };
     // one packed input record per tree: [a | bls]
     const size_t in_tree = a_bytes + b_bytes;
     // pack on the fly only when bls is present and separate; otherwise pass through
@@ -219,8 +226,7 @@ static int coph_host(const void* in_a, int idx_bytes, const double* bls, int64_t
             in_a, a_bytes, out, out_tree, status, B,
             [&](int64_t nb) { return cophenetic_workspace_bytes(nb, k); },
             [&](void* din, void* dout, int32_t* dst, int64_t nb, void* ws, size_t wsb, cudaStream_t st) {
-                return launch_cophenetic(din, idx_bytes, nullptr, nb, k, unrooted, rb, re, (double*)dout, dst,
-                                         ws, wsb, st);
+                return run(din, nullptr, dout, dst, nb, ws, wsb, st);
             });
     }
     // v and bls are separate host arrays: copy bls per chunk inside the launch lambda
@@ -242,8 +248,7 @@ static int coph_host(const void* in_a, int idx_bytes, const double* bls, int64_t
                                 cudaMemcpyHostToDevice, st);
             done += nb;
             if (e != cudaSuccess) return e;
-            return launch_cophenetic(din, idx_bytes, dbl[s], nb, k, unrooted, rb, re, (double*)dout, dst, ws,
-                                     wsb, st);
+            return run(din, dbl[s], dout, dst, nb, ws, wsb, st);
         });
     cudaDeviceSynchronize();
     cleanup();
@@ -335,6 +340,68 @@ int p2v_cophenetic_rows_batch(void* ws, size_t ws_bytes, int64_t B, int64_t k, i
     if (ws_bytes < cophenetic_workspace_bytes(B, k)) return fail(P2V_ERR_WORKSPACE, "cophenetic workspace too small");
     return from_cuda(launch_cophenetic_rows(ws, ws_bytes, B, k, weighted, row_begin, row_end, out,
                                             (cudaStream_t)stream), "cophenetic rows");
+}
+
+// ---- variance-covariance and node depths -----------------------------------------------
+static int vcv_check(int64_t k) {
+    if (k < 1) return fail(P2V_ERR_INVALID_ARG, "Variance-covariance matrix not supported for trees with < 2 leaves.");
+    return P2V_OK;
+}
+int p2v_vcv_batch(const void* v, int idx_bytes, const double* bls, int64_t B, int64_t k, int64_t row_begin,
+                  int64_t row_end, double* out, int32_t* status, void* ws, size_t ws_bytes, p2v_stream_t stream) {
+    if (idx_bytes != 4 && idx_bytes != 8) return fail(P2V_ERR_INVALID_ARG, "idx_bytes must be 4 or 8");
+    int rc = coph_check(v, out, B, k, row_begin, row_end);
+    if (!rc) rc = vcv_check(k);
+    if (rc) return rc;
+    if (ws_bytes < cophenetic_workspace_bytes(B, k)) return fail(P2V_ERR_WORKSPACE, "cophenetic workspace too small");
+    return from_cuda(launch_cophenetic(v, idx_bytes, bls, B, k, 0, row_begin, row_end, out, status, ws, ws_bytes,
+                                       (cudaStream_t)stream, 1), "vcv launch");
+}
+int p2v_vcv_matrix_batch(const double* m, int64_t B, int64_t k, int64_t row_begin, int64_t row_end, double* out,
+                         int32_t* status, void* ws, size_t ws_bytes, p2v_stream_t stream) {
+    int rc = coph_check(m, out, B, k, row_begin, row_end);
+    if (!rc) rc = vcv_check(k);
+    if (rc) return rc;
+    if (ws_bytes < cophenetic_workspace_bytes(B, k)) return fail(P2V_ERR_WORKSPACE, "cophenetic workspace too small");
+    return from_cuda(launch_cophenetic(m, 0, nullptr, B, k, 0, row_begin, row_end, out, status, ws, ws_bytes,
+                                       (cudaStream_t)stream, 1), "vcv launch");
+}
+int p2v_vcv_rows_batch(void* ws, size_t ws_bytes, int64_t B, int64_t k, int weighted, int64_t row_begin,
+                       int64_t row_end, double* out, p2v_stream_t stream) {
+    int rc = coph_check(ws, out, B, k, row_begin, row_end);
+    if (!rc) rc = vcv_check(k);
+    if (rc) return rc;
+    if (ws_bytes < cophenetic_workspace_bytes(B, k)) return fail(P2V_ERR_WORKSPACE, "cophenetic workspace too small");
+    return from_cuda(launch_cophenetic_rows(ws, ws_bytes, B, k, weighted, row_begin, row_end, out,
+                                            (cudaStream_t)stream, 1), "vcv rows");
+}
+int p2v_node_depths_batch(const void* v_or_matrix, int idx_bytes, const double* bls, int64_t B, int64_t k,
+                          double* out, int32_t* status, void* ws, size_t ws_bytes, p2v_stream_t stream) {
+    if (idx_bytes != 0 && idx_bytes != 4 && idx_bytes != 8) return fail(P2V_ERR_INVALID_ARG, "idx_bytes must be 0, 4 or 8");
+    if (B < 0 || k < 0) return fail(P2V_ERR_INVALID_ARG, "negative batch or length");
+    if (B > 0 && (!out || (k > 0 && !v_or_matrix))) return fail(P2V_ERR_INVALID_ARG, "null buffer");
+    if (k > LARGE_K_MAX) return fail(P2V_ERR_UNSUPPORTED, "k above the supported maximum (2^19)");
+    if (ws_bytes < cophenetic_workspace_bytes(B, k)) return fail(P2V_ERR_WORKSPACE, "cophenetic workspace too small");
+    return from_cuda(launch_node_depths(v_or_matrix, idx_bytes, bls, B, k, out, status, ws, ws_bytes,
+                                        (cudaStream_t)stream), "node depths launch");
+}
+int p2v_vcv_host(const void* v, int idx_bytes, const double* bls, int64_t B, int64_t k, int64_t row_begin,
+                 int64_t row_end, double* out, int32_t* status) {
+    if (idx_bytes != 4 && idx_bytes != 8) return fail(P2V_ERR_INVALID_ARG, "idx_bytes must be 4 or 8");
+    int rc = vcv_check(k);
+    if (rc) return rc;
+    return coph_host(v, idx_bytes, bls, B, k, 0, row_begin, row_end, out, status, 1);
+}
+int p2v_vcv_matrix_host(const double* m, int64_t B, int64_t k, int64_t row_begin, int64_t row_end, double* out,
+                        int32_t* status) {
+    int rc = vcv_check(k);
+    if (rc) return rc;
+    return coph_host(m, 0, nullptr, B, k, 0, row_begin, row_end, out, status, 1);
+}
+int p2v_node_depths_host(const void* v_or_matrix, int idx_bytes, const double* bls, int64_t B, int64_t k,
+                         double* out, int32_t* status) {
+    if (idx_bytes != 0 && idx_bytes != 4 && idx_bytes != 8) return fail(P2V_ERR_INVALID_ARG, "idx_bytes must be 0, 4 or 8");
+    return coph_host(v_or_matrix, idx_bytes, bls, B, k, 0, 0, k + 1, out, status, 2);
 }
 
 int p2v_to_pairs_host(const void* v, int idx_bytes, int64_t B, int64_t k, void* out, int32_t* status) {

@@ -164,17 +164,49 @@ __global__ void matrix_v_kernel(const double* __restrict__ m, int64_t count, int
 __global__ void tiny_sum_kernel(const double* __restrict__ bl, int64_t bl_tree_stride, int64_t B,
                                 double* __restrict__ sums) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < B; t += (int64_t)gridDim.x * blockDim.x)
-        sums[2 * t] = bl ? bl[t * bl_tree_stride] + bl[t * bl_tree_stride + 1] : 2.0;
+    {
+        sums[2 * t] = bl ? bl[t * bl_tree_stride] : 1.0;
+        sums[2 * t + 1] = bl ? bl[t * bl_tree_stride + 1] : 1.0;
+    }
 }
 
+// what = 1: variance-covariance (graph.rs:211-258 with k = 1: diag = the two lengths, 0 elsewhere)
 __global__ void tiny_kernel(const double* __restrict__ sums, int64_t B, int k, int64_t row_begin,
-                            int64_t row_end, double* __restrict__ out) {
+                            int64_t row_end, double* __restrict__ out, int what) {
     const int n = k + 1;
     const int64_t rows = row_end - row_begin;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < B; t += (int64_t)gridDim.x * blockDim.x) {
-        const double s = (k == 1) ? sums[2 * t] : 0.0;
+        const double s = (k == 1 && !what) ? sums[2 * t] + sums[2 * t + 1] : 0.0;
         for (int64_t r = row_begin; r < row_end; ++r)
-            for (int c = 0; c < n; ++c) out[(t * rows + (r - row_begin)) * n + c] = (r == c) ? 0.0 : s;
+            for (int c = 0; c < n; ++c) {
+                double x = (r == c) ? 0.0 : s;
+                if (what && r == c && k == 1) x = sums[2 * t + r];
+                out[(t * rows + (r - row_begin)) * n + c] = x;
+            }
+    }
+}
+
+// node depths (vector/ops.rs:201-233): depth of every node 0..2k from the prepared tables
+__global__ void node_depths_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int k,
+                                   int weighted, double* __restrict__ out, const int32_t* __restrict__ status) {
+    const int N = 2 * k + 1;
+    if (k < 2) {    // the table area holds the two root edge lengths (k == 1) or nothing (k == 0)
+        const double* sums = reinterpret_cast<const double*>(tab);
+        for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < B; t += (int64_t)gridDim.x * blockDim.x) {
+            if (status && status[t] != 0) continue;
+            if (k == 1) { out[3 * t] = sums[2 * t]; out[3 * t + 1] = sums[2 * t + 1]; out[3 * t + 2] = 0.0; }
+            else out[t] = 0.0;
+        }
+        return;
+    }
+    const CophLayout L = coph_layout(k);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B * N; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = i / N;
+        const int u = (int)(i - t * N);
+        if (status && status[t] != 0) continue;
+        const unsigned char* T = tab + (size_t)t * tab_stride;
+        out[i] = weighted ? reinterpret_cast<const double*>(T + L.jDH)[u]
+                          : (double)reinterpret_cast<const int*>(T + L.jDI)[u];
     }
 }
 
@@ -562,7 +594,10 @@ __device__ __forceinline__ unsigned long long shfl_down64(unsigned long long x, 
 
 constexpr int rows_min_blocks(int threads) { return threads >= 256 ? 3 : (threads == 128 ? 6 : (threads == 64 ? 10 : 16)); }
 
-template <bool TOPO, bool VEC2, int THREADS>
+// VCV: write depth(LCA) instead of the distance (vector/graph.rs:211-258: out[l][r] = root_to_x of
+// the node where l and r meet, diagonal = root_to_x[leaf]) -- the same candidates, min instead of
+// the three-term sum.
+template <bool TOPO, bool VEC2, int THREADS, bool VCV>
 __global__ void __launch_bounds__(THREADS, rows_min_blocks(THREADS))
 rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int k,
             int64_t row_begin, int64_t row_end, double* __restrict__ out,
@@ -783,11 +818,12 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
         const bool staged = nin <= nincap;
         auto inblock_value = [&](int r, int e) -> double {
             const int q = S.qpos[r], p = s_inlist[e];
-            if (p == q) return 0.0;
+            if (p == q) return VCV ? (TOPO ? int_to_f64(S.di[r]) : S.dhi[r]) : 0.0;
             const int a = min(p, q) + 1 - lo, b = max(p, q) - lo;     // sep offsets a..b
             const int lev = 31 - __clz(b - a + 1);
             const int x = s_st[lev * pmax + a], y = s_st[lev * pmax + b - (1 << lev) + 1];
             const int arg = (s_kblk[x] <= s_kblk[y]) ? x : y;
+            if (VCV) return TOPO ? int_to_f64(s_kblk[arg]) : s_sephi[arg];
             if (TOPO) return int_to_f64(S.di[r] + s_indi[e] - 2 * s_kblk[arg]);
             const dd m = dd{-s_sephi[arg], -s_seplo[arg]};
             const dd xa = dd_add(dd{S.dhi[r], S.dlo[r]}, m);
@@ -815,7 +851,7 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
                 for (int c = 0; c < ROW_CPT; ++c) {
                     const int a = side[c] ? a1 : a0;
                     const int u = side[c] ? u1 : u0;
-                    val[c] = int_to_f64(u + uji[c] + abs(a - bi[c]));
+                    val[c] = VCV ? int_to_f64(min(a, bi[c])) : int_to_f64(u + uji[c] + abs(a - bi[c]));
                 }
             } else {
                 const double a0h = S.ahi[0][r], a0l = S.alo[0][r], a1h = S.ahi[1][r], a1l = S.alo[1][r];
@@ -825,8 +861,13 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
                     const double ah = side[c] ? a1h : a0h;
                     const double al = side[c] ? a1l : a0l;
                     const double u = side[c] ? u1 : u0;
-                    const double m = __dadd_rn(__dadd_rn(ah, -bhi[c]), __dadd_rn(al, -blo[c]));
-                    val[c] = __dadd_rn(__dadd_rn(u, ujf[c]), fabs(m));
+                    if (VCV) {      // the shallower candidate; both lie on one root path
+                        const bool rowmin = ah < bhi[c] || (ah == bhi[c] && al < blo[c]);
+                        val[c] = rowmin ? ah : bhi[c];
+                    } else {
+                        const double m = __dadd_rn(__dadd_rn(ah, -bhi[c]), __dadd_rn(al, -blo[c]));
+                        val[c] = __dadd_rn(__dadd_rn(u, ujf[c]), fabs(m));
+                    }
                 }
             }
             if (warp_has_in) {           // warp-uniform
@@ -996,7 +1037,8 @@ cudaError_t launch_cophenetic_prepare(const void* v_or_matrix, int idx_bytes, co
 
 // Phase 3+4: rows [row_begin,row_end) of every prepared tree.
 cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t k, int weighted,
-                                   int64_t row_begin, int64_t row_end, double* out, cudaStream_t stream) {
+                                   int64_t row_begin, int64_t row_end, double* out, cudaStream_t stream,
+                                   int what) {
     if (B <= 0) return cudaSuccess;
     const int64_t n = k + 1;
     if (row_begin < 0 || row_end > n || row_begin > row_end) return cudaErrorInvalidValue;
@@ -1008,7 +1050,7 @@ cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t
     cudaError_t e;
     if (k < 2) {
         tiny_kernel<<<(int)((B + 255) / 256 < 1024 ? (B + 255) / 256 : 1024), 256, 0, stream>>>(
-            reinterpret_cast<const double*>(wsb + W.tab), B, (int)k, row_begin, row_end, out);
+            reinterpret_cast<const double*>(wsb + W.tab), B, (int)k, row_begin, row_end, out, what);
         count_launch();
         return cudaGetLastError();
     }
@@ -1046,7 +1088,7 @@ cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t
     const int grid = (int)(work < cap ? work : cap);
 #define P2V_ROWS4(T_, V_, TH_)                                                                        \
     do {                                                                                              \
-        auto kern = rows_kernel<T_, V_, TH_>;                                                         \
+        auto kern = what ? rows_kernel<T_, V_, TH_, true> : rows_kernel<T_, V_, TH_, false>;          \
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
         if (e != cudaSuccess) return e;                                                               \
         kern<<<grid, TH_, smem, stream>>>(tab, L.total, B, (int)k, row_begin, row_end, out, st, chunks, \
@@ -1071,13 +1113,30 @@ cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t
 cudaError_t launch_cophenetic(const void* v_or_matrix, int idx_bytes, const double* bls, int64_t B,
                               int64_t k, int unrooted, int64_t row_begin, int64_t row_end,
                               double* out, int32_t* status, void* ws, size_t ws_bytes,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, int what) {
     if (B <= 0) return cudaSuccess;
     if (row_begin < 0 || row_end > k + 1 || row_begin > row_end) return cudaErrorInvalidValue;
     cudaError_t e = launch_cophenetic_prepare(v_or_matrix, idx_bytes, bls, B, k, unrooted, status, ws, ws_bytes, stream);
     if (e != cudaSuccess) return e;
     const int weighted = (idx_bytes == 0) || (bls != nullptr);
-    return launch_cophenetic_rows(ws, ws_bytes, B, k, weighted, row_begin, row_end, out, stream);
+    return launch_cophenetic_rows(ws, ws_bytes, B, k, weighted, row_begin, row_end, out, stream, what);
+}
+
+// Depths of all 2k+1 nodes of every tree, (B, 2k+1) float64: prepare + one gather.
+cudaError_t launch_node_depths(const void* v_or_matrix, int idx_bytes, const double* bls, int64_t B, int64_t k,
+                               double* out, int32_t* status, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    cudaError_t e = launch_cophenetic_prepare(v_or_matrix, idx_bytes, bls, B, k, 0, status, ws, ws_bytes, stream);
+    if (e != cudaSuccess) return e;
+    const CophWs W = coph_ws(B, k);
+    unsigned char* wsb = static_cast<unsigned char*>(ws);
+    const int weighted = (idx_bytes == 0) || (bls != nullptr);
+    const int64_t want = (B * (2 * k + 1) + 255) / 256, cap = (int64_t)sm_count() * 16;
+    node_depths_kernel<<<(int)(want < cap ? want : cap), 256, 0, stream>>>(
+        wsb + W.tab, k >= 2 ? coph_layout(k).total : 16, B, (int)k, weighted, out,
+        reinterpret_cast<const int32_t*>(wsb + W.status));
+    count_launch();
+    return cudaGetLastError();
 }
 
 cudaError_t launch_fill_f64(double* out, int64_t count, double value, cudaStream_t stream) {

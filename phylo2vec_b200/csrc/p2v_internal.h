@@ -36,12 +36,16 @@ size_t cophenetic_workspace_bytes(int64_t B, int64_t k);
 cudaError_t launch_cophenetic(const void* v_or_matrix, int idx_bytes, const double* bls, int64_t B,
                               int64_t k, int unrooted, int64_t row_begin, int64_t row_end,
                               double* out, int32_t* status, void* ws, size_t ws_bytes,
-                              cudaStream_t stream);
+                              cudaStream_t stream, int what = 0 /* 0 distances, 1 variance-covariance */);
 cudaError_t launch_cophenetic_prepare(const void* v_or_matrix, int idx_bytes, const double* bls, int64_t B,
                                       int64_t k, int unrooted, int32_t* status, void* ws, size_t ws_bytes,
                                       cudaStream_t stream);
 cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t k, int weighted,
-                                   int64_t row_begin, int64_t row_end, double* out, cudaStream_t stream);
+                                   int64_t row_begin, int64_t row_end, double* out, cudaStream_t stream,
+                                   int what = 0);
+// depth of every node, (B, 2k+1) f64 (vector/ops.rs:201-233)
+cudaError_t launch_node_depths(const void* v_or_matrix, int idx_bytes, const double* bls, int64_t B, int64_t k,
+                               double* out, int32_t* status, void* ws, size_t ws_bytes, cudaStream_t stream);
 cudaError_t launch_fill_f64(double* out, int64_t count, double value, cudaStream_t stream);
 
 }  // namespace p2v

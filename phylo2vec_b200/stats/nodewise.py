@@ -1,4 +1,4 @@
-"""Node-wise distances; drop-in for py-phylo2vec/phylo2vec/stats/nodewise.py:10-52."""
+"""Node-wise distances and covariance; drop-in for py-phylo2vec/phylo2vec/stats/nodewise.py:10-71."""
 
 import numpy as np
 
@@ -44,3 +44,35 @@ NODEWISE_DISTANCES = {"cophenetic": cophenetic_distances}
 def pairwise_distances(tree, metric="cophenetic") -> np.ndarray:
     """py-phylo2vec/phylo2vec/stats/nodewise.py:31-52 (rooted only)."""
     return NODEWISE_DISTANCES[metric](tree)
+
+
+def cov(tree) -> np.ndarray:
+    """Variance-covariance matrix of a Phylo2Vec vector (unit lengths) or matrix: float64 (n,n),
+    like core.vcv (py-phylo2vec/src/lib.rs:166-172; phylo2vec/src/vector/graph.rs:211-282;
+    phylo2vec/src/matrix/graph.rs:61-64; py-phylo2vec/phylo2vec/stats/nodewise.py:55-71)."""
+    t = tree if isinstance(tree, np.ndarray) else np.asarray(tree)
+    lib = _capi.load()
+    status = np.zeros(1, dtype=np.int32)
+    if t.ndim == 2 and t.dtype == np.float64:
+        m = np.ascontiguousarray(t)
+        if m.shape[1] != 3:
+            raise TypeError("matrix input must have 3 columns [v, bl1, bl2]")
+        k, v = m.shape[0], m[:, 0].astype(np.int64)
+    elif t.ndim == 1:
+        v = as_index_array(t, 1, "vcv")
+        k, m = v.shape[0], None
+    else:
+        raise TypeError("tree must be a 1-D integer vector or a 2-D float64 matrix")
+    if k == 0:      # the reference's assert, vector/graph.rs:214-217
+        raise AssertionError("Variance-covariance matrix not supported for trees with < 2 leaves.")
+    out = np.zeros((k + 1, k + 1), dtype=np.float64)
+    if m is not None:
+        rc = lib.p2v_vcv_matrix_host(ptr(m), 1, k, 0, k + 1, ptr(out), ptr(status))
+    else:
+        rc = lib.p2v_vcv_host(ptr(v), 8, None, 1, k, 0, k + 1, ptr(out), ptr(status))
+    _capi.check(rc, "vcv")
+    raise_status(status, v)
+    return out
+
+
+vcv = cov

@@ -87,3 +87,34 @@ def test_cophenetic_matrix(goldens):
             assert np.allclose(got, exp, rtol=1e-5, atol=1e-8), g["src"]
         rows = O.cophenetic_rows(m, g["unrooted"], 0, exp.shape[0])
         assert np.allclose(rows, got, rtol=1e-14, atol=0), g["src"]
+
+
+def test_vcv_vector(goldens):
+    for g in goldens["vcv_vector"]:
+        v = np.array(g["v"], dtype=np.int64)
+        exp = np.array(g["c"], dtype=np.float64)
+        got = O.vcv(v)
+        assert got.dtype == np.float64 and np.array_equal(got, exp), g["src"]   # reference: assert_eq
+        assert np.array_equal(O.vcv_rows(v, 0, exp.shape[0]), exp), g["src"]
+    with pytest.raises(AssertionError):      # vector/graph.rs:636-641 (should_panic)
+        O.vcv(np.zeros(0, dtype=np.int64))
+
+
+def test_vcv_matrix(goldens):
+    for g in goldens["vcv_matrix"]:
+        m = np.array(g["m"], dtype=np.float64)
+        exp = np.array(g["c"], dtype=np.float64)
+        got = O.vcv(m)
+        assert np.allclose(got, exp, rtol=1e-5, atol=1e-8), g["src"]   # matrix/graph.rs:72-88
+        assert np.array_equal(O.vcv_rows(m, 0, exp.shape[0]), got), g["src"]
+
+
+def test_node_depths(goldens):
+    for g in goldens["node_depths"]:
+        t = np.array(g["tree"])
+        t = t.astype(np.float64) if t.ndim == 2 else t.astype(np.int64)
+        got = O.get_node_depths(t)
+        k = t.shape[0]
+        assert got.shape == (2 * k + 1,) and got[2 * k] == 0.0
+        for node, d in g["depths"].items():
+            assert abs(got[int(node)] - d) < 1e-10, (g["src"], node)   # vector/ops.rs:609-612
