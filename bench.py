@@ -380,6 +380,19 @@ def bench_cophenetic(torch, lib, device, rank, world, peak, args):
         res[label] = {"prepare_ms": prep_ms, "rows_ms": rows_ms, "achieved_gbs": gbs, "frac_of_peak": gbs / peak}
         if weighted:
             res["rows_ms"] = rows_ms
+        # the variance-covariance matrix from the same prepared tables
+        for _ in range(2):
+            rc = lib.p2v_vcv_rows_batch(ws.data_ptr(), need, 1, k, weighted, r0, r1, out.data_ptr(), stream.cuda_stream)
+            assert rc == 0, lib.p2v_last_error()
+        torch.cuda.synchronize()
+        e[2].record(stream)
+        for _ in range(reps):
+            lib.p2v_vcv_rows_batch(ws.data_ptr(), need, 1, k, weighted, r0, r1, out.data_ptr(), stream.cuda_stream)
+        e[3].record(stream)
+        torch.cuda.synchronize()
+        vcv_ms = e[2].elapsed_time(e[3]) / reps
+        res[label]["vcv_rows_ms"] = vcv_ms
+        res[label]["vcv_achieved_gbs"] = rows * n * 8 / (vcv_ms * 1e-3) / 1e9
     # write-only ceiling: a plain 128-bit streaming fill of the same bytes
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lib.p2v_fill_f64(out.data_ptr(), rows * n, 1.0, stream.cuda_stream)
