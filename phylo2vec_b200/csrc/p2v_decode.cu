@@ -22,6 +22,8 @@
 //    slot of every root's segment.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "p2v_common.cuh"
 #include "p2v_internal.h"
 
@@ -85,8 +87,30 @@ __device__ __forceinline__ void batch_rank_pair(const uint16_t* __restrict__ sv,
     R_hi = (uint32_t)__half2int_rz(__high2half(R)) - (uint32_t)lane;
 }
 
+// The same scan with 32-bit integers (SHFL.DOWN + ISETP + predicated IADD per step and batch) for
+// trees whose ranks do not fit the exact range of fp16.  rank_step uses SHFL's in-range predicate,
+// so there are no wrapped steps to take off.
+__device__ __forceinline__ void batch_rank_pair_int(const uint16_t* __restrict__ sv, int b, int k, int lane,
+                                                    uint32_t& R_hi, uint32_t& R_lo) {
+    const int t1 = b * 32 + lane, t0 = t1 - 32;
+    const uint32_t x1 = sv[t1];
+    const uint32_t x0 = (t0 >= 0) ? (uint32_t)sv[t0] : 0u;
+    const uint32_t i1 = (t1 < k) ? (x1 <= (uint32_t)t1 ? 0u : x1 - (uint32_t)t1) : BIG;
+    const uint32_t i0 = (t0 >= 0) ? (x0 <= (uint32_t)t0 ? 0u : x0 - (uint32_t)t0) : BIG;
+    uint32_t R1 = i1, R0 = i0;
+#pragma unroll
+    for (int d = 1; d < 32; ++d) {
+        rank_step(R1, i1, d);
+        rank_step(R0, i0, d);
+    }
+    R_hi = R1; R_lo = R0;
+}
+
 // WPL = free-mask words per lane: 1 for k <= 1024, 2 for k <= 2016 (the half2 rank scan is exact
-// for integers up to 2048 and overshoots the true rank by at most 31 before the correction).
+// for integers up to 2048 and overshoots the true rank by at most 31 before the correction);
+// 4 / 8 / 16 for mid-size trees (k <= 4096 / 8192 / 16384) with the integer rank scan and one
+// warp per CTA, so that the per-tree shared memory (6 bytes per leaf) still leaves several trees
+// in flight per SM.
 template <typename IdxT, int MODE, int WPL>
 __global__ void __launch_bounds__(SMALL_WARPS * 32)
 decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restrict__ out,
@@ -96,6 +120,7 @@ decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
     const int warp = threadIdx.x >> 5;
     const int KA = K + 32;
     const int narr = (MODE == MODE_PAIRS) ? 2 : 3;
+    const int nwarps = blockDim.x >> 5;
     uint16_t* base = reinterpret_cast<uint16_t*>(smem_raw) + (size_t)warp * (narr * KA + 64 * WPL);
     uint16_t* sv = base;            // v[t]                                   (by time)
     uint16_t* stime = sv + KA;      // element at slot s                      (by slot)
@@ -103,8 +128,8 @@ decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
     uint32_t* smask = reinterpret_cast<uint32_t*>(base + narr * KA);  // 32*WPL words of free-slot bits
     const int nb = K >> 5;
 
-    for (int64_t tree = (int64_t)blockIdx.x * SMALL_WARPS + warp; tree < B;
-         tree += (int64_t)gridDim.x * SMALL_WARPS) {
+    for (int64_t tree = (int64_t)blockIdx.x * nwarps + warp; tree < B;
+         tree += (int64_t)gridDim.x * nwarps) {
         const IdxT* vt = v + tree * k;
         // ---- A: load (8 loads in flight per lane), validate (check_v), narrow ----------
         int bad = -1;
@@ -147,10 +172,14 @@ decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
         // ---- B: slot assignment, walking time backwards, two batches per rank scan; the scan
         //         of the next pair is independent of the placement of the current one ------------
         uint32_t Rn_hi, Rn_lo;
-        batch_rank_pair(sv, nb - 1, k, lane, Rn_hi, Rn_lo);
+        if (WPL <= 2) batch_rank_pair(sv, nb - 1, k, lane, Rn_hi, Rn_lo);
+        else batch_rank_pair_int(sv, nb - 1, k, lane, Rn_hi, Rn_lo);
         for (int bp = nb - 1; bp >= 0; bp -= 2) {
             const uint32_t Rpair[2] = {Rn_hi, Rn_lo};
-            if (bp >= 2) batch_rank_pair(sv, bp - 2, k, lane, Rn_hi, Rn_lo);
+            if (bp >= 2) {
+                if (WPL <= 2) batch_rank_pair(sv, bp - 2, k, lane, Rn_hi, Rn_lo);
+                else batch_rank_pair_int(sv, bp - 2, k, lane, Rn_hi, Rn_lo);
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int b = bp - h;
@@ -171,13 +200,38 @@ decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
                 }
                 w &= 31;
                 uint32_t rr = R - __shfl_sync(FULL, incl - cnt, w);     // rank inside lane w's words
-                uint32_t wd = __shfl_sync(FULL, word[0], w);
-                uint32_t g = w * WPL;
+                uint32_t wd, g = w * WPL;
+                if (WPL <= 2) {
+                    wd = __shfl_sync(FULL, word[0], w);
 #pragma unroll
-                for (int j = 1; j < WPL; ++j) {
-                    const uint32_t nxt = __shfl_sync(FULL, word[j], w);
-                    const uint32_t c = __popc(wd);
-                    if (rr >= c) { rr -= c; wd = nxt; g = w * WPL + j; }
+                    for (int j = 1; j < WPL; ++j) {
+                        const uint32_t nxt = __shfl_sync(FULL, word[j], w);
+                        const uint32_t c = __popc(wd);
+                        if (rr >= c) { rr -= c; wd = nxt; g = w * WPL + j; }
+                    }
+                } else {
+                    // the words of lane w straight from shared memory (current: see the barrier below),
+                    // four at a time; first the group of four, then the word inside it
+                    const uint4* q4 = reinterpret_cast<const uint4*>(smask + w * WPL);
+                    uint4 q = q4[0];
+                    bool adv = true;
+#pragma unroll
+                    for (int jj = 1; jj < WPL / 4; ++jj) {
+                        const uint4 nq = q4[jj];
+                        const uint32_t c4 = __popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w);
+                        adv = adv && rr >= c4;
+                        if (adv) { rr -= c4; q = nq; g += 4; }
+                    }
+                    wd = q.x;
+                    uint32_t c = __popc(q.x);
+                    adv = rr >= c;
+                    if (adv) { rr -= c; wd = q.y; ++g; }
+                    c = __popc(q.y);
+                    adv = adv && rr >= c;
+                    if (adv) { rr -= c; wd = q.z; ++g; }
+                    c = __popc(q.z);
+                    adv = adv && rr >= c;
+                    if (adv) { rr -= c; wd = q.w; ++g; }
                 }
                 const uint32_t pos = nth_set_bit(wd, rr);
                 if (act) {
@@ -185,8 +239,16 @@ decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
                     atomicAnd(&smask[g], ~(1u << pos));
                 }
                 __syncwarp();
+                if (WPL <= 2) {
 #pragma unroll
-                for (int j = 0; j < WPL; ++j) word[j] = smask[lane * WPL + j];
+                    for (int j = 0; j < WPL; ++j) word[j] = smask[lane * WPL + j];
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < WPL / 4; ++jj) {
+                        const uint4 q = reinterpret_cast<const uint4*>(smask + lane * WPL)[jj];
+                        word[4 * jj] = q.x; word[4 * jj + 1] = q.y; word[4 * jj + 2] = q.z; word[4 * jj + 3] = q.w;
+                    }
+                }
             }
         }
 
@@ -481,6 +543,17 @@ constexpr int LARGE_THREADS_SINGLE = 512;
 constexpr int LARGE_THREADS_CLUSTER = 1024;
 constexpr int MID_THREADS = 256;
 constexpr int MID_K_MAX = 12287;           // work arrays as uint16 in shared memory up to here
+constexpr int WARP_K_MAX = 16384;          // warp-per-tree kernel for batches of trees up to here
+static int warp_k_max() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("P2V_DECODE_WARP_KMAX");      // tuning knob for benchmarks/sweep.py
+        v = e ? atoi(e) : WARP_K_MAX;
+        if (v > WARP_K_MAX) v = WARP_K_MAX;
+        if (v < SMALL_K_MAX) v = SMALL_K_MAX;
+    }
+    return v;
+}
 static size_t mid_smem_bytes(int64_t k) {
     const size_t K = ((size_t)k + 31) & ~(size_t)31;
     const size_t tbl = ((size_t)k + 2 + 7) & ~(size_t)7;
@@ -544,22 +617,30 @@ template <typename IdxT, int MODE>
 static cudaError_t launch_decode_t(const void* v, int64_t B, int64_t k, void* out, int32_t* status,
                                    void* ws, size_t ws_bytes, cudaStream_t stream, int64_t out_stride) {
     if (out_stride <= 0) out_stride = k * (MODE == MODE_PAIRS ? 2 : (MODE == MODE_ANCESTRY ? 3 : 4));
-    if (k <= SMALL_K_MAX) {
+    // few large trees go to the merge kernel (all SMs on one tree); batches of mid-size trees keep
+    // the warp-per-tree kernel, which does a fraction of the work per tree
+    const bool warp_per_tree = k <= SMALL_K_MAX || (k <= warp_k_max() && B * 4 > sm_count());
+    if (warp_per_tree) {
         const int K = (int)((k + 31) & ~31);
         const int narr = (MODE == MODE_PAIRS) ? 2 : 3;
-        const int wpl = (k <= 1024) ? 1 : 2;
-        const size_t smem = (size_t)SMALL_WARPS * ((size_t)narr * (K + 32) + 64 * wpl) * sizeof(uint16_t);
-        auto kern = (wpl == 1) ? decode_small_kernel<IdxT, MODE, 1> : decode_small_kernel<IdxT, MODE, 2>;
+        const int wpl = (k <= 1024) ? 1 : (k <= SMALL_K_MAX ? 2 : (k <= 4096 ? 4 : (k <= 8192 ? 8 : 16)));
+        const int warps = (wpl <= 2) ? SMALL_WARPS : 1;
+        const size_t smem = (size_t)warps * ((size_t)narr * (K + 32) + 64 * wpl) * sizeof(uint16_t);
+        auto kern = decode_small_kernel<IdxT, MODE, 1>;
+        if (wpl == 2) kern = decode_small_kernel<IdxT, MODE, 2>;
+        else if (wpl == 4) kern = decode_small_kernel<IdxT, MODE, 4>;
+        else if (wpl == 8) kern = decode_small_kernel<IdxT, MODE, 8>;
+        else if (wpl == 16) kern = decode_small_kernel<IdxT, MODE, 16>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SMALL_WARPS * 32, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
-        int64_t want = (B + SMALL_WARPS - 1) / SMALL_WARPS;
+        int64_t want = (B + warps - 1) / warps;
         int64_t cap = (int64_t)sm_count() * per_sm;
         int grid = (int)(want < cap ? want : cap);
-        kern<<<grid, SMALL_WARPS * 32, smem, stream>>>((const IdxT*)v, B, (int)k, (IdxT*)out, out_stride, status, K);
+        kern<<<grid, warps * 32, smem, stream>>>((const IdxT*)v, B, (int)k, (IdxT*)out, out_stride, status, K);
     } else if (k <= MID_K_MAX) {
         // mid-size trees: the same merge kernel with uint16 work arrays in shared memory
         const size_t smem = mid_smem_bytes(k);

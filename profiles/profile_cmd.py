@@ -27,6 +27,22 @@ if what in ("decode", "encode"):
     if what == "encode":
         for _ in range(3):
             p2v.from_ancestry_batch(anc, check=False)
+elif what.startswith("cophsmall"):
+    # small trees (BASELINE config C1 shape n=100): which kernel of the distance path costs what
+    n = int(what[9:] or 100)
+    B = max(1, (1 << 31) // (n * n * 8))
+    k = n - 1
+    lib = _capi.load()
+    hi = (2 * torch.arange(k, device=dev) + 1).to(torch.float64)
+    v = (torch.rand((B, k), generator=g, device=dev, dtype=torch.float64) * hi).to(torch.int64)
+    bls = torch.rand((B, k, 2), generator=g, device=dev, dtype=torch.float64)
+    out = torch.empty((B, n, n), dtype=torch.float64, device=dev)
+    need = lib.p2v_cophenetic_workspace_bytes(B, k)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    for blp in (bls.data_ptr(), 0):
+        for _ in range(2):
+            lib.p2v_cophenetic_batch(v.data_ptr(), 8, blp, B, k, 0, 0, n, out.data_ptr(), None, ws.data_ptr(), need, s)
 elif what == "rows2000":
     # BASELINE config C3 shape: batch of n=2000 trees, fp64 branch lengths
     n, B = 2000, 256

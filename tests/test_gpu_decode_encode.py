@@ -106,6 +106,35 @@ def test_decode_parity(p2v, n_leaves, dtype):
         assert np.array_equal(got.cpu().numpy().astype(np.int64), ref), (name, n_leaves)
 
 
+# Batches of mid-size trees stay on the warp-per-tree kernel (4 / 8 / 16 mask words per lane,
+# integer rank scan); a handful of such trees goes to the merge kernel (test_decode_parity above).
+MID_SIZES = [2017, 2049, 3000, 4096, 4097, 4098, 5000, 8192, 8193, 8194, 12289, 16384, 16385, 16386]
+
+
+@pytest.mark.parametrize("n_leaves", MID_SIZES)
+@pytest.mark.parametrize("dtype", [torch.int64, torch.int32])
+def test_decode_parity_mid_batches(p2v, n_leaves, dtype):
+    B = 48
+    V = sample_vectors(B, n_leaves, seed=7 * n_leaves)
+    V[1] = sample_vectors(1, n_leaves, seed=1, ordered=True)[0]
+    adv = list(adversarial_vectors(n_leaves).values())
+    V[2:2 + len(adv)] = np.stack(adv)
+    k = n_leaves - 1
+    Vd = dev(V, dtype)
+    for name, fn in (("to_pairs", p2v.to_pairs_batch), ("to_ancestry", p2v.to_ancestry_batch),
+                     ("to_edges", p2v.to_edges_batch)):
+        ref, st = O.batch(name, V, k)
+        assert not st.any()
+        got = fn(Vd)
+        assert np.array_equal(got.cpu().numpy().astype(np.int64), ref), (name, n_leaves)
+    # the same trees through the few-trees path give the same bits
+    assert torch.equal(p2v.to_ancestry_batch(Vd[:5]), p2v.to_ancestry_batch(Vd)[:5])
+    V[3, k // 2] = 2 * (k // 2) + 1
+    status = torch.zeros(B, dtype=torch.int32, device="cuda")
+    p2v.to_ancestry_batch(dev(V, dtype), status=status, check=False)
+    assert status[3].item() == k // 2 + 1 and int(status.count_nonzero()) == 1
+
+
 @pytest.mark.parametrize("n_leaves", SIZES)
 @pytest.mark.parametrize("dtype", [torch.int64, torch.int32])
 def test_encode_parity_and_round_trip(p2v, n_leaves, dtype):
