@@ -38,8 +38,9 @@
 //        same CTA from a sparse table over the block's separators.
 #include <cooperative_groups.h>
 
-#include "p2v_common.cuh"
-#include "p2v_internal.h"
+#include <cstdlib>
+
+#include "p2v_decode_warp.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -896,6 +897,231 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
     }
 }
 
+// ---- small trees: one CTA per tree, decode + tables + matrix in one kernel --------------------
+// For n <= 512 the general path above (five kernels with per-tree tables in global memory, CTAs of
+// 1024 threads) spends most of its time in per-tree fixed costs.  Here a CTA of 128 threads keeps
+// everything about one tree in shared memory:
+//   1. warp 0 decodes v to the ancestry (the warp-per-tree decoder of p2v_decode_warp.cuh);
+//   2. subtree leaf counts (rows are in child-before-parent order), then depths (int and
+//      double-double) and DFS offsets of every node by double-buffered pointer jumping;
+//   3. separators by DFS position, keyed (depth << 16 | position), and a sparse table over them;
+//   4. each warp takes rows i (label order): the LCA of (i, leaf at position p) is one O(1)
+//      range-minimum query, the row is built in DFS order in shared memory and leaves permuted to
+//      label order as coalesced 128-bit streaming stores.
+// Same arithmetic as the row kernel's in-block values: distances are (d_i - d_lca) + (d_j - d_lca),
+// each difference of double-doubles rounded once.
+constexpr int CS_N_MAX = 512;            // capacity of the fused kernel
+constexpr int CS_N_DEFAULT = 320;        // used up to here (above, the general kernels are faster)
+constexpr int CS_THREADS = 128;
+constexpr unsigned CS_NONE = 0xFFFFu;
+
+struct SmallLayout {
+    size_t dec, anc, ja, jd, jo, sz, pos, leaf_at, dipos, sepd, ddpos, jh, jl, st, rowbuf, total;
+    int levels;
+};
+__host__ __device__ inline SmallLayout small_layout(int k, bool topo) {
+    SmallLayout L;
+    const size_t n = (size_t)k + 1, N = 2 * (size_t)k + 1, K = ((size_t)k + 31) & ~(size_t)31;
+    L.levels = 1;                                       // floor(log2(n - 1)) + 1
+    while (((size_t)2 << (L.levels - 1)) <= (n > 1 ? n - 1 : 1)) ++L.levels;
+    size_t o = 0;
+    L.dec = o; o = al16(o + 2 * ((size_t)3 * (K + 32) + 64));
+    L.anc = o; o = al16(o + 4 * 3 * (size_t)k);
+    L.ja = o; o = al16(o + 2 * 2 * N);
+    L.jd = o; o = al16(o + 2 * 2 * N);
+    L.jo = o; o = al16(o + 2 * 2 * N);
+    L.sz = o; o = al16(o + 2 * N);
+    L.pos = o; o = al16(o + 2 * n);
+    L.leaf_at = o; o = al16(o + 2 * n);
+    L.dipos = o; o = al16(o + 2 * n);
+    L.sepd = o; o = al16(o + (topo ? 0 : 16 * (n + 1)));
+    L.ddpos = o; o = al16(o + (topo ? 0 : 16 * n));
+    // sparse table: level 0 (the separator keys) is written while the jumping buffers of the
+    // double-double depths are still being read; the upper levels and the row buffers are only
+    // written after that and live on top of those buffers
+    const size_t stn = (n + 1 + 3) & ~(size_t)3;        // entries per level, 16-byte multiple
+    L.st = o; o = o + 4 * stn;
+    const size_t a0 = o;
+    L.jh = o; o = al16(o + (topo ? 0 : 8 * 2 * N));
+    L.jl = o; o = al16(o + (topo ? 0 : 8 * 2 * N));
+    const size_t a1 = o;
+    o = a0 + 4 * stn * (size_t)(L.levels - 1);
+    o = al16(o);
+    L.rowbuf = o; o = al16(o + (size_t)(CS_THREADS / 32) * 8 * ((n + 1) & ~(size_t)1));
+    L.total = (o > a1 ? o : a1);
+    return L;
+}
+
+// double-double x - y for x >= y >= 0 on one root path, rounded to one double
+__device__ __forceinline__ double dd_sub_round(double xh, double xl, double yh, double yl) {
+    const dd s = two_sum(xh, -yh);
+    return __dadd_rn(s.hi, __dadd_rn(s.lo, __dadd_rn(xl, -yl)));
+}
+
+template <bool TOPO, bool VCV, bool VEC2>
+__global__ void __launch_bounds__(CS_THREADS)
+coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, int bl_stride, int64_t bl_tree_stride,
+                  int64_t B, int k, int unrooted, int64_t row_begin, int64_t row_end, double* __restrict__ out,
+                  int32_t* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ int s_bad;
+    const SmallLayout L = small_layout(k, TOPO);
+    const int n = k + 1, N = 2 * k + 1, K = (k + 31) & ~31, root = 2 * k;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = CS_THREADS / 32;
+    uint16_t* dec = reinterpret_cast<uint16_t*>(dyn + L.dec);
+    int* anc = reinterpret_cast<int*>(dyn + L.anc);
+    uint16_t* ja = reinterpret_cast<uint16_t*>(dyn + L.ja);
+    uint16_t* jd = reinterpret_cast<uint16_t*>(dyn + L.jd);
+    uint16_t* jo = reinterpret_cast<uint16_t*>(dyn + L.jo);
+    uint16_t* sz = reinterpret_cast<uint16_t*>(dyn + L.sz);
+    uint16_t* pos = reinterpret_cast<uint16_t*>(dyn + L.pos);
+    uint16_t* leaf_at = reinterpret_cast<uint16_t*>(dyn + L.leaf_at);
+    uint16_t* dipos = reinterpret_cast<uint16_t*>(dyn + L.dipos);
+    double2* sepd = reinterpret_cast<double2*>(dyn + L.sepd);
+    double2* ddpos = reinterpret_cast<double2*>(dyn + L.ddpos);
+    double* jh = reinterpret_cast<double*>(dyn + L.jh);
+    double* jl = reinterpret_cast<double*>(dyn + L.jl);
+    uint32_t* st = reinterpret_cast<uint32_t*>(dyn + L.st);
+    const int rb_stride = (n + 1) & ~1;
+    double* rowbuf = reinterpret_cast<double*>(dyn + L.rowbuf) + (size_t)warp * rb_stride;
+    const int64_t rows = row_end - row_begin;
+    const int stn = (n + 1 + 3) & ~3;             // entries per sparse-table level
+
+    for (int64_t tree = blockIdx.x; tree < B; tree += gridDim.x) {
+        __syncthreads();                          // the previous tree's readers are done
+        // ---- 1. decode ------------------------------------------------------------------
+        if (warp == 0) {
+            const int bad = decode_tree_warp<int, int, MODE_ANCESTRY, 1>(v32 + tree * k, k, K, anc, dec, lane);
+            if (lane == 0) { s_bad = bad; status[tree] = bad + 1; }
+        }
+        __syncthreads();
+        if (s_bad >= 0) continue;                 // uniform
+        // ---- 2. parents, edge weights, subtree sizes ----------------------------------------
+        const double* blt = bl ? bl + tree * bl_tree_stride : nullptr;
+        for (int x = tid; x < N; x += CS_THREADS) sz[x] = (x <= k) ? 1 : 0;
+        for (int r = tid; r < k; r += CS_THREADS) {
+            const int c1 = anc[3 * r], c2 = anc[3 * r + 1], p = k + 1 + r;
+            double b1 = 1.0, b2 = 1.0;
+            if (!TOPO) { b1 = blt[(size_t)r * bl_stride]; b2 = blt[(size_t)r * bl_stride + 1]; }
+            int w1 = 1, w2 = 1;
+            if (unrooted) {                       // graph.rs:46-50: the root edge to node 2k-1 has length 0
+                if (c1 == 2 * k - 1) { w1 = 0; b1 = 0.0; }
+                if (c2 == 2 * k - 1) { w2 = 0; b2 = 0.0; }
+            }
+            ja[c1] = (uint16_t)p; ja[c2] = (uint16_t)p;
+            jd[c1] = (uint16_t)w1; jd[c2] = (uint16_t)w2;
+            if (!TOPO) { jh[c1] = b1; jh[c2] = b2; jl[c1] = 0.0; jl[c2] = 0.0; }
+        }
+        if (tid == 0) {
+            ja[root] = (uint16_t)CS_NONE; jd[root] = 0; jo[root] = 0;
+            if (!TOPO) { jh[root] = 0.0; jl[root] = 0.0; }
+        }
+        __syncthreads();
+        if (tid == 0)                             // children come before parents in row order
+            for (int r = 0; r < k; ++r) sz[k + 1 + r] = (uint16_t)(sz[anc[3 * r]] + sz[anc[3 * r + 1]]);
+        __syncthreads();
+        for (int r = tid; r < k; r += CS_THREADS) {   // DFS offset of a node = sum over its root path
+            const int c1 = anc[3 * r], c2 = anc[3 * r + 1];
+            jo[c1] = 0; jo[c2] = sz[c1];
+        }
+        __syncthreads();
+        // ---- root-path sums by pointer jumping (buffers 0 / 1) ---------------------------------
+        int cur = 0;
+        for (;;) {
+            const uint16_t* a_in = ja + cur * N; uint16_t* a_out = ja + (cur ^ 1) * N;
+            const uint16_t* d_in = jd + cur * N; uint16_t* d_out = jd + (cur ^ 1) * N;
+            const uint16_t* o_in = jo + cur * N; uint16_t* o_out = jo + (cur ^ 1) * N;
+            const double* h_in = jh + cur * N; double* h_out = jh + (cur ^ 1) * N;
+            const double* l_in = jl + cur * N; double* l_out = jl + (cur ^ 1) * N;
+            int live = 0;
+            for (int x = tid; x < N; x += CS_THREADS) {
+                const unsigned a = a_in[x];
+                unsigned d = d_in[x], o = o_in[x], na = CS_NONE;
+                dd f = {0.0, 0.0};
+                if (!TOPO) f = dd{h_in[x], l_in[x]};
+                if (a != CS_NONE) {
+                    d += d_in[a]; o += o_in[a];
+                    if (!TOPO) f = dd_add(f, dd{h_in[a], l_in[a]});
+                    na = a_in[a];
+                    live |= (na != CS_NONE);
+                }
+                a_out[x] = (uint16_t)na; d_out[x] = (uint16_t)d; o_out[x] = (uint16_t)o;
+                if (!TOPO) { h_out[x] = f.hi; l_out[x] = f.lo; }
+            }
+            cur ^= 1;
+            if (!__syncthreads_or(live)) break;
+        }
+        // ---- 3. positions, separators, sparse table -------------------------------------------
+        {
+            const uint16_t* dres = jd + cur * N;
+            const uint16_t* ores = jo + cur * N;
+            const double* hres = jh + cur * N;
+            const double* lres = jl + cur * N;
+            for (int c = tid; c <= k; c += CS_THREADS) {
+                const int p = ores[c];
+                pos[c] = (uint16_t)p; leaf_at[p] = (uint16_t)c; dipos[p] = dres[c];
+                if (!TOPO) ddpos[p] = make_double2(hres[c], lres[c]);
+            }
+            for (int r = tid; r < k; r += CS_THREADS) {
+                const int u = k + 1 + r;
+                const int rp = ores[u] + sz[anc[3 * r]];          // first position of the second child
+                st[rp] = ((uint32_t)dres[u] << 16) | (uint32_t)rp;
+                if (!TOPO) sepd[rp] = make_double2(hres[u], lres[u]);
+            }
+            if (tid == 0) { st[0] = 0xFFFFFFFFu; st[n] = 0xFFFFFFFFu; }
+        }
+        __syncthreads();
+        for (int lev = 1; lev < L.levels; ++lev) {
+            const int half = 1 << (lev - 1);
+            for (int r = 1 + tid; r + (1 << lev) <= n; r += CS_THREADS)
+                st[lev * stn + r] = min(st[(lev - 1) * stn + r], st[(lev - 1) * stn + r + half]);
+            __syncthreads();
+        }
+        // ---- 4. rows ------------------------------------------------------------------------------
+        double* obase = out + (size_t)tree * rows * n;
+        for (int64_t i = row_begin + warp; i < row_end; i += NW) {
+            const int q = pos[i];
+            const int di = dipos[q];
+            double2 dq = make_double2(0.0, 0.0);
+            if (!TOPO) dq = ddpos[q];
+            for (int c0 = 0; c0 < n; c0 += 32) {
+                const int p = c0 + lane;
+                if (p < n) {
+                    double val;
+                    if (p == q) {
+                        val = VCV ? (TOPO ? int_to_f64(di) : dq.x) : 0.0;
+                    } else {
+                        const int a = min(p, q) + 1, b = max(p, q);
+                        const int lev = 31 - __clz(b - a + 1);
+                        const uint32_t m = min(st[lev * stn + a], st[lev * stn + b - (1 << lev) + 1]);
+                        if (TOPO) {
+                            const int dl = (int)(m >> 16);
+                            val = VCV ? int_to_f64(dl) : int_to_f64(di + (int)dipos[p] - 2 * dl);
+                        } else {
+                            const double2 s = sepd[m & 0xFFFFu];
+                            if (VCV) val = s.x;
+                            else {
+                                const double2 dj = ddpos[p];
+                                val = __dadd_rn(dd_sub_round(dq.x, dq.y, s.x, s.y), dd_sub_round(dj.x, dj.y, s.x, s.y));
+                            }
+                        }
+                    }
+                    rowbuf[p] = val;
+                }
+            }
+            __syncwarp();
+            double* orow = obase + (size_t)(i - row_begin) * n;
+            for (int j = 2 * lane; j < n; j += 64) {
+                const double a = rowbuf[pos[j]];
+                if (j + 1 < n) store2<VEC2>(orow + j, a, rowbuf[pos[j + 1]]);
+                else __stcs(orow + j, a);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 __global__ void fill_f64_kernel(double* __restrict__ out, int64_t count, double value) {
     const int64_t n2 = count >> 1;
     double2 v; v.x = value; v.y = value;
@@ -1110,12 +1336,84 @@ cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t
     return cudaGetLastError();
 }
 
+static int coph_small_n_max() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("P2V_COPH_SMALL_NMAX");       // tuning knob for benchmarks/sweep.py
+        v = e ? atoi(e) : CS_N_DEFAULT;
+        if (v > CS_N_MAX) v = CS_N_MAX;
+        if (v < 0) v = 0;
+    }
+    return v;
+}
+
+// One-shot path for small trees (3 <= n <= 512): input adapters + the fused kernel.
+static cudaError_t launch_cophenetic_small(const void* v_or_matrix, int idx_bytes, const double* bls, int64_t B,
+                                           int64_t k, int unrooted, int64_t row_begin, int64_t row_end, double* out,
+                                           int32_t* status, void* ws, size_t ws_bytes, cudaStream_t stream,
+                                           int what) {
+    const CophWs W = coph_ws(B, k);
+    if (!ws || ws_bytes < W.total) return cudaErrorInvalidValue;
+    unsigned char* wsb = static_cast<unsigned char*>(ws);
+    int32_t* st = reinterpret_cast<int32_t*>(wsb + W.status);
+    int* v32 = reinterpret_cast<int*>(wsb + W.v32);
+    const int grid1d = sm_count() * 8;
+    const double* bl = bls;
+    int bl_stride = 2;
+    int64_t bl_tree_stride = 2 * k;
+    const int* vin = static_cast<const int*>(v_or_matrix);
+    if (idx_bytes == 0) {
+        const double* m = static_cast<const double*>(v_or_matrix);
+        bl = m + 1; bl_stride = 3; bl_tree_stride = 3 * k;
+        matrix_v_kernel<<<grid1d, 256, 0, stream>>>(m, B * k, v32);
+        count_launch();
+        vin = v32;
+    } else if (idx_bytes == 8) {
+        narrow_v_kernel<<<grid1d, 256, 0, stream>>>(static_cast<const long long*>(v_or_matrix), B * k, v32);
+        count_launch();
+        vin = v32;
+    } else if (idx_bytes != 4) {
+        return cudaErrorInvalidValue;
+    }
+    const bool topo = (bl == nullptr);
+    const int64_t n = k + 1;
+    const size_t smem = small_layout((int)k, topo).total;
+    const bool vec2 = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    cudaError_t e = cudaSuccess;
+#define P2V_SMALL(T_, W_, V_)                                                                          \
+    do {                                                                                               \
+        auto kern = coph_small_kernel<T_, W_, V_>;                                                     \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+        if (e != cudaSuccess) return e;                                                                \
+        int per_sm = 0;                                                                                \
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CS_THREADS, smem);            \
+        if (e != cudaSuccess) return e;                                                                \
+        if (per_sm < 1) per_sm = 1;                                                                    \
+        const int64_t cap = (int64_t)sm_count() * per_sm;                                              \
+        kern<<<(int)(B < cap ? B : cap), CS_THREADS, smem, stream>>>(vin, bl, bl_stride, bl_tree_stride, B, (int)k, \
+                                                                     unrooted, row_begin, row_end, out, st);       \
+    } while (0)
+#define P2V_SMALL2(T_, W_) do { if (vec2) P2V_SMALL(T_, W_, true); else P2V_SMALL(T_, W_, false); } while (0)
+    if (topo) { if (what) P2V_SMALL2(true, true); else P2V_SMALL2(true, false); }
+    else { if (what) P2V_SMALL2(false, true); else P2V_SMALL2(false, false); }
+#undef P2V_SMALL2
+#undef P2V_SMALL
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (status) e = cudaMemcpyAsync(status, st, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, stream);
+    return e;
+}
+
 cudaError_t launch_cophenetic(const void* v_or_matrix, int idx_bytes, const double* bls, int64_t B,
                               int64_t k, int unrooted, int64_t row_begin, int64_t row_end,
                               double* out, int32_t* status, void* ws, size_t ws_bytes,
                               cudaStream_t stream, int what) {
     if (B <= 0) return cudaSuccess;
     if (row_begin < 0 || row_end > k + 1 || row_begin > row_end) return cudaErrorInvalidValue;
+    if (k >= 2 && k + 1 <= coph_small_n_max())
+        return launch_cophenetic_small(v_or_matrix, idx_bytes, bls, B, k, unrooted, row_begin, row_end, out, status,
+                                       ws, ws_bytes, stream, what);
     cudaError_t e = launch_cophenetic_prepare(v_or_matrix, idx_bytes, bls, B, k, unrooted, status, ws, ws_bytes, stream);
     if (e != cudaSuccess) return e;
     const int weighted = (idx_bytes == 0) || (bls != nullptr);

@@ -1,0 +1,266 @@
+// Warp-per-tree decode of one tree with all state in shared memory (sm_100a); shared by the
+// batched decode kernel (p2v_decode.cu) and the fused small-tree distance kernel
+// (p2v_cophenetic.cu).  See p2v_decode.cu for the formulation.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "p2v_common.cuh"
+#include "p2v_internal.h"
+
+namespace p2v {
+
+constexpr uint32_t BIG = 0x7FFFFFFFu;
+
+template <typename IdxT> struct Vec2;
+template <> struct Vec2<long long> { using type = longlong2; };
+template <> struct Vec2<int> { using type = int2; };
+template <typename IdxT> struct Vec4;
+template <> struct Vec4<int> { using type = int4; };
+
+template <typename IdxT>
+__device__ __forceinline__ void store_pair(IdxT* p, IdxT a, IdxT b) {
+    typename Vec2<IdxT>::type v;
+    v.x = a; v.y = b;
+    *reinterpret_cast<typename Vec2<IdxT>::type*>(p) = v;
+}
+
+template <typename IdxT, int MODE>
+__device__ __forceinline__ void store_row(IdxT* tree_out, int s, IdxT c1p, IdxT c2p, IdxT par) {
+    if (MODE == MODE_ANCESTRY) {
+        IdxT* o = tree_out + 3 * (size_t)s;
+        o[0] = c1p; o[1] = c2p; o[2] = par;
+    } else {  // MODE_EDGES: (c1p,par),(c2p,par)
+        IdxT* o = tree_out + 4 * (size_t)s;
+        store_pair<IdxT>(o, c1p, par);
+        store_pair<IdxT>(o + 2, c2p, par);
+    }
+}
+
+// --------------------------------------------------------------------------
+// k <= 1024: one warp per tree, all state in shared memory (uint16).
+// --------------------------------------------------------------------------
+
+// Rank of element t = 32b+lane among the elements [0, 32b+32) at the end of its batch.
+// Lane i scans the later lanes i+1.. in time order: R = ins_i; R += (ins_j <= R).  SHFL.DOWN past
+// lane 31 hands back the lane's own value, which always compares <= R, so the `lane` wrapped
+// steps are taken off at the end (they all come after the real ones).
+// Two batches (b and b-1) are scanned at once in the two halves of a half2: all values are
+// integers <= 1024, exact in fp16, so one 32-bit shuffle, one HSET2.LE and one HADD2 advance
+// both scans.  The 31 shuffles do not depend on R and are issued back to back.
+__device__ __forceinline__ void batch_rank_pair(const uint16_t* __restrict__ sv, int b, int k, int lane,
+                                                uint32_t& R_hi, uint32_t& R_lo) {
+    const int t1 = b * 32 + lane, t0 = t1 - 32;            // batch b and batch b-1 (t0 < 0 if b == 0)
+    const uint32_t x1 = sv[t1];
+    const uint32_t x0 = (t0 >= 0) ? (uint32_t)sv[t0] : 0u;
+    const __half inf = __ushort_as_half((unsigned short)0x7C00);
+    const __half i1 = (t1 < k) ? __uint2half_rn(x1 <= (uint32_t)t1 ? 0u : x1 - (uint32_t)t1) : inf;
+    const __half i0 = (t0 >= 0) ? __uint2half_rn(x0 <= (uint32_t)t0 ? 0u : x0 - (uint32_t)t0) : inf;
+    const __half2 ins = __halves2half2(i0, i1);
+    __half2 R = ins;
+#pragma unroll
+    for (int d = 1; d < 32; ++d) {
+        const __half2 y = __shfl_down_sync(FULL, ins, d);
+        R = __hadd2(R, __hle2(y, R));
+    }
+    R_lo = (uint32_t)__half2int_rz(__low2half(R)) - (uint32_t)lane;    // garbage for inactive lanes
+    R_hi = (uint32_t)__half2int_rz(__high2half(R)) - (uint32_t)lane;
+}
+
+// The same scan with 32-bit integers (SHFL.DOWN + ISETP + predicated IADD per step and batch) for
+// trees whose ranks do not fit the exact range of fp16.  rank_step uses SHFL's in-range predicate,
+// so there are no wrapped steps to take off.
+__device__ __forceinline__ void batch_rank_pair_int(const uint16_t* __restrict__ sv, int b, int k, int lane,
+                                                    uint32_t& R_hi, uint32_t& R_lo) {
+    const int t1 = b * 32 + lane, t0 = t1 - 32;
+    const uint32_t x1 = sv[t1];
+    const uint32_t x0 = (t0 >= 0) ? (uint32_t)sv[t0] : 0u;
+    const uint32_t i1 = (t1 < k) ? (x1 <= (uint32_t)t1 ? 0u : x1 - (uint32_t)t1) : BIG;
+    const uint32_t i0 = (t0 >= 0) ? (x0 <= (uint32_t)t0 ? 0u : x0 - (uint32_t)t0) : BIG;
+    uint32_t R1 = i1, R0 = i0;
+#pragma unroll
+    for (int d = 1; d < 32; ++d) {
+        rank_step(R1, i1, d);
+        rank_step(R0, i0, d);
+    }
+    R_hi = R1; R_lo = R0;
+}
+
+// uint16 entries of per-tree scratch the warp needs: sv, stime, (stbl), then the free-slot mask
+__host__ __device__ inline size_t decode_warp_scratch_u16(int K, int mode, int wpl) {
+    return (size_t)((mode == MODE_PAIRS) ? 2 : 3) * (K + 32) + 64 * wpl;
+}
+
+// Decodes v (k entries, K = k rounded up to 32) into `ot` (pairs / ancestry / edges rows of
+// OutT; any address space).  Returns -1, or the first index i with v[i] outside [0, 2i]
+// (check_v, vector/base.rs:50-67), in which case nothing is written.
+// WPL = free-mask words per lane: 1 for k <= 1024, 2 for k <= 2016 (the half2 rank scan is exact
+// for integers up to 2048 and overshoots the true rank by at most 31 before the correction);
+// 4 / 8 / 16 for mid-size trees (k <= 4096 / 8192 / 16384) with the integer rank scan.
+template <typename IdxT, typename OutT, int MODE, int WPL>
+__device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int k, int K, OutT* ot,
+                                                uint16_t* base, int lane) {
+    const int KA = K + 32;
+    const int narr = (MODE == MODE_PAIRS) ? 2 : 3;
+    uint16_t* sv = base;            // v[t]                                   (by time)
+    uint16_t* stime = sv + KA;      // element at slot s                      (by slot)
+    uint16_t* stbl = stime + KA;    // last row so far whose label is x       (by label)  [!PAIRS]
+    uint32_t* smask = reinterpret_cast<uint32_t*>(base + narr * KA);  // 32*WPL words of free-slot bits
+    const int nb = K >> 5;
+    // ---- A: load (8 loads in flight per lane), validate (check_v), narrow ----------
+    int bad = -1;
+    for (int b0 = 0; b0 < nb; b0 += 8) {
+        long long xs[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = (b0 + j) * 32 + lane;
+            xs[j] = (i < k) ? (long long)__ldg(vt + i) : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int i = (b0 + j) * 32 + lane;
+            if (b0 + j < nb) {
+                const bool ok = (i >= k) || (xs[j] >= 0 && xs[j] <= 2LL * i);
+                const unsigned bm = __ballot_sync(FULL, !ok);
+                if (bm && bad < 0) bad = (b0 + j) * 32 + __ffs(bm) - 1;
+                sv[i] = (uint16_t)xs[j];
+                if (MODE != MODE_PAIRS) stbl[i] = (uint16_t)NONE16;
+            }
+        }
+    }
+    if (MODE != MODE_PAIRS) stbl[K + lane] = (uint16_t)NONE16;
+    if (bad >= 0) return bad;
+    // free-slot mask: bit i of word g <-> slot 32g+i, 1 = free; lane l holds words l*WPL .. l*WPL+WPL-1
+    uint32_t word[WPL];
+#pragma unroll
+    for (int j = 0; j < WPL; ++j) {
+        const int g = lane * WPL + j;
+        word[j] = (g * 32 + 32 <= k) ? 0xFFFFFFFFu : (g * 32 >= k ? 0u : ((1u << (k - g * 32)) - 1u));
+        smask[g] = word[j];
+    }
+    __syncwarp();
+
+    // ---- B: slot assignment, walking time backwards, two batches per rank scan; the scan
+    //         of the next pair is independent of the placement of the current one ------------
+    uint32_t Rn_hi, Rn_lo;
+    if (WPL <= 2) batch_rank_pair(sv, nb - 1, k, lane, Rn_hi, Rn_lo);
+    else batch_rank_pair_int(sv, nb - 1, k, lane, Rn_hi, Rn_lo);
+    for (int bp = nb - 1; bp >= 0; bp -= 2) {
+        const uint32_t Rpair[2] = {Rn_hi, Rn_lo};
+        if (bp >= 2) {
+            if (WPL <= 2) batch_rank_pair(sv, bp - 2, k, lane, Rn_hi, Rn_lo);
+            else batch_rank_pair_int(sv, bp - 2, k, lane, Rn_hi, Rn_lo);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int b = bp - h;
+            if (b < 0) break;
+            const int t = b * 32 + lane;
+            const bool act = t < k;
+            const uint32_t R = Rpair[h];
+            // rank-select R among the free slots
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int j = 0; j < WPL; ++j) cnt += __popc(word[j]);
+            const uint32_t incl = warp_incl_scan(cnt, lane);
+            uint32_t w = 0;
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const uint32_t y = __shfl_sync(FULL, incl, (w + step - 1) & 31);
+                if (y <= R) w += step;
+            }
+            w &= 31;
+            uint32_t rr = R - __shfl_sync(FULL, incl - cnt, w);     // rank inside lane w's words
+            uint32_t wd, g = w * WPL;
+            if (WPL <= 2) {
+                wd = __shfl_sync(FULL, word[0], w);
+#pragma unroll
+                for (int j = 1; j < WPL; ++j) {
+                    const uint32_t nxt = __shfl_sync(FULL, word[j], w);
+                    const uint32_t c = __popc(wd);
+                    if (rr >= c) { rr -= c; wd = nxt; g = w * WPL + j; }
+                }
+            } else {
+                // the words of lane w straight from shared memory (current: see the barrier below),
+                // four at a time; first the group of four, then the word inside it
+                const uint4* q4 = reinterpret_cast<const uint4*>(smask + w * WPL);
+                uint4 q = q4[0];
+                bool adv = true;
+#pragma unroll
+                for (int jj = 1; jj < WPL / 4; ++jj) {
+                    const uint4 nq = q4[jj];
+                    const uint32_t c4 = __popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w);
+                    adv = adv && rr >= c4;
+                    if (adv) { rr -= c4; q = nq; g += 4; }
+                }
+                wd = q.x;
+                uint32_t c = __popc(q.x);
+                adv = rr >= c;
+                if (adv) { rr -= c; wd = q.y; ++g; }
+                c = __popc(q.y);
+                adv = adv && rr >= c;
+                if (adv) { rr -= c; wd = q.z; ++g; }
+                c = __popc(q.z);
+                adv = adv && rr >= c;
+                if (adv) { rr -= c; wd = q.w; ++g; }
+            }
+            const uint32_t pos = nth_set_bit(wd, rr);
+            if (act) {
+                stime[g * 32 + pos] = (uint16_t)t;
+                atomicAnd(&smask[g], ~(1u << pos));
+            }
+            __syncwarp();
+            if (WPL <= 2) {
+#pragma unroll
+                for (int j = 0; j < WPL; ++j) word[j] = smask[lane * WPL + j];
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < WPL / 4; ++jj) {
+                    const uint4 q = reinterpret_cast<const uint4*>(smask + lane * WPL)[jj];
+                    word[4 * jj] = q.x; word[4 * jj + 1] = q.y; word[4 * jj + 2] = q.z; word[4 * jj + 3] = q.w;
+                }
+            }
+        }
+    }
+
+    // ---- D: forward sweep over the slots, 32 rows at a time -------------------------------
+    // label of a row = v[t] of the nearest root (rank-0 insertion) at or left of it.
+    // Ancestry / edges: the reference's parents[] pass (convert.rs:174-185) only ever looks
+    // up the last earlier row with a given label; stbl keeps that row per label, same-batch
+    // occurrences are resolved with MATCH.ANY.
+    uint32_t lab_carry = 0;
+    for (int b = 0; b < nb; ++b) {
+        const int s = b * 32 + lane;
+        const bool act = s < k;
+        const uint32_t t = act ? stime[s] : 0u;
+        const uint32_t x = sv[t];
+        const bool root = act && x <= t;
+        const uint32_t m = __ballot_sync(FULL, root) & lanes_le(lane);
+        const int src = m ? 31 - __clz(m) : 0;
+        uint32_t lab = __shfl_sync(FULL, x, src);
+        if (!m) lab = lab_carry;
+        lab_carry = __shfl_sync(FULL, lab, 31);
+        if (MODE == MODE_PAIRS) {
+            if (act) store_pair<OutT>(ot + 2 * (size_t)s, (OutT)lab, (OutT)(t + 1));
+        } else {
+            const uint32_t peers = __match_any_sync(FULL, act ? lab : (0x10000u + lane));
+            uint32_t c1p = (uint32_t)(k + s);            // non-root: the previous row's parent
+            if (root) {
+                const uint32_t lower = peers & lanes_lt(lane);
+                const uint32_t cand = lower ? (uint32_t)(b * 32 + 31 - __clz(lower)) : (uint32_t)stbl[lab];
+                c1p = (cand != NONE16) ? (uint32_t)(k + 1) + cand : lab;
+            }
+            __syncwarp();
+            if (act && (peers & lanes_gt(lane)) == 0) stbl[lab] = (uint16_t)s;
+            __syncwarp();
+            if (act) {
+                const uint32_t q = stbl[t + 1];
+                const uint32_t c2p = (q != NONE16) ? (uint32_t)(k + 1) + q : t + 1;
+                store_row<OutT, MODE>(ot, s, (OutT)c1p, (OutT)c2p, (OutT)(k + 1 + s));
+            }
+        }
+    }
+    __syncwarp();
+    return -1;
+}
+
+}  // namespace p2v

@@ -212,3 +212,51 @@ def test_host_entry_point_matrix(p2v):
     rc = lib.p2v_cophenetic_host(V.ctypes.data_as(ctypes.c_void_p), 8, bls.ctypes.data_as(ctypes.c_void_p), 5,
                                  n - 1, 1, 0, n, out2.ctypes.data_as(ctypes.c_void_p), None)
     assert rc == 0 and rel_err(out2, O.cophenetic_batch(V, bls, True)) <= RTOL
+
+
+@pytest.mark.parametrize("n_leaves", [3, 5, 33, 100, 257, 512, 513])
+def test_two_phase_api_matches_one_shot(p2v, n_leaves):
+    """p2v_cophenetic_prepare_batch + p2v_cophenetic_rows_batch (the general kernels at every size)
+    against the one-shot call (the fused small-tree kernel up to n = 512)."""
+    from phylo2vec_b200 import _capi
+    lib = _capi.load()
+    B, k = 7, n_leaves - 1
+    V = sample_vectors(B, n_leaves, seed=3 * n_leaves)
+    bls = sample_bls(B, n_leaves, seed=3 * n_leaves)
+    Vd, bd = dev(V), dev(bls)
+    need = lib.p2v_cophenetic_workspace_bytes(B, k)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    for unrooted in (0, 1):
+        for weighted, blp in ((0, 0), (1, bd.data_ptr())):
+            out = torch.empty((B, n_leaves, n_leaves), dtype=torch.float64, device="cuda")
+            assert lib.p2v_cophenetic_prepare_batch(Vd.data_ptr(), 8, blp, B, k, unrooted, None, ws.data_ptr(), need, s) == 0
+            assert lib.p2v_cophenetic_rows_batch(ws.data_ptr(), need, B, k, weighted, 0, n_leaves, out.data_ptr(), s) == 0
+            one = p2v.cophenetic_distances_batch(Vd, unrooted=bool(unrooted), bls=bd if weighted else None)
+            ref = O.cophenetic_batch(V, bls if weighted else None, bool(unrooted))
+            if weighted:
+                assert rel_err(out.cpu().numpy(), ref) <= RTOL and rel_err(one.cpu().numpy(), ref) <= RTOL
+            else:
+                assert np.array_equal(out.cpu().numpy(), ref) and torch.equal(one, out)
+        # variance-covariance through both paths
+        out = torch.empty((B, n_leaves, n_leaves), dtype=torch.float64, device="cuda")
+        assert lib.p2v_cophenetic_prepare_batch(Vd.data_ptr(), 8, bd.data_ptr(), B, k, 0, None, ws.data_ptr(), need, s) == 0
+        assert lib.p2v_vcv_rows_batch(ws.data_ptr(), need, B, k, 1, 0, n_leaves, out.data_ptr(), s) == 0
+        assert torch.equal(out, p2v.vcv_batch(Vd, bls=bd))
+
+
+def test_small_tree_batches(p2v):
+    """Batches large enough to fill the GPU with the fused small-tree kernel (BASELINE.json
+    configs[0] shape n = 100), row blocks and odd sizes included."""
+    for n_leaves, B in ((100, 3000), (16, 5000), (101, 700), (300, 300), (512, 160)):
+        V = sample_vectors(B, n_leaves, seed=n_leaves + 1)
+        bls = sample_bls(B, n_leaves, seed=n_leaves + 1)
+        idx = np.linspace(0, B - 1, 12).astype(int)
+        got = p2v.cophenetic_distances_batch(dev(V)).cpu().numpy()
+        assert np.array_equal(got[idx], O.cophenetic_batch(V[idx], None))
+        assert np.array_equal(got, np.swapaxes(got, 1, 2))
+        got = p2v.cophenetic_distances_batch(dev(V), bls=dev(bls), unrooted=True).cpu().numpy()
+        assert rel_err(got[idx], O.cophenetic_batch(V[idx], bls[idx], True)) <= RTOL
+        r0, r1 = n_leaves // 3, n_leaves // 3 + 9
+        part = p2v.cophenetic_distances_batch(dev(V), bls=dev(bls), unrooted=True, rows=(r0, r1)).cpu().numpy()
+        assert np.array_equal(part, got[:, r0:r1])
