@@ -915,9 +915,12 @@ constexpr int CS_N_DEFAULT = 320;        // used up to here (above, the general 
 constexpr int CS_THREADS = 128;
 constexpr unsigned CS_NONE = 0xFFFFu;
 
+constexpr int CS_TREES = CS_THREADS / 32;       // trees decoded side by side (one per warp) per CTA pass
+
 struct SmallLayout {
-    size_t dec, anc, ja, jd, jo, sz, pos, leaf_at, dipos, sepd, ddpos, jh, jl, st, rowbuf, total;
-    int levels;
+    size_t dec, anc, ja, jd, dl, dr, nxt, cnt, pos, leaf_at, dipos, sepd, ddpos, jh, jl, st, rowbuf, total;
+    size_t dec_stride, anc_stride;
+    int levels, tpp;                    // tpp: trees decoded side by side per pass (one per warp)
 };
 __host__ __device__ inline SmallLayout small_layout(int k, bool topo) {
     SmallLayout L;
@@ -925,17 +928,23 @@ __host__ __device__ inline SmallLayout small_layout(int k, bool topo) {
     L.levels = 1;                                       // floor(log2(n - 1)) + 1
     while (((size_t)2 << (L.levels - 1)) <= (n > 1 ? n - 1 : 1)) ++L.levels;
     size_t o = 0;
-    L.dec = o; o = al16(o + 2 * ((size_t)3 * (K + 32) + 64));
-    L.anc = o; o = al16(o + 4 * 3 * (size_t)k);
+    L.dec_stride = al16(2 * ((size_t)3 * (K + 32) + 64));
+    L.anc_stride = al16(4 * 3 * (size_t)k);
+    L.tpp = (n <= 128) ? CS_TREES : 1;  // bigger trees: one at a time, fewer bytes per CTA
+    L.dec = o; o += L.tpp * L.dec_stride;
+    L.anc = o; o += L.tpp * L.anc_stride;
     L.ja = o; o = al16(o + 2 * 2 * N);
     L.jd = o; o = al16(o + 2 * 2 * N);
-    L.jo = o; o = al16(o + 2 * 2 * N);
-    L.sz = o; o = al16(o + 2 * N);
+    L.dl = o; o = al16(o + 2 * 2 * N);
+    L.dr = o; o = al16(o + 2 * 2 * N);
+    L.nxt = o; o = al16(o + 2 * 2 * n);
+    L.cnt = o; o = al16(o + 2 * 2 * n);
     L.pos = o; o = al16(o + 2 * n);
     L.leaf_at = o; o = al16(o + 2 * n);
-    L.dipos = o; o = al16(o + 2 * n);
+    const size_t P32 = (n + 31) & ~(size_t)31;          // positions padded to whole chunks of 32
+    L.dipos = o; o = al16(o + 2 * P32);
     L.sepd = o; o = al16(o + (topo ? 0 : 16 * (n + 1)));
-    L.ddpos = o; o = al16(o + (topo ? 0 : 16 * n));
+    L.ddpos = o; o = al16(o + (topo ? 0 : 16 * P32));
     // sparse table: level 0 (the separator keys) is written while the jumping buffers of the
     // double-double depths are still being read; the upper levels and the row buffers are only
     // written after that and live on top of those buffers
@@ -947,34 +956,35 @@ __host__ __device__ inline SmallLayout small_layout(int k, bool topo) {
     const size_t a1 = o;
     o = a0 + 4 * stn * (size_t)(L.levels - 1);
     o = al16(o);
-    L.rowbuf = o; o = al16(o + (size_t)(CS_THREADS / 32) * 8 * ((n + 1) & ~(size_t)1));
+    L.rowbuf = o; o = al16(o + (size_t)(CS_THREADS / 32) * 8 * P32);
     L.total = (o > a1 ? o : a1);
     return L;
 }
 
 // double-double x - y for x >= y >= 0 on one root path, rounded to one double
 __device__ __forceinline__ double dd_sub_round(double xh, double xl, double yh, double yl) {
-    const dd s = two_sum(xh, -yh);
-    return __dadd_rn(s.hi, __dadd_rn(s.lo, __dadd_rn(xl, -yl)));
+    const double s = __dadd_rn(xh, -yh);                     // Fast2Sum: xh >= yh >= 0
+    const double e = __dadd_rn(__dadd_rn(xh, -s), -yh);
+    return __dadd_rn(s, __dadd_rn(e, __dadd_rn(xl, -yl)));
 }
 
 template <bool TOPO, bool VCV, bool VEC2>
-__global__ void __launch_bounds__(CS_THREADS)
+__global__ void __launch_bounds__(CS_THREADS, 8)
 coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, int bl_stride, int64_t bl_tree_stride,
                   int64_t B, int k, int unrooted, int64_t row_begin, int64_t row_end, double* __restrict__ out,
                   int32_t* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char dyn[];
-    __shared__ int s_bad;
+    __shared__ int s_bad[CS_TREES];
     const SmallLayout L = small_layout(k, TOPO);
     const int n = k + 1, N = 2 * k + 1, K = (k + 31) & ~31, root = 2 * k;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = CS_THREADS / 32;
-    uint16_t* dec = reinterpret_cast<uint16_t*>(dyn + L.dec);
-    int* anc = reinterpret_cast<int*>(dyn + L.anc);
     uint16_t* ja = reinterpret_cast<uint16_t*>(dyn + L.ja);
     uint16_t* jd = reinterpret_cast<uint16_t*>(dyn + L.jd);
-    uint16_t* jo = reinterpret_cast<uint16_t*>(dyn + L.jo);
-    uint16_t* sz = reinterpret_cast<uint16_t*>(dyn + L.sz);
+    uint16_t* dl = reinterpret_cast<uint16_t*>(dyn + L.dl);
+    uint16_t* dr = reinterpret_cast<uint16_t*>(dyn + L.dr);
+    uint16_t* nxt = reinterpret_cast<uint16_t*>(dyn + L.nxt);
+    uint16_t* cnt = reinterpret_cast<uint16_t*>(dyn + L.cnt);
     uint16_t* pos = reinterpret_cast<uint16_t*>(dyn + L.pos);
     uint16_t* leaf_at = reinterpret_cast<uint16_t*>(dyn + L.leaf_at);
     uint16_t* dipos = reinterpret_cast<uint16_t*>(dyn + L.dipos);
@@ -983,23 +993,30 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
     double* jh = reinterpret_cast<double*>(dyn + L.jh);
     double* jl = reinterpret_cast<double*>(dyn + L.jl);
     uint32_t* st = reinterpret_cast<uint32_t*>(dyn + L.st);
-    const int rb_stride = (n + 1) & ~1;
+    const int rb_stride = (n + 31) & ~31;
     double* rowbuf = reinterpret_cast<double*>(dyn + L.rowbuf) + (size_t)warp * rb_stride;
     const int64_t rows = row_end - row_begin;
     const int stn = (n + 1 + 3) & ~3;             // entries per sparse-table level
 
-    for (int64_t tree = blockIdx.x; tree < B; tree += gridDim.x) {
-        __syncthreads();                          // the previous tree's readers are done
-        // ---- 1. decode ------------------------------------------------------------------
-        if (warp == 0) {
-            const int bad = decode_tree_warp<int, int, MODE_ANCESTRY, 1>(v32 + tree * k, k, K, anc, dec, lane);
-            if (lane == 0) { s_bad = bad; status[tree] = bad + 1; }
+    const int tpp = L.tpp;
+    for (int64_t base = (int64_t)blockIdx.x * tpp; base < B; base += (int64_t)gridDim.x * tpp) {
+        __syncthreads();                          // the previous pass's readers are done
+        // ---- 1. decode: every warp its own tree ---------------------------------------------
+        if (warp < tpp && base + warp < B) {
+            const int64_t tree = base + warp;
+            const int bad = decode_tree_warp<int, int, MODE_ANCESTRY, 1>(
+                v32 + tree * k, k, K, reinterpret_cast<int*>(dyn + L.anc + warp * L.anc_stride),
+                reinterpret_cast<uint16_t*>(dyn + L.dec + warp * L.dec_stride), lane);
+            if (lane == 0) { s_bad[warp] = bad; status[tree] = bad + 1; }
         }
         __syncthreads();
-        if (s_bad >= 0) continue;                 // uniform
-        // ---- 2. parents, edge weights, subtree sizes ----------------------------------------
+        for (int sub = 0; sub < tpp && base + sub < B; ++sub) {
+        if (s_bad[sub] >= 0) continue;            // uniform
+        const int64_t tree = base + sub;
+        const int* anc = reinterpret_cast<const int*>(dyn + L.anc + sub * L.anc_stride);
+        // ---- 2. parents, edge weights, first / last child pointers -----------------------------
         const double* blt = bl ? bl + tree * bl_tree_stride : nullptr;
-        for (int x = tid; x < N; x += CS_THREADS) sz[x] = (x <= k) ? 1 : 0;
+        for (int c = tid; c <= k; c += CS_THREADS) { dl[c] = (uint16_t)c; dr[c] = (uint16_t)c; }
         for (int r = tid; r < k; r += CS_THREADS) {
             const int c1 = anc[3 * r], c2 = anc[3 * r + 1], p = k + 1 + r;
             double b1 = 1.0, b2 = 1.0;
@@ -1011,63 +1028,85 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
             }
             ja[c1] = (uint16_t)p; ja[c2] = (uint16_t)p;
             jd[c1] = (uint16_t)w1; jd[c2] = (uint16_t)w2;
+            dl[p] = (uint16_t)c1; dr[p] = (uint16_t)c2;
             if (!TOPO) { jh[c1] = b1; jh[c2] = b2; jl[c1] = 0.0; jl[c2] = 0.0; }
         }
         if (tid == 0) {
-            ja[root] = (uint16_t)CS_NONE; jd[root] = 0; jo[root] = 0;
+            ja[root] = (uint16_t)CS_NONE; jd[root] = 0;
             if (!TOPO) { jh[root] = 0.0; jl[root] = 0.0; }
         }
         __syncthreads();
-        if (tid == 0)                             // children come before parents in row order
-            for (int r = 0; r < k; ++r) sz[k + 1 + r] = (uint16_t)(sz[anc[3 * r]] + sz[anc[3 * r + 1]]);
-        __syncthreads();
-        for (int r = tid; r < k; r += CS_THREADS) {   // DFS offset of a node = sum over its root path
-            const int c1 = anc[3 * r], c2 = anc[3 * r + 1];
-            jo[c1] = 0; jo[c2] = sz[c1];
-        }
-        __syncthreads();
-        // ---- root-path sums by pointer jumping (buffers 0 / 1) ---------------------------------
+        // ---- pointer jumping (buffers 0 / 1): root-path sums upwards, leftmost / rightmost leaf
+        //      downwards (leaves are fixed points) ---------------------------------------------------
         int cur = 0;
         for (;;) {
             const uint16_t* a_in = ja + cur * N; uint16_t* a_out = ja + (cur ^ 1) * N;
             const uint16_t* d_in = jd + cur * N; uint16_t* d_out = jd + (cur ^ 1) * N;
-            const uint16_t* o_in = jo + cur * N; uint16_t* o_out = jo + (cur ^ 1) * N;
+            const uint16_t* l_in = dl + cur * N; uint16_t* l_out = dl + (cur ^ 1) * N;
+            const uint16_t* r_in = dr + cur * N; uint16_t* r_out = dr + (cur ^ 1) * N;
             const double* h_in = jh + cur * N; double* h_out = jh + (cur ^ 1) * N;
-            const double* l_in = jl + cur * N; double* l_out = jl + (cur ^ 1) * N;
+            const double* w_in = jl + cur * N; double* w_out = jl + (cur ^ 1) * N;
             int live = 0;
             for (int x = tid; x < N; x += CS_THREADS) {
                 const unsigned a = a_in[x];
-                unsigned d = d_in[x], o = o_in[x], na = CS_NONE;
+                unsigned d = d_in[x], na = CS_NONE;
                 dd f = {0.0, 0.0};
-                if (!TOPO) f = dd{h_in[x], l_in[x]};
+                if (!TOPO) f = dd{h_in[x], w_in[x]};
                 if (a != CS_NONE) {
-                    d += d_in[a]; o += o_in[a];
-                    if (!TOPO) f = dd_add(f, dd{h_in[a], l_in[a]});
+                    d += d_in[a];
+                    if (!TOPO) f = dd_add(f, dd{h_in[a], w_in[a]});
                     na = a_in[a];
                     live |= (na != CS_NONE);
                 }
-                a_out[x] = (uint16_t)na; d_out[x] = (uint16_t)d; o_out[x] = (uint16_t)o;
-                if (!TOPO) { h_out[x] = f.hi; l_out[x] = f.lo; }
+                const unsigned nl = l_in[l_in[x]], nr = r_in[r_in[x]];
+                live |= ((int)nl > k) | ((int)nr > k);
+                a_out[x] = (uint16_t)na; d_out[x] = (uint16_t)d;
+                l_out[x] = (uint16_t)nl; r_out[x] = (uint16_t)nr;
+                if (!TOPO) { h_out[x] = f.hi; w_out[x] = f.lo; }
             }
             cur ^= 1;
             if (!__syncthreads_or(live)) break;
         }
+        const uint16_t* dres = jd + cur * N;
+        const uint16_t* lres = dl + cur * N;
+        const uint16_t* rres = dr + cur * N;
+        // ---- leaves as a linked list in DFS order: every internal node links the last leaf of its
+        //      first child's subtree to the first leaf of its second child's; ranking by jumping -----
+        for (int r = tid; r < k; r += CS_THREADS) {
+            const int a = rres[anc[3 * r]], b = lres[anc[3 * r + 1]];
+            nxt[a] = (uint16_t)b; cnt[a] = 1;
+        }
+        if (tid == 0) { const int e = rres[root]; nxt[e] = (uint16_t)CS_NONE; cnt[e] = 0; }
+        __syncthreads();
+        int lc = 0;
+        for (;;) {
+            const uint16_t* n_in = nxt + lc * n; uint16_t* n_out = nxt + (lc ^ 1) * n;
+            const uint16_t* c_in = cnt + lc * n; uint16_t* c_out = cnt + (lc ^ 1) * n;
+            int live = 0;
+            for (int x = tid; x < n; x += CS_THREADS) {
+                const unsigned a = n_in[x];
+                unsigned c = c_in[x], na = CS_NONE;
+                if (a != CS_NONE) { c += c_in[a]; na = n_in[a]; live |= (na != CS_NONE); }
+                n_out[x] = (uint16_t)na; c_out[x] = (uint16_t)c;
+            }
+            lc ^= 1;
+            if (!__syncthreads_or(live)) break;
+        }
         // ---- 3. positions, separators, sparse table -------------------------------------------
         {
-            const uint16_t* dres = jd + cur * N;
-            const uint16_t* ores = jo + cur * N;
+            const uint16_t* cres = cnt + lc * n;          // leaves after this one
             const double* hres = jh + cur * N;
-            const double* lres = jl + cur * N;
+            const double* wres = jl + cur * N;
             for (int c = tid; c <= k; c += CS_THREADS) {
-                const int p = ores[c];
+                const int p = k - cres[c];
                 pos[c] = (uint16_t)p; leaf_at[p] = (uint16_t)c; dipos[p] = dres[c];
-                if (!TOPO) ddpos[p] = make_double2(hres[c], lres[c]);
+                if (!TOPO) ddpos[p] = make_double2(hres[c], wres[c]);
             }
             for (int r = tid; r < k; r += CS_THREADS) {
                 const int u = k + 1 + r;
-                const int rp = ores[u] + sz[anc[3 * r]];          // first position of the second child
+                const int rp = k - cres[lres[anc[3 * r + 1]]];     // first position of the second child
                 st[rp] = ((uint32_t)dres[u] << 16) | (uint32_t)rp;
-                if (!TOPO) sepd[rp] = make_double2(hres[u], lres[u]);
+                if (!TOPO) sepd[rp] = make_double2(hres[u], wres[u]);
             }
             if (tid == 0) { st[0] = 0xFFFFFFFFu; st[n] = 0xFFFFFFFFu; }
         }
@@ -1079,46 +1118,53 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
             __syncthreads();
         }
         // ---- 4. rows ------------------------------------------------------------------------------
-        double* obase = out + (size_t)tree * rows * n;
-        for (int64_t i = row_begin + warp; i < row_end; i += NW) {
+        double* orow = out + ((size_t)tree * rows + warp) * n;
+        const int i_end = (int)row_end;
+        for (int i = (int)row_begin + warp; i < i_end; i += NW, orow += (size_t)NW * n) {
             const int q = pos[i];
             const int di = dipos[q];
             double2 dq = make_double2(0.0, 0.0);
             if (!TOPO) dq = ddpos[q];
+            // positions past n - 1 (last chunk) compute a harmless value into the padding of rowbuf
+#pragma unroll 1
             for (int c0 = 0; c0 < n; c0 += 32) {
                 const int p = c0 + lane;
-                if (p < n) {
-                    double val;
-                    if (p == q) {
-                        val = VCV ? (TOPO ? int_to_f64(di) : dq.x) : 0.0;
-                    } else {
-                        const int a = min(p, q) + 1, b = max(p, q);
-                        const int lev = 31 - __clz(b - a + 1);
-                        const uint32_t m = min(st[lev * stn + a], st[lev * stn + b - (1 << lev) + 1]);
-                        if (TOPO) {
-                            const int dl = (int)(m >> 16);
-                            val = VCV ? int_to_f64(dl) : int_to_f64(di + (int)dipos[p] - 2 * dl);
-                        } else {
-                            const double2 s = sepd[m & 0xFFFFu];
-                            if (VCV) val = s.x;
-                            else {
-                                const double2 dj = ddpos[p];
-                                val = __dadd_rn(dd_sub_round(dq.x, dq.y, s.x, s.y), dd_sub_round(dj.x, dj.y, s.x, s.y));
-                            }
-                        }
+                const int pc = min(p, k);
+                const int a = min(pc, q) + 1, b = max(pc, q);
+                const int lev = 31 - __clz(max(b - a + 1, 1));
+                const uint32_t m = min(st[lev * stn + a], st[lev * stn + b - (1 << lev) + 1]);
+                double val;
+                if (TOPO) {
+                    const int dlca = (int)(m >> 16);
+                    val = VCV ? int_to_f64(dlca) : int_to_f64(di + (int)dipos[p] - 2 * dlca);
+                    if (p == q) val = VCV ? int_to_f64(di) : 0.0;
+                } else {
+                    const double2 sd = sepd[m & 0xFFFFu];
+                    if (VCV) val = sd.x;
+                    else {
+                        const double2 dj = ddpos[p];
+                        val = __dadd_rn(dd_sub_round(dq.x, dq.y, sd.x, sd.y), dd_sub_round(dj.x, dj.y, sd.x, sd.y));
                     }
-                    rowbuf[p] = val;
+                    if (p == q) val = VCV ? dq.x : 0.0;
                 }
+                rowbuf[p] = val;
             }
             __syncwarp();
-            double* orow = obase + (size_t)(i - row_begin) * n;
-            for (int j = 2 * lane; j < n; j += 64) {
-                const double a = rowbuf[pos[j]];
-                if (j + 1 < n) store2<VEC2>(orow + j, a, rowbuf[pos[j + 1]]);
-                else __stcs(orow + j, a);
+            if (VEC2) {                           // n even: whole pairs, positions read two at a time
+#pragma unroll 1
+                for (int j = 2 * lane; j < n; j += 64) {
+                    const uint32_t pp = *reinterpret_cast<const uint32_t*>(pos + j);
+                    double2 v2;
+                    v2.x = rowbuf[pp & 0xFFFFu]; v2.y = rowbuf[pp >> 16];
+                    __stcs(reinterpret_cast<double2*>(orow + j), v2);
+                }
+            } else {
+                for (int j = lane; j < n; j += 32) __stcs(orow + j, rowbuf[pos[j]]);
             }
             __syncwarp();
         }
+        __syncthreads();                          // rows done before the next tree's tables are built
+        }  // sub
     }
 }
 
@@ -1377,7 +1423,9 @@ static cudaError_t launch_cophenetic_small(const void* v_or_matrix, int idx_byte
     }
     const bool topo = (bl == nullptr);
     const int64_t n = k + 1;
-    const size_t smem = small_layout((int)k, topo).total;
+    const SmallLayout SL = small_layout((int)k, topo);
+    const size_t smem = SL.total;
+    const int tpp = SL.tpp;
     const bool vec2 = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     cudaError_t e = cudaSuccess;
 #define P2V_SMALL(T_, W_, V_)                                                                          \
@@ -1389,8 +1437,8 @@ static cudaError_t launch_cophenetic_small(const void* v_or_matrix, int idx_byte
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, CS_THREADS, smem);            \
         if (e != cudaSuccess) return e;                                                                \
         if (per_sm < 1) per_sm = 1;                                                                    \
-        const int64_t cap = (int64_t)sm_count() * per_sm;                                              \
-        kern<<<(int)(B < cap ? B : cap), CS_THREADS, smem, stream>>>(vin, bl, bl_stride, bl_tree_stride, B, (int)k, \
+        const int64_t cap = (int64_t)sm_count() * per_sm, want = (B + tpp - 1) / tpp;                  \
+        kern<<<(int)(want < cap ? want : cap), CS_THREADS, smem, stream>>>(vin, bl, bl_stride, bl_tree_stride, B, (int)k, \
                                                                      unrooted, row_begin, row_end, out, st);       \
     } while (0)
 #define P2V_SMALL2(T_, W_) do { if (vec2) P2V_SMALL(T_, W_, true); else P2V_SMALL(T_, W_, false); } while (0)

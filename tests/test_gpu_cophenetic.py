@@ -259,4 +259,8 @@ def test_small_tree_batches(p2v):
         assert rel_err(got[idx], O.cophenetic_batch(V[idx], bls[idx], True)) <= RTOL
         r0, r1 = n_leaves // 3, n_leaves // 3 + 9
         part = p2v.cophenetic_distances_batch(dev(V), bls=dev(bls), unrooted=True, rows=(r0, r1)).cpu().numpy()
-        assert np.array_equal(part, got[:, r0:r1])
+        # the fused kernel computes every entry on its own; above its size limit the general kernels
+        # agree to the last bits only (DESIGN.md "fp64 parity")
+        assert rel_err(part, got[:, r0:r1]) <= 1e-15
+        if n_leaves <= 256:
+            assert np.array_equal(part, got[:, r0:r1])
