@@ -37,6 +37,27 @@ __device__ __forceinline__ uint32_t nth_set_bit(uint32_t wd, uint32_t r) {
     return pos;
 }
 
+// The same through a 2 KB table in shared memory for the last three levels:
+// lut[byte * 8 + r] = position of the r-th set bit of `byte`.
+__device__ __forceinline__ void nth_bit_lut_init(uint8_t* lut, int tid, int nthreads) {
+    for (int e = tid; e < 2048; e += nthreads) {
+        uint32_t byte = (uint32_t)e >> 3, r = (uint32_t)e & 7u, pos = 0;
+        for (uint32_t i = 0; i < 8; ++i) {
+            if ((byte >> i) & 1u) {
+                if (r == 0) { pos = i; break; }
+                --r;
+            }
+        }
+        lut[e] = (uint8_t)pos;
+    }
+}
+__device__ __forceinline__ uint32_t nth_set_bit_lut(uint32_t wd, uint32_t r, const uint8_t* __restrict__ lut) {
+    uint32_t pos = 0, c;
+    c = __popc(wd & 0xFFFFu);          if (r >= c) { r -= c; pos = 16; }
+    c = __popc((wd >> pos) & 0xFFu);   if (r >= c) { r -= c; pos += 8; }
+    return pos + lut[(((wd >> pos) & 0xFFu) << 3) | (r & 7u)];
+}
+
 // One step of the in-batch rank scan: lane i looks at lane i+d (if it exists)
 // and bumps R when that later element was inserted at or before R.
 // SHFL.DOWN delivers the "source lane in range" predicate for free.

@@ -975,6 +975,8 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
                   int32_t* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int s_bad[CS_TREES];
+    __shared__ uint8_t s_lut[2048];
+    nth_bit_lut_init(s_lut, threadIdx.x, CS_THREADS);
     const SmallLayout L = small_layout(k, TOPO);
     const int n = k + 1, N = 2 * k + 1, K = (k + 31) & ~31, root = 2 * k;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1006,7 +1008,7 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
             const int64_t tree = base + warp;
             const int bad = decode_tree_warp<int, int, MODE_ANCESTRY, 1>(
                 v32 + tree * k, k, K, reinterpret_cast<int*>(dyn + L.anc + warp * L.anc_stride),
-                reinterpret_cast<uint16_t*>(dyn + L.dec + warp * L.dec_stride), lane);
+                reinterpret_cast<uint16_t*>(dyn + L.dec + warp * L.dec_stride), lane, s_lut);
             if (lane == 0) { s_bad[warp] = bad; status[tree] = bad + 1; }
         }
         __syncthreads();

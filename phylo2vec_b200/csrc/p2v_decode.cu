@@ -36,13 +36,16 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32)
 decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restrict__ out,
                     int64_t out_stride, int32_t* __restrict__ status, int K) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint8_t s_lut[2048];
+    nth_bit_lut_init(s_lut, threadIdx.x, blockDim.x);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
     uint16_t* base = reinterpret_cast<uint16_t*>(smem_raw) + (size_t)warp * decode_warp_scratch_u16(K, MODE, WPL);
     for (int64_t tree = (int64_t)blockIdx.x * nwarps + warp; tree < B;
          tree += (int64_t)gridDim.x * nwarps) {
-        const int bad = decode_tree_warp<IdxT, IdxT, MODE, WPL>(v + tree * k, k, K, out + tree * out_stride, base, lane);
+        const int bad = decode_tree_warp<IdxT, IdxT, MODE, WPL>(v + tree * k, k, K, out + tree * out_stride, base, lane, s_lut);
         if (lane == 0 && status) status[tree] = bad + 1;
     }
 }

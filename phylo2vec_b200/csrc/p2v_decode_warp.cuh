@@ -98,7 +98,7 @@ __host__ __device__ inline size_t decode_warp_scratch_u16(int K, int mode, int w
 // 4 / 8 / 16 for mid-size trees (k <= 4096 / 8192 / 16384) with the integer rank scan.
 template <typename IdxT, typename OutT, int MODE, int WPL>
 __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int k, int K, OutT* ot,
-                                                uint16_t* base, int lane) {
+                                                uint16_t* base, int lane, const uint8_t* __restrict__ lut) {
     const int KA = K + 32;
     const int narr = (MODE == MODE_PAIRS) ? 2 : 3;
     uint16_t* sv = base;            // v[t]                                   (by time)
@@ -107,7 +107,11 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
     uint32_t* smask = reinterpret_cast<uint32_t*>(base + narr * KA);  // 32*WPL words of free-slot bits
     const int nb = K >> 5;
     // ---- A: load (8 loads in flight per lane), validate (check_v), narrow ----------
-    int bad = -1;
+    if (MODE != MODE_PAIRS) {                   // "no row yet" for every label, 8 entries per store
+        uint4 ones; ones.x = ones.y = ones.z = ones.w = 0xFFFFFFFFu;
+        for (int i = lane * 8; i < KA; i += 256) *reinterpret_cast<uint4*>(stbl + i) = ones;
+    }
+    bool anybad = false;
     for (int b0 = 0; b0 < nb; b0 += 8) {
         long long xs[8];
 #pragma unroll
@@ -118,17 +122,18 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int i = (b0 + j) * 32 + lane;
-            if (b0 + j < nb) {
-                const bool ok = (i >= k) || (xs[j] >= 0 && xs[j] <= 2LL * i);
-                const unsigned bm = __ballot_sync(FULL, !ok);
-                if (bm && bad < 0) bad = (b0 + j) * 32 + __ffs(bm) - 1;
-                sv[i] = (uint16_t)xs[j];
-                if (MODE != MODE_PAIRS) stbl[i] = (uint16_t)NONE16;
-            }
+            anybad |= (unsigned long long)xs[j] > (unsigned long long)(2 * i);     // also catches negatives
+            if (b0 + j < nb) sv[i] = (uint16_t)xs[j];
         }
     }
-    if (MODE != MODE_PAIRS) stbl[K + lane] = (uint16_t)NONE16;
-    if (bad >= 0) return bad;
+    if (__any_sync(FULL, anybad)) {             // rare: find the first offending index
+        for (int b = 0; b < nb; ++b) {
+            const int i = b * 32 + lane;
+            const bool ok = (i >= k) || (unsigned long long)(long long)__ldg(vt + i) <= (unsigned long long)(2 * i);
+            const unsigned bm = __ballot_sync(FULL, !ok);
+            if (bm) return b * 32 + __ffs(bm) - 1;
+        }
+    }
     // free-slot mask: bit i of word g <-> slot 32g+i, 1 = free; lane l holds words l*WPL .. l*WPL+WPL-1
     uint32_t word[WPL];
 #pragma unroll
@@ -203,7 +208,7 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
                 adv = adv && rr >= c;
                 if (adv) { rr -= c; wd = q.w; ++g; }
             }
-            const uint32_t pos = nth_set_bit(wd, rr);
+            const uint32_t pos = nth_set_bit_lut(wd, rr, lut);    // lut: nth_bit_lut_init, 2 KB per CTA
             if (act) {
                 stime[g * 32 + pos] = (uint16_t)t;
                 atomicAnd(&smask[g], ~(1u << pos));
@@ -227,26 +232,50 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
     // Ancestry / edges: the reference's parents[] pass (convert.rs:174-185) only ever looks
     // up the last earlier row with a given label; stbl keeps that row per label, same-batch
     // occurrences are resolved with MATCH.ANY.
+    // Software pipeline: the loads of a batch are issued two iterations ahead (stime) and one
+    // iteration ahead (sv), and its label resolution (ballot / shuffles / MATCH) runs while the
+    // table lookup of the batch before it is in flight.
     uint32_t lab_carry = 0;
-    for (int b = 0; b < nb; ++b) {
-        const int s = b * 32 + lane;
+    uint32_t n_t, n_lab = 0, n_peers = 0;        // batch b + 1 after its label stage
+    bool n_root = false;
+    auto label_stage = [&](int bb, uint32_t t, uint32_t x) {
+        const int s = bb * 32 + lane;
         const bool act = s < k;
-        const uint32_t t = act ? stime[s] : 0u;
-        const uint32_t x = sv[t];
-        const bool root = act && x <= t;
-        const uint32_t m = __ballot_sync(FULL, root) & lanes_le(lane);
+        n_root = act && x <= t;
+        const uint32_t m = __ballot_sync(FULL, n_root) & lanes_le(lane);
         const int src = m ? 31 - __clz(m) : 0;
         uint32_t lab = __shfl_sync(FULL, x, src);
         if (!m) lab = lab_carry;
         lab_carry = __shfl_sync(FULL, lab, 31);
+        n_t = t; n_lab = lab;
+        if (MODE != MODE_PAIRS) n_peers = __match_any_sync(FULL, act ? lab : (0x10000u + lane));
+    };
+    uint32_t t1 = (lane < k) ? (uint32_t)stime[lane] : 0u;              // batch 0
+    uint32_t x1 = sv[t1];
+    label_stage(0, t1, x1);
+    t1 = (32 + lane < k) ? (uint32_t)stime[32 + lane] : 0u;             // batch 1 (stime has K + 32 entries)
+    x1 = sv[t1];
+    uint32_t t2 = (64 + lane < k) ? (uint32_t)stime[64 + lane] : 0u;    // batch 2
+    for (int b = 0; b < nb; ++b) {
+        const int s = b * 32 + lane;
+        const bool act = s < k;
+        const uint32_t t = n_t, lab = n_lab, peers = n_peers;
+        const bool root = n_root;
+        // loads of the batches ahead
+        const uint32_t x2 = sv[t2];
+        const int s3 = s + 96;
+        const uint32_t t3 = (s3 < k) ? (uint32_t)stime[s3] : 0u;
         if (MODE == MODE_PAIRS) {
             if (act) store_pair<OutT>(ot + 2 * (size_t)s, (OutT)lab, (OutT)(t + 1));
+            label_stage(b + 1, t1, x1);
         } else {
-            const uint32_t peers = __match_any_sync(FULL, act ? lab : (0x10000u + lane));
+            const uint32_t lower = peers & lanes_lt(lane);
+            uint32_t cand = NONE16;
+            if (root && !lower) cand = stbl[lab];
+            label_stage(b + 1, t1, x1);                 // independent of the table: overlaps the lookup
             uint32_t c1p = (uint32_t)(k + s);            // non-root: the previous row's parent
             if (root) {
-                const uint32_t lower = peers & lanes_lt(lane);
-                const uint32_t cand = lower ? (uint32_t)(b * 32 + 31 - __clz(lower)) : (uint32_t)stbl[lab];
+                if (lower) cand = (uint32_t)(b * 32 + 31 - __clz(lower));
                 c1p = (cand != NONE16) ? (uint32_t)(k + 1) + cand : lab;
             }
             __syncwarp();
@@ -258,6 +287,7 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
                 store_row<OutT, MODE>(ot, s, (OutT)c1p, (OutT)c2p, (OutT)(k + 1 + s));
             }
         }
+        t1 = t2; x1 = x2; t2 = t3;
     }
     __syncwarp();
     return -1;
