@@ -134,34 +134,28 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
             if (bm) return b * 32 + __ffs(bm) - 1;
         }
     }
-    // free-slot mask: bit i of word g <-> slot 32g+i, 1 = free; lane l holds words l*WPL .. l*WPL+WPL-1
+    // free-slot mask: bit i of word g <-> slot 32g+i, 1 = free; lane l holds words l*WPL .. l*WPL+WPL-1.
+    // The K - k padding elements (times k .. K-1, top batch only) are placed like real ones: with
+    // rank t they take slots k .. K-1 before anything else is placed, so the placement code needs
+    // no "is this lane a real element" predicate.
     uint32_t word[WPL];
 #pragma unroll
     for (int j = 0; j < WPL; ++j) {
         const int g = lane * WPL + j;
-        word[j] = (g * 32 + 32 <= k) ? 0xFFFFFFFFu : (g * 32 >= k ? 0u : ((1u << (k - g * 32)) - 1u));
+        word[j] = (g * 32 < K) ? 0xFFFFFFFFu : 0u;
         smask[g] = word[j];
     }
     __syncwarp();
 
     // ---- B: slot assignment, walking time backwards, two batches per rank scan; the scan
     //         of the next pair is independent of the placement of the current one ------------
-    uint32_t Rn_hi, Rn_lo;
-    if (WPL <= 2) batch_rank_pair(sv, nb - 1, k, lane, Rn_hi, Rn_lo);
-    else batch_rank_pair_int(sv, nb - 1, k, lane, Rn_hi, Rn_lo);
-    for (int bp = nb - 1; bp >= 0; bp -= 2) {
-        const uint32_t Rpair[2] = {Rn_hi, Rn_lo};
-        if (bp >= 2) {
-            if (WPL <= 2) batch_rank_pair(sv, bp - 2, k, lane, Rn_hi, Rn_lo);
-            else batch_rank_pair_int(sv, bp - 2, k, lane, Rn_hi, Rn_lo);
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int b = bp - h;
-            if (b < 0) break;
+    auto rank_pair = [&](int b, uint32_t& hi, uint32_t& lo) {      // batches b (hi) and b - 1 (lo)
+        if (WPL <= 2) batch_rank_pair(sv, b, k, lane, hi, lo);
+        else batch_rank_pair_int(sv, b, k, lane, hi, lo);
+    };
+    auto place = [&](int b, uint32_t Rin) {
             const int t = b * 32 + lane;
-            const bool act = t < k;
-            const uint32_t R = Rpair[h];
+            const uint32_t R = (t < k) ? Rin : (uint32_t)t;
             // rank-select R among the free slots
             uint32_t cnt = 0;
 #pragma unroll
@@ -209,10 +203,8 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
                 if (adv) { rr -= c; wd = q.w; ++g; }
             }
             const uint32_t pos = nth_set_bit_lut(wd, rr, lut);    // lut: nth_bit_lut_init, 2 KB per CTA
-            if (act) {
-                stime[g * 32 + pos] = (uint16_t)t;
-                atomicAnd(&smask[g], ~(1u << pos));
-            }
+            stime[g * 32 + pos] = (uint16_t)t;
+            atomicAnd(&smask[g], ~(1u << pos));
             __syncwarp();
             if (WPL <= 2) {
 #pragma unroll
@@ -224,7 +216,20 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
                     word[4 * jj] = q.x; word[4 * jj + 1] = q.y; word[4 * jj + 2] = q.z; word[4 * jj + 3] = q.w;
                 }
             }
-        }
+    };
+    int bp = nb - 1;
+    uint32_t Rn_hi, Rn_lo;
+    if (nb & 1) {                                  // odd number of batches: the top one goes alone
+        rank_pair(bp, Rn_hi, Rn_lo);
+        place(bp, Rn_hi);
+        --bp;
+    }
+    if (bp >= 1) rank_pair(bp, Rn_hi, Rn_lo);
+    for (; bp >= 1; bp -= 2) {                     // whole pairs (bp, bp - 1)
+        const uint32_t R1 = Rn_hi, R0 = Rn_lo;
+        if (bp >= 3) rank_pair(bp - 2, Rn_hi, Rn_lo);
+        place(bp, R1);
+        place(bp - 1, R0);
     }
 
     // ---- D: forward sweep over the slots, 32 rows at a time -------------------------------
