@@ -576,11 +576,12 @@ struct RowShared {
     int incount;
 };
 // dynamic shared memory of rows_kernel: midhi[nidb], midlo[nidb] (doubles), midk[nidb], mida[nidb],
-// ptab[rcap * nincap], sephi[bsz], seplo[bsz], inhi[bsz], inlo[bsz] (doubles), then kblk[bsz],
+// ptab[rcap * nincap], sephi[bsz], seplo[bsz], inhi[nincap], inlo[nincap] (doubles), then kblk[bsz],
 // inlist[bsz], inlab[bsz], indi[bsz] (ints), st[levels][bsz] (uint16)
 inline size_t rows_dyn_smem(const CophCall& c) {
     const int levels = ilog2c(c.bsz) + 1;
-    return (((size_t)24 * c.nidb + 15) & ~(size_t)15) + (size_t)8 * c.rcap * c.nincap + (size_t)48 * c.bsz +
+    return (((size_t)24 * c.nidb + 15) & ~(size_t)15) + (size_t)8 * c.rcap * c.nincap + (size_t)20 * c.bsz +
+           (size_t)28 * c.nincap +
            (size_t)2 * levels * c.bsz + 16;
 }
 
@@ -617,13 +618,12 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
     double* s_ptab = reinterpret_cast<double*>(dyn + (((size_t)24 * nidb + 15) & ~(size_t)15));   // rcap*nincap: row x in-block column
     double* s_sephi = s_ptab + (size_t)rcap * nincap; // pmax: dd depth of the block's separators
     double* s_seplo = s_sephi + pmax;
-    double* s_inhi = s_seplo + pmax;                  // pmax: dd depth of the in-block leaves of this chunk
-    double* s_inlo = s_inhi + pmax;
-    int* s_kblk = reinterpret_cast<int*>(s_inlo + pmax);   // pmax: separator keys of the block
-    int* s_inlist = s_kblk + pmax;                    // pmax: in-block leaves whose column is in this chunk (positions)
-    int* s_inlab = s_inlist + pmax;                   // pmax: their labels
-    int* s_indi = s_inlab + pmax;                     // pmax: their topological depths
-    unsigned short* s_st = reinterpret_cast<unsigned short*>(s_indi + pmax);   // [levels][pmax] argmin offsets
+    double* s_inhi = s_seplo + pmax;                  // nincap: dd depth of the staged in-block leaves of this chunk
+    double* s_inlo = s_inhi + nincap;
+    int* s_kblk = reinterpret_cast<int*>(s_inlo + nincap);  // pmax: separator keys of the block
+    int* s_inlist = s_kblk + pmax;                    // nincap: staged in-block leaves of this chunk (positions)
+    int* s_indi = s_inlist + nincap;                  // nincap: their topological depths
+    unsigned short* s_st = reinterpret_cast<unsigned short*>(s_indi + nincap);   // [levels][pmax] argmin offsets
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t rows = row_end - row_begin;
 
@@ -771,6 +771,7 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
         // ---- column side: 4 columns per thread (two adjacent pairs) ----------------------
         int col[ROW_CPT], side[ROW_CPT];
         unsigned inpack = 0;               // per column: slot + 1 in the in-block list, 0 = outside (8 bits each)
+        unsigned inmask = 0;               // per column: 1 = in-block (whether staged or not)
         int bi[ROW_CPT], uji[ROW_CPT];
         double bhi[ROW_CPT], blo[ROW_CPT], ujf[ROW_CPT];
 #pragma unroll
@@ -790,8 +791,9 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
                 int slot = -1;
                 if (J == I) {                      // its LCA with the rows lies inside the block
                     slot = atomicAdd(&S.incount, 1);
-                    s_inlist[slot] = pos[j]; s_inlab[slot] = j;
-                    if (slot < nincap) inpack |= (unsigned)(slot + 1) << (8 * c);
+                    inmask |= 1u << c;
+                    if (slot < nincap) { s_inlist[slot] = pos[j]; inpack |= (unsigned)(slot + 1) << (8 * c); }
+                    else slot = -1;
                 }
                 if (TOPO) {
                     const int dj = jDI[j];
@@ -817,24 +819,25 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
         __syncthreads();
         const int nin = S.incount;
         const bool staged = nin <= nincap;
-        auto inblock_value = [&](int r, int e) -> double {
-            const int q = S.qpos[r], p = s_inlist[e];
+        auto inblock_value = [&](int r, int p, int dj_i, dd dj) -> double {
+            const int q = S.qpos[r];
             if (p == q) return VCV ? (TOPO ? int_to_f64(S.di[r]) : S.dhi[r]) : 0.0;
             const int a = min(p, q) + 1 - lo, b = max(p, q) - lo;     // sep offsets a..b
             const int lev = 31 - __clz(b - a + 1);
             const int x = s_st[lev * pmax + a], y = s_st[lev * pmax + b - (1 << lev) + 1];
             const int arg = (s_kblk[x] <= s_kblk[y]) ? x : y;
             if (VCV) return TOPO ? int_to_f64(s_kblk[arg]) : s_sephi[arg];
-            if (TOPO) return int_to_f64(S.di[r] + s_indi[e] - 2 * s_kblk[arg]);
+            if (TOPO) return int_to_f64(S.di[r] + dj_i - 2 * s_kblk[arg]);
             const dd m = dd{-s_sephi[arg], -s_seplo[arg]};
             const dd xa = dd_add(dd{S.dhi[r], S.dlo[r]}, m);
-            const dd xb = dd_add(dd{s_inhi[e], s_inlo[e]}, m);
+            const dd xb = dd_add(dj, m);
             return __dadd_rn(__dadd_rn(xa.hi, xb.hi), __dadd_rn(xa.lo, xb.lo));
         };
         if (staged) {
             for (int w = tid; w < nin * nrow; w += THREADS) {
                 const int r = w / nin, e = w - r * nin;
-                s_ptab[r * nincap + e] = inblock_value(r, e);
+                s_ptab[r * nincap + e] = TOPO ? inblock_value(r, s_inlist[e], s_indi[e], dd{0.0, 0.0})
+                                              : inblock_value(r, s_inlist[e], 0, dd{s_inhi[e], s_inlo[e]});
             }
             __syncthreads();
         }
@@ -887,9 +890,14 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
 
         if (!staged) {   // rare: more in-block columns in this chunk than the staging table holds
             __syncthreads();   // orders the streamed stores of this CTA before the patch stores
-            for (int w = tid; w < nin * nrow; w += THREADS) {
-                const int r = w / nin, e = w - r * nin;
-                obase[(size_t)(S.label[r] - row_begin) * n + s_inlab[e]] = inblock_value(r, e);
+#pragma unroll
+            for (int c = 0; c < ROW_CPT; ++c) {
+                if (!((inmask >> c) & 1u)) continue;        // every thread patches its own columns
+                const int j = col[c], p = pos[j];
+                const int dj_i = TOPO ? jDI[j] : 0;
+                const dd dj = TOPO ? dd{0.0, 0.0} : dd{jDH[j], jDL[j]};
+                for (int r = 0; r < nrow; ++r)
+                    obase[(size_t)(S.label[r] - row_begin) * n + j] = inblock_value(r, p, dj_i, dj);
             }
         }
         __syncthreads();   // the patch has read inlist / incount before the next chunk resets them
@@ -1353,7 +1361,13 @@ cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t
     int64_t tiles_bound = call.nidb;
     if (tiles_bound > L.nbmax) tiles_bound = L.nbmax;
     // small matrices: one CTA walks all column chunks of its tile (row-side setup done once)
-    const int chunks_per_cta = (chunks <= 4) ? chunks : 1;
+    // and bigger ones as many as still leave every SM a few CTAs: the per-tile set-up (row side,
+    // minima over the blocks in between, sparse table of the block) is then paid once per group
+    int chunks_per_cta = (chunks <= 4) ? chunks : 1;
+    if (chunks > 4) {
+        for (int c = 8; c > 1; c >>= 1)
+            if (B * tiles_bound * ((chunks + c - 1) / c) >= (int64_t)sm_count() * 18) { chunks_per_cta = c; break; }
+    }
     const int64_t work = B * tiles_bound * ((chunks + chunks_per_cta - 1) / chunks_per_cta);
     const size_t smem = rows_dyn_smem(call);
     const bool topo = !weighted;
