@@ -386,7 +386,8 @@ blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int
         const int per_warp = (((n + NW - 1) / NW) + 31) & ~31;
         const int w0 = min(n, warp * per_warp), w1 = min(n, w0 + per_warp);
         int cnt = 0;
-        for (int base = w0; base < w1; base += 32) {
+#pragma unroll 8
+        for (int base = w0; base < w1; base += 32) {     // independent loads: several in flight
             const int p = base + lane;
             const int lab = (p < w1) ? leaf_at[p] : -1;
             cnt += __popc(__ballot_sync(FULL, lab >= row_begin && lab < row_end));
@@ -401,10 +402,14 @@ blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int
         __syncthreads();
         int c0 = s_part[warp];                       // requested rows at positions < w0
         int prev_last = (w0 > 0) ? (w0 - 1) / pcap + max(0, c0 - 1) / rcap : -1;   // id of position w0-1
+        int lab_next = (w0 + lane < w1) ? leaf_at[w0 + lane] : -1;
+        int lab_next2 = (w0 + 32 + lane < w1) ? leaf_at[w0 + 32 + lane] : -1;
         for (int base = w0; base < w1; base += 32) {
             const int p = base + lane;
             const bool in = p < w1;
-            const int lab = in ? leaf_at[p] : -1;
+            const int lab = lab_next;                     // loaded two iterations ahead
+            lab_next = lab_next2;
+            lab_next2 = (p + 64 < w1) ? leaf_at[p + 64] : -1;
             const bool own = lab >= row_begin && lab < row_end;
             const unsigned bm = __ballot_sync(FULL, own);
             const int c = c0 + __popc(bm & lanes_le(lane));          // requested rows at positions <= p
