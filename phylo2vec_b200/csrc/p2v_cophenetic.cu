@@ -563,6 +563,13 @@ __device__ __forceinline__ void store2(double* p, double a, double b) {
     }
 }
 
+// double-double x - y for x >= y >= 0 on one root path, rounded to one double
+__device__ __forceinline__ double dd_sub_round(double xh, double xl, double yh, double yl) {
+    const double s = __dadd_rn(xh, -yh);                     // Fast2Sum: xh >= yh >= 0
+    const double e = __dadd_rn(__dadd_rn(xh, -s), -yh);
+    return __dadd_rn(s, __dadd_rn(e, __dadd_rn(xl, -yl)));
+}
+
 // double-double a - b, rounded to one double
 __device__ __forceinline__ double dd_diff_round(dd a, dd b) {
     return __dadd_rn(__dadd_rn(a.hi, -b.hi), __dadd_rn(a.lo, -b.lo));
@@ -833,10 +840,9 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
             const int arg = (s_kblk[x] <= s_kblk[y]) ? x : y;
             if (VCV) return TOPO ? int_to_f64(s_kblk[arg]) : s_sephi[arg];
             if (TOPO) return int_to_f64(S.di[r] + dj_i - 2 * s_kblk[arg]);
-            const dd m = dd{-s_sephi[arg], -s_seplo[arg]};
-            const dd xa = dd_add(dd{S.dhi[r], S.dlo[r]}, m);
-            const dd xb = dd_add(dj, m);
-            return __dadd_rn(__dadd_rn(xa.hi, xb.hi), __dadd_rn(xa.lo, xb.lo));
+            // (d_i - d_lca) + (d_j - d_lca): each difference of double-doubles rounded once
+            const double lh = s_sephi[arg], ll = s_seplo[arg];
+            return __dadd_rn(dd_sub_round(S.dhi[r], S.dlo[r], lh, ll), dd_sub_round(dj.hi, dj.lo, lh, ll));
         };
         if (staged) {
             for (int w = tid; w < nin * nrow; w += THREADS) {
@@ -974,12 +980,6 @@ __host__ __device__ inline SmallLayout small_layout(int k, bool topo) {
     return L;
 }
 
-// double-double x - y for x >= y >= 0 on one root path, rounded to one double
-__device__ __forceinline__ double dd_sub_round(double xh, double xl, double yh, double yl) {
-    const double s = __dadd_rn(xh, -yh);                     // Fast2Sum: xh >= yh >= 0
-    const double e = __dadd_rn(__dadd_rn(xh, -s), -yh);
-    return __dadd_rn(s, __dadd_rn(e, __dadd_rn(xl, -yl)));
-}
 
 template <bool TOPO, bool VCV, bool VEC2>
 __global__ void __launch_bounds__(CS_THREADS, 8)
