@@ -7,6 +7,13 @@
 #include "p2v_common.cuh"
 #include "p2v_internal.h"
 
+// 1: issue the rank scan of the next pair of batches between the dependent shuffles of the current
+// placements.  Measured on B200 (profiles/decode_timing.py): no gain at n = 1000 (the kernel is
+// bound by issue slots and the shared-memory pipe, not by that chain), -17 % at n = 4096; off.
+#ifndef P2V_DECODE_INTERLEAVE
+#define P2V_DECODE_INTERLEAVE 0
+#endif
+
 namespace p2v {
 
 constexpr uint32_t BIG = 0x7FFFFFFFu;
@@ -153,25 +160,80 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
         if (WPL <= 2) batch_rank_pair(sv, b, k, lane, hi, lo);
         else batch_rank_pair_int(sv, b, k, lane, hi, lo);
     };
-    auto place = [&](int b, uint32_t Rin) {
+    // The rank scan of the NEXT pair of batches is resumable (scan_begin / scan_step / scan_end) and
+    // its 31 steps are issued between the dependent shuffles of the two placements of the CURRENT
+    // pair (`fill(i)` at the 13 stall points of a placement), so that the two chains overlap.
+    __half2 h_ins = __float2half2_rn(0.0f), h_R = h_ins;
+    uint32_t i_ins1 = 0, i_ins0 = 0, i_R1 = 0, i_R0 = 0;
+    auto scan_begin = [&](int b) {                 // batches b (hi half) and b - 1 (lo half)
+        const int t1 = b * 32 + lane, t0 = t1 - 32;
+        const uint32_t x1 = sv[t1];
+        const uint32_t x0 = (t0 >= 0) ? (uint32_t)sv[t0] : 0u;
+        const uint32_t a1 = x1 <= (uint32_t)t1 ? 0u : x1 - (uint32_t)t1;
+        const uint32_t a0 = x0 <= (uint32_t)t0 ? 0u : x0 - (uint32_t)t0;
+        if (WPL <= 2) {
+            const __half inf = __ushort_as_half((unsigned short)0x7C00);
+            h_ins = __halves2half2((t0 >= 0) ? __uint2half_rn(a0) : inf, (t1 < k) ? __uint2half_rn(a1) : inf);
+            h_R = h_ins;
+        } else {
+            i_ins1 = (t1 < k) ? a1 : BIG; i_ins0 = (t0 >= 0) ? a0 : BIG;
+            i_R1 = i_ins1; i_R0 = i_ins0;
+        }
+    };
+    auto scan_step = [&](int d) {
+        if (WPL <= 2) {
+            const __half2 y = __shfl_down_sync(FULL, h_ins, d);
+            h_R = __hadd2(h_R, __hle2(y, h_R));
+        } else {
+            rank_step(i_R1, i_ins1, d);
+            rank_step(i_R0, i_ins0, d);
+        }
+    };
+    auto scan_end = [&](uint32_t& hi, uint32_t& lo) {
+        if (WPL <= 2) {      // the `lane` wrapped steps (SHFL.DOWN past lane 31 returns the own value)
+            lo = (uint32_t)__half2int_rz(__low2half(h_R)) - (uint32_t)lane;
+            hi = (uint32_t)__half2int_rz(__high2half(h_R)) - (uint32_t)lane;
+        } else {
+            hi = i_R1; lo = i_R0;
+        }
+    };
+    auto fill_none = [&](int) {};
+    auto fill_first = [&](int i) {                 // steps 1..16 over the 13 points of the first placement
+        if (i < 3) { scan_step(2 * i + 1); scan_step(2 * i + 2); }
+        else scan_step(i + 4);
+    };
+    auto fill_second = [&](int i) {                // steps 17..31 over the second placement
+        if (i < 2) { scan_step(17 + 2 * i); scan_step(18 + 2 * i); }
+        else scan_step(i + 19);
+    };
+    auto place = [&](int b, uint32_t Rin, auto&& fill) {
             const int t = b * 32 + lane;
             const uint32_t R = (t < k) ? Rin : (uint32_t)t;
             // rank-select R among the free slots
             uint32_t cnt = 0;
 #pragma unroll
             for (int j = 0; j < WPL; ++j) cnt += __popc(word[j]);
-            const uint32_t incl = warp_incl_scan(cnt, lane);
+            uint32_t incl = cnt;
+            { const uint32_t y = __shfl_up_sync(FULL, incl, 1); fill(0); if (lane >= 1) incl += y; }
+            { const uint32_t y = __shfl_up_sync(FULL, incl, 2); fill(1); if (lane >= 2) incl += y; }
+            { const uint32_t y = __shfl_up_sync(FULL, incl, 4); fill(2); if (lane >= 4) incl += y; }
+            { const uint32_t y = __shfl_up_sync(FULL, incl, 8); fill(3); if (lane >= 8) incl += y; }
+            { const uint32_t y = __shfl_up_sync(FULL, incl, 16); fill(4); if (lane >= 16) incl += y; }
             uint32_t w = 0;
-#pragma unroll
-            for (int step = 16; step >= 1; step >>= 1) {
-                const uint32_t y = __shfl_sync(FULL, incl, (w + step - 1) & 31);
-                if (y <= R) w += step;
-            }
+            { const uint32_t y = __shfl_sync(FULL, incl, 15); fill(5); if (y <= R) w = 16; }
+            { const uint32_t y = __shfl_sync(FULL, incl, w + 7); fill(6); if (y <= R) w += 8; }
+            { const uint32_t y = __shfl_sync(FULL, incl, w + 3); fill(7); if (y <= R) w += 4; }
+            { const uint32_t y = __shfl_sync(FULL, incl, w + 1); fill(8); if (y <= R) w += 2; }
+            { const uint32_t y = __shfl_sync(FULL, incl, w); fill(9); if (y <= R) w += 1; }
             w &= 31;
-            uint32_t rr = R - __shfl_sync(FULL, incl - cnt, w);     // rank inside lane w's words
+            const uint32_t before = __shfl_sync(FULL, incl - cnt, w);
+            uint32_t wd0 = 0;
+            if (WPL <= 2) wd0 = __shfl_sync(FULL, word[0], w);
+            fill(10);
+            uint32_t rr = R - before;                                // rank inside lane w's words
             uint32_t wd, g = w * WPL;
             if (WPL <= 2) {
-                wd = __shfl_sync(FULL, word[0], w);
+                wd = wd0;
 #pragma unroll
                 for (int j = 1; j < WPL; ++j) {
                     const uint32_t nxt = __shfl_sync(FULL, word[j], w);
@@ -205,6 +267,7 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
             const uint32_t pos = nth_set_bit_lut(wd, rr, lut);    // lut: nth_bit_lut_init, 2 KB per CTA
             stime[g * 32 + pos] = (uint16_t)t;
             atomicAnd(&smask[g], ~(1u << pos));
+            fill(11);
             __syncwarp();
             if (WPL <= 2) {
 #pragma unroll
@@ -216,20 +279,32 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
                     word[4 * jj] = q.x; word[4 * jj + 1] = q.y; word[4 * jj + 2] = q.z; word[4 * jj + 3] = q.w;
                 }
             }
+            fill(12);
     };
     int bp = nb - 1;
     uint32_t Rn_hi, Rn_lo;
     if (nb & 1) {                                  // odd number of batches: the top one goes alone
         rank_pair(bp, Rn_hi, Rn_lo);
-        place(bp, Rn_hi);
+        place(bp, Rn_hi, fill_none);
         --bp;
     }
     if (bp >= 1) rank_pair(bp, Rn_hi, Rn_lo);
-    for (; bp >= 1; bp -= 2) {                     // whole pairs (bp, bp - 1)
+    for (; bp >= 3; bp -= 2) {                     // whole pairs (bp, bp - 1), the next pair's scan inside
         const uint32_t R1 = Rn_hi, R0 = Rn_lo;
-        if (bp >= 3) rank_pair(bp - 2, Rn_hi, Rn_lo);
-        place(bp, R1);
-        place(bp - 1, R0);
+#if P2V_DECODE_INTERLEAVE
+        scan_begin(bp - 2);
+        place(bp, R1, fill_first);
+        place(bp - 1, R0, fill_second);
+        scan_end(Rn_hi, Rn_lo);
+#else
+        rank_pair(bp - 2, Rn_hi, Rn_lo);
+        place(bp, R1, fill_none);
+        place(bp - 1, R0, fill_none);
+#endif
+    }
+    if (bp >= 1) {                                 // last pair
+        place(bp, Rn_hi, fill_none);
+        place(bp - 1, Rn_lo, fill_none);
     }
 
     // ---- D: forward sweep over the slots, 32 rows at a time -------------------------------
