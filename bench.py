@@ -321,13 +321,13 @@ def run_b200(args):
                        "l2": "inputs (8 GB) and outputs (24 GB) per step exceed the 126 MB L2"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_TREE * B,
-                         "traffic_source": "ncu --set full capture profiles/r01_decode_small_v5.summary.txt: "
-                                           "dram read+write 4.1337 GB per launch of 131072 trees = "
+                         "traffic_source": "ncu --set full capture profiles/r01_decode_small_v6.summary.txt: "
+                                           "dram read+write 4.1343 GB per launch of 131072 trees = "
                                            f"{NCU_DRAM_BYTES_PER_TREE} B/tree, scaled to this launch's {B} trees",
                          "peak_source": peak_src,
                          "kernel": "decode_small_kernel<int64, ancestry>",
                          "algorithmic_bytes_per_tree": 4 * K * 8,
-                         "note": "issue/latency-bound integer kernel (SURVEY 7 hard part 1); HBM fraction reported as required"},
+                         "note": "integer kernel bound by the L1/shared-memory data pipe (ncu: 90 % of peak), not by HBM; HBM fraction reported as required"},
             "cpu_baseline": {"value": cb_rate, "unit": "trees/s", "cores": cb_cores, "kind": "port",
                              "sample": f"65536 trees of n=1000, {cb_dt:.2f} s, OpenMP over trees"},
             "e2e": {"value": e2e_value, "unit": "trees/s", "h2d_bytes_per_step": Be * K * 8,
@@ -414,8 +414,8 @@ def bench_cophenetic(torch, lib, device, rank, world, peak, args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of decode_small_kernel<int64, ancestry> per tree
-# (profiles/r01_decode_small_v5.summary.txt: (1.048728 + 3.084973) GB / 131072 trees)
-NCU_DRAM_BYTES_PER_TREE = 31538
+# (profiles/r01_decode_small_v6.summary.txt: (1.049686 + 3.084584) GB / 131072 trees)
+NCU_DRAM_BYTES_PER_TREE = 31542
 
 
 def main():
