@@ -21,6 +21,12 @@ extern "C" {
                                row_begin: i64, row_end: i64, out: *mut f64, status: *mut i32) -> c_int;
     pub fn p2v_cophenetic_matrix_host(m: *const f64, b: i64, k: i64, unrooted: c_int, row_begin: i64, row_end: i64,
                                       out: *mut f64, status: *mut i32) -> c_int;
+    pub fn p2v_vcv_host(v: *const c_void, idx_bytes: c_int, bls: *const f64, b: i64, k: i64, row_begin: i64, row_end: i64,
+                        out: *mut f64, status: *mut i32) -> c_int;
+    pub fn p2v_vcv_matrix_host(m: *const f64, b: i64, k: i64, row_begin: i64, row_end: i64, out: *mut f64,
+                               status: *mut i32) -> c_int;
+    pub fn p2v_node_depths_host(v_or_m: *const c_void, idx_bytes: c_int, bls: *const f64, b: i64, k: i64,
+                                out: *mut f64, status: *mut i32) -> c_int;
     // device-pointer entry points (asynchronous on `stream`, caller-owned buffers)
     pub fn p2v_decode_workspace_bytes(b: i64, k: i64) -> usize;
     pub fn p2v_to_ancestry_batch(v: *const c_void, idx_bytes: c_int, b: i64, k: i64, out: *mut c_void, status: *mut i32,
@@ -83,6 +89,32 @@ pub fn cophenetic_distances(v: &[usize], unrooted: bool) -> Vec<f64> {
     let rc = unsafe {
         p2v_cophenetic_host(v.as_ptr().cast(), 8, std::ptr::null(), 1, k as i64, unrooted as c_int, 0, n as i64,
                             out.as_mut_ptr(), &mut status)
+    };
+    check(rc, status, v);
+    out
+}
+
+/// Drop-in for `phylo2vec::vector::graph::vcv` (graph.rs:280-282); row-major (n, n).
+pub fn vcv(v: &[usize]) -> Vec<f64> {
+    let k = v.len();
+    assert!(k > 0, "Variance-covariance matrix not supported for trees with < 2 leaves.");
+    let n = k + 1;
+    let mut out = vec![0f64; n * n];
+    let mut status = 0i32;
+    let rc = unsafe {
+        p2v_vcv_host(v.as_ptr().cast(), 8, std::ptr::null(), 1, k as i64, 0, n as i64, out.as_mut_ptr(), &mut status)
+    };
+    check(rc, status, v);
+    out
+}
+
+/// Drop-in for `phylo2vec::vector::ops::get_node_depths` (ops.rs:287-289).
+pub fn get_node_depths(v: &[usize]) -> Vec<f64> {
+    let k = v.len();
+    let mut out = vec![0f64; 2 * k + 1];
+    let mut status = 0i32;
+    let rc = unsafe {
+        p2v_node_depths_host(v.as_ptr().cast(), 8, std::ptr::null(), 1, k as i64, out.as_mut_ptr(), &mut status)
     };
     check(rc, status, v);
     out
