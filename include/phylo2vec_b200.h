@@ -144,6 +144,17 @@ int p2v_node_depths_batch(const void *v_or_matrix, int idx_bytes, const double *
                           double *out, int32_t *status, void *workspace, size_t workspace_bytes,
                           p2v_stream_t stream);
 
+/* ---- to_newick (second "next" row; vectors only) ------------------------------------------
+ * replaces vector::convert::to_newick / build_newick (vector/convert.rs:341-397); PyO3 entry
+ * point to_newick, vector arm (py-phylo2vec/src/lib.rs:90-96); Python phylo2vec.base.newick.
+ * to_newick (base/newick.py:29-43).  Tree b's string is written NUL-terminated at
+ * out + b * out_stride (out_stride >= p2v_newick_max_bytes(k)); lengths[b] (may be NULL) gets
+ * its length without the NUL, 0 for an invalid vector.  1 <= k <= 1023 for now
+ * (P2V_ERR_UNSUPPORTED above; the matrix form with branch lengths is not built). */
+size_t p2v_newick_max_bytes(int64_t k);
+int p2v_to_newick_batch(const void *v, int idx_bytes, int64_t B, int64_t k, char *out, int64_t out_stride,
+                        int64_t *lengths, int32_t *status, p2v_stream_t stream);
+
 /* ---- host-buffer entry points (H2D + kernels + D2H inside the call) ------ */
 int p2v_to_pairs_host(const void *v, int idx_bytes, int64_t B, int64_t k, void *pairs, int32_t *status);
 int p2v_to_ancestry_host(const void *v, int idx_bytes, int64_t B, int64_t k, void *ancestry, int32_t *status);
@@ -163,6 +174,9 @@ int p2v_vcv_matrix_host(const double *matrix, int64_t B, int64_t k, int64_t row_
                         double *out, int32_t *status);
 int p2v_node_depths_host(const void *v_or_matrix, int idx_bytes, const double *bls, int64_t B, int64_t k,
                          double *out, int32_t *status);
+
+int p2v_to_newick_host(const void *v, int idx_bytes, int64_t B, int64_t k, char *out, int64_t out_stride,
+                       int64_t *lengths, int32_t *status);
 
 /* The *_host entry points cache three streams and their device staging buffers per host
  * thread (they grow on demand).  This frees the calling thread's cache. */

@@ -680,7 +680,10 @@ static size_t dec_len(i64 x) { size_t l = 1; while (x >= 10) { x /= 10; ++l; } r
 
 i64 p2vo_to_newick(const i64 *v, i64 k, char *buf, i64 cap) {
     i64 n = k + 1;
-    if (k == 0) return P2VO_EBADINPUT;
+    if (k == 0) { /* no pairs: the cache of the single leaf, convert.rs:361-381 */
+        if (buf && cap > 2) { buf[0] = '0'; buf[1] = ';'; buf[2] = 0; }
+        return 2;
+    }
     i64 *pairs = (i64 *)malloc(sizeof(i64) * 2 * (size_t)k);
     if (!pairs) return P2VO_ENOMEM;
     int rc = p2vo_to_pairs(v, k, pairs);

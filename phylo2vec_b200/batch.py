@@ -291,3 +291,29 @@ def node_depths_batch(trees, out=None, bls=None, status=None, check: bool = True
     if check and bool(status.any()):
         raise_for_status(status, T[..., 0].to(torch.int64) if is_matrix else T)
     return out
+
+
+def to_newick_batch(V, status=None, check: bool = True, raw: bool = False):
+    """Newick strings of a batch of vectors ``(B,k)`` (k <= 1023).  Returns a list of ``str``; with
+    ``raw=True`` the device buffers instead: a uint8 tensor ``(B, stride)`` of NUL-terminated strings
+    and an int64 tensor of their lengths.
+    Replaces vector::convert::to_newick (phylo2vec/src/vector/convert.rs:341-397)."""
+    V = _idx_tensor(V, 2, "to_newick")
+    B, k = V.shape
+    lib = _capi.load()
+    stride = (int(lib.p2v_newick_max_bytes(k)) + 15) & ~15
+    out = torch.empty((B, stride), dtype=torch.uint8, device=V.device)
+    lengths = torch.empty(B, dtype=torch.int64, device=V.device)
+    if status is None:
+        status = torch.empty(B, dtype=torch.int32, device=V.device)
+    with torch.cuda.device(V.device):
+        rc = lib.p2v_to_newick_batch(V.data_ptr(), V.element_size(), B, k, out.data_ptr(), stride,
+                                     lengths.data_ptr(), status.data_ptr(), _stream_ptr(V.device))
+    _capi.check(rc, "to_newick")
+    if check and bool(status.any()):
+        raise_for_status(status, V)
+    if raw:
+        return out, lengths
+    host = out.cpu().numpy()
+    ln = lengths.cpu().numpy()
+    return [host[b, :ln[b]].tobytes().decode("ascii") for b in range(B)]

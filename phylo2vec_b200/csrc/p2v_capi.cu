@@ -404,6 +404,72 @@ int p2v_node_depths_host(const void* v_or_matrix, int idx_bytes, const double* b
     return coph_host(v_or_matrix, idx_bytes, bls, B, k, 0, 0, k + 1, out, status, 2);
 }
 
+// ---- to_newick --------------------------------------------------------------------------
+size_t p2v_newick_max_bytes(int64_t k) { return newick_max_bytes(k); }
+static int newick_check(const void* v, const char* out, int idx_bytes, int64_t B, int64_t k, int64_t out_stride) {
+    if (idx_bytes != 4 && idx_bytes != 8) return fail(P2V_ERR_INVALID_ARG, "idx_bytes must be 4 or 8");
+    if (B < 0 || k < 0) return fail(P2V_ERR_INVALID_ARG, "negative batch or length");
+    if (k > 1023) return fail(P2V_ERR_UNSUPPORTED, "to_newick: k above 1023 is not built yet");
+    if (B > 0 && (!out || (k > 0 && !v))) return fail(P2V_ERR_INVALID_ARG, "null buffer");
+    if (out_stride < (int64_t)newick_max_bytes(k)) return fail(P2V_ERR_INVALID_ARG, "out_stride below p2v_newick_max_bytes(k)");
+    return P2V_OK;
+}
+__global__ void newick_k0_kernel(char* out, int64_t out_stride, int64_t B, int64_t* lengths, int32_t* status) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < B; t += (int64_t)gridDim.x * blockDim.x) {
+        char* o = out + t * out_stride;          // a single leaf: "0;" (convert.rs:361-381 with no pairs)
+        o[0] = '0'; o[1] = ';'; o[2] = 0;
+        if (lengths) lengths[t] = 2;
+        if (status) status[t] = 0;
+    }
+}
+static cudaError_t newick_launch_any(const void* v, int idx_bytes, int64_t B, int64_t k, char* out, int64_t out_stride,
+                                     int64_t* lengths, int32_t* status, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    if (k == 0) {
+        newick_k0_kernel<<<(int)((B + 255) / 256 < 1024 ? (B + 255) / 256 : 1024), 256, 0, st>>>(out, out_stride, B, lengths, status);
+        count_launch();
+        return cudaGetLastError();
+    }
+    return launch_to_newick(v, idx_bytes, B, k, out, out_stride, lengths, status, st);
+}
+int p2v_to_newick_batch(const void* v, int idx_bytes, int64_t B, int64_t k, char* out, int64_t out_stride,
+                        int64_t* lengths, int32_t* status, p2v_stream_t stream) {
+    int rc = newick_check(v, out, idx_bytes, B, k, out_stride);
+    if (rc) return rc;
+    return from_cuda(newick_launch_any(v, idx_bytes, B, k, out, out_stride, lengths, status, (cudaStream_t)stream),
+                     "to_newick launch");
+}
+int p2v_to_newick_host(const void* v, int idx_bytes, int64_t B, int64_t k, char* out, int64_t out_stride,
+                       int64_t* lengths, int32_t* status) {
+    int rc = newick_check(v, out, idx_bytes, B, k, out_stride);
+    if (rc) return rc;
+    if (B == 0) return P2V_OK;
+    // device lengths ride behind each tree's string: the staged row is out_stride bytes + 8
+    const size_t row = ((size_t)out_stride + 7) & ~(size_t)7;
+    int64_t done = 0;
+    int64_t* dlen[HOST_STREAMS] = {};
+    int64_t cap_chunk = 0;
+    int flip = 0;
+    (void)row;
+    int r = host_chunked(
+        v, (size_t)k * idx_bytes, out, (size_t)out_stride, status, B,
+        [&](int64_t nb) { cap_chunk = nb; return (size_t)0; },
+        [&](void* din, void* dout, int32_t* dst, int64_t nb, void*, size_t, cudaStream_t st) {
+            cudaError_t e = cudaSuccess;
+            const int s = flip; flip = (flip + 1) % HOST_STREAMS;
+            if (!dlen[s]) e = cudaMalloc((void**)&dlen[s], sizeof(int64_t) * (size_t)cap_chunk);
+            if (e != cudaSuccess) return e;
+            e = newick_launch_any(din, idx_bytes, nb, k, (char*)dout, out_stride, dlen[s], dst, st);
+            if (e == cudaSuccess && lengths)
+                e = cudaMemcpyAsync(lengths + done, dlen[s], sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, st);
+            done += nb;
+            return e;
+        });
+    cudaDeviceSynchronize();
+    for (int i = 0; i < HOST_STREAMS; ++i) if (dlen[i]) cudaFree(dlen[i]);
+    return r;
+}
+
 int p2v_to_pairs_host(const void* v, int idx_bytes, int64_t B, int64_t k, void* out, int32_t* status) {
     return decode_host(MODE_PAIRS, 2, v, idx_bytes, B, k, out, status);
 }

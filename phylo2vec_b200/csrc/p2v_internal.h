@@ -48,4 +48,9 @@ cudaError_t launch_node_depths(const void* v_or_matrix, int idx_bytes, const dou
                                double* out, int32_t* status, void* ws, size_t ws_bytes, cudaStream_t stream);
 cudaError_t launch_fill_f64(double* out, int64_t count, double value, cudaStream_t stream);
 
+// to_newick (vectors, k <= 1023): strings at out + b * out_stride, NUL-terminated; lengths without the NUL
+size_t newick_max_bytes(int64_t k);
+cudaError_t launch_to_newick(const void* v, int idx_bytes, int64_t B, int64_t k, char* out, int64_t out_stride,
+                             int64_t* lengths, int32_t* status, cudaStream_t stream);
+
 }  // namespace p2v

@@ -30,6 +30,12 @@ def test_to_newick(goldens):
         assert O.to_newick(g["v"]) == g["newick"], g["src"]
 
 
+def test_to_newick_single_leaf():
+    # build_newick with no pairs returns the cache of leaf 0 (vector/convert.rs:361-381)
+    assert O.to_newick(np.zeros(0, dtype=np.int64)) == "0;"
+    assert O.to_newick([0]) == "(0,1)2;"
+
+
 def test_encode(goldens):
     for g in goldens["from_pairs"]:
         assert np.array_equal(O.from_pairs(g["pairs"]), g["v"]), g["src"]
