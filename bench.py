@@ -302,6 +302,12 @@ def run_b200(args):
         coph = bench_cophenetic(torch, lib, device, rank, world, peak, args)
     except Exception as exc:  # keep the headline line even if this part fails
         coph = {"error": repr(exc)}
+    newick = None
+    if rank == 0:
+        try:
+            newick = bench_newick(torch, lib, device, peak)
+        except Exception as exc:
+            newick = {"error": repr(exc)}
     if world > 1:
         gathered = [None] * world
         dist.all_gather_object(gathered, coph)
@@ -334,11 +340,57 @@ def run_b200(args):
                     "d2h_bytes_per_step": Be * K * 24 + Be * 4, "batch_per_gpu": Be, "steps": e2e_steps,
                     "api": "p2v_to_ancestry_host (C ABI, pinned host buffers)", "matches_device_path": e2e_ok},
             "gpu_launches": launches, "clocks": clocks, "parity_spot_check": parity,
-            "config_c2_other_functions": c2, "cophenetic": coph,
+            "config_c2_other_functions": c2, "cophenetic": coph, "next_rows": {"to_newick": newick},
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_newick(torch, lib, device, peak):
+    """The second row beyond the scope table: batched to_newick, GPU next to the CPU
+    restatement on a bounded sample.  Bytes = v read + string bytes written."""
+    import numpy as np
+    from oracle import p2v_oracle as O
+    res = {}
+    for n, B in ((100, 1_000_000), (1000, 100_000)):
+        k = n - 1
+        g = torch.Generator(device=device).manual_seed(n)
+        hi = (2 * torch.arange(k, device=device) + 1).to(torch.float64)
+        V = (torch.rand((B, k), generator=g, device=device, dtype=torch.float64) * hi).to(torch.int64)
+        stride = (int(lib.p2v_newick_max_bytes(k)) + 15) & ~15
+        out = torch.empty((B, stride), dtype=torch.uint8, device=device)
+        lengths = torch.empty(B, dtype=torch.int64, device=device)
+        st = torch.empty(B, dtype=torch.int32, device=device)
+        stream = torch.cuda.current_stream(device)
+
+        def call():
+            rc = lib.p2v_to_newick_batch(V.data_ptr(), 8, B, k, out.data_ptr(), stride, lengths.data_ptr(),
+                                         st.data_ptr(), stream.cuda_stream)
+            assert rc == 0, lib.p2v_last_error()
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(5):
+            call()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / 5 * 1e-3
+        nbytes = int(lengths.sum()) + B + B * k * 8
+        Bc = min(B, 20000 if n == 100 else 4000)
+        Vc = V[:Bc].cpu().numpy()
+        t0 = time.perf_counter()
+        ref, reflen = O.to_newick_batch(Vc, stride, nthreads=host_threads())
+        tc = time.perf_counter() - t0
+        same = bool(np.array_equal(reflen, lengths[:Bc].cpu().numpy())) and bool(
+            np.array_equal(ref[:, :int(reflen.max())], out[:Bc, :int(reflen.max())].cpu().numpy()))
+        res[f"n{n}"] = {"batch": B, "trees_per_s": B / t, "gbs": nbytes / t / 1e9, "frac_of_peak": nbytes / t / 1e9 / peak,
+                        "cpu": {"sample": Bc, "trees_per_s": Bc / tc, "cores": host_threads(), "kind": "port"},
+                        "matches_cpu": same}
+        del V, out
+    return res
 
 
 def bench_cophenetic(torch, lib, device, rank, world, peak, args):

@@ -777,6 +777,21 @@ int p2vo_batch(int op, const i64 *in, i64 B, i64 k, i64 *out, int32_t *status, i
     return any;
 }
 
+/* batch to_newick: string b at out + b*stride (NUL-terminated), lengths[b] without the NUL */
+int p2vo_to_newick_batch(const i64 *v, i64 B, i64 k, char *out, i64 stride, i64 *lengths, int nthreads) {
+    int bad = 0;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads) reduction(| : bad)
+#endif
+    for (i64 b = 0; b < B; ++b) {
+        i64 len = p2vo_to_newick(v + b * k, k, out + b * stride, stride);
+        if (len < 0 || len >= stride) bad |= 1;
+        if (lengths) lengths[b] = len;
+    }
+    return bad ? P2VO_EBADINPUT : 0;
+}
+
 /* batch cophenetic (literal algorithm), out (B, n, n); bls may be NULL */
 int p2vo_cophenetic_batch(const i64 *v, const double *bls, i64 B, i64 k, int unrooted,
                           double *out, int nthreads) {

@@ -68,6 +68,8 @@ def lib() -> ctypes.CDLL:
         _lib.p2vo_node_depths.argtypes = [p, p, i64, p]
         _lib.p2vo_to_newick.restype = i64
         _lib.p2vo_to_newick.argtypes = [p, i64, ctypes.c_char_p, i64]
+        _lib.p2vo_to_newick_batch.restype = ctypes.c_int
+        _lib.p2vo_to_newick_batch.argtypes = [p, i64, i64, p, i64, p, ctypes.c_int]
         _lib.p2vo_num_threads.restype = ctypes.c_int
         _lib.p2vo_batch.restype = ctypes.c_int
         _lib.p2vo_batch.argtypes = [ctypes.c_int, p, i64, i64, p, p, ctypes.c_int]
@@ -298,3 +300,15 @@ def cophenetic_batch(v: np.ndarray, bls: Optional[np.ndarray], unrooted: bool = 
     out = np.empty((B, k + 1, k + 1), dtype=np.float64)
     lib().p2vo_cophenetic_batch(_ptr(v), _ptr(bls), B, k, int(unrooted), _ptr(out), nthreads)
     return out
+
+
+def to_newick_batch(v: np.ndarray, stride: int, nthreads: int = 0):
+    """One reference call per tree (OpenMP over trees): uint8 (B, stride) buffer and lengths."""
+    v = _i64(v)
+    B, k = v.shape
+    out = np.zeros((B, stride), dtype=np.uint8)
+    lengths = np.zeros(B, dtype=np.int64)
+    rc = lib().p2vo_to_newick_batch(_ptr(v), B, k, _ptr(out), stride, _ptr(lengths), nthreads)
+    if rc:
+        raise ValueError(f"oracle: to_newick_batch failed ({rc})")
+    return out, lengths
