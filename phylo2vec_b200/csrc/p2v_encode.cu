@@ -22,6 +22,8 @@
 namespace p2v {
 
 constexpr int ENC_SMALL_WARPS = 4;
+constexpr int ENC_WARP_K_MAX = 4096;      // warp-per-tree encode for batches of trees up to here (above, two
+                                          // trees per SM are too few: measured 0.6x at n = 8192)
 constexpr int ENC_LARGE_THREADS = 256;
 constexpr int ENC_LARGE_WARPS = ENC_LARGE_THREADS / 32;
 
@@ -78,6 +80,20 @@ __device__ __forceinline__ void count_smaller_pair(uint32_t r_a, bool act_a, uin
     cnt_b = (uint32_t)__half2int_rz(__high2half(cnt));
 }
 
+// The same count with 32-bit integers for rows >= 2048 (mid-size trees).
+__device__ __forceinline__ void count_smaller_pair_int(uint32_t r_a, bool act_a, uint32_t r_b, bool act_b,
+                                                       uint32_t& cnt_a, uint32_t& cnt_b) {
+    const uint32_t ma = act_a ? r_a : 0x7FFFFFFFu, mb = act_b ? r_b : 0x7FFFFFFFu;
+    cnt_a = 0; cnt_b = 0;
+#pragma unroll
+    for (int d = 1; d < 32; ++d) {
+        count_smaller_step(cnt_a, ma, d);
+        count_smaller_step(cnt_b, mb, d);
+    }
+}
+
+// WPL = "rows seen" mask words per lane: 1 / 2 for k <= 1024 / 2047 (four warps per CTA, half2
+// counts), 4 for batches of mid-size trees (k <= 4096; one warp per CTA, integer counts).
 template <typename IdxT, int MODE, int WPL>
 __global__ void __launch_bounds__(ENC_SMALL_WARPS * 32)
 encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restrict__ vout,
@@ -99,8 +115,9 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
     const int in_cols = (MODE == FROM_PAIRS) ? 2 : (MODE == FROM_ANCESTRY ? 3 : 4);
     const uint32_t kint = (uint32_t)k + 1;      // first internal label
 
-    for (int64_t tree = (int64_t)blockIdx.x * ENC_SMALL_WARPS + warp; tree < B;
-         tree += (int64_t)gridDim.x * ENC_SMALL_WARPS) {
+    const int nwarps = blockDim.x >> 5;
+    for (int64_t tree = (int64_t)blockIdx.x * nwarps + warp; tree < B;
+         tree += (int64_t)gridDim.x * nwarps) {
         const IdxT* it = in + tree * ((int64_t)k * in_cols);
         bool bad = false;
         // ---- E1: load rows (4 batches of loads in flight) -------------------------------------
@@ -245,7 +262,8 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
             const uint32_t ra = act_a ? (uint32_t)spr[ca] : 0u;
             const uint32_t rb = act_b ? (uint32_t)spr[cb] : 0u;
             uint32_t inb_a, inb_b;
-            count_smaller_pair(ra, act_a, rb, act_b, inb_a, inb_b);
+            if (WPL <= 2) count_smaller_pair(ra, act_a, rb, act_b, inb_a, inb_b);
+            else count_smaller_pair_int(ra, act_a, rb, act_b, inb_a, inb_b);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int c = h ? cb : ca;
@@ -259,12 +277,27 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                 const uint32_t src = g / WPL;
                 uint32_t idx = __shfl_sync(FULL, excl, src) + (h ? inb_b : inb_a);
                 const uint32_t low = (1u << (r & 31)) - 1u;
+                if (WPL <= 2) {
 #pragma unroll
-                for (int j = 0; j < WPL; ++j) {
-                    const uint32_t wj = __shfl_sync(FULL, word[j], src);
+                    for (int j = 0; j < WPL; ++j) {
+                        const uint32_t wj = __shfl_sync(FULL, word[j], src);
+                        const uint32_t jj = g - src * WPL;
+                        if ((uint32_t)j < jj) idx += __popc(wj);
+                        else if ((uint32_t)j == jj) idx += __popc(wj & low);
+                    }
+                } else {      // the words of lane `src` straight from shared memory (current: barrier below)
                     const uint32_t jj = g - src * WPL;
-                    if ((uint32_t)j < jj) idx += __popc(wj);
-                    else if ((uint32_t)j == jj) idx += __popc(wj & low);
+#pragma unroll
+                    for (int j4 = 0; j4 < WPL / 4; ++j4) {
+                        const uint4 q = reinterpret_cast<const uint4*>(smask + src * WPL)[j4];
+                        const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t jx = (uint32_t)(4 * j4 + j);
+                            if (jx < jj) idx += __popc(qq[j]);
+                            else if (jx == jj) idx += __popc(qq[j] & low);
+                        }
+                    }
                 }
                 if (act) {
                     const uint32_t lo = min((uint32_t)sc1[r], (uint32_t)sc2[r]);
@@ -463,22 +496,26 @@ size_t encode_workspace_bytes(int64_t B, int64_t k) {
 template <typename IdxT, int MODE>
 static cudaError_t launch_encode_t(const void* in, int64_t B, int64_t k, void* v, int32_t* status,
                                    void* ws, size_t ws_bytes, cudaStream_t stream) {
-    if (k <= ENC_SMALL_K_MAX) {
+    // batches of mid-size trees stay on the warp-per-tree kernel (a fraction of the CTA kernel's work)
+    if (k <= ENC_SMALL_K_MAX || (k <= ENC_WARP_K_MAX && B * 4 > sm_count())) {
         const int K = (int)((k + 31) & ~31);
-        const int wpl = (k <= 1024) ? 1 : 2;
+        const int wpl = (k <= 1024) ? 1 : (k <= ENC_SMALL_K_MAX ? 2 : 4);
+        const int warps = (wpl <= 2) ? ENC_SMALL_WARPS : 1;
         const size_t per_warp = (size_t)(MODE != FROM_PAIRS ? 5 : 3) * (K + 32) + 64 * wpl;
-        const size_t smem = ENC_SMALL_WARPS * per_warp * sizeof(uint16_t);
-        auto kern = (wpl == 1) ? encode_small_kernel<IdxT, MODE, 1> : encode_small_kernel<IdxT, MODE, 2>;
+        const size_t smem = warps * per_warp * sizeof(uint16_t);
+        auto kern = encode_small_kernel<IdxT, MODE, 1>;
+        if (wpl == 2) kern = encode_small_kernel<IdxT, MODE, 2>;
+        else if (wpl == 4) kern = encode_small_kernel<IdxT, MODE, 4>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, ENC_SMALL_WARPS * 32, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
-        int64_t want = (B + ENC_SMALL_WARPS - 1) / ENC_SMALL_WARPS;
+        int64_t want = (B + warps - 1) / warps;
         int64_t cap = (int64_t)sm_count() * per_sm;
         const int grid = (int)(want < cap ? want : cap);
-        kern<<<grid, ENC_SMALL_WARPS * 32, smem, stream>>>((const IdxT*)in, B, (int)k, (IdxT*)v, status, K);
+        kern<<<grid, warps * 32, smem, stream>>>((const IdxT*)in, B, (int)k, (IdxT*)v, status, K);
     } else {
         const size_t stride = enc_large_stride(k);
         const int grid = enc_large_grid(B);

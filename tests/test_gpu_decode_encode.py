@@ -135,6 +135,33 @@ def test_decode_parity_mid_batches(p2v, n_leaves, dtype):
     assert status[3].item() == k // 2 + 1 and int(status.count_nonzero()) == 1
 
 
+@pytest.mark.parametrize("n_leaves", [2048, 2049, 2050, 3000, 4096, 4097, 4098, 5000, 8192, 8193, 8194, 9000])
+@pytest.mark.parametrize("dtype", [torch.int64, torch.int32])
+def test_encode_parity_mid_batches(p2v, n_leaves, dtype):
+    """Batches of mid-size trees on the warp-per-tree encode kernel (4 / 8 mask words per lane)."""
+    B = 40
+    V = sample_vectors(B, n_leaves, seed=13 * n_leaves)
+    adv = list(adversarial_vectors(n_leaves).values())
+    V[:len(adv)] = np.stack(adv)
+    k = n_leaves - 1
+    pairs, _ = O.batch("to_pairs", V, k)
+    anc, _ = O.batch("to_ancestry", V, k)
+    edges, _ = O.batch("to_edges", V, k)
+    rng = np.random.default_rng(n_leaves)
+    perm = rng.permutation(k)
+    shuffled = edges.reshape(B, k, 2, 2)[:, perm].reshape(B, 2 * k, 2)     # from_edges orders by parent itself
+    for name, fn, x in (("from_pairs", p2v.from_pairs_batch, pairs), ("from_ancestry", p2v.from_ancestry_batch, anc),
+                        ("from_edges", p2v.from_edges_batch, edges), ("from_edges", p2v.from_edges_batch, shuffled)):
+        got = fn(dev(x, dtype))
+        assert got.dtype == dtype
+        assert np.array_equal(got.cpu().numpy().astype(np.int64), V), (name, n_leaves)
+    bad = anc.copy()
+    bad[5, 3, 2] = 1                      # a leaf label as parent
+    status = torch.zeros(B, dtype=torch.int32, device="cuda")
+    p2v.from_ancestry_batch(dev(bad, dtype), status=status, check=False)
+    assert status[5].item() == -2 and int(status.count_nonzero()) == 1
+
+
 @pytest.mark.parametrize("n_leaves", SIZES)
 @pytest.mark.parametrize("dtype", [torch.int64, torch.int32])
 def test_encode_parity_and_round_trip(p2v, n_leaves, dtype):
