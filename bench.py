@@ -362,11 +362,13 @@ def bench_newick(torch, lib, device, peak):
         out = torch.empty((B, stride), dtype=torch.uint8, device=device)
         lengths = torch.empty(B, dtype=torch.int64, device=device)
         st = torch.empty(B, dtype=torch.int32, device=device)
+        need = int(lib.p2v_newick_workspace_bytes(B, k))
+        ws = torch.empty(max(need, 16), dtype=torch.uint8, device=device)
         stream = torch.cuda.current_stream(device)
 
         def call():
             rc = lib.p2v_to_newick_batch(V.data_ptr(), 8, B, k, out.data_ptr(), stride, lengths.data_ptr(),
-                                         st.data_ptr(), stream.cuda_stream)
+                                         st.data_ptr(), ws.data_ptr(), need, stream.cuda_stream)
             assert rc == 0, lib.p2v_last_error()
         for _ in range(3):
             call()
@@ -389,7 +391,7 @@ def bench_newick(torch, lib, device, peak):
         res[f"n{n}"] = {"batch": B, "trees_per_s": B / t, "gbs": nbytes / t / 1e9, "frac_of_peak": nbytes / t / 1e9 / peak,
                         "cpu": {"sample": Bc, "trees_per_s": Bc / tc, "cores": host_threads(), "kind": "port"},
                         "matches_cpu": same}
-        del V, out
+        del V, out, ws
     return res
 
 

@@ -152,8 +152,10 @@ int p2v_node_depths_batch(const void *v_or_matrix, int idx_bytes, const double *
  * its length without the NUL, 0 for an invalid vector.  1 <= k <= 1023 for now
  * (P2V_ERR_UNSUPPORTED above; the matrix form with branch lengths is not built). */
 size_t p2v_newick_max_bytes(int64_t k);
+size_t p2v_newick_workspace_bytes(int64_t B, int64_t k);     /* the int32 ancestry of the batch */
 int p2v_to_newick_batch(const void *v, int idx_bytes, int64_t B, int64_t k, char *out, int64_t out_stride,
-                        int64_t *lengths, int32_t *status, p2v_stream_t stream);
+                        int64_t *lengths, int32_t *status, void *workspace, size_t workspace_bytes,
+                        p2v_stream_t stream);
 
 /* ---- host-buffer entry points (H2D + kernels + D2H inside the call) ------ */
 int p2v_to_pairs_host(const void *v, int idx_bytes, int64_t B, int64_t k, void *pairs, int32_t *status);

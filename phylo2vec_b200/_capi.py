@@ -42,7 +42,8 @@ SIGNATURES = {
     "p2v_vcv_matrix_host": (_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "p2v_node_depths_host": (_int, [_vp, _int, _vp, _i64, _i64, _vp, _vp]),
     "p2v_newick_max_bytes": (_sz, [_i64]),
-    "p2v_to_newick_batch": (_int, [_vp, _int, _i64, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "p2v_newick_workspace_bytes": (_sz, [_i64, _i64]),
+    "p2v_to_newick_batch": (_int, [_vp, _int, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "p2v_to_newick_host": (_int, [_vp, _int, _i64, _i64, _vp, _i64, _vp, _vp]),
     "p2v_cophenetic_host": (_int, [_vp, _int, _vp, _i64, _i64, _int, _i64, _i64, _vp, _vp]),
     "p2v_cophenetic_matrix_host": (_int, [_vp, _i64, _i64, _int, _i64, _i64, _vp, _vp]),

@@ -306,9 +306,12 @@ def to_newick_batch(V, status=None, check: bool = True, raw: bool = False):
     lengths = torch.empty(B, dtype=torch.int64, device=V.device)
     if status is None:
         status = torch.empty(B, dtype=torch.int32, device=V.device)
+    need = int(lib.p2v_newick_workspace_bytes(B, k))
     with torch.cuda.device(V.device):
+        ws = torch.empty(max(need, 16), dtype=torch.uint8, device=V.device)
         rc = lib.p2v_to_newick_batch(V.data_ptr(), V.element_size(), B, k, out.data_ptr(), stride,
-                                     lengths.data_ptr(), status.data_ptr(), _stream_ptr(V.device))
+                                     lengths.data_ptr(), status.data_ptr(), ws.data_ptr(), need,
+                                     _stream_ptr(V.device))
     _capi.check(rc, "to_newick")
     if check and bool(status.any()):
         raise_for_status(status, V)

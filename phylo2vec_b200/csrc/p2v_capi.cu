@@ -406,6 +406,7 @@ int p2v_node_depths_host(const void* v_or_matrix, int idx_bytes, const double* b
 
 // ---- to_newick --------------------------------------------------------------------------
 size_t p2v_newick_max_bytes(int64_t k) { return newick_max_bytes(k); }
+size_t p2v_newick_workspace_bytes(int64_t B, int64_t k) { return newick_workspace_bytes(B, k); }
 static int newick_check(const void* v, const char* out, int idx_bytes, int64_t B, int64_t k, int64_t out_stride) {
     if (idx_bytes != 4 && idx_bytes != 8) return fail(P2V_ERR_INVALID_ARG, "idx_bytes must be 4 or 8");
     if (B < 0 || k < 0) return fail(P2V_ERR_INVALID_ARG, "negative batch or length");
@@ -423,43 +424,42 @@ __global__ void newick_k0_kernel(char* out, int64_t out_stride, int64_t B, int64
     }
 }
 static cudaError_t newick_launch_any(const void* v, int idx_bytes, int64_t B, int64_t k, char* out, int64_t out_stride,
-                                     int64_t* lengths, int32_t* status, cudaStream_t st) {
+                                     int64_t* lengths, int32_t* status, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     if (k == 0) {
         newick_k0_kernel<<<(int)((B + 255) / 256 < 1024 ? (B + 255) / 256 : 1024), 256, 0, st>>>(out, out_stride, B, lengths, status);
         count_launch();
         return cudaGetLastError();
     }
-    return launch_to_newick(v, idx_bytes, B, k, out, out_stride, lengths, status, st);
+    return launch_to_newick(v, idx_bytes, B, k, out, out_stride, lengths, status, ws, ws_bytes, st);
 }
 int p2v_to_newick_batch(const void* v, int idx_bytes, int64_t B, int64_t k, char* out, int64_t out_stride,
-                        int64_t* lengths, int32_t* status, p2v_stream_t stream) {
+                        int64_t* lengths, int32_t* status, void* ws, size_t ws_bytes, p2v_stream_t stream) {
     int rc = newick_check(v, out, idx_bytes, B, k, out_stride);
     if (rc) return rc;
-    return from_cuda(newick_launch_any(v, idx_bytes, B, k, out, out_stride, lengths, status, (cudaStream_t)stream),
-                     "to_newick launch");
+    if (ws_bytes < newick_workspace_bytes(B, k) || (!ws && newick_workspace_bytes(B, k) > 0))
+        return fail(P2V_ERR_WORKSPACE, "to_newick workspace too small");
+    return from_cuda(newick_launch_any(v, idx_bytes, B, k, out, out_stride, lengths, status, ws, ws_bytes,
+                                       (cudaStream_t)stream), "to_newick launch");
 }
 int p2v_to_newick_host(const void* v, int idx_bytes, int64_t B, int64_t k, char* out, int64_t out_stride,
                        int64_t* lengths, int32_t* status) {
     int rc = newick_check(v, out, idx_bytes, B, k, out_stride);
     if (rc) return rc;
     if (B == 0) return P2V_OK;
-    // device lengths ride behind each tree's string: the staged row is out_stride bytes + 8
-    const size_t row = ((size_t)out_stride + 7) & ~(size_t)7;
     int64_t done = 0;
     int64_t* dlen[HOST_STREAMS] = {};
     int64_t cap_chunk = 0;
     int flip = 0;
-    (void)row;
     int r = host_chunked(
         v, (size_t)k * idx_bytes, out, (size_t)out_stride, status, B,
-        [&](int64_t nb) { cap_chunk = nb; return (size_t)0; },
-        [&](void* din, void* dout, int32_t* dst, int64_t nb, void*, size_t, cudaStream_t st) {
+        [&](int64_t nb) { cap_chunk = nb; return newick_workspace_bytes(nb, k); },
+        [&](void* din, void* dout, int32_t* dst, int64_t nb, void* ws, size_t wsb, cudaStream_t st) {
             cudaError_t e = cudaSuccess;
             const int s = flip; flip = (flip + 1) % HOST_STREAMS;
             if (!dlen[s]) e = cudaMalloc((void**)&dlen[s], sizeof(int64_t) * (size_t)cap_chunk);
             if (e != cudaSuccess) return e;
-            e = newick_launch_any(din, idx_bytes, nb, k, (char*)dout, out_stride, dlen[s], dst, st);
+            e = newick_launch_any(din, idx_bytes, nb, k, (char*)dout, out_stride, dlen[s], dst, ws, wsb, st);
             if (e == cudaSuccess && lengths)
                 e = cudaMemcpyAsync(lengths + done, dlen[s], sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, st);
             done += nb;

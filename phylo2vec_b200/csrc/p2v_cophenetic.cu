@@ -148,6 +148,13 @@ __global__ void narrow_v_kernel(const long long* __restrict__ v, int64_t count, 
     }
 }
 
+cudaError_t launch_narrow_v(const long long* v, int64_t count, int* out, cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    narrow_v_kernel<<<sm_count() * 8, 256, 0, stream>>>(v, count, out);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // parse_matrix (matrix/base.rs:108-121): v = m[:,0] as usize (truncating, saturating cast)
 __global__ void matrix_v_kernel(const double* __restrict__ m, int64_t count, int* __restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;

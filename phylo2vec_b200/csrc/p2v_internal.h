@@ -50,7 +50,10 @@ cudaError_t launch_fill_f64(double* out, int64_t count, double value, cudaStream
 
 // to_newick (vectors, k <= 1023): strings at out + b * out_stride, NUL-terminated; lengths without the NUL
 size_t newick_max_bytes(int64_t k);
+size_t newick_workspace_bytes(int64_t B, int64_t k);
 cudaError_t launch_to_newick(const void* v, int idx_bytes, int64_t B, int64_t k, char* out, int64_t out_stride,
-                             int64_t* lengths, int32_t* status, cudaStream_t stream);
+                             int64_t* lengths, int32_t* status, void* ws, size_t ws_bytes, cudaStream_t stream);
+// int64 -> int32 index vectors (values that do not fit become -1 and fail check_v downstream)
+cudaError_t launch_narrow_v(const long long* v, int64_t count, int* out, cudaStream_t stream);
 
 }  // namespace p2v
