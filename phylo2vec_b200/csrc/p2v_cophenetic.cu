@@ -937,6 +937,7 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
 // Same arithmetic as the row kernel's in-block values: distances are (d_i - d_lca) + (d_j - d_lca),
 // each difference of double-doubles rounded once.
 constexpr int CS_N_MAX = 512;            // capacity of the fused kernel
+constexpr int CS_MAXLC = 5;              // label-order column pairs per lane: 64 * 5 = 320 columns
 constexpr int CS_N_DEFAULT = 320;        // used up to here (above, the general kernels are faster)
 constexpr int CS_THREADS = 128;
 constexpr unsigned CS_NONE = 0xFFFFu;
@@ -944,7 +945,7 @@ constexpr unsigned CS_NONE = 0xFFFFu;
 constexpr int CS_TREES = CS_THREADS / 32;       // trees decoded side by side (one per warp) per CTA pass
 
 struct SmallLayout {
-    size_t dec, anc, ja, jd, dl, dr, nxt, cnt, pos, leaf_at, dipos, sepd, ddpos, jh, jl, st, rowbuf, total;
+    size_t dec, anc, ja, jd, dl, dr, nxt, cnt, pos, leaf_at, dipos, sepd, ddpos, jh, jl, st, rowbuf, colk, total;
     size_t dec_stride, anc_stride;
     int levels, tpp;                    // tpp: trees decoded side by side per pass (one per warp)
 };
@@ -965,7 +966,7 @@ __host__ __device__ inline SmallLayout small_layout(int k, bool topo) {
     L.dr = o; o = al16(o + 2 * 2 * N);
     L.nxt = o; o = al16(o + 2 * 2 * n);
     L.cnt = o; o = al16(o + 2 * 2 * n);
-    L.pos = o; o = al16(o + 2 * n);
+    L.pos = o; o = al16(o + 2 * (n + 1));
     L.leaf_at = o; o = al16(o + 2 * n);
     const size_t P32 = (n + 31) & ~(size_t)31;          // positions padded to whole chunks of 32
     L.dipos = o; o = al16(o + 2 * P32);
@@ -983,12 +984,15 @@ __host__ __device__ inline SmallLayout small_layout(int k, bool topo) {
     o = a0 + 4 * stn * (size_t)(L.levels - 1);
     o = al16(o);
     L.rowbuf = o; o = al16(o + (size_t)(CS_THREADS / 32) * 8 * P32);
+    L.colk = o; o = al16(o + (size_t)(CS_THREADS / 32) * 4 * P32);     // column candidates of a warp's tile
     L.total = (o > a1 ? o : a1);
     return L;
 }
 
 
-template <bool TOPO, bool VCV, bool VEC2>
+// TILED: rows by tiles of 32 DFS positions with per-lane label-order columns in registers (pays off
+// from n ~ 150); otherwise one sparse-table query per element and a DFS-ordered row buffer.
+template <bool TOPO, bool VCV, bool VEC2, bool TILED>
 __global__ void __launch_bounds__(CS_THREADS, 8)
 coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, int bl_stride, int64_t bl_tree_stride,
                   int64_t B, int k, int unrooted, int64_t row_begin, int64_t row_end, double* __restrict__ out,
@@ -1017,6 +1021,7 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
     uint32_t* st = reinterpret_cast<uint32_t*>(dyn + L.st);
     const int rb_stride = (n + 31) & ~31;
     double* rowbuf = reinterpret_cast<double*>(dyn + L.rowbuf) + (size_t)warp * rb_stride;
+    uint32_t* colk = reinterpret_cast<uint32_t*>(dyn + L.colk) + (size_t)warp * rb_stride;
     const int64_t rows = row_end - row_begin;
     const int stn = (n + 1 + 3) & ~3;             // entries per sparse-table level
 
@@ -1139,6 +1144,7 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
                 st[lev * stn + r] = min(st[(lev - 1) * stn + r], st[(lev - 1) * stn + r + half]);
             __syncthreads();
         }
+        if (!TILED) {
         // ---- 4. rows ------------------------------------------------------------------------------
         double* orow = out + ((size_t)tree * rows + warp) * n;
         const int i_end = (int)row_end;
@@ -1184,6 +1190,141 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
                 for (int j = lane; j < n; j += 32) __stcs(orow + j, rowbuf[pos[j]]);
             }
             __syncwarp();
+        }
+        } else {
+        // ---- 4. rows, a tile of 32 consecutive DFS positions per warp ---------------------------------
+        // For a row at position q of tile t and a column at position p of another chunk c the range
+        // of separators (min(p,q), max(p,q)] splits at the tile boundary: the row's part (inside the
+        // tile, one value per row and side) and the column's part (from the tile boundary to p, one
+        // value per column and tile, from chunk-wise min scans) -- the LCA key is the min of the two.
+        // Columns inside the tile itself take one sparse-table query each.
+        double* obase = out + (size_t)tree * rows * n;
+        const int nch = (n + 31) >> 5;
+        const uint32_t KINF = 0xFFFFFFFFu;
+        // fewer tiles than warps (n <= 96): the rows of a tile are dealt round-robin to NS warps
+        const int NS = (nch < NW) ? NW / nch : 1;
+        const int rsub = (nch < NW) ? warp / nch : 0;
+        for (int t = (nch < NW) ? warp % nch : warp; t < nch && rsub < NS; t += NW) {
+            const int base = t << 5;
+            // does the tile hold any requested row?  (labels of its positions)
+            const int qmine = base + lane;
+            const int lab_mine = (qmine < n) ? (int)leaf_at[qmine] : -1;
+            const bool want = lab_mine >= (int)row_begin && lab_mine < (int)row_end;
+            const unsigned wantmask = __ballot_sync(FULL, want);
+            if (!wantmask) continue;              // warp-uniform
+            // column parts: right of the tile ...
+            uint32_t carry = KINF;
+            for (int c = t + 1; c < nch; ++c) {
+                const int p = (c << 5) + lane;
+                uint32_t x = (p < n) ? st[p] : KINF;          // key[p]: separator between p - 1 and p
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(FULL, x, d);
+                    if (lane >= d) x = min(x, y);
+                }
+                x = min(x, carry);
+                colk[p] = x;
+                carry = __shfl_sync(FULL, x, 31);
+            }
+            // ... and left of it (separators p + 1 .. base)
+            carry = KINF;
+            for (int c = t - 1; c >= 0; --c) {
+                const int p = (c << 5) + lane;
+                uint32_t x = st[p + 1];                        // p + 1 <= base <= n - 1
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_down_sync(FULL, x, d);
+                    if (lane + d < 32) x = min(x, y);
+                }
+                x = min(x, carry);
+                colk[p] = x;
+                carry = __shfl_sync(FULL, x, 0);
+            }
+            // row parts of lane's own row: separators q + 1 .. base + 31 and base + 1 .. q
+            uint32_t rowR, rowL;
+            {
+                const int qn = qmine + 1;
+                uint32_t x = (lane < 31 && qn < n) ? st[qn] : KINF;      // key[q + 1], not past the tile
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_down_sync(FULL, x, d);
+                    if (lane + d < 32) x = min(x, y);
+                }
+                rowR = x;
+                uint32_t z = (lane > 0 && qmine < n) ? st[qmine] : KINF; // key[q], not before the tile
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(FULL, z, d);
+                    if (lane >= d) z = min(z, y);
+                }
+                rowL = z;
+            }
+            __syncwarp();
+            // per-lane columns in LABEL order: pairs (j, j + 1), j = 64 * lc + 2 * lane.  Their
+            // positions, column candidates and depths stay in registers for all rows of the tile.
+            uint32_t cpos[CS_MAXLC], ckey0[CS_MAXLC], ckey1[CS_MAXLC], cdi[CS_MAXLC];
+#pragma unroll
+            for (int lc = 0; lc < CS_MAXLC; ++lc) {
+                const int j = 64 * lc + 2 * lane;
+                cpos[lc] = 0; ckey0[lc] = KINF; ckey1[lc] = KINF; cdi[lc] = 0;
+                if (j < n) {
+                    const uint32_t pp = *reinterpret_cast<const uint32_t*>(pos + j);   // pos is padded to even n
+                    const uint32_t p0 = pp & 0xFFFFu, p1 = (j + 1 < n) ? (pp >> 16) : p0;
+                    cpos[lc] = p0 | (p1 << 16);
+                    ckey0[lc] = colk[p0]; ckey1[lc] = colk[p1];          // (unused for in-tile columns)
+                    cdi[lc] = (uint32_t)dipos[p0] | ((uint32_t)dipos[p1] << 16);
+                }
+            }
+            double* tilebuf = rowbuf;             // 32 in-tile values of the current row
+            for (int r = 0; r < 32; ++r) {
+                if (!((wantmask >> r) & 1u) || (r % NS) != rsub) continue;        // warp-uniform
+                const int q = base + r;
+                const int i = __shfl_sync(FULL, lab_mine, r);
+                const uint32_t rR = __shfl_sync(FULL, rowR, r), rL = __shfl_sync(FULL, rowL, r);
+                const int di = dipos[q];
+                double2 dq = make_double2(0.0, 0.0);
+                if (!TOPO) dq = ddpos[q];
+                auto value = [&](uint32_t m, uint32_t p, int dj_i) -> double {
+                    if (TOPO) {
+                        const int dlca = (int)(m >> 16);
+                        return VCV ? int_to_f64(dlca) : int_to_f64(di + dj_i - 2 * dlca);
+                    }
+                    const double2 sd = sepd[min(m & 0xFFFFu, (uint32_t)n)];
+                    if (VCV) return sd.x;
+                    const double2 dj = ddpos[p];
+                    return __dadd_rn(dd_sub_round(dq.x, dq.y, sd.x, sd.y), dd_sub_round(dj.x, dj.y, sd.x, sd.y));
+                };
+                {   // inside the tile: one sparse-table query per position
+                    const int p = base + lane;
+                    const int pc = min(p, k);
+                    const int a = min(pc, q) + 1, b = max(pc, q);
+                    const int lev = 31 - __clz(max(b - a + 1, 1));
+                    const uint32_t m = min(st[lev * stn + a], st[lev * stn + b - (1 << lev) + 1]);
+                    double val = value(m, (uint32_t)pc, (int)dipos[pc]);
+                    if (p == q) val = VCV ? (TOPO ? int_to_f64(di) : dq.x) : 0.0;
+                    tilebuf[lane] = val;
+                }
+                __syncwarp();
+                double* orow = obase + (size_t)(i - (int)row_begin) * n;
+#pragma unroll
+                for (int lc = 0; lc < CS_MAXLC; ++lc) {
+                    const int j = 64 * lc + 2 * lane;
+                    if (j < n) {
+                        const uint32_t p0 = cpos[lc] & 0xFFFFu, p1 = cpos[lc] >> 16;
+                        const uint32_t o0 = p0 - (uint32_t)base, o1 = p1 - (uint32_t)base;   // < 32: in the tile
+                        const uint32_t m0 = min(p0 > (uint32_t)base ? rR : rL, ckey0[lc]);
+                        const uint32_t m1 = min(p1 > (uint32_t)base ? rR : rL, ckey1[lc]);
+                        double v0 = value(m0, p0, (int)(cdi[lc] & 0xFFFFu));
+                        double v1 = value(m1, p1, (int)(cdi[lc] >> 16));
+                        if (o0 < 32u) v0 = tilebuf[o0];
+                        if (o1 < 32u) v1 = tilebuf[o1];
+                        if (j + 1 < n) store2<VEC2>(orow + j, v0, v1);
+                        else __stcs(orow + j, v0);
+                    }
+                }
+                __syncwarp();
+            }
+        }
         }
         __syncthreads();                          // rows done before the next tree's tables are built
         }  // sub
@@ -1455,10 +1596,13 @@ static cudaError_t launch_cophenetic_small(const void* v_or_matrix, int idx_byte
     const size_t smem = SL.total;
     const int tpp = SL.tpp;
     const bool vec2 = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    // measured: fp64 distance rows are bound by the double-double math either way, so only the
+    // integer and vcv rows take the tiled path
+    const bool tiled = (n > 160) && (topo || what != 0);
     cudaError_t e = cudaSuccess;
 #define P2V_SMALL(T_, W_, V_)                                                                          \
     do {                                                                                               \
-        auto kern = coph_small_kernel<T_, W_, V_>;                                                     \
+        auto kern = tiled ? coph_small_kernel<T_, W_, V_, true> : coph_small_kernel<T_, W_, V_, false>; \
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
         if (e != cudaSuccess) return e;                                                                \
         int per_sm = 0;                                                                                \
