@@ -28,6 +28,9 @@ namespace p2v {
 
 constexpr int SMALL_WARPS = 4;             // warps (= trees in flight) per CTA, small kernel
 
+// uint32 entries of the merge kernel's per-team work arrays (K = k rounded up to 32)
+__host__ __device__ inline size_t large_base_stride(size_t K) { return 7 * K + (K >> 5) + 128; }
+
 // One warp per tree, all state in shared memory (p2v_decode_warp.cuh).  k <= 2016: four warps
 // per CTA; mid-size trees (k <= 16384): one warp per CTA, so that the per-tree shared memory
 // (6 bytes per leaf) still leaves several trees in flight per SM.
@@ -220,6 +223,78 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
         }
         if (MODE == MODE_PAIRS) { team_sync<CSIZE>(); continue; }
 
+        // ---- ancestry / edges, few large trees: the relabel sweep split over W warps ------------------
+        // Worker w owns a contiguous range of slots and a private "last row with label x" table.
+        // 1. every worker records the last row of each label inside its range; 2. an exclusive
+        // prefix over the workers turns table w into "last row with label x before range w";
+        // 3. every worker runs the sweep below on its range, starting from that state.
+        const int K2 = K + 32;
+        const int W = (CSIZE > 1) ? (int)((ws_stride - large_base_stride((size_t)K)) / (size_t)K2) : 0;
+        if (CSIZE > 1 && W >= 2) {
+            uint32_t* ptab = reinterpret_cast<uint32_t*>(ws + (size_t)team * ws_stride) + large_base_stride((size_t)K);
+            for (size_t i = tid; i < (size_t)W * K2; i += TT) ptab[i] = NONE32;
+            team_sync<CSIZE>();
+            const int wstep = NWT / W;                       // workers are spread over the CTAs of the cluster
+            const bool worker = (gw % wstep) == 0 && (gw / wstep) < W;
+            const int w = gw / wstep;
+            const int bpw = (nbat + W - 1) / W;
+            const int b0 = min(nbat, w * bpw), b1 = min(nbat, b0 + bpw);
+            uint32_t* mytab = ptab + (size_t)w * K2;
+            if (worker) {
+                for (int b = b0; b < b1; ++b) {
+                    const int s = b * 32 + lane;
+                    const bool act = s < k;
+                    const uint32_t lab = act ? ((uint32_t)wlab[s] & (ROOTBIT - 1u)) : 0u;
+                    const uint32_t peers = __match_any_sync(FULL, act ? lab : (0x40000000u + lane));
+                    if (act && (peers & lanes_gt(lane)) == 0) mytab[lab] = (uint32_t)s;
+                    __syncwarp();                            // the next batch may write the same label
+                }
+            }
+            team_sync<CSIZE>();
+            for (int x = tid; x < K2; x += TT) {             // exclusive prefix over the workers
+                uint32_t run = NONE32;
+                for (int ww = 0; ww < W; ++ww) {
+                    const uint32_t cur = ptab[(size_t)ww * K2 + x];
+                    ptab[(size_t)ww * K2 + x] = run;
+                    if (cur != NONE32) run = cur;            // rows grow with the worker index
+                }
+            }
+            team_sync<CSIZE>();
+            if (worker && b0 < b1) {
+                uint32_t nlab = (b0 * 32 + lane < k) ? (uint32_t)wlab[b0 * 32 + lane] : 0u;
+                uint32_t nt = (b0 * 32 + lane < k) ? (uint32_t)time_at[b0 * 32 + lane] : 0u;
+                for (int b = b0; b < b1; ++b) {
+                    const int s = b * 32 + lane;
+                    const bool act = s < k;
+                    const uint32_t labr = nlab, t = nt;
+                    if (b + 1 < b1) {                        // prefetch the next batch
+                        const int s2 = s + 32;
+                        nlab = (s2 < k) ? (uint32_t)wlab[s2] : 0u;
+                        nt = (s2 < k) ? (uint32_t)time_at[s2] : 0u;
+                    }
+                    const uint32_t lab = labr & (ROOTBIT - 1u);
+                    const bool root = act && (labr & ROOTBIT);
+                    const uint32_t peers = __match_any_sync(FULL, act ? lab : (0x40000000u + lane));
+                    uint32_t c1p = (uint32_t)(k + s);
+                    if (root) {
+                        const uint32_t lower = peers & lanes_lt(lane);
+                        const uint32_t cand = lower ? (uint32_t)(b * 32 + 31 - __clz(lower)) : mytab[lab];
+                        c1p = (cand != NONE32) ? (uint32_t)(k + 1) + cand : lab;
+                    }
+                    __syncwarp();
+                    if (act && (peers & lanes_gt(lane)) == 0) mytab[lab] = (uint32_t)s;
+                    __syncwarp();
+                    if (act) {
+                        const uint32_t q = mytab[t + 1];
+                        const uint32_t c2p = (q != NONE32) ? (uint32_t)(k + 1) + q : t + 1;
+                        store_row<IdxT, MODE>(ot, s, (IdxT)c1p, (IdxT)c2p, (IdxT)(k + 1 + s));
+                    }
+                }
+            }
+            team_sync<CSIZE>();
+            continue;
+        }
+
         // ---- ancestry / edges: forward relabel sweep, one warp, table of the last row per label --
         if (SMEMTBL) {
             if (crank == 0)
@@ -316,9 +391,13 @@ static size_t mid_smem_bytes(int64_t k) {
     return (tbl + 6 * K + (K >> 5) + 32 + 2) * sizeof(uint16_t) + 16 * sizeof(int) + 16;
 }
 
-static size_t large_ws_stride(int64_t k) {  // uint32 elements per team
+constexpr int SWEEP_WORKERS = 64;          // warps sharing the relabel sweep of one large tree (cluster mode)
+static bool few_large_trees(int64_t B, int64_t k) { return (B * 8 <= sm_count()) && k >= 8192; }
+static size_t large_ws_stride(int64_t B, int64_t k) {  // uint32 elements per team
     const size_t K = ((size_t)k + 31) & ~(size_t)31;
-    return 7 * K + (K >> 5) + 128;
+    size_t stride = large_base_stride(K);
+    if (few_large_trees(B, k)) stride += (size_t)SWEEP_WORKERS * (K + 32);   // per-worker label tables
+    return stride;
 }
 static int large_teams(int64_t B) {
     const int64_t cap = (int64_t)sm_count() * 4;
@@ -327,7 +406,7 @@ static int large_teams(int64_t B) {
 
 size_t decode_workspace_bytes(int64_t B, int64_t k) {
     if (k <= MID_K_MAX || B <= 0) return 0;
-    return (size_t)large_teams(B) * large_ws_stride(k) * sizeof(uint32_t);
+    return (size_t)large_teams(B) * large_ws_stride(B, k) * sizeof(uint32_t);
 }
 
 template <typename IdxT, int MODE, int CSIZE, int THREADS, bool SMEMTBL, typename WT = uint32_t, bool SMEMARR = false>
@@ -407,14 +486,14 @@ static cudaError_t launch_decode_t(const void* v, int64_t B, int64_t k, void* ou
             return cudaErrorLaunchFailure;
     } else {
         if (k > LARGE_K_MAX) return cudaErrorNotSupported;
-        const size_t stride = large_ws_stride(k);
+        const size_t stride = large_ws_stride(B, k);
         const int teams = large_teams(B);
         if (!ws || ws_bytes < (size_t)teams * stride * sizeof(uint32_t)) return cudaErrorInvalidValue;
         // last-row-per-label table in shared memory as uint16 while slots fit (k <= 65535)
         const bool smemtbl = (MODE != MODE_PAIRS) && (k <= 65535);
         const size_t smem = smemtbl ? ((size_t)k + 2 + 7) / 8 * 8 * sizeof(uint16_t) : 0;
         bool ok = false;
-        const bool few_large = (B * 8 <= sm_count()) && k >= 8192;
+        const bool few_large = few_large_trees(B, k);
 #define P2V_LARGE(CS_, TH_)                                                                            \
         (smemtbl ? launch_large<IdxT, MODE, CS_, TH_, (MODE != MODE_PAIRS)>(v, B, k, out, out_stride, status, ws, stride, teams, smem, stream) \
                  : launch_large<IdxT, MODE, CS_, TH_, false>(v, B, k, out, out_stride, status, ws, stride, teams, smem, stream))
