@@ -231,7 +231,7 @@ tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* 
     const int crank = team_rank<CSIZE>();
     const int tid = crank * TAB_THREADS + threadIdx.x;       // thread index inside the team
     constexpr int TT = CSIZE * TAB_THREADS;                   // threads per team
-    const int n = L.n, N = L.N, A = L.A, root = 2 * k;
+    const int n = L.n, N = L.N, root = 2 * k;
     const int64_t team = blockIdx.x / CSIZE, nteams = gridDim.x / CSIZE;
     for (int64_t tree = team; tree < B; tree += nteams) {
         if (status && status[tree] != 0) continue;   // uniform per team
@@ -270,18 +270,14 @@ tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* 
         }
         if (tid == 0) { jA[root] = -1; jDI[root] = 0; jDH[root] = 0.0; jDL[root] = 0.0; }
         team_sync<CSIZE>();
-        // Euler tour arcs: down(c) = 2c, up(c) = 2c+1 for every non-root node c.
-        for (int c = tid; c < 2 * k; c += TT) {
-            const int p = jA[c];
-            int nd, wd;
-            if (c <= k) { nd = 2 * c + 1; wd = 1; }                     // leaf: turn around
-            else { nd = 2 * anc[3 * (c - k - 1)]; wd = 0; }              // internal: into child 0
-            int nu;
-            const int* prow = anc + 3 * (p - k - 1);
-            if (prow[0] == c) nu = 2 * prow[1];                          // then the sibling (child 1)
-            else nu = (p == root) ? -1 : 2 * p + 1;                      // or further up
-            tn[2 * c] = nd; tc[2 * c] = wd;
-            tn[2 * c + 1] = nu; tc[2 * c + 1] = 0;
+        // first / second child pointers for the leftmost / rightmost-leaf jumping (leaves: themselves).
+        // dl = tn[0 .. 2N), dr = tc[0 .. 2N) (two buffers each); the leaf list lives behind them.
+        int* dl = tn; int* dr = tc;
+        int* lnx = tn + 2 * N; int* lct = tc + 2 * N;        // 2 buffers x n each (2N + 2n <= 8k)
+        for (int u = tid; u < N; u += TT) {
+            int l = u, r = u;
+            if (u > k) { l = anc[3 * (u - k - 1)]; r = anc[3 * (u - k - 1) + 1]; }
+            dl[u] = l; dr[u] = r;
         }
         team_sync<CSIZE>();
         // root-path sums by pointer jumping; an even number of rounds leaves the result in buffer 0
@@ -293,9 +289,14 @@ tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* 
                 const int* i_in = jDI + cur * N; int* i_out = jDI + (cur ^ 1) * N;
                 const double* h_in = jDH + cur * N; double* h_out = jDH + (cur ^ 1) * N;
                 const double* l_in = jDL + cur * N; double* l_out = jDL + (cur ^ 1) * N;
+                const int* dl_in = dl + cur * N; int* dl_out = dl + (cur ^ 1) * N;
+                const int* dr_in = dr + cur * N; int* dr_out = dr + (cur ^ 1) * N;
                 int live = 0;
 #pragma unroll 2
                 for (int u = tid; u < N; u += TT) {
+                    const int nl = dl_in[dl_in[u]], nr = dr_in[dr_in[u]];   // leaves are fixed points
+                    dl_out[u] = nl; dr_out[u] = nr;
+                    live |= (nl > k) | (nr > k);
                     const int a = a_in[u];
                     int di = i_in[u];
                     dd d = {h_in[u], l_in[u]};
@@ -313,40 +314,47 @@ tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* 
                 if (!any && cur == 0) { ++fround; break; }
             }
         }
-        // rank the tour: tc[a] becomes the number of leaf arcs from a to the end (inclusive)
-        {
-            int cur = 0;
-            for (;; ++fround) {
-                const int* n_in = tn + cur * A; int* n_out = tn + (cur ^ 1) * A;
-                const int* c_in = tc + cur * A; int* c_out = tc + (cur ^ 1) * A;
-                int live = 0;
-#pragma unroll 4
-                for (int a = tid; a < A; a += TT) {
-                    const int nx = n_in[a];
-                    int c = c_in[a];
-                    int nn = -1;
-                    if (nx >= 0) {
-                        c += c_in[nx];
-                        nn = n_in[nx];
-                        live |= (nn >= 0);
-                    }
-                    n_out[a] = nn; c_out[a] = c;
-                }
-                cur ^= 1;
-                const int any = team_any<CSIZE>(live, flags + min(fround, TAB_FLAGS - 1));
-                if (!any && cur == 0) break;
-            }
+        // The leaves as a linked list in DFS order: every internal node links the last leaf of its
+        // first child's subtree to the first leaf of its second child's (and is the separator of that
+        // pair); ranking the list by pointer jumping gives the DFS positions.
+        for (int r = tid; r < k; r += TT) {
+            const int a = dr[anc[3 * r]], b = dl[anc[3 * r + 1]];
+            lnx[a] = b; lct[a] = 1;
         }
+        if (tid == 0) { const int e = dr[root]; lnx[e] = -1; lct[e] = 0; }
+        team_sync<CSIZE>();
+        int lc = 0;
+        for (;; ++fround) {
+            const int* n_in = lnx + lc * n; int* n_out = lnx + (lc ^ 1) * n;
+            const int* c_in = lct + lc * n; int* c_out = lct + (lc ^ 1) * n;
+            int live = 0;
+#pragma unroll 4
+            for (int x = tid; x < n; x += TT) {
+                const int nx = n_in[x];
+                int c = c_in[x];
+                int nn = -1;
+                if (nx >= 0) {
+                    c += c_in[nx];
+                    nn = n_in[nx];
+                    live |= (nn >= 0);
+                }
+                n_out[x] = nn; c_out[x] = c;
+            }
+            lc ^= 1;
+            const int any = team_any<CSIZE>(live, flags + min(fround, TAB_FLAGS - 1));
+            if (!any) break;
+        }
+        const int* after = lct + lc * n;              // number of leaves after this one
         // DFS positions of the leaves; separators by position
         for (int c = tid; c <= k; c += TT) {
-            const int p = n - tc[2 * c];
+            const int p = k - after[c];
             pos[c] = p;
             leaf_at[p] = c;
         }
         if (tid == 0) { sepk[0] = KEY_INF; sephi[0] = 0.0; seplo[0] = 0.0; sepk[n] = KEY_INF; sephi[n] = 0.0; seplo[n] = 0.0; }
         for (int u = k + 1 + tid; u <= 2 * k; u += TT) {
             const int c1 = anc[3 * (u - k - 1) + 1];      // child 1: its first leaf opens the right part
-            const int r = n - tc[2 * c1];
+            const int r = k - after[dl[c1]];
             sepk[r] = jDI[u]; sephi[r] = jDH[u]; seplo[r] = jDL[u];
         }
         team_sync<CSIZE>();

@@ -234,10 +234,11 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
             uint32_t* ptab = reinterpret_cast<uint32_t*>(ws + (size_t)team * ws_stride) + large_base_stride((size_t)K);
             for (size_t i = tid; i < (size_t)W * K2; i += TT) ptab[i] = NONE32;
             team_sync<CSIZE>();
-            const int wstep = NWT / W;                       // workers are spread over the CTAs of the cluster
+            const int Wd = (W > 0) ? W : 1;
+            const int wstep = NWT / Wd;                      // workers are spread over the CTAs of the cluster
             const bool worker = (gw % wstep) == 0 && (gw / wstep) < W;
             const int w = gw / wstep;
-            const int bpw = (nbat + W - 1) / W;
+            const int bpw = (nbat + Wd - 1) / Wd;
             const int b0 = min(nbat, w * bpw), b1 = min(nbat, b0 + bpw);
             uint32_t* mytab = ptab + (size_t)w * K2;
             if (worker) {
