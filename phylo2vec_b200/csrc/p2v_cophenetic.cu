@@ -17,10 +17,12 @@
 //   prepare (independent of the requested rows)
 //     1. decode v -> ancestry (p2v_decode.cu)
 //     2. tables_kernel: parent pointers; root-path sums (topological depth and
-//        double-double branch-length depth) by pointer jumping; Euler tour of the
-//        tree ranked by pointer jumping -> DFS position of every leaf and, for
-//        every DFS position r, the internal node sep[r] that separates leaves
-//        r-1 and r.  LCA(a,b) for DFS positions a<b is the shallowest sep in (a,b].
+//        double-double branch-length depth) and leftmost / rightmost leaf of every
+//        node by pointer jumping; every internal node links the last leaf of its
+//        first child to the first leaf of its second, and ranking that leaf list
+//        by pointer jumping gives the DFS position of every leaf and, for every
+//        DFS position r, the internal node sep[r] that separates leaves r-1 and r.
+//        LCA(a,b) for DFS positions a<b is the shallowest sep in (a,b].
 //   rows [row_begin,row_end)
 //     3. blocks_kernel: the DFS positions are cut into blocks that hold at most
 //        ROW_R requested rows and at most ROW_PMAX positions; per block: prefix /
