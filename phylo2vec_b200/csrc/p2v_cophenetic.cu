@@ -372,16 +372,23 @@ __device__ __forceinline__ unsigned long long pack_key(int key, int p) {
     return ((unsigned long long)(unsigned)key << 32) | (unsigned)p;
 }
 
+// CSIZE > 1: a thread-block cluster per tree (few, large trees): every CTA takes a contiguous part
+// of the positions, the per-warp counts of requested rows go through global scratch.
+template <int CSIZE>
 __global__ void __launch_bounds__(BLK_THREADS)
 blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int k, int64_t row_begin,
               int64_t row_end, int pcap, int rcap, const int32_t* __restrict__ status) {
     __shared__ int s_part[BLK_THREADS / 32];
     __shared__ int s_total;
     const CophLayout L = coph_layout(k);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = BLK_THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int crank = team_rank<CSIZE>();
+    constexpr int NWC = BLK_THREADS / 32;          // warps per CTA
+    constexpr int NW = CSIZE * NWC;                // warps per team
+    const int warp = crank * NWC + (tid >> 5);     // warp index inside the team
     const int n = L.n;
-    for (int64_t tree = blockIdx.x; tree < B; tree += gridDim.x) {
+    const int64_t team = blockIdx.x / CSIZE, nteams = gridDim.x / CSIZE;
+    for (int64_t tree = team; tree < B; tree += nteams) {
         if (status && status[tree] != 0) continue;
         unsigned char* T = tab + (size_t)tree * tab_stride;
         const int* leaf_at = reinterpret_cast<const int*>(T + L.leaf_at);
@@ -395,8 +402,9 @@ blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int
         int* blka = reinterpret_cast<int*>(T + L.blka);
         int* hdr = reinterpret_cast<int*>(T + L.hdr);
 
-        __syncthreads();   // shared scratch of the previous tree is no longer read
-        for (int i = tid; i < L.nbmax; i += BLK_THREADS) {
+        int* wcount = reinterpret_cast<int*>(T + L.tilelist);   // per-warp counts (tilelist is filled last)
+        team_sync<CSIZE>();   // shared scratch of the previous tree is no longer read
+        for (int i = crank * BLK_THREADS + tid; i < L.nbmax; i += CSIZE * BLK_THREADS) {
             bstart[i] = -1; bend[i] = -1; rowoff[i] = 0; cend[i] = 0; blkk[i] = KEY_INF; blka[i] = -1;
         }
         // every warp owns a contiguous range of positions and reads it with coalesced loads
@@ -409,15 +417,26 @@ blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int
             const int lab = (p < w1) ? leaf_at[p] : -1;
             cnt += __popc(__ballot_sync(FULL, lab >= row_begin && lab < row_end));
         }
-        if (lane == 0) s_part[warp] = cnt;
-        __syncthreads();
-        if (warp == 0) {
-            const int v = s_part[lane];
-            const int sc = (int)warp_incl_scan((uint32_t)v, lane);
-            s_part[lane] = sc - v;
+        int c0;                                      // requested rows at positions < w0
+        if (CSIZE == 1) {
+            if (lane == 0) s_part[warp] = cnt;
+            __syncthreads();
+            if (warp == 0) {
+                const int v = s_part[lane];
+                const int sc = (int)warp_incl_scan((uint32_t)v, lane);
+                s_part[lane] = sc - v;
+            }
+            __syncthreads();
+            c0 = s_part[warp];
+        } else {
+            if (lane == 0) wcount[warp] = cnt;
+            team_sync<CSIZE>();
+            int acc = 0;
+            for (int w = lane; w < warp; w += 32) acc += wcount[w];
+#pragma unroll
+            for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(FULL, acc, d);
+            c0 = acc;
         }
-        __syncthreads();
-        int c0 = s_part[warp];                       // requested rows at positions < w0
         int prev_last = (w0 > 0) ? (w0 - 1) / pcap + max(0, c0 - 1) / rcap : -1;   // id of position w0-1
         int lab_next = (w0 + lane < w1) ? leaf_at[w0 + lane] : -1;
         int lab_next2 = (w0 + 32 + lane < w1) ? leaf_at[w0 + 32 + lane] : -1;
@@ -446,9 +465,10 @@ blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int
             const int last = __shfl_sync(FULL, id, 31);
             if (last >= 0) prev_last = last;
         }
-        __syncthreads();
+        team_sync<CSIZE>();
         // compact the blocks that hold requested rows into tilelist
-        {
+        if (crank == 0) {
+            const int warp = tid >> 5;
             int* tilelist = reinterpret_cast<int*>(T + L.tilelist);
             const int nid = hdr[0];
             int base_count = 0;
@@ -472,6 +492,31 @@ blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int
             if (tid == 0) hdr[1] = base_count;
         }
     }
+}
+
+template <int CSIZE>
+static bool launch_blocks_cluster(unsigned char* tab, size_t tab_stride, int64_t B, int k, int64_t row_begin,
+                                  int64_t row_end, int pcap, int rcap, const int32_t* st, cudaStream_t stream) {
+    auto kern = blocks_kernel<CSIZE>;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * CSIZE));
+    cfg.blockDim = dim3(BLK_THREADS);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CSIZE; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError();
+        return false;
+    }
+    if (cudaLaunchKernelEx(&cfg, kern, tab, tab_stride, B, k, row_begin, row_end, pcap, rcap, st) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return true;
 }
 
 // prefix / suffix minima of sep inside every block: one warp per (tree, block), whole grid
@@ -1505,7 +1550,11 @@ cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t
     {
         const int64_t cap = (int64_t)sm_count() * 2;
         const int grid = (int)(B < cap ? B : cap);
-        blocks_kernel<<<grid, BLK_THREADS, 0, stream>>>(tab, L.total, B, (int)k, row_begin, row_end, call.pcap, call.rcap, st);
+        bool launched = false;
+        if (B * 8 <= sm_count() && k >= 4096)    // few large trees: a cluster of 8 CTAs per tree
+            launched = launch_blocks_cluster<8>(tab, L.total, B, (int)k, row_begin, row_end, call.pcap, call.rcap, st, stream);
+        if (!launched)
+            blocks_kernel<1><<<grid, BLK_THREADS, 0, stream>>>(tab, L.total, B, (int)k, row_begin, row_end, call.pcap, call.rcap, st);
         count_launch();
         const int64_t warps = B * (int64_t)L.nbmax;
         const int64_t want = (warps + 7) / 8, cap2 = (int64_t)sm_count() * 8;
