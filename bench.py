@@ -461,9 +461,9 @@ def bench_cophenetic(torch, lib, device, rank, world, peak, args):
     res["roofline"] = {"bound": "hbm", "achieved": res["fp64_branch_lengths"]["achieved_gbs"], "peak": peak,
                        "unit": "GB/s", "frac": res["fp64_branch_lengths"]["achieved_gbs"] / peak,
                        "kernel": "rows_kernel<fp64>", "algorithmic_bytes": rows * n * 8,
-                       "traffic": int(34.317283e9 * rows / n),
-                       "traffic_source": "ncu --set full, profiles/r01_rows_full_fp64_v5.summary.txt: 34.300 GB written "
-                                         "+ 0.017 GB read for all 65536 rows, scaled to this rank's rows"}
+                       "traffic": int(34.332404e9 * rows / n),
+                       "traffic_source": "ncu --set full, profiles/r01_rows_full_fp64_v7.summary.txt: 34.303 GB written "
+                                         "+ 0.030 GB read for all 65536 rows, scaled to this rank's rows"}
     return res
 
 
