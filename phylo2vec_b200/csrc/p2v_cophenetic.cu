@@ -1390,8 +1390,12 @@ __global__ void fill_f64_kernel(double* __restrict__ out, int64_t count, double 
     const int64_t n2 = count >> 1;
     double2 v; v.x = value; v.y = value;
     double2* o2 = reinterpret_cast<double2*>(out);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x)
-        __stcs(o2 + i, v);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n2; i += 4 * stride) {     // four 128-bit streaming stores in flight per thread
+        __stcs(o2 + i, v); __stcs(o2 + i + stride, v); __stcs(o2 + i + 2 * stride, v); __stcs(o2 + i + 3 * stride, v);
+    }
+    for (; i < n2; i += stride) __stcs(o2 + i, v);
     if ((count & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[count - 1] = value;
 }
 
@@ -1718,7 +1722,7 @@ cudaError_t launch_node_depths(const void* v_or_matrix, int idx_bytes, const dou
 
 cudaError_t launch_fill_f64(double* out, int64_t count, double value, cudaStream_t stream) {
     if (count <= 0) return cudaSuccess;
-    fill_f64_kernel<<<sm_count() * 8, 256, 0, stream>>>(out, count, value);
+    fill_f64_kernel<<<sm_count() * 6, 256, 0, stream>>>(out, count, value);
     count_launch();
     return cudaGetLastError();
 }
