@@ -1,8 +1,17 @@
 // C ABI of the library (declared in include/phylo2vec_b200.h).
+#include <emmintrin.h>
+#include <sched.h>
+
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/phylo2vec_b200.h"
 #include "p2v_internal.h"
@@ -179,6 +188,188 @@ static int decode_host(int mode, int cols, const void* v, int idx_bytes, int64_t
         [&](void* din, void* dout, int32_t* dst, int64_t nb, void* ws, size_t wsb, cudaStream_t st) {
             return launch_decode(mode, din, idx_bytes, nb, k, dout, dst, ws, wsb, st);
         });
+}
+
+// ---- to_ancestry through host buffers, int64: compact transport ------------------------------
+// The (k,3) int64 ancestry is 24 bytes per row on the wire, but its third column is always
+// k+1+row and the first two fit 32 bits.  For big batches the device therefore produces the two
+// informative columns as int32 (MODE_ANC2, 8 bytes per row), they cross PCIe into a pinned
+// staging buffer of the library, and host threads widen them into the caller's int64 rows with
+// streaming stores while the next chunks are in flight.  PCIe carries a third of the bytes; the
+// widening runs at host-memory speed (profiles/host_widen_probe.c: 115 GB/s written with 16
+// threads on the GPU box).  P2V_HOST_COMPACT=0 switches it off, P2V_HOST_THREADS sets the threads.
+struct CompactCtx {
+    void* stage[HOST_STREAMS] = {};
+    int32_t* hstat[HOST_STREAMS] = {};      // pinned: the status of a chunk (the caller's array may be pageable)
+    int32_t* v32[HOST_STREAMS] = {};
+    cudaEvent_t ev[HOST_STREAMS] = {};
+    size_t cap_stage = 0, cap_v32 = 0, cap_hstat = 0;
+    void release() {
+        for (int i = 0; i < HOST_STREAMS; ++i) {
+            if (stage[i]) cudaFreeHost(stage[i]);
+            if (hstat[i]) cudaFreeHost(hstat[i]);
+            if (v32[i]) cudaFree(v32[i]);
+            if (ev[i]) cudaEventDestroy(ev[i]);
+            stage[i] = nullptr; hstat[i] = nullptr; v32[i] = nullptr; ev[i] = nullptr;
+        }
+        cap_stage = cap_v32 = cap_hstat = 0;
+    }
+};
+static thread_local CompactCtx g_compact;
+
+static int host_thread_count() {
+    const char* e = getenv("P2V_HOST_THREADS");
+    if (e && atoi(e) > 0) return atoi(e);
+    cpu_set_t set;
+    int n = 0;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+    if (n <= 0) n = (int)std::thread::hardware_concurrency();
+    if (n > 16) n = 16;
+    return n < 1 ? 1 : n;
+}
+static bool host_compact_enabled() {
+    const char* e = getenv("P2V_HOST_COMPACT");
+    return !(e && e[0] == '0');
+}
+
+// whole trees: (c1, c2) int32 -> (c1, c2, k+1+row) int64, non-temporal stores
+static void widen_trees(const int32_t* src, long long* dst, int64_t ntrees, int64_t k) {
+    for (int64_t t = 0; t < ntrees; ++t) {
+        for (int64_t r = 0; r < k; ++r) {
+            _mm_stream_si64(dst, (long long)src[0]);
+            _mm_stream_si64(dst + 1, (long long)src[1]);
+            _mm_stream_si64(dst + 2, (long long)(k + 1 + r));
+            src += 2; dst += 3;
+        }
+    }
+}
+
+struct WidenJob { const int32_t* src; long long* dst; int64_t ntrees; int chunk; };
+
+static int ancestry_host_compact(const void* v, int64_t B, int64_t k, void* out, int32_t* status) {
+    HostCtx& H = g_host;
+    CompactCtx& C = g_compact;
+    // chunk: ~48 K trees of n = 1000 (v 8 B + v32 4 B + pairs 8 B per element on the device)
+    int64_t chunk = (int64_t)(((size_t)960 << 20) / ((size_t)k * 20));
+    if (chunk < 1) chunk = 1;
+    if (chunk > B) chunk = B;
+    const size_t in_b = (size_t)k * 8 * chunk, out_b = (size_t)k * 8 * chunk, v32_b = (size_t)k * 4 * chunk;
+    const size_t wsb = decode_workspace_bytes(chunk, k);
+    cudaError_t e = host_ensure(H, in_b, out_b, wsb, sizeof(int32_t) * chunk);
+    if (e != cudaSuccess) { H.release(); return from_cuda(e, "host entry: device allocation"); }
+    for (int i = 0; i < HOST_STREAMS && e == cudaSuccess; ++i) {
+        if (out_b > C.cap_stage || !C.stage[i]) {
+            if (C.stage[i]) cudaFreeHost(C.stage[i]);
+            C.stage[i] = nullptr;
+            e = cudaHostAlloc(&C.stage[i], out_b, cudaHostAllocDefault);
+        }
+        if (e == cudaSuccess && (sizeof(int32_t) * (size_t)chunk > C.cap_hstat || !C.hstat[i])) {
+            if (C.hstat[i]) cudaFreeHost(C.hstat[i]);
+            C.hstat[i] = nullptr;
+            e = cudaHostAlloc((void**)&C.hstat[i], sizeof(int32_t) * (size_t)chunk, cudaHostAllocDefault);
+        }
+        if (e == cudaSuccess && (v32_b > C.cap_v32 || !C.v32[i])) {
+            if (C.v32[i]) cudaFree(C.v32[i]);
+            C.v32[i] = nullptr;
+            e = cudaMalloc((void**)&C.v32[i], v32_b);
+        }
+        if (e == cudaSuccess && !C.ev[i]) e = cudaEventCreateWithFlags(&C.ev[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) { C.release(); return from_cuda(e, "host entry: staging allocation"); }
+    if (out_b > C.cap_stage) C.cap_stage = out_b;
+    if (sizeof(int32_t) * (size_t)chunk > C.cap_hstat) C.cap_hstat = sizeof(int32_t) * (size_t)chunk;
+    if (v32_b > C.cap_v32) C.cap_v32 = v32_b;
+
+    // widening workers
+    const int nthreads = host_thread_count();
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    std::deque<WidenJob> jobs;
+    const int64_t nchunks = (B + chunk - 1) / chunk;
+    std::vector<int> pending((size_t)nchunks, 0);      // slices of a chunk not yet widened
+    bool stop = false;
+    std::vector<std::thread> pool;
+    pool.reserve(nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+        pool.emplace_back([&]() {
+            for (;;) {
+                WidenJob j;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv_job.wait(lk, [&] { return stop || !jobs.empty(); });
+                    if (jobs.empty()) return;
+                    j = jobs.front(); jobs.pop_front();
+                }
+                widen_trees(j.src, j.dst, j.ntrees, k);
+                _mm_sfence();
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (--pending[(size_t)j.chunk] == 0) cv_done.notify_all();
+                }
+            }
+        });
+    }
+    auto enqueue = [&](int64_t c) {     // chunk c has landed in its staging buffer
+        const int s = (int)(c % HOST_STREAMS);
+        const int64_t b0 = c * chunk, nb = (B - b0 < chunk) ? (B - b0) : chunk;
+        // slices of whole trees so that the row number inside a tree starts at 0 in every slice
+        const int64_t per = (nb + nthreads - 1) / nthreads;
+        std::lock_guard<std::mutex> lk(mu);
+        for (int64_t t0 = 0; t0 < nb; t0 += per) {
+            const int64_t nt = (nb - t0 < per) ? (nb - t0) : per;
+            jobs.push_back(WidenJob{static_cast<const int32_t*>(C.stage[s]) + (size_t)t0 * k * 2,
+                                    static_cast<long long*>(out) + (size_t)(b0 + t0) * k * 3, nt, (int)c});
+            ++pending[(size_t)c];
+        }
+        cv_job.notify_all();
+    };
+    auto wait_done = [&](int64_t c) {
+        if (c < 0) return;
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending[(size_t)c] == 0; });
+    };
+    auto finish = [&]() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv_job.notify_all();
+        for (auto& th : pool) th.join();
+    };
+
+    int rc = P2V_OK;
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int s = (int)(c % HOST_STREAMS);
+        const int64_t b0 = c * chunk, nb = (B - b0 < chunk) ? (B - b0) : chunk;
+        if (c >= HOST_STREAMS) {                         // staging buffer s is free once chunk c - 3 is widened
+            // (its jobs were enqueued two iterations ago)
+            wait_done(c - HOST_STREAMS);
+        }
+        e = cudaMemcpyAsync(H.din[s], (const char*)v + (size_t)b0 * k * 8, (size_t)k * 8 * nb, cudaMemcpyHostToDevice, H.st[s]);
+        if (e == cudaSuccess) e = launch_narrow_v(static_cast<const long long*>(H.din[s]), nb * k, C.v32[s], H.st[s]);
+        if (e == cudaSuccess) e = launch_decode(MODE_ANC2, C.v32[s], 4, nb, k, H.dout[s], H.dstat[s], H.dws[s], wsb, H.st[s], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(C.stage[s], H.dout[s], (size_t)k * 8 * nb, cudaMemcpyDeviceToHost, H.st[s]);
+        if (e == cudaSuccess && status)
+            e = cudaMemcpyAsync(C.hstat[s], H.dstat[s], sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, H.st[s]);
+        if (e == cudaSuccess) e = cudaEventRecord(C.ev[s], H.st[s]);
+        if (e == cudaSuccess && c >= 1) {               // the previous chunk: wait for it, hand it to the workers
+            e = cudaEventSynchronize(C.ev[(c - 1) % HOST_STREAMS]);
+            if (e == cudaSuccess) {
+                if (status) memcpy(status + (c - 1) * chunk, C.hstat[(c - 1) % HOST_STREAMS], sizeof(int32_t) * chunk);
+                enqueue(c - 1);
+            }
+        }
+        if (e != cudaSuccess) { rc = from_cuda(e, "host entry: chunk"); break; }
+    }
+    if (rc == P2V_OK) {
+        e = cudaEventSynchronize(C.ev[(nchunks - 1) % HOST_STREAMS]);
+        if (e == cudaSuccess) {
+            const int64_t b0 = (nchunks - 1) * chunk;
+            if (status) memcpy(status + b0, C.hstat[(nchunks - 1) % HOST_STREAMS], sizeof(int32_t) * (B - b0));
+            enqueue(nchunks - 1);
+        } else rc = from_cuda(e, "host entry: synchronize");
+    }
+    if (rc == P2V_OK) for (int64_t c = (nchunks > HOST_STREAMS ? nchunks - HOST_STREAMS : 0); c < nchunks; ++c) wait_done(c);
+    finish();
+    for (int i = 0; i < HOST_STREAMS; ++i) cudaStreamSynchronize(H.st[i]);
+    return rc;
 }
 
 static int encode_host(int mode, int cols, const void* in, int idx_bytes, int64_t B, int64_t k, void* v,
@@ -474,6 +665,12 @@ int p2v_to_pairs_host(const void* v, int idx_bytes, int64_t B, int64_t k, void* 
     return decode_host(MODE_PAIRS, 2, v, idx_bytes, B, k, out, status);
 }
 int p2v_to_ancestry_host(const void* v, int idx_bytes, int64_t B, int64_t k, void* out, int32_t* status) {
+    // big int64 batches: two int32 columns over PCIe, widened by host threads (see ancestry_host_compact)
+    if (idx_bytes == 8 && k > 0 && k <= 0x3FFFFFFF / 2 && B * k >= ((int64_t)1 << 22) && host_compact_enabled()) {
+        int rc = check_common(v, out, idx_bytes, B, k);
+        if (rc) return rc;
+        return ancestry_host_compact(v, B, k, out, status);
+    }
     return decode_host(MODE_ANCESTRY, 3, v, idx_bytes, B, k, out, status);
 }
 int p2v_to_edges_host(const void* v, int idx_bytes, int64_t B, int64_t k, void* out, int32_t* status) {
@@ -509,7 +706,7 @@ int p2v_cophenetic_matrix_host(const double* m, int64_t B, int64_t k, int unroot
     return coph_host(m, 0, nullptr, B, k, unrooted, row_begin, row_end, out, status);
 }
 
-void p2v_host_release(void) { g_host.release(); }
+void p2v_host_release(void) { g_host.release(); g_compact.release(); }
 
 int p2v_fill_f64(double* out, int64_t count, double value, p2v_stream_t stream) {
     if (count > 0 && !out) return fail(P2V_ERR_INVALID_ARG, "null buffer");

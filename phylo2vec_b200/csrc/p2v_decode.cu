@@ -452,7 +452,7 @@ static bool launch_large(const void* v, int64_t B, int64_t k, void* out, int64_t
 template <typename IdxT, int MODE>
 static cudaError_t launch_decode_t(const void* v, int64_t B, int64_t k, void* out, int32_t* status,
                                    void* ws, size_t ws_bytes, cudaStream_t stream, int64_t out_stride) {
-    if (out_stride <= 0) out_stride = k * (MODE == MODE_PAIRS ? 2 : (MODE == MODE_ANCESTRY ? 3 : 4));
+    if (out_stride <= 0) out_stride = k * ((MODE == MODE_PAIRS || MODE == MODE_ANC2) ? 2 : (MODE == MODE_ANCESTRY ? 3 : 4));
     // few large trees go to the merge kernel (all SMs on one tree); batches of mid-size trees keep
     // the warp-per-tree kernel, which does a fraction of the work per tree
     const bool warp_per_tree = k <= SMALL_K_MAX || (k <= warp_k_max() && B * 4 > sm_count());
@@ -516,6 +516,7 @@ cudaError_t launch_decode(int mode, const void* v, int idx_bytes, int64_t B, int
     case MODE_PAIRS: return launch_decode_t<T, MODE_PAIRS>(v, B, k, out, status, ws, ws_bytes, stream, out_stride);     \
     case MODE_ANCESTRY: return launch_decode_t<T, MODE_ANCESTRY>(v, B, k, out, status, ws, ws_bytes, stream, out_stride); \
     case MODE_EDGES: return launch_decode_t<T, MODE_EDGES>(v, B, k, out, status, ws, ws_bytes, stream, out_stride);     \
+    case MODE_ANC2: return launch_decode_t<T, MODE_ANC2>(v, B, k, out, status, ws, ws_bytes, stream, out_stride);       \
     default: return cudaErrorInvalidValue;                                                         \
     }
     if (idx_bytes == 8) { P2V_DISPATCH(long long) }

@@ -36,6 +36,8 @@ __device__ __forceinline__ void store_row(IdxT* tree_out, int s, IdxT c1p, IdxT 
     if (MODE == MODE_ANCESTRY) {
         IdxT* o = tree_out + 3 * (size_t)s;
         o[0] = c1p; o[1] = c2p; o[2] = par;
+    } else if (MODE == MODE_ANC2) {
+        store_pair<IdxT>(tree_out + 2 * (size_t)s, c1p, c2p);
     } else {  // MODE_EDGES: (c1p,par),(c2p,par)
         IdxT* o = tree_out + 4 * (size_t)s;
         store_pair<IdxT>(o, c1p, par);

@@ -6,7 +6,9 @@
 
 namespace p2v {
 
-enum DecodeMode { MODE_PAIRS = 0, MODE_ANCESTRY = 1, MODE_EDGES = 2 };
+// MODE_ANC2: the first two columns of the ancestry only, (k,2) -- the third is always k+1+row; this is
+// the compact transport of the host entry point, not a public output format
+enum DecodeMode { MODE_PAIRS = 0, MODE_ANCESTRY = 1, MODE_EDGES = 2, MODE_ANC2 = 3 };
 enum EncodeMode { FROM_PAIRS = 0, FROM_ANCESTRY = 1, FROM_EDGES = 2 };
 
 constexpr int SMALL_K_MAX = 2016;      // warp-per-tree decode in shared memory; the half2 rank scan needs K + 30 <= 2048

@@ -328,3 +328,32 @@ def test_host_entry_points_batched(p2v):
     rc = lib.p2v_to_edges_host(V32.ctypes.data_as(ctypes.c_void_p), 4, 300, k,
                                out32.ctypes.data_as(ctypes.c_void_p), None)
     assert rc == 0 and np.array_equal(out32.astype(np.int64), O.batch("to_edges", V, k)[0])
+
+
+def test_host_to_ancestry_compact_transport(p2v):
+    """Big int64 batches through p2v_to_ancestry_host travel as two int32 columns and are widened by
+    host threads of the library (several chunks, pageable buffers, an invalid tree in the middle);
+    the result must be what the device path and the oracle give."""
+    import ctypes
+    from phylo2vec_b200 import _capi
+    lib = _capi.load()
+    vp = ctypes.c_void_p
+    for n_leaves, B in ((1000, 120_000), (100, 60_000), (3000, 3_000), (20000, 300)):
+        k = n_leaves - 1
+        V = sample_vectors(B, n_leaves, seed=n_leaves + 5)
+        bad = B // 2 + 1
+        V[bad, k // 3] = 2 * (k // 3) + 7
+        out = np.full((B, k, 3), -1, dtype=np.int64)
+        st = np.full(B, 77, dtype=np.int32)
+        rc = lib.p2v_to_ancestry_host(V.ctypes.data_as(vp), 8, B, k, out.ctypes.data_as(vp), st.ctypes.data_as(vp))
+        assert rc == 0, lib.p2v_last_error()
+        assert st[bad] == k // 3 + 1 and np.count_nonzero(st) == 1
+        idx = np.concatenate([np.arange(0, 40), np.linspace(40, B - 1, 200).astype(int)])
+        idx = idx[idx != bad]
+        ref, _ = O.batch("to_ancestry", V[idx], k)
+        assert np.array_equal(out[idx], ref), n_leaves
+        dev_out = p2v.to_ancestry_batch(dev(V), check=False).cpu().numpy()
+        good = np.ones(B, dtype=bool)
+        good[bad] = False
+        assert np.array_equal(out[good], dev_out[good]), n_leaves
+    lib.p2v_host_release()
