@@ -337,10 +337,10 @@ def run_b200(args):
             "cpu_baseline": {"value": cb_rate, "unit": "trees/s", "cores": cb_cores, "kind": "port",
                              "sample": f"65536 trees of n=1000, {cb_dt:.2f} s, OpenMP over trees"},
             "e2e": {"value": e2e_value, "unit": "trees/s", "h2d_bytes_per_step": Be * K * 8,
-                    "d2h_bytes_per_step": Be * K * 8 + Be * 4, "batch_per_gpu": Be, "steps": e2e_steps,
+                    "d2h_bytes_per_step": Be * K * 4 + Be * 4, "batch_per_gpu": Be, "steps": e2e_steps,
                     "result_bytes_per_step": Be * K * 24 + Be * 4,
-                    "transport": "the int64 (k,3) result crosses PCIe as its two informative int32 columns (the third "
-                                 "is k+1+row); host threads of the library widen them into the caller's int64 rows",
+                    "transport": "the int64 (k,3) result crosses PCIe as its two informative columns in 16 bits each (the "
+                                 "third is k+1+row); host threads of the library widen them into the caller's int64 rows",
                     "api": "p2v_to_ancestry_host (C ABI, pinned host buffers)", "matches_device_path": e2e_ok},
             "gpu_launches": launches, "clocks": clocks, "parity_spot_check": parity,
             "config_c2_other_functions": c2, "cophenetic": coph, "next_rows": {"to_newick": newick},

@@ -232,6 +232,24 @@ static bool host_compact_enabled() {
     return !(e && e[0] == '0');
 }
 
+// (c1, c2) int32 pairs -> uint16 pairs on the device (labels < 65536): half the PCIe bytes again
+__global__ void pack_pairs_u16_kernel(const int2* __restrict__ in, int64_t count, ushort2* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const int2 x = in[i];
+        out[i] = make_ushort2((unsigned short)x.x, (unsigned short)x.y);
+    }
+}
+static void widen_trees_u16(const uint16_t* src, long long* dst, int64_t ntrees, int64_t k) {
+    for (int64_t t = 0; t < ntrees; ++t) {
+        for (int64_t r = 0; r < k; ++r) {
+            _mm_stream_si64(dst, (long long)src[0]);
+            _mm_stream_si64(dst + 1, (long long)src[1]);
+            _mm_stream_si64(dst + 2, (long long)(k + 1 + r));
+            src += 2; dst += 3;
+        }
+    }
+}
+
 // whole trees: (c1, c2) int32 -> (c1, c2, k+1+row) int64, non-temporal stores
 static void widen_trees(const int32_t* src, long long* dst, int64_t ntrees, int64_t k) {
     for (int64_t t = 0; t < ntrees; ++t) {
@@ -244,7 +262,7 @@ static void widen_trees(const int32_t* src, long long* dst, int64_t ntrees, int6
     }
 }
 
-struct WidenJob { const int32_t* src; long long* dst; int64_t ntrees; int chunk; };
+struct WidenJob { const void* src; long long* dst; int64_t ntrees; int chunk; };
 
 static int ancestry_host_compact(const void* v, int64_t B, int64_t k, void* out, int32_t* status) {
     HostCtx& H = g_host;
@@ -253,6 +271,9 @@ static int ancestry_host_compact(const void* v, int64_t B, int64_t k, void* out,
     int64_t chunk = (int64_t)(((size_t)960 << 20) / ((size_t)k * 20));
     if (chunk < 1) chunk = 1;
     if (chunk > B) chunk = B;
+    const bool u16 = 2 * k + 1 <= 65535;                 // labels fit 16 bits: 4 bytes per row on the wire
+    const size_t wire_row = u16 ? 4 : 8;
+    // device per element: v 8 B, v32 4 B (reused for the packed pairs), int32 pairs 8 B
     const size_t in_b = (size_t)k * 8 * chunk, out_b = (size_t)k * 8 * chunk, v32_b = (size_t)k * 4 * chunk;
     const size_t wsb = decode_workspace_bytes(chunk, k);
     cudaError_t e = host_ensure(H, in_b, out_b, wsb, sizeof(int32_t) * chunk);
@@ -300,7 +321,8 @@ static int ancestry_host_compact(const void* v, int64_t B, int64_t k, void* out,
                     if (jobs.empty()) return;
                     j = jobs.front(); jobs.pop_front();
                 }
-                widen_trees(j.src, j.dst, j.ntrees, k);
+                if (u16) widen_trees_u16(static_cast<const uint16_t*>(j.src), j.dst, j.ntrees, k);
+                else widen_trees(static_cast<const int32_t*>(j.src), j.dst, j.ntrees, k);
                 _mm_sfence();
                 {
                     std::lock_guard<std::mutex> lk(mu);
@@ -317,7 +339,7 @@ static int ancestry_host_compact(const void* v, int64_t B, int64_t k, void* out,
         std::lock_guard<std::mutex> lk(mu);
         for (int64_t t0 = 0; t0 < nb; t0 += per) {
             const int64_t nt = (nb - t0 < per) ? (nb - t0) : per;
-            jobs.push_back(WidenJob{static_cast<const int32_t*>(C.stage[s]) + (size_t)t0 * k * 2,
+            jobs.push_back(WidenJob{static_cast<const char*>(C.stage[s]) + (size_t)t0 * k * wire_row,
                                     static_cast<long long*>(out) + (size_t)(b0 + t0) * k * 3, nt, (int)c});
             ++pending[(size_t)c];
         }
@@ -345,7 +367,15 @@ static int ancestry_host_compact(const void* v, int64_t B, int64_t k, void* out,
         e = cudaMemcpyAsync(H.din[s], (const char*)v + (size_t)b0 * k * 8, (size_t)k * 8 * nb, cudaMemcpyHostToDevice, H.st[s]);
         if (e == cudaSuccess) e = launch_narrow_v(static_cast<const long long*>(H.din[s]), nb * k, C.v32[s], H.st[s]);
         if (e == cudaSuccess) e = launch_decode(MODE_ANC2, C.v32[s], 4, nb, k, H.dout[s], H.dstat[s], H.dws[s], wsb, H.st[s], 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(C.stage[s], H.dout[s], (size_t)k * 8 * nb, cudaMemcpyDeviceToHost, H.st[s]);
+        const void* wire = H.dout[s];
+        if (e == cudaSuccess && u16) {                  // the int32 v is dead after the decode: its buffer takes the packed pairs
+            pack_pairs_u16_kernel<<<sm_count() * 8, 256, 0, H.st[s]>>>(static_cast<const int2*>(H.dout[s]), nb * k,
+                                                                       reinterpret_cast<ushort2*>(C.v32[s]));
+            count_launch();
+            e = cudaGetLastError();
+            wire = C.v32[s];
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(C.stage[s], wire, (size_t)k * wire_row * nb, cudaMemcpyDeviceToHost, H.st[s]);
         if (e == cudaSuccess && status)
             e = cudaMemcpyAsync(C.hstat[s], H.dstat[s], sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, H.st[s]);
         if (e == cudaSuccess) e = cudaEventRecord(C.ev[s], H.st[s]);

@@ -338,7 +338,8 @@ def test_host_to_ancestry_compact_transport(p2v):
     from phylo2vec_b200 import _capi
     lib = _capi.load()
     vp = ctypes.c_void_p
-    for n_leaves, B in ((1000, 120_000), (100, 60_000), (3000, 3_000), (20000, 300)):
+    # labels below 65536 travel as uint16 pairs, larger trees (n = 40000) as int32 pairs
+    for n_leaves, B in ((1000, 120_000), (100, 60_000), (3000, 3_000), (20000, 300), (40000, 120)):
         k = n_leaves - 1
         V = sample_vectors(B, n_leaves, seed=n_leaves + 5)
         bad = B // 2 + 1
