@@ -200,19 +200,21 @@ static int decode_host(int mode, int cols, const void* v, int idx_bytes, int64_t
 // threads on the GPU box).  P2V_HOST_COMPACT=0 switches it off, P2V_HOST_THREADS sets the threads.
 struct CompactCtx {
     void* stage[HOST_STREAMS] = {};
+    int32_t* vstage[HOST_STREAMS] = {};     // pinned: int32 copy of a pageable input chunk
     int32_t* hstat[HOST_STREAMS] = {};      // pinned: the status of a chunk (the caller's array may be pageable)
     int32_t* v32[HOST_STREAMS] = {};
     cudaEvent_t ev[HOST_STREAMS] = {};
-    size_t cap_stage = 0, cap_v32 = 0, cap_hstat = 0;
+    size_t cap_stage = 0, cap_v32 = 0, cap_hstat = 0, cap_vstage = 0;
     void release() {
         for (int i = 0; i < HOST_STREAMS; ++i) {
             if (stage[i]) cudaFreeHost(stage[i]);
+            if (vstage[i]) cudaFreeHost(vstage[i]);
             if (hstat[i]) cudaFreeHost(hstat[i]);
             if (v32[i]) cudaFree(v32[i]);
             if (ev[i]) cudaEventDestroy(ev[i]);
-            stage[i] = nullptr; hstat[i] = nullptr; v32[i] = nullptr; ev[i] = nullptr;
+            stage[i] = nullptr; vstage[i] = nullptr; hstat[i] = nullptr; v32[i] = nullptr; ev[i] = nullptr;
         }
-        cap_stage = cap_v32 = cap_hstat = 0;
+        cap_stage = cap_v32 = cap_hstat = cap_vstage = 0;
     }
 };
 static thread_local CompactCtx g_compact;
@@ -262,7 +264,21 @@ static void widen_trees(const int32_t* src, long long* dst, int64_t ntrees, int6
     }
 }
 
-struct WidenJob { const void* src; long long* dst; int64_t ntrees; int chunk; };
+// kind 0: widen `ntrees` trees from the wire format into dst; kind 1: narrow `ntrees * k` int64 inputs at
+// src into int32 at dst (values that do not fit become -1 and fail check_v on the device)
+struct WidenJob { const void* src; void* dst; int64_t ntrees; int chunk; int kind; };
+
+static void narrow_inputs(const long long* src, int32_t* dst, int64_t count) {
+    for (int64_t i = 0; i < count; ++i) {
+        const long long x = src[i];
+        dst[i] = (x < 0 || x > 0x7FFFFFFFLL) ? -1 : (int32_t)x;
+    }
+}
+static bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
 
 static int ancestry_host_compact(const void* v, int64_t B, int64_t k, void* out, int32_t* status) {
     HostCtx& H = g_host;
@@ -276,7 +292,10 @@ static int ancestry_host_compact(const void* v, int64_t B, int64_t k, void* out,
     // device per element: v 8 B, v32 4 B (reused for the packed pairs), int32 pairs 8 B
     const size_t in_b = (size_t)k * 8 * chunk, out_b = (size_t)k * 8 * chunk, v32_b = (size_t)k * 4 * chunk;
     const size_t wsb = decode_workspace_bytes(chunk, k);
-    cudaError_t e = host_ensure(H, in_b, out_b, wsb, sizeof(int32_t) * chunk);
+    // a pageable input (a plain numpy array) would be staged by the driver on one thread: the workers
+    // narrow it into pinned int32 staging instead, and that goes to the device
+    const bool pageable_in = is_pageable(v);
+    cudaError_t e = host_ensure(H, pageable_in ? 0 : in_b, out_b, wsb, sizeof(int32_t) * chunk);
     if (e != cudaSuccess) { H.release(); return from_cuda(e, "host entry: device allocation"); }
     for (int i = 0; i < HOST_STREAMS && e == cudaSuccess; ++i) {
         if (out_b > C.cap_stage || !C.stage[i]) {
@@ -294,9 +313,15 @@ static int ancestry_host_compact(const void* v, int64_t B, int64_t k, void* out,
             C.v32[i] = nullptr;
             e = cudaMalloc((void**)&C.v32[i], v32_b);
         }
+        if (e == cudaSuccess && pageable_in && (v32_b > C.cap_vstage || !C.vstage[i])) {
+            if (C.vstage[i]) cudaFreeHost(C.vstage[i]);
+            C.vstage[i] = nullptr;
+            e = cudaHostAlloc((void**)&C.vstage[i], v32_b, cudaHostAllocDefault);
+        }
         if (e == cudaSuccess && !C.ev[i]) e = cudaEventCreateWithFlags(&C.ev[i], cudaEventDisableTiming);
     }
     if (e != cudaSuccess) { C.release(); return from_cuda(e, "host entry: staging allocation"); }
+    if (pageable_in && v32_b > C.cap_vstage) C.cap_vstage = v32_b;
     if (out_b > C.cap_stage) C.cap_stage = out_b;
     if (sizeof(int32_t) * (size_t)chunk > C.cap_hstat) C.cap_hstat = sizeof(int32_t) * (size_t)chunk;
     if (v32_b > C.cap_v32) C.cap_v32 = v32_b;
@@ -308,6 +333,7 @@ static int ancestry_host_compact(const void* v, int64_t B, int64_t k, void* out,
     std::deque<WidenJob> jobs;
     const int64_t nchunks = (B + chunk - 1) / chunk;
     std::vector<int> pending((size_t)nchunks, 0);      // slices of a chunk not yet widened
+    std::vector<int> pending_in((size_t)nchunks, 0);   // slices of an input chunk not yet narrowed
     bool stop = false;
     std::vector<std::thread> pool;
     pool.reserve(nthreads);
@@ -321,12 +347,14 @@ static int ancestry_host_compact(const void* v, int64_t B, int64_t k, void* out,
                     if (jobs.empty()) return;
                     j = jobs.front(); jobs.pop_front();
                 }
-                if (u16) widen_trees_u16(static_cast<const uint16_t*>(j.src), j.dst, j.ntrees, k);
-                else widen_trees(static_cast<const int32_t*>(j.src), j.dst, j.ntrees, k);
+                if (j.kind == 1) narrow_inputs(static_cast<const long long*>(j.src), static_cast<int32_t*>(j.dst), j.ntrees * k);
+                else if (u16) widen_trees_u16(static_cast<const uint16_t*>(j.src), static_cast<long long*>(j.dst), j.ntrees, k);
+                else widen_trees(static_cast<const int32_t*>(j.src), static_cast<long long*>(j.dst), j.ntrees, k);
                 _mm_sfence();
                 {
                     std::lock_guard<std::mutex> lk(mu);
-                    if (--pending[(size_t)j.chunk] == 0) cv_done.notify_all();
+                    int& left = (j.kind == 1) ? pending_in[(size_t)j.chunk] : pending[(size_t)j.chunk];
+                    if (--left == 0) cv_done.notify_all();
                 }
             }
         });
@@ -340,10 +368,27 @@ static int ancestry_host_compact(const void* v, int64_t B, int64_t k, void* out,
         for (int64_t t0 = 0; t0 < nb; t0 += per) {
             const int64_t nt = (nb - t0 < per) ? (nb - t0) : per;
             jobs.push_back(WidenJob{static_cast<const char*>(C.stage[s]) + (size_t)t0 * k * wire_row,
-                                    static_cast<long long*>(out) + (size_t)(b0 + t0) * k * 3, nt, (int)c});
+                                    static_cast<long long*>(out) + (size_t)(b0 + t0) * k * 3, nt, (int)c, 0});
             ++pending[(size_t)c];
         }
         cv_job.notify_all();
+    };
+    auto enqueue_narrow = [&](int64_t c) {     // input chunk c: caller's int64 -> pinned int32 staging
+        const int s = (int)(c % HOST_STREAMS);
+        const int64_t b0 = c * chunk, nb = (B - b0 < chunk) ? (B - b0) : chunk;
+        const int64_t per = (nb + nthreads - 1) / nthreads;
+        std::lock_guard<std::mutex> lk(mu);
+        for (int64_t t0 = 0; t0 < nb; t0 += per) {
+            const int64_t nt = (nb - t0 < per) ? (nb - t0) : per;
+            jobs.push_back(WidenJob{static_cast<const long long*>(v) + (size_t)(b0 + t0) * k,
+                                    C.vstage[s] + (size_t)t0 * k, nt, (int)c, 1});
+            ++pending_in[(size_t)c];
+        }
+        cv_job.notify_all();
+    };
+    auto wait_narrowed = [&](int64_t c) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending_in[(size_t)c] == 0; });
     };
     auto wait_done = [&](int64_t c) {
         if (c < 0) return;
@@ -357,6 +402,7 @@ static int ancestry_host_compact(const void* v, int64_t B, int64_t k, void* out,
     };
 
     int rc = P2V_OK;
+    if (pageable_in) enqueue_narrow(0);
     for (int64_t c = 0; c < nchunks; ++c) {
         const int s = (int)(c % HOST_STREAMS);
         const int64_t b0 = c * chunk, nb = (B - b0 < chunk) ? (B - b0) : chunk;
@@ -364,8 +410,16 @@ static int ancestry_host_compact(const void* v, int64_t B, int64_t k, void* out,
             // (its jobs were enqueued two iterations ago)
             wait_done(c - HOST_STREAMS);
         }
-        e = cudaMemcpyAsync(H.din[s], (const char*)v + (size_t)b0 * k * 8, (size_t)k * 8 * nb, cudaMemcpyHostToDevice, H.st[s]);
-        if (e == cudaSuccess) e = launch_narrow_v(static_cast<const long long*>(H.din[s]), nb * k, C.v32[s], H.st[s]);
+        if (pageable_in) {
+            wait_narrowed(c);
+            // staging (c + 1) % 3 was last read by the H2D of chunk c - 2, whose event was waited for
+            // in the previous iteration
+            if (c + 1 < nchunks) enqueue_narrow(c + 1);
+            e = cudaMemcpyAsync(C.v32[s], C.vstage[s], (size_t)k * 4 * nb, cudaMemcpyHostToDevice, H.st[s]);
+        } else {
+            e = cudaMemcpyAsync(H.din[s], (const char*)v + (size_t)b0 * k * 8, (size_t)k * 8 * nb, cudaMemcpyHostToDevice, H.st[s]);
+            if (e == cudaSuccess) e = launch_narrow_v(static_cast<const long long*>(H.din[s]), nb * k, C.v32[s], H.st[s]);
+        }
         if (e == cudaSuccess) e = launch_decode(MODE_ANC2, C.v32[s], 4, nb, k, H.dout[s], H.dstat[s], H.dws[s], wsb, H.st[s], 0);
         const void* wire = H.dout[s];
         if (e == cudaSuccess && u16) {                  // the int32 v is dead after the decode: its buffer takes the packed pairs
