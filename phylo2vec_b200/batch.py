@@ -1,4 +1,5 @@
-"""Batched device API: torch tensors (or any DLPack producer) in, torch tensors out.
+"""Batched API: torch CUDA tensors (or any DLPack producer) in, torch tensors out -- or numpy
+arrays in, numpy arrays out through the host entry points of the C ABI.
 
 These are additions next to the reference's single-tree functions
 (SURVEY section 8b): ``(B,k)`` vectors -> ``(B,k,3)`` ancestry etc.  Tensors
@@ -12,9 +13,11 @@ from __future__ import annotations
 
 from typing import Optional, Tuple
 
+import numpy as np
 import torch
 
 from . import _capi
+from ._host import ptr as _np_ptr, raise_status as _np_raise_status
 
 _DECODE = {"to_pairs": 2, "to_ancestry": 3, "to_edges": 4}
 _ENCODE = {"from_pairs": 2, "from_ancestry": 3, "from_edges": 4}
@@ -70,8 +73,29 @@ def raise_for_status(status: torch.Tensor, v: Optional[torch.Tensor] = None) -> 
     raise ValueError(f"malformed tree input (tree {b} of the batch, code {code})")
 
 
-def _decode(name: str, V, out=None, status=None, check: bool = True) -> torch.Tensor:
+def _host_call(name: str, X: np.ndarray, out_shape, k: int, check: bool, v_for_msg=None) -> np.ndarray:
+    """numpy in, numpy out: the *_host entry point (H2D, kernels, D2H inside the call)."""
+    if X.dtype not in (np.int64, np.int32):
+        raise TypeError(f"{name}: dtype must be int64 or int32, got {X.dtype}")
+    X = np.ascontiguousarray(X)
+    B = X.shape[0]
+    out = np.empty(out_shape, dtype=X.dtype)
+    status = np.zeros(max(B, 1), dtype=np.int32)
+    rc = getattr(_capi.load(), f"p2v_{name}_host")(_np_ptr(X), X.itemsize, B, k, _np_ptr(out), _np_ptr(status))
+    _capi.check(rc, name)
+    if check:
+        _np_raise_status(status[:B], v_for_msg)
+    return out
+
+
+def _decode(name: str, V, out=None, status=None, check: bool = True):
     cols = _DECODE[name]
+    if isinstance(V, np.ndarray):           # host data: numpy in, numpy out
+        if V.ndim != 2:
+            raise ValueError(f"{name}: expected 2 dimensions, got {V.ndim}")
+        B, k = V.shape
+        shape = {"to_pairs": (B, k, 2), "to_ancestry": (B, k, 3), "to_edges": (B, 2 * k, 2)}[name]
+        return _host_call(name, V, shape, k, check, V)
     V = _idx_tensor(V, 2, name)
     B, k = V.shape
     shape = {"to_pairs": (B, k, 2), "to_ancestry": (B, k, 3), "to_edges": (B, 2 * k, 2)}[name]
@@ -114,8 +138,17 @@ def to_edges_batch(V, out=None, status=None, check=True):
     return _decode("to_edges", V, out, status, check)
 
 
-def _encode(name: str, X, out=None, status=None, check: bool = True) -> torch.Tensor:
+def _encode(name: str, X, out=None, status=None, check: bool = True):
     cols = _ENCODE[name]
+    if isinstance(X, np.ndarray):           # host data: numpy in, numpy out
+        if X.ndim != 3:
+            raise ValueError(f"{name}: expected 3 dimensions, got {X.ndim}")
+        if name == "from_edges" and X.shape[1] % 2 != 0:
+            raise AssertionError("The number of edges must be even")
+        k = X.shape[1] // 2 if name == "from_edges" else X.shape[1]
+        if X.shape[2] != (2 if name == "from_edges" else cols):
+            raise ValueError(f"{name}: bad trailing dimension {tuple(X.shape)}")
+        return _host_call(name, X, (X.shape[0], k), k, check)
     X = _idx_tensor(X, 3, name)
     B = X.shape[0]
     if name == "from_edges":

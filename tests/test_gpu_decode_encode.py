@@ -358,3 +358,25 @@ def test_host_to_ancestry_compact_transport(p2v):
         good[bad] = False
         assert np.array_equal(out[good], dev_out[good]), n_leaves
     lib.p2v_host_release()
+
+
+def test_numpy_batches_go_through_the_host_entry_points(p2v):
+    """numpy in, numpy out for the batched functions (no torch tensors involved)."""
+    n, B = 700, 9000                      # 6.3 M elements: the compact int64 transport for to_ancestry
+    k = n - 1
+    V = sample_vectors(B, n, seed=21)
+    anc = p2v.to_ancestry_batch(V)
+    assert isinstance(anc, np.ndarray) and anc.dtype == np.int64 and anc.shape == (B, k, 3)
+    idx = np.linspace(0, B - 1, 64).astype(int)
+    assert np.array_equal(anc[idx], O.batch("to_ancestry", V[idx], k)[0])
+    assert np.array_equal(p2v.to_pairs_batch(V[:50]), O.batch("to_pairs", V[:50], k)[0])
+    assert np.array_equal(p2v.to_edges_batch(V[:50].astype(np.int32)).astype(np.int64), O.batch("to_edges", V[:50], k)[0])
+    assert np.array_equal(p2v.from_ancestry_batch(anc), V)
+    assert np.array_equal(p2v.from_pairs_batch(p2v.to_pairs_batch(V[:50])), V[:50])
+    assert np.array_equal(p2v.from_edges_batch(p2v.to_edges_batch(V[:50])), V[:50])
+    bad = V[:8].copy()
+    bad[3, 5] = 11
+    with pytest.raises(AssertionError, match=r"v\[5\] = 11"):
+        p2v.to_ancestry_batch(bad)
+    with pytest.raises(TypeError):
+        p2v.to_ancestry_batch(V.astype(np.float64))
