@@ -226,8 +226,10 @@ static int host_thread_count() {
     int n = 0;
     if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
     if (n <= 0) n = (int)std::thread::hardware_concurrency();
+    const char* lw = getenv("LOCAL_WORLD_SIZE");         // one process per GPU (torchrun): share the cores
+    if (lw && atoi(lw) > 1) n /= atoi(lw);
     if (n > 16) n = 16;
-    return n < 1 ? 1 : n;
+    return n < 2 ? 2 : n;
 }
 static bool host_compact_enabled() {
     const char* e = getenv("P2V_HOST_COMPACT");
