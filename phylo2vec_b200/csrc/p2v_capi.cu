@@ -140,6 +140,159 @@ static cudaError_t host_ensure(HostCtx& H, size_t in_b, size_t out_b, size_t ws_
     return cudaSuccess;
 }
 
+static int host_thread_count();
+static bool is_pageable(const void* p);
+
+// Pinned staging of the generic host path: a pageable buffer (a plain numpy array) would be staged
+// by the driver on one thread at ~10 GB/s; here worker threads copy it through pinned buffers of
+// the library, chunk by chunk, while the other chunks are in flight.
+struct StageCtx {
+    void* hin[HOST_STREAMS] = {};
+    void* hout[HOST_STREAMS] = {};
+    int32_t* hstat[HOST_STREAMS] = {};
+    cudaEvent_t ev[HOST_STREAMS] = {};
+    size_t cap_in = 0, cap_out = 0, cap_stat = 0;
+    void release() {
+        for (int i = 0; i < HOST_STREAMS; ++i) {
+            if (hin[i]) cudaFreeHost(hin[i]);
+            if (hout[i]) cudaFreeHost(hout[i]);
+            if (hstat[i]) cudaFreeHost(hstat[i]);
+            if (ev[i]) cudaEventDestroy(ev[i]);
+            hin[i] = hout[i] = nullptr; hstat[i] = nullptr; ev[i] = nullptr;
+        }
+        cap_in = cap_out = cap_stat = 0;
+    }
+};
+static thread_local StageCtx g_stage;
+
+struct CopyJob { const void* src; void* dst; size_t bytes; int chunk; int kind; };   // kind 0: out, 1: in
+
+template <typename Launch>
+static int host_chunked_staged(const void* in, size_t in_tree_bytes, void* out, size_t out_tree_bytes,
+                               int32_t* status, int64_t B, int64_t chunk, size_t wsb, bool page_in, bool page_out,
+                               Launch launch) {
+    HostCtx& H = g_host;
+    StageCtx& S = g_stage;
+    cudaError_t e = cudaSuccess;
+    const size_t in_b = in_tree_bytes * chunk, out_b = out_tree_bytes * chunk, st_b = sizeof(int32_t) * (size_t)chunk;
+    for (int i = 0; i < HOST_STREAMS && e == cudaSuccess; ++i) {
+        if (page_in && (in_b > S.cap_in || !S.hin[i])) {
+            if (S.hin[i]) cudaFreeHost(S.hin[i]);
+            S.hin[i] = nullptr;
+            e = cudaHostAlloc(&S.hin[i], in_b, cudaHostAllocDefault);
+        }
+        if (e == cudaSuccess && page_out && (out_b > S.cap_out || !S.hout[i])) {
+            if (S.hout[i]) cudaFreeHost(S.hout[i]);
+            S.hout[i] = nullptr;
+            e = cudaHostAlloc(&S.hout[i], out_b, cudaHostAllocDefault);
+        }
+        if (e == cudaSuccess && (st_b > S.cap_stat || !S.hstat[i])) {
+            if (S.hstat[i]) cudaFreeHost(S.hstat[i]);
+            S.hstat[i] = nullptr;
+            e = cudaHostAlloc((void**)&S.hstat[i], st_b, cudaHostAllocDefault);
+        }
+        if (e == cudaSuccess && !S.ev[i]) e = cudaEventCreateWithFlags(&S.ev[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) { S.release(); return from_cuda(e, "host entry: staging allocation"); }
+    if (page_in && in_b > S.cap_in) S.cap_in = in_b;
+    if (page_out && out_b > S.cap_out) S.cap_out = out_b;
+    if (st_b > S.cap_stat) S.cap_stat = st_b;
+
+    const int nthreads = host_thread_count();
+    const int64_t nchunks = (B + chunk - 1) / chunk;
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    std::deque<CopyJob> jobs;
+    std::vector<int> pend_out((size_t)nchunks, 0), pend_in((size_t)nchunks, 0);
+    bool stop = false;
+    std::vector<std::thread> pool;
+    pool.reserve(nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+        pool.emplace_back([&]() {
+            for (;;) {
+                CopyJob j;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv_job.wait(lk, [&] { return stop || !jobs.empty(); });
+                    if (jobs.empty()) return;
+                    j = jobs.front(); jobs.pop_front();
+                }
+                memcpy(j.dst, j.src, j.bytes);
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    int& left = j.kind ? pend_in[(size_t)j.chunk] : pend_out[(size_t)j.chunk];
+                    if (--left == 0) cv_done.notify_all();
+                }
+            }
+        });
+    }
+    auto enqueue_copy = [&](const void* src, void* dst, size_t bytes, int64_t c, int kind) {
+        const size_t per = ((bytes + nthreads - 1) / nthreads + 63) & ~(size_t)63;
+        std::lock_guard<std::mutex> lk(mu);
+        for (size_t o = 0; o < bytes; o += per) {
+            jobs.push_back(CopyJob{static_cast<const char*>(src) + o, static_cast<char*>(dst) + o,
+                                   (bytes - o < per) ? (bytes - o) : per, (int)c, kind});
+            ++(kind ? pend_in : pend_out)[(size_t)c];
+        }
+        cv_job.notify_all();
+    };
+    auto wait_for = [&](std::vector<int>& pend, int64_t c) {
+        if (c < 0) return;
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pend[(size_t)c] == 0; });
+    };
+    auto chunk_trees = [&](int64_t c) { const int64_t b0 = c * chunk; return (B - b0 < chunk) ? (B - b0) : chunk; };
+    auto landed = [&](int64_t c) {              // chunk c is complete on the host side of the wire
+        const int s = (int)(c % HOST_STREAMS);
+        const int64_t b0 = c * chunk, nb = chunk_trees(c);
+        if (status) memcpy(status + b0, S.hstat[s], sizeof(int32_t) * nb);
+        if (page_out && out_tree_bytes)
+            enqueue_copy(S.hout[s], static_cast<char*>(out) + (size_t)b0 * out_tree_bytes, out_tree_bytes * nb, c, 0);
+    };
+
+    int rc = P2V_OK;
+    if (page_in && in_tree_bytes) enqueue_copy(in, S.hin[0], in_tree_bytes * chunk_trees(0), 0, 1);
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int s = (int)(c % HOST_STREAMS);
+        const int64_t b0 = c * chunk, nb = chunk_trees(c);
+        if (page_out) wait_for(pend_out, c - HOST_STREAMS);           // staging s has been copied out
+        const void* src = static_cast<const char*>(in) + (size_t)b0 * in_tree_bytes;
+        if (page_in && in_tree_bytes) {
+            wait_for(pend_in, c);
+            if (c + 1 < nchunks)                 // staging (c+1)%3 was read by chunk c-2, complete since the last iteration
+                enqueue_copy(static_cast<const char*>(in) + (size_t)(c + 1) * chunk * in_tree_bytes,
+                             S.hin[(c + 1) % HOST_STREAMS], in_tree_bytes * chunk_trees(c + 1), c + 1, 1);
+            src = S.hin[s];
+        }
+        e = cudaSuccess;
+        if (in_tree_bytes) e = cudaMemcpyAsync(H.din[s], src, in_tree_bytes * nb, cudaMemcpyHostToDevice, H.st[s]);
+        if (e == cudaSuccess) e = launch(H.din[s], H.dout[s], H.dstat[s], nb, H.dws[s], wsb, H.st[s]);
+        if (e == cudaSuccess && out_tree_bytes)
+            e = cudaMemcpyAsync(page_out ? S.hout[s] : static_cast<void*>(static_cast<char*>(out) + (size_t)b0 * out_tree_bytes),
+                                H.dout[s], out_tree_bytes * nb, cudaMemcpyDeviceToHost, H.st[s]);
+        if (e == cudaSuccess && status)
+            e = cudaMemcpyAsync(S.hstat[s], H.dstat[s], sizeof(int32_t) * nb, cudaMemcpyDeviceToHost, H.st[s]);
+        if (e == cudaSuccess) e = cudaEventRecord(S.ev[s], H.st[s]);
+        if (e == cudaSuccess && c >= 1) {
+            e = cudaEventSynchronize(S.ev[(c - 1) % HOST_STREAMS]);
+            if (e == cudaSuccess) landed(c - 1);
+        }
+        if (e != cudaSuccess) { rc = from_cuda(e, "host entry: chunk"); break; }
+    }
+    if (rc == P2V_OK) {
+        e = cudaEventSynchronize(S.ev[(nchunks - 1) % HOST_STREAMS]);
+        if (e == cudaSuccess) landed(nchunks - 1);
+        else rc = from_cuda(e, "host entry: synchronize");
+    }
+    if (rc == P2V_OK && page_out)
+        for (int64_t c = (nchunks > HOST_STREAMS ? nchunks - HOST_STREAMS : 0); c < nchunks; ++c) wait_for(pend_out, c);
+    { std::lock_guard<std::mutex> lk(mu); stop = true; }
+    cv_job.notify_all();
+    for (auto& th : pool) th.join();
+    for (int i = 0; i < HOST_STREAMS; ++i) cudaStreamSynchronize(H.st[i]);
+    return rc;
+}
+
 template <typename Launch, typename WsBytes>
 static int host_chunked(const void* in, size_t in_tree_bytes, void* out, size_t out_tree_bytes,
                         int32_t* status, int64_t B, WsBytes ws_bytes_of, Launch launch) {
@@ -154,6 +307,17 @@ static int host_chunked(const void* in, size_t in_tree_bytes, void* out, size_t 
     const size_t wsb = ws_bytes_of(chunk);
     cudaError_t e = host_ensure(H, in_tree_bytes * chunk, out_tree_bytes * chunk, wsb, sizeof(int32_t) * chunk);
     if (e != cudaSuccess) { H.release(); return from_cuda(e, "host entry: device allocation"); }
+    // big calls on pageable buffers: threaded staging through pinned memory
+    if ((in_tree_bytes + out_tree_bytes) * (size_t)B >= ((size_t)32 << 20)) {
+        const bool page_in = in_tree_bytes && in && is_pageable(in);
+        const bool page_out = out_tree_bytes && out && is_pageable(out);
+        if (page_in || page_out) {
+            int64_t cs = (int64_t)(((size_t)256 << 20) / per);      // smaller chunks: the staging is pinned memory
+            if (cs < 1) cs = 1;
+            if (cs > chunk) cs = chunk;
+            return host_chunked_staged(in, in_tree_bytes, out, out_tree_bytes, status, B, cs, wsb, page_in, page_out, launch);
+        }
+    }
     int c = 0;
     for (int64_t b0 = 0; b0 < B; b0 += chunk, ++c) {
         const int s = c % HOST_STREAMS;
@@ -792,7 +956,7 @@ int p2v_cophenetic_matrix_host(const double* m, int64_t B, int64_t k, int unroot
     return coph_host(m, 0, nullptr, B, k, unrooted, row_begin, row_end, out, status);
 }
 
-void p2v_host_release(void) { g_host.release(); g_compact.release(); }
+void p2v_host_release(void) { g_host.release(); g_compact.release(); g_stage.release(); }
 
 int p2v_fill_f64(double* out, int64_t count, double value, p2v_stream_t stream) {
     if (count > 0 && !out) return fail(P2V_ERR_INVALID_ARG, "null buffer");

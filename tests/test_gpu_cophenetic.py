@@ -264,3 +264,23 @@ def test_small_tree_batches(p2v):
         assert rel_err(part, got[:, r0:r1]) <= 1e-15
         if n_leaves <= 256:
             assert np.array_equal(part, got[:, r0:r1])
+
+
+def test_host_entry_point_large_pageable(p2v):
+    """Big pageable output (numpy): the host entry point stages it through pinned memory with threads."""
+    import ctypes
+    from phylo2vec_b200 import _capi
+    lib = _capi.load()
+    n, B = 300, 400                       # 288 MB of distances
+    V = sample_vectors(B, n, seed=12)
+    bls = sample_bls(B, n, seed=12)
+    M = np.ascontiguousarray(to_matrix_input(V, bls))
+    out = np.zeros((B, n, n))
+    st = np.ones(B, dtype=np.int32)
+    vp = ctypes.c_void_p
+    rc = lib.p2v_cophenetic_matrix_host(M.ctypes.data_as(vp), B, n - 1, 0, 0, n, out.ctypes.data_as(vp), st.ctypes.data_as(vp))
+    assert rc == 0 and not st.any()
+    idx = np.linspace(0, B - 1, 16).astype(int)
+    assert rel_err(out[idx], O.cophenetic_batch(V[idx], bls[idx])) <= RTOL
+    dev_out = p2v.cophenetic_distances_batch(dev(M)).cpu().numpy()
+    assert np.array_equal(out, dev_out)

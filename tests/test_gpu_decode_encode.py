@@ -372,6 +372,13 @@ def test_numpy_batches_go_through_the_host_entry_points(p2v):
     assert np.array_equal(p2v.to_pairs_batch(V[:50]), O.batch("to_pairs", V[:50], k)[0])
     assert np.array_equal(p2v.to_edges_batch(V[:50].astype(np.int32)).astype(np.int64), O.batch("to_edges", V[:50], k)[0])
     assert np.array_equal(p2v.from_ancestry_batch(anc), V)
+    # big pageable buffers: threaded staging through pinned memory, several chunks
+    edges = p2v.to_edges_batch(V)
+    assert np.array_equal(edges[idx], O.batch("to_edges", V[idx], k)[0])
+    assert np.array_equal(p2v.from_edges_batch(edges), V)
+    pairs = p2v.to_pairs_batch(V)
+    assert np.array_equal(pairs[idx], O.batch("to_pairs", V[idx], k)[0])
+    assert np.array_equal(p2v.from_pairs_batch(pairs), V)
     assert np.array_equal(p2v.from_pairs_batch(p2v.to_pairs_batch(V[:50])), V[:50])
     assert np.array_equal(p2v.from_edges_batch(p2v.to_edges_batch(V[:50])), V[:50])
     bad = V[:8].copy()
