@@ -206,21 +206,45 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                     if (d2 != NONE16 && d2 >= (uint32_t)s) d2 = NONE16;
                 }
                 uint32_t done = __ballot_sync(FULL, !act);
+                // A row fires when the rows defining its internal children have fired.  Rows that only
+                // wait for the row just before them (the usual case: a non-root row continues the
+                // previous row's subtree) form chains; a whole chain hanging off a fired or ready row
+                // is resolved in one step with a segmented min-scan, so the number of rounds is the
+                // depth of the OTHER in-batch dependencies, not the chain length.
                 while (done != FULL) {
-                    bool ready = false;
-                    if (!((done >> lane) & 1u)) {
-                        const bool w1 = d1 != NONE16 && d1 >= (uint32_t)base_row && !((done >> (d1 - base_row)) & 1u);
-                        const bool w2 = d2 != NONE16 && d2 >= (uint32_t)base_row && !((done >> (d2 - base_row)) & 1u);
-                        ready = !w1 && !w2;
-                        if (ready) {
-                            const uint32_t m1 = (d1 != NONE16) ? (uint32_t)smd[c1 - kint] : c1;
-                            const uint32_t m2 = (d2 != NONE16) ? (uint32_t)smd[c2 - kint] : c2;
-                            smd[p - kint] = (uint16_t)min(m1, m2);
-                            sc1[s] = (uint16_t)m1; sc2[s] = (uint16_t)m2;
-                        }
+                    const bool mine_pending = !((done >> lane) & 1u);
+                    const bool w1 = d1 != NONE16 && d1 >= (uint32_t)base_row && !((done >> (d1 - base_row)) & 1u);
+                    const bool w2 = d2 != NONE16 && d2 >= (uint32_t)base_row && !((done >> (d2 - base_row)) & 1u);
+                    bool prev1 = w1 && d1 + 1 == (uint32_t)s, prev2 = w2 && d2 + 1 == (uint32_t)s;
+                    const bool other = (w1 && !prev1) || (w2 && !prev2) || (prev1 && prev2);
+                    const bool avail = mine_pending && !other;
+                    const uint32_t A = __ballot_sync(FULL, avail);
+                    const uint32_t Lk = __ballot_sync(FULL, avail && (prev1 || prev2));
+                    const uint32_t H = A & ~Lk;                      // ready on their own
+                    const uint32_t T = (H << 1) & Lk;                // chain links right above a ready row
+                    const uint32_t Rm = H | (((Lk + T) ^ Lk) & Lk);  // ... and the whole runs of links above them
+                    const bool mine = (Rm >> lane) & 1u;
+                    uint32_t o1 = 0xFFFFu, o2 = 0xFFFFu;
+                    if (mine) {
+                        if (!prev1) o1 = (d1 != NONE16) ? (uint32_t)smd[c1 - kint] : c1;
+                        if (!prev2) o2 = (d2 != NONE16) ? (uint32_t)smd[c2 - kint] : c2;
+                    }
+                    uint32_t val = min(o1, o2);
+                    const uint32_t hb = H & lanes_le(lane);
+                    const int dist = hb ? lane - (31 - __clz(hb)) : 0;  // distance to the head of my run
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t y = __shfl_up_sync(FULL, val, d);
+                        if (mine && dist >= d) val = min(val, y);
+                    }
+                    const uint32_t pm = __shfl_up_sync(FULL, val, 1);   // min descendant of the row before
+                    if (mine) {
+                        const uint32_t m1 = prev1 ? pm : o1, m2 = prev2 ? pm : o2;
+                        smd[p - kint] = (uint16_t)val;
+                        sc1[s] = (uint16_t)m1; sc2[s] = (uint16_t)m2;
                     }
                     __syncwarp();
-                    done |= __ballot_sync(FULL, ready);
+                    done |= Rm;
                 }
             }
             __syncwarp();
