@@ -149,13 +149,29 @@ int p2v_node_depths_batch(const void *v_or_matrix, int idx_bytes, const double *
  * point to_newick, vector arm (py-phylo2vec/src/lib.rs:90-96); Python phylo2vec.base.newick.
  * to_newick (base/newick.py:29-43).  Tree b's string is written NUL-terminated at
  * out + b * out_stride (out_stride >= p2v_newick_max_bytes(k)); lengths[b] (may be NULL) gets
- * its length without the NUL, 0 for an invalid vector.  1 <= k <= 1023 for now
- * (P2V_ERR_UNSUPPORTED above; the matrix form with branch lengths is not built). */
+ * its length without the NUL, 0 for an invalid vector.  k <= 2^19 (the matrix form with
+ * branch lengths is not built).  The workspace holds the int32 ancestry of the batch, the
+ * decoder's scratch and, for trees too large for shared memory, per-CTA tables. */
 size_t p2v_newick_max_bytes(int64_t k);
 size_t p2v_newick_workspace_bytes(int64_t B, int64_t k);     /* the int32 ancestry of the batch */
 int p2v_to_newick_batch(const void *v, int idx_bytes, int64_t B, int64_t k, char *out, int64_t out_stride,
                         int64_t *lengths, int32_t *status, void *workspace, size_t workspace_bytes,
                         p2v_stream_t stream);
+
+/* ---- from_newick (second "next" row; vectors, Newick with parent labels) -------------------
+ * replaces newick::parse (phylo2vec/src/newick/mod.rs:73-127) and vector::convert::from_newick,
+ * has_parents arm (vector/convert.rs:268-278: parse, order_cherries, build_vector); PyO3 entry
+ * point to_vector (py-phylo2vec/src/lib.rs:98-101); Python phylo2vec.base.newick.from_newick.
+ * Every tree of the batch has k + 1 leaves labelled 0..k and internal nodes k+1..2k.  Tree b's
+ * string starts at newick + b * in_stride and is lengths[b] bytes long (lengths == NULL: it is
+ * NUL-terminated inside its row).  status[b]: 0, P2V_TREE_MALFORMED (not a binary Newick of
+ * k + 1 leaves made of "(),;" and digits, or labels that do not form a tree), or
+ * P2V_ERR_UNSUPPORTED for a string without parent labels ("((0,1),2);" -- the reference's
+ * order_cherries_no_parents arm is not built). */
+size_t p2v_from_newick_workspace_bytes(int64_t B, int64_t k, int idx_bytes);
+int p2v_from_newick_batch(const char *newick, int64_t in_stride, const int64_t *lengths, int64_t B, int64_t k,
+                          void *v, int idx_bytes, int32_t *status, void *workspace, size_t workspace_bytes,
+                          p2v_stream_t stream);
 
 /* ---- host-buffer entry points (H2D + kernels + D2H inside the call) ------ */
 int p2v_to_pairs_host(const void *v, int idx_bytes, int64_t B, int64_t k, void *pairs, int32_t *status);
@@ -179,6 +195,10 @@ int p2v_node_depths_host(const void *v_or_matrix, int idx_bytes, const double *b
 
 int p2v_to_newick_host(const void *v, int idx_bytes, int64_t B, int64_t k, char *out, int64_t out_stride,
                        int64_t *lengths, int32_t *status);
+
+/* NUL-terminated strings, one per in_stride bytes */
+int p2v_from_newick_host(const char *newick, int64_t in_stride, int64_t B, int64_t k, void *v, int idx_bytes,
+                         int32_t *status);
 
 /* The *_host entry points cache three streams and their device staging buffers per host
  * thread (they grow on demand).  This frees the calling thread's cache. */

@@ -721,6 +721,124 @@ i64 p2vo_to_newick(const i64 *v, i64 k, char *buf, i64 cap) {
 }
 
 /* ------------------------------------------------------------------------ */
+/* from_newick, vectors (convert.rs:268-278) on top of newick::parse          */
+/* (newick/mod.rs:73-127): the literal stack walk; has_parents = some ")" is  */
+/* followed by a digit (newick_patterns.rs `\)(\d+)`).                        */
+/* anc: up to cap rows [c1, c2, p]; returns the number of rows or <0.         */
+/* ------------------------------------------------------------------------ */
+i64 p2vo_newick_parse(const char *s, i64 len, i64 *anc, i64 cap) {
+    i64 *stack = (i64 *)malloc(sizeof(i64) * (size_t)(len + 2));
+    if (!stack) return P2VO_ENOMEM;
+    i64 sp = 0, rows = 0, i = 0, rc = 0;
+    while (i < len) {
+        char c = s[i];
+        if (c == ')') {
+            if (sp < 2) { rc = P2VO_EBADINPUT; break; }          /* StackUnderflow */
+            i64 c2 = stack[--sp], c1 = stack[--sp];
+            i64 e = i + 1;                                        /* node_substr: up to , ) ; */
+            while (e < len && s[e] != ',' && s[e] != ')' && s[e] != ';') ++e;
+            if (e == len) e = i + 1;                              /* no terminator: node_substr returns "" (mod.rs:23-38) */
+            if (rows >= cap) { rc = P2VO_EBADINPUT; break; }
+            if (e == i + 1) {                                     /* no parent label */
+                i64 lo = c1 < c2 ? c1 : c2, hi = c1 < c2 ? c2 : c1;
+                anc[3 * rows] = c1; anc[3 * rows + 1] = c2; anc[3 * rows + 2] = hi; ++rows;
+                stack[sp++] = lo;
+            } else {
+                i64 p = 0;
+                for (i64 j = i + 1; j < e; ++j) {
+                    if (s[j] < '0' || s[j] > '9') { rc = P2VO_EBADINPUT; break; }   /* ParseIntError */
+                    p = p * 10 + (s[j] - '0');
+                }
+                if (rc) break;
+                anc[3 * rows] = c1; anc[3 * rows + 1] = c2; anc[3 * rows + 2] = p; ++rows;
+                stack[sp++] = p;
+                i = e - 1;
+            }
+        } else if (c >= '0' && c <= '9') {
+            i64 e = i;
+            while (e < len && s[e] != ',' && s[e] != ')' && s[e] != ';') ++e;
+            if (e == len) { rc = P2VO_EBADINPUT; break; }         /* "" does not parse as an integer */
+            i64 x = 0;
+            for (i64 j = i; j < e; ++j) {
+                if (s[j] < '0' || s[j] > '9') { rc = P2VO_EBADINPUT; break; }
+                x = x * 10 + (s[j] - '0');
+            }
+            if (rc) break;
+            stack[sp++] = x;
+            i = e - 1;
+        }
+        ++i;
+    }
+    free(stack);
+    return rc ? rc : rows;
+}
+
+/* convert.rs:534-573 (order_cherries_no_parents), in place */
+static int order_cherries_no_parents(i64 *anc, i64 k) {
+    i64 *sister = (i64 *)malloc(sizeof(i64) * (size_t)k);
+    i64 *visited = (i64 *)malloc(sizeof(i64) * (size_t)(2 * k + 2));
+    i64 *idx = (i64 *)malloc(sizeof(i64) * (size_t)k);
+    i64 *tmp = (i64 *)malloc(sizeof(i64) * 3 * (size_t)k);
+    if (!sister || !visited || !idx || !tmp) { free(sister); free(visited); free(idx); free(tmp); return P2VO_ENOMEM; }
+    int rc = 0;
+    for (i64 i = 0; i < 2 * k + 2; ++i) visited[i] = -1;
+    for (i64 r = 0; r < k && !rc; ++r) {
+        i64 c1 = anc[3 * r], c2 = anc[3 * r + 1], cm = anc[3 * r + 2];
+        i64 lo = c1 < c2 ? c1 : c2;
+        if (lo < 0 || lo > 2 * k + 1) { rc = P2VO_EBADINPUT; break; }
+        i64 sis = (visited[lo] >= 0 && visited[lo] < cm) ? visited[lo] : cm;
+        sister[r] = sis; visited[lo] = sis;
+    }
+    if (!rc) {      /* stable argsort, descending by sister: insertion sort keeps equal keys in row order */
+        for (i64 r = 0; r < k; ++r) idx[r] = r;
+        for (i64 a = 1; a < k; ++a) {
+            i64 x = idx[a], b = a;
+            while (b > 0 && sister[idx[b - 1]] < sister[x]) { idx[b] = idx[b - 1]; --b; }
+            idx[b] = x;
+        }
+        for (i64 r = 0; r < k; ++r) memcpy(tmp + 3 * r, anc + 3 * idx[r], sizeof(i64) * 3);
+        memcpy(anc, tmp, sizeof(i64) * 3 * (size_t)k);
+    }
+    free(sister); free(visited); free(idx); free(tmp);
+    return rc;
+}
+
+/* v gets k = (number of cherries) entries; returns k or <0 */
+i64 p2vo_from_newick(const char *s, i64 len, i64 *v, i64 cap) {
+    if (len == 0) return 0;
+    i64 *anc = (i64 *)malloc(sizeof(i64) * 3 * (size_t)(len + 1));
+    if (!anc) return P2VO_ENOMEM;
+    i64 k = p2vo_newick_parse(s, len, anc, len);
+    if (k < 0 || k > cap) { free(anc); return k < 0 ? k : P2VO_EBADINPUT; }
+    int parents = 0;
+    for (i64 i = 0; i + 1 < len; ++i) if (s[i] == ')' && s[i + 1] >= '0' && s[i + 1] <= '9') { parents = 1; break; }
+    int rc = 0;
+    if (k > 0) {
+        rc = parents ? p2vo_order_cherries(anc, k) : order_cherries_no_parents(anc, k);
+        if (!rc) rc = p2vo_build_vector(anc, k, v);
+    }
+    free(anc);
+    return rc ? rc : k;
+}
+
+/* strings at in + b*stride, lengths[b] bytes each; v (B,k); status per tree */
+int p2vo_from_newick_batch(const char *in, i64 stride, const i64 *lengths, i64 B, i64 k, i64 *v, int32_t *status,
+                           int nthreads) {
+    int bad = 0;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads) reduction(| : bad)
+#endif
+    for (i64 b = 0; b < B; ++b) {
+        i64 got = p2vo_from_newick(in + b * stride, lengths[b], v + b * k, k);
+        int rc = (got == k) ? 0 : (got < 0 ? (int)got : P2VO_EBADINPUT);
+        if (status) status[b] = rc;
+        if (rc) bad |= 1;
+    }
+    return bad;
+}
+
+/* ------------------------------------------------------------------------ */
 /* Batch drivers for the CPU baseline: the reference has no batch API and no  */
 /* threads; one reference call == one tree on one core, so the    */
 /* baseline is an OpenMP parallel-for over trees.                            */

@@ -68,6 +68,12 @@ def lib() -> ctypes.CDLL:
         _lib.p2vo_node_depths.argtypes = [p, p, i64, p]
         _lib.p2vo_to_newick.restype = i64
         _lib.p2vo_to_newick.argtypes = [p, i64, ctypes.c_char_p, i64]
+        _lib.p2vo_newick_parse.restype = i64
+        _lib.p2vo_newick_parse.argtypes = [ctypes.c_char_p, i64, p, i64]
+        _lib.p2vo_from_newick.restype = i64
+        _lib.p2vo_from_newick.argtypes = [ctypes.c_char_p, i64, p, i64]
+        _lib.p2vo_from_newick_batch.restype = ctypes.c_int
+        _lib.p2vo_from_newick_batch.argtypes = [p, i64, p, i64, i64, p, p, ctypes.c_int]
         _lib.p2vo_to_newick_batch.restype = ctypes.c_int
         _lib.p2vo_to_newick_batch.argtypes = [p, i64, i64, p, i64, p, ctypes.c_int]
         _lib.p2vo_num_threads.restype = ctypes.c_int
@@ -312,3 +318,34 @@ def to_newick_batch(v: np.ndarray, stride: int, nthreads: int = 0):
     if rc:
         raise ValueError(f"oracle: to_newick_batch failed ({rc})")
     return out, lengths
+
+
+def newick_parse(newick: str) -> np.ndarray:
+    """newick::parse (newick/mod.rs:73-127): rows [c1, c2, p] in string order."""
+    data = newick.encode("ascii")
+    anc = np.zeros((len(data) + 1, 3), dtype=np.int64)
+    rows = int(lib().p2vo_newick_parse(data, len(data), _ptr(anc), anc.shape[0]))
+    if rows < 0:
+        raise ValueError(f"oracle: newick parse failed ({rows})")
+    return anc[:rows].copy()
+
+
+def from_newick(newick: str) -> np.ndarray:
+    """vector::convert::from_newick (convert.rs:268-278), with or without parent labels."""
+    data = newick.encode("ascii")
+    v = np.zeros(len(data) + 1, dtype=np.int64)
+    k = int(lib().p2vo_from_newick(data, len(data), _ptr(v), v.size))
+    if k < 0:
+        raise ValueError(f"oracle: from_newick failed ({k})")
+    return v[:k].copy()
+
+
+def from_newick_batch(buf: np.ndarray, lengths: np.ndarray, k: int, nthreads: int = 0):
+    """buf uint8 (B, stride); returns (v (B,k) int64, status int32)."""
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+    B, stride = buf.shape
+    v = np.zeros((B, k), dtype=np.int64)
+    status = np.zeros(B, dtype=np.int32)
+    lib().p2vo_from_newick_batch(_ptr(buf), stride, _ptr(lengths), B, k, _ptr(v), _ptr(status), nthreads)
+    return v, status

@@ -327,7 +327,7 @@ def node_depths_batch(trees, out=None, bls=None, status=None, check: bool = True
 
 
 def to_newick_batch(V, status=None, check: bool = True, raw: bool = False):
-    """Newick strings of a batch of vectors ``(B,k)`` (k <= 1023).  Returns a list of ``str``; with
+    """Newick strings of a batch of vectors ``(B,k)`` .  Returns a list of ``str``; with
     ``raw=True`` the device buffers instead: a uint8 tensor ``(B, stride)`` of NUL-terminated strings
     and an int64 tensor of their lengths.
     Replaces vector::convert::to_newick (phylo2vec/src/vector/convert.rs:341-397)."""
@@ -353,3 +353,55 @@ def to_newick_batch(V, status=None, check: bool = True, raw: bool = False):
     host = out.cpu().numpy()
     ln = lengths.cpu().numpy()
     return [host[b, :ln[b]].tobytes().decode("ascii") for b in range(B)]
+
+
+def from_newick_batch(newick, lengths=None, n_leaves: Optional[int] = None, dtype=torch.int64, status=None,
+                      check: bool = True, device=None) -> torch.Tensor:
+    """Vectors ``(B,k)`` of a batch of Newick strings with parent labels; every tree has the same
+    number of leaves.  ``newick`` is a list of ``str`` or the raw form :func:`to_newick_batch` returns
+    (uint8 tensor ``(B, stride)`` on the GPU, with ``lengths`` or NUL-terminated rows).
+    Replaces newick::parse + vector::convert::from_newick (phylo2vec/src/newick/mod.rs:73-127,
+    vector/convert.rs:268-278)."""
+    if isinstance(newick, (list, tuple)):
+        if len(newick) == 0:
+            raise ValueError("from_newick: empty batch")
+        enc = [s.encode("ascii") for s in newick]
+        if n_leaves is None:
+            n_leaves = enc[0].count(b",") + 1
+        stride = (max(len(e) for e in enc) + 1 + 15) & ~15
+        host = np.zeros((len(enc), stride), dtype=np.uint8)
+        for b, e in enumerate(enc):
+            host[b, :len(e)] = np.frombuffer(e, dtype=np.uint8)
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        newick = torch.from_numpy(host).to(dev)
+        lengths = torch.tensor([len(e) for e in enc], dtype=torch.int64, device=dev)
+    if not (isinstance(newick, torch.Tensor) and newick.dtype == torch.uint8 and newick.dim() == 2 and newick.is_cuda):
+        raise TypeError("from_newick: expected a list of str or a uint8 CUDA tensor (B, stride)")
+    if n_leaves is None:
+        raise ValueError("from_newick: n_leaves is required with a raw buffer")
+    newick = newick.contiguous()
+    B, stride = newick.shape
+    k = int(n_leaves) - 1
+    lib = _capi.load()
+    idx_bytes = 8 if dtype == torch.int64 else 4
+    if dtype not in (torch.int64, torch.int32):
+        raise TypeError("from_newick: dtype must be torch.int64 or torch.int32")
+    v = torch.empty((B, k), dtype=dtype, device=newick.device)
+    if status is None:
+        status = torch.empty(B, dtype=torch.int32, device=newick.device)
+    if lengths is not None:
+        lengths = lengths.to(device=newick.device, dtype=torch.int64).contiguous()
+    need = int(lib.p2v_from_newick_workspace_bytes(B, k, idx_bytes))
+    with torch.cuda.device(newick.device):
+        ws = torch.empty(max(need, 16), dtype=torch.uint8, device=newick.device)
+        rc = lib.p2v_from_newick_batch(newick.data_ptr(), stride, 0 if lengths is None else lengths.data_ptr(), B, k,
+                                       v.data_ptr(), idx_bytes, status.data_ptr(), ws.data_ptr(), need,
+                                       _stream_ptr(newick.device))
+    _capi.check(rc, "from_newick")
+    if check:
+        st = status.cpu().numpy()
+        if (st == -3).any():
+            raise NotImplementedError("from_newick of a string without parent labels is not built in phylo2vec_b200")
+        if st.any():
+            raise ValueError(f"malformed Newick string (tree {int(np.flatnonzero(st)[0])})")
+    return v

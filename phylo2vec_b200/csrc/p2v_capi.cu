@@ -851,7 +851,7 @@ size_t p2v_newick_workspace_bytes(int64_t B, int64_t k) { return newick_workspac
 static int newick_check(const void* v, const char* out, int idx_bytes, int64_t B, int64_t k, int64_t out_stride) {
     if (idx_bytes != 4 && idx_bytes != 8) return fail(P2V_ERR_INVALID_ARG, "idx_bytes must be 4 or 8");
     if (B < 0 || k < 0) return fail(P2V_ERR_INVALID_ARG, "negative batch or length");
-    if (k > 1023) return fail(P2V_ERR_UNSUPPORTED, "to_newick: k above 1023 is not built yet");
+    if (k > LARGE_K_MAX) return fail(P2V_ERR_UNSUPPORTED, "to_newick: k above 2^19");
     if (B > 0 && (!out || (k > 0 && !v))) return fail(P2V_ERR_INVALID_ARG, "null buffer");
     if (out_stride < (int64_t)newick_max_bytes(k)) return fail(P2V_ERR_INVALID_ARG, "out_stride below p2v_newick_max_bytes(k)");
     return P2V_OK;
@@ -909,6 +909,43 @@ int p2v_to_newick_host(const void* v, int idx_bytes, int64_t B, int64_t k, char*
     cudaDeviceSynchronize();
     for (int i = 0; i < HOST_STREAMS; ++i) if (dlen[i]) cudaFree(dlen[i]);
     return r;
+}
+
+// ---- from_newick (vectors, Newick with parent labels) ------------------------------------------
+size_t p2v_from_newick_workspace_bytes(int64_t B, int64_t k, int idx_bytes) { return from_newick_workspace_bytes(B, k, idx_bytes); }
+static int from_newick_check(const char* newick, int64_t in_stride, const void* v, int idx_bytes, int64_t B, int64_t k) {
+    if (idx_bytes != 4 && idx_bytes != 8) return fail(P2V_ERR_INVALID_ARG, "idx_bytes must be 4 or 8");
+    if (B < 0 || k < 0) return fail(P2V_ERR_INVALID_ARG, "negative batch or length");
+    if (k > LARGE_K_MAX) return fail(P2V_ERR_UNSUPPORTED, "from_newick: k above 2^19");
+    if (B > 0 && (!newick || (k > 0 && !v))) return fail(P2V_ERR_INVALID_ARG, "null buffer");
+    if (in_stride < 1) return fail(P2V_ERR_INVALID_ARG, "in_stride must be positive");
+    return P2V_OK;
+}
+int p2v_from_newick_batch(const char* newick, int64_t in_stride, const int64_t* lengths, int64_t B, int64_t k, void* v,
+                          int idx_bytes, int32_t* status, void* ws, size_t ws_bytes, p2v_stream_t stream) {
+    int rc = from_newick_check(newick, in_stride, v, idx_bytes, B, k);
+    if (rc) return rc;
+    if (B == 0) return P2V_OK;
+    if (k == 0) {                                 // "0;": the empty vector
+        if (status) return from_cuda(cudaMemsetAsync(status, 0, sizeof(int32_t) * B, (cudaStream_t)stream), "from_newick status");
+        return P2V_OK;
+    }
+    if (ws_bytes < from_newick_workspace_bytes(B, k, idx_bytes) || !ws)
+        return fail(P2V_ERR_WORKSPACE, "from_newick workspace too small");
+    return from_cuda(launch_from_newick(newick, in_stride, lengths, B, k, v, idx_bytes, status, ws, ws_bytes,
+                                        (cudaStream_t)stream), "from_newick launch");
+}
+int p2v_from_newick_host(const char* newick, int64_t in_stride, int64_t B, int64_t k, void* v, int idx_bytes,
+                         int32_t* status) {
+    int rc = from_newick_check(newick, in_stride, v, idx_bytes, B, k);
+    if (rc) return rc;
+    if (k == 0) { if (status && B > 0) memset(status, 0, sizeof(int32_t) * B); return P2V_OK; }
+    return host_chunked(
+        newick, (size_t)in_stride, v, (size_t)k * idx_bytes, status, B,
+        [&](int64_t nb) { return from_newick_workspace_bytes(nb, k, idx_bytes); },
+        [&](void* din, void* dout, int32_t* dst, int64_t nb, void* ws, size_t wsb, cudaStream_t st) {
+            return launch_from_newick((const char*)din, in_stride, nullptr, nb, k, dout, idx_bytes, dst, ws, wsb, st);
+        });
 }
 
 int p2v_to_pairs_host(const void* v, int idx_bytes, int64_t B, int64_t k, void* out, int32_t* status) {

@@ -50,11 +50,16 @@ cudaError_t launch_node_depths(const void* v_or_matrix, int idx_bytes, const dou
                                double* out, int32_t* status, void* ws, size_t ws_bytes, cudaStream_t stream);
 cudaError_t launch_fill_f64(double* out, int64_t count, double value, cudaStream_t stream);
 
-// to_newick (vectors, k <= 1023): strings at out + b * out_stride, NUL-terminated; lengths without the NUL
+// to_newick (vectors): strings at out + b * out_stride, NUL-terminated; lengths without the NUL
 size_t newick_max_bytes(int64_t k);
 size_t newick_workspace_bytes(int64_t B, int64_t k);
 cudaError_t launch_to_newick(const void* v, int idx_bytes, int64_t B, int64_t k, char* out, int64_t out_stride,
                              int64_t* lengths, int32_t* status, void* ws, size_t ws_bytes, cudaStream_t stream);
+// from_newick (vectors, Newick with parent labels): strings at in + b * in_stride, lengths[b] bytes each
+// (lengths == nullptr: NUL-terminated inside the row)
+size_t from_newick_workspace_bytes(int64_t B, int64_t k, int idx_bytes);
+cudaError_t launch_from_newick(const char* in, int64_t in_stride, const int64_t* lengths, int64_t B, int64_t k, void* v,
+                               int idx_bytes, int32_t* status, void* ws, size_t ws_bytes, cudaStream_t stream);
 // int64 -> int32 index vectors (values that do not fit become -1 and fail check_v downstream)
 cudaError_t launch_narrow_v(const long long* v, int64_t count, int* out, cudaStream_t stream);
 

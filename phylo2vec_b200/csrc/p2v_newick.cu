@@ -19,9 +19,11 @@
 //      its byte offset;
 //   4. leaves write [","] "(((" label, internal nodes write ")" label, the string is assembled in
 //      shared memory and copied out with coalesced stores.
-// Sizes: k <= 1023 (one mask word per lane in the decoder, uint16 tables).  Larger trees and the
-// matrix form (branch lengths need the reference's shortest-round-trip float formatting) are
-// not built yet: P2V_ERR_UNSUPPORTED.
+// Sizes: while the tables fit in shared memory (k <= 3200 or so) they are uint16 and the string is
+// assembled in shared memory; larger trees run the same code with uint32 tables in a per-CTA slice
+// of the workspace (L2 resident), 1024 threads, and write their tokens straight into the output
+// row.  The matrix form (branch lengths need the reference's shortest-round-trip float
+// formatting) is not built: P2V_ERR_UNSUPPORTED.
 #include <cstdlib>
 
 #include "p2v_common.cuh"
@@ -29,18 +31,20 @@
 
 namespace p2v {
 
-constexpr int NW_THREADS = 128;
-constexpr int NW_K_MAX = 1023;
-constexpr unsigned NW_NONE = 0xFFFFu;
+constexpr int NW_THREADS_MAX = 1024;
+constexpr size_t NW_SMEM_MAX = 227 * 1024;
 
 __host__ __device__ inline int dec_digits(unsigned x) {
-    return 1 + (x >= 10u) + (x >= 100u) + (x >= 1000u) + (x >= 10000u);
+    return 1 + (x >= 10u) + (x >= 100u) + (x >= 1000u) + (x >= 10000u) + (x >= 100000u) + (x >= 1000000u) +
+           (x >= 10000000u);
 }
 
 // exact length of the string of a tree with k + 1 leaves (without the terminating NUL)
 __host__ __device__ inline size_t newick_bytes(int64_t k) {
     size_t total = 3 * (size_t)k + 1;                  // "(", ",", ")" per internal node and the ";"
-    for (int64_t x = 0; x <= 2 * k; ++x) total += (size_t)dec_digits((unsigned)x);
+    const int64_t top = 2 * k;                         // labels 0 .. 2k: one digit each, plus one per power of ten passed
+    total += (size_t)(top + 1);
+    for (int64_t p = 10; p <= top; p *= 10) total += (size_t)(top - p + 1);
     return total;
 }
 
@@ -49,51 +53,63 @@ struct NewickLayout {
     size_t strcap;
 };
 __host__ __device__ inline size_t nw_al16(size_t x) { return (x + 15) & ~(size_t)15; }
-__host__ __device__ inline NewickLayout newick_layout(int k) {      // all byte counts fit uint16: <= 11.3 KB
+// es = bytes per table entry: 2 in shared memory (ancestry copy and string staging included),
+// 4 in the workspace (the ancestry is read in place and the string is written in place)
+__host__ __device__ inline NewickLayout newick_layout(int64_t k, size_t es) {
     NewickLayout L;
     const size_t n = (size_t)k + 1, N = 2 * (size_t)k + 1;
+    const bool staged = es == 2;
     size_t o = 0;
-    L.anc = o; o = nw_al16(o + 4 * 3 * (size_t)k);
-    L.dl = o; o = nw_al16(o + 2 * 2 * N);           // first-child jump pointers, two buffers
-    L.dr = o; o = nw_al16(o + 2 * 2 * N);           // second-child jump pointers
-    L.al = o; o = nw_al16(o + 2 * 2 * N);           // "(" opened along the first-child chain
-    L.ar = o; o = nw_al16(o + 2 * 2 * N);           // bytes closed along the second-child chain
-    L.nxt = o; o = nw_al16(o + 2 * 2 * n);          // leaf list, two buffers
-    L.wsum = o; o = nw_al16(o + 2 * 2 * n);         // bytes from this leaf to the end of the string
-    L.wleaf = o; o = nw_al16(o + 2 * n);            // bytes emitted around one leaf
-    L.open = o; o = nw_al16(o + 2 * n);
-    L.closel = o; o = nw_al16(o + 2 * n);
-    L.start = o; o = nw_al16(o + 2 * n);
-    L.strcap = nw_al16(newick_bytes(k) + 2);
+    L.anc = o; o = nw_al16(o + (staged ? 4 * 3 * (size_t)k : 0));
+    L.dl = o; o = nw_al16(o + es * 2 * N);           // first-child jump pointers, two buffers
+    L.dr = o; o = nw_al16(o + es * 2 * N);           // second-child jump pointers
+    L.al = o; o = nw_al16(o + es * 2 * N);           // "(" opened along the first-child chain
+    L.ar = o; o = nw_al16(o + es * 2 * N);           // bytes closed along the second-child chain
+    L.nxt = o; o = nw_al16(o + es * 2 * n);          // leaf list, two buffers
+    L.wsum = o; o = nw_al16(o + es * 2 * n);         // bytes from this leaf to the end of the string
+    L.wleaf = o; o = nw_al16(o + es * n);            // bytes emitted around one leaf
+    L.open = o; o = nw_al16(o + es * n);
+    L.closel = o; o = nw_al16(o + es * n);
+    L.start = o; o = nw_al16(o + es * n);
+    L.strcap = staged ? nw_al16(newick_bytes(k) + 2) : 0;
     L.str = o; o = nw_al16(o + L.strcap);
     L.total = o;
     return L;
+}
+// shared-memory variant: the tables fit and every byte offset fits uint16
+static bool newick_fits_smem(int64_t k) {
+    return k <= 4000 && newick_bytes(k) + 2 < 65535 && newick_layout(k, 2).total <= NW_SMEM_MAX;
 }
 
 __device__ __forceinline__ void put_dec(char* p, unsigned x, int digits) {
     for (int i = digits - 1; i >= 0; --i) { p[i] = (char)('0' + x % 10u); x /= 10u; }
 }
 
-__global__ void __launch_bounds__(NW_THREADS)
-newick_small_kernel(const int* __restrict__ anc_all, int64_t B, int k, char* __restrict__ out, int64_t out_stride,
-                    int64_t* __restrict__ lengths, const int32_t* __restrict__ status) {
-    extern __shared__ __align__(16) unsigned char dyn[];
-    const NewickLayout L = newick_layout(k);
+// T = T: tables, ancestry copy and string staging in dynamic shared memory;
+// T = uint32_t: tables in this CTA's slice of the workspace, ancestry and string in place.
+template <typename T>
+__global__ void __launch_bounds__(NW_THREADS_MAX)
+newick_kernel(const int* __restrict__ anc_all, int64_t B, int k, char* __restrict__ out, int64_t out_stride,
+              int64_t* __restrict__ lengths, const int32_t* __restrict__ status, unsigned char* __restrict__ tables,
+              size_t tables_stride) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    constexpr bool STAGED = sizeof(T) == 2;
+    constexpr unsigned NW_NONE = (unsigned)(T)~(T)0;
+    unsigned char* dyn = STAGED ? dyn_smem : tables + (size_t)blockIdx.x * tables_stride;
+    const NewickLayout L = newick_layout(k, sizeof(T));
     const int n = k + 1, N = 2 * k + 1, root = 2 * k;
     const int tid = threadIdx.x;
-    const int NT = blockDim.x;                    // 32 / 64 / 128 threads: small trees get small CTAs
-    int* anc = reinterpret_cast<int*>(dyn + L.anc);
-    uint16_t* dl = reinterpret_cast<uint16_t*>(dyn + L.dl);
-    uint16_t* dr = reinterpret_cast<uint16_t*>(dyn + L.dr);
-    uint16_t* al = reinterpret_cast<uint16_t*>(dyn + L.al);
-    uint16_t* ar = reinterpret_cast<uint16_t*>(dyn + L.ar);
-    uint16_t* nxt = reinterpret_cast<uint16_t*>(dyn + L.nxt);
-    uint16_t* wsum = reinterpret_cast<uint16_t*>(dyn + L.wsum);
-    uint16_t* wleaf = reinterpret_cast<uint16_t*>(dyn + L.wleaf);
-    uint16_t* nopen = reinterpret_cast<uint16_t*>(dyn + L.open);
-    uint16_t* closel = reinterpret_cast<uint16_t*>(dyn + L.closel);
-    uint16_t* start = reinterpret_cast<uint16_t*>(dyn + L.start);
-    char* str = reinterpret_cast<char*>(dyn + L.str);
+    const int NT = blockDim.x;
+    T* dl = reinterpret_cast<T*>(dyn + L.dl);
+    T* dr = reinterpret_cast<T*>(dyn + L.dr);
+    T* al = reinterpret_cast<T*>(dyn + L.al);
+    T* ar = reinterpret_cast<T*>(dyn + L.ar);
+    T* nxt = reinterpret_cast<T*>(dyn + L.nxt);
+    T* wsum = reinterpret_cast<T*>(dyn + L.wsum);
+    T* wleaf = reinterpret_cast<T*>(dyn + L.wleaf);
+    T* nopen = reinterpret_cast<T*>(dyn + L.open);
+    T* closel = reinterpret_cast<T*>(dyn + L.closel);
+    T* start = reinterpret_cast<T*>(dyn + L.start);
 
     for (int64_t tree = blockIdx.x; tree < B; tree += gridDim.x) {
         __syncthreads();                          // the previous tree's readers are done
@@ -102,45 +118,49 @@ newick_small_kernel(const int* __restrict__ anc_all, int64_t B, int k, char* __r
             continue;
         }
         // ---- 1. the ancestry rows of this tree ----------------------------------------------
-        {
-            const int* src = anc_all + (size_t)tree * 3 * k;
-            for (int i = tid; i < 3 * k; i += NT) anc[i] = src[i];
+        const int* anc = anc_all + (size_t)tree * 3 * k;
+        char* str = out + tree * out_stride;
+        if (STAGED) {
+            int* sanc = reinterpret_cast<int*>(dyn + L.anc);
+            for (int i = tid; i < 3 * k; i += NT) sanc[i] = anc[i];
+            anc = sanc;
+            str = reinterpret_cast<char*>(dyn + L.str);
+            __syncthreads();
         }
-        __syncthreads();
         // ---- 2. child pointers and chain weights ------------------------------------------
         for (int c = tid; c <= k; c += NT) {
-            dl[c] = (uint16_t)c; dr[c] = (uint16_t)c; al[c] = 0; ar[c] = 0;
+            dl[c] = (T)c; dr[c] = (T)c; al[c] = 0; ar[c] = 0;
             nopen[c] = 0; closel[c] = 0;
         }
         for (int r = tid; r < k; r += NT) {
             const int u = k + 1 + r;
-            dl[u] = (uint16_t)anc[3 * r]; dr[u] = (uint16_t)anc[3 * r + 1];
-            al[u] = 1; ar[u] = (uint16_t)(1 + dec_digits((unsigned)u));      // "(" ; ")" + label
+            dl[u] = (T)anc[3 * r]; dr[u] = (T)anc[3 * r + 1];
+            al[u] = 1; ar[u] = (T)(1 + dec_digits((unsigned)u));      // "(" ; ")" + label
         }
         __syncthreads();
         int cur = 0;
         for (;;) {      // jump down both chains; leaves are fixed points with weight 0
-            const uint16_t* l_in = dl + cur * N; uint16_t* l_out = dl + (cur ^ 1) * N;
-            const uint16_t* r_in = dr + cur * N; uint16_t* r_out = dr + (cur ^ 1) * N;
-            const uint16_t* a_in = al + cur * N; uint16_t* a_out = al + (cur ^ 1) * N;
-            const uint16_t* b_in = ar + cur * N; uint16_t* b_out = ar + (cur ^ 1) * N;
+            const T* l_in = dl + cur * N; T* l_out = dl + (cur ^ 1) * N;
+            const T* r_in = dr + cur * N; T* r_out = dr + (cur ^ 1) * N;
+            const T* a_in = al + cur * N; T* a_out = al + (cur ^ 1) * N;
+            const T* b_in = ar + cur * N; T* b_out = ar + (cur ^ 1) * N;
             int live = 0;
             for (int x = tid; x < N; x += NT) {
                 const unsigned l = l_in[x], r = r_in[x];
                 const unsigned nl = l_in[l], nr = r_in[r];
-                a_out[x] = (uint16_t)(a_in[x] + a_in[l]);
-                b_out[x] = (uint16_t)(b_in[x] + b_in[r]);
-                l_out[x] = (uint16_t)nl; r_out[x] = (uint16_t)nr;
+                a_out[x] = (T)(a_in[x] + a_in[l]);
+                b_out[x] = (T)(b_in[x] + b_in[r]);
+                l_out[x] = (T)nl; r_out[x] = (T)nr;
                 live |= ((int)nl > k) | ((int)nr > k);
             }
             cur ^= 1;
             if (!__syncthreads_or(live)) break;
         }
         // NOTE: a node whose chain has already reached a leaf keeps adding the leaf's weight 0.
-        const uint16_t* lres = dl + cur * N;      // leftmost leaf of every node
-        const uint16_t* rres = dr + cur * N;      // rightmost leaf
-        const uint16_t* ares = al + cur * N;      // "(" from this node down its first-child chain
-        const uint16_t* bres = ar + cur * N;      // bytes of ")label" from this node down its second-child chain
+        const T* lres = dl + cur * N;      // leftmost leaf of every node
+        const T* rres = dr + cur * N;      // rightmost leaf
+        const T* ares = al + cur * N;      // "(" from this node down its first-child chain
+        const T* bres = ar + cur * N;      // bytes of ")label" from this node down its second-child chain
         // ---- 3. per-leaf runs, the leaf list and its weighted ranking ---------------------------
         // the top of a first-child chain is a second child (or the root): it opens the whole run of
         // "(" before its leftmost leaf; the top of a second-child chain is a first child (or the
@@ -152,37 +172,37 @@ newick_small_kernel(const int* __restrict__ anc_all, int64_t B, int k, char* __r
             nxt[rres[c1]] = lres[c2];
         }
         if (tid == 0) {
-            nxt[rres[root]] = (uint16_t)NW_NONE;
+            nxt[rres[root]] = (T)NW_NONE;
             nopen[lres[root]] = ares[root]; closel[rres[root]] = bres[root];
         }
         __syncthreads();
         const int first_leaf = lres[root];
         for (int c = tid; c <= k; c += NT) {
             const uint32_t w = (c != first_leaf ? 1u : 0u) + nopen[c] + (uint32_t)dec_digits((unsigned)c) + closel[c];
-            wleaf[c] = (uint16_t)w; wsum[c] = (uint16_t)w;
+            wleaf[c] = (T)w; wsum[c] = (T)w;
         }
         __syncthreads();
         int lc = 0;
         for (;;) {
-            const uint16_t* n_in = nxt + lc * n; uint16_t* n_out = nxt + (lc ^ 1) * n;
-            const uint16_t* s_in = wsum + lc * n; uint16_t* s_out = wsum + (lc ^ 1) * n;
+            const T* n_in = nxt + lc * n; T* n_out = nxt + (lc ^ 1) * n;
+            const T* s_in = wsum + lc * n; T* s_out = wsum + (lc ^ 1) * n;
             int live = 0;
             for (int x = tid; x < n; x += NT) {
                 const unsigned a = n_in[x];
                 uint32_t s = s_in[x];
                 unsigned na = NW_NONE;
                 if (a != NW_NONE) { s += s_in[a]; na = n_in[a]; live |= (na != NW_NONE); }
-                n_out[x] = (uint16_t)na; s_out[x] = (uint16_t)s;
+                n_out[x] = (T)na; s_out[x] = (T)s;
             }
             lc ^= 1;
             if (!__syncthreads_or(live)) break;
         }
-        const uint16_t* sres = wsum + lc * n;     // bytes from the leaf's run to the end (";" excluded)
+        const T* sres = wsum + lc * n;     // bytes from the leaf's run to the end (";" excluded)
         const uint32_t total = sres[first_leaf];
         // ---- 4. tokens ---------------------------------------------------------------------------
         for (int c = tid; c <= k; c += NT) {
             uint32_t o = total - sres[c];
-            start[c] = (uint16_t)o;
+            start[c] = (T)o;
             if (c != first_leaf) str[o++] = ',';
             const uint32_t no = nopen[c];
             for (uint32_t i = 0; i < no; ++i) str[o + i] = '(';
@@ -201,15 +221,17 @@ newick_small_kernel(const int* __restrict__ anc_all, int64_t B, int k, char* __r
         if (tid == 0) { str[total] = ';'; str[total + 1] = 0; }
         __syncthreads();
         // ---- copy out (the row is out_stride bytes; bytes past the NUL are left untouched) --------
-        char* o = out + tree * out_stride;
-        const uint32_t nbytes = total + 2;
-        if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-            const uint32_t nvec = nbytes >> 4;
-            for (uint32_t i = tid; i < nvec; i += NT)
-                reinterpret_cast<uint4*>(o)[i] = reinterpret_cast<const uint4*>(str)[i];
-            for (uint32_t i = (nvec << 4) + tid; i < nbytes; i += NT) o[i] = str[i];
-        } else {
-            for (uint32_t i = tid; i < nbytes; i += NT) o[i] = str[i];
+        if (STAGED) {
+            char* o = out + tree * out_stride;
+            const uint32_t nbytes = total + 2;
+            if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                const uint32_t nvec = nbytes >> 4;
+                for (uint32_t i = tid; i < nvec; i += NT)
+                    reinterpret_cast<uint4*>(o)[i] = reinterpret_cast<const uint4*>(str)[i];
+                for (uint32_t i = (nvec << 4) + tid; i < nbytes; i += NT) o[i] = str[i];
+            } else {
+                for (uint32_t i = tid; i < nbytes; i += NT) o[i] = str[i];
+            }
         }
         if (tid == 0 && lengths) lengths[tree] = (int64_t)total + 1;
     }
@@ -217,14 +239,25 @@ newick_small_kernel(const int* __restrict__ anc_all, int64_t B, int k, char* __r
 
 size_t newick_max_bytes(int64_t k) { return k < 0 ? 0 : newick_bytes(k) + 1; }
 
-// workspace: [ status scratch (B int32) | int32 v (B*k, only for int64 input) | int32 ancestry (B*k*3) ]
-struct NewickWs { size_t status, v32, anc, total; };
+// CTAs of the workspace variant (each owns a slice of tables)
+static int64_t newick_teams(int64_t B, int64_t k) {
+    const int64_t cap = (int64_t)sm_count() * (k <= 16384 ? 2 : 1);
+    return B < cap ? B : cap;
+}
+
+// workspace: [ status scratch (B int32) | int32 v (B*k, only for int64 input) | int32 ancestry (B*k*3)
+//              | decode workspace | per-CTA tables (large trees only) ]
+struct NewickWs { size_t status, v32, anc, dec, dec_bytes, tables, tables_stride, total; };
 static NewickWs newick_ws(int64_t B, int64_t k) {
     NewickWs w;
     size_t o = 0;
     w.status = o; o = nw_al16(o + 4 * (size_t)B);
     w.v32 = o; o = nw_al16(o + 4 * (size_t)B * (size_t)k);
     w.anc = o; o = nw_al16(o + 12 * (size_t)B * (size_t)k);
+    w.dec_bytes = decode_workspace_bytes(B, k);
+    w.dec = o; o = nw_al16(o + w.dec_bytes);
+    w.tables_stride = newick_fits_smem(k) ? 0 : nw_al16(newick_layout(k, 4).total);
+    w.tables = o; o = nw_al16(o + w.tables_stride * (size_t)newick_teams(B, k));
     w.total = o;
     return w;
 }
@@ -233,7 +266,7 @@ size_t newick_workspace_bytes(int64_t B, int64_t k) { return (B <= 0 || k <= 0) 
 cudaError_t launch_to_newick(const void* v, int idx_bytes, int64_t B, int64_t k, char* out, int64_t out_stride,
                              int64_t* lengths, int32_t* status, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (B <= 0) return cudaSuccess;
-    if (k < 1 || k > NW_K_MAX) return cudaErrorNotSupported;
+    if (k < 1 || k > LARGE_K_MAX) return cudaErrorNotSupported;
     if (out_stride < (int64_t)newick_max_bytes(k)) return cudaErrorInvalidValue;
     const NewickWs W = newick_ws(B, k);
     if (!ws || ws_bytes < W.total) return cudaErrorInvalidValue;
@@ -249,22 +282,281 @@ cudaError_t launch_to_newick(const void* v, int idx_bytes, int64_t B, int64_t k,
     } else if (idx_bytes != 4) {
         return cudaErrorInvalidValue;
     }
-    e = launch_decode(MODE_ANCESTRY, vin, 4, B, k, anc, st, nullptr, 0, stream, 0);     // k <= 1023: no workspace
+    e = launch_decode(MODE_ANCESTRY, vin, 4, B, k, anc, st, W.dec_bytes ? wsb + W.dec : nullptr, W.dec_bytes, stream, 0);
     if (e != cudaSuccess) return e;
-    const size_t smem = newick_layout((int)k).total;
-    e = cudaFuncSetAttribute(newick_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const int threads = NW_THREADS;      // measured at n = 100: 32-thread CTAs are no faster (32 CTAs/SM cap)
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, newick_small_kernel, threads, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    const int64_t cap = (int64_t)sm_count() * per_sm;
-    newick_small_kernel<<<(int)(B < cap ? B : cap), threads, smem, stream>>>(anc, B, (int)k, out, out_stride, lengths, st);
+    if (newick_fits_smem(k)) {
+        const size_t smem = newick_layout(k, 2).total;
+        e = cudaFuncSetAttribute(newick_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        // measured at n = 100: 32-thread CTAs are no faster than 128 (32 CTAs/SM cap); big trees
+        // leave room for one or two CTAs per SM only and get more threads each
+        const int threads = k <= 1023 ? 128 : (k <= 2047 ? 256 : 512);
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, newick_kernel<uint16_t>, threads, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        const int64_t cap = (int64_t)sm_count() * per_sm;
+        newick_kernel<uint16_t><<<(int)(B < cap ? B : cap), threads, smem, stream>>>(anc, B, (int)k, out, out_stride, lengths,
+                                                                                   st, nullptr, 0);
+    } else {
+        newick_kernel<uint32_t><<<(int)newick_teams(B, k), NW_THREADS_MAX, 0, stream>>>(
+            anc, B, (int)k, out, out_stride, lengths, st, wsb + W.tables, W.tables_stride);
+    }
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (status) e = cudaMemcpyAsync(status, st, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, stream);
+    return e;
+}
+
+
+// ======================================================================================
+// from_newick (vectors; Newick with parent labels)
+//
+// Replaces (reference):
+//   newick::parse                                   phylo2vec/src/newick/mod.rs:73-127
+//   vector::convert::from_newick (has_parents arm)  phylo2vec/src/vector/convert.rs:268-278
+//   PyO3 to_vector                                  py-phylo2vec/src/lib.rs:98-101
+//
+// The reference walks the string with a stack: a number pushes a node, ")" pops two children and
+// pushes the label that follows.  The nodes therefore appear in post-order, and with S(i) = stack
+// height after node i (leaf +1, internal -1): the second child of internal node i is node i-1,
+// the first child is the latest node j < i with S(j) = S(i).  One CTA per tree:
+//   1. the string is staged in shared memory; every thread classifies a contiguous piece
+//      (leaf token, ")" with its label, punctuation) and a block scan numbers the nodes and
+//      gives S; the labels are parsed where the tokens start;
+//   2. one warp sweeps the nodes 32 at a time with a table "latest node of height h"
+//      (same-batch matches through MATCH.ANY) and writes row r = (c1, p), (c2, p) of the
+//      cherry list in string order -- newick::parse's output as an edge list;
+//   3. the batched encode kernel (from_edges: order_cherries + build_cherries + build_vector)
+//      turns the rows into v.
+// Strings without parent labels ("((0,1),2);", order_cherries_no_parents) are not built: such a
+// tree gets status P2V_ERR_UNSUPPORTED; anything that is not a well-formed binary Newick of k + 1
+// leaves gets P2V_TREE_MALFORMED.
+// ======================================================================================
+
+constexpr int NP_UNSUPPORTED = -3;      // P2V_ERR_UNSUPPORTED as a per-tree status
+constexpr int NP_MALFORMED = -2;        // P2V_TREE_MALFORMED
+constexpr uint32_t NP_INTERNAL = 0x80000000u;
+
+struct ParseLayout { size_t str, lab, sh, last, total; };
+__host__ __device__ inline ParseLayout parse_layout(int64_t k, bool staged) {
+    ParseLayout L;
+    const size_t N = 2 * (size_t)k + 1;
+    size_t o = 0;
+    L.str = o; o = nw_al16(o + (staged ? newick_bytes(k) + 16 : 0));
+    L.lab = o; o = nw_al16(o + 4 * N);
+    L.sh = o; o = nw_al16(o + 4 * N);
+    L.last = o; o = nw_al16(o + 4 * ((size_t)k + 3));
+    L.total = o;
+    return L;
+}
+static bool parse_fits_smem(int64_t k) { return k <= 8192 && parse_layout(k, true).total <= 200 * 1024; }
+
+__device__ __forceinline__ bool np_digit(char c) { return c >= '0' && c <= '9'; }
+
+template <typename OutT, bool STAGED>
+__global__ void __launch_bounds__(NW_THREADS_MAX)
+newick_parse_kernel(const char* __restrict__ in, int64_t in_stride, const int64_t* __restrict__ lengths, int64_t B, int k,
+                    OutT* __restrict__ edges, int32_t* __restrict__ pstatus, unsigned char* __restrict__ tables,
+                    size_t tables_stride, int maxlen) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ int s_cnt[32], s_del[32];
+    __shared__ int s_len, s_bad;
+    unsigned char* dyn = STAGED ? dyn_smem : tables + (size_t)blockIdx.x * tables_stride;
+    const ParseLayout L = parse_layout(k, STAGED);
+    const int N = 2 * k + 1;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
+    uint32_t* lab = reinterpret_cast<uint32_t*>(dyn + L.lab);      // label | NP_INTERNAL, by node (post-order)
+    int* sh = reinterpret_cast<int*>(dyn + L.sh);                  // stack height after the node
+    int* last = reinterpret_cast<int*>(dyn + L.last);              // latest node of height h
+
+    for (int64_t tree = blockIdx.x; tree < B; tree += gridDim.x) {
+        const char* src = in + tree * in_stride;
+        OutT* erow = edges + (size_t)tree * 4 * (size_t)k;
+        __syncthreads();                          // the previous tree is done with the tables
+        if (tid == 0) { s_bad = 0; s_len = maxlen + 1; }
+        __syncthreads();
+        int len;
+        if (lengths) {
+            const int64_t l64 = lengths[tree];
+            len = (l64 < 1 || l64 > maxlen) ? 0 : (int)l64;
+        } else {                                  // NUL-terminated inside the row
+            const int lim = (int)(in_stride < (int64_t)maxlen + 1 ? in_stride : (int64_t)maxlen + 1);
+            for (int i = tid; i < lim; i += NT) if (src[i] == 0) { atomicMin(&s_len, i); break; }
+            __syncthreads();
+            len = (s_len < 1 || s_len > maxlen) ? 0 : s_len;
+        }
+        const char* s = src;
+        if (STAGED) {
+            char* sstr = reinterpret_cast<char*>(dyn + L.str);
+            for (int i = tid; i < len; i += NT) sstr[i] = src[i];
+            s = sstr;
+            __syncthreads();
+        }
+        // ---- 1. classify, count, scan ----------------------------------------------------------
+        const int CH = (len + NT - 1) / NT;
+        const int i0 = min(len, tid * CH), i1 = min(len, i0 + CH);
+        int cnt = 0, del = 0, bad = (len == 0 || s[len - 1] != ';') ? NP_MALFORMED : 0;    // node_substr needs the ";"
+        for (int i = i0; i < i1; ++i) {
+            const char c = s[i];
+            const char prev = i > 0 ? s[i - 1] : '\0';
+            if (c == ')') { ++cnt; --del; }
+            else if (np_digit(c)) { if (prev == '(' || prev == ',') { ++cnt; ++del; } else if (i == 0) bad = NP_MALFORMED; }
+            else if (c == '(' || c == ',') {}
+            else if (c == ';') { if (i != len - 1) bad = NP_MALFORMED; }
+            else bad = NP_MALFORMED;
+        }
+        int icnt = cnt, idel = del;               // inclusive scans over the threads
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int a = __shfl_up_sync(FULL, icnt, d), b = __shfl_up_sync(FULL, idel, d);
+            if (lane >= d) { icnt += a; idel += b; }
+        }
+        if (lane == 31) { s_cnt[warp] = icnt; s_del[warp] = idel; }
+        __syncthreads();
+        if (warp == 0) {
+            int a = lane < nwarp ? s_cnt[lane] : 0, b = lane < nwarp ? s_del[lane] : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int x = __shfl_up_sync(FULL, a, d), y = __shfl_up_sync(FULL, b, d);
+                if (lane >= d) { a += x; b += y; }
+            }
+            s_cnt[lane] = a; s_del[lane] = b;
+        }
+        __syncthreads();
+        const int tot_nodes = s_cnt[nwarp - 1], tot_del = s_del[nwarp - 1];
+        if (tot_nodes != N || tot_del != 1) bad = bad ? bad : NP_MALFORMED;
+        int idx = icnt - cnt + (warp ? s_cnt[warp - 1] : 0);
+        int S = idel - del + (warp ? s_del[warp - 1] : 0);
+        if (!bad) {
+            for (int i = i0; i < i1; ++i) {
+                const char c = s[i];
+                int from;
+                uint32_t kind;
+                if (c == ')') { from = i + 1; kind = NP_INTERNAL; --S; }
+                else if (np_digit(c) && (s[i - 1] == '(' || s[i - 1] == ',')) { from = i; kind = 0; ++S; }
+                else continue;
+                uint32_t val = 0;
+                int nd = 0;
+                while (from + nd < len && nd < 9 && np_digit(s[from + nd])) { val = val * 10u + (uint32_t)(s[from + nd] - '0'); ++nd; }
+                if (nd == 0) bad = NP_UNSUPPORTED;                 // ")" without a parent label
+                else if (nd > 8 || val > 2u * (uint32_t)k) bad = NP_MALFORMED;
+                if (S < 1) bad = bad ? bad : NP_MALFORMED;
+                lab[idx] = val | kind; sh[idx] = S;
+                ++idx;
+            }
+        }
+        if (bad) atomicMin(&s_bad, bad);          // UNSUPPORTED (-3) wins over MALFORMED (-2)
+        __syncthreads();
+        if (s_bad) {                              // uniform
+            if (tid == 0) {
+                pstatus[tree] = s_bad;
+                erow[0] = (OutT)-1; erow[1] = (OutT)-1;           // the encoder rejects the tree as well
+            }
+            continue;
+        }
+        if (tid == 0) pstatus[tree] = 0;
+        // ---- 2. children of every internal node: one warp, 32 nodes at a time ------------------
+        if (warp == 0) {
+            for (int base = 0; base < N; base += 32) {
+                const int node = base + lane;
+                const bool act = node < N;
+                const uint32_t lb = act ? lab[node] : 0u;
+                const int Sv = act ? sh[node] : -1 - lane;
+                const uint32_t peers = __match_any_sync(FULL, Sv);
+                if (act && (lb & NP_INTERNAL)) {
+                    const uint32_t lower = peers & lanes_lt(lane);
+                    const int j = lower ? base + 31 - __clz(lower) : last[Sv];
+                    const uint32_t c1 = lab[j] & ~NP_INTERNAL, c2 = lab[node - 1] & ~NP_INTERNAL, pl = lb & ~NP_INTERNAL;
+                    const int r = ((node + 1 - Sv) >> 1) - 1;          // internal nodes before this one
+                    OutT* o = erow + 4 * (size_t)r;
+                    o[0] = (OutT)c1; o[1] = (OutT)pl; o[2] = (OutT)c2; o[3] = (OutT)pl;
+                }
+                __syncwarp();
+                if (act && (peers & lanes_gt(lane)) == 0) last[Sv] = node;
+                __syncwarp();
+            }
+        }
+    }
+}
+
+__global__ void merge_status_kernel(const int32_t* __restrict__ pst, int32_t* __restrict__ status, int64_t B) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < B; t += (int64_t)gridDim.x * blockDim.x)
+        if (pst[t] != 0) status[t] = pst[t];
+}
+
+// workspace: [ parse status (B int32) | edges (B,2k,2) of the index type | encode workspace | per-CTA tables ]
+struct FromNewickWs { size_t pst, edges, enc, enc_bytes, tables, tables_stride, total; };
+static int64_t parse_teams(int64_t B, int64_t k) {
+    const int64_t cap = (int64_t)sm_count() * 2;
+    return B < cap ? B : cap;
+}
+static FromNewickWs from_newick_ws(int64_t B, int64_t k, int idx_bytes) {
+    FromNewickWs w;
+    size_t o = 0;
+    w.pst = o; o = nw_al16(o + 4 * (size_t)B);
+    w.edges = o; o = nw_al16(o + (size_t)idx_bytes * 4 * (size_t)B * (size_t)k);
+    w.enc_bytes = encode_workspace_bytes(B, k);
+    w.enc = o; o = nw_al16(o + w.enc_bytes);
+    w.tables_stride = parse_fits_smem(k) ? 0 : nw_al16(parse_layout(k, false).total);
+    w.tables = o; o = nw_al16(o + w.tables_stride * (size_t)parse_teams(B, k));
+    w.total = o;
+    return w;
+}
+size_t from_newick_workspace_bytes(int64_t B, int64_t k, int idx_bytes) {
+    return (B <= 0 || k <= 0) ? 0 : from_newick_ws(B, k, idx_bytes).total;
+}
+
+template <typename OutT>
+static cudaError_t launch_parse_t(const char* in, int64_t in_stride, const int64_t* lengths, int64_t B, int64_t k,
+                                  OutT* edges, int32_t* pst, unsigned char* tables, size_t tables_stride, cudaStream_t stream) {
+    const int maxlen = (int)newick_bytes(k);
+    if (parse_fits_smem(k)) {
+        const size_t smem = parse_layout(k, true).total;
+        auto kern = newick_parse_kernel<OutT, true>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const int threads = k <= 255 ? 64 : (k <= 2047 ? 128 : 256);
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        const int64_t cap = (int64_t)sm_count() * per_sm;
+        kern<<<(int)(B < cap ? B : cap), threads, smem, stream>>>(in, in_stride, lengths, B, (int)k, edges, pst, nullptr, 0, maxlen);
+    } else {
+        newick_parse_kernel<OutT, false><<<(int)parse_teams(B, k), NW_THREADS_MAX, 0, stream>>>(
+            in, in_stride, lengths, B, (int)k, edges, pst, tables, tables_stride, maxlen);
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_from_newick(const char* in, int64_t in_stride, const int64_t* lengths, int64_t B, int64_t k, void* v,
+                               int idx_bytes, int32_t* status, void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    if (k < 1 || k > LARGE_K_MAX) return cudaErrorNotSupported;
+    if (idx_bytes != 4 && idx_bytes != 8) return cudaErrorInvalidValue;
+    const FromNewickWs W = from_newick_ws(B, k, idx_bytes);
+    if (!ws || ws_bytes < W.total) return cudaErrorInvalidValue;
+    unsigned char* wsb = static_cast<unsigned char*>(ws);
+    int32_t* pst = reinterpret_cast<int32_t*>(wsb + W.pst);
+    cudaError_t e;
+    if (idx_bytes == 8)
+        e = launch_parse_t<long long>(in, in_stride, lengths, B, k, reinterpret_cast<long long*>(wsb + W.edges), pst,
+                                      wsb + W.tables, W.tables_stride, stream);
+    else
+        e = launch_parse_t<int>(in, in_stride, lengths, B, k, reinterpret_cast<int*>(wsb + W.edges), pst, wsb + W.tables,
+                                W.tables_stride, stream);
+    if (e != cudaSuccess) return e;
+    e = launch_encode(FROM_EDGES, wsb + W.edges, idx_bytes, B, k, v, status, W.enc_bytes ? wsb + W.enc : nullptr,
+                      W.enc_bytes, stream);
+    if (e != cudaSuccess) return e;
+    if (status) {
+        merge_status_kernel<<<(int)((B + 255) / 256 < 2048 ? (B + 255) / 256 : 2048), 256, 0, stream>>>(pst, status, B);
+        count_launch();
+        e = cudaGetLastError();
+    }
     return e;
 }
 

@@ -1,6 +1,6 @@
-"""GPU parity tests for to_newick (run with -m gpu on a B200): byte-exact against the restatement
-of phylo2vec/src/vector/convert.rs:341-397, which tests/test_oracle_goldens.py pins to the
-reference's own Newick goldens."""
+"""GPU parity tests for to_newick / from_newick (run with -m gpu on a B200): byte-exact against the
+restatements of phylo2vec/src/vector/convert.rs:341-397 and newick/mod.rs:73-127 +
+convert.rs:268-278, which tests/test_oracle_goldens.py pins to the reference's own Newick goldens."""
 
 import ctypes
 
@@ -41,6 +41,8 @@ def test_goldens_single_tree(p2v, goldens):
 
 
 SIZES = [2, 3, 4, 5, 9, 10, 11, 33, 64, 65, 99, 100, 101, 129, 500, 999, 1000, 1001, 1023, 1024]
+# shared-memory tables with 256 / 512 threads, then uint32 tables in the workspace
+BIG_SIZES = [1025, 2000, 2049, 3000, 3300, 5000, 9999, 10001, 20000]
 
 
 @pytest.mark.parametrize("n_leaves", SIZES)
@@ -73,8 +75,6 @@ def test_invalid_and_limits(p2v):
     assert list(status.cpu().numpy()) == [0, 0, 0, 0, 8, 0] and int(lengths[4]) == 0
     with pytest.raises(AssertionError, match=r"v\[7\] = 15"):
         p2v.to_newick_batch(dev(V))
-    with pytest.raises(RuntimeError, match="1023"):                 # larger trees: not built yet
-        p2v.to_newick_batch(dev(sample_vectors(2, 1026, seed=1)))
     lib = _capi.load()
     assert lib.p2v_newick_max_bytes(3) == len("((0,1)5,(2,3)4)6;") + 1
 
@@ -98,3 +98,123 @@ def test_large_batch_and_host_entry(p2v):
     assert rc == 0 and not st.any()
     for b in (0, 1, B // 2, B - 1):
         assert out[b, :lengths[b]].tobytes().decode() == got[b]
+
+
+@pytest.mark.parametrize("n_leaves", BIG_SIZES)
+def test_big_trees_parity(p2v, n_leaves):
+    B = 12 if n_leaves < 10000 else 5
+    V = sample_vectors(B, n_leaves, seed=5 * n_leaves)
+    adv = list(adversarial_vectors(n_leaves).values())[:B - 1]
+    V[1:1 + len(adv)] = np.stack(adv)
+    for dtype in (torch.int64, torch.int32):
+        got = p2v.to_newick_batch(dev(V, dtype))
+        for b in range(B):
+            assert got[b] == O.to_newick(V[b]), (n_leaves, b)
+    # and back: string -> vector
+    back = p2v.from_newick_batch(got)
+    assert np.array_equal(back.cpu().numpy(), V)
+    buf, lengths = p2v.to_newick_batch(dev(V), raw=True)
+    back32 = p2v.from_newick_batch(buf, n_leaves=n_leaves, dtype=torch.int32)       # NUL-terminated rows
+    assert back32.dtype == torch.int32 and np.array_equal(back32.cpu().numpy(), V)
+
+
+def test_from_newick_goldens(p2v, goldens):
+    from phylo2vec_b200.base.newick import from_newick
+    for g in goldens["from_newick"]:
+        if ")," in g["newick"] or "))" in g["newick"] or ");" in g["newick"]:        # without parent labels: not built
+            with pytest.raises(NotImplementedError):
+                from_newick(g["newick"])
+            continue
+        got = from_newick(g["newick"])
+        assert got.dtype == np.int64 and np.array_equal(got, np.array(g["v"])), g["src"]
+    assert from_newick("0;").size == 0
+    assert np.array_equal(from_newick("(0,1)2;"), [0])
+    with pytest.raises(NotImplementedError):
+        from_newick("((0:0.1,1:0.2)3:0.3,2:0.1)4;")
+    assert np.array_equal(from_newick("(0,1)5,(2,3)4)6;"), [0, 2, 2])      # like the reference, "(" is not checked
+    for bad in ("((0,1)5,(2,3)4)6", "((0,1)5,(2,3)4)9;", "((0,1)5,(2,x)4)6;", "((0,1)5,2,3)6;",
+                "((0,1)5,(2,2)4)6;", "((0,1)5,(2,3)5)6;", "((0,1)5;(2,3)4)6;"):
+        with pytest.raises(ValueError):
+            from_newick(bad)
+
+
+@pytest.mark.parametrize("n_leaves", SIZES)
+@pytest.mark.parametrize("dtype", [torch.int64, torch.int32])
+def test_from_newick_batch_parity(p2v, n_leaves, dtype):
+    """to_newick strings, and the same trees with subtrees swapped / in another label order, against
+    the restatement of parse + order_cherries + build_vector."""
+    B = 40
+    V = sample_vectors(B, n_leaves, seed=17 * n_leaves)
+    V[1] = sample_vectors(1, n_leaves, seed=1, ordered=True)[0]
+    adv = list(adversarial_vectors(n_leaves).values())
+    V[2:2 + len(adv)] = np.stack(adv)
+    strings = [O.to_newick(v) for v in V]
+    got = p2v.from_newick_batch(strings, dtype=dtype)
+    assert got.dtype == dtype and np.array_equal(got.cpu().numpy().astype(np.int64), V)      # round trip
+    # children swapped at every internal node (py tests/test_base.py:75-104 permutes cherries)
+    rng = np.random.default_rng(n_leaves)
+    swapped = [_swap_children(s, rng) for s in strings]
+    ref = np.stack([O.from_newick(s) for s in swapped])
+    got = p2v.from_newick_batch(swapped, dtype=dtype)
+    assert np.array_equal(got.cpu().numpy().astype(np.int64), ref)
+    # a malformed and an unlabelled string inside a batch
+    import re
+    mixed = list(strings)
+    mixed[3] = re.sub(r"\)\d+", ")", strings[3])
+    mixed[5] = strings[5].replace(",", ";", 1)
+    status = torch.zeros(B, dtype=torch.int32, device="cuda")
+    got = p2v.from_newick_batch(mixed, n_leaves=n_leaves, dtype=dtype, status=status, check=False)
+    st = status.cpu().numpy()
+    assert st[3] == -3 and st[5] == -2 and np.count_nonzero(st) == 2
+    keep = [b for b in range(B) if b not in (3, 5)]
+    assert np.array_equal(got.cpu().numpy().astype(np.int64)[keep], V[keep])
+    with pytest.raises(NotImplementedError):
+        p2v.from_newick_batch(mixed[:4], n_leaves=n_leaves)
+
+
+def _swap_children(newick, rng):
+    """The same tree with the two children of random internal nodes exchanged."""
+    def parse(s, i):
+        if s[i] == "(":
+            a, i = parse(s, i + 1)
+            assert s[i] == ","
+            b, i = parse(s, i + 1)
+            assert s[i] == ")"
+            j = i + 1
+            while s[j].isdigit():
+                j += 1
+            return (a, b, s[i + 1:j]), j
+        j = i
+        while s[j].isdigit():
+            j += 1
+        return s[i:j], j
+
+    import sys
+    sys.setrecursionlimit(max(sys.getrecursionlimit(), 20000))
+    tree, _ = parse(newick, 0)
+
+    def emit(t):
+        if isinstance(t, str):
+            return t
+        a, b, lab = t
+        if rng.random() < 0.5:
+            a, b = b, a
+        return "(" + emit(a) + "," + emit(b) + ")" + lab
+
+    return emit(tree) + ";"
+
+
+def test_from_newick_host_entry(p2v):
+    from phylo2vec_b200 import _capi
+    lib = _capi.load()
+    n, B = 100, 5000
+    V = sample_vectors(B, n, seed=21)
+    buf, lengths = O.to_newick_batch(V, int(lib.p2v_newick_max_bytes(n - 1)))
+    out = np.zeros((B, n - 1), dtype=np.int64)
+    st = np.ones(B, dtype=np.int32)
+    vp = ctypes.c_void_p
+    rc = lib.p2v_from_newick_host(buf.ctypes.data_as(vp), buf.shape[1], B, n - 1, out.ctypes.data_as(vp), 8,
+                                  st.ctypes.data_as(vp))
+    assert rc == 0 and not st.any() and np.array_equal(out, V)
+    ref, rst = O.from_newick_batch(buf, lengths, n - 1)
+    assert not rst.any() and np.array_equal(ref, V)

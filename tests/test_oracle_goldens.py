@@ -124,3 +124,24 @@ def test_node_depths(goldens):
         assert got.shape == (2 * k + 1,) and got[2 * k] == 0.0
         for node, d in g["depths"].items():
             assert abs(got[int(node)] - d) < 1e-10, (g["src"], node)   # vector/ops.rs:609-612
+
+
+def test_from_newick(goldens):
+    # with parent labels and without (convert.rs:259-266, 662-664, 674-676)
+    for g in goldens["from_newick"]:
+        assert np.array_equal(O.from_newick(g["newick"]), np.array(g["v"])), g["src"]
+    for g in goldens["newick_parse"]:
+        assert np.array_equal(O.newick_parse(g["newick"]), np.array(g["ancestry"])), g["src"]
+    assert O.from_newick("").size == 0
+
+
+def test_newick_round_trip_oracle():
+    # test_newick (convert.rs:640-656): v -> to_newick -> from_newick == v, n = 10, 100, 1000;
+    # without parent labels (py tests/test_base.py:56-72 does the same for matrices) as well
+    import re
+    from .helpers import sample_vectors
+    for n in (2, 3, 10, 100, 1000):
+        for v in sample_vectors(4, n, seed=n):
+            nw = O.to_newick(v)
+            assert np.array_equal(O.from_newick(nw), v), n
+            assert np.array_equal(O.from_newick(re.sub(r"\)\d+", ")", nw)), v), n
