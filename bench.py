@@ -302,12 +302,12 @@ def run_b200(args):
         coph = bench_cophenetic(torch, lib, device, rank, world, peak, args)
     except Exception as exc:  # keep the headline line even if this part fails
         coph = {"error": repr(exc)}
-    newick = None
+    newick = (None, None)
     if rank == 0:
         try:
             newick = bench_newick(torch, lib, device, peak)
         except Exception as exc:
-            newick = {"error": repr(exc)}
+            newick = ({"error": repr(exc)}, {"error": repr(exc)})
     if world > 1:
         gathered = [None] * world
         dist.all_gather_object(gathered, coph)
@@ -352,7 +352,7 @@ def run_b200(args):
                                  "third is k+1+row); host threads of the library widen them into the caller's int64 rows",
                     "api": "p2v_to_ancestry_host (C ABI, pinned host buffers)", "matches_device_path": e2e_ok},
             "gpu_launches": launches, "clocks": clocks, "parity_spot_check": parity,
-            "config_c2_other_functions": c2, "cophenetic": coph, "next_rows": {"to_newick": newick},
+            "config_c2_other_functions": c2, "cophenetic": coph, "next_rows": {"to_newick": newick[0], "from_newick": newick[1]},
         }
         print(json.dumps(line))
     if world > 1:
@@ -364,7 +364,7 @@ def bench_newick(torch, lib, device, peak):
     restatement on a bounded sample.  Bytes = v read + string bytes written."""
     import numpy as np
     from oracle import p2v_oracle as O
-    res = {}
+    res, res2 = {}, {}
     for n, B in ((100, 1_000_000), (1000, 100_000)):
         k = n - 1
         g = torch.Generator(device=device).manual_seed(n)
@@ -403,8 +403,34 @@ def bench_newick(torch, lib, device, peak):
         res[f"n{n}"] = {"batch": B, "trees_per_s": B / t, "gbs": nbytes / t / 1e9, "frac_of_peak": nbytes / t / 1e9 / peak,
                         "cpu": {"sample": Bc, "trees_per_s": Bc / tc, "cores": host_threads(), "kind": "port"},
                         "matches_cpu": same}
-        del V, out, ws
-    return res
+        # and back: from_newick on the strings just written (bytes = string bytes read + v written)
+        back = torch.empty((B, k), dtype=torch.int64, device=device)
+        need2 = int(lib.p2v_from_newick_workspace_bytes(B, k, 8))
+        del ws
+        ws2 = torch.empty(max(need2, 16), dtype=torch.uint8, device=device)
+
+        def call2():
+            rc = lib.p2v_from_newick_batch(out.data_ptr(), stride, lengths.data_ptr(), B, k, back.data_ptr(), 8,
+                                           st.data_ptr(), ws2.data_ptr(), need2, stream.cuda_stream)
+            assert rc == 0, lib.p2v_last_error()
+        for _ in range(3):
+            call2()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(5):
+            call2()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t2 = e0.elapsed_time(e1) / 5 * 1e-3
+        t0 = time.perf_counter()
+        refv, refst = O.from_newick_batch(ref, reflen, k, nthreads=host_threads())
+        tc2 = time.perf_counter() - t0
+        res2[f"n{n}"] = {"batch": B, "trees_per_s": B / t2, "gbs": nbytes / t2 / 1e9, "frac_of_peak": nbytes / t2 / 1e9 / peak,
+                         "cpu": {"sample": Bc, "trees_per_s": Bc / tc2, "cores": host_threads(), "kind": "port"},
+                         "round_trip_equal": bool(torch.equal(back, V)) and not bool(st.any()),
+                         "matches_cpu": bool(np.array_equal(refv, Vc)) and not bool(refst.any())}
+        del V, out, ws2, back
+    return res, res2
 
 
 def bench_cophenetic(torch, lib, device, rank, world, peak, args):

@@ -158,16 +158,16 @@ int p2v_to_newick_batch(const void *v, int idx_bytes, int64_t B, int64_t k, char
                         int64_t *lengths, int32_t *status, void *workspace, size_t workspace_bytes,
                         p2v_stream_t stream);
 
-/* ---- from_newick (second "next" row; vectors, Newick with parent labels) -------------------
- * replaces newick::parse (phylo2vec/src/newick/mod.rs:73-127) and vector::convert::from_newick,
- * has_parents arm (vector/convert.rs:268-278: parse, order_cherries, build_vector); PyO3 entry
- * point to_vector (py-phylo2vec/src/lib.rs:98-101); Python phylo2vec.base.newick.from_newick.
- * Every tree of the batch has k + 1 leaves labelled 0..k and internal nodes k+1..2k.  Tree b's
- * string starts at newick + b * in_stride and is lengths[b] bytes long (lengths == NULL: it is
- * NUL-terminated inside its row).  status[b]: 0, P2V_TREE_MALFORMED (not a binary Newick of
- * k + 1 leaves made of "(),;" and digits, or labels that do not form a tree), or
- * P2V_ERR_UNSUPPORTED for a string without parent labels ("((0,1),2);" -- the reference's
- * order_cherries_no_parents arm is not built). */
+/* ---- from_newick (second "next" row; vectors) ------------------------------------------------
+ * replaces newick::parse (phylo2vec/src/newick/mod.rs:73-127) and vector::convert::from_newick
+ * (vector/convert.rs:268-278: parse, then order_cherries for strings with parent labels or
+ * order_cherries_no_parents :534-573 for strings without, then build_vector); PyO3 entry point
+ * to_vector (py-phylo2vec/src/lib.rs:98-101); Python phylo2vec.base.newick.from_newick.
+ * Every tree of the batch has k + 1 leaves labelled 0..k (and, if labelled, internal nodes
+ * k+1..2k).  Tree b's string starts at newick + b * in_stride and is lengths[b] bytes long
+ * (lengths == NULL: it is NUL-terminated inside its row).  status[b]: 0 or P2V_TREE_MALFORMED
+ * (not a binary Newick of k + 1 leaves made of "(),;" and digits and ending in ";", parent
+ * labels on some ")" only, or labels that do not form a tree). */
 size_t p2v_from_newick_workspace_bytes(int64_t B, int64_t k, int idx_bytes);
 int p2v_from_newick_batch(const char *newick, int64_t in_stride, const int64_t *lengths, int64_t B, int64_t k,
                           void *v, int idx_bytes, int32_t *status, void *workspace, size_t workspace_bytes,

@@ -1,7 +1,7 @@
 """Newick conversion; drop-in for py-phylo2vec/phylo2vec/base/newick.py (to_newick and from_newick,
 vectors).
 
-The matrix forms (branch lengths) and from_newick of a string without parent labels are not built."""
+The matrix forms (branch lengths) are not built."""
 
 import ctypes
 
@@ -33,10 +33,10 @@ def to_newick(vector_or_matrix) -> str:
 
 
 def from_newick(newick: str) -> np.ndarray:
-    """Phylo2Vec vector of a Newick string with parent labels, like core.to_vector
-    (py-phylo2vec/src/lib.rs:98-101; phylo2vec/src/vector/convert.rs:268-278, has_parents arm):
-    ``from_newick("((0,1)5,(2,3)4)6;") -> [0, 2, 2]``.  Branch lengths (the matrix form) and
-    strings without parent labels raise NotImplementedError."""
+    """Phylo2Vec vector of a Newick string with or without parent labels, like core.to_vector
+    (py-phylo2vec/src/lib.rs:98-101; phylo2vec/src/vector/convert.rs:268-278):
+    ``from_newick("((0,1)5,(2,3)4)6;") -> [0, 2, 2]``, ``from_newick("((0,1),(2,3));") -> [0, 2, 2]``.
+    Branch lengths (the matrix form) raise NotImplementedError."""
     if not isinstance(newick, str):
         raise TypeError("newick must be a str")
     if ":" in newick:
@@ -51,8 +51,6 @@ def from_newick(newick: str) -> np.ndarray:
     status = np.zeros(1, dtype=np.int32)
     rc = _capi.load().p2v_from_newick_host(ctypes.cast(buf, ctypes.c_void_p), len(data) + 1, 1, k, ptr(v), 8, ptr(status))
     _capi.check(rc, "from_newick")
-    if int(status[0]) == -3:
-        raise NotImplementedError("from_newick of a string without parent labels is not built in phylo2vec_b200")
     if int(status[0]) != 0:
         raise ValueError("malformed Newick string: not a binary tree with leaves 0..n-1 and parents n..2n-2")
     return v

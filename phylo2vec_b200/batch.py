@@ -357,11 +357,11 @@ def to_newick_batch(V, status=None, check: bool = True, raw: bool = False):
 
 def from_newick_batch(newick, lengths=None, n_leaves: Optional[int] = None, dtype=torch.int64, status=None,
                       check: bool = True, device=None) -> torch.Tensor:
-    """Vectors ``(B,k)`` of a batch of Newick strings with parent labels; every tree has the same
+    """Vectors ``(B,k)`` of a batch of Newick strings (with or without parent labels); every tree has the same
     number of leaves.  ``newick`` is a list of ``str`` or the raw form :func:`to_newick_batch` returns
     (uint8 tensor ``(B, stride)`` on the GPU, with ``lengths`` or NUL-terminated rows).
     Replaces newick::parse + vector::convert::from_newick (phylo2vec/src/newick/mod.rs:73-127,
-    vector/convert.rs:268-278)."""
+    vector/convert.rs:268-278, 534-573)."""
     if isinstance(newick, (list, tuple)):
         if len(newick) == 0:
             raise ValueError("from_newick: empty batch")
@@ -400,8 +400,6 @@ def from_newick_batch(newick, lengths=None, n_leaves: Optional[int] = None, dtyp
     _capi.check(rc, "from_newick")
     if check:
         st = status.cpu().numpy()
-        if (st == -3).any():
-            raise NotImplementedError("from_newick of a string without parent labels is not built in phylo2vec_b200")
         if st.any():
             raise ValueError(f"malformed Newick string (tree {int(np.flatnonzero(st)[0])})")
     return v

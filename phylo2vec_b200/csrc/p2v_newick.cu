@@ -311,17 +311,19 @@ cudaError_t launch_to_newick(const void* v, int idx_bytes, int64_t B, int64_t k,
 
 
 // ======================================================================================
-// from_newick (vectors; Newick with parent labels)
+// from_newick (vectors)
 //
 // Replaces (reference):
 //   newick::parse                                   phylo2vec/src/newick/mod.rs:73-127
-//   vector::convert::from_newick (has_parents arm)  phylo2vec/src/vector/convert.rs:268-278
+//   vector::convert::from_newick                    phylo2vec/src/vector/convert.rs:268-278
+//   order_cherries_no_parents                       phylo2vec/src/vector/convert.rs:534-573
 //   PyO3 to_vector                                  py-phylo2vec/src/lib.rs:98-101
 //
 // The reference walks the string with a stack: a number pushes a node, ")" pops two children and
-// pushes the label that follows.  The nodes therefore appear in post-order, and with S(i) = stack
-// height after node i (leaf +1, internal -1): the second child of internal node i is node i-1,
-// the first child is the latest node j < i with S(j) = S(i).  One CTA per tree:
+// pushes the label that follows (or, without parent labels, the smaller child).  The nodes
+// therefore appear in post-order, and with S(i) = stack height after node i (leaf +1, internal
+// -1): the second child of internal node i is node i-1, the first child is the latest node
+// j < i with S(j) = S(i).  One CTA per tree:
 //   1. the string is staged in shared memory; every thread classifies a contiguous piece
 //      (leaf token, ")" with its label, punctuation) and a block scan numbers the nodes and
 //      gives S; the labels are parsed where the tokens start;
@@ -330,30 +332,138 @@ cudaError_t launch_to_newick(const void* v, int idx_bytes, int64_t B, int64_t k,
 //      cherry list in string order -- newick::parse's output as an edge list;
 //   3. the batched encode kernel (from_edges: order_cherries + build_cherries + build_vector)
 //      turns the rows into v.
-// Strings without parent labels ("((0,1),2);", order_cherries_no_parents) are not built: such a
-// tree gets status P2V_ERR_UNSUPPORTED; anything that is not a well-formed binary Newick of k + 1
-// leaves gets P2V_TREE_MALFORMED.
+// Strings without parent labels take a second kernel (newick_parse_np_kernel) that gives every
+// internal node the label the reference's ordering implies.  order_cherries_no_parents sorts the
+// cherries by their "sister" key, descending and stable; along the chain of cherries that share a
+// smaller child m the key is the running minimum of the larger children, i.e. the second-smallest
+// leaf label of the cherry's subtree.  A subtree is a contiguous range of leaves in string order,
+// so the key is three range-minimum queries on a sparse table over the leaf labels; equal keys
+// only occur along one chain, in row order.  The cherry with sorted position q is labelled
+// k + 1 + q and the tree goes through the same from_edges encoder.
+// Anything that is not a well-formed binary Newick of k + 1 leaves gets P2V_TREE_MALFORMED.
 // ======================================================================================
 
-constexpr int NP_UNSUPPORTED = -3;      // P2V_ERR_UNSUPPORTED as a per-tree status
+constexpr int NP_NOPARENTS = -3;        // first kernel -> second kernel: ")" without a label seen
 constexpr int NP_MALFORMED = -2;        // P2V_TREE_MALFORMED
 constexpr uint32_t NP_INTERNAL = 0x80000000u;
 
-struct ParseLayout { size_t str, lab, sh, last, total; };
-__host__ __device__ inline ParseLayout parse_layout(int64_t k, bool staged) {
+struct ParseLayout { size_t str, lab, sh, last, c1a, first, leaf, sister, gt, sparse, total; int levels; };
+// noparents: the extra tables of the second kernel
+__host__ __device__ inline ParseLayout parse_layout(int64_t k, bool staged, bool noparents) {
     ParseLayout L;
-    const size_t N = 2 * (size_t)k + 1;
+    const size_t N = 2 * (size_t)k + 1, n = (size_t)k + 1;
     size_t o = 0;
     L.str = o; o = nw_al16(o + (staged ? newick_bytes(k) + 16 : 0));
     L.lab = o; o = nw_al16(o + 4 * N);
     L.sh = o; o = nw_al16(o + 4 * N);
     L.last = o; o = nw_al16(o + 4 * ((size_t)k + 3));
+    int lv = 1;
+    while (((size_t)1 << lv) <= n) ++lv;          // levels 0 .. lv-1, 2^(lv-1) <= n
+    L.levels = lv;
+    L.c1a = o; o = nw_al16(o + (noparents ? 4 * N : 0));
+    L.first = o; o = nw_al16(o + (noparents ? 4 * N : 0));
+    L.leaf = o; o = nw_al16(o + (noparents ? 4 * n : 0));
+    L.sister = o; o = nw_al16(o + (noparents ? 4 * n : 0));
+    L.gt = o; o = nw_al16(o + (noparents ? 4 * (n + 1) : 0));
+    L.sparse = o; o = nw_al16(o + (noparents ? 4 * n * (size_t)lv : 0));
     L.total = o;
     return L;
 }
-static bool parse_fits_smem(int64_t k) { return k <= 8192 && parse_layout(k, true).total <= 200 * 1024; }
+static bool parse_fits_smem(int64_t k, bool noparents) {
+    return k <= 8192 && parse_layout(k, true, noparents).total <= 200 * 1024;
+}
 
 __device__ __forceinline__ bool np_digit(char c) { return c >= '0' && c <= '9'; }
+
+struct ParseShared { int cnt[32], del[32]; int len, bad; };
+
+// Length of tree's string (0 = unusable), staged copy, node labels (lab: label | NP_INTERNAL, in
+// post-order) and stack heights (sh).  LABELLED: every ")" carries a label (a ")" without one
+// makes the tree NP_NOPARENTS); otherwise no ")" may carry one.  Returns the tree's verdict
+// (uniform over the CTA): 0, NP_NOPARENTS or NP_MALFORMED.
+template <bool LABELLED, bool STAGED>
+__device__ __forceinline__ int newick_tokenize(const char* __restrict__ src, int64_t in_stride, const int64_t* __restrict__ lengths,
+                                               int64_t tree, int k, int maxlen, char* sstr, uint32_t* lab, int* sh,
+                                               ParseShared& P) {
+    const int N = 2 * k + 1;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
+    __syncthreads();                          // the previous tree is done with the tables
+    if (tid == 0) { P.bad = 0; P.len = maxlen + 1; }
+    __syncthreads();
+    int len;
+    if (lengths) {
+        const int64_t l64 = lengths[tree];
+        len = (l64 < 1 || l64 > maxlen) ? 0 : (int)l64;
+    } else {                                  // NUL-terminated inside the row
+        const int lim = (int)(in_stride < (int64_t)maxlen + 1 ? in_stride : (int64_t)maxlen + 1);
+        for (int i = tid; i < lim; i += NT) if (src[i] == 0) { atomicMin(&P.len, i); break; }
+        __syncthreads();
+        len = (P.len < 1 || P.len > maxlen) ? 0 : P.len;
+    }
+    const char* s = src;
+    if (STAGED) {
+        for (int i = tid; i < len; i += NT) sstr[i] = src[i];
+        s = sstr;
+        __syncthreads();
+    }
+    // classify, count, scan
+    const int CH = (len + NT - 1) / NT;
+    const int i0 = min(len, tid * CH), i1 = min(len, i0 + CH);
+    int cnt = 0, del = 0, bad = (len == 0 || s[len - 1] != ';') ? NP_MALFORMED : 0;    // node_substr needs the ";"
+    for (int i = i0; i < i1; ++i) {
+        const char c = s[i];
+        const char prev = i > 0 ? s[i - 1] : '\0';
+        if (c == ')') { ++cnt; --del; }
+        else if (np_digit(c)) { if (prev == '(' || prev == ',') { ++cnt; ++del; } else if (i == 0) bad = NP_MALFORMED; }
+        else if (c == '(' || c == ',') {}
+        else if (c == ';') { if (i != len - 1) bad = NP_MALFORMED; }
+        else bad = NP_MALFORMED;
+    }
+    int icnt = cnt, idel = del;               // inclusive scans over the threads
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int a = __shfl_up_sync(FULL, icnt, d), b = __shfl_up_sync(FULL, idel, d);
+        if (lane >= d) { icnt += a; idel += b; }
+    }
+    if (lane == 31) { P.cnt[warp] = icnt; P.del[warp] = idel; }
+    __syncthreads();
+    if (warp == 0) {
+        int a = lane < nwarp ? P.cnt[lane] : 0, b = lane < nwarp ? P.del[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int x = __shfl_up_sync(FULL, a, d), y = __shfl_up_sync(FULL, b, d);
+            if (lane >= d) { a += x; b += y; }
+        }
+        P.cnt[lane] = a; P.del[lane] = b;
+    }
+    __syncthreads();
+    const int tot_nodes = P.cnt[nwarp - 1], tot_del = P.del[nwarp - 1];
+    if (tot_nodes != N || tot_del != 1) bad = bad ? bad : NP_MALFORMED;
+    int idx = icnt - cnt + (warp ? P.cnt[warp - 1] : 0);
+    int S = idel - del + (warp ? P.del[warp - 1] : 0);
+    if (!bad) {
+        for (int i = i0; i < i1; ++i) {
+            const char c = s[i];
+            int from;
+            uint32_t kind;
+            if (c == ')') { from = i + 1; kind = NP_INTERNAL; --S; }
+            else if (np_digit(c) && (s[i - 1] == '(' || s[i - 1] == ',')) { from = i; kind = 0; ++S; }
+            else continue;
+            uint32_t val = 0;
+            int nd = 0;
+            while (from + nd < len && nd < 9 && np_digit(s[from + nd])) { val = val * 10u + (uint32_t)(s[from + nd] - '0'); ++nd; }
+            if (kind && !LABELLED) { if (nd != 0) bad = NP_MALFORMED; }           // labelled and unlabelled ")" mixed
+            else if (nd == 0) bad = NP_NOPARENTS;                                 // ")" without a parent label
+            else if (nd > 8 || val > (kind ? 2u * (uint32_t)k : (uint32_t)k)) bad = bad ? bad : NP_MALFORMED;
+            if (S < 1) bad = NP_MALFORMED;
+            lab[idx] = val | kind; sh[idx] = S;
+            ++idx;
+        }
+    }
+    if (bad) atomicMax(&P.bad, bad == NP_MALFORMED ? 2 : 1);      // malformed wins
+    __syncthreads();
+    return P.bad == 0 ? 0 : (P.bad == 2 ? NP_MALFORMED : NP_NOPARENTS);
+}
 
 template <typename OutT, bool STAGED>
 __global__ void __launch_bounds__(NW_THREADS_MAX)
@@ -361,103 +471,28 @@ newick_parse_kernel(const char* __restrict__ in, int64_t in_stride, const int64_
                     OutT* __restrict__ edges, int32_t* __restrict__ pstatus, unsigned char* __restrict__ tables,
                     size_t tables_stride, int maxlen) {
     extern __shared__ __align__(16) unsigned char dyn_smem[];
-    __shared__ int s_cnt[32], s_del[32];
-    __shared__ int s_len, s_bad;
+    __shared__ ParseShared P;
     unsigned char* dyn = STAGED ? dyn_smem : tables + (size_t)blockIdx.x * tables_stride;
-    const ParseLayout L = parse_layout(k, STAGED);
+    const ParseLayout L = parse_layout(k, STAGED, false);
     const int N = 2 * k + 1;
-    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* lab = reinterpret_cast<uint32_t*>(dyn + L.lab);      // label | NP_INTERNAL, by node (post-order)
     int* sh = reinterpret_cast<int*>(dyn + L.sh);                  // stack height after the node
     int* last = reinterpret_cast<int*>(dyn + L.last);              // latest node of height h
 
     for (int64_t tree = blockIdx.x; tree < B; tree += gridDim.x) {
-        const char* src = in + tree * in_stride;
         OutT* erow = edges + (size_t)tree * 4 * (size_t)k;
-        __syncthreads();                          // the previous tree is done with the tables
-        if (tid == 0) { s_bad = 0; s_len = maxlen + 1; }
-        __syncthreads();
-        int len;
-        if (lengths) {
-            const int64_t l64 = lengths[tree];
-            len = (l64 < 1 || l64 > maxlen) ? 0 : (int)l64;
-        } else {                                  // NUL-terminated inside the row
-            const int lim = (int)(in_stride < (int64_t)maxlen + 1 ? in_stride : (int64_t)maxlen + 1);
-            for (int i = tid; i < lim; i += NT) if (src[i] == 0) { atomicMin(&s_len, i); break; }
-            __syncthreads();
-            len = (s_len < 1 || s_len > maxlen) ? 0 : s_len;
-        }
-        const char* s = src;
-        if (STAGED) {
-            char* sstr = reinterpret_cast<char*>(dyn + L.str);
-            for (int i = tid; i < len; i += NT) sstr[i] = src[i];
-            s = sstr;
-            __syncthreads();
-        }
-        // ---- 1. classify, count, scan ----------------------------------------------------------
-        const int CH = (len + NT - 1) / NT;
-        const int i0 = min(len, tid * CH), i1 = min(len, i0 + CH);
-        int cnt = 0, del = 0, bad = (len == 0 || s[len - 1] != ';') ? NP_MALFORMED : 0;    // node_substr needs the ";"
-        for (int i = i0; i < i1; ++i) {
-            const char c = s[i];
-            const char prev = i > 0 ? s[i - 1] : '\0';
-            if (c == ')') { ++cnt; --del; }
-            else if (np_digit(c)) { if (prev == '(' || prev == ',') { ++cnt; ++del; } else if (i == 0) bad = NP_MALFORMED; }
-            else if (c == '(' || c == ',') {}
-            else if (c == ';') { if (i != len - 1) bad = NP_MALFORMED; }
-            else bad = NP_MALFORMED;
-        }
-        int icnt = cnt, idel = del;               // inclusive scans over the threads
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int a = __shfl_up_sync(FULL, icnt, d), b = __shfl_up_sync(FULL, idel, d);
-            if (lane >= d) { icnt += a; idel += b; }
-        }
-        if (lane == 31) { s_cnt[warp] = icnt; s_del[warp] = idel; }
-        __syncthreads();
-        if (warp == 0) {
-            int a = lane < nwarp ? s_cnt[lane] : 0, b = lane < nwarp ? s_del[lane] : 0;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int x = __shfl_up_sync(FULL, a, d), y = __shfl_up_sync(FULL, b, d);
-                if (lane >= d) { a += x; b += y; }
-            }
-            s_cnt[lane] = a; s_del[lane] = b;
-        }
-        __syncthreads();
-        const int tot_nodes = s_cnt[nwarp - 1], tot_del = s_del[nwarp - 1];
-        if (tot_nodes != N || tot_del != 1) bad = bad ? bad : NP_MALFORMED;
-        int idx = icnt - cnt + (warp ? s_cnt[warp - 1] : 0);
-        int S = idel - del + (warp ? s_del[warp - 1] : 0);
-        if (!bad) {
-            for (int i = i0; i < i1; ++i) {
-                const char c = s[i];
-                int from;
-                uint32_t kind;
-                if (c == ')') { from = i + 1; kind = NP_INTERNAL; --S; }
-                else if (np_digit(c) && (s[i - 1] == '(' || s[i - 1] == ',')) { from = i; kind = 0; ++S; }
-                else continue;
-                uint32_t val = 0;
-                int nd = 0;
-                while (from + nd < len && nd < 9 && np_digit(s[from + nd])) { val = val * 10u + (uint32_t)(s[from + nd] - '0'); ++nd; }
-                if (nd == 0) bad = NP_UNSUPPORTED;                 // ")" without a parent label
-                else if (nd > 8 || val > 2u * (uint32_t)k) bad = NP_MALFORMED;
-                if (S < 1) bad = bad ? bad : NP_MALFORMED;
-                lab[idx] = val | kind; sh[idx] = S;
-                ++idx;
-            }
-        }
-        if (bad) atomicMin(&s_bad, bad);          // UNSUPPORTED (-3) wins over MALFORMED (-2)
-        __syncthreads();
-        if (s_bad) {                              // uniform
-            if (tid == 0) {
-                pstatus[tree] = s_bad;
+        const int verdict = newick_tokenize<true, STAGED>(in + tree * in_stride, in_stride, lengths, tree, k, maxlen,
+                                                          reinterpret_cast<char*>(dyn + L.str), lab, sh, P);
+        if (verdict) {                            // uniform
+            if (threadIdx.x == 0) {
+                pstatus[tree] = verdict;
                 erow[0] = (OutT)-1; erow[1] = (OutT)-1;           // the encoder rejects the tree as well
             }
             continue;
         }
-        if (tid == 0) pstatus[tree] = 0;
-        // ---- 2. children of every internal node: one warp, 32 nodes at a time ------------------
+        if (threadIdx.x == 0) pstatus[tree] = 0;
+        // children of every internal node: one warp, 32 nodes at a time
         if (warp == 0) {
             for (int base = 0; base < N; base += 32) {
                 const int node = base + lane;
@@ -481,17 +516,166 @@ newick_parse_kernel(const char* __restrict__ in, int64_t in_stride, const int64_
     }
 }
 
+// Trees the first kernel marked NP_NOPARENTS.
+template <typename OutT, bool STAGED>
+__global__ void __launch_bounds__(NW_THREADS_MAX)
+newick_parse_np_kernel(const char* __restrict__ in, int64_t in_stride, const int64_t* __restrict__ lengths, int64_t B, int k,
+                       OutT* __restrict__ edges, int32_t* __restrict__ pstatus, unsigned char* __restrict__ tables,
+                       size_t tables_stride, int maxlen) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ ParseShared P;
+    __shared__ int s_scan[32];
+    unsigned char* dyn = STAGED ? dyn_smem : tables + (size_t)blockIdx.x * tables_stride;
+    const ParseLayout L = parse_layout(k, STAGED, true);
+    const int N = 2 * k + 1, n = k + 1;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
+    uint32_t* lab = reinterpret_cast<uint32_t*>(dyn + L.lab);
+    int* sh = reinterpret_cast<int*>(dyn + L.sh);
+    int* last = reinterpret_cast<int*>(dyn + L.last);
+    int* c1a = reinterpret_cast<int*>(dyn + L.c1a);                // first child (node index) of an internal node
+    int* first = reinterpret_cast<int*>(dyn + L.first);            // first node of the node's subtree
+    uint32_t* leaf = reinterpret_cast<uint32_t*>(dyn + L.leaf);    // leaf labels in string order
+    uint32_t* sister = reinterpret_cast<uint32_t*>(dyn + L.sister);  // sort key of cherry r
+    int* gt = reinterpret_cast<int*>(dyn + L.gt);                  // histogram, then cherries with a larger key
+    uint32_t* sparse = reinterpret_cast<uint32_t*>(dyn + L.sparse);  // argmin of leaf[] over [a, a + 2^l)
+    const int levels = L.levels;
+
+    for (int64_t tree = blockIdx.x; tree < B; tree += gridDim.x) {
+        if (pstatus[tree] != NP_NOPARENTS) continue;               // uniform
+        OutT* erow = edges + (size_t)tree * 4 * (size_t)k;
+        const int verdict = newick_tokenize<false, STAGED>(in + tree * in_stride, in_stride, lengths, tree, k, maxlen,
+                                                           reinterpret_cast<char*>(dyn + L.str), lab, sh, P);
+        if (verdict) {                            // uniform; row 0 already holds the reject marker
+            if (tid == 0) pstatus[tree] = NP_MALFORMED;
+            continue;
+        }
+        // ---- first child and first node of every subtree: one warp, 32 nodes at a time ----------
+        if (warp == 0) {
+            for (int base = 0; base < N; base += 32) {
+                const int node = base + lane;
+                const bool act = node < N;
+                const bool internal = act && (lab[act ? node : 0] & NP_INTERNAL);
+                const int Sv = act ? sh[node] : -1 - lane;
+                const uint32_t peers = __match_any_sync(FULL, Sv);
+                int val = node, ptr = lane;       // leaves (and padding) are resolved: their subtree starts at themselves
+                if (internal) {
+                    const uint32_t lower = peers & lanes_lt(lane);
+                    const int j = lower ? base + 31 - __clz(lower) : last[Sv];
+                    c1a[node] = j;
+                    if (j >= base) ptr = j - base;                 // first(node) = first(first child), still open
+                    else val = first[j];
+                }
+#pragma unroll
+                for (int it = 0; it < 5; ++it) {                   // chains inside the batch
+                    const int nv = __shfl_sync(FULL, val, ptr), np = __shfl_sync(FULL, ptr, ptr);
+                    if (ptr != lane) { val = nv; ptr = np; }
+                }
+                if (act) first[node] = val;
+                __syncwarp();
+                if (act && (peers & lanes_gt(lane)) == 0) last[Sv] = node;
+                __syncwarp();
+            }
+        }
+        // ---- leaf labels in string order, sparse table of argmins ---------------------------------
+        for (int i = tid; i < N; i += NT) {
+            const uint32_t lb = lab[i];
+            if (!(lb & NP_INTERNAL)) {
+                const int ord = ((i + 1 + sh[i]) >> 1) - 1;          // leaves before this one
+                leaf[ord] = lb; sparse[ord] = (uint32_t)ord;
+            }
+        }
+        for (int i = tid; i <= n; i += NT) gt[i] = 0;
+        __syncthreads();
+        for (int l = 1; l < levels; ++l) {
+            const uint32_t* lo = sparse + (size_t)(l - 1) * n;
+            uint32_t* hi = sparse + (size_t)l * n;
+            const int half = 1 << (l - 1);
+            for (int a = tid; a + 2 * half <= n; a += NT) {
+                const uint32_t x = lo[a], y = lo[a + half];
+                hi[a] = leaf[y] < leaf[x] ? y : x;
+            }
+            __syncthreads();
+        }
+        auto argmin = [&](int a, int b) -> int {                   // [a, b], a <= b
+            const int l = 31 - __clz(b - a + 1);
+            const uint32_t x = sparse[(size_t)l * n + a], y = sparse[(size_t)l * n + b - (1 << l) + 1];
+            return (int)(leaf[y] < leaf[x] ? y : x);
+        };
+        // ---- sort key of every cherry: the second-smallest leaf of its subtree ------------------------
+        for (int i = tid; i < N; i += NT) {
+            if (!(lab[i] & NP_INTERNAL)) continue;
+            const int f = first[i];
+            const int la = f == 0 ? 0 : (f + sh[f - 1]) >> 1;       // leaves before the subtree
+            const int lb = ((i + 1 + sh[i]) >> 1) - 1;              // its last leaf
+            const int a = argmin(la, lb);
+            uint32_t m2 = 0xFFFFFFFFu;
+            if (a > la) m2 = leaf[argmin(la, a - 1)];
+            if (a < lb) m2 = min(m2, leaf[argmin(a + 1, lb)]);
+            const int r = ((i + 1 - sh[i]) >> 1) - 1;
+            sister[r] = m2;
+            atomicAdd(&gt[m2 <= (uint32_t)k ? m2 : 0], 1);
+        }
+        __syncthreads();
+        // ---- gt[s] = cherries whose key is larger than s (suffix sums over the bins 0..k) ------------
+        {
+            const int CH = (n + NT - 1) / NT;
+            const int hi_end = n - tid * CH, lo_end = max(0, hi_end - CH);      // this thread's bins [lo_end, hi_end), from the top
+            int sum = 0;
+            for (int b = hi_end - 1; b >= lo_end; --b) sum += gt[b];
+            int inc = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(FULL, inc, d); if (lane >= d) inc += y; }
+            if (lane == 31) s_scan[warp] = inc;
+            __syncthreads();
+            if (warp == 0) {
+                int a = lane < nwarp ? s_scan[lane] : 0;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(FULL, a, d); if (lane >= d) a += y; }
+                s_scan[lane] = a;
+            }
+            __syncthreads();
+            int run = inc - sum + (warp ? s_scan[warp - 1] : 0);                 // cherries in the bins above this thread's
+            for (int b = hi_end - 1; b >= lo_end; --b) { const int c = gt[b]; gt[b] = run; run += c; }
+        }
+        __syncthreads();
+        // ---- position of every cherry: larger keys first, equal keys in row order; label k + 1 + q ---
+        if (warp == 0) {
+            for (int base = 0; base < N; base += 32) {
+                const int node = base + lane;
+                const bool internal = node < N && (lab[node < N ? node : 0] & NP_INTERNAL);
+                const int r = internal ? ((node + 1 - sh[node]) >> 1) - 1 : 0;
+                const uint32_t key = internal ? sister[r] : 0x80000000u + (uint32_t)lane;
+                const uint32_t peers = __match_any_sync(FULL, key);
+                if (internal) {
+                    const uint32_t bin = key <= (uint32_t)k ? key : 0u;
+                    const int q = gt[bin] + __popc(peers & lanes_lt(lane));
+                    lab[node] = NP_INTERNAL | (uint32_t)(k + 1 + q);
+                }
+                __syncwarp();
+                if (internal && (peers & lanes_gt(lane)) == 0) gt[key <= (uint32_t)k ? key : 0u] += __popc(peers);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < N; i += NT) {
+            const uint32_t lb = lab[i];
+            if (!(lb & NP_INTERNAL)) continue;
+            const uint32_t c1 = lab[c1a[i]] & ~NP_INTERNAL, c2 = lab[i - 1] & ~NP_INTERNAL, pl = lb & ~NP_INTERNAL;
+            const int r = ((i + 1 - sh[i]) >> 1) - 1;
+            OutT* o = erow + 4 * (size_t)r;
+            o[0] = (OutT)c1; o[1] = (OutT)pl; o[2] = (OutT)c2; o[3] = (OutT)pl;
+        }
+        if (tid == 0) pstatus[tree] = 0;
+    }
+}
+
 __global__ void merge_status_kernel(const int32_t* __restrict__ pst, int32_t* __restrict__ status, int64_t B) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < B; t += (int64_t)gridDim.x * blockDim.x)
         if (pst[t] != 0) status[t] = pst[t];
 }
 
 // workspace: [ parse status (B int32) | edges (B,2k,2) of the index type | encode workspace | per-CTA tables ]
-struct FromNewickWs { size_t pst, edges, enc, enc_bytes, tables, tables_stride, total; };
-static int64_t parse_teams(int64_t B, int64_t k) {
-    const int64_t cap = (int64_t)sm_count() * 2;
-    return B < cap ? B : cap;
-}
+struct FromNewickWs { size_t pst, edges, enc, enc_bytes, tables, tables_stride, total; int64_t teams, teams_np; };
 static FromNewickWs from_newick_ws(int64_t B, int64_t k, int idx_bytes) {
     FromNewickWs w;
     size_t o = 0;
@@ -499,8 +683,19 @@ static FromNewickWs from_newick_ws(int64_t B, int64_t k, int idx_bytes) {
     w.edges = o; o = nw_al16(o + (size_t)idx_bytes * 4 * (size_t)B * (size_t)k);
     w.enc_bytes = encode_workspace_bytes(B, k);
     w.enc = o; o = nw_al16(o + w.enc_bytes);
-    w.tables_stride = parse_fits_smem(k) ? 0 : nw_al16(parse_layout(k, false).total);
-    w.tables = o; o = nw_al16(o + w.tables_stride * (size_t)parse_teams(B, k));
+    // the two parse kernels run one after the other and share the table area
+    const size_t s1 = parse_fits_smem(k, false) ? 0 : nw_al16(parse_layout(k, false, false).total);
+    const size_t s2 = parse_fits_smem(k, true) ? 0 : nw_al16(parse_layout(k, false, true).total);
+    const int64_t cap = (int64_t)sm_count() * 2;
+    w.teams = B < cap ? B : cap;
+    w.tables_stride = s2 > s1 ? s2 : s1;
+    w.teams_np = w.teams;
+    if (s2) {                                     // the sparse table is 4 (k+1) log2(k+1) bytes per CTA: at most 1 GB in all
+        const int64_t fit = (int64_t)(((size_t)1 << 30) / s2);
+        w.teams_np = fit < 1 ? 1 : (fit < w.teams ? fit : w.teams);
+    }
+    const size_t area1 = s1 * (size_t)w.teams, area2 = s2 * (size_t)w.teams_np;
+    w.tables = o; o = nw_al16(o + (area1 > area2 ? area1 : area2));
     w.total = o;
     return w;
 }
@@ -510,26 +705,33 @@ size_t from_newick_workspace_bytes(int64_t B, int64_t k, int idx_bytes) {
 
 template <typename OutT>
 static cudaError_t launch_parse_t(const char* in, int64_t in_stride, const int64_t* lengths, int64_t B, int64_t k,
-                                  OutT* edges, int32_t* pst, unsigned char* tables, size_t tables_stride, cudaStream_t stream) {
+                                  OutT* edges, int32_t* pst, unsigned char* tables, const FromNewickWs& W, cudaStream_t stream) {
     const int maxlen = (int)newick_bytes(k);
-    if (parse_fits_smem(k)) {
-        const size_t smem = parse_layout(k, true).total;
-        auto kern = newick_parse_kernel<OutT, true>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int pass = 0; pass < 2; ++pass) {        // 0: strings with parent labels, 1: the trees pass 0 left as NP_NOPARENTS
+        const bool np = pass == 1;
+        if (parse_fits_smem(k, np)) {
+            const size_t smem = parse_layout(k, true, np).total;
+            auto kern = np ? newick_parse_np_kernel<OutT, true> : newick_parse_kernel<OutT, true>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            const int threads = k <= 255 ? 64 : (k <= 2047 ? 128 : 256);
+            int per_sm = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+            if (e != cudaSuccess) return e;
+            if (per_sm < 1) per_sm = 1;
+            const int64_t cap = (int64_t)sm_count() * per_sm;
+            kern<<<(int)(B < cap ? B : cap), threads, smem, stream>>>(in, in_stride, lengths, B, (int)k, edges, pst, nullptr, 0, maxlen);
+        } else {
+            const size_t stride = nw_al16(parse_layout(k, false, np).total);
+            auto kern = np ? newick_parse_np_kernel<OutT, false> : newick_parse_kernel<OutT, false>;
+            kern<<<(int)(np ? W.teams_np : W.teams), NW_THREADS_MAX, 0, stream>>>(in, in_stride, lengths, B, (int)k, edges, pst,
+                                                                                 tables, stride, maxlen);
+        }
+        count_launch();
+        const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        const int threads = k <= 255 ? 64 : (k <= 2047 ? 128 : 256);
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) per_sm = 1;
-        const int64_t cap = (int64_t)sm_count() * per_sm;
-        kern<<<(int)(B < cap ? B : cap), threads, smem, stream>>>(in, in_stride, lengths, B, (int)k, edges, pst, nullptr, 0, maxlen);
-    } else {
-        newick_parse_kernel<OutT, false><<<(int)parse_teams(B, k), NW_THREADS_MAX, 0, stream>>>(
-            in, in_stride, lengths, B, (int)k, edges, pst, tables, tables_stride, maxlen);
     }
-    count_launch();
-    return cudaGetLastError();
+    return cudaSuccess;
 }
 
 cudaError_t launch_from_newick(const char* in, int64_t in_stride, const int64_t* lengths, int64_t B, int64_t k, void* v,
@@ -544,10 +746,10 @@ cudaError_t launch_from_newick(const char* in, int64_t in_stride, const int64_t*
     cudaError_t e;
     if (idx_bytes == 8)
         e = launch_parse_t<long long>(in, in_stride, lengths, B, k, reinterpret_cast<long long*>(wsb + W.edges), pst,
-                                      wsb + W.tables, W.tables_stride, stream);
+                                      wsb + W.tables, W, stream);
     else
-        e = launch_parse_t<int>(in, in_stride, lengths, B, k, reinterpret_cast<int*>(wsb + W.edges), pst, wsb + W.tables,
-                                W.tables_stride, stream);
+        e = launch_parse_t<int>(in, in_stride, lengths, B, k, reinterpret_cast<int*>(wsb + W.edges), pst, wsb + W.tables, W,
+                                stream);
     if (e != cudaSuccess) return e;
     e = launch_encode(FROM_EDGES, wsb + W.edges, idx_bytes, B, k, v, status, W.enc_bytes ? wsb + W.enc : nullptr,
                       W.enc_bytes, stream);

@@ -116,15 +116,14 @@ def test_big_trees_parity(p2v, n_leaves):
     buf, lengths = p2v.to_newick_batch(dev(V), raw=True)
     back32 = p2v.from_newick_batch(buf, n_leaves=n_leaves, dtype=torch.int32)       # NUL-terminated rows
     assert back32.dtype == torch.int32 and np.array_equal(back32.cpu().numpy(), V)
+    import re
+    bare = [re.sub(r"\)\d+", ")", s) for s in got]                                    # without parent labels
+    assert np.array_equal(p2v.from_newick_batch(bare).cpu().numpy(), V)
 
 
 def test_from_newick_goldens(p2v, goldens):
     from phylo2vec_b200.base.newick import from_newick
-    for g in goldens["from_newick"]:
-        if ")," in g["newick"] or "))" in g["newick"] or ");" in g["newick"]:        # without parent labels: not built
-            with pytest.raises(NotImplementedError):
-                from_newick(g["newick"])
-            continue
+    for g in goldens["from_newick"]:                                     # with and without parent labels
         got = from_newick(g["newick"])
         assert got.dtype == np.int64 and np.array_equal(got, np.array(g["v"])), g["src"]
     assert from_newick("0;").size == 0
@@ -157,19 +156,31 @@ def test_from_newick_batch_parity(p2v, n_leaves, dtype):
     ref = np.stack([O.from_newick(s) for s in swapped])
     got = p2v.from_newick_batch(swapped, dtype=dtype)
     assert np.array_equal(got.cpu().numpy().astype(np.int64), ref)
-    # a malformed and an unlabelled string inside a batch
+    # without parent labels (order_cherries_no_parents, convert.rs:534-573): the same vectors back,
+    # and the swapped trees like the restatement
     import re
+    bare = [re.sub(r"\)\d+", ")", s) for s in strings]
+    got = p2v.from_newick_batch(bare, dtype=dtype)
+    assert np.array_equal(got.cpu().numpy().astype(np.int64), V)
+    bare_swapped = [re.sub(r"\)\d+", ")", s) for s in swapped]
+    ref = np.stack([O.from_newick(s) for s in bare_swapped])
+    got = p2v.from_newick_batch(bare_swapped, dtype=dtype)
+    assert np.array_equal(got.cpu().numpy().astype(np.int64), ref)
+    # labelled, unlabelled, malformed and half-labelled strings inside one batch
     mixed = list(strings)
-    mixed[3] = re.sub(r"\)\d+", ")", strings[3])
+    mixed[3] = bare[3]
     mixed[5] = strings[5].replace(",", ";", 1)
+    if n_leaves > 2:
+        mixed[7] = re.sub(r"\)\d+", ")", strings[7], count=1)
     status = torch.zeros(B, dtype=torch.int32, device="cuda")
     got = p2v.from_newick_batch(mixed, n_leaves=n_leaves, dtype=dtype, status=status, check=False)
     st = status.cpu().numpy()
-    assert st[3] == -3 and st[5] == -2 and np.count_nonzero(st) == 2
-    keep = [b for b in range(B) if b not in (3, 5)]
+    bad = [5, 7] if n_leaves > 2 else [5]
+    assert all(st[b] == -2 for b in bad) and np.count_nonzero(st) == len(bad)
+    keep = [b for b in range(B) if b not in bad]
     assert np.array_equal(got.cpu().numpy().astype(np.int64)[keep], V[keep])
-    with pytest.raises(NotImplementedError):
-        p2v.from_newick_batch(mixed[:4], n_leaves=n_leaves)
+    with pytest.raises(ValueError):
+        p2v.from_newick_batch(mixed[:8], n_leaves=n_leaves)
 
 
 def _swap_children(newick, rng):
