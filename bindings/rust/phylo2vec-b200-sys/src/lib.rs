@@ -27,6 +27,11 @@ extern "C" {
                                status: *mut i32) -> c_int;
     pub fn p2v_node_depths_host(v_or_m: *const c_void, idx_bytes: c_int, bls: *const f64, b: i64, k: i64,
                                 out: *mut f64, status: *mut i32) -> c_int;
+    pub fn p2v_newick_max_bytes(k: i64) -> usize;
+    pub fn p2v_to_newick_host(v: *const c_void, idx_bytes: c_int, b: i64, k: i64, out: *mut c_char, out_stride: i64,
+                              lengths: *mut i64, status: *mut i32) -> c_int;
+    pub fn p2v_from_newick_host(newick: *const c_char, in_stride: i64, b: i64, k: i64, v: *mut c_void, idx_bytes: c_int,
+                                status: *mut i32) -> c_int;
     // device-pointer entry points (asynchronous on `stream`, caller-owned buffers)
     pub fn p2v_decode_workspace_bytes(b: i64, k: i64) -> usize;
     pub fn p2v_to_ancestry_batch(v: *const c_void, idx_bytes: c_int, b: i64, k: i64, out: *mut c_void, status: *mut i32,
@@ -118,4 +123,36 @@ pub fn get_node_depths(v: &[usize]) -> Vec<f64> {
     };
     check(rc, status, v);
     out
+}
+
+/// Drop-in for `phylo2vec::vector::convert::to_newick` (convert.rs:394-397).
+pub fn to_newick(v: &[usize]) -> String {
+    let k = v.len();
+    let stride = unsafe { p2v_newick_max_bytes(k as i64) };
+    let mut buf = vec![0u8; stride];
+    let (mut len, mut status) = (0i64, 0i32);
+    let rc = unsafe {
+        p2v_to_newick_host(v.as_ptr().cast(), 8, 1, k as i64, buf.as_mut_ptr().cast(), stride as i64, &mut len, &mut status)
+    };
+    check(rc, status, v);
+    buf.truncate(len as usize);
+    String::from_utf8(buf).expect("ASCII")
+}
+
+/// Drop-in for `phylo2vec::vector::convert::from_newick` (convert.rs:268-278), with or without
+/// parent labels.  Panics on a malformed string like the reference's `expect("failed to get cherries")`.
+pub fn from_newick(newick: &str) -> Vec<usize> {
+    let k = newick.bytes().filter(|&c| c == b',').count();
+    let mut v = vec![0usize; k];
+    if k == 0 {
+        return v;
+    }
+    let c = std::ffi::CString::new(newick).expect("NUL inside the Newick string");
+    let mut status = 0i32;
+    let rc = unsafe {
+        p2v_from_newick_host(c.as_ptr(), (newick.len() + 1) as i64, 1, k as i64, v.as_mut_ptr().cast(), 8, &mut status)
+    };
+    check(rc, 0, &v);
+    assert!(status == 0, "failed to get cherries");
+    v
 }

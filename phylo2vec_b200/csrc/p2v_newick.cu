@@ -237,6 +237,148 @@ newick_kernel(const int* __restrict__ anc_all, int64_t B, int k, char* __restric
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// k <= 1023: one warp per tree, no block-wide barrier.  S(u) = "(" S(c1) "," S(c2) ")" u, so with
+// len[u] = bytes of S(u) and off[u] = where S(u) starts, every internal node places its own tokens
+// and the labels of its leaf children:
+//   1. bottom-up over the ancestry rows, 32 at a time: len[u] = 3 + len[c1] + len[c2] + digits(u);
+//      a child that is a row of the same batch is picked up with a shuffle once it is known
+//      (rounds = dependency depth inside the batch); every internal child records its parent row;
+//   2. top-down, 32 rows at a time from the root: off[u] = off[parent] + 1 (first child) or
+//      + 2 + len[c1(parent)]; parents inside the batch are followed by pointer doubling
+//      (5 shuffle rounds, whatever the shape);
+//   3. tokens; the string is assembled in shared memory and copied out with 128-bit stores.
+// Input: the first two ancestry columns as int32 (MODE_ANC2).  Per tree: children (2 x uint16 per
+// row), len, off and parent (uint16 per row), the string: 21 KB at n = 1000.
+// --------------------------------------------------------------------------------------------
+constexpr int NWW_K_MAX = 1023;
+__host__ __device__ inline size_t newick_warp_bytes(int k) {
+    return nw_al16(4 * (size_t)k) + 3 * nw_al16(2 * (size_t)k) + nw_al16(newick_bytes(k) + 2);
+}
+
+__device__ __forceinline__ void put_dec4(char* p, unsigned x, int digits) {      // x < 10000
+    const unsigned a = x / 10u, b = a / 10u, c = b / 10u;
+    const char d0 = (char)('0' + (x - a * 10u)), d1 = (char)('0' + (a - b * 10u)), d2 = (char)('0' + (b - c * 10u)),
+               d3 = (char)('0' + c);
+    if (digits == 1) { p[0] = d0; }
+    else if (digits == 2) { p[0] = d1; p[1] = d0; }
+    else if (digits == 3) { p[0] = d2; p[1] = d1; p[2] = d0; }
+    else { p[0] = d3; p[1] = d2; p[2] = d1; p[3] = d0; }
+}
+
+__global__ void __launch_bounds__(128)
+newick_warp_kernel(const int* __restrict__ anc_all, int64_t B, int k, char* __restrict__ out, int64_t out_stride,
+                   int64_t* __restrict__ lengths, const int32_t* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    unsigned char* mine = dyn + (size_t)warp * newick_warp_bytes(k);
+    const size_t tb = nw_al16(2 * (size_t)k);
+    uint32_t* ch = reinterpret_cast<uint32_t*>(mine);                                   // c1 | c2 << 16 of row r
+    uint16_t* len = reinterpret_cast<uint16_t*>(mine + nw_al16(4 * (size_t)k));         // by row
+    uint16_t* off = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(len) + tb);
+    uint16_t* par = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(off) + tb);   // parent row << 1 | second child
+    char* str = reinterpret_cast<char*>(reinterpret_cast<unsigned char*>(par) + tb);
+    const int nb = (k + 31) >> 5;
+
+    for (int64_t tree = (int64_t)blockIdx.x * nwarps + warp; tree < B; tree += (int64_t)gridDim.x * nwarps) {
+        if (status[tree] != 0) {                  // invalid vector, nothing decoded
+            if (lane == 0 && lengths) lengths[tree] = 0;
+            continue;
+        }
+        const int2* anc = reinterpret_cast<const int2*>(anc_all + (size_t)tree * 2 * k);
+        for (int r = lane; r < k; r += 32) {
+            const int2 x = anc[r];
+            ch[r] = (uint32_t)x.x | ((uint32_t)x.y << 16);
+        }
+        __syncwarp();
+        // ---- 1. len, bottom-up ---------------------------------------------------------------------
+        for (int b = 0; b < nb; ++b) {
+            const int base = b * 32, r = base + lane;
+            const bool act = r < k;
+            const uint32_t cc = act ? ch[r] : 0u;
+            const int c1 = (int)(cc & 0xFFFFu), c2 = (int)(cc >> 16);
+            const int r1 = c1 - k - 1, r2 = c2 - k - 1;             // child rows (negative: a leaf)
+            int l1 = 0, l2 = 0, d1 = -1, d2 = -1;                  // d: lane of a child row inside this batch
+            if (r1 < 0) l1 = dec_digits((unsigned)c1); else if (r1 < base) l1 = len[r1]; else d1 = r1 - base;
+            if (r2 < 0) l2 = dec_digits((unsigned)c2); else if (r2 < base) l2 = len[r2]; else d2 = r2 - base;
+            if (act && r1 >= 0) par[r1] = (uint16_t)(r << 1);
+            if (act && r2 >= 0) par[r2] = (uint16_t)((r << 1) | 1);
+            const int own = 3 + dec_digits((unsigned)(k + 1 + r));
+            int mylen = act ? 0 : 1;                                // 0 = not known yet
+            for (;;) {
+                if (mylen == 0 && (d1 & d2) < 0) mylen = own + l1 + l2;
+                if (__all_sync(FULL, mylen != 0)) break;
+                const int v1 = __shfl_sync(FULL, mylen, d1), v2 = __shfl_sync(FULL, mylen, d2);
+                if (d1 >= 0 && v1) { l1 = v1; d1 = -1; }
+                if (d2 >= 0 && v2) { l2 = v2; d2 = -1; }
+            }
+            if (act) len[r] = (uint16_t)mylen;
+            __syncwarp();
+        }
+        const uint32_t total = len[k - 1];
+        // ---- 2. off, top-down ------------------------------------------------------------------------
+        for (int b = nb - 1; b >= 0; --b) {
+            const int base = b * 32, r = base + lane;
+            const bool act = r < k;
+            uint32_t acc = 0;
+            int ptr = lane;                       // lane of the parent row while it is inside the batch and not final
+            bool fin = true;
+            if (act && r != k - 1) {
+                const uint32_t p = par[r];
+                const int pr = (int)(p >> 1);
+                uint32_t delta = 1;
+                if (p & 1u) {
+                    const int pc1 = (int)(ch[pr] & 0xFFFFu);
+                    delta = 2u + (pc1 <= k ? (uint32_t)dec_digits((unsigned)pc1) : (uint32_t)len[pc1 - k - 1]);
+                }
+                acc = delta;
+                if (pr >= base + 32) acc += off[pr];               // a later batch: final
+                else { ptr = pr - base; fin = false; }
+            }
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                const uint32_t a = __shfl_sync(FULL, acc | (fin ? 0x80000000u : 0u), ptr);     // offsets are below 2^16
+                const int pp = __shfl_sync(FULL, ptr, ptr);
+                if (!fin) { acc += a & 0x7FFFFFFFu; fin = (a >> 31) != 0u; ptr = pp; }
+            }
+            if (act) off[r] = (uint16_t)acc;
+            __syncwarp();
+        }
+        // ---- 3. tokens -----------------------------------------------------------------------------------
+        for (int r = lane; r < k; r += 32) {
+            const uint32_t cc = ch[r];
+            const int c1 = (int)(cc & 0xFFFFu), c2 = (int)(cc >> 16);
+            const uint32_t o = off[r];
+            uint32_t l1, l2;
+            str[o] = '(';
+            if (c1 <= k) { l1 = (uint32_t)dec_digits((unsigned)c1); put_dec4(str + o + 1, (unsigned)c1, (int)l1); }
+            else l1 = len[c1 - k - 1];
+            str[o + 1 + l1] = ',';
+            if (c2 <= k) { l2 = (uint32_t)dec_digits((unsigned)c2); put_dec4(str + o + 2 + l1, (unsigned)c2, (int)l2); }
+            else l2 = len[c2 - k - 1];
+            const uint32_t p = o + 2 + l1 + l2;
+            str[p] = ')';
+            const unsigned u = (unsigned)(k + 1 + r);
+            put_dec4(str + p + 1, u, dec_digits(u));
+        }
+        if (lane == 0) { str[total] = ';'; str[total + 1] = 0; }
+        __syncwarp();
+        // ---- copy out (the row is out_stride bytes; bytes past the NUL are left untouched) --------
+        char* o = out + tree * out_stride;
+        const uint32_t nbytes = total + 2;
+        if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+            const uint32_t nvec = nbytes >> 4;
+            for (uint32_t i = lane; i < nvec; i += 32)
+                reinterpret_cast<uint4*>(o)[i] = reinterpret_cast<const uint4*>(str)[i];
+            for (uint32_t i = (nvec << 4) + lane; i < nbytes; i += 32) o[i] = str[i];
+        } else {
+            for (uint32_t i = lane; i < nbytes; i += 32) o[i] = str[i];
+        }
+        if (lane == 0 && lengths) lengths[tree] = (int64_t)total + 1;
+        __syncwarp();
+    }
+}
+
 size_t newick_max_bytes(int64_t k) { return k < 0 ? 0 : newick_bytes(k) + 1; }
 
 // CTAs of the workspace variant (each owns a slice of tables)
@@ -282,9 +424,31 @@ cudaError_t launch_to_newick(const void* v, int idx_bytes, int64_t B, int64_t k,
     } else if (idx_bytes != 4) {
         return cudaErrorInvalidValue;
     }
-    e = launch_decode(MODE_ANCESTRY, vin, 4, B, k, anc, st, W.dec_bytes ? wsb + W.dec : nullptr, W.dec_bytes, stream, 0);
+    e = launch_decode(k <= NWW_K_MAX ? MODE_ANC2 : MODE_ANCESTRY, vin, 4, B, k, anc, st, W.dec_bytes ? wsb + W.dec : nullptr,
+                      W.dec_bytes, stream, 0);
     if (e != cudaSuccess) return e;
-    if (newick_fits_smem(k)) {
+    if (k <= NWW_K_MAX) {
+        // warps (= trees in flight) per CTA: enough small CTAs to fill the SM's warp slots
+        const size_t per = newick_warp_bytes((int)k);
+        int wpc = 1, best = 0;
+        for (int w = 4; w >= 1; w >>= 1) {
+            if (per * w > NW_SMEM_MAX) continue;
+            size_t ctas = ((size_t)228 * 1024) / (per * w + 1024);
+            if (ctas > 32) ctas = 32;
+            if (ctas > (size_t)(64 / w)) ctas = 64 / w;
+            if ((int)ctas * w > best) { best = (int)ctas * w; wpc = w; }
+        }
+        const size_t smem = per * wpc;
+        e = cudaFuncSetAttribute(newick_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, newick_warp_kernel, wpc * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        const int64_t cap = (int64_t)sm_count() * per_sm;
+        const int64_t want = (B + wpc - 1) / wpc;
+        newick_warp_kernel<<<(int)(want < cap ? want : cap), wpc * 32, smem, stream>>>(anc, B, (int)k, out, out_stride, lengths, st);
+    } else if (newick_fits_smem(k)) {
         const size_t smem = newick_layout(k, 2).total;
         e = cudaFuncSetAttribute(newick_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

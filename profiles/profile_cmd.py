@@ -5,6 +5,7 @@
     python profiles/profile_cmd.py rows      # cophenetic rows, n=65536, rows [0,8192), fp64 + topological
     python profiles/profile_cmd.py rowsfull  # the same with all 65536 rows (34 GB)
     python profiles/profile_cmd.py encode    # from_ancestry, 131072 trees
+    python profiles/profile_cmd.py newick    # to_newick + from_newick, 32768 trees of n=1000
 """
 import os
 import sys
@@ -27,6 +28,15 @@ if what in ("decode", "encode"):
     if what == "encode":
         for _ in range(3):
             p2v.from_ancestry_batch(anc, check=False)
+elif what == "newick":
+    # to_newick and from_newick, 32768 trees of n=1000
+    B, k = 32768, 999
+    hi = (2 * torch.arange(k, device=dev) + 1).to(torch.float64)
+    V = (torch.rand((B, k), generator=g, device=dev, dtype=torch.float64) * hi).to(torch.int64)
+    for _ in range(2):
+        buf, ln = p2v.to_newick_batch(V, raw=True)
+    for _ in range(2):
+        p2v.from_newick_batch(buf, lengths=ln, n_leaves=k + 1)
 elif what.startswith("cophsmall"):
     # small trees (BASELINE config C1 shape n=100): which kernel of the distance path costs what
     n = int(what[9:] or 100)
