@@ -304,13 +304,27 @@ newick_warp_kernel(const int* __restrict__ anc_all, int64_t B, int k, char* __re
             if (act && r1 >= 0) par[r1] = (uint16_t)(r << 1);
             if (act && r2 >= 0) par[r2] = (uint16_t)((r << 1) | 1);
             const int own = 3 + dec_digits((unsigned)(k + 1 + r));
-            int mylen = act ? 0 : 1;                                // 0 = not known yet
+            // Rows hanging off one another form chains inside the batch (the usual case: a row
+            // continues the subtree of the row before it).  A row with one open child follows that
+            // link; a chain is summed by pointer doubling in one round, so the number of rounds is the
+            // nesting depth through rows with two open children, not the length of the chains.
+            uint32_t mylen = act ? 0u : 1u;                         // 0 = not known yet
             for (;;) {
-                if (mylen == 0 && (d1 & d2) < 0) mylen = own + l1 + l2;
-                if (__all_sync(FULL, mylen != 0)) break;
-                const int v1 = __shfl_sync(FULL, mylen, d1), v2 = __shfl_sync(FULL, mylen, d2);
-                if (d1 >= 0 && v1) { l1 = v1; d1 = -1; }
-                if (d2 >= 0 && v2) { l2 = v2; d2 = -1; }
+                const bool one = mylen == 0u && ((d1 ^ d2) < 0);    // exactly one child still open
+                uint32_t acc = mylen ? mylen : (uint32_t)(own + l1 + l2);      // open children count 0 so far
+                bool fin = mylen != 0u || (d1 & d2) < 0;
+                int ptr = one ? (d1 >= 0 ? d1 : d2) : lane;         // two open children: the row blocks its chain
+#pragma unroll
+                for (int it = 0; it < 5; ++it) {
+                    const uint32_t a = __shfl_sync(FULL, acc | (fin ? 0x80000000u : 0u), ptr);
+                    const int pp = __shfl_sync(FULL, ptr, ptr);
+                    if (!fin && ptr != lane) { acc += a & 0x7FFFFFFFu; fin = (a >> 31) != 0u; ptr = pp; }
+                }
+                if (fin) mylen = acc;
+                if (__all_sync(FULL, mylen != 0u)) break;
+                const uint32_t v1 = __shfl_sync(FULL, mylen, d1), v2 = __shfl_sync(FULL, mylen, d2);
+                if (d1 >= 0 && v1) { l1 = (int)v1; d1 = -1; }
+                if (d2 >= 0 && v2) { l2 = (int)v2; d2 = -1; }
             }
             if (act) len[r] = (uint16_t)mylen;
             __syncwarp();
