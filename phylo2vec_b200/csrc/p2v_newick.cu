@@ -694,6 +694,190 @@ newick_parse_kernel(const char* __restrict__ in, int64_t in_stride, const int64_
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// k <= 1023 and 16-byte aligned rows: one warp per tree, no block-wide barrier, the string is
+// read straight from global memory, 512 bytes per step (one 128-bit load per lane).
+//   * every lane classifies its 16 characters into bit masks (")", start of a leaf token, digit);
+//     a warp scan of the packed (nodes, leaves) counts gives its first node number and stack
+//     height; it then walks its characters once more: stack height after every node, and the
+//     value of every digit run that ends inside its piece;
+//   * a digit run that touches the end of a lane's piece is finished by the next lane (labels have
+//     at most 8 digits, so a run spans at most two pieces);
+//   * a node is internal iff the stack height drops at it, so only values are stored (uint16).
+// The sweep over the nodes is the one of newick_parse_kernel with uint16 tables: 10 KB per tree.
+// --------------------------------------------------------------------------------------------
+constexpr uint32_t NPW_NONE = 0xFFFFu;            // ")" without a label
+__host__ __device__ inline size_t parse_warp_bytes(int k) {
+    return 2 * nw_al16(2 * (2 * (size_t)k + 1)) + nw_al16(2 * ((size_t)k + 3));
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(128)
+newick_parse_warp_kernel(const char* __restrict__ in, int64_t in_stride, const int64_t* __restrict__ lengths, int64_t B, int k,
+                         OutT* __restrict__ edges, int32_t* __restrict__ pstatus, int maxlen) {
+    extern __shared__ __align__(16) unsigned char dyn[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int N = 2 * k + 1;
+    unsigned char* mine = dyn + (size_t)warp * parse_warp_bytes(k);
+    uint16_t* lab = reinterpret_cast<uint16_t*>(mine);                                   // label value by node
+    uint16_t* sh = reinterpret_cast<uint16_t*>(mine + nw_al16(2 * (size_t)N));           // stack height after the node
+    uint16_t* last = reinterpret_cast<uint16_t*>(mine + 2 * nw_al16(2 * (size_t)N));     // latest node of height h
+
+    for (int64_t tree = (int64_t)blockIdx.x * nwarps + warp; tree < B; tree += (int64_t)gridDim.x * nwarps) {
+        const char* src = in + tree * in_stride;
+        OutT* erow = edges + (size_t)tree * 4 * (size_t)k;
+        const int chunks = (int)((in_stride < (int64_t)maxlen + 16 ? in_stride : (int64_t)maxlen + 16) >> 4);   // readable 16-byte pieces
+        int len = 0;
+        if (lengths) {
+            const int64_t l64 = lengths[tree];
+            len = (l64 < 1 || l64 > maxlen || l64 > in_stride) ? 0 : (int)l64;
+        } else {                                  // NUL-terminated inside the row
+            for (int c0 = 0; c0 < chunks; c0 += 32) {
+                const int c = c0 + lane;
+                uint4 w = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+                if (c < chunks) w = reinterpret_cast<const uint4*>(src)[c];
+                int z = 16;                       // first zero byte of the piece
+                const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int q = 3; q >= 0; --q)
+#pragma unroll
+                    for (int j = 3; j >= 0; --j) if (((ws[q] >> (8 * j)) & 0xFFu) == 0u) z = 4 * q + j;
+                const uint32_t m = __ballot_sync(FULL, z < 16);
+                if (m) {
+                    const int l0 = __ffs(m) - 1;
+                    const int p = (c0 + l0) * 16 + __shfl_sync(FULL, z, l0);
+                    len = (p < 1 || p > maxlen) ? 0 : p;
+                    break;
+                }
+            }
+        }
+        int bad = (len == 0) ? 1 : 0;
+        // ---- tokens --------------------------------------------------------------------------------
+        int carry_idx = 0, carry_S = 0;
+        uint32_t carry_prev = 0, carry_tail = 0;                    // tail: value << 4 | digits
+        for (int pos = 0; pos < len; pos += 512) {
+            const int p0 = pos + lane * 16;
+            uint4 w = make_uint4(0, 0, 0, 0);
+            if (p0 < len) w = reinterpret_cast<const uint4*>(src)[p0 >> 4];
+            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+            uint32_t prev = __shfl_up_sync(FULL, ws[3] >> 24, 1);
+            if (lane == 0) prev = carry_prev;
+            uint32_t mclose = 0, mleaf = 0, mdig = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t c = (ws[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                const bool valid = p0 + j < len;
+                const bool isclose = c == ')', isdig = (c - '0') <= 9u, issep = (c == '(') | (c == ',');
+                const bool pdig = (prev - '0') <= 9u, psep = (prev == '(') | (prev == ','), pclose = prev == ')';
+                if (valid) {
+                    if (!(isclose | isdig | issep | (c == ';'))) bad = 1;
+                    if (c == ';' && p0 + j != len - 1) bad = 1;
+                    if (isdig && !(pdig | psep | pclose)) bad = 1;
+                    mclose |= (uint32_t)isclose << j;
+                    mleaf |= (uint32_t)(isdig & psep) << j;
+                    mdig |= (uint32_t)isdig << j;
+                }
+                prev = c;
+            }
+            if (p0 + 15 == len - 1 && prev != ';') bad = 1;        // node_substr needs the ";"
+            if (p0 < len && p0 + 15 > len - 1 && ((ws[(len - 1 - p0) >> 2] >> (8 * ((len - 1 - p0) & 3))) & 0xFFu) != ';') bad = 1;
+            const int ncl = __popc(mclose), nlf = __popc(mleaf);
+            uint32_t sc = (uint32_t)(ncl + nlf) | ((uint32_t)nlf << 16);                // inclusive scan of (nodes, leaves)
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(FULL, sc, d); if (lane >= d) sc += y; }
+            const uint32_t tot = __shfl_sync(FULL, sc, 31);
+            const uint32_t ex = sc - ((uint32_t)(ncl + nlf) | ((uint32_t)nlf << 16));
+            int idx = carry_idx + (int)(ex & 0xFFFFu);
+            int S = carry_S + 2 * (int)(ex >> 16) - (int)(ex & 0xFFFFu);
+            const int idx0 = idx;
+            // second walk: heights, and the digit runs that end inside this piece
+            uint32_t val = 0, nd = 0, headval = 0, headlen = 0;
+            bool inhead = (mdig & 1u) && !(mleaf & 1u);              // the piece starts inside a run
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t c = (ws[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                const bool isdig = (mdig >> j) & 1u;
+                if (!isdig) {                     // a run ends before this character: it belongs to the latest node
+                    if (inhead) { headval = val; headlen = nd; inhead = false; }
+                    else if (nd) {
+                        if (nd > 8) bad = 1;
+                        if (idx - 1 < N) lab[idx - 1] = (uint16_t)(val > 0xFFFEu ? 0xFFFEu : val);
+                    }
+                    val = 0; nd = 0;
+                }
+                if ((mleaf >> j) & 1u) { ++S; if (idx < N) sh[idx] = (uint16_t)S; ++idx; }
+                if ((mclose >> j) & 1u) {
+                    --S;
+                    if (S < 1) bad = 1;
+                    if (idx < N) { sh[idx] = (uint16_t)S; lab[idx] = (uint16_t)NPW_NONE; }
+                    ++idx;
+                }
+                if (isdig) { val = val * 10u + (c - '0'); ++nd; }
+            }
+            if (inhead) bad = 1;                                       // 16 digits in a row
+            if (nd > 8) bad = 1;
+            const uint32_t tail = nd ? ((val << 4) | nd) : 0u;         // a run touching the end of the piece (<= 8 digits: 27 + 4 bits)
+            __syncwarp();
+            // runs that started in the piece before this one
+            uint32_t ptail = __shfl_up_sync(FULL, tail, 1);
+            if (lane == 0) ptail = carry_tail;
+            if (ptail | headlen) {
+                const uint32_t pv = ptail >> 4, pn = ptail & 15u;
+                if (pn + headlen > 8) bad = 1;
+                uint32_t total = pv;
+                for (uint32_t q = 0; q < headlen; ++q) total *= 10u;
+                total += headval;
+                if (idx0 >= 1 && idx0 - 1 < N) lab[idx0 - 1] = (uint16_t)(total > 0xFFFEu ? 0xFFFEu : total);
+                else bad = 1;
+            }
+            carry_idx += (int)(tot & 0xFFFFu);
+            carry_S += 2 * (int)(tot >> 16) - (int)(tot & 0xFFFFu);
+            carry_prev = __shfl_sync(FULL, ws[3] >> 24, 31);
+            carry_tail = __shfl_sync(FULL, tail, 31);
+        }
+        if (carry_idx != N || carry_S != 1) bad = 1;
+        __syncwarp();
+        if (__any_sync(FULL, bad)) {
+            if (lane == 0) { pstatus[tree] = NP_MALFORMED; erow[0] = (OutT)-1; erow[1] = (OutT)-1; }
+            continue;
+        }
+        // ---- children of every internal node, 32 nodes at a time -----------------------------------------
+        int verdict = 0;                          // bit 0: malformed label, bit 1: ")" without a label
+        int carryS = 0;
+        for (int base = 0; base < N; base += 32) {
+            const int node = base + lane;
+            const bool act = node < N;
+            const int Sv = act ? (int)sh[node] : -1 - lane;
+            int Sp = __shfl_up_sync(FULL, Sv, 1);
+            if (lane == 0) Sp = carryS;
+            carryS = __shfl_sync(FULL, Sv, 31);
+            const bool internal = act && Sv < Sp;
+            const uint32_t lb = act ? (uint32_t)lab[node] : 0u;
+            const uint32_t peers = __match_any_sync(FULL, Sv);
+            if (act && !internal && lb > (uint32_t)k) verdict |= 1;
+            if (internal) {
+                if (lb == NPW_NONE) verdict |= 2; else if (lb > 2u * (uint32_t)k) verdict |= 1;
+                const uint32_t lower = peers & lanes_lt(lane);
+                const int j = lower ? base + 31 - __clz(lower) : (int)last[Sv];
+                const uint32_t c1 = lab[j], c2 = lab[node - 1];
+                const int r = ((node + 1 - Sv) >> 1) - 1;            // internal nodes before this one
+                OutT* o = erow + 4 * (size_t)r;
+                o[0] = (OutT)c1; o[1] = (OutT)lb; o[2] = (OutT)c2; o[3] = (OutT)lb;
+            }
+            __syncwarp();
+            if (act && (peers & lanes_gt(lane)) == 0) last[Sv] = (uint16_t)node;
+            __syncwarp();
+        }
+        const uint32_t anym = __ballot_sync(FULL, verdict & 1), anyn = __ballot_sync(FULL, verdict & 2);
+        if (lane == 0) {
+            const int v = anym ? NP_MALFORMED : (anyn ? NP_NOPARENTS : 0);
+            pstatus[tree] = v;
+            if (v) { erow[0] = (OutT)-1; erow[1] = (OutT)-1; }
+        }
+        __syncwarp();
+    }
+}
+
 // Trees the first kernel marked NP_NOPARENTS.
 template <typename OutT, bool STAGED>
 __global__ void __launch_bounds__(NW_THREADS_MAX)
@@ -887,7 +1071,26 @@ static cudaError_t launch_parse_t(const char* in, int64_t in_stride, const int64
     const int maxlen = (int)newick_bytes(k);
     for (int pass = 0; pass < 2; ++pass) {        // 0: strings with parent labels, 1: the trees pass 0 left as NP_NOPARENTS
         const bool np = pass == 1;
-        if (parse_fits_smem(k, np)) {
+        if (!np && k <= NWW_K_MAX && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (in_stride & 15) == 0) {
+            const size_t per = parse_warp_bytes((int)k);
+            int wpc = 1, best = 0;
+            for (int w = 4; w >= 1; w >>= 1) {
+                size_t ctas = ((size_t)228 * 1024) / (per * w + 1024);
+                if (ctas > 32) ctas = 32;
+                if (ctas > (size_t)(64 / w)) ctas = 64 / w;
+                if ((int)ctas * w > best) { best = (int)ctas * w; wpc = w; }
+            }
+            const size_t smem = per * wpc;
+            auto kern = newick_parse_warp_kernel<OutT>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            int per_sm = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpc * 32, smem);
+            if (e != cudaSuccess) return e;
+            if (per_sm < 1) per_sm = 1;
+            const int64_t cap = (int64_t)sm_count() * per_sm, want = (B + wpc - 1) / wpc;
+            kern<<<(int)(want < cap ? want : cap), wpc * 32, smem, stream>>>(in, in_stride, lengths, B, (int)k, edges, pst, maxlen);
+        } else if (parse_fits_smem(k, np)) {
             const size_t smem = parse_layout(k, true, np).total;
             auto kern = np ? newick_parse_np_kernel<OutT, true> : newick_parse_kernel<OutT, true>;
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
