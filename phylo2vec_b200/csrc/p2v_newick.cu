@@ -19,10 +19,10 @@
 //      its byte offset;
 //   4. leaves write [","] "(((" label, internal nodes write ")" label, the string is assembled in
 //      shared memory and copied out with coalesced stores.
-// Sizes: while the tables fit in shared memory (k <= 3200 or so) they are uint16 and the string is
-// assembled in shared memory; larger trees run the same code with uint32 tables in a per-CTA slice
-// of the workspace (L2 resident), 1024 threads, and write their tokens straight into the output
-// row.  The matrix form (branch lengths need the reference's shortest-round-trip float
+// Sizes: this CTA-per-tree kernel serves k > 4095 with uint32 tables in a per-CTA slice of the
+// workspace (L2 resident), 1024 threads, tokens written straight into the output row (the uint16 /
+// shared-memory instantiation of the template was the first version for small trees); k <= 4095
+// runs newick_warp_kernel below.  The matrix form (branch lengths need the reference's shortest-round-trip float
 // formatting) is not built: P2V_ERR_UNSUPPORTED.
 #include <cstdlib>
 
@@ -76,11 +76,6 @@ __host__ __device__ inline NewickLayout newick_layout(int64_t k, size_t es) {
     L.total = o;
     return L;
 }
-// shared-memory variant: the tables fit and every byte offset fits uint16
-static bool newick_fits_smem(int64_t k) {
-    return k <= 4000 && newick_bytes(k) + 2 < 65535 && newick_layout(k, 2).total <= NW_SMEM_MAX;
-}
-
 __device__ __forceinline__ void put_dec(char* p, unsigned x, int digits) {
     for (int i = digits - 1; i >= 0; --i) { p[i] = (char)('0' + x % 10u); x /= 10u; }
 }
@@ -238,7 +233,7 @@ newick_kernel(const int* __restrict__ anc_all, int64_t B, int k, char* __restric
 }
 
 // --------------------------------------------------------------------------------------------
-// k <= 1023: one warp per tree, no block-wide barrier.  S(u) = "(" S(c1) "," S(c2) ")" u, so with
+// k <= 4095: one warp per tree, no block-wide barrier.  S(u) = "(" S(c1) "," S(c2) ")" u, so with
 // len[u] = bytes of S(u) and off[u] = where S(u) starts, every internal node places its own tokens
 // and the labels of its leaf children:
 //   1. bottom-up over the ancestry rows, 32 at a time: len[u] = 3 + len[c1] + len[c2] + digits(u);
@@ -251,7 +246,7 @@ newick_kernel(const int* __restrict__ anc_all, int64_t B, int k, char* __restric
 // Input: the first two ancestry columns as int32 (MODE_ANC2).  Per tree: children (2 x uint16 per
 // row), len, off and parent (uint16 per row), the string: 21 KB at n = 1000.
 // --------------------------------------------------------------------------------------------
-constexpr int NWW_K_MAX = 1023;
+constexpr int NWW_K_MAX = 4095;
 __host__ __device__ inline size_t newick_warp_bytes(int k) {
     return nw_al16(4 * (size_t)k) + 3 * nw_al16(2 * (size_t)k) + nw_al16(newick_bytes(k) + 2);
 }
@@ -412,7 +407,7 @@ static NewickWs newick_ws(int64_t B, int64_t k) {
     w.anc = o; o = nw_al16(o + 12 * (size_t)B * (size_t)k);
     w.dec_bytes = decode_workspace_bytes(B, k);
     w.dec = o; o = nw_al16(o + w.dec_bytes);
-    w.tables_stride = newick_fits_smem(k) ? 0 : nw_al16(newick_layout(k, 4).total);
+    w.tables_stride = k <= NWW_K_MAX ? 0 : nw_al16(newick_layout(k, 4).total);
     w.tables = o; o = nw_al16(o + w.tables_stride * (size_t)newick_teams(B, k));
     w.total = o;
     return w;
@@ -462,20 +457,6 @@ cudaError_t launch_to_newick(const void* v, int idx_bytes, int64_t B, int64_t k,
         const int64_t cap = (int64_t)sm_count() * per_sm;
         const int64_t want = (B + wpc - 1) / wpc;
         newick_warp_kernel<<<(int)(want < cap ? want : cap), wpc * 32, smem, stream>>>(anc, B, (int)k, out, out_stride, lengths, st);
-    } else if (newick_fits_smem(k)) {
-        const size_t smem = newick_layout(k, 2).total;
-        e = cudaFuncSetAttribute(newick_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        // measured at n = 100: 32-thread CTAs are no faster than 128 (32 CTAs/SM cap); big trees
-        // leave room for one or two CTAs per SM only and get more threads each
-        const int threads = k <= 1023 ? 128 : (k <= 2047 ? 256 : 512);
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, newick_kernel<uint16_t>, threads, smem);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) per_sm = 1;
-        const int64_t cap = (int64_t)sm_count() * per_sm;
-        newick_kernel<uint16_t><<<(int)(B < cap ? B : cap), threads, smem, stream>>>(anc, B, (int)k, out, out_stride, lengths,
-                                                                                   st, nullptr, 0);
     } else {
         newick_kernel<uint32_t><<<(int)newick_teams(B, k), NW_THREADS_MAX, 0, stream>>>(
             anc, B, (int)k, out, out_stride, lengths, st, wsb + W.tables, W.tables_stride);
@@ -695,7 +676,7 @@ newick_parse_kernel(const char* __restrict__ in, int64_t in_stride, const int64_
 }
 
 // --------------------------------------------------------------------------------------------
-// k <= 1023 and 16-byte aligned rows: one warp per tree, no block-wide barrier, the string is
+// k <= 4095 and 16-byte aligned rows: one warp per tree, no block-wide barrier, the string is
 // read straight from global memory, 512 bytes per step (one 128-bit load per lane).
 //   * every lane classifies its 16 characters into bit masks (")", start of a leaf token, digit);
 //     a warp scan of the packed (nodes, leaves) counts gives its first node number and stack

@@ -41,8 +41,8 @@ def test_goldens_single_tree(p2v, goldens):
 
 
 SIZES = [2, 3, 4, 5, 9, 10, 11, 33, 64, 65, 99, 100, 101, 129, 500, 999, 1000, 1001, 1023, 1024]
-# shared-memory tables with 256 / 512 threads, then uint32 tables in the workspace
-BIG_SIZES = [1025, 2000, 2049, 3000, 3300, 5000, 9999, 10001, 20000]
+# warp-per-tree kernels up to k = 4095, then uint32 tables in the workspace
+BIG_SIZES = [1025, 2000, 2049, 3000, 4095, 4096, 4097, 5000, 9999, 10001, 20000]
 
 
 @pytest.mark.parametrize("n_leaves", SIZES)
