@@ -688,6 +688,36 @@ newick_parse_kernel(const char* __restrict__ in, int64_t in_stride, const int64_
 // The sweep over the nodes is the one of newick_parse_kernel with uint16 tables: 10 KB per tree.
 // --------------------------------------------------------------------------------------------
 constexpr uint32_t NPW_NONE = 0xFFFFu;            // ")" without a label
+// SWAR helpers on 4 characters in one word (byte 0 = first character)
+__device__ __forceinline__ uint32_t swar_zero(uint32_t v) {          // 0x80 in every byte of v that is zero
+    return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v | 0x7F7F7F7Fu);
+}
+__device__ __forceinline__ uint32_t swar_eq(uint32_t v, char c) { return swar_zero(v ^ (0x01010101u * (uint32_t)(unsigned char)c)); }
+__device__ __forceinline__ uint32_t swar_digit(uint32_t v) {         // 0x80 in every byte that is '0'..'9'
+    const uint32_t t = v ^ 0x30303030u;
+    return ~(((t & 0x7F7F7F7Fu) + 0x76767676u) | t | 0x7F7F7F7Fu);
+}
+__device__ __forceinline__ uint32_t swar_nibble(uint32_t f) {        // the four 0x80 flags as bits 0..3
+    return (((f >> 7) * 0x00204081u) >> 21) & 0xFu;
+}
+__device__ __forceinline__ uint32_t swar_parse4(uint32_t x) {        // four ASCII digits, first one in byte 0
+    x = ((x & 0x0F0F0F0Fu) * 2561u) >> 8;
+    return ((x & 0x00FF00FFu) * 6553601u) >> 16;
+}
+// value of the L (1..8) digits that start at byte a (0..15) of the 16-byte piece ws
+__device__ __forceinline__ uint32_t swar_value(const uint32_t (&ws)[4], int a, int L) {
+    const int q = a >> 2, r8 = (a & 3) * 8;
+    const uint32_t x0 = q == 0 ? ws[0] : (q == 1 ? ws[1] : (q == 2 ? ws[2] : ws[3]));
+    const uint32_t x1 = q == 0 ? ws[1] : (q == 1 ? ws[2] : (q == 2 ? ws[3] : 0u));
+    const uint32_t x2 = q == 0 ? ws[2] : (q == 1 ? ws[3] : 0u);
+    const uint32_t lo = __funnelshift_r(x0, x1, r8), hi = __funnelshift_r(x1, x2, r8);    // 8 bytes from a on
+    // left-align: the L digits become the last L of 8 characters, zero bytes (digit 0) in front
+    const int sl = 8 * (8 - L);
+    const uint32_t hi2 = sl >= 32 ? lo << (sl - 32) : __funnelshift_l(lo, hi, sl);
+    const uint32_t lo2 = sl >= 32 ? 0u : lo << sl;
+    return swar_parse4(lo2) * 10000u + swar_parse4(hi2);
+}
+
 __host__ __device__ inline size_t parse_warp_bytes(int k) {
     return 2 * nw_al16(2 * (2 * (size_t)k + 1)) + nw_al16(2 * ((size_t)k + 3));
 }
@@ -743,63 +773,71 @@ newick_parse_warp_kernel(const char* __restrict__ in, int64_t in_stride, const i
             const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
             uint32_t prev = __shfl_up_sync(FULL, ws[3] >> 24, 1);
             if (lane == 0) prev = carry_prev;
-            uint32_t mclose = 0, mleaf = 0, mdig = 0;
+            // character classes of the 16 bytes as bit masks (SWAR compares, 4 bytes at a time)
+            uint32_t mclose = 0, msep = 0, msemi = 0, mdig = 0;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const uint32_t c = (ws[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-                const bool valid = p0 + j < len;
-                const bool isclose = c == ')', isdig = (c - '0') <= 9u, issep = (c == '(') | (c == ',');
-                const bool pdig = (prev - '0') <= 9u, psep = (prev == '(') | (prev == ','), pclose = prev == ')';
-                if (valid) {
-                    if (!(isclose | isdig | issep | (c == ';'))) bad = 1;
-                    if (c == ';' && p0 + j != len - 1) bad = 1;
-                    if (isdig && !(pdig | psep | pclose)) bad = 1;
-                    mclose |= (uint32_t)isclose << j;
-                    mleaf |= (uint32_t)(isdig & psep) << j;
-                    mdig |= (uint32_t)isdig << j;
-                }
-                prev = c;
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t x = ws[q];
+                mclose |= swar_nibble(swar_eq(x, ')')) << (4 * q);
+                msep |= swar_nibble(swar_eq(x, '(') | swar_eq(x, ',')) << (4 * q);
+                msemi |= swar_nibble(swar_eq(x, ';')) << (4 * q);
+                mdig |= swar_nibble(swar_digit(x)) << (4 * q);
             }
-            if (p0 + 15 == len - 1 && prev != ';') bad = 1;        // node_substr needs the ";"
-            if (p0 < len && p0 + 15 > len - 1 && ((ws[(len - 1 - p0) >> 2] >> (8 * ((len - 1 - p0) & 3))) & 0xFFu) != ';') bad = 1;
+            const int left = len - p0;                               // valid characters from p0 on
+            const uint32_t vm = left >= 16 ? 0xFFFFu : (left > 0 ? (1u << left) - 1u : 0u);
+            if ((mclose | msep | msemi | mdig) != 0xFFFFu && ((mclose | msep | msemi | mdig) & vm) != vm) bad = 1;
+            mclose &= vm; msep &= vm; msemi &= vm; mdig &= vm;
+            const uint32_t lastbit = (left >= 1 && left <= 16) ? 1u << (left - 1) : 0u;     // the ";" closes the string
+            if (msemi != lastbit) bad = 1;
+            const uint32_t pdig = ((mdig << 1) | ((prev - '0') <= 9u ? 1u : 0u)) & 0xFFFFu;
+            const uint32_t psep = ((msep << 1) | ((prev == '(' || prev == ',') ? 1u : 0u)) & 0xFFFFu;
+            const uint32_t pclose = ((mclose << 1) | (prev == ')' ? 1u : 0u)) & 0xFFFFu;
+            if (mdig & ~(pdig | psep | pclose)) bad = 1;             // a digit after ";" or at the very start
+            const uint32_t mleaf = mdig & psep;
+            const uint32_t mnode = mclose | mleaf;
             const int ncl = __popc(mclose), nlf = __popc(mleaf);
             uint32_t sc = (uint32_t)(ncl + nlf) | ((uint32_t)nlf << 16);                // inclusive scan of (nodes, leaves)
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(FULL, sc, d); if (lane >= d) sc += y; }
             const uint32_t tot = __shfl_sync(FULL, sc, 31);
             const uint32_t ex = sc - ((uint32_t)(ncl + nlf) | ((uint32_t)nlf << 16));
-            int idx = carry_idx + (int)(ex & 0xFFFFu);
-            int S = carry_S + 2 * (int)(ex >> 16) - (int)(ex & 0xFFFFu);
-            const int idx0 = idx;
-            // second walk: heights, and the digit runs that end inside this piece
-            uint32_t val = 0, nd = 0, headval = 0, headlen = 0;
-            bool inhead = (mdig & 1u) && !(mleaf & 1u);              // the piece starts inside a run
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const uint32_t c = (ws[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-                const bool isdig = (mdig >> j) & 1u;
-                if (!isdig) {                     // a run ends before this character: it belongs to the latest node
-                    if (inhead) { headval = val; headlen = nd; inhead = false; }
-                    else if (nd) {
-                        if (nd > 8) bad = 1;
-                        if (idx - 1 < N) lab[idx - 1] = (uint16_t)(val > 0xFFFEu ? 0xFFFEu : val);
+            const int idx0 = carry_idx + (int)(ex & 0xFFFFu);
+            const int S0 = carry_S + 2 * (int)(ex >> 16) - (int)(ex & 0xFFFFu);
+            // the nodes of this piece, one per round: height after the node, and its label if the
+            // digits end inside the piece; digits touching the end are handed to the next lane
+            uint32_t tail = 0;
+            uint32_t mrem = mnode;
+            const int rounds = __reduce_max_sync(FULL, ncl + nlf);
+            for (int it = 0; it < rounds; ++it) {
+                if (mrem) {
+                    const int j = __ffs(mrem) - 1;
+                    mrem &= mrem - 1;
+                    const uint32_t upto = (2u << j) - 1u;
+                    const int nidx = idx0 + __popc(mnode & (upto >> 1));
+                    const int Sj = S0 + __popc(mleaf & upto) - __popc(mclose & upto);
+                    const bool isclose = (mclose >> j) & 1u;
+                    if (Sj < 1) bad = 1;
+                    const int a0 = j + (isclose ? 1 : 0);            // where the node's digits start
+                    const int L = __ffs(~(mdig >> a0)) - 1;          // mdig has 16 bits: L <= 16 - a0
+                    uint32_t v = isclose ? NPW_NONE : 0u;
+                    if (L > 0) {
+                        if (L > 8) bad = 1;
+                        const uint32_t val = swar_value(ws, a0, L);
+                        if (a0 + L == 16) tail = (val << 4) | (uint32_t)L;
+                        else v = val > 0xFFFEu ? 0xFFFEu : val;
                     }
-                    val = 0; nd = 0;
+                    if (nidx < N) { sh[nidx] = (uint16_t)Sj; lab[nidx] = (uint16_t)v; }
+                    else bad = 1;
                 }
-                if ((mleaf >> j) & 1u) { ++S; if (idx < N) sh[idx] = (uint16_t)S; ++idx; }
-                if ((mclose >> j) & 1u) {
-                    --S;
-                    if (S < 1) bad = 1;
-                    if (idx < N) { sh[idx] = (uint16_t)S; lab[idx] = (uint16_t)NPW_NONE; }
-                    ++idx;
-                }
-                if (isdig) { val = val * 10u + (c - '0'); ++nd; }
             }
-            if (inhead) bad = 1;                                       // 16 digits in a row
-            if (nd > 8) bad = 1;
-            const uint32_t tail = nd ? ((val << 4) | nd) : 0u;         // a run touching the end of the piece (<= 8 digits: 27 + 4 bits)
+            // a piece that starts inside a run (a label continued from, or starting right after, the piece before)
+            uint32_t headval = 0, headlen = 0;
+            if ((mdig & 1u) && !(mleaf & 1u)) {
+                const int L0 = __ffs(~mdig) - 1;
+                if (L0 >= 16 || L0 > 8) bad = 1;
+                else { headlen = (uint32_t)L0; headval = swar_value(ws, 0, L0); }
+            }
             __syncwarp();
-            // runs that started in the piece before this one
             uint32_t ptail = __shfl_up_sync(FULL, tail, 1);
             if (lane == 0) ptail = carry_tail;
             if (ptail | headlen) {

@@ -137,6 +137,28 @@ def test_from_newick_goldens(p2v, goldens):
             from_newick(bad)
 
 
+def test_from_newick_batch_goldens_and_malformed(p2v, goldens):
+    """The same known answers and malformed strings through the batched entry point (16-byte aligned
+    rows: the warp-per-tree tokenizer), one string per call and all of one size in one call."""
+    for g in goldens["from_newick"]:
+        got = p2v.from_newick_batch([g["newick"]])
+        assert np.array_equal(got.cpu().numpy()[0], np.array(g["v"])), g["src"]
+    bad = ["((0,1)5,(2,3)4)6", "((0,1)5,(2,3)4)9;", "((0,1)5,(2,x)4)6;", "((0,1)5,2,3)6;", "((0,1)5,(2,2)4)6;",
+           "((0,1)5,(2,3)5)6;", "((0,1)5;(2,3)4)6;", "((0,1)5,(2,3)4)6;;", "0,1)5,(2,3)4)6;", "((0,1)5,(2,3)4)123456789;",
+           "((0,1)5,(2,3)),6;", "((0 ,1)5,(2,3)4)6;", "((0,1)5,(7,3)4)6;"]
+    for b in bad:
+        with pytest.raises(ValueError):
+            p2v.from_newick_batch([b], n_leaves=4)
+    # leading zeros make a string longer than the canonical length of its size: rejected (the reference parses them)
+    bad.append("((00,1)5,(2,3)004)6;")
+    good = ["((0,1)5,(2,3)4)6;", "((0,1),(2,3));", "((0,2)5,(1,3)4)6;", "(0,1)5,(2,3)4)6;"]
+    status = torch.zeros(len(bad) + len(good), dtype=torch.int32, device="cuda")
+    got = p2v.from_newick_batch(bad + good, n_leaves=4, status=status, check=False).cpu().numpy()
+    st = status.cpu().numpy()
+    assert (st[:len(bad)] == -2).all() and not st[len(bad):].any()
+    assert np.array_equal(got[len(bad):], [[0, 2, 2], [0, 2, 2], [0, 0, 1], [0, 2, 2]])
+
+
 @pytest.mark.parametrize("n_leaves", SIZES)
 @pytest.mark.parametrize("dtype", [torch.int64, torch.int32])
 def test_from_newick_batch_parity(p2v, n_leaves, dtype):
