@@ -302,12 +302,12 @@ def run_b200(args):
         coph = bench_cophenetic(torch, lib, device, rank, world, peak, args)
     except Exception as exc:  # keep the headline line even if this part fails
         coph = {"error": repr(exc)}
-    newick = (None, None)
+    newick = (None, None, None)
     if rank == 0:
         try:
             newick = bench_newick(torch, lib, device, peak)
         except Exception as exc:
-            newick = ({"error": repr(exc)}, {"error": repr(exc)})
+            newick = ({"error": repr(exc)},) * 3
     if world > 1:
         gathered = [None] * world
         dist.all_gather_object(gathered, coph)
@@ -352,7 +352,7 @@ def run_b200(args):
                                  "third is k+1+row); host threads of the library widen them into the caller's int64 rows",
                     "api": "p2v_to_ancestry_host (C ABI, pinned host buffers)", "matches_device_path": e2e_ok},
             "gpu_launches": launches, "clocks": clocks, "parity_spot_check": parity,
-            "config_c2_other_functions": c2, "cophenetic": coph, "next_rows": {"to_newick": newick[0], "from_newick": newick[1]},
+            "config_c2_other_functions": c2, "cophenetic": coph, "next_rows": {"to_newick": newick[0], "from_newick": newick[1], "balance_indices": newick[2]},
         }
         print(json.dumps(line))
     if world > 1:
@@ -364,7 +364,7 @@ def bench_newick(torch, lib, device, peak):
     restatement on a bounded sample.  Bytes = v read + string bytes written."""
     import numpy as np
     from oracle import p2v_oracle as O
-    res, res2 = {}, {}
+    res, res2, res3 = {}, {}, {}
     for n, B in ((100, 1_000_000), (1000, 100_000)):
         k = n - 1
         g = torch.Generator(device=device).manual_seed(n)
@@ -429,8 +429,37 @@ def bench_newick(torch, lib, device, peak):
                          "cpu": {"sample": Bc, "trees_per_s": Bc / tc2, "cores": host_threads(), "kind": "port"},
                          "round_trip_equal": bool(torch.equal(back, V)) and not bool(st.any()),
                          "matches_cpu": bool(np.array_equal(refv, Vc)) and not bool(refst.any())}
-        del V, out, ws2, back
-    return res, res2
+        del out, ws2, back
+        # third row beyond the scope table, first half: Sackin / leaf-depth variance / B2 (bytes = v read + 24 written)
+        bal = torch.empty((B, 3), dtype=torch.float64, device=device)
+        need3 = int(lib.p2v_balance_workspace_bytes(B, k))
+        ws3 = torch.empty(max(need3, 16), dtype=torch.uint8, device=device)
+
+        def call3():
+            rc = lib.p2v_balance_batch(V.data_ptr(), 8, B, k, bal.data_ptr(), st.data_ptr(), ws3.data_ptr(), need3,
+                                       stream.cuda_stream)
+            assert rc == 0, lib.p2v_last_error()
+        for _ in range(3):
+            call3()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(5):
+            call3()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t3 = e0.elapsed_time(e1) / 5 * 1e-3
+        Bc3 = min(Bc, 2000)
+        t0 = time.perf_counter()
+        refb = np.stack([O.balance(v) for v in Vc[:Bc3]])
+        tc3 = time.perf_counter() - t0
+        gotb = bal[:Bc3].cpu().numpy()
+        nb3 = B * k * 8 + B * 24
+        res3[f"n{n}"] = {"batch": B, "trees_per_s": B / t3, "gbs": nb3 / t3 / 1e9, "frac_of_peak": nb3 / t3 / 1e9 / peak,
+                         "cpu": {"sample": Bc3, "trees_per_s": Bc3 / tc3, "cores": 1, "kind": "port"},
+                         "matches_cpu": bool(np.array_equal(gotb[:, :2], refb[:, :2])) and bool(
+                             np.all(np.abs(gotb[:, 2] - refb[:, 2]) <= 1e-12 * np.abs(refb[:, 2])))}
+        del V, ws3, bal
+    return res, res2, res3
 
 
 def bench_cophenetic(torch, lib, device, rank, world, peak, args):

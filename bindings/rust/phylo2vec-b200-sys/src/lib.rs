@@ -27,6 +27,7 @@ extern "C" {
                                status: *mut i32) -> c_int;
     pub fn p2v_node_depths_host(v_or_m: *const c_void, idx_bytes: c_int, bls: *const f64, b: i64, k: i64,
                                 out: *mut f64, status: *mut i32) -> c_int;
+    pub fn p2v_balance_host(v: *const c_void, idx_bytes: c_int, b: i64, k: i64, out: *mut f64, status: *mut i32) -> c_int;
     pub fn p2v_newick_max_bytes(k: i64) -> usize;
     pub fn p2v_to_newick_host(v: *const c_void, idx_bytes: c_int, b: i64, k: i64, out: *mut c_char, out_stride: i64,
                               lengths: *mut i64, status: *mut i32) -> c_int;
@@ -156,3 +157,16 @@ pub fn from_newick(newick: &str) -> Vec<usize> {
     assert!(status == 0, "failed to get cherries");
     v
 }
+
+fn balance(v: &[usize]) -> [f64; 3] {
+    let mut out = [0f64; 3];
+    let mut status = 0i32;
+    let rc = unsafe { p2v_balance_host(v.as_ptr().cast(), 8, 1, v.len() as i64, out.as_mut_ptr(), &mut status) };
+    check(rc, status, v);
+    out
+}
+
+/// Drop-ins for `phylo2vec::vector::balance::{sackin, leaf_depth_variance, b2}` (balance.rs:14-58).
+pub fn sackin(v: &[usize]) -> usize { balance(v)[0] as usize }
+pub fn leaf_depth_variance(v: &[usize]) -> f64 { balance(v)[1] }
+pub fn b2(v: &[usize]) -> f64 { balance(v)[2] }

@@ -144,6 +144,15 @@ int p2v_node_depths_batch(const void *v_or_matrix, int idx_bytes, const double *
                           double *out, int32_t *status, void *workspace, size_t workspace_bytes,
                           p2v_stream_t stream);
 
+/* ---- balance indices (third "next" row, first half) ------------------------------------------
+ * replaces vector::balance::sackin / leaf_depth_variance / b2 (phylo2vec/src/vector/balance.rs:14-58);
+ * PyO3 sackin, leaf_depth_variance, b2 (py-phylo2vec/src/lib.rs:311-325); Python
+ * phylo2vec.stats.balance.  out (B,3) float64: [Sackin index, variance of the leaf depths, B2] of
+ * the topology of every vector. */
+size_t p2v_balance_workspace_bytes(int64_t B, int64_t k);
+int p2v_balance_batch(const void *v, int idx_bytes, int64_t B, int64_t k, double *out, int32_t *status,
+                      void *workspace, size_t workspace_bytes, p2v_stream_t stream);
+
 /* ---- to_newick (second "next" row; vectors only) ------------------------------------------
  * replaces vector::convert::to_newick / build_newick (vector/convert.rs:341-397); PyO3 entry
  * point to_newick, vector arm (py-phylo2vec/src/lib.rs:90-96); Python phylo2vec.base.newick.
@@ -195,6 +204,8 @@ int p2v_node_depths_host(const void *v_or_matrix, int idx_bytes, const double *b
 
 int p2v_to_newick_host(const void *v, int idx_bytes, int64_t B, int64_t k, char *out, int64_t out_stride,
                        int64_t *lengths, int32_t *status);
+
+int p2v_balance_host(const void *v, int idx_bytes, int64_t B, int64_t k, double *out, int32_t *status);
 
 /* NUL-terminated strings, one per in_stride bytes */
 int p2v_from_newick_host(const char *newick, int64_t in_stride, int64_t B, int64_t k, void *v, int idx_bytes,

@@ -721,6 +721,30 @@ i64 p2vo_to_newick(const i64 *v, i64 k, char *buf, i64 cap) {
 }
 
 /* ------------------------------------------------------------------------ */
+/* Balance indices (vector/balance.rs:14-58), literally: sums over the leaf    */
+/* depths of get_node_depths in leaf order.  out[0] = sackin (the reference    */
+/* casts the f64 sum to usize), out[1] = leaf_depth_variance, out[2] = b2.     */
+/* ------------------------------------------------------------------------ */
+int p2vo_balance(const i64 *v, i64 k, double *out) {
+    i64 n = k + 1;
+    double *depths = (double *)malloc(sizeof(double) * (size_t)(2 * k + 1));
+    if (!depths) return P2VO_ENOMEM;
+    int rc = p2vo_node_depths(v, NULL, k, depths);
+    if (rc) { free(depths); return rc; }
+    double sum = 0.0, sum_sq = 0.0, b2 = 0.0;
+    for (i64 i = 0; i < n; ++i) sum += depths[i];                                  /* :17 */
+    out[0] = (double)(unsigned long long)sum;
+    sum = 0.0;
+    for (i64 i = 0; i < n; ++i) { sum += depths[i]; sum_sq += depths[i] * depths[i]; }   /* :25-30 */
+    double nn = (double)n, m = sum / nn;
+    out[1] = sum_sq / nn - m * m;                                                  /* powi(2) */
+    for (i64 i = 0; i < n; ++i) b2 += depths[i] * ldexp(1.0, -(int)depths[i]);     /* 2f64.powi(-d) :55 */
+    out[2] = b2;
+    free(depths);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------ */
 /* from_newick, vectors (convert.rs:268-278) on top of newick::parse          */
 /* (newick/mod.rs:73-127): the literal stack walk; has_parents = some ")" is  */
 /* followed by a digit (newick_patterns.rs `\)(\d+)`).                        */

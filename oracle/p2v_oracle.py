@@ -68,6 +68,8 @@ def lib() -> ctypes.CDLL:
         _lib.p2vo_node_depths.argtypes = [p, p, i64, p]
         _lib.p2vo_to_newick.restype = i64
         _lib.p2vo_to_newick.argtypes = [p, i64, ctypes.c_char_p, i64]
+        _lib.p2vo_balance.restype = ctypes.c_int
+        _lib.p2vo_balance.argtypes = [p, i64, p]
         _lib.p2vo_newick_parse.restype = i64
         _lib.p2vo_newick_parse.argtypes = [ctypes.c_char_p, i64, p, i64]
         _lib.p2vo_from_newick.restype = i64
@@ -349,3 +351,13 @@ def from_newick_batch(buf: np.ndarray, lengths: np.ndarray, k: int, nthreads: in
     status = np.zeros(B, dtype=np.int32)
     lib().p2vo_from_newick_batch(_ptr(buf), stride, _ptr(lengths), B, k, _ptr(v), _ptr(status), nthreads)
     return v, status
+
+
+def balance(v) -> np.ndarray:
+    """[sackin, leaf_depth_variance, b2] (vector/balance.rs:14-58)."""
+    v = _i64(v)
+    out = np.zeros(3, dtype=np.float64)
+    rc = lib().p2vo_balance(_ptr(v), v.size, _ptr(out))
+    if rc:
+        raise ValueError(f"oracle: balance failed ({rc})")
+    return out

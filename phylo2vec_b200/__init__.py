@@ -21,12 +21,12 @@ __all__ = [
     "cophenetic_distances", "pairwise_distances", "check_v", "cov", "to_newick", "from_newick", "get_node_depths", "get_node_depth",
     "to_ancestry_batch", "to_pairs_batch", "to_edges_batch", "from_ancestry_batch",
     "from_pairs_batch", "from_edges_batch", "cophenetic_distances_batch", "check_v_batch",
-    "vcv_batch", "node_depths_batch", "to_newick_batch", "from_newick_batch",
+    "vcv_batch", "node_depths_batch", "to_newick_batch", "from_newick_batch", "balance_indices_batch",
 ]
 
 _BATCH = {"to_ancestry_batch", "to_pairs_batch", "to_edges_batch", "from_ancestry_batch",
           "from_pairs_batch", "from_edges_batch", "cophenetic_distances_batch", "check_v_batch",
-          "vcv_batch", "node_depths_batch", "to_newick_batch", "from_newick_batch"}
+          "vcv_batch", "node_depths_batch", "to_newick_batch", "from_newick_batch", "balance_indices_batch"}
 
 
 def __getattr__(name):

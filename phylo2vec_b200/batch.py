@@ -403,3 +403,23 @@ def from_newick_batch(newick, lengths=None, n_leaves: Optional[int] = None, dtyp
         if st.any():
             raise ValueError(f"malformed Newick string (tree {int(np.flatnonzero(st)[0])})")
     return v
+
+
+def balance_indices_batch(V, out=None, status=None, check: bool = True) -> torch.Tensor:
+    """Sackin index, leaf-depth variance and B2 of every vector of a batch ``(B,k)``: float64 ``(B,3)``.
+    Replaces vector::balance::{sackin, leaf_depth_variance, b2} (phylo2vec/src/vector/balance.rs:14-58)."""
+    V = _idx_tensor(V, 2, "balance")
+    B, k = V.shape
+    lib = _capi.load()
+    out = _out_f64(out, (B, 3), V.device)
+    if status is None:
+        status = torch.empty(B, dtype=torch.int32, device=V.device)
+    need = int(lib.p2v_balance_workspace_bytes(B, k))
+    with torch.cuda.device(V.device):
+        ws = torch.empty(max(need, 16), dtype=torch.uint8, device=V.device)
+        rc = lib.p2v_balance_batch(V.data_ptr(), V.element_size(), B, k, out.data_ptr(), status.data_ptr(),
+                                   ws.data_ptr(), need, _stream_ptr(V.device))
+    _capi.check(rc, "balance")
+    if check and bool(status.any()):
+        raise_for_status(status, V)
+    return out

@@ -845,6 +845,92 @@ int p2v_node_depths_host(const void* v_or_matrix, int idx_bytes, const double* b
     return coph_host(v_or_matrix, idx_bytes, bls, B, k, 0, 0, k + 1, out, status, 2);
 }
 
+// ---- balance indices (third "next" row, first half): Sackin, leaf-depth variance, B2 -----------
+// vector/balance.rs:14-56: all three are sums over the topological depths of the leaves
+// (get_node_depths), so they run on the prepared tables of the distance path: node depths into the
+// workspace, then one warp per tree.  sum d and sum d^2 are integers (exact in fp64 below 2^53, in
+// any order); B2 = sum d * 2^-d is a sum of positive terms added pairwise.
+__global__ void balance_kernel(const double* __restrict__ depths, int64_t B, int k, double* __restrict__ out,
+                               const int32_t* __restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int N = 2 * k + 1, n = k + 1;
+    for (int64_t t = warp; t < B; t += nwarps) {
+        if (status[t] != 0) {
+            if (lane < 3) out[3 * t + lane] = 0.0;
+            continue;
+        }
+        const double* d = depths + t * N;
+        double s = 0.0, s2 = 0.0, b2 = 0.0;
+        for (int i = lane; i < n; i += 32) {
+            const double x = d[i];
+            s += x; s2 += x * x;
+            b2 += x * ldexp(1.0, -(int)x);        // 2f64.powi(-d): 0 once it underflows, like the reference
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+            s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
+            b2 += __shfl_xor_sync(0xFFFFFFFFu, b2, o);
+        }
+        if (lane == 0) {
+            const double nn = (double)n, m = __ddiv_rn(s, nn);
+            out[3 * t] = s;                       // sackin (balance.rs:14-18)
+            out[3 * t + 1] = __dsub_rn(__ddiv_rn(s2, nn), __dmul_rn(m, m));     // leaf_depth_variance (:20-33), no FMA like Rust
+            out[3 * t + 2] = b2;                  // b2 (:49-58)
+        }
+    }
+}
+static size_t bal_al(size_t x) { return (x + 255) & ~(size_t)255; }
+size_t p2v_balance_workspace_bytes(int64_t B, int64_t k) {
+    if (B <= 0 || k < 0) return 0;
+    return bal_al(cophenetic_workspace_bytes(B, k)) + bal_al(sizeof(double) * (size_t)B * (size_t)(2 * k + 1)) +
+           bal_al(sizeof(int32_t) * (size_t)B);
+}
+static cudaError_t launch_balance(const void* v, int idx_bytes, int64_t B, int64_t k, double* out, int32_t* status,
+                                  void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (B <= 0) return cudaSuccess;
+    unsigned char* wsb = static_cast<unsigned char*>(ws);
+    const size_t cw = bal_al(cophenetic_workspace_bytes(B, k));
+    double* depths = reinterpret_cast<double*>(wsb + cw);
+    int32_t* dst = reinterpret_cast<int32_t*>(wsb + cw + bal_al(sizeof(double) * (size_t)B * (size_t)(2 * k + 1)));
+    cudaError_t e = cudaMemsetAsync(dst, 0, sizeof(int32_t) * B, st);
+    if (e != cudaSuccess) return e;
+    e = launch_node_depths(v, idx_bytes, nullptr, B, k, depths, dst, ws, cw, st);
+    if (e != cudaSuccess) return e;
+    const int64_t want = (B * 32 + 255) / 256, cap = (int64_t)sm_count() * 8;
+    balance_kernel<<<(int)(want < cap ? want : cap), 256, 0, st>>>(depths, B, (int)k, out, dst);
+    count_launch();
+    e = cudaGetLastError();
+    if (e == cudaSuccess && status) e = cudaMemcpyAsync(status, dst, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st);
+    return e;
+}
+static int balance_check(const void* v, const double* out, int idx_bytes, int64_t B, int64_t k) {
+    if (idx_bytes != 4 && idx_bytes != 8) return fail(P2V_ERR_INVALID_ARG, "idx_bytes must be 4 or 8");
+    if (B < 0 || k < 0) return fail(P2V_ERR_INVALID_ARG, "negative batch or length");
+    if (k > LARGE_K_MAX) return fail(P2V_ERR_UNSUPPORTED, "k above the supported maximum (2^19)");
+    if (B > 0 && (!out || (k > 0 && !v))) return fail(P2V_ERR_INVALID_ARG, "null buffer");
+    return P2V_OK;
+}
+int p2v_balance_batch(const void* v, int idx_bytes, int64_t B, int64_t k, double* out, int32_t* status, void* ws,
+                      size_t ws_bytes, p2v_stream_t stream) {
+    int rc = balance_check(v, out, idx_bytes, B, k);
+    if (rc) return rc;
+    if (B == 0) return P2V_OK;
+    if (!ws || ws_bytes < p2v_balance_workspace_bytes(B, k)) return fail(P2V_ERR_WORKSPACE, "balance workspace too small");
+    return from_cuda(launch_balance(v, idx_bytes, B, k, out, status, ws, ws_bytes, (cudaStream_t)stream), "balance launch");
+}
+int p2v_balance_host(const void* v, int idx_bytes, int64_t B, int64_t k, double* out, int32_t* status) {
+    int rc = balance_check(v, out, idx_bytes, B, k);
+    if (rc) return rc;
+    return host_chunked(
+        v, (size_t)k * idx_bytes, out, 3 * sizeof(double), status, B,
+        [&](int64_t nb) { return p2v_balance_workspace_bytes(nb, k); },
+        [&](void* din, void* dout, int32_t* dst, int64_t nb, void* ws, size_t wsb, cudaStream_t st) {
+            return launch_balance(din, idx_bytes, nb, k, (double*)dout, dst, ws, wsb, st);
+        });
+}
+
 // ---- to_newick --------------------------------------------------------------------------
 size_t p2v_newick_max_bytes(int64_t k) { return newick_max_bytes(k); }
 size_t p2v_newick_workspace_bytes(int64_t B, int64_t k) { return newick_workspace_bytes(B, k); }

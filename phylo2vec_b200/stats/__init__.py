@@ -1,4 +1,5 @@
-"""Same module layout as py-phylo2vec/phylo2vec/stats (nodewise part only)."""
+"""Same module layout as py-phylo2vec/phylo2vec/stats (node-wise distances / covariance, balance indices)."""
+from .balance import b2, leaf_depth_variance, sackin
 from .nodewise import cophenetic_distances, cov, pairwise_distances, vcv
 
-__all__ = ["cophenetic_distances", "pairwise_distances", "cov", "vcv"]
+__all__ = ["cophenetic_distances", "pairwise_distances", "cov", "vcv", "sackin", "b2", "leaf_depth_variance"]

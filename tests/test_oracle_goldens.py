@@ -145,3 +145,15 @@ def test_newick_round_trip_oracle():
             nw = O.to_newick(v)
             assert np.array_equal(O.from_newick(nw), v), n
             assert np.array_equal(O.from_newick(re.sub(r"\)\d+", ")", nw)), v), n
+
+
+def test_balance(goldens):
+    # vector/balance.rs tests: exact Sackin values, rtol 1e-5 / atol 1e-8 for the floats (their `close`)
+    for g in goldens["balance"]:
+        got = O.balance(g["v"])
+        if "sackin" in g:
+            assert got[0] == g["sackin"], g["src"]
+        if "variance" in g:
+            assert abs(got[1] - g["variance"]) <= 1e-8 + 1e-5 * abs(g["variance"]), g["src"]
+        assert abs(got[2] - g["b2"]) <= 1e-8 + 1e-5 * abs(g["b2"]), g["src"]
+    assert np.array_equal(O.balance(np.zeros(0, dtype=np.int64)), [0.0, 0.0, 0.0])
