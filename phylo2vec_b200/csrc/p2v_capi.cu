@@ -881,9 +881,89 @@ __global__ void balance_kernel(const double* __restrict__ depths, int64_t B, int
         }
     }
 }
+// 2 <= k <= 4095: one warp per tree on the two informative ancestry columns (MODE_ANC2, int32), all
+// state in shared memory (8 bytes per leaf).  Every internal child records its parent row; the depth
+// of the internal nodes comes top-down, 32 rows at a time from the root, parents inside the batch by
+// pointer doubling (the sweep of the to_newick kernel with unit weights); a row then adds depth + 1
+// for each of its leaf children.  The two integer sums are accumulated as integers.
+constexpr int BAL_WARP_K_MAX = 4095;
+static size_t bal_warp_bytes(int64_t k) { return (((size_t)8 * k) + 15) & ~(size_t)15; }
+__global__ void __launch_bounds__(128)
+balance_warp_kernel(const int* __restrict__ anc2, int64_t B, int k, double* __restrict__ out,
+                    const int32_t* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char bal_dyn[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    unsigned char* mine = bal_dyn + (size_t)warp * ((((size_t)8 * k) + 15) & ~(size_t)15);
+    uint32_t* ch = reinterpret_cast<uint32_t*>(mine);                       // c1 | c2 << 16 of row r
+    uint16_t* par = reinterpret_cast<uint16_t*>(mine + 4 * (size_t)k);      // parent row of the node of row r
+    uint16_t* dep = par + k;                                                 // depth of the node of row r
+    const int nb = (k + 31) >> 5;
+    for (int64_t t = (int64_t)blockIdx.x * nwarps + warp; t < B; t += (int64_t)gridDim.x * nwarps) {
+        if (status[t] != 0) {
+            if (lane < 3) out[3 * t + lane] = 0.0;
+            continue;
+        }
+        const int2* anc = reinterpret_cast<const int2*>(anc2 + (size_t)t * 2 * k);
+        for (int r = lane; r < k; r += 32) {
+            const int2 x = anc[r];
+            ch[r] = (uint32_t)x.x | ((uint32_t)x.y << 16);
+            if (x.x > k) par[x.x - k - 1] = (uint16_t)r;
+            if (x.y > k) par[x.y - k - 1] = (uint16_t)r;
+        }
+        __syncwarp();
+        unsigned long long s = 0, s2 = 0;
+        double b2 = 0.0;
+        for (int b = nb - 1; b >= 0; --b) {
+            const int base = b * 32, r = base + lane;
+            const bool act = r < k;
+            uint32_t acc = 0;
+            int ptr = lane;
+            bool fin = true;
+            if (act && r != k - 1) {
+                const int pr = (int)par[r];
+                acc = 1;
+                if (pr >= base + 32) acc += dep[pr];
+                else { ptr = pr - base; fin = false; }
+            }
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                const uint32_t a = __shfl_sync(0xFFFFFFFFu, acc | (fin ? 0x80000000u : 0u), ptr);
+                const int pp = __shfl_sync(0xFFFFFFFFu, ptr, ptr);
+                if (!fin) { acc += a & 0x7FFFFFFFu; fin = (a >> 31) != 0u; ptr = pp; }
+            }
+            if (act) {
+                dep[r] = (uint16_t)acc;
+                const uint32_t cc = ch[r];
+                const int leaves = ((int)(cc & 0xFFFFu) <= k) + ((int)(cc >> 16) <= k);
+                const unsigned long long d = acc + 1u;                      // depth of this row's leaf children
+                s += (unsigned long long)leaves * d;
+                s2 += (unsigned long long)leaves * d * d;
+                b2 += (double)leaves * ((double)d * ldexp(1.0, -(int)d));
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+            s2 += __shfl_xor_sync(0xFFFFFFFFu, s2, o);
+            b2 += __shfl_xor_sync(0xFFFFFFFFu, b2, o);
+        }
+        if (lane == 0) {
+            const double nn = (double)(k + 1), sd = (double)s, m = __ddiv_rn(sd, nn);
+            out[3 * t] = sd;
+            out[3 * t + 1] = __dsub_rn(__ddiv_rn((double)s2, nn), __dmul_rn(m, m));
+            out[3 * t + 2] = b2;
+        }
+    }
+}
+
 static size_t bal_al(size_t x) { return (x + 255) & ~(size_t)255; }
+static bool bal_warp_path(int64_t k) { return k >= 2 && k <= BAL_WARP_K_MAX; }
 size_t p2v_balance_workspace_bytes(int64_t B, int64_t k) {
     if (B <= 0 || k < 0) return 0;
+    if (bal_warp_path(k))      // [ status | int32 v | int32 (k,2) ancestry columns | decode scratch ]
+        return bal_al(sizeof(int32_t) * (size_t)B) + bal_al(4 * (size_t)B * (size_t)k) + bal_al(8 * (size_t)B * (size_t)k) +
+               bal_al(decode_workspace_bytes(B, k));
     return bal_al(cophenetic_workspace_bytes(B, k)) + bal_al(sizeof(double) * (size_t)B * (size_t)(2 * k + 1)) +
            bal_al(sizeof(int32_t) * (size_t)B);
 }
@@ -891,6 +971,39 @@ static cudaError_t launch_balance(const void* v, int idx_bytes, int64_t B, int64
                                   void* ws, size_t ws_bytes, cudaStream_t st) {
     if (B <= 0) return cudaSuccess;
     unsigned char* wsb = static_cast<unsigned char*>(ws);
+    if (bal_warp_path(k)) {
+        int32_t* dst = reinterpret_cast<int32_t*>(wsb);
+        int* v32 = reinterpret_cast<int*>(wsb + bal_al(sizeof(int32_t) * (size_t)B));
+        int* anc2 = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(v32) + bal_al(4 * (size_t)B * (size_t)k));
+        unsigned char* dws = reinterpret_cast<unsigned char*>(anc2) + bal_al(8 * (size_t)B * (size_t)k);
+        const size_t dwb = decode_workspace_bytes(B, k);
+        const void* vin = v;
+        cudaError_t e = cudaSuccess;
+        if (idx_bytes == 8) {
+            e = launch_narrow_v(static_cast<const long long*>(v), B * k, v32, st);
+            if (e != cudaSuccess) return e;
+            vin = v32;
+        }
+        e = launch_decode(MODE_ANC2, vin, 4, B, k, anc2, dst, dwb ? dws : nullptr, dwb, st, 0);
+        if (e != cudaSuccess) return e;
+        const size_t per = bal_warp_bytes(k);
+        int wpc = 1, best = 0;
+        for (int w = 4; w >= 1; w >>= 1) {
+            size_t ctas = ((size_t)228 * 1024) / (per * w + 1024);
+            if (ctas > 32) ctas = 32;
+            if (ctas > (size_t)(64 / w)) ctas = 64 / w;
+            if ((int)ctas * w > best) { best = (int)ctas * w; wpc = w; }
+        }
+        const size_t smem = per * wpc;
+        e = cudaFuncSetAttribute(balance_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const int64_t cap = (int64_t)sm_count() * (best / wpc), want = (B + wpc - 1) / wpc;
+        balance_warp_kernel<<<(int)(want < cap ? want : cap), wpc * 32, smem, st>>>(anc2, B, (int)k, out, dst);
+        count_launch();
+        e = cudaGetLastError();
+        if (e == cudaSuccess && status) e = cudaMemcpyAsync(status, dst, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st);
+        return e;
+    }
     const size_t cw = bal_al(cophenetic_workspace_bytes(B, k));
     double* depths = reinterpret_cast<double*>(wsb + cw);
     int32_t* dst = reinterpret_cast<int32_t*>(wsb + cw + bal_al(sizeof(double) * (size_t)B * (size_t)(2 * k + 1)));
