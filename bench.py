@@ -667,4 +667,13 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # stdout carries the JSON line(s) only: libraries that write to file descriptor 1 on their own
+    # (NCCL's version banner and NCCL_DEBUG output) are sent to stderr for the whole run
+    sys.stdout.flush()
+    _json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _json_out
+    try:
+        main()
+    finally:
+        _json_out.flush()
