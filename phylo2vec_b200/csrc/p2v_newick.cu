@@ -1,29 +1,31 @@
-// Batched to_newick for Phylo2Vec vectors (topology only), sm_100a.
+// Batched to_newick / from_newick for Phylo2Vec vectors (topology only), sm_100a.
 //
 // Replaces (reference, paths relative to /root/reference):
 //   vector::convert::to_newick / build_newick / prepare_cache   phylo2vec/src/vector/convert.rs:341-397
 //   PyO3 to_newick (vector arm)                                    py-phylo2vec/src/lib.rs:90-96
+//   newick::parse, vector::convert::from_newick                 newick/mod.rs:73-127, vector/convert.rs:268-278
+//   (see the second half of this file)
 //
-// The reference concatenates per-leaf string caches pair by pair; the result is the Newick string
-// of the ancestry tree with children in (c1, c2) order and every node labelled by its id:
+// to_newick.  The reference concatenates per-leaf string caches pair by pair; the result is the
+// Newick string of the ancestry tree with children in (c1, c2) order and every node labelled:
 //   S(leaf) = dec(leaf),  S(u) = "(" S(c1) "," S(c2) ")" dec(u),  out = S(root) ";".
-// The batch is first decoded to an int32 ancestry by the batched decode kernel (workspace); then
-// one 128-thread CTA per tree keeps the tree in shared memory and places every token directly:
-//   1. the ancestry rows are copied in;
-//   2. pointer jumping down the first-child and second-child pointers gives every node its
-//      leftmost / rightmost leaf, the number of "(" a first-child chain opens and the bytes a
-//      second-child chain closes (")" + label per node);
-//   3. every internal node links the last leaf of its first child to the first leaf of its second
-//      child: the leaves form a list in string order; weighted list ranking (weight = bytes
-//      emitted around the leaf: ",", the "(" run, its label, the ")label" run) gives every leaf
-//      its byte offset;
-//   4. leaves write [","] "(((" label, internal nodes write ")" label, the string is assembled in
-//      shared memory and copied out with coalesced stores.
-// Sizes: this CTA-per-tree kernel serves k > 4095 with uint32 tables in a per-CTA slice of the
-// workspace (L2 resident), 1024 threads, tokens written straight into the output row (the uint16 /
-// shared-memory instantiation of the template was the first version for small trees); k <= 4095
-// runs newick_warp_kernel below.  The matrix form (branch lengths need the reference's shortest-round-trip float
-// formatting) is not built: P2V_ERR_UNSUPPORTED.
+// The batch is first decoded by the batched decode kernel (int32, workspace).
+//   * k <= 4095: newick_warp_kernel, one warp per tree (described where it is defined);
+//   * larger trees: newick_kernel<uint32_t>, one 1024-thread CTA per tree with its tables in a
+//     per-CTA slice of the workspace (L2 resident) and the tokens written straight into the
+//     output row:
+//       1. pointer jumping down the first-child and second-child pointers gives every node its
+//          leftmost / rightmost leaf, the number of "(" a first-child chain opens and the bytes a
+//          second-child chain closes (")" + label per node);
+//       2. every internal node links the last leaf of its first child to the first leaf of its
+//          second child: the leaves form a list in string order; weighted list ranking (weight =
+//          bytes emitted around the leaf: ",", the "(" run, its label, the ")label" run) gives
+//          every leaf its byte offset;
+//       3. leaves write [","] "(((" label, internal nodes write ")" label.
+//     (The template's uint16_t form -- tables, ancestry copy and string staging in shared memory
+//     -- was the first version for small trees; it is no longer instantiated.)
+// The matrix form (branch lengths need the reference's shortest-round-trip float formatting) is
+// not built.
 #include <cstdlib>
 
 #include "p2v_common.cuh"
