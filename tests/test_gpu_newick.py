@@ -251,3 +251,16 @@ def test_from_newick_host_entry(p2v):
     assert rc == 0 and not st.any() and np.array_equal(out, V)
     ref, rst = O.from_newick_batch(buf, lengths, n - 1)
     assert not rst.any() and np.array_equal(ref, V)
+
+
+@pytest.mark.parametrize("n_leaves", [2, 17, 500, 1500, 3000, 5000, 7000])
+def test_single_tree_round_trip_unaligned_rows(p2v, n_leaves):
+    """The reference-named single-tree functions go through the host entry points with rows that are
+    not 16-byte aligned: the CTA-per-tree tokenizer at every size (test_newick, convert.rs:640-656)."""
+    import re
+    from phylo2vec_b200.base.newick import from_newick, to_newick
+    for v in sample_vectors(2, n_leaves, seed=23 * n_leaves):
+        s = to_newick(v)
+        assert s == O.to_newick(v)
+        assert np.array_equal(from_newick(s), v)
+        assert np.array_equal(from_newick(re.sub(r"\)\d+", ")", s)), v)
