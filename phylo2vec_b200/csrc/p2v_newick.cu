@@ -787,7 +787,7 @@ newick_parse_warp_kernel(const char* __restrict__ in, int64_t in_stride, const i
             }
             const int left = len - p0;                               // valid characters from p0 on
             const uint32_t vm = left >= 16 ? 0xFFFFu : (left > 0 ? (1u << left) - 1u : 0u);
-            if ((mclose | msep | msemi | mdig) != 0xFFFFu && ((mclose | msep | msemi | mdig) & vm) != vm) bad = 1;
+            if (((mclose | msep | msemi | mdig) & vm) != vm) bad = 1;           // a character outside "(),;" and the digits
             mclose &= vm; msep &= vm; msemi &= vm; mdig &= vm;
             const uint32_t lastbit = (left >= 1 && left <= 16) ? 1u << (left - 1) : 0u;     // the ";" closes the string
             if (msemi != lastbit) bad = 1;
