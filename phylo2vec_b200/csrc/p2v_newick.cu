@@ -1116,7 +1116,8 @@ static cudaError_t launch_parse_t(const char* in, int64_t in_stride, const int64
             auto kern = np ? newick_parse_np_kernel<OutT, true> : newick_parse_kernel<OutT, true>;
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            const int threads = k <= 255 ? 64 : (k <= 2047 ? 128 : 256);
+            // the kernel for unlabelled strings has more all-thread phases (sparse table, keys): wider CTAs
+            const int threads = np ? (k <= 127 ? 64 : (k <= 511 ? 128 : 512)) : (k <= 255 ? 64 : (k <= 2047 ? 128 : 256));
             int per_sm = 0;
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
             if (e != cudaSuccess) return e;
