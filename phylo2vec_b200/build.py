@@ -45,19 +45,45 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Every source is compiled to its own object file (in parallel, only the stale ones) and the
+    objects are linked into the shared library."""
     if not force and not _stale():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIBDIR, exist_ok=True)
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
     extra = os.environ.get("P2V_NVCC_EXTRA", "").split()
-    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    if verbose:
-        print(" ".join(cmd))
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
+    tag = "_".join(extra).replace("/", "_").replace("=", "_")
+    hdr_t = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
+    hdr_t = max(hdr_t, os.path.getmtime(os.path.abspath(__file__)))
+    nvcc = _nvcc()
+    compile_flags = [f for f in NVCC_FLAGS if f != "--shared"]
+
+    def one(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + (("." + tag) if tag else "") + ".o")
+        path = os.path.join(CSRC, src)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(hdr_t, os.path.getmtime(path)):
+            return obj, None
+        cmd = [nvcc] + compile_flags + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, path]
+        if verbose:
+            print(" ".join(cmd))
+        return obj, subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(one, SOURCES))
+    for obj, r in results:
+        if r is None:
+            continue
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed building libphylo2vec_b200.so")
+    r = subprocess.run([nvcc, "--shared", "-o", LIB] + [o for o, _ in results] + ["-lpthread"],
+                       capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libphylo2vec_b200.so")
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed linking libphylo2vec_b200.so")
     return LIB
 
 
