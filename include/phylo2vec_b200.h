@@ -19,7 +19,14 @@
  *  - status (B int32, may be NULL) receives per tree: 0 = ok; i+1 = v[i] is out of
  *    bounds (the reference panics with "Validation failed: v[i] = .. is out of
  *    bounds", vector/base.rs:60-67); P2V_TREE_MALFORMED for encode input that is
- *    not a tree in the reference's format.  Output of a failed tree is unspecified.
+ *    not a tree in the reference's format; P2V_TREE_NEGATIVE_BRANCH for a tree with a negative
+ *    or NaN branch length (check_m and every function that takes branch lengths: the reference's
+ *    distance functions do not validate them, here such a tree is flagged instead of producing
+ *    a meaningless matrix).  Output of a failed tree is unspecified.
+ *  - Alignment: every index buffer is aligned to idx_bytes; pairs and edges OUTPUT buffers to
+ *    2 * idx_bytes (they are written as two-element vector stores: 16 bytes for int64);
+ *    float64 buffers to 8 bytes (16 gets the 128-bit store path of the distance kernels).
+ *    A misaligned buffer is rejected with P2V_ERR_INVALID_ARG.
  *  - *_host functions take HOST pointers, copy in, run and copy out in chunks on
  *    internal streams and return after completion (what a single-tree drop-in of
  *    the reference's functions calls).
@@ -43,6 +50,7 @@ extern "C" {
 #define P2V_ERR_WORKSPACE (-4)
 
 #define P2V_TREE_MALFORMED (-2)
+#define P2V_TREE_NEGATIVE_BRANCH (-3) /* a branch length below zero or NaN (check_m, matrix/base.rs:88-94) */
 
 typedef void *p2v_stream_t; /* cudaStream_t */
 
@@ -56,8 +64,9 @@ int64_t p2v_launch_count(void);
  * to_ancestry (convert.rs:167-188), to_edges (convert.rs:227-248), i.e. the
  * PyO3 entry points get_pairs / get_ancestry / get_edges
  * (py-phylo2vec/src/lib.rs:108-131), batched.
- * Trees with k <= 1024 need no workspace; larger trees need
- * p2v_decode_workspace_bytes(B,k) bytes of device scratch. */
+ * Trees with k <= 12287 (batches of trees: k <= 16384) keep all state in shared memory and need
+ * no workspace; larger trees need p2v_decode_workspace_bytes(B,k) bytes of device scratch
+ * (0 is returned when none is needed). */
 size_t p2v_decode_workspace_bytes(int64_t B, int64_t k);
 int p2v_to_pairs_batch(const void *v, int idx_bytes, int64_t B, int64_t k, void *pairs,
                        int32_t *status, void *workspace, size_t workspace_bytes,
@@ -88,6 +97,14 @@ int p2v_from_edges_batch(const void *edges, int idx_bytes, int64_t B, int64_t k,
 /* ---- validation: vector::base::check_v (base.rs:50-67) ------------------- */
 int p2v_check_v_batch(const void *v, int idx_bytes, int64_t B, int64_t k, int32_t *status,
                       p2v_stream_t stream);
+
+/* ---- validation of matrices: matrix::base::check_m (matrix/base.rs:76-95), PyO3 check_m
+ * (py-phylo2vec/src/lib.rs:68-88), Python phylo2vec.utils.matrix.check_matrix.
+ * matrix (B,k,3) float64 [v, bl1, bl2]; status[b] = 0, i + 1 (v[i] = column 0 cast like Rust's
+ * `as usize` is above 2i) or P2V_TREE_NEGATIVE_BRANCH.  The reference's other two assertions
+ * (empty matrix, column count) are shape checks the caller makes. */
+int p2v_check_m_batch(const double *matrix, int64_t B, int64_t k, int32_t *status, p2v_stream_t stream);
+int p2v_check_m_host(const double *matrix, int64_t B, int64_t k, int32_t *status);
 
 /* ---- cophenetic distances ------------------------------------------------
  * replaces vector::graph::_cophenetic_distances (vector/graph.rs:20-90) and
@@ -211,9 +228,20 @@ int p2v_balance_host(const void *v, int idx_bytes, int64_t B, int64_t k, double 
 int p2v_from_newick_host(const char *newick, int64_t in_stride, int64_t B, int64_t k, void *v, int idx_bytes,
                          int32_t *status);
 
-/* The *_host entry points cache three streams and their device staging buffers per host
- * thread (they grow on demand).  This frees the calling thread's cache. */
+/* The *_host entry points keep three streams, their device staging buffers and (for pageable
+ * or compact transport) pinned host staging per host thread; they grow on demand, up to about
+ * 3 GB of device memory and 1.2 GB of pinned memory for a 1 M-tree to_ancestry call.
+ * A call that would leave more than the cache limit behind (default 512 MiB; device + pinned
+ * bytes per thread) frees its staging before it returns; a caller that streams many large
+ * batches raises the limit (-1 = keep everything) to keep the allocations between calls.
+ * A thread that exits frees its cache.  p2v_host_release() frees the calling thread's cache now. */
 void p2v_host_release(void);
+int64_t p2v_host_cache_bytes(void);          /* bytes the calling thread currently keeps */
+void p2v_host_cache_limit(int64_t bytes);    /* process-wide limit per thread */
+
+/* profiling aid: nanosecond stamps at the phase boundaries of the last whole-grid
+ * decode (which = 0) / tables (which = 1) kernel; out[64] */
+int p2v_debug_phase_ns(int which, uint64_t *out);
 
 /* ---- measurement helper: a plain 128-bit streaming fill of `bytes` bytes, the
  * write-only ceiling the distance kernel is compared with in bench.py -------- */

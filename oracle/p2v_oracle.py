@@ -113,6 +113,21 @@ def check_v(v) -> None:
     _raise(int(lib().p2vo_check_v(_ptr(v), v.size)), v)
 
 
+def check_m(m) -> None:
+    """matrix/base.rs:76-95, in the reference's order: non-empty; check_v on column 0 cast like
+    ``as usize`` (saturating: NaN and negatives give 0); exactly three columns; lengths >= 0."""
+    m = np.asarray(m, dtype=np.float64)
+    if m.size == 0:
+        raise AssertionError("Matrix should not be empty")
+    col = np.nan_to_num(m[:, 0], nan=0.0, posinf=9.0e18, neginf=0.0)
+    check_v(np.clip(np.trunc(col), 0.0, 9.0e18).astype(np.int64))
+    if m.shape[1] != 3:
+        raise AssertionError("Matrix must have at least 3 columns (vector and two branch lengths)")
+    for row in m:
+        if not (row[1] >= 0.0 and row[2] >= 0.0):
+            raise AssertionError("Branch lengths must be positive")
+
+
 def is_unordered(v) -> bool:
     """vector/base.rs:92-101"""
     v = _i64(v)

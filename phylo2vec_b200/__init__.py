@@ -14,18 +14,19 @@ from .base.edges import from_edges, to_edges
 from .base.newick import from_newick, to_newick
 from .base.pairs import from_pairs, to_pairs
 from .stats.nodewise import cophenetic_distances, cov, pairwise_distances
+from .utils.matrix import check_m, check_matrix
 from .utils.vector import check_v, get_node_depth, get_node_depths
 
 __all__ = [
     "to_ancestry", "to_pairs", "to_edges", "from_ancestry", "from_pairs", "from_edges",
-    "cophenetic_distances", "pairwise_distances", "check_v", "cov", "to_newick", "from_newick", "get_node_depths", "get_node_depth",
+    "cophenetic_distances", "pairwise_distances", "check_v", "check_m", "check_matrix", "cov", "to_newick", "from_newick", "get_node_depths", "get_node_depth",
     "to_ancestry_batch", "to_pairs_batch", "to_edges_batch", "from_ancestry_batch",
-    "from_pairs_batch", "from_edges_batch", "cophenetic_distances_batch", "check_v_batch",
+    "from_pairs_batch", "from_edges_batch", "cophenetic_distances_batch", "check_v_batch", "check_m_batch",
     "vcv_batch", "node_depths_batch", "to_newick_batch", "from_newick_batch", "balance_indices_batch",
 ]
 
 _BATCH = {"to_ancestry_batch", "to_pairs_batch", "to_edges_batch", "from_ancestry_batch",
-          "from_pairs_batch", "from_edges_batch", "cophenetic_distances_batch", "check_v_batch",
+          "from_pairs_batch", "from_edges_batch", "cophenetic_distances_batch", "check_v_batch", "check_m_batch",
           "vcv_batch", "node_depths_batch", "to_newick_batch", "from_newick_batch", "balance_indices_batch"}
 
 

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libphylo2vec_b200.so")
 
 P2V_OK = 0
 P2V_TREE_MALFORMED = -2
+P2V_TREE_NEGATIVE_BRANCH = -3
 
 _i64 = ctypes.c_int64
 _int = ctypes.c_int
@@ -54,6 +55,11 @@ SIGNATURES = {
     "p2v_cophenetic_host": (_int, [_vp, _int, _vp, _i64, _i64, _int, _i64, _i64, _vp, _vp]),
     "p2v_cophenetic_matrix_host": (_int, [_vp, _i64, _i64, _int, _i64, _i64, _vp, _vp]),
     "p2v_host_release": (None, []),
+    "p2v_host_cache_bytes": (_i64, []),
+    "p2v_host_cache_limit": (None, [_i64]),
+    "p2v_debug_phase_ns": (_int, [_int, _vp]),
+    "p2v_check_m_batch": (_int, [_vp, _i64, _i64, _vp, _vp]),
+    "p2v_check_m_host": (_int, [_vp, _i64, _i64, _vp]),
     "p2v_fill_f64": (_int, [_vp, _i64, ctypes.c_double, _vp]),
 }
 for _name in ("to_pairs", "to_ancestry", "to_edges", "from_pairs", "from_ancestry", "from_edges"):
@@ -83,7 +89,24 @@ def load() -> ctypes.CDLL:
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    import atexit
+    atexit.register(release_host_cache)
     return lib
+
+
+def release_host_cache() -> None:
+    """Free the staging (device + pinned memory) the *_host entry points keep for the calling thread."""
+    if _lib is not None:
+        _lib.p2v_host_release()
+
+
+def host_cache_bytes() -> int:
+    return int(load().p2v_host_cache_bytes())
+
+
+def set_host_cache_limit(nbytes: int) -> None:
+    """Bytes of staging a host thread may keep between *_host calls (-1: everything)."""
+    load().p2v_host_cache_limit(int(nbytes))
 
 
 def check(rc: int, what: str) -> None:

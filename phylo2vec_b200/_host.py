@@ -48,6 +48,8 @@ def raise_status(status: np.ndarray, v: Optional[np.ndarray] = None) -> None:
         val = int(v.reshape(status.size, -1)[b, i]) if v is not None else "?"
         # message of check_max, phylo2vec/src/vector/base.rs:60-67
         raise AssertionError(f"Validation failed: v[{i}] = {val} is out of bounds (max = {2 * i})")
+    if code == _capi.P2V_TREE_NEGATIVE_BRANCH:      # check_m, phylo2vec/src/matrix/base.rs:88-94
+        raise AssertionError("Branch lengths must be positive")
     raise ValueError("malformed tree: the input is not a phylo2vec ancestry / pair / edge list")
 
 

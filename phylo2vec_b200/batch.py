@@ -43,6 +43,16 @@ def _idx_tensor(x, ndim: int, what: str) -> torch.Tensor:
     return t.contiguous()
 
 
+def _check_status(status, B: int, device, what: str) -> torch.Tensor:
+    """A caller-supplied status tensor is written by the kernels: int32, B entries, same device."""
+    if status is None:
+        return torch.empty(B, dtype=torch.int32, device=device)
+    status = as_tensor(status)
+    if status.dtype != torch.int32 or status.numel() != B or status.device != device or not status.is_contiguous():
+        raise ValueError(f"{what}: status must be a contiguous int32 tensor of {B} entries on {device}")
+    return status
+
+
 def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -70,6 +80,9 @@ def raise_for_status(status: torch.Tensor, v: Optional[torch.Tensor] = None) -> 
         raise AssertionError(
             f"Validation failed: v[{i}] = {val} is out of bounds (max = {2 * i})" +
             (f" [tree {b} of the batch]" if status.numel() > 1 else ""))
+    if code == _capi.P2V_TREE_NEGATIVE_BRANCH:      # check_m, phylo2vec/src/matrix/base.rs:88-94
+        raise AssertionError("Branch lengths must be positive" +
+                             (f" [tree {b} of the batch]" if status.numel() > 1 else ""))
     raise ValueError(f"malformed tree input (tree {b} of the batch, code {code})")
 
 
@@ -105,8 +118,11 @@ def _decode(name: str, V, out=None, status=None, check: bool = True):
         out = as_tensor(out)
         if tuple(out.shape) != shape or out.dtype != V.dtype or not out.is_contiguous() or out.device != V.device:
             raise ValueError(f"{name}: out must be a contiguous {shape} {V.dtype} tensor on {V.device}")
-    if status is None:
-        status = torch.empty(B, dtype=torch.int32, device=V.device)
+        if name != "to_ancestry" and out.data_ptr() % (2 * out.element_size()) != 0:
+            # pairs / edges are written as two-element vector stores (include/phylo2vec_b200.h, "Alignment")
+            raise ValueError(f"{name}: out must be aligned to {2 * out.element_size()} bytes "
+                             "(a view at an odd element offset is not)")
+    status = _check_status(status, B, V.device, name)
     lib = _capi.load()
     with torch.cuda.device(V.device):
         ws_t, ws_p = _ws(lib.p2v_decode_workspace_bytes(B, k), V.device)
@@ -167,8 +183,7 @@ def _encode(name: str, X, out=None, status=None, check: bool = True):
         out = as_tensor(out)
         if tuple(out.shape) != (B, k) or out.dtype != X.dtype or not out.is_contiguous() or out.device != X.device:
             raise ValueError(f"{name}: out must be a contiguous {(B, k)} {X.dtype} tensor on {X.device}")
-    if status is None:
-        status = torch.empty(B, dtype=torch.int32, device=X.device)
+    status = _check_status(status, B, X.device, name)
     lib = _capi.load()
     with torch.cuda.device(X.device):
         ws_t, ws_p = _ws(lib.p2v_encode_workspace_bytes(B, k), X.device)
@@ -205,6 +220,21 @@ def check_v_batch(V) -> torch.Tensor:
         rc = _capi.load().p2v_check_v_batch(V.data_ptr(), V.element_size(), B, k, status.data_ptr(),
                                             _stream_ptr(V.device))
     _capi.check(rc, "check_v")
+    return status
+
+
+def check_m_batch(M) -> torch.Tensor:
+    """Per-tree status of check_m (phylo2vec/src/matrix/base.rs:76-95) for float64 ``(B,k,3)`` matrices:
+    0, bad index + 1 (column 0 fails check_v) or ``_capi.P2V_TREE_NEGATIVE_BRANCH``."""
+    M = as_tensor(M)
+    if not M.is_cuda or M.dtype != torch.float64 or M.dim() != 3 or M.shape[2] != 3:
+        raise TypeError("check_m: expected a float64 CUDA tensor (B,k,3)")
+    M = M.contiguous()
+    B, k = M.shape[0], M.shape[1]
+    status = torch.empty(B, dtype=torch.int32, device=M.device)
+    with torch.cuda.device(M.device):
+        rc = _capi.load().p2v_check_m_batch(M.data_ptr(), B, k, status.data_ptr(), _stream_ptr(M.device))
+    _capi.check(rc, "check_m")
     return status
 
 
@@ -255,8 +285,7 @@ def _rows_call(what, trees, unrooted, rows, out, bls, status, check, workspace):
     if not (0 <= r0 <= r1 <= n):
         raise ValueError(f"rows {rows} outside [0, {n}]")
     out = _out_f64(out, (B, r1 - r0, n), T.device)
-    if status is None:
-        status = torch.empty(B, dtype=torch.int32, device=T.device)
+    status = _check_status(status, B, T.device, what)
     need = lib.p2v_cophenetic_workspace_bytes(B, k)
     with torch.cuda.device(T.device):
         if workspace is None or workspace.numel() * workspace.element_size() < need:
@@ -310,8 +339,7 @@ def node_depths_batch(trees, out=None, bls=None, status=None, check: bool = True
     lib = _capi.load()
     B, k = T.shape[0], T.shape[1]
     out = _out_f64(out, (B, 2 * k + 1), T.device)
-    if status is None:
-        status = torch.empty(B, dtype=torch.int32, device=T.device)
+    status = _check_status(status, B, T.device, "get_node_depths")
     need = lib.p2v_cophenetic_workspace_bytes(B, k)
     with torch.cuda.device(T.device):
         if workspace is None or workspace.numel() * workspace.element_size() < need:

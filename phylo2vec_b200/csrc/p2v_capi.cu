@@ -62,6 +62,11 @@ static int decode_entry(int mode, const void* v, int idx_bytes, int64_t B, int64
     int rc = check_common(v, out, idx_bytes, B, k);
     if (rc) return rc;
     if (ws_bytes < decode_workspace_bytes(B, k)) return fail(P2V_ERR_WORKSPACE, "decode workspace too small");
+    // pairs and edges are written as (x, y) vector stores: 2 * idx_bytes alignment (see the header)
+    if (mode != MODE_ANCESTRY && B > 0 && k > 0 && (reinterpret_cast<uintptr_t>(out) % (2 * (size_t)idx_bytes)) != 0)
+        return fail(P2V_ERR_INVALID_ARG, "pairs / edges output must be aligned to 2 * idx_bytes bytes");
+    if ((reinterpret_cast<uintptr_t>(v) % (size_t)idx_bytes) != 0 || (reinterpret_cast<uintptr_t>(out) % (size_t)idx_bytes) != 0)
+        return fail(P2V_ERR_INVALID_ARG, "index buffers must be aligned to idx_bytes");
     return from_cuda(launch_decode(mode, v, idx_bytes, B, k, out, status, ws, ws_bytes, (cudaStream_t)stream),
                      "decode launch");
 }
@@ -101,9 +106,14 @@ struct HostCtx {
         cap_in = cap_out = cap_ws = cap_stat = 0;
         dev = -1;
     }
-    ~HostCtx() { /* the CUDA context may already be gone at thread exit: leave it to the driver */ }
+    size_t bytes() const { return HOST_STREAMS * (cap_in + cap_out + cap_ws + cap_stat); }
+    // thread exit: give the memory back (errors such as cudaErrorCudartUnloading at process exit are ignored)
+    ~HostCtx() { release(); cudaGetLastError(); }
 };
 static thread_local HostCtx g_host;
+// Staging the *_host entry points may keep between calls, per host thread (device + pinned bytes).
+// A call that leaves more than this behind frees its staging before it returns.
+static std::atomic<int64_t> g_host_cache_limit{(int64_t)512 << 20};
 
 static cudaError_t host_ensure(HostCtx& H, size_t in_b, size_t out_b, size_t ws_b, size_t stat_b) {
     int dev = 0;
@@ -152,6 +162,8 @@ struct StageCtx {
     int32_t* hstat[HOST_STREAMS] = {};
     cudaEvent_t ev[HOST_STREAMS] = {};
     size_t cap_in = 0, cap_out = 0, cap_stat = 0;
+    size_t bytes() const { return HOST_STREAMS * (cap_in + cap_out + cap_stat); }
+    ~StageCtx() { release(); cudaGetLastError(); }
     void release() {
         for (int i = 0; i < HOST_STREAMS; ++i) {
             if (hin[i]) cudaFreeHost(hin[i]);
@@ -304,7 +316,10 @@ static int host_chunked(const void* in, size_t in_tree_bytes, void* out, size_t 
     if (chunk < 1) chunk = 1;
     if (chunk > B) chunk = B;
     HostCtx& H = g_host;
-    const size_t wsb = ws_bytes_of(chunk);
+    // the workspace of a short tail chunk can exceed the full chunk's (a few large trees take the
+    // whole-GPU kernels with per-worker tables): size for both
+    size_t wsb = ws_bytes_of(chunk);
+    if (B % chunk != 0) { const size_t wt = ws_bytes_of(B % chunk); if (wt > wsb) wsb = wt; }
     cudaError_t e = host_ensure(H, in_tree_bytes * chunk, out_tree_bytes * chunk, wsb, sizeof(int32_t) * chunk);
     if (e != cudaSuccess) { H.release(); return from_cuda(e, "host entry: device allocation"); }
     // big calls on pageable buffers: threaded staging through pinned memory
@@ -369,6 +384,8 @@ struct CompactCtx {
     int32_t* v32[HOST_STREAMS] = {};
     cudaEvent_t ev[HOST_STREAMS] = {};
     size_t cap_stage = 0, cap_v32 = 0, cap_hstat = 0, cap_vstage = 0;
+    size_t bytes() const { return HOST_STREAMS * (cap_stage + cap_v32 + cap_hstat + cap_vstage); }
+    ~CompactCtx() { release(); cudaGetLastError(); }
     void release() {
         for (int i = 0; i < HOST_STREAMS; ++i) {
             if (stage[i]) cudaFreeHost(stage[i]);
@@ -382,6 +399,17 @@ struct CompactCtx {
     }
 };
 static thread_local CompactCtx g_compact;
+
+// End of every *_host entry point: staging above the limit goes back to the driver.
+static void host_trim() {
+    const int64_t lim = g_host_cache_limit.load(std::memory_order_relaxed);
+    if (lim < 0) return;
+    if ((int64_t)(g_host.bytes() + g_stage.bytes() + g_compact.bytes()) > lim) {
+        g_host.release(); g_compact.release(); g_stage.release();
+        cudaGetLastError();
+    }
+}
+struct HostTrim { ~HostTrim() { host_trim(); } };
 
 static int host_thread_count() {
     const char* e = getenv("P2V_HOST_THREADS");
@@ -457,7 +485,8 @@ static int ancestry_host_compact(const void* v, int64_t B, int64_t k, void* out,
     const size_t wire_row = u16 ? 4 : 8;
     // device per element: v 8 B, v32 4 B (reused for the packed pairs), int32 pairs 8 B
     const size_t in_b = (size_t)k * 8 * chunk, out_b = (size_t)k * 8 * chunk, v32_b = (size_t)k * 4 * chunk;
-    const size_t wsb = decode_workspace_bytes(chunk, k);
+    size_t wsb = decode_workspace_bytes(chunk, k);
+    if (B % chunk != 0) { const size_t wt = decode_workspace_bytes(B % chunk, k); if (wt > wsb) wsb = wt; }
     // a pageable input (a plain numpy array) would be staged by the driver on one thread: the workers
     // narrow it into pinned int32 staging instead, and that goes to the device
     const bool pageable_in = is_pageable(v);
@@ -828,6 +857,7 @@ int p2v_node_depths_batch(const void* v_or_matrix, int idx_bytes, const double* 
 }
 int p2v_vcv_host(const void* v, int idx_bytes, const double* bls, int64_t B, int64_t k, int64_t row_begin,
                  int64_t row_end, double* out, int32_t* status) {
+    HostTrim trim_on_return;
     if (idx_bytes != 4 && idx_bytes != 8) return fail(P2V_ERR_INVALID_ARG, "idx_bytes must be 4 or 8");
     int rc = vcv_check(k);
     if (rc) return rc;
@@ -835,12 +865,14 @@ int p2v_vcv_host(const void* v, int idx_bytes, const double* bls, int64_t B, int
 }
 int p2v_vcv_matrix_host(const double* m, int64_t B, int64_t k, int64_t row_begin, int64_t row_end, double* out,
                         int32_t* status) {
+    HostTrim trim_on_return;
     int rc = vcv_check(k);
     if (rc) return rc;
     return coph_host(m, 0, nullptr, B, k, 0, row_begin, row_end, out, status, 1);
 }
 int p2v_node_depths_host(const void* v_or_matrix, int idx_bytes, const double* bls, int64_t B, int64_t k,
                          double* out, int32_t* status) {
+    HostTrim trim_on_return;
     if (idx_bytes != 0 && idx_bytes != 4 && idx_bytes != 8) return fail(P2V_ERR_INVALID_ARG, "idx_bytes must be 0, 4 or 8");
     return coph_host(v_or_matrix, idx_bytes, bls, B, k, 0, 0, k + 1, out, status, 2);
 }
@@ -1034,6 +1066,7 @@ int p2v_balance_batch(const void* v, int idx_bytes, int64_t B, int64_t k, double
     return from_cuda(launch_balance(v, idx_bytes, B, k, out, status, ws, ws_bytes, (cudaStream_t)stream), "balance launch");
 }
 int p2v_balance_host(const void* v, int idx_bytes, int64_t B, int64_t k, double* out, int32_t* status) {
+    HostTrim trim_on_return;
     int rc = balance_check(v, out, idx_bytes, B, k);
     if (rc) return rc;
     return host_chunked(
@@ -1084,6 +1117,7 @@ int p2v_to_newick_batch(const void* v, int idx_bytes, int64_t B, int64_t k, char
 }
 int p2v_to_newick_host(const void* v, int idx_bytes, int64_t B, int64_t k, char* out, int64_t out_stride,
                        int64_t* lengths, int32_t* status) {
+    HostTrim trim_on_return;
     int rc = newick_check(v, out, idx_bytes, B, k, out_stride);
     if (rc) return rc;
     if (B == 0) return P2V_OK;
@@ -1136,6 +1170,7 @@ int p2v_from_newick_batch(const char* newick, int64_t in_stride, const int64_t* 
 }
 int p2v_from_newick_host(const char* newick, int64_t in_stride, int64_t B, int64_t k, void* v, int idx_bytes,
                          int32_t* status) {
+    HostTrim trim_on_return;
     int rc = from_newick_check(newick, in_stride, v, idx_bytes, B, k);
     if (rc) return rc;
     if (k == 0) { if (status && B > 0) memset(status, 0, sizeof(int32_t) * B); return P2V_OK; }
@@ -1148,9 +1183,11 @@ int p2v_from_newick_host(const char* newick, int64_t in_stride, int64_t B, int64
 }
 
 int p2v_to_pairs_host(const void* v, int idx_bytes, int64_t B, int64_t k, void* out, int32_t* status) {
+    HostTrim trim_on_return;
     return decode_host(MODE_PAIRS, 2, v, idx_bytes, B, k, out, status);
 }
 int p2v_to_ancestry_host(const void* v, int idx_bytes, int64_t B, int64_t k, void* out, int32_t* status) {
+    HostTrim trim_on_return;
     // big int64 batches: two int32 columns over PCIe, widened by host threads (see ancestry_host_compact)
     if (idx_bytes == 8 && k > 0 && k <= 0x3FFFFFFF / 2 && B * k >= ((int64_t)1 << 22) && host_compact_enabled()) {
         int rc = check_common(v, out, idx_bytes, B, k);
@@ -1160,18 +1197,23 @@ int p2v_to_ancestry_host(const void* v, int idx_bytes, int64_t B, int64_t k, voi
     return decode_host(MODE_ANCESTRY, 3, v, idx_bytes, B, k, out, status);
 }
 int p2v_to_edges_host(const void* v, int idx_bytes, int64_t B, int64_t k, void* out, int32_t* status) {
+    HostTrim trim_on_return;
     return decode_host(MODE_EDGES, 4, v, idx_bytes, B, k, out, status);
 }
 int p2v_from_pairs_host(const void* in, int idx_bytes, int64_t B, int64_t k, void* v, int32_t* status) {
+    HostTrim trim_on_return;
     return encode_host(FROM_PAIRS, 2, in, idx_bytes, B, k, v, status);
 }
 int p2v_from_ancestry_host(const void* in, int idx_bytes, int64_t B, int64_t k, void* v, int32_t* status) {
+    HostTrim trim_on_return;
     return encode_host(FROM_ANCESTRY, 3, in, idx_bytes, B, k, v, status);
 }
 int p2v_from_edges_host(const void* in, int idx_bytes, int64_t B, int64_t k, void* v, int32_t* status) {
+    HostTrim trim_on_return;
     return encode_host(FROM_EDGES, 4, in, idx_bytes, B, k, v, status);
 }
 int p2v_check_v_host(const void* v, int idx_bytes, int64_t B, int64_t k, int32_t* status) {
+    HostTrim trim_on_return;
     if (!status) return fail(P2V_ERR_INVALID_ARG, "status is required");
     int rc = check_common(v, status, idx_bytes, B, k);
     if (rc) return rc;
@@ -1184,15 +1226,54 @@ int p2v_check_v_host(const void* v, int idx_bytes, int64_t B, int64_t k, int32_t
 }
 int p2v_cophenetic_host(const void* v, int idx_bytes, const double* bls, int64_t B, int64_t k, int unrooted,
                         int64_t row_begin, int64_t row_end, double* out, int32_t* status) {
+    HostTrim trim_on_return;
     if (idx_bytes != 4 && idx_bytes != 8) return fail(P2V_ERR_INVALID_ARG, "idx_bytes must be 4 or 8");
     return coph_host(v, idx_bytes, bls, B, k, unrooted, row_begin, row_end, out, status);
 }
 int p2v_cophenetic_matrix_host(const double* m, int64_t B, int64_t k, int unrooted, int64_t row_begin,
                                int64_t row_end, double* out, int32_t* status) {
+    HostTrim trim_on_return;
     return coph_host(m, 0, nullptr, B, k, unrooted, row_begin, row_end, out, status);
 }
 
 void p2v_host_release(void) { g_host.release(); g_compact.release(); g_stage.release(); }
+int64_t p2v_host_cache_bytes(void) { return (int64_t)(g_host.bytes() + g_stage.bytes() + g_compact.bytes()); }
+void p2v_host_cache_limit(int64_t bytes) { g_host_cache_limit.store(bytes, std::memory_order_relaxed); }
+
+// ---- check_m (matrix/base.rs:76-95) ---------------------------------------------------------
+static int check_m_args(const double* m, const int32_t* status, int64_t B, int64_t k) {
+    if (!status) return fail(P2V_ERR_INVALID_ARG, "status is required");
+    if (B < 0 || k < 0) return fail(P2V_ERR_INVALID_ARG, "negative batch or length");
+    if (B > 0 && k > 0 && !m) return fail(P2V_ERR_INVALID_ARG, "null buffer");
+    if (k > LARGE_K_MAX) return fail(P2V_ERR_UNSUPPORTED, "k above the supported maximum (2^19)");
+    return P2V_OK;
+}
+int p2v_check_m_batch(const double* m, int64_t B, int64_t k, int32_t* status, p2v_stream_t stream) {
+    int rc = check_m_args(m, status, B, k);
+    if (rc) return rc;
+    if (B == 0) return P2V_OK;
+    if (k == 0) return from_cuda(cudaMemsetAsync(status, 0, sizeof(int32_t) * B, (cudaStream_t)stream), "memset");
+    return from_cuda(launch_check_m(m, m + 1, 3, 3 * k, B, k, status, 0, (cudaStream_t)stream), "check_m launch");
+}
+int p2v_check_m_host(const double* m, int64_t B, int64_t k, int32_t* status) {
+    HostTrim trim_on_return;
+    int rc = check_m_args(m, status, B, k);
+    if (rc) return rc;
+    if (k == 0 || B == 0) { if (B > 0) memset(status, 0, sizeof(int32_t) * B); return P2V_OK; }
+    return host_chunked(
+        m, (size_t)k * 3 * sizeof(double), nullptr, 0, status, B, [&](int64_t) { return (size_t)0; },
+        [&](void* din, void*, int32_t* dst, int64_t nb, void*, size_t, cudaStream_t st) {
+            const double* dm = static_cast<const double*>(din);
+            return launch_check_m(dm, dm + 1, 3, 3 * k, nb, k, dst, 0, st);
+        });
+}
+
+// profiling aid: which = 0 decode_large_kernel, 1 tables_kernel (whole-grid forms); out[64] u64
+int p2v_debug_phase_ns(int which, uint64_t* out) {
+    cudaDeviceSynchronize();
+    return from_cuda(which ? debug_phase_ns_coph((unsigned long long*)out) : debug_phase_ns_decode((unsigned long long*)out),
+                     "phase stamps");
+}
 
 int p2v_fill_f64(double* out, int64_t count, double value, p2v_stream_t stream) {
     if (count > 0 && !out) return fail(P2V_ERR_INVALID_ARG, "null buffer");

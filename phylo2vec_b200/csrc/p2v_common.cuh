@@ -88,24 +88,79 @@ __device__ __forceinline__ void count_smaller_step(uint32_t& cnt, uint32_t mine,
         : "r"(mine), "r"(d));
 }
 
-// ---- teams: one CTA, or a thread-block cluster of CSIZE CTAs working on one tree ---------
+// ---- phase stamps of the team kernels (profiling aid) -----------------------------------------
+// Thread 0 of team CTA 0 stores the global nanosecond timer at phase boundaries; p2v_debug_phase_ns()
+// copies the stamps out.  One predicated store per phase: left in release builds.
+constexpr int PHASE_SLOTS = 64;
+static __device__ unsigned long long g_phase_ns[PHASE_SLOTS];    // one copy per translation unit
+__device__ __forceinline__ void phase_stamp(int slot, bool who) {
+    if (who) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_phase_ns[slot] = t;
+    }
+}
+
+// ---- teams: the CTAs that work on one tree ------------------------------------------------
+// CSIZE = 1: one CTA; CSIZE > 1: a thread-block cluster of CSIZE CTAs (hardware cluster barrier);
+// CSIZE = 0: the whole grid of a cooperative launch (one huge tree on all SMs, grid barrier).
 template <int CSIZE>
 __device__ __forceinline__ void team_sync() {
     if (CSIZE == 1) __syncthreads();
+    else if (CSIZE == 0) cooperative_groups::this_grid().sync();
     else cooperative_groups::this_cluster().sync();
 }
 template <int CSIZE>
 __device__ __forceinline__ int team_rank() {
-    return (CSIZE == 1) ? 0 : (int)cooperative_groups::this_cluster().block_rank();
+    if (CSIZE == 1) return 0;
+    if (CSIZE == 0) return (int)blockIdx.x;
+    return (int)cooperative_groups::this_cluster().block_rank();
 }
+// CTAs per team, number of teams in the grid, index of this CTA's team
+template <int CSIZE>
+__device__ __forceinline__ int team_ctas() { return CSIZE == 0 ? (int)gridDim.x : CSIZE; }
+template <int CSIZE>
+__device__ __forceinline__ int64_t team_count() { return CSIZE == 0 ? 1 : (int64_t)(gridDim.x / CSIZE); }
+template <int CSIZE>
+__device__ __forceinline__ int64_t team_index() { return CSIZE == 0 ? 0 : (int64_t)(blockIdx.x / CSIZE); }
 // OR of `live` over the whole team; `flag` is a zero-initialised word owned by the team
 template <int CSIZE>
 __device__ __forceinline__ int team_any(int live, int* flag) {
     const int any_cta = __syncthreads_or(live);
     if (CSIZE == 1) return any_cta;
     if (threadIdx.x == 0 && any_cta) atomicOr(flag, 1);
-    cooperative_groups::this_cluster().sync();
+    team_sync<CSIZE>();
     return *reinterpret_cast<volatile int*>(flag);
+}
+
+// Cooperative launch of a CSIZE = 0 kernel: at most `want_ctas` CTAs, never more than are co-resident
+// (the grid barrier needs every CTA on an SM).  false: not launched (the caller falls back).
+template <typename Kern, typename... Args>
+static inline bool launch_grid_team(Kern kern, int threads, size_t smem, int want_ctas, cudaStream_t stream,
+                                    Args... args) {
+    int dev = 0, coop = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return false; }
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!coop || sms <= 0) return false;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        return false;
+    }
+    int grid = want_ctas < 1 ? 1 : want_ctas;
+    if (grid > sms * per_sm) grid = sms * per_sm;
+    void* argv[] = {(void*)&args...};
+    if (cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)grid), dim3((unsigned)threads), argv, smem,
+                                    stream) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return true;
 }
 
 // ---- double-double helpers (fp64 branch-length depths) --------------------

@@ -48,6 +48,10 @@ namespace cg = cooperative_groups;
 
 namespace p2v {
 
+cudaError_t debug_phase_ns_coph(unsigned long long* out) {
+    return cudaMemcpyFromSymbol(out, g_phase_ns, sizeof(unsigned long long) * PHASE_SLOTS);
+}
+
 constexpr int TAB_THREADS = 1024;
 constexpr int TAB_CLUSTER = 16;            // CTAs per tree when there are few, large trees
 constexpr int TAB_FLAGS = 128;             // per-tree convergence flags (one per jumping round)
@@ -89,7 +93,7 @@ constexpr int KEY_INF = 0x3FFFFFFF;
 
 struct CophLayout {
     // byte offsets inside one tree's table area
-    size_t anc, jA, jDI, jDH, jDL, tn, tc, pos, leaf_at, sepk, sephi, seplo;     // prepare
+    size_t anc, jAD, jDD, jDI, jDH, jDL, tn, tc, pos, leaf_at, sepk, sephi, seplo;     // prepare
     size_t blk_of, rowlist, prek, prea, sufk, sufa, bstart, bend, rowoff, cend, blkk, blka, tilelist, hdr, flags;  // rows call (+ flags: prepare)
     size_t c_blk, c_prek, c_sufk, c_prehi, c_prelo, c_sufhi, c_suflo;      // rows call, by leaf label
     size_t total;
@@ -104,11 +108,12 @@ __host__ __device__ inline CophLayout coph_layout(int64_t k) {
     L.nbmax = L.n / 32 + L.n / 32 + 4;     // bound on block ids for any call (pcap >= 32, rcap >= 32)
     size_t o = 0;
     L.anc = o; o = al16(o + 4 * 3 * (size_t)k);
-    L.jA = o; o = al16(o + 4 * 2 * (size_t)L.N);
-    L.jDI = o; o = al16(o + 4 * 2 * (size_t)L.N);
-    L.jDH = o; o = al16(o + 8 * 2 * (size_t)L.N);
-    L.jDL = o; o = al16(o + 8 * 2 * (size_t)L.N);
-    L.tn = o; o = al16(o + 4 * 2 * (size_t)L.A);
+    L.jAD = o; o = al16(o + 8 * 2 * (size_t)L.N);      // jumping buffers: (ancestor, int depth) x 2
+    L.jDD = o; o = al16(o + 16 * 2 * (size_t)L.N);     //                  double-double depth x 2
+    L.jDI = o; o = al16(o + 4 * (size_t)L.N);          // results: depth of every node (int, dd hi, dd lo)
+    L.jDH = o; o = al16(o + 8 * (size_t)L.N);
+    L.jDL = o; o = al16(o + 8 * (size_t)L.N);
+    L.tn = o; o = al16(o + 4 * (2 * (size_t)L.A + 16));   // dl x 2 buffers, then the (next leaf, count) list x 2
     L.tc = o; o = al16(o + 4 * 2 * (size_t)L.A);
     L.pos = o; o = al16(o + 4 * (size_t)L.n);
     L.leaf_at = o; o = al16(o + 4 * (size_t)L.n);
@@ -170,6 +175,64 @@ __global__ void matrix_v_kernel(const double* __restrict__ m, int64_t count, int
     }
 }
 
+// check_m (matrix/base.rs:76-95), one warp per tree.  bl == m + 1, bl_stride == 3 for a (k,3) matrix.
+//   v_from_matrix: also check_v on column 0 cast like `as usize` (negatives and NaN -> 0, too big
+//   saturates): status = first i with v[i] > 2i, + 1.
+//   Lengths: any bl < 0 or NaN ("Branch lengths must be positive") -> P2V_TREE_NEGATIVE_BRANCH,
+//   only for trees whose status is still 0 (keep_status: the v part was checked by the decoder).
+__global__ void check_m_kernel(const double* __restrict__ m, const double* __restrict__ bl, int bl_stride,
+                               int64_t bl_tree_stride, int64_t B, int k, int32_t* __restrict__ status,
+                               int keep_status) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t tree = wid; tree < B; tree += nwarps) {
+        int st = keep_status ? status[tree] : 0;
+        if (m && st == 0) {
+            const double* mt = m + tree * 3 * (int64_t)k;
+            for (int b = 0; b < k; b += 32) {
+                const int i = b + lane;
+                const bool bad = (i < k) && (mt[3 * (size_t)i] >= 2.0 * i + 1.0);     // (x as usize) > 2i
+                const unsigned bm = __ballot_sync(FULL, bad);
+                if (bm) { st = b + __ffs(bm); break; }
+            }
+        }
+        if (bl && st == 0) {
+            const double* bt = bl + tree * bl_tree_stride;
+            bool neg = false;
+            for (int i = lane; i < k; i += 32) {
+                const double b1 = bt[(size_t)i * bl_stride], b2 = bt[(size_t)i * bl_stride + 1];
+                neg |= !(b1 >= 0.0 && b2 >= 0.0);
+            }
+            if (__any_sync(FULL, neg)) st = -3;   // P2V_TREE_NEGATIVE_BRANCH
+        }
+        if (lane == 0) status[tree] = st;
+    }
+}
+
+// The distance path's own guard: a tree with a negative or NaN branch length gets
+// P2V_TREE_NEGATIVE_BRANCH (if its vector was valid) instead of a silently wrong matrix -- the
+// three-term distance assumes depth grows downwards.  One thread per row of the batch.
+__global__ void flag_negative_bl_kernel(const double* __restrict__ bl, int bl_stride, int64_t bl_tree_stride,
+                                        int64_t B, int k, int32_t* __restrict__ status) {
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < B * k; w += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t tree = w / k;
+        const int i = (int)(w - tree * k);
+        const double* bt = bl + tree * bl_tree_stride + (size_t)i * bl_stride;
+        if (!(bt[0] >= 0.0 && bt[1] >= 0.0)) atomicCAS(status + tree, 0, -3);
+    }
+}
+
+cudaError_t launch_check_m(const double* m, const double* bl, int bl_stride, int64_t bl_tree_stride, int64_t B,
+                           int64_t k, int32_t* status, int keep_status, cudaStream_t stream) {
+    if (B <= 0) return cudaSuccess;
+    const int64_t want = (B * 32 + 255) / 256, cap = (int64_t)sm_count() * 8;
+    check_m_kernel<<<(int)(want < cap ? want : cap), 256, 0, stream>>>(m, bl, bl_stride, bl_tree_stride, B, (int)k,
+                                                                      status, keep_status);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // ---- k < 2 special cases (graph.rs:28-42) ---------------------------------------------
 __global__ void tiny_sum_kernel(const double* __restrict__ bl, int64_t bl_tree_stride, int64_t B,
                                 double* __restrict__ sums) {
@@ -221,9 +284,15 @@ __global__ void node_depths_kernel(const unsigned char* __restrict__ tab, size_t
 }
 
 // ---- 2. per-tree tables ------------------------------------------------------------------
-// A team of CSIZE CTAs works on one tree: CSIZE = 1 for batches (one CTA per tree), a thread-block
-// cluster of TAB_CLUSTER CTAs when there are only a few large trees (the jumping rounds are then
-// spread over 16 SMs and separated by cluster barriers).
+// A team of CTAs works on one tree: one CTA per tree for batches (CSIZE = 1); for a few large trees
+// a thread-block cluster of TAB_CLUSTER CTAs (the jumping rounds spread over 16 SMs, cluster
+// barriers), and for one to four huge trees the whole cooperatively launched grid (CSIZE = 0: every
+// round is bound by scattered L2 accesses per SM, so all 148 SMs take a tree together and the trees
+// go one after the other).
+// The pointer jumping is radix 4: a round composes the current jump four times (three dependent
+// gathers), so root-path sums and the leaf ranking take ceil(log4) rounds -- half the barriers of
+// the radix-2 form for 1.5x the gathers.  (ancestor, int depth) travel as one int2 and the
+// double-double depth as one double2; the latter only exist for weighted trees.
 template <int CSIZE>
 __global__ void __launch_bounds__(TAB_THREADS)
 tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* __restrict__ bl,
@@ -232,14 +301,16 @@ tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* 
     const CophLayout L = coph_layout(k);
     const int crank = team_rank<CSIZE>();
     const int tid = crank * TAB_THREADS + threadIdx.x;       // thread index inside the team
-    constexpr int TT = CSIZE * TAB_THREADS;                   // threads per team
+    const int TT = team_ctas<CSIZE>() * TAB_THREADS;          // threads per team
     const int n = L.n, N = L.N, root = 2 * k;
-    const int64_t team = blockIdx.x / CSIZE, nteams = gridDim.x / CSIZE;
+    const bool weighted = bl != nullptr;
+    const int64_t team = team_index<CSIZE>(), nteams = team_count<CSIZE>();
     for (int64_t tree = team; tree < B; tree += nteams) {
         if (status && status[tree] != 0) continue;   // uniform per team
         unsigned char* T = tab + (size_t)tree * tab_stride;
         const int* anc = reinterpret_cast<const int*>(T + L.anc);
-        int* jA = reinterpret_cast<int*>(T + L.jA);
+        int2* jAD = reinterpret_cast<int2*>(T + L.jAD);
+        double2* jDD = reinterpret_cast<double2*>(T + L.jDD);
         int* jDI = reinterpret_cast<int*>(T + L.jDI);
         double* jDH = reinterpret_cast<double*>(T + L.jDH);
         double* jDL = reinterpret_cast<double*>(T + L.jDL);
@@ -253,67 +324,76 @@ tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* 
         int* flags = reinterpret_cast<int*>(T + L.flags);
         const double* blt = bl ? bl + tree * bl_tree_stride : nullptr;
 
+        phase_stamp(15, CSIZE == 0 && tid == 0);
         if (tid < TAB_FLAGS) flags[tid] = 0;
         // parents and edge weights (row r of bls: lengths above ancestry[r][0], [r][1];
-        // graph.rs:57-58).  jA/jDI/jDH/jDL buffer 0 = initial state of the jumping.
-        for (int r = tid; r < k; r += TT) {
-            const int c1 = anc[3 * r], c2 = anc[3 * r + 1], p = k + 1 + r;
-            double b1 = 1.0, b2 = 1.0;
-            if (blt) { b1 = blt[(size_t)r * bl_stride]; b2 = blt[(size_t)r * bl_stride + 1]; }
-            int w1 = 1, w2 = 1;
-            if (unrooted) {
-                if (c1 == 2 * k - 1) { w1 = 0; b1 = 0.0; }
-                if (c2 == 2 * k - 1) { w2 = 0; b2 = 0.0; }
-            }
-            jA[c1] = p; jA[c2] = p;
-            jDI[c1] = w1; jDI[c2] = w2;
-            jDH[c1] = b1; jDH[c2] = b2;
-            jDL[c1] = 0.0; jDL[c2] = 0.0;
-        }
-        if (tid == 0) { jA[root] = -1; jDI[root] = 0; jDH[root] = 0.0; jDL[root] = 0.0; }
-        team_sync<CSIZE>();
+        // graph.rs:57-58).  Buffer 0 of jAD / jDD = initial state of the jumping.
         // first / second child pointers for the leftmost / rightmost-leaf jumping (leaves: themselves).
         // dl = tn[0 .. 2N), dr = tc[0 .. 2N) (two buffers each); the leaf list lives behind them.
         int* dl = tn; int* dr = tc;
-        int* lnx = tn + 2 * N; int* lct = tc + 2 * N;        // 2 buffers x n each (2N + 2n <= 8k)
-        for (int u = tid; u < N; u += TT) {
-            int l = u, r = u;
-            if (u > k) { l = anc[3 * (u - k - 1)]; r = anc[3 * (u - k - 1) + 1]; }
-            dl[u] = l; dr[u] = r;
+        int2* lnc = reinterpret_cast<int2*>(tn + 2 * N);     // 2 buffers x n (next leaf, count): 2N + 4n <= 8k
+        for (int r = tid; r < k; r += TT) {
+            const int c1 = anc[3 * r], c2 = anc[3 * r + 1], p = k + 1 + r;
+            int w1 = 1, w2 = 1;
+            if (unrooted) {
+                if (c1 == 2 * k - 1) w1 = 0;
+                if (c2 == 2 * k - 1) w2 = 0;
+            }
+            jAD[c1] = make_int2(p, w1); jAD[c2] = make_int2(p, w2);
+            if (weighted) {
+                const double b1 = w1 ? blt[(size_t)r * bl_stride] : 0.0;
+                const double b2 = w2 ? blt[(size_t)r * bl_stride + 1] : 0.0;
+                jDD[c1] = make_double2(b1, 0.0); jDD[c2] = make_double2(b2, 0.0);
+            }
+            dl[p] = c1; dr[p] = c2;
         }
+        for (int c = tid; c <= k; c += TT) { dl[c] = c; dr[c] = c; }
+        if (tid == 0) { jAD[root] = make_int2(-1, 0); if (weighted) jDD[root] = make_double2(0.0, 0.0); }
         team_sync<CSIZE>();
-        // root-path sums by pointer jumping; an even number of rounds leaves the result in buffer 0
+        phase_stamp(0, CSIZE == 0 && tid == 0);
+        // root-path sums and leftmost / rightmost leaves by pointer jumping
         int fround = 0;
-        {
-            int cur = 0;
-            for (;; ++fround) {
-                const int* a_in = jA + cur * N; int* a_out = jA + (cur ^ 1) * N;
-                const int* i_in = jDI + cur * N; int* i_out = jDI + (cur ^ 1) * N;
-                const double* h_in = jDH + cur * N; double* h_out = jDH + (cur ^ 1) * N;
-                const double* l_in = jDL + cur * N; double* l_out = jDL + (cur ^ 1) * N;
-                const int* dl_in = dl + cur * N; int* dl_out = dl + (cur ^ 1) * N;
-                const int* dr_in = dr + cur * N; int* dr_out = dr + (cur ^ 1) * N;
-                int live = 0;
+        int cur = 0;
+        for (;; ++fround) {
+            const int2* a_in = jAD + cur * N; int2* a_out = jAD + (cur ^ 1) * N;
+            const double2* d_in = jDD + cur * N; double2* d_out = jDD + (cur ^ 1) * N;
+            const int* dl_in = dl + cur * N; int* dl_out = dl + (cur ^ 1) * N;
+            const int* dr_in = dr + cur * N; int* dr_out = dr + (cur ^ 1) * N;
+            int live = 0;
 #pragma unroll 2
-                for (int u = tid; u < N; u += TT) {
-                    const int nl = dl_in[dl_in[u]], nr = dr_in[dr_in[u]];   // leaves are fixed points
-                    dl_out[u] = nl; dr_out[u] = nr;
-                    live |= (nl > k) | (nr > k);
-                    const int a = a_in[u];
-                    int di = i_in[u];
-                    dd d = {h_in[u], l_in[u]};
-                    int na = -1;
-                    if (a >= 0) {
-                        di += i_in[a];
-                        d = dd_add(d, dd{h_in[a], l_in[a]});
-                        na = a_in[a];
-                        live |= (na >= 0);
+            for (int u = tid; u < N; u += TT) {
+                int nl = dl_in[u], nr = dr_in[u];               // leaves are fixed points
+                int2 s = a_in[u];
+                dd d = {0.0, 0.0};
+                if (weighted) { const double2 x = d_in[u]; d = dd{x.x, x.y}; }
+#pragma unroll
+                for (int hop = 0; hop < 3; ++hop) {
+                    nl = dl_in[nl]; nr = dr_in[nr];
+                    if (s.x >= 0) {
+                        const int a = s.x;
+                        const int2 t = a_in[a];
+                        if (weighted) { const double2 x = d_in[a]; d = dd_add(d, dd{x.x, x.y}); }
+                        s.x = t.x; s.y += t.y;
                     }
-                    a_out[u] = na; i_out[u] = di; h_out[u] = d.hi; l_out[u] = d.lo;
                 }
-                cur ^= 1;
-                const int any = team_any<CSIZE>(live, flags + min(fround, TAB_FLAGS - 1));
-                if (!any && cur == 0) { ++fround; break; }
+                live |= (nl > k) | (nr > k) | (s.x >= 0);
+                dl_out[u] = nl; dr_out[u] = nr;
+                a_out[u] = s;
+                if (weighted) d_out[u] = make_double2(d.hi, d.lo);
+            }
+            cur ^= 1;
+            const int any = team_any<CSIZE>(live, flags + min(fround, TAB_FLAGS - 1));
+            if (!any) { ++fround; break; }
+        }
+        phase_stamp(1, CSIZE == 0 && tid == 0);
+        if (CSIZE == 0 && tid == 0) g_phase_ns[16] = (unsigned long long)fround;
+        dl += cur * N; dr += cur * N;
+        {   // depth of every node, where the other kernels read it
+            const int2* a_res = jAD + cur * N;
+            const double2* d_res = jDD + cur * N;
+            for (int u = tid; u < N; u += TT) {
+                jDI[u] = a_res[u].y;
+                if (weighted) { const double2 x = d_res[u]; jDH[u] = x.x; jDL[u] = x.y; }
             }
         }
         // The leaves as a linked list in DFS order: every internal node links the last leaf of its
@@ -321,45 +401,53 @@ tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* 
         // pair); ranking the list by pointer jumping gives the DFS positions.
         for (int r = tid; r < k; r += TT) {
             const int a = dr[anc[3 * r]], b = dl[anc[3 * r + 1]];
-            lnx[a] = b; lct[a] = 1;
+            lnc[a] = make_int2(b, 1);
         }
-        if (tid == 0) { const int e = dr[root]; lnx[e] = -1; lct[e] = 0; }
+        if (tid == 0) lnc[dr[root]] = make_int2(-1, 0);
         team_sync<CSIZE>();
         int lc = 0;
         for (;; ++fround) {
-            const int* n_in = lnx + lc * n; int* n_out = lnx + (lc ^ 1) * n;
-            const int* c_in = lct + lc * n; int* c_out = lct + (lc ^ 1) * n;
+            const int2* in = lnc + lc * n; int2* out = lnc + (lc ^ 1) * n;
             int live = 0;
-#pragma unroll 4
+#pragma unroll 2
             for (int x = tid; x < n; x += TT) {
-                const int nx = n_in[x];
-                int c = c_in[x];
-                int nn = -1;
-                if (nx >= 0) {
-                    c += c_in[nx];
-                    nn = n_in[nx];
-                    live |= (nn >= 0);
+                int2 s = in[x];
+#pragma unroll
+                for (int hop = 0; hop < 3; ++hop) {
+                    if (s.x >= 0) { const int2 t = in[s.x]; s.x = t.x; s.y += t.y; }
                 }
-                n_out[x] = nn; c_out[x] = c;
+                live |= (s.x >= 0);
+                out[x] = s;
             }
             lc ^= 1;
             const int any = team_any<CSIZE>(live, flags + min(fround, TAB_FLAGS - 1));
             if (!any) break;
         }
-        const int* after = lct + lc * n;              // number of leaves after this one
+        phase_stamp(2, CSIZE == 0 && tid == 0);
+        if (CSIZE == 0 && tid == 0) g_phase_ns[17] = (unsigned long long)fround;
+        const int2* after = lnc + lc * n;             // .y = number of leaves after this one
         // DFS positions of the leaves; separators by position
         for (int c = tid; c <= k; c += TT) {
-            const int p = k - after[c];
+            const int p = k - after[c].y;
             pos[c] = p;
             leaf_at[p] = c;
         }
-        if (tid == 0) { sepk[0] = KEY_INF; sephi[0] = 0.0; seplo[0] = 0.0; sepk[n] = KEY_INF; sephi[n] = 0.0; seplo[n] = 0.0; }
-        for (int u = k + 1 + tid; u <= 2 * k; u += TT) {
-            const int c1 = anc[3 * (u - k - 1) + 1];      // child 1: its first leaf opens the right part
-            const int r = k - after[dl[c1]];
-            sepk[r] = jDI[u]; sephi[r] = jDH[u]; seplo[r] = jDL[u];
+        if (tid == 0) {
+            sepk[0] = KEY_INF; sepk[n] = KEY_INF;
+            if (weighted) { sephi[0] = 0.0; seplo[0] = 0.0; sephi[n] = 0.0; seplo[n] = 0.0; }
+        }
+        {
+            const int2* a_res = jAD + cur * N;
+            const double2* d_res = jDD + cur * N;
+            for (int u = k + 1 + tid; u <= 2 * k; u += TT) {
+                const int c1 = anc[3 * (u - k - 1) + 1];      // child 1: its first leaf opens the right part
+                const int r = k - after[dl[c1]].y;
+                sepk[r] = a_res[u].y;
+                if (weighted) { const double2 x = d_res[u]; sephi[r] = x.x; seplo[r] = x.y; }
+            }
         }
         team_sync<CSIZE>();
+        phase_stamp(3, CSIZE == 0 && tid == 0);
     }
 }
 
@@ -372,22 +460,88 @@ __device__ __forceinline__ unsigned long long pack_key(int key, int p) {
     return ((unsigned long long)(unsigned)key << 32) | (unsigned)p;
 }
 
+// prefix / suffix minima of sep inside block `id` of one tree: one warp
+__device__ __forceinline__ void block_minima_one(unsigned char* T, const CophLayout& L, int id, int lane) {
+    const int* sepk = reinterpret_cast<const int*>(T + L.sepk);
+    int* prek = reinterpret_cast<int*>(T + L.prek);
+    int* prea = reinterpret_cast<int*>(T + L.prea);
+    int* sufk = reinterpret_cast<int*>(T + L.sufk);
+    int* sufa = reinterpret_cast<int*>(T + L.sufa);
+    int* blkk = reinterpret_cast<int*>(T + L.blkk);
+    int* blka = reinterpret_cast<int*>(T + L.blka);
+    const int lo = reinterpret_cast<const int*>(T + L.bstart)[id];
+    const int hi = reinterpret_cast<const int*>(T + L.bend)[id];
+    if (lo < 0) return;
+    unsigned long long carry = pack_key(KEY_INF, 0);
+    for (int base = lo; base < hi; base += 32) {       // pre[p] = min sep[lo..p]
+        const int p = base + lane;
+        unsigned long long m = (p < hi) ? pack_key(sepk[p], p) : pack_key(KEY_INF, 0);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long y = __shfl_up_sync(FULL, m, d);
+            if (lane >= d) m = min(m, y);
+        }
+        m = min(m, carry);
+        if (p < hi) { prek[p] = (int)(m >> 32); prea[p] = (int)(m & 0xFFFFFFFFu); }
+        carry = __shfl_sync(FULL, m, 31);
+    }
+    if (lane == 0) { blkk[id] = (int)(carry >> 32); blka[id] = (int)(carry & 0xFFFFFFFFu); }
+    carry = pack_key(KEY_INF, 0);
+    for (int base = lo + ((hi - lo - 1) / 32) * 32; base >= lo; base -= 32) {   // suf[p] = min sep[p+1..hi-1]
+        const int p = base + lane;
+        unsigned long long m = (p < hi) ? pack_key(sepk[p], p) : pack_key(KEY_INF, 0);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long y = __shfl_down_sync(FULL, m, d);
+            if (lane + d < 32) m = min(m, y);
+        }
+        unsigned long long ex = __shfl_down_sync(FULL, m, 1);
+        if (lane == 31) ex = pack_key(KEY_INF, 0);
+        ex = min(ex, carry);
+        if (p < hi) { sufk[p] = (int)(ex >> 32); sufa[p] = (int)(ex & 0xFFFFFFFFu); }
+        carry = min(carry, __shfl_sync(FULL, m, 0));
+    }
+}
+
+// Per-label copies of what rows_kernel needs about column j, so that its column setup is one level
+// of coalesced loads: block of the leaf, and the two in-block candidates (prefix / suffix minimum
+// at the leaf's position) with their double-double depths.
+__device__ __forceinline__ void column_tables_one(unsigned char* T, const CophLayout& L, int j, int weighted) {
+    const int p = reinterpret_cast<const int*>(T + L.pos)[j];
+    const int pk = reinterpret_cast<const int*>(T + L.prek)[p], sk = reinterpret_cast<const int*>(T + L.sufk)[p];
+    reinterpret_cast<int*>(T + L.c_blk)[j] = reinterpret_cast<const int*>(T + L.blk_of)[p];
+    reinterpret_cast<int*>(T + L.c_prek)[j] = pk;
+    reinterpret_cast<int*>(T + L.c_sufk)[j] = sk;
+    if (weighted) {
+        const double* sephi = reinterpret_cast<const double*>(T + L.sephi);
+        const double* seplo = reinterpret_cast<const double*>(T + L.seplo);
+        const int pa = reinterpret_cast<const int*>(T + L.prea)[p], sa = reinterpret_cast<const int*>(T + L.sufa)[p];
+        const bool hp = pk < KEY_INF, hs = sk < KEY_INF;
+        reinterpret_cast<double*>(T + L.c_prehi)[j] = hp ? sephi[pa] : 0.0;
+        reinterpret_cast<double*>(T + L.c_prelo)[j] = hp ? seplo[pa] : 0.0;
+        reinterpret_cast<double*>(T + L.c_sufhi)[j] = hs ? sephi[sa] : 0.0;
+        reinterpret_cast<double*>(T + L.c_suflo)[j] = hs ? seplo[sa] : 0.0;
+    }
+}
+
 // CSIZE > 1: a thread-block cluster per tree (few, large trees): every CTA takes a contiguous part
 // of the positions, the per-warp counts of requested rows go through global scratch.
+// CSIZE == 0 (the whole grid on one tree) also runs the block minima and the per-label column tables
+// behind two more grid barriers instead of two more launches.
 template <int CSIZE>
 __global__ void __launch_bounds__(BLK_THREADS)
 blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int k, int64_t row_begin,
-              int64_t row_end, int pcap, int rcap, const int32_t* __restrict__ status) {
+              int64_t row_end, int pcap, int rcap, const int32_t* __restrict__ status, int weighted) {
     __shared__ int s_part[BLK_THREADS / 32];
     __shared__ int s_total;
     const CophLayout L = coph_layout(k);
     const int tid = threadIdx.x, lane = tid & 31;
     const int crank = team_rank<CSIZE>();
     constexpr int NWC = BLK_THREADS / 32;          // warps per CTA
-    constexpr int NW = CSIZE * NWC;                // warps per team
+    const int NW = team_ctas<CSIZE>() * NWC;       // warps per team
     const int warp = crank * NWC + (tid >> 5);     // warp index inside the team
     const int n = L.n;
-    const int64_t team = blockIdx.x / CSIZE, nteams = gridDim.x / CSIZE;
+    const int64_t team = team_index<CSIZE>(), nteams = team_count<CSIZE>();
     for (int64_t tree = team; tree < B; tree += nteams) {
         if (status && status[tree] != 0) continue;
         unsigned char* T = tab + (size_t)tree * tab_stride;
@@ -404,7 +558,7 @@ blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int
 
         int* wcount = reinterpret_cast<int*>(T + L.tilelist);   // per-warp counts (tilelist is filled last)
         team_sync<CSIZE>();   // shared scratch of the previous tree is no longer read
-        for (int i = crank * BLK_THREADS + tid; i < L.nbmax; i += CSIZE * BLK_THREADS) {
+        for (int i = crank * BLK_THREADS + tid; i < L.nbmax; i += team_ctas<CSIZE>() * BLK_THREADS) {
             bstart[i] = -1; bend[i] = -1; rowoff[i] = 0; cend[i] = 0; blkk[i] = KEY_INF; blka[i] = -1;
         }
         // every warp owns a contiguous range of positions and reads it with coalesced loads
@@ -491,6 +645,14 @@ blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int
             }
             if (tid == 0) hdr[1] = base_count;
         }
+        if (CSIZE == 0) {
+            team_sync<CSIZE>();                       // hdr, bstart / bend of every block are final
+            const int nid = hdr[0];
+            for (int id = warp; id < nid; id += NW) block_minima_one(T, L, id, lane);
+            team_sync<CSIZE>();
+            for (int j = crank * BLK_THREADS + tid; j < n; j += team_ctas<CSIZE>() * BLK_THREADS)
+                column_tables_one(T, L, j, weighted);
+        }
     }
 }
 
@@ -512,14 +674,14 @@ static bool launch_blocks_cluster(unsigned char* tab, size_t tab_stride, int64_t
         cudaGetLastError();
         return false;
     }
-    if (cudaLaunchKernelEx(&cfg, kern, tab, tab_stride, B, k, row_begin, row_end, pcap, rcap, st) != cudaSuccess) {
+    if (cudaLaunchKernelEx(&cfg, kern, tab, tab_stride, B, k, row_begin, row_end, pcap, rcap, st, 0) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
     return true;
 }
 
-// prefix / suffix minima of sep inside every block: one warp per (tree, block), whole grid
+// one warp per (tree, block), whole grid
 __global__ void __launch_bounds__(256)
 block_minima_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int k,
                     const int32_t* __restrict__ status) {
@@ -532,55 +694,11 @@ block_minima_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t 
         const int id = (int)(w % L.nbmax);
         if (status && status[tree] != 0) continue;
         unsigned char* T = tab + (size_t)tree * tab_stride;
-        const int* hdr = reinterpret_cast<const int*>(T + L.hdr);
-        if (id >= hdr[0]) continue;
-        const int* sepk = reinterpret_cast<const int*>(T + L.sepk);
-        int* prek = reinterpret_cast<int*>(T + L.prek);
-        int* prea = reinterpret_cast<int*>(T + L.prea);
-        int* sufk = reinterpret_cast<int*>(T + L.sufk);
-        int* sufa = reinterpret_cast<int*>(T + L.sufa);
-        int* blkk = reinterpret_cast<int*>(T + L.blkk);
-        int* blka = reinterpret_cast<int*>(T + L.blka);
-        const int lo = reinterpret_cast<const int*>(T + L.bstart)[id];
-        const int hi = reinterpret_cast<const int*>(T + L.bend)[id];
-        if (lo < 0) continue;
-        {
-            unsigned long long carry = pack_key(KEY_INF, 0);
-            for (int base = lo; base < hi; base += 32) {       // pre[p] = min sep[lo..p]
-                const int p = base + lane;
-                unsigned long long m = (p < hi) ? pack_key(sepk[p], p) : pack_key(KEY_INF, 0);
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const unsigned long long y = __shfl_up_sync(FULL, m, d);
-                    if (lane >= d) m = min(m, y);
-                }
-                m = min(m, carry);
-                if (p < hi) { prek[p] = (int)(m >> 32); prea[p] = (int)(m & 0xFFFFFFFFu); }
-                carry = __shfl_sync(FULL, m, 31);
-            }
-            if (lane == 0) { blkk[id] = (int)(carry >> 32); blka[id] = (int)(carry & 0xFFFFFFFFu); }
-            carry = pack_key(KEY_INF, 0);
-            for (int base = lo + ((hi - lo - 1) / 32) * 32; base >= lo; base -= 32) {   // suf[p] = min sep[p+1..hi-1]
-                const int p = base + lane;
-                unsigned long long m = (p < hi) ? pack_key(sepk[p], p) : pack_key(KEY_INF, 0);
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const unsigned long long y = __shfl_down_sync(FULL, m, d);
-                    if (lane + d < 32) m = min(m, y);
-                }
-                unsigned long long ex = __shfl_down_sync(FULL, m, 1);
-                if (lane == 31) ex = pack_key(KEY_INF, 0);
-                ex = min(ex, carry);
-                if (p < hi) { sufk[p] = (int)(ex >> 32); sufa[p] = (int)(ex & 0xFFFFFFFFu); }
-                carry = min(carry, __shfl_sync(FULL, m, 0));
-            }
-        }
+        if (id >= reinterpret_cast<const int*>(T + L.hdr)[0]) continue;
+        block_minima_one(T, L, id, lane);
     }
 }
 
-// Per-label copies of what rows_kernel needs about a column, so that its column setup is one level
-// of coalesced loads: block of the leaf, and the two in-block candidates (prefix / suffix minimum
-// at the leaf's position) with their double-double depths.
 __global__ void __launch_bounds__(256)
 column_tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int k, int weighted,
                      const int32_t* __restrict__ status) {
@@ -590,22 +708,7 @@ column_tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t
         const int64_t tree = w / n;
         const int j = (int)(w % n);
         if (status && status[tree] != 0) continue;
-        unsigned char* T = tab + (size_t)tree * tab_stride;
-        const int p = reinterpret_cast<const int*>(T + L.pos)[j];
-        const int pk = reinterpret_cast<const int*>(T + L.prek)[p], sk = reinterpret_cast<const int*>(T + L.sufk)[p];
-        reinterpret_cast<int*>(T + L.c_blk)[j] = reinterpret_cast<const int*>(T + L.blk_of)[p];
-        reinterpret_cast<int*>(T + L.c_prek)[j] = pk;
-        reinterpret_cast<int*>(T + L.c_sufk)[j] = sk;
-        if (weighted) {
-            const double* sephi = reinterpret_cast<const double*>(T + L.sephi);
-            const double* seplo = reinterpret_cast<const double*>(T + L.seplo);
-            const int pa = reinterpret_cast<const int*>(T + L.prea)[p], sa = reinterpret_cast<const int*>(T + L.sufa)[p];
-            const bool hp = pk < KEY_INF, hs = sk < KEY_INF;
-            reinterpret_cast<double*>(T + L.c_prehi)[j] = hp ? sephi[pa] : 0.0;
-            reinterpret_cast<double*>(T + L.c_prelo)[j] = hp ? seplo[pa] : 0.0;
-            reinterpret_cast<double*>(T + L.c_sufhi)[j] = hs ? sephi[sa] : 0.0;
-            reinterpret_cast<double*>(T + L.c_suflo)[j] = hs ? seplo[sa] : 0.0;
-        }
+        column_tables_one(tab + (size_t)tree * tab_stride, L, j, weighted);
     }
 }
 
@@ -1496,6 +1599,11 @@ cudaError_t launch_cophenetic_prepare(const void* v_or_matrix, int idx_bytes, co
             tiny_sum_kernel<<<(int)((B + 255) / 256 < 1024 ? (B + 255) / 256 : 1024), 256, 0, stream>>>(
                 bl, bl_tree_stride, B, sums);
             count_launch();
+            if (bl) {
+                flag_negative_bl_kernel<<<(int)((B + 255) / 256 < 1024 ? (B + 255) / 256 : 1024), 256, 0, stream>>>(
+                    bl, bl_stride, bl_tree_stride, B, (int)k, st);
+                count_launch();
+            }
         }
     } else {
         const CophLayout L = coph_layout(k);
@@ -1504,9 +1612,21 @@ cudaError_t launch_cophenetic_prepare(const void* v_or_matrix, int idx_bytes, co
         e = launch_decode(MODE_ANCESTRY, vin, vin_bytes, B, k, tab + L.anc, st, wsb + W.dec, W.tab - W.dec,
                           stream, (int64_t)(L.total / sizeof(int)));
         if (e != cudaSuccess) return e;
+        if (bl) {
+            const int64_t want = (B * k + 255) / 256, capb = (int64_t)sm_count() * 8;
+            flag_negative_bl_kernel<<<(int)(want < capb ? want : capb), 256, 0, stream>>>(bl, bl_stride, bl_tree_stride,
+                                                                                       B, (int)k, st);
+            count_launch();
+        }
         const int64_t cap = (int64_t)sm_count() * 2;
         bool launched = false;
-        if (B * 8 <= sm_count() && k >= 4096) {
+        if (grid_team_trees(B, k)) {
+            // one to four huge trees: the whole grid works on one tree at a time (cooperative launch)
+            launched = launch_grid_team(tables_kernel<0>, TAB_THREADS, 0, grid_team_ctas(2 * k + 1, TAB_THREADS), stream,
+                                        tab, (size_t)L.total, bl, bl_stride, bl_tree_stride, B, (int)k, unrooted,
+                                        (const int32_t*)st);
+        }
+        if (!launched && B * 8 <= sm_count() && k >= 4096) {
             // few large trees: a thread-block cluster per tree (16 CTAs, else the portable 8)
             launched = launch_tables_cluster<TAB_CLUSTER>(tab, L.total, bl, bl_stride, bl_tree_stride, B, (int)k,
                                                           unrooted, st, stream) ||
@@ -1554,20 +1674,30 @@ cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t
     {
         const int64_t cap = (int64_t)sm_count() * 2;
         const int grid = (int)(B < cap ? B : cap);
-        bool launched = false;
-        if (B * 8 <= sm_count() && k >= 4096)    // few large trees: a cluster of 8 CTAs per tree
+        bool launched = false, fused = false;
+        if (grid_team_trees(B, k)) {
+            // one to four huge trees: blocks, block minima and column tables in one cooperative launch
+            int ctas = grid_team_ctas(n, BLK_THREADS);
+            if (ctas * (BLK_THREADS / 32) > L.nbmax) ctas = L.nbmax / (BLK_THREADS / 32);   // per-warp counts live in tilelist
+            if (ctas >= 1)
+                launched = fused = launch_grid_team(blocks_kernel<0>, BLK_THREADS, 0, ctas, stream, tab, (size_t)L.total, B,
+                                                    (int)k, row_begin, row_end, call.pcap, call.rcap, st, weighted);
+        }
+        if (!launched && B * 8 <= sm_count() && k >= 4096)    // few large trees: a cluster of 8 CTAs per tree
             launched = launch_blocks_cluster<8>(tab, L.total, B, (int)k, row_begin, row_end, call.pcap, call.rcap, st, stream);
         if (!launched)
-            blocks_kernel<1><<<grid, BLK_THREADS, 0, stream>>>(tab, L.total, B, (int)k, row_begin, row_end, call.pcap, call.rcap, st);
+            blocks_kernel<1><<<grid, BLK_THREADS, 0, stream>>>(tab, L.total, B, (int)k, row_begin, row_end, call.pcap, call.rcap, st, 0);
         count_launch();
-        const int64_t warps = B * (int64_t)L.nbmax;
-        const int64_t want = (warps + 7) / 8, cap2 = (int64_t)sm_count() * 8;
-        block_minima_kernel<<<(int)(want < cap2 ? want : cap2), 256, 0, stream>>>(tab, L.total, B, (int)k, st);
-        count_launch();
-        const int64_t want3 = (B * n + 255) / 256;
-        column_tables_kernel<<<(int)(want3 < cap2 * 4 ? want3 : cap2 * 4), 256, 0, stream>>>(tab, L.total, B, (int)k,
-                                                                                           weighted, st);
-        count_launch();
+        if (!fused) {
+            const int64_t warps = B * (int64_t)L.nbmax;
+            const int64_t want = (warps + 7) / 8, cap2 = (int64_t)sm_count() * 8;
+            block_minima_kernel<<<(int)(want < cap2 ? want : cap2), 256, 0, stream>>>(tab, L.total, B, (int)k, st);
+            count_launch();
+            const int64_t want3 = (B * n + 255) / 256;
+            column_tables_kernel<<<(int)(want3 < cap2 * 4 ? want3 : cap2 * 4), 256, 0, stream>>>(tab, L.total, B, (int)k,
+                                                                                               weighted, st);
+            count_launch();
+        }
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -1684,6 +1814,12 @@ static cudaError_t launch_cophenetic_small(const void* v_or_matrix, int idx_byte
     count_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (bl) {      // the matrices of such trees are already written and meaningless; the status says so
+        const int64_t want = (B * k + 255) / 256, capb = (int64_t)sm_count() * 8;
+        flag_negative_bl_kernel<<<(int)(want < capb ? want : capb), 256, 0, stream>>>(bl, bl_stride, bl_tree_stride, B,
+                                                                                   (int)k, st);
+        count_launch();
+    }
     if (status) e = cudaMemcpyAsync(status, st, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, stream);
     return e;
 }

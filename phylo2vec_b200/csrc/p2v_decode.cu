@@ -26,6 +26,10 @@
 
 namespace p2v {
 
+cudaError_t debug_phase_ns_decode(unsigned long long* out) {
+    return cudaMemcpyFromSymbol(out, g_phase_ns, sizeof(unsigned long long) * PHASE_SLOTS);
+}
+
 constexpr int SMALL_WARPS = 4;             // warps (= trees in flight) per CTA, small kernel
 
 // uint32 entries of the merge kernel's per-team work arrays (K = k rounded up to 32)
@@ -78,13 +82,13 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
     constexpr uint32_t ROOTBIT = 1u << (sizeof(WT) * 8 - 1);
     const int crank = team_rank<CSIZE>();
     const int tid = crank * THREADS + threadIdx.x;            // thread index inside the team
-    constexpr int TT = CSIZE * THREADS;
-    constexpr int NWT = TT / 32;
+    const int TT = team_ctas<CSIZE>() * THREADS;
+    const int NWT = TT / 32;
     const int lane = threadIdx.x & 31;
     const int gw = tid >> 5;                                   // warp index inside the team
     const int K = (k + 31) & ~31;
     const int nbat = K >> 5;
-    const int64_t team = blockIdx.x / CSIZE, nteams = gridDim.x / CSIZE;
+    const int64_t team = team_index<CSIZE>(), nteams = team_count<CSIZE>();
     const size_t tbl_entries = SMEMTBL ? (((size_t)k + 2 + 7) & ~(size_t)7) : 0;
     WT* wv = SMEMARR ? reinterpret_cast<WT*>(s_tbl + tbl_entries)
                      : reinterpret_cast<WT*>(ws + (size_t)team * ws_stride);
@@ -99,6 +103,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
 
     for (int64_t tree = team; tree < B; tree += nteams) {
         const IdxT* vt = v + tree * k;
+        phase_stamp(15, CSIZE == 0 && tid == 0);
         if (tid < 16) flags[tid] = 0;
         // ---- A: load, validate, narrow ---------------------------------------------------
         int badlocal = 0x7FFFFFFF;
@@ -108,6 +113,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
             wv[i] = (WT)x;
         }
         team_sync<CSIZE>();
+        phase_stamp(0, CSIZE == 0 && tid == 0);
         if (badlocal != 0x7FFFFFFF) atomicMax(&flags[1], K - badlocal);     // K - i >= 1
         team_sync<CSIZE>();
         const int badmark = *reinterpret_cast<volatile int*>(&flags[1]);
@@ -141,6 +147,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
             if (act) { rk0[b * 32 + p] = (WT)R; el0[b * 32 + p] = (WT)t; }
         }
         team_sync<CSIZE>();
+        phase_stamp(1, CSIZE == 0 && tid == 0);
 
         // ---- merge levels ----------------------------------------------------------------------
         int cur = 0;
@@ -175,6 +182,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
             cur ^= 1;
             team_sync<CSIZE>();
         }
+        phase_stamp(2, CSIZE == 0 && tid == 0);
         const WT* time_at = cur ? el1 : el0;                  // element at slot s
 
         // ---- labels: nearest root (rank-0 insertion) at or left of every slot ------------------
@@ -206,6 +214,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
             }
         }
         team_sync<CSIZE>();
+        phase_stamp(3, CSIZE == 0 && tid == 0);
         IdxT* ot = out + tree * out_stride;
         for (int g = gw; g < nbat; g += NWT) {
             const int s = g * 32 + lane;
@@ -221,6 +230,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
                 else wlab[s] = (WT)(lab | (root ? ROOTBIT : 0u));
             }
         }
+        phase_stamp(4, CSIZE == 0 && tid == 0);
         if (MODE == MODE_PAIRS) { team_sync<CSIZE>(); continue; }
 
         // ---- ancestry / edges, few large trees: the relabel sweep split over W warps ------------------
@@ -229,13 +239,14 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
         // prefix over the workers turns table w into "last row with label x before range w";
         // 3. every worker runs the sweep below on its range, starting from that state.
         const int K2 = K + 32;
-        const int W = (CSIZE > 1) ? (int)((ws_stride - large_base_stride((size_t)K)) / (size_t)K2) : 0;
-        if (CSIZE > 1 && W >= 2) {
+        const int W = (CSIZE != 1) ? (int)((ws_stride - large_base_stride((size_t)K)) / (size_t)K2) : 0;
+        if (CSIZE != 1 && W >= 2) {
             uint32_t* ptab = reinterpret_cast<uint32_t*>(ws + (size_t)team * ws_stride) + large_base_stride((size_t)K);
             for (size_t i = tid; i < (size_t)W * K2; i += TT) ptab[i] = NONE32;
             team_sync<CSIZE>();
+        phase_stamp(5, CSIZE == 0 && tid == 0);
             const int Wd = (W > 0) ? W : 1;
-            const int wstep = NWT / Wd;                      // workers are spread over the CTAs of the cluster
+            const int wstep = max(1, NWT / Wd);              // workers are spread over the CTAs of the team
             const bool worker = (gw % wstep) == 0 && (gw / wstep) < W;
             const int w = gw / wstep;
             const int bpw = (nbat + Wd - 1) / Wd;
@@ -252,6 +263,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
                 }
             }
             team_sync<CSIZE>();
+        phase_stamp(6, CSIZE == 0 && tid == 0);
             for (int x = tid; x < K2; x += TT) {             // exclusive prefix over the workers
                 uint32_t run = NONE32;
                 for (int ww = 0; ww < W; ++ww) {
@@ -261,6 +273,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
                 }
             }
             team_sync<CSIZE>();
+        phase_stamp(7, CSIZE == 0 && tid == 0);
             if (worker && b0 < b1) {
                 uint32_t nlab = (b0 * 32 + lane < k) ? (uint32_t)wlab[b0 * 32 + lane] : 0u;
                 uint32_t nt = (b0 * 32 + lane < k) ? (uint32_t)time_at[b0 * 32 + lane] : 0u;
@@ -293,6 +306,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
                 }
             }
             team_sync<CSIZE>();
+        phase_stamp(8, CSIZE == 0 && tid == 0);
             continue;
         }
 
@@ -422,14 +436,21 @@ static bool launch_large(const void* v, int64_t B, int64_t k, void* out, int64_t
         cudaGetLastError();
         return false;
     }
+    if (CSIZE == 0) {      // the whole cooperatively launched grid per tree
+        const IdxT* vp0 = (const IdxT*)v;
+        IdxT* op0 = (IdxT*)out;
+        uint32_t* wp0 = (uint32_t*)ws;
+        return launch_grid_team(kern, THREADS, smem, grid_team_ctas(k, THREADS), stream, vp0, B, (int)k, op0, out_stride,
+                                status, wp0, stride);
+    }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(teams * CSIZE));
+    cfg.gridDim = dim3((unsigned)(teams * (CSIZE ? CSIZE : 1)));
     cfg.blockDim = dim3(THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CSIZE; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = CSIZE ? CSIZE : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = (CSIZE > 1) ? 1 : 0;
     if (CSIZE > 1) {
         int max_clusters = 0;
@@ -498,7 +519,8 @@ static cudaError_t launch_decode_t(const void* v, int64_t B, int64_t k, void* ou
 #define P2V_LARGE(CS_, TH_)                                                                            \
         (smemtbl ? launch_large<IdxT, MODE, CS_, TH_, (MODE != MODE_PAIRS)>(v, B, k, out, out_stride, status, ws, stride, teams, smem, stream) \
                  : launch_large<IdxT, MODE, CS_, TH_, false>(v, B, k, out, out_stride, status, ws, stride, teams, smem, stream))
-        if (few_large) ok = P2V_LARGE(16, LARGE_THREADS_CLUSTER) || P2V_LARGE(8, LARGE_THREADS_CLUSTER);
+        if (few_large && grid_team_trees(B, k)) ok = P2V_LARGE(0, LARGE_THREADS_CLUSTER);
+        if (!ok && few_large) ok = P2V_LARGE(16, LARGE_THREADS_CLUSTER) || P2V_LARGE(8, LARGE_THREADS_CLUSTER);
         if (!ok) ok = P2V_LARGE(1, LARGE_THREADS_SINGLE);
 #undef P2V_LARGE
         if (!ok) return cudaErrorLaunchFailure;

@@ -16,6 +16,19 @@ constexpr int ENC_SMALL_K_MAX = 2047;  // warp-per-tree encode (rows exact in fp
 constexpr int LARGE_K_MAX = 1 << 19;   // CTA-per-tree kernels (bit mask + Fenwick in shared memory)
 
 int sm_count();
+// profiling aid: phase stamps (ns) of the last whole-grid decode / tables kernel
+cudaError_t debug_phase_ns_decode(unsigned long long* out);
+cudaError_t debug_phase_ns_coph(unsigned long long* out);
+// One to four huge trees: every team kernel takes the whole cooperatively launched grid per tree
+// (the trees go one after the other); more trees than that are faster side by side on clusters.
+inline bool grid_team_trees(int64_t B, int64_t k) { return B >= 1 && B <= 4 && k >= 8192; }
+// CTAs of such a grid: enough threads for one element each, at least 16, at most one per SM
+inline int grid_team_ctas(int64_t elements, int threads) {
+    int64_t c = (elements + threads - 1) / threads;
+    if (c < 16) c = 16;
+    const int sms = sm_count();
+    return (int)(c > sms ? sms : c);
+}
 void count_launch(int n = 1);
 
 // decode: v -> pairs / ancestry / edges
@@ -48,6 +61,9 @@ cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t
 // depth of every node, (B, 2k+1) f64 (vector/ops.rs:201-233)
 cudaError_t launch_node_depths(const void* v_or_matrix, int idx_bytes, const double* bls, int64_t B, int64_t k,
                                double* out, int32_t* status, void* ws, size_t ws_bytes, cudaStream_t stream);
+// check_m (matrix/base.rs:76-95) on (B,k,3) matrices: status 0, i+1 (v[i] out of bounds) or -3 (negative length)
+cudaError_t launch_check_m(const double* m, const double* bl, int bl_stride, int64_t bl_tree_stride, int64_t B,
+                           int64_t k, int32_t* status, int keep_status, cudaStream_t stream);
 cudaError_t launch_fill_f64(double* out, int64_t count, double value, cudaStream_t stream);
 
 // to_newick (vectors): strings at out + b * out_stride, NUL-terminated; lengths without the NUL

@@ -63,6 +63,20 @@ def test_validation(goldens):
             assert O.is_unordered(g["v"]) == g["expected"], g["src"]
 
 
+CHECK_M_MSG = {"columns": "Matrix must have at least 3 columns", "v": "out of bounds", "negative": "Branch lengths must be positive"}
+
+
+def test_check_m(goldens):
+    # phylo2vec/src/matrix/base.rs:76-95, test table :131-170
+    for m in goldens["check_m"]["ok"]:
+        O.check_m(m)
+    for g in goldens["check_m"]["panic"]:
+        with pytest.raises(AssertionError, match=CHECK_M_MSG[g["why"]]):
+            O.check_m(g["m"])
+    with pytest.raises(AssertionError, match="Matrix should not be empty"):
+        O.check_m(np.zeros((1, 0)))
+
+
 def test_check_v_message():
     # phylo2vec/src/vector/base.rs:60-67
     with pytest.raises(AssertionError) as e:
