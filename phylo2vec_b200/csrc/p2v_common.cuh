@@ -123,11 +123,31 @@ template <int CSIZE>
 __device__ __forceinline__ int64_t team_count() { return CSIZE == 0 ? 1 : (int64_t)(gridDim.x / CSIZE); }
 template <int CSIZE>
 __device__ __forceinline__ int64_t team_index() { return CSIZE == 0 ? 0 : (int64_t)(blockIdx.x / CSIZE); }
+// Whole-grid barrier that also ORs a predicate: every CTA adds (any << 16) + 1 to a fresh zero word
+// and waits until the low half counts all CTAs -- one atomic and one spin instead of a flag
+// update, a grid barrier and a flag read.  Same fence / barrier structure as the cooperative-groups
+// grid barrier, so data written before it is visible after it.
+__device__ __forceinline__ int grid_barrier_any(int any_cta, unsigned* word) {
+    __shared__ unsigned s_seen;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(word, (any_cta ? 0x10000u : 0u) + 1u);
+        unsigned v;
+        do { v = *reinterpret_cast<volatile unsigned*>(word); } while ((v & 0xFFFFu) != gridDim.x);
+        __threadfence();
+        s_seen = v >> 16;
+    }
+    __syncthreads();
+    const int r = (int)s_seen;
+    __syncthreads();          // s_seen may be rewritten by the next round
+    return r;
+}
 // OR of `live` over the whole team; `flag` is a zero-initialised word owned by the team
 template <int CSIZE>
 __device__ __forceinline__ int team_any(int live, int* flag) {
     const int any_cta = __syncthreads_or(live);
     if (CSIZE == 1) return any_cta;
+    if (CSIZE == 0) return grid_barrier_any(any_cta, reinterpret_cast<unsigned*>(flag));
     if (threadIdx.x == 0 && any_cta) atomicOr(flag, 1);
     team_sync<CSIZE>();
     return *reinterpret_cast<volatile int*>(flag);

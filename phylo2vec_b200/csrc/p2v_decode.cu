@@ -195,22 +195,40 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
             if (lane == 0) grp[g] = (WT)(rm ? (uint32_t)(g * 32 + 31 - __clz(rm)) : 0u);
         }
         team_sync<CSIZE>();
-        if (gw == 0) {  // exclusive prefix max over groups (slot 0 is always a root)
-            uint32_t carry = 0;
-            for (int c = 0; c < nbat; c += 32) {
-                const int g = c + lane;
-                const uint32_t val = g < nbat ? grp[g] : 0u;
-                uint32_t m = val;
+        if (crank == 0) {  // exclusive prefix max over groups (slot 0 is always a root): block scan in CTA 0
+            __shared__ uint32_t s_scan[32];
+            const int per = (nbat + THREADS - 1) / THREADS;
+            const int g0 = min(nbat, (int)threadIdx.x * per), g1 = min(nbat, g0 + per);
+            uint32_t loc = 0;
+            for (int g = g0; g < g1; ++g) loc = max(loc, (uint32_t)grp[g]);
+            uint32_t inc = loc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(FULL, inc, d);
+                if (lane >= d) inc = max(inc, y);
+            }
+            const int wq = threadIdx.x >> 5;
+            if (lane == 31) s_scan[wq] = inc;
+            __syncthreads();
+            if (wq == 0) {
+                uint32_t t = (lane < THREADS / 32) ? s_scan[lane] : 0u;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t y = __shfl_up_sync(FULL, m, d);
-                    if (lane >= d) m = max(m, y);
+                    const uint32_t y = __shfl_up_sync(FULL, t, d);
+                    if (lane >= d) t = max(t, y);
                 }
-                uint32_t ex = __shfl_up_sync(FULL, m, 1);
+                uint32_t ex = __shfl_up_sync(FULL, t, 1);
                 if (lane == 0) ex = 0;
-                ex = max(ex, carry);
-                carry = max(carry, __shfl_sync(FULL, m, 31));
-                if (g < nbat) grp[g] = (WT)ex;
+                s_scan[lane] = ex;
+            }
+            __syncthreads();
+            uint32_t run = __shfl_up_sync(FULL, inc, 1);
+            if (lane == 0) run = 0;
+            run = max(run, s_scan[wq]);
+            for (int g = g0; g < g1; ++g) {
+                const uint32_t cur = grp[g];
+                grp[g] = (WT)run;
+                run = max(run, cur);
             }
         }
         team_sync<CSIZE>();
@@ -232,6 +250,99 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
         }
         phase_stamp(4, CSIZE == 0 && tid == 0);
         if (MODE == MODE_PAIRS) { team_sync<CSIZE>(); continue; }
+
+        // ---- ancestry / edges, one huge tree on the whole grid, slots fit 16 bits: one worker per CTA with
+        //      its "last row with label x" table in SHARED memory.  1. warp 0 of every CTA records the last
+        //      row of each label inside its slot range; 2. the tables are published (uint16) and an exclusive
+        //      prefix over the workers -- eight labels per thread and step -- turns table w into "last row with
+        //      label x before range w"; 3. every CTA loads its prefix state back and warp 0 runs the ordinary
+        //      sweep on its range.  All table traffic of the two sequential passes is shared-memory latency.
+        if (CSIZE == 0 && SMEMTBL && !SMEMARR) {
+            const int TBL = (int)tbl_entries;                                  // k + 2 rounded up to 8
+            const size_t base16 = (large_base_stride((size_t)K) + 3) & ~(size_t)3;     // 16-byte aligned rows
+            uint16_t* ptab16 = reinterpret_cast<uint16_t*>(ws + (size_t)team * ws_stride + base16);
+            const int cap = (int)(((ws_stride - base16) * 2) / (size_t)TBL);
+            const int W = min(team_ctas<CSIZE>(), cap);
+            const int bpw = (nbat + W - 1) / W;
+            const int w = crank;
+            const int b0 = min(nbat, w * bpw), b1 = (w < W) ? min(nbat, b0 + bpw) : b0;
+            const int wq = threadIdx.x >> 5;
+            uint4 ones; ones.x = ones.y = ones.z = ones.w = 0xFFFFFFFFu;
+            for (int i = threadIdx.x * 8; i < TBL; i += THREADS * 8) *reinterpret_cast<uint4*>(s_tbl + i) = ones;
+            __syncthreads();
+            if (wq == 0) {
+                for (int b = b0; b < b1; ++b) {
+                    const int s = b * 32 + lane;
+                    const bool act = s < k;
+                    const uint32_t lab = act ? ((uint32_t)wlab[s] & (ROOTBIT - 1u)) : 0u;
+                    const uint32_t peers = __match_any_sync(FULL, act ? lab : (0x40000000u + lane));
+                    if (act && (peers & lanes_gt(lane)) == 0) s_tbl[lab] = (uint16_t)s;
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            if (w < W)
+                for (int i = threadIdx.x * 8; i < TBL; i += THREADS * 8)
+                    *reinterpret_cast<uint4*>(ptab16 + (size_t)w * TBL + i) = *reinterpret_cast<const uint4*>(s_tbl + i);
+            team_sync<CSIZE>();
+            phase_stamp(6, tid == 0);
+            for (int x8 = tid * 8; x8 < TBL; x8 += TT * 8) {      // exclusive prefix over the workers
+                uint4 run = ones;
+#pragma unroll 8
+                for (int ww = 0; ww < W; ++ww) {
+                    uint4* q = reinterpret_cast<uint4*>(ptab16 + (size_t)ww * TBL + x8);
+                    const uint4 cur = *q;
+                    *q = run;
+                    // per 16-bit lane: keep `run` where cur is "none" (0xFFFF), else take cur (rows grow with w)
+                    const uint32_t mx = __vcmpeq2(cur.x, 0xFFFFFFFFu), my = __vcmpeq2(cur.y, 0xFFFFFFFFu);
+                    const uint32_t mz = __vcmpeq2(cur.z, 0xFFFFFFFFu), mw = __vcmpeq2(cur.w, 0xFFFFFFFFu);
+                    run.x = (run.x & mx) | (cur.x & ~mx); run.y = (run.y & my) | (cur.y & ~my);
+                    run.z = (run.z & mz) | (cur.z & ~mz); run.w = (run.w & mw) | (cur.w & ~mw);
+                }
+            }
+            team_sync<CSIZE>();
+            phase_stamp(7, tid == 0);
+            if (w < W)
+                for (int i = threadIdx.x * 8; i < TBL; i += THREADS * 8)
+                    *reinterpret_cast<uint4*>(s_tbl + i) = *reinterpret_cast<const uint4*>(ptab16 + (size_t)w * TBL + i);
+            __syncthreads();
+            if (wq == 0 && b0 < b1) {
+                uint32_t nlab = (b0 * 32 + lane < k) ? (uint32_t)wlab[b0 * 32 + lane] : 0u;
+                uint32_t nt = (b0 * 32 + lane < k) ? (uint32_t)time_at[b0 * 32 + lane] : 0u;
+                for (int b = b0; b < b1; ++b) {
+                    const int s = b * 32 + lane;
+                    const bool act = s < k;
+                    const uint32_t labr = nlab, t = nt;
+                    if (b + 1 < b1) {                        // prefetch the next batch
+                        const int s2 = s + 32;
+                        nlab = (s2 < k) ? (uint32_t)wlab[s2] : 0u;
+                        nt = (s2 < k) ? (uint32_t)time_at[s2] : 0u;
+                    }
+                    const uint32_t lab = labr & (ROOTBIT - 1u);
+                    const bool root = act && (labr & ROOTBIT);
+                    const uint32_t peers = __match_any_sync(FULL, act ? lab : (0x40000000u + lane));
+                    uint32_t c1p = (uint32_t)(k + s);
+                    if (root) {
+                        const uint32_t lower = peers & lanes_lt(lane);
+                        uint32_t cand;
+                        if (lower) cand = (uint32_t)(b * 32 + 31 - __clz(lower));
+                        else { const uint32_t q = s_tbl[lab]; cand = (q == NONE16) ? NONE32 : q; }
+                        c1p = (cand != NONE32) ? (uint32_t)(k + 1) + cand : lab;
+                    }
+                    __syncwarp();
+                    if (act && (peers & lanes_gt(lane)) == 0) s_tbl[lab] = (uint16_t)s;
+                    __syncwarp();
+                    if (act) {
+                        const uint32_t q16 = s_tbl[t + 1];
+                        const uint32_t c2p = (q16 != NONE16) ? (uint32_t)(k + 1) + q16 : t + 1;
+                        store_row<IdxT, MODE>(ot, s, (IdxT)c1p, (IdxT)c2p, (IdxT)(k + 1 + s));
+                    }
+                }
+            }
+            team_sync<CSIZE>();
+            phase_stamp(8, tid == 0);
+            continue;
+        }
 
         // ---- ancestry / edges, few large trees: the relabel sweep split over W warps ------------------
         // Worker w owns a contiguous range of slots and a private "last row with label x" table.
@@ -440,7 +551,7 @@ static bool launch_large(const void* v, int64_t B, int64_t k, void* out, int64_t
         const IdxT* vp0 = (const IdxT*)v;
         IdxT* op0 = (IdxT*)out;
         uint32_t* wp0 = (uint32_t*)ws;
-        return launch_grid_team(kern, THREADS, smem, grid_team_ctas(k, THREADS), stream, vp0, B, (int)k, op0, out_stride,
+        return launch_grid_team(kern, THREADS, smem, grid_team_ctas(2 * k, THREADS), stream, vp0, B, (int)k, op0, out_stride,
                                 status, wp0, stride);
     }
     cudaLaunchConfig_t cfg = {};

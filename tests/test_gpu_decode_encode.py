@@ -106,6 +106,38 @@ def test_decode_parity(p2v, n_leaves, dtype):
         assert np.array_equal(got.cpu().numpy().astype(np.int64), ref), (name, n_leaves)
 
 
+# One to four huge trees take the whole-grid (cooperative) form of the merge kernel: every SM works on the
+# same tree; slots that fit 16 bits (k <= 65535) use the per-CTA shared-memory label tables, larger
+# trees the per-worker tables in the workspace.  Sizes straddle both limits; adversarial shapes
+# (one label for every row, one row per label) stress the cross-worker prefix.
+@pytest.mark.parametrize("n_leaves", [8193, 8200, 12289, 20000, 40000, 65535, 65536, 65537, 70000, 100000])
+def test_decode_parity_whole_grid(p2v, n_leaves):
+    k = n_leaves - 1
+    adv = adversarial_vectors(n_leaves)
+    cases = [sample_vectors(1, n_leaves, seed=n_leaves)[0], sample_vectors(1, n_leaves, seed=3, ordered=True)[0],
+             adv["ladder_zero"], adv["two_i"], adv["identity"], adv["alt"]]
+    for B in (1, 2, 4):
+        for first in range(0, len(cases), B):
+            V = np.stack([cases[(first + j) % len(cases)] for j in range(B)])
+            for dtype in ((torch.int64, torch.int32) if B == 1 else (torch.int32,)):
+                Vd = dev(V, dtype)
+                for name, fn in (("to_ancestry", p2v.to_ancestry_batch), ("to_pairs", p2v.to_pairs_batch),
+                                 ("to_edges", p2v.to_edges_batch)):
+                    if name != "to_ancestry" and (first or B == 2):
+                        continue
+                    ref, st = O.batch(name, V, k)
+                    assert not st.any()
+                    got = fn(Vd)
+                    assert np.array_equal(got.cpu().numpy().astype(np.int64), ref), (name, n_leaves, B, first)
+    # an invalid entry anywhere in a huge tree is reported with its index
+    bad = cases[0].copy()
+    bad[k // 2] = k + 7 if k // 2 < (k + 7) // 2 else 2 * (k // 2) + 1
+    bad[k // 2] = 2 * (k // 2) + 1
+    st = torch.zeros(1, dtype=torch.int32, device="cuda")
+    p2v.to_ancestry_batch(dev(bad[None], torch.int64), status=st, check=False)
+    assert int(st[0]) == k // 2 + 1
+
+
 # Batches of mid-size trees stay on the warp-per-tree kernel (4 / 8 / 16 mask words per lane,
 # integer rank scan); a handful of such trees goes to the merge kernel (test_decode_parity above).
 MID_SIZES = [2017, 2049, 3000, 4096, 4097, 4098, 5000, 8192, 8193, 8194, 12289, 16384, 16385, 16386]
