@@ -29,6 +29,9 @@ BATCH = 1_000_000
 METRIC = "trees/s to_ancestry @n=1k batch 1M; cophenetic matrix HBM GB/s @n=64k"
 WORKLOAD = "to_ancestry: batch of 1M random trees n=1000, int64 (BASELINE.json configs[1]); v ~ UniformInt{0..2i}"
 COPH_N = 65536
+C3_TREES, C3_N = 10_000, 2000        # BASELINE.json configs[2]
+E2E_BATCH = 500_000                  # trees per GPU per end-to-end step, the same at every N
+CPU_SAMPLE = 262_144                 # trees of the cpu_baseline leg (about 2 s on 16 threads)
 
 
 def measured_peaks():
@@ -119,6 +122,18 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def host_threads_per_rank(world):
+    """Worker threads the host entry points use per process (p2v_capi.cu host_thread_count)."""
+    e = os.environ.get("P2V_HOST_THREADS")
+    if e and int(e) > 0:
+        return int(e)
+    n = host_threads()
+    lw = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    if lw > 1:
+        n //= lw
+    return max(2, min(16, n))
+
+
 def cpu_baseline(np, sample_trees, nthreads=0, repeats=1):
     """The reference's CPU algorithm (oracle port: AVL decode + relabel pass,
     phylo2vec/src/vector/avl.rs, convert.rs:167-188), one reference call per tree,
@@ -140,27 +155,34 @@ def cpu_baseline(np, sample_trees, nthreads=0, repeats=1):
 
 
 def run_reference(args):
+    """The reference's CPU algorithm on the accelerated arm's own configuration: every step decodes
+    --batch trees (1 M by default) of n = 1000 with all host threads."""
     import numpy as np
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 65536
-    rates = []
+    sample = args.batch
+    from oracle import p2v_oracle as O
+    nthreads = host_threads()
+    V = synth_vectors_host(np, sample, K, seed=1)
+    out = np.empty((sample, K, 3), dtype=np.int64)
     for _ in range(args.warmup):
-        cpu_baseline(np, 4096)
+        O.batch("to_ancestry", V[:min(sample, 65536)], K, nthreads=nthreads, out=out[:min(sample, 65536)])
     t_all = 0.0
-    cores = 0
     for _ in range(args.steps):
-        r, cores, dt = cpu_baseline(np, sample)
-        rates.append(r)
-        t_all += dt
-    value = sample * len(rates) / t_all
+        t0 = time.perf_counter()
+        O.batch("to_ancestry", V, K, nthreads=nthreads, out=out)
+        t_all += time.perf_counter() - t0
+    value = sample * args.steps / t_all
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "trees/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, len(rates)),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": f"{sample} trees per step"},
-        "cpu_baseline": {"value": value, "unit": "trees/s", "cores": cores, "kind": "port",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": sample, "n_leaves": N_LEAVES, "idx_bytes": 8,
+                   "note": "host arm: one process, all host threads, the same trees per step as the accelerated arm's "
+                           "per-GPU batch; warm-up steps use 65536 trees"},
+        "cpu_baseline": {"value": value, "unit": "trees/s", "cores": nthreads, "kind": "port",
                          "sample": f"{sample} trees of n=1000 per step, all host threads (OpenMP over trees)"},
         "e2e": {"value": value, "unit": "trees/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -269,21 +291,24 @@ def run_b200(args):
         c2["batch"] = Bs
         del vb
 
-    # ---- end to end: host buffers through the C ABI (H2D + kernels + D2H in the timed region)
-    Be = args.e2e_batch if args.e2e_batch > 0 else (B if world == 1 else B // 4)
+    # ---- end to end: host buffers through the C ABI (H2D + kernels + D2H in the timed region) ----
+    # The same per-GPU batch at every N, --steps timed steps; the staging of the host entry points is
+    # kept between the steps (a streaming caller's setting, include/phylo2vec_b200.h).
+    Be = args.e2e_batch if args.e2e_batch > 0 else min(B, E2E_BATCH)
+    lib.p2v_host_cache_limit(-1)
     hV = torch.empty((Be, K), dtype=torch.int64).pin_memory()
     hV.copy_(V[:Be])
     hOut = torch.empty((Be, K, 3), dtype=torch.int64).pin_memory()
     hSt = torch.empty(Be, dtype=torch.int32).pin_memory()
 
-    def e2e_step():
-        rc = lib.p2v_to_ancestry_host(hV.data_ptr(), 8, Be, K, hOut.data_ptr(), hSt.data_ptr())
+    def e2e_step(hv=hV, ho=hOut, hs=hSt, nb=Be):
+        rc = lib.p2v_to_ancestry_host(hv.data_ptr(), 8, nb, K, ho.data_ptr(), hs.data_ptr())
         if rc != 0:
             raise RuntimeError(f"p2v_to_ancestry_host failed: {lib.p2v_last_error()}")
 
     e2e_step()
     barrier()
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, args.steps)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
@@ -293,31 +318,52 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * Be * e2e_steps / float(te.item())
-    e2e_ok = bool(torch.equal(hOut[:1024], out[:1024].cpu())) and int(hSt.count_nonzero()) == 0
+    # every 997th tree of the whole output against the device path (a strided sample over all chunks)
+    sel = torch.arange(0, Be, 997)
+    e2e_ok = bool(torch.equal(hOut[sel], out[sel.to(device)].cpu())) and int(hSt.count_nonzero()) == 0
+    # the same call on pageable buffers (what a plain numpy caller passes), rank 0, bounded
+    e2e_pageable = None
+    if rank == 0:
+        Bp = min(Be, 200_000)
+        pV = hV[:Bp].numpy().copy()
+        pOut = np.empty((Bp, K, 3), dtype=np.int64)
+        pSt = np.zeros(Bp, dtype=np.int32)
+        cp = lambda a: a.ctypes.data_as(ctypes.c_void_p)     # noqa: E731
+        lib.p2v_to_ancestry_host(cp(pV), 8, Bp, K, cp(pOut), cp(pSt))
+        t0 = time.perf_counter()
+        rc = lib.p2v_to_ancestry_host(cp(pV), 8, Bp, K, cp(pOut), cp(pSt))
+        tp = time.perf_counter() - t0
+        e2e_pageable = {"value": Bp / tp, "unit": "trees/s", "batch": Bp, "ok": rc == 0 and bool(
+            np.array_equal(pOut[::997], hOut[:Bp][::997].numpy()))}
+        del pV, pOut
     del hV, hOut, hSt
+    lib.p2v_host_release()
 
-    # ---- second half of the metric: cophenetic rows at n = 65536 (row block of this rank) ----
+    del V, out
+    torch.cuda.empty_cache()
+    # ---- second half of the metric: the n = 65536 matrix, row blocks over the ranks (config C4) ----
     coph = None
     try:
-        coph = bench_cophenetic(torch, lib, device, rank, world, peak, args)
+        coph = bench_c4(torch, dist, lib, device, rank, world, peak, args)
     except Exception as exc:  # keep the headline line even if this part fails
         coph = {"error": repr(exc)}
+    torch.cuda.empty_cache()
+    # ---- config C3: 10 k trees of n = 2000, topological and branch-length matrices, batch-sharded ----
+    c3 = None
+    try:
+        c3 = bench_c3(torch, dist, lib, device, rank, world, peak, args)
+    except Exception as exc:
+        c3 = {"error": repr(exc)}
+    torch.cuda.empty_cache()
     newick = (None, None, None)
     if rank == 0:
         try:
             newick = bench_newick(torch, lib, device, peak)
         except Exception as exc:
             newick = ({"error": repr(exc)},) * 3
-    if world > 1:
-        gathered = [None] * world
-        dist.all_gather_object(gathered, coph)
-        if rank == 0 and all(isinstance(g, dict) and "rows_ms" in g for g in gathered):
-            worst = max(g["rows_ms"] for g in gathered)
-            coph["rows_ms_max_over_ranks"] = worst
-            coph["aggregate_gbs"] = sum(g["bytes"] for g in gathered) / (worst * 1e-3) / 1e9
 
     if rank == 0:
-        cb_rate, cb_cores, cb_dt = cpu_baseline(np, 65536)
+        cb_rate, cb_cores, cb_dt = cpu_baseline(np, CPU_SAMPLE)
         cb1_rate, _, cb1_dt = cpu_baseline(np, 4096, nthreads=1)      # what one reference call does: one core
         try:
             import phylo2vec as _ref_pkg  # noqa: F401  (a driver-provided install of the real reference)
@@ -334,25 +380,28 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "frac_of_8tbs_spec": achieved / 8000.0,
                          "traffic": NCU_DRAM_BYTES_PER_TREE * B,
-                         "traffic_source": "ncu --set full capture profiles/r01_decode_small_v6.summary.txt: "
-                                           "dram read+write 4.1343 GB per launch of 131072 trees = "
+                         "traffic_source": f"ncu --set full capture {NCU_DRAM_SOURCE}: "
+                                           "dram read+write per launch of 131072 trees = "
                                            f"{NCU_DRAM_BYTES_PER_TREE} B/tree, scaled to this launch's {B} trees",
                          "peak_source": peak_src,
                          "kernel": "decode_small_kernel<int64, ancestry>",
                          "algorithmic_bytes_per_tree": 4 * K * 8,
                          "note": "integer kernel bound by the L1/shared-memory data pipe (ncu: 90 % of peak), not by HBM; HBM fraction reported as required"},
             "cpu_baseline": {"value": cb_rate, "unit": "trees/s", "cores": cb_cores, "kind": "port",
-                             "sample": f"65536 trees of n=1000, {cb_dt:.2f} s, OpenMP over trees",
+                             "sample": f"{CPU_SAMPLE} trees of n=1000, {cb_dt:.2f} s, OpenMP over trees",
                              "single_core_value": cb1_rate, "single_core_sample": f"4096 trees, {cb1_dt:.2f} s",
                              "reference_python_package": ref_python},
             "e2e": {"value": e2e_value, "unit": "trees/s", "h2d_bytes_per_step": Be * K * 8,
                     "d2h_bytes_per_step": Be * K * 4 + Be * 4, "batch_per_gpu": Be, "steps": e2e_steps,
+                    "host_gbs": world * Be * e2e_steps * K * (8 + 4 + 24) / float(te.item()) / 1e9,
+                    "host_threads_per_rank": host_threads_per_rank(world),
+                    "pageable_buffers": e2e_pageable,
                     "result_bytes_per_step": Be * K * 24 + Be * 4,
                     "transport": "the int64 (k,3) result crosses PCIe as its two informative columns in 16 bits each (the "
                                  "third is k+1+row); host threads of the library widen them into the caller's int64 rows",
                     "api": "p2v_to_ancestry_host (C ABI, pinned host buffers)", "matches_device_path": e2e_ok},
             "gpu_launches": launches, "clocks": clocks, "parity_spot_check": parity,
-            "config_c2_other_functions": c2, "cophenetic": coph, "next_rows": {"to_newick": newick[0], "from_newick": newick[1], "balance_indices": newick[2]},
+            "config_c2_other_functions": c2, "cophenetic_c4": coph, "c3": c3, "next_rows": {"to_newick": newick[0], "from_newick": newick[1], "balance_indices": newick[2]},
         }
         print(json.dumps(line))
     if world > 1:
@@ -462,81 +511,250 @@ def bench_newick(torch, lib, device, peak):
     return res, res2, res3
 
 
-def bench_cophenetic(torch, lib, device, rank, world, peak, args):
-    """One tree, n = 65536, float64 branch lengths; this rank writes its row block
-    [n*rank/world, n*(rank+1)/world).  Times the row kernel alone (prepared tables)."""
+def _evt_ms(torch, stream, fn, reps):
+    """Mean device time of fn() over reps back-to-back calls, CUDA events on the launching stream."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(reps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def _max_over_ranks(torch, dist, device, world, x):
+    t = torch.tensor([float(x)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _all_true(torch, dist, device, world, ok):
+    t = torch.tensor([0.0 if ok else 1.0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) == 0.0
+
+
+def bench_c4(torch, dist, lib, device, rank, world, peak, args):
+    """BASELINE config C4: ONE tree of n = 65536, float64 matrix, strong-scaled: rank r writes rows
+    [n*r/W, n*(r+1)/W) of the matrix into its slice of a preallocated (n,n) buffer; every rank decodes
+    the tree and builds its tables itself (prepare), then writes its rows.  Timed per rank with CUDA
+    events, max over ranks: prepare, the rows call, and the one-shot call (prepare + rows, the number
+    the 70 % target is about).  The optional NCCL all-gather of the row blocks is in place
+    (all_gather_into_tensor on the same buffer) and timed separately.  Sampled rows of every rank are
+    checked against the closed-form CPU restatement (never timed)."""
+    import numpy as np
+    from phylo2vec_b200 import distributed as pd
     n = COPH_N
     k = n - 1
     g = torch.Generator(device=device).manual_seed(7)            # same tree on every rank
     hi = (2 * torch.arange(k, device=device) + 1).to(torch.float64)
     v = (torch.rand((1, k), generator=g, device=device, dtype=torch.float64) * hi).to(torch.int64)
     bls = torch.rand((1, k, 2), generator=g, device=device, dtype=torch.float64)
-    r0, r1 = n * rank // world, n * (rank + 1) // world
+    r0, r1 = pd.shard_rows(n, rank, world)
     rows = r1 - r0
-    out = torch.empty((rows, n), dtype=torch.float64, device=device)
+    full = torch.empty((n, n), dtype=torch.float64, device=device)
+    mine = full[r0:r1]
     need = lib.p2v_cophenetic_workspace_bytes(1, k)
     ws = torch.empty(need, dtype=torch.uint8, device=device)
     stream = torch.cuda.current_stream(device)
-    res = {"n_leaves": n, "rows": [r0, r1], "bytes": rows * n * 8}
+    sp = stream.cuda_stream
+    reps = max(3, min(args.steps, 10))
+    res = {"workload": "one tree n=65536, float64 matrix, row blocks over the ranks (BASELINE.json configs[3])",
+           "n_leaves": n, "n_gpus": world, "scaling": "strong", "rows_this_rank": [r0, r1],
+           "bytes_per_rank": rows * n * 8, "reps": reps}
+    nbytes = rows * n * 8
+    hv = v[0].cpu().numpy()
+    hb = bls[0].cpu().numpy()
     for label, weighted, blp in (("fp64_branch_lengths", 1, bls.data_ptr()), ("topological", 0, 0)):
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        rc = lib.p2v_cophenetic_prepare_batch(v.data_ptr(), 8, blp, 1, k, 0, None, ws.data_ptr(), need, stream.cuda_stream)
-        assert rc == 0, lib.p2v_last_error()
-        for _ in range(2):
-            rc = lib.p2v_cophenetic_rows_batch(ws.data_ptr(), need, 1, k, weighted, r0, r1, out.data_ptr(), stream.cuda_stream)
+        def prep():
+            rc = lib.p2v_cophenetic_prepare_batch(v.data_ptr(), 8, blp, 1, k, 0, None, ws.data_ptr(), need, sp)
             assert rc == 0, lib.p2v_last_error()
-        torch.cuda.synchronize()
-        e[0].record(stream)
-        rc = lib.p2v_cophenetic_prepare_batch(v.data_ptr(), 8, blp, 1, k, 0, None, ws.data_ptr(), need, stream.cuda_stream)
-        e[1].record(stream)
-        reps = 5
-        e[2].record(stream)
-        for _ in range(reps):
-            lib.p2v_cophenetic_rows_batch(ws.data_ptr(), need, 1, k, weighted, r0, r1, out.data_ptr(), stream.cuda_stream)
-        e[3].record(stream)
-        torch.cuda.synchronize()
-        prep_ms = e[0].elapsed_time(e[1])
-        rows_ms = e[2].elapsed_time(e[3]) / reps
-        gbs = rows * n * 8 / (rows_ms * 1e-3) / 1e9
-        res[label] = {"prepare_ms": prep_ms, "rows_ms": rows_ms, "achieved_gbs": gbs, "frac_of_peak": gbs / peak}
+
+        def rws():
+            rc = lib.p2v_cophenetic_rows_batch(ws.data_ptr(), need, 1, k, weighted, r0, r1, mine.data_ptr(), sp)
+            assert rc == 0, lib.p2v_last_error()
+
+        def oneshot():
+            rc = lib.p2v_cophenetic_batch(v.data_ptr(), 8, blp, 1, k, 0, r0, r1, mine.data_ptr(), None, ws.data_ptr(), need, sp)
+            assert rc == 0, lib.p2v_last_error()
+        for _ in range(3):
+            oneshot()
+        if world > 1:
+            dist.barrier()
+        prep_ms = _max_over_ranks(torch, dist, device, world, _evt_ms(torch, stream, prep, reps))
+        rows_ms = _max_over_ranks(torch, dist, device, world, _evt_ms(torch, stream, rws, reps))
+        launches0 = int(lib.p2v_launch_count())
+        total_ms = _max_over_ranks(torch, dist, device, world, _evt_ms(torch, stream, oneshot, reps))
+        launches = (int(lib.p2v_launch_count()) - launches0) // reps
+        # parity of this rank's block: four sampled rows against the closed form (long-double sums)
+        ok, worst = True, 0.0
+        tree = np.concatenate([hv[:, None].astype(np.float64), hb], axis=1) if weighted else hv
+        from oracle import p2v_oracle as O
+        for rr in sorted({r0, r0 + rows // 3, r0 + (2 * rows) // 3, r1 - 1}):
+            ref = O.cophenetic_rows(tree, False, rr, rr + 1)[0]
+            got = mine[rr - r0].cpu().numpy()
+            if weighted:
+                err = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)))
+                worst = max(worst, err)
+                ok = ok and err <= 1e-12
+            else:
+                ok = ok and bool(np.array_equal(got, ref))
+        res[label] = {
+            "prepare_ms": prep_ms, "rows_ms": rows_ms, "total_ms": total_ms, "launches_per_call": launches,
+            "rows_gbs_per_gpu": nbytes / (rows_ms * 1e-3) / 1e9, "rows_frac_of_measured_hbm": nbytes / (rows_ms * 1e-3) / 1e9 / peak,
+            "total_gbs_per_gpu": nbytes / (total_ms * 1e-3) / 1e9,
+            "total_frac_of_measured_hbm": nbytes / (total_ms * 1e-3) / 1e9 / peak,
+            "total_frac_of_8tbs_spec": nbytes / (total_ms * 1e-3) / 1e9 / 8000.0,
+            "aggregate_gbs": n * n * 8 / (total_ms * 1e-3) / 1e9,
+            "parity": _all_true(torch, dist, device, world, ok),
+            "parity_bar": "<= 1e-12 relative, 4 rows per rank vs closed form" if weighted else "bit-exact, 4 rows per rank",
+        }
         if weighted:
-            res["rows_ms"] = rows_ms
-        # the variance-covariance matrix (SURVEY 8f rank 1) from the same prepared tables
-        for _ in range(2):
-            rc = lib.p2v_vcv_rows_batch(ws.data_ptr(), need, 1, k, weighted, r0, r1, out.data_ptr(), stream.cuda_stream)
-            assert rc == 0, lib.p2v_last_error()
-        torch.cuda.synchronize()
-        e[2].record(stream)
-        for _ in range(reps):
-            lib.p2v_vcv_rows_batch(ws.data_ptr(), need, 1, k, weighted, r0, r1, out.data_ptr(), stream.cuda_stream)
-        e[3].record(stream)
-        torch.cuda.synchronize()
-        vcv_ms = e[2].elapsed_time(e[3]) / reps
-        res[label]["vcv_rows_ms"] = vcv_ms
-        res[label]["vcv_achieved_gbs"] = rows * n * 8 / (vcv_ms * 1e-3) / 1e9
-    # write-only ceiling: a plain 128-bit streaming fill of the same bytes
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    lib.p2v_fill_f64(out.data_ptr(), rows * n, 1.0, stream.cuda_stream)
-    torch.cuda.synchronize()
-    e0.record(stream)
-    for _ in range(5):
-        lib.p2v_fill_f64(out.data_ptr(), rows * n, 1.0, stream.cuda_stream)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    fill_ms = e0.elapsed_time(e1) / 5
-    res["fill_ceiling_gbs"] = rows * n * 8 / (fill_ms * 1e-3) / 1e9
-    res["roofline"] = {"bound": "hbm", "achieved": res["fp64_branch_lengths"]["achieved_gbs"], "peak": peak,
-                       "unit": "GB/s", "frac": res["fp64_branch_lengths"]["achieved_gbs"] / peak,
-                       "kernel": "rows_kernel<fp64>", "algorithmic_bytes": rows * n * 8,
-                       "traffic": int(34.332404e9 * rows / n),
+            res[label]["max_rel_err_this_rank"] = worst
+    # ---- optional collective: in-place all-gather of the row blocks (NCCL over NVLink / NVSwitch) ----
+    if world > 1:
+        try:
+            lib.p2v_cophenetic_batch(v.data_ptr(), 8, bls.data_ptr(), 1, k, 0, r0, r1, mine.data_ptr(), None, ws.data_ptr(), need, sp)
+            torch.cuda.synchronize()
+            pd.all_gather_rows_(full, n)           # warm-up (communicator set-up)
+            ag_ms = _max_over_ranks(torch, dist, device, world, _evt_ms(torch, stream, lambda: pd.all_gather_rows_(full, n), 2))
+            # one row of the next rank's block must now be here, equal to the closed form
+            o0, _o1 = pd.shard_rows(n, (rank + 1) % world, world)
+            from oracle import p2v_oracle as O
+            tree = np.concatenate([hv[:, None].astype(np.float64), hb], axis=1)
+            ref = O.cophenetic_rows(tree, False, o0 + 5, o0 + 6)[0]
+            got = full[o0 + 5].cpu().numpy()
+            err = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)))
+            res["all_gather"] = {
+                "ms": ag_ms, "bytes_received_per_gpu": (n - rows) * n * 8,
+                "algbw_gbs": n * n * 8 / (ag_ms * 1e-3) / 1e9, "busbw_gbs": (n - rows) * n * 8 / (ag_ms * 1e-3) / 1e9,
+                "in_place": True, "parity": _all_true(torch, dist, device, world, err <= 1e-12),
+                "note": "dist.all_gather_into_tensor on the preallocated (n,n) buffer, sendcount = rows*n float64"}
+        except Exception as exc:
+            res["all_gather"] = {"error": repr(exc)}
+    fp = res["fp64_branch_lengths"]
+    res["roofline"] = {"bound": "hbm", "achieved": fp["total_gbs_per_gpu"], "peak": peak, "unit": "GB/s",
+                       "frac": fp["total_frac_of_measured_hbm"], "kernel": "prepare (decode + tables) + rows_kernel<fp64>, per GPU",
+                       "algorithmic_bytes": nbytes, "traffic": int(34.332404e9 * rows / n),
                        "traffic_source": "ncu --set full, profiles/r01_rows_full_fp64_v7.summary.txt: 34.303 GB written "
                                          "+ 0.030 GB read for all 65536 rows, scaled to this rank's rows"}
     return res
 
 
+def bench_c3(torch, dist, lib, device, rank, world, peak, args):
+    """BASELINE config C3: 10 000 trees of n = 2000; topological matrices from the vectors and
+    branch-length matrices from the (k,3) float64 matrices, float64 (n,n) each (32 MB per tree, 320 GB in
+    all).  Strong-scaled: the batch is sharded by tree index over the ranks, no collective; every rank
+    walks its shard in chunks that reuse one output buffer.  Max over ranks; one full matrix per rank and
+    mode is checked against the literal CPU restatement (never timed)."""
+    import numpy as np
+    from oracle import p2v_oracle as O
+    from phylo2vec_b200 import distributed as pd
+    n, k = C3_N, C3_N - 1
+    total = args.c3_trees
+    b0, b1 = pd.shard_batch(total, rank, world)
+    Bl = b1 - b0
+    rng = np.random.Generator(np.random.Philox(2000))
+    hV = (rng.random((total, k)) * (2 * np.arange(k) + 1)).astype(np.int64)[b0:b1]
+    hB = np.random.Generator(np.random.Philox(2001)).random((total, k, 2))[b0:b1]
+    V = torch.from_numpy(np.ascontiguousarray(hV)).to(device)
+    M = torch.from_numpy(np.concatenate([hV[..., None].astype(np.float64), hB], axis=2)).to(device)
+    chunk = max(1, min(Bl, 512))
+    out = torch.empty((chunk, n, n), dtype=torch.float64, device=device)
+    need = lib.p2v_cophenetic_workspace_bytes(chunk, k)
+    ws = torch.empty(need, dtype=torch.uint8, device=device)
+    st = torch.empty(chunk, dtype=torch.int32, device=device)
+    stream = torch.cuda.current_stream(device)
+    sp = stream.cuda_stream
+    res = {"workload": "10k trees n=2000: cophenetic_distances, topological (vectors) and branch lengths "
+                       "((k,3) float64 matrices), float64 (n,n) out (BASELINE.json configs[2])",
+           "trees": total, "n_leaves": n, "n_gpus": world, "scaling": "strong", "sharding": "tree-batch index, no collective",
+           "trees_this_rank": Bl, "chunk_trees": chunk, "bytes_total": total * n * n * 8}
+
+    def sweep(weighted):
+        for c0 in range(0, Bl, chunk):
+            nb = min(chunk, Bl - c0)
+            if weighted:
+                rc = lib.p2v_cophenetic_matrix_batch(M[c0:c0 + nb].data_ptr(), nb, k, 0, 0, n, out.data_ptr(), st.data_ptr(),
+                                                     ws.data_ptr(), need, sp)
+            else:
+                rc = lib.p2v_cophenetic_batch(V[c0:c0 + nb].data_ptr(), 8, 0, nb, k, 0, 0, n, out.data_ptr(), st.data_ptr(),
+                                              ws.data_ptr(), need, sp)
+            assert rc == 0, lib.p2v_last_error()
+
+    for label, weighted in (("topological", 0), ("fp64_branch_lengths", 1)):
+        sweep(weighted)                                      # warm-up pass over the shard
+        if world > 1:
+            dist.barrier()
+        launches0 = int(lib.p2v_launch_count())
+        ms_local = _evt_ms(torch, stream, lambda: sweep(weighted), 1)
+        launches = int(lib.p2v_launch_count()) - launches0
+        ms = _max_over_ranks(torch, dist, device, world, ms_local)
+        # parity: the last chunk is still in `out`; its first tree against the literal reference loop
+        last0 = ((Bl - 1) // chunk) * chunk
+        got = out[0].cpu().numpy()
+        tree = M[last0].cpu().numpy() if weighted else hV[last0]
+        ref = O.cophenetic_distances(tree)
+        if weighted:
+            err = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)))
+            ok = err <= 1e-12
+        else:
+            err = 0.0
+            ok = bool(np.array_equal(got, ref))
+        ok = ok and int(st.count_nonzero()) == 0
+        res[label] = {"ms": ms, "trees_per_s": total / (ms * 1e-3), "aggregate_gbs": total * n * n * 8 / (ms * 1e-3) / 1e9,
+                      "gbs_per_gpu": Bl * n * n * 8 / (ms_local * 1e-3) / 1e9,
+                      "frac_of_measured_hbm_per_gpu": Bl * n * n * 8 / (ms_local * 1e-3) / 1e9 / peak,
+                      "launches": launches, "includes": "input adapters + decode + tables + blocks + rows, every chunk",
+                      "parity": _all_true(torch, dist, device, world, ok),
+                      "parity_bar": "<= 1e-12 relative, one full matrix per rank vs the literal reference loop" if weighted
+                      else "bit-exact, one full matrix per rank vs the literal reference loop",
+                      "max_rel_err_this_rank": err}
+    del out, ws
+    torch.cuda.empty_cache()
+    # ---- the same call end to end: host (pinned) buffers through p2v_cophenetic_matrix_host, rank 0's shard ----
+    try:
+        Be = min(Bl, 64)
+        hM = torch.empty((Be, k, 3), dtype=torch.float64).pin_memory()
+        hM.copy_(M[:Be])
+        hD = torch.empty((Be, n, n), dtype=torch.float64).pin_memory()
+        hS = torch.empty(Be, dtype=torch.int32).pin_memory()
+
+        def host_call():
+            rc = lib.p2v_cophenetic_matrix_host(hM.data_ptr(), Be, k, 0, 0, n, hD.data_ptr(), hS.data_ptr())
+            assert rc == 0, lib.p2v_last_error()
+        lib.p2v_host_cache_limit(-1)
+        host_call()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        steps = 3
+        for _ in range(steps):
+            host_call()
+        dt = _max_over_ranks(torch, dist, device, world, time.perf_counter() - t0)
+        ref = O.cophenetic_distances(hM[Be - 1].numpy())
+        got = hD[Be - 1].numpy()
+        err = float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-300)))
+        res["e2e"] = {"value": world * Be * steps / dt, "unit": "trees/s", "api": "p2v_cophenetic_matrix_host (pinned host buffers)",
+                      "batch_per_gpu": Be, "steps": steps, "h2d_bytes_per_step": Be * k * 24, "d2h_bytes_per_step": Be * n * n * 8 + Be * 4,
+                      "d2h_gbs_per_gpu": Be * steps * n * n * 8 / dt / 1e9,
+                      "parity": _all_true(torch, dist, device, world, err <= 1e-12 and int(hS.count_nonzero()) == 0)}
+        del hM, hD, hS
+        lib.p2v_host_release()
+        lib.p2v_host_cache_limit(512 << 20)
+    except Exception as exc:
+        res["e2e"] = {"error": repr(exc)}
+    return res
+
+
 # dram__bytes_read.sum + dram__bytes_write.sum of decode_small_kernel<int64, ancestry> per tree
-# (profiles/r01_decode_small_v6.summary.txt: (1.049686 + 3.084584) GB / 131072 trees)
-NCU_DRAM_BYTES_PER_TREE = 31542
+# (profiles/r01_decode_small_v7.summary.txt: (1.049430 + 3.083787) GB / 131072 trees)
+NCU_DRAM_BYTES_PER_TREE = 31534
+NCU_DRAM_SOURCE = "profiles/r01_decode_small_v7.summary.txt"
 
 
 
@@ -654,6 +872,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="trees per GPU per step")
     ap.add_argument("--e2e-batch", type=int, default=0)
+    ap.add_argument("--c3-trees", type=int, default=C3_TREES, help="trees of the C3 leg (whole job)")
     ap.add_argument("--sweep", action="store_true", help="per-size sweep instead of the bench line")
     ap.add_argument("--sweep-out", default=os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_sweep.json"))
     ap.add_argument("--sweep-quick", action="store_true")

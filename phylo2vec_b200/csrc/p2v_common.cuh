@@ -133,9 +133,10 @@ __device__ __forceinline__ int grid_barrier_any(int any_cta, unsigned* word) {
         __threadfence();
         atomicAdd(word, (any_cta ? 0x10000u : 0u) + 1u);
         unsigned v;
-        do { v = *reinterpret_cast<volatile unsigned*>(word); } while ((v & 0xFFFFu) != gridDim.x);
+        unsigned spins = 0;         // bounded: a lost CTA must not hang the device (the result is then garbage, never a hang)
+        do { v = *reinterpret_cast<volatile unsigned*>(word); } while ((v & 0xFFFFu) < gridDim.x && ++spins < (1u << 22));
         __threadfence();
-        s_seen = v >> 16;
+        s_seen = (spins >= (1u << 22)) ? 0u : (v >> 16);
     }
     __syncthreads();
     const int r = (int)s_seen;

@@ -269,7 +269,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
             const int wq = threadIdx.x >> 5;
             uint4 ones; ones.x = ones.y = ones.z = ones.w = 0xFFFFFFFFu;
             for (int i = threadIdx.x * 8; i < TBL; i += THREADS * 8) *reinterpret_cast<uint4*>(s_tbl + i) = ones;
-            __syncthreads();
+            team_sync<CSIZE>();                          // the labels of every slot are written (and the table is filled)
             if (wq == 0) {
                 for (int b = b0; b < b1; ++b) {
                     const int s = b * 32 + lane;
@@ -286,18 +286,26 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
                     *reinterpret_cast<uint4*>(ptab16 + (size_t)w * TBL + i) = *reinterpret_cast<const uint4*>(s_tbl + i);
             team_sync<CSIZE>();
             phase_stamp(6, tid == 0);
-            for (int x8 = tid * 8; x8 < TBL; x8 += TT * 8) {      // exclusive prefix over the workers
-                uint4 run = ones;
-#pragma unroll 8
-                for (int ww = 0; ww < W; ++ww) {
-                    uint4* q = reinterpret_cast<uint4*>(ptab16 + (size_t)ww * TBL + x8);
-                    const uint4 cur = *q;
-                    *q = run;
-                    // per 16-bit lane: keep `run` where cur is "none" (0xFFFF), else take cur (rows grow with w)
-                    const uint32_t mx = __vcmpeq2(cur.x, 0xFFFFFFFFu), my = __vcmpeq2(cur.y, 0xFFFFFFFFu);
-                    const uint32_t mz = __vcmpeq2(cur.z, 0xFFFFFFFFu), mw = __vcmpeq2(cur.w, 0xFFFFFFFFu);
-                    run.x = (run.x & mx) | (cur.x & ~mx); run.y = (run.y & my) | (cur.y & ~my);
-                    run.z = (run.z & mz) | (cur.z & ~mz); run.w = (run.w & mw) | (cur.w & ~mw);
+            // exclusive prefix over the workers: four labels per thread; the loads of 16 workers are issued
+            // together (a store to the same row between them would serialise the L2 round trips)
+            // (warps are dealt round-robin over the CTAs: 4 labels x 32 lanes per warp, every SM takes part)
+            const int nct = team_ctas<CSIZE>();
+            for (int x4 = ((wq * nct + crank) * 32 + lane) * 4; x4 < TBL; x4 += TT * 4) {
+                uint2 run; run.x = run.y = 0xFFFFFFFFu;
+                for (int w0 = 0; w0 < W; w0 += 16) {
+                    uint2 cur[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (w0 + j < W) cur[j] = __ldcg(reinterpret_cast<const uint2*>(ptab16 + (size_t)(w0 + j) * TBL + x4));
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (w0 + j < W) {
+                            __stcg(reinterpret_cast<uint2*>(ptab16 + (size_t)(w0 + j) * TBL + x4), run);
+                            // per 16-bit lane: keep `run` where cur is "none" (0xFFFF), else take cur (rows grow with w)
+                            const uint32_t mx = __vcmpeq2(cur[j].x, 0xFFFFFFFFu), my = __vcmpeq2(cur[j].y, 0xFFFFFFFFu);
+                            run.x = (run.x & mx) | (cur[j].x & ~mx); run.y = (run.y & my) | (cur[j].y & ~my);
+                        }
+                    }
                 }
             }
             team_sync<CSIZE>();

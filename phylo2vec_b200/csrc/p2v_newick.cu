@@ -554,7 +554,7 @@ __device__ __forceinline__ int newick_tokenize(const char* __restrict__ src, int
     int len;
     if (lengths) {
         const int64_t l64 = lengths[tree];
-        len = (l64 < 1 || l64 > maxlen) ? 0 : (int)l64;
+        len = (l64 < 1 || l64 > maxlen || l64 > in_stride) ? 0 : (int)l64;    // never read past the row
     } else {                                  // NUL-terminated inside the row
         const int lim = (int)(in_stride < (int64_t)maxlen + 1 ? in_stride : (int64_t)maxlen + 1);
         for (int i = tid; i < lim; i += NT) if (src[i] == 0) { atomicMin(&P.len, i); break; }

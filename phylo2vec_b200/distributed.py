@@ -77,18 +77,43 @@ def cophenetic_rows_sharded(tree, unrooted: bool = False, bls=None, group=None,
     return D[0], (r0, r1)
 
 
-def all_gather_rows(local_rows: torch.Tensor, n_leaves: int, group=None) -> torch.Tensor:
-    """Optional: assemble the full (n,n) matrix on every rank from the row blocks.
+def all_gather_rows_(full: torch.Tensor, n_leaves: int, group=None) -> torch.Tensor:
+    """Optional collective, IN PLACE: ``full`` is the preallocated (n,n) matrix of which this rank has
+    written its own row block ``shard_rows(n, rank, world)`` (e.g. by passing ``out=full[r0:r1]`` to
+    :func:`cophenetic_rows_sharded`); afterwards every rank holds every block.  Equal blocks
+    (``n % world == 0``) are one ``all_gather_into_tensor`` whose input is the rank's own slice of the
+    output -- ncclAllGather in place, ``sendcount = rows * n`` float64, no staging buffer (SURVEY
+    section 8e).  Unequal blocks are broadcast block by block, also in place."""
+    rank, world = _world(group)
+    if world == 1:
+        return full
+    if tuple(full.shape) != (n_leaves, n_leaves) or not full.is_contiguous():
+        raise ValueError(f"all_gather_rows_: expected a contiguous ({n_leaves},{n_leaves}) tensor")
+    shards = all_shards(n_leaves, world)
+    r0, r1 = shards[rank]
+    if n_leaves % world == 0:
+        dist.all_gather_into_tensor(full, full[r0:r1], group=group)
+    else:
+        for src, (a, b) in enumerate(shards):
+            if b > a:
+                dist.broadcast(full[a:b], src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+    return full
 
-    Row blocks differ by at most one row, so the gather pads to the largest block and
-    trims; on GPUs this is ncclAllGather over NVLink / NVSwitch."""
+
+def all_gather_rows(local_rows: torch.Tensor, n_leaves: int, group=None,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Optional: assemble the full (n,n) matrix on every rank from the row blocks.  ``out`` is the
+    (n,n) destination (allocated here if absent); the rank's block is copied into its slice unless
+    ``local_rows`` already is that slice, then :func:`all_gather_rows_` gathers in place."""
     rank, world = _world(group)
     if world == 1:
         return local_rows
-    shards = all_shards(n_leaves, world)
-    max_rows = max(b - a for a, b in shards)
-    pad = torch.zeros((max_rows, n_leaves), dtype=local_rows.dtype, device=local_rows.device)
-    pad[: local_rows.shape[0]] = local_rows
-    gathered = torch.empty((world, max_rows, n_leaves), dtype=local_rows.dtype, device=local_rows.device)
-    dist.all_gather_into_tensor(gathered.view(world * max_rows, n_leaves), pad, group=group)
-    return torch.cat([gathered[r, : b - a] for r, (a, b) in enumerate(shards)], dim=0)
+    r0, r1 = shard_rows(n_leaves, rank, world)
+    if tuple(local_rows.shape) != (r1 - r0, n_leaves):
+        raise ValueError(f"all_gather_rows: rank {rank} holds {tuple(local_rows.shape)}, expected {(r1 - r0, n_leaves)}")
+    if out is None:
+        out = torch.empty((n_leaves, n_leaves), dtype=local_rows.dtype, device=local_rows.device)
+    mine = out[r0:r1]
+    if mine.data_ptr() != local_rows.data_ptr():
+        mine.copy_(local_rows)
+    return all_gather_rows_(out, n_leaves, group)

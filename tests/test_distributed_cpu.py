@@ -50,6 +50,12 @@ def _worker(rank, world, port, n_leaves, q):
         local = torch.from_numpy(O.cophenetic_rows(m, False, r0, r1))
         gathered = D.all_gather_rows(local, n_leaves)
         ok_rows = np.allclose(gathered.numpy(), full, rtol=1e-13, atol=0)
+        # the in-place form: the rank writes its block into its slice of the (n,n) buffer, nothing is staged
+        buf = torch.full((n_leaves, n_leaves), -1.0, dtype=torch.float64)
+        buf[r0:r1] = local
+        same = D.all_gather_rows_(buf, n_leaves)
+        ok_rows = ok_rows and same.data_ptr() == buf.data_ptr() and np.array_equal(buf.numpy(), gathered.numpy())
+        ok_rows = ok_rows and D.all_gather_rows(buf[r0:r1], n_leaves, out=buf).data_ptr() == buf.data_ptr()
         # batch sharding: shards are disjoint and cover the batch
         B = 37
         V = sample_vectors(B, 50, seed=3)
