@@ -91,7 +91,7 @@ __device__ __forceinline__ void count_smaller_step(uint32_t& cnt, uint32_t mine,
 // ---- phase stamps of the team kernels (profiling aid) -----------------------------------------
 // Thread 0 of team CTA 0 stores the global nanosecond timer at phase boundaries; p2v_debug_phase_ns()
 // copies the stamps out.  One predicated store per phase: left in release builds.
-constexpr int PHASE_SLOTS = 64;
+constexpr int PHASE_SLOTS = 256;
 static __device__ unsigned long long g_phase_ns[PHASE_SLOTS];    // one copy per translation unit
 __device__ __forceinline__ void phase_stamp(int slot, bool who) {
     if (who) {
@@ -107,7 +107,12 @@ __device__ __forceinline__ void phase_stamp(int slot, bool who) {
 template <int CSIZE>
 __device__ __forceinline__ void team_sync() {
     if (CSIZE == 1) __syncthreads();
-    else if (CSIZE == 0) cooperative_groups::this_grid().sync();
+    else if (CSIZE == 0) {
+        cooperative_groups::this_grid().sync();
+        // the warp of the CTA's master thread comes out of the barrier's spin DIVERGED (measured: its
+        // shuffle-heavy code then runs ten times slower until something reconverges it)
+        __syncwarp();
+    }
     else cooperative_groups::this_cluster().sync();
 }
 template <int CSIZE>
@@ -138,10 +143,28 @@ __device__ __forceinline__ int grid_barrier_any(int any_cta, unsigned* word) {
         __threadfence();
         s_seen = (spins >= (1u << 22)) ? 0u : (v >> 16);
     }
+    __syncwarp();
     __syncthreads();
     const int r = (int)s_seen;
     __syncthreads();          // s_seen may be rewritten by the next round
     return r;
+}
+// Whole-grid barrier on a monotone counter word: every barrier on the word adds gridDim.x arrivals, so
+// the word never needs a reset between barriers or launches -- it only has to START at a multiple of
+// gridDim.x (zero).  Bounded spin like grid_barrier_any.
+__device__ __forceinline__ void grid_barrier(unsigned* word) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned G = gridDim.x;
+        const unsigned old = atomicAdd(word, 1u);
+        const unsigned target = old - old % G + G;
+        unsigned spins = 0;
+        while ((int)(*reinterpret_cast<volatile unsigned*>(word) - target) < 0 && ++spins < (1u << 22)) {}
+        __threadfence();
+    }
+    __syncwarp();
+    __syncthreads();
 }
 // OR of `live` over the whole team; `flag` is a zero-initialised word owned by the team
 template <int CSIZE>

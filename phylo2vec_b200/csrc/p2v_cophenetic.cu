@@ -57,34 +57,43 @@ constexpr int TAB_CLUSTER = 16;            // CTAs per tree when there are few, 
 constexpr int TAB_FLAGS = 128;             // per-tree convergence flags (one per jumping round)
 constexpr int BLK_THREADS = 1024;
 #ifndef P2V_ROW_R
-#define P2V_ROW_R 64
+#define P2V_ROW_R 96
 #endif
-constexpr int ROW_R = P2V_ROW_R;           // requested rows per CTA (tile)
+constexpr int ROW_R = P2V_ROW_R;           // capacity: requested rows per CTA (tile)
+constexpr int ROW_RT = 64;                 // rows a tile is meant to hold
 constexpr int ROW_PMAX_LARGE = 1024;       // capacity: DFS positions per block at most (n > 512)
 constexpr int ROW_PMAX_SMALL = 64;         //                                            (n <= 512)
 constexpr int ilog2c(int x) { return x <= 1 ? 0 : 1 + ilog2c(x >> 1); }
 constexpr int ROW_CPT = 4;                 // columns per thread (two 16-byte stores per row)
 constexpr int ROW_NINCAP = 64;             // in-block columns per chunk whose values are staged in shared memory
-// Shape of one rows call.  Blocks are cut every `rcap` requested rows and every `pcap` DFS
-// positions; the requested rows of a block span about rcap*n/m positions, and pcap sits 25% above
-// that so that it rarely cuts a second time (no cap at all when every row is requested).  `bsz`
-// bounds the positions in a block (capacity of the in-block tables), `nidb` the number of block ids.
+// Shape of one rows call.  Block ids follow two lattices: a cut every `pcap` DFS positions and a cut
+// every `rcap` requested rows.  All rows requested: blocks of exactly ROW_RT positions = rows.  A row
+// subset (one rank's block of a huge tree): the requested rows are spread over the DFS order, so the
+// POSITION lattice is the one that shapes the tiles -- pcap = ROW_RT * n / m positions hold ROW_RT
+// requested rows on average -- and the row lattice (rcap = ROW_R, 1.5x the mean) only catches dense
+// stretches.  (Cutting at 64 rows AND at 1.25x their mean span, as round 1 did, left tiles of 36 rows
+// on average: both lattices cut all the time.)  `bsz` bounds the positions in a block (capacity of
+// the in-block tables), `nidb` the number of block ids.
 struct CophCall { int pcap, rcap, bsz, nidb, nincap; };
 inline CophCall coph_call(int64_t n, int64_t m) {
     CophCall c;
-    c.rcap = (n <= 512) ? 32 : ROW_R;
     if (m >= n) {
+        c.rcap = (n <= 512) ? 32 : ROW_RT;
         c.pcap = 1 << 30; c.bsz = c.rcap;
+        c.nincap = c.bsz < ROW_NINCAP ? c.bsz : ROW_NINCAP;
     } else {
-        int64_t want = (5 * (int64_t)c.rcap * n) / (4 * (m > 0 ? m : 1));
+        const int rt = (n <= 512) ? 32 : ROW_RT;
+        c.rcap = (n <= 512) ? 32 : ROW_R;
+        int64_t want = ((int64_t)rt * n) / (m > 0 ? m : 1);
         want = (want + 31) & ~(int64_t)31;
-        if (want < c.rcap) want = c.rcap;
+        if (want < rt) want = rt;
         const int64_t cap = (n <= 512) ? ROW_PMAX_SMALL : ROW_PMAX_LARGE;
         if (want > cap) want = cap;
         c.pcap = (int)want; c.bsz = c.pcap;
+        // a chunk of 1024 label-ordered columns holds about 1024 * bsz / n of the block's own leaves
+        c.nincap = (n > 512 && c.bsz * 1024 <= 16 * n) ? 32 : (c.bsz < ROW_NINCAP ? c.bsz : ROW_NINCAP);
     }
     c.nidb = (int)(n / c.pcap + (m + c.rcap - 1) / c.rcap + 2);
-    c.nincap = c.bsz < ROW_NINCAP ? c.bsz : ROW_NINCAP;
     return c;
 }
 // threads per rows-CTA: 4 columns per thread, so small trees get small CTAs
@@ -460,7 +469,8 @@ __device__ __forceinline__ unsigned long long pack_key(int key, int p) {
     return ((unsigned long long)(unsigned)key << 32) | (unsigned)p;
 }
 
-// prefix / suffix minima of sep inside block `id` of one tree: one warp
+// prefix / suffix minima of sep inside block `id` of one tree: one warp, 32 positions per step, the
+// next step's keys loaded while the current one is scanned.
 __device__ __forceinline__ void block_minima_one(unsigned char* T, const CophLayout& L, int id, int lane) {
     const int* sepk = reinterpret_cast<const int*>(T + L.sepk);
     int* prek = reinterpret_cast<int*>(T + L.prek);
@@ -473,9 +483,12 @@ __device__ __forceinline__ void block_minima_one(unsigned char* T, const CophLay
     const int hi = reinterpret_cast<const int*>(T + L.bend)[id];
     if (lo < 0) return;
     unsigned long long carry = pack_key(KEY_INF, 0);
+    int knext = (lo + lane < hi) ? sepk[lo + lane] : KEY_INF;
     for (int base = lo; base < hi; base += 32) {       // pre[p] = min sep[lo..p]
         const int p = base + lane;
-        unsigned long long m = (p < hi) ? pack_key(sepk[p], p) : pack_key(KEY_INF, 0);
+        const int kcur = knext;
+        knext = (p + 32 < hi) ? sepk[p + 32] : KEY_INF;
+        unsigned long long m = (p < hi) ? pack_key(kcur, p) : pack_key(KEY_INF, 0);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const unsigned long long y = __shfl_up_sync(FULL, m, d);
@@ -487,9 +500,13 @@ __device__ __forceinline__ void block_minima_one(unsigned char* T, const CophLay
     }
     if (lane == 0) { blkk[id] = (int)(carry >> 32); blka[id] = (int)(carry & 0xFFFFFFFFu); }
     carry = pack_key(KEY_INF, 0);
-    for (int base = lo + ((hi - lo - 1) / 32) * 32; base >= lo; base -= 32) {   // suf[p] = min sep[p+1..hi-1]
+    const int last = lo + ((hi - lo - 1) / 32) * 32;
+    knext = (last + lane < hi) ? sepk[last + lane] : KEY_INF;
+    for (int base = last; base >= lo; base -= 32) {   // suf[p] = min sep[p+1..hi-1]
         const int p = base + lane;
-        unsigned long long m = (p < hi) ? pack_key(sepk[p], p) : pack_key(KEY_INF, 0);
+        const int kcur = knext;
+        knext = (base - 32 >= lo) ? sepk[p - 32] : KEY_INF;
+        unsigned long long m = (p < hi) ? pack_key(kcur, p) : pack_key(KEY_INF, 0);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const unsigned long long y = __shfl_down_sync(FULL, m, d);
@@ -558,6 +575,7 @@ blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int
 
         int* wcount = reinterpret_cast<int*>(T + L.tilelist);   // per-warp counts (tilelist is filled last)
         team_sync<CSIZE>();   // shared scratch of the previous tree is no longer read
+        phase_stamp(32, CSIZE == 0 && crank == 0 && tid == 0);
         for (int i = crank * BLK_THREADS + tid; i < L.nbmax; i += team_ctas<CSIZE>() * BLK_THREADS) {
             bstart[i] = -1; bend[i] = -1; rowoff[i] = 0; cend[i] = 0; blkk[i] = KEY_INF; blka[i] = -1;
         }
@@ -591,6 +609,7 @@ blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int
             for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(FULL, acc, d);
             c0 = acc;
         }
+        phase_stamp(33, CSIZE == 0 && crank == 0 && tid == 0);
         int prev_last = (w0 > 0) ? (w0 - 1) / pcap + max(0, c0 - 1) / rcap : -1;   // id of position w0-1
         int lab_next = (w0 + lane < w1) ? leaf_at[w0 + lane] : -1;
         int lab_next2 = (w0 + 32 + lane < w1) ? leaf_at[w0 + 32 + lane] : -1;
@@ -620,6 +639,7 @@ blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int
             if (last >= 0) prev_last = last;
         }
         team_sync<CSIZE>();
+        phase_stamp(34, CSIZE == 0 && crank == 0 && tid == 0);
         // compact the blocks that hold requested rows into tilelist
         if (crank == 0) {
             const int warp = tid >> 5;
@@ -647,11 +667,24 @@ blocks_kernel(unsigned char* __restrict__ tab, size_t tab_stride, int64_t B, int
         }
         if (CSIZE == 0) {
             team_sync<CSIZE>();                       // hdr, bstart / bend of every block are final
+            phase_stamp(35, crank == 0 && tid == 0);
             const int nid = hdr[0];
-            for (int id = warp; id < nid; id += NW) block_minima_one(T, L, id, lane);
-            team_sync<CSIZE>();
+            {   // blocks dealt round-robin over the CTAs first: every SM takes a few, none takes 32
+                const int nct = team_ctas<CSIZE>();
+                // Blocks are dealt round-robin over the CTAs (every SM takes a few), and never to warp 0:
+                // measured on B200, the warp of the CTA's master thread runs shuffle-heavy code about ten
+                // times slower after a grid barrier (63 us instead of 6 for a 512-position block;
+                // profiles/r02_c4_notes.md), whatever reconverges it.
+                const int wq = tid >> 5;
+                if (wq > 0)
+                    for (int id = (wq - 1) * nct + crank; id < nid; id += (NWC - 1) * nct) block_minima_one(T, L, id, lane);
+            }
+            if (CSIZE == 0) grid_barrier(reinterpret_cast<unsigned*>(T + L.flags) + 100);
+            else team_sync<CSIZE>();
+            phase_stamp(36, crank == 0 && tid == 0);
             for (int j = crank * BLK_THREADS + tid; j < n; j += team_ctas<CSIZE>() * BLK_THREADS)
                 column_tables_one(T, L, j, weighted);
+            phase_stamp(37, crank == 0 && tid == 0);
         }
     }
 }
@@ -743,13 +776,16 @@ __device__ __forceinline__ double dd_diff_round(dd a, dd b) {
 struct RowShared {
     int label[ROW_R];          // leaf label of the row
     int qpos[ROW_R];           // its DFS position
-    int ai[2][ROW_R];          // topological depth of the row candidate  [0]: columns left  [1]: right
-    int ui[2][ROW_R];          // d_i - that depth
     int di[ROW_R];
-    double ahi[2][ROW_R], alo[2][ROW_R];   // double-double depth of the row candidate
-    double uf[2][ROW_R];                   // d_i - d_rl, rounded once
     double dhi[ROW_R], dlo[ROW_R];
     unsigned long long wtotR[8], wtotL[8]; // per-warp totals of the block scan
+    long long roff[ROW_R];                 // (label - row_begin) * n: element offset of the row in the output
+    // what the streaming loop reads per column, indexed [row][side] ([0]: columns left of the tile, [1]:
+    // right) so that a column's side is an address offset instead of three 64-bit selects:
+    // sv = (double-double depth of the row candidate hi, lo; d_i - d_rl rounded once),
+    // si = (topological depth of the row candidate; d_i - that depth)
+    double sv[ROW_R][2][3];
+    int si[ROW_R][2][2];
     int incount;
 };
 // dynamic shared memory of rows_kernel: midhi[nidb], midlo[nidb] (doubles), midk[nidb], mida[nidb],
@@ -852,6 +888,7 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
             const int q = rowlist[roff + r];
             const int i = leaf_at[q];
             S.label[r] = i; S.qpos[r] = q;
+            S.roff[r] = (long long)(i - row_begin) * n;
             const int di = jDI[i];
             S.di[r] = di;
             const dd d = {jDH[i], jDL[i]};
@@ -863,11 +900,11 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
                 const bool none = ck >= KEY_INF;         // no separator on that side inside the block
                 if (TOPO) {
                     const int a = none ? di : ck;        // key == topological depth of the candidate
-                    S.ai[side][r] = a; S.ui[side][r] = di - a;
+                    S.si[r][side][0] = a; S.si[r][side][1] = di - a;
                 } else {
                     const dd a = none ? d : dd{sephi[ca], seplo[ca]};
-                    S.ahi[side][r] = a.hi; S.alo[side][r] = a.lo;
-                    S.uf[side][r] = none ? 0.0 : dd_diff_round(d, a);
+                    const double ufv = none ? 0.0 : dd_diff_round(d, a);
+                    S.sv[r][side][0] = a.hi; S.sv[r][side][1] = a.lo; S.sv[r][side][2] = ufv;
                 }
             }
         }
@@ -1018,50 +1055,69 @@ rows_kernel(const unsigned char* __restrict__ tab, size_t tab_stride, int64_t B,
             __syncthreads();
         }
         const bool warp_has_in = staged && __any_sync(FULL, inpack != 0);
+        // a thread with ONE staged in-block column (the usual case) merges it with one shared-memory load
+        // and four predicated moves per row; a warp where some thread has several takes the general form
+        int in_c = -1, in_e = 0;
+#pragma unroll
+        for (int c = 0; c < ROW_CPT; ++c) {
+            const unsigned e = (inpack >> (8 * c)) & 0xFFu;
+            if (e) { in_c = (in_c < 0) ? c : 4; in_e = (int)e - 1; }
+        }
+        const bool warp_multi = warp_has_in && __any_sync(FULL, in_c == 4);
+        const bool pin0 = in_c == 0, pin1 = in_c == 1, pin2 = in_c == 2, pin3 = in_c == 3;
+        // store targets and predicates of this thread's two column pairs (VEC2: n is even, a pair is in or out)
+        double* const cp0 = obase + col[0];
+        double* const cp1 = obase + col[2];
+        const bool full0 = col[0] + 1 < n, full1 = col[2] + 1 < n;
+        const bool half0 = !full0 && col[0] < n, half1 = !full1 && col[2] < n;
+        const int sx0 = side[0], sx1 = side[1], sx2 = side[2], sx3 = side[3];
+        const int sxs[ROW_CPT] = {sx0, sx1, sx2, sx3};
 
         // ---- streamed part: requested rows x 4 columns per thread -----------------------------
 #pragma unroll 2
         for (int r = 0; r < nrow; ++r) {
-            const int i = S.label[r];
-            double* orow = obase + (size_t)(i - row_begin) * n;
+            const long long ro = S.roff[r];
             double val[ROW_CPT];
             if (TOPO) {
-                const int a0 = S.ai[0][r], a1 = S.ai[1][r], u0 = S.ui[0][r], u1 = S.ui[1][r];
 #pragma unroll
                 for (int c = 0; c < ROW_CPT; ++c) {
-                    const int a = side[c] ? a1 : a0;
-                    const int u = side[c] ? u1 : u0;
-                    val[c] = VCV ? int_to_f64(min(a, bi[c])) : int_to_f64(u + uji[c] + abs(a - bi[c]));
+                    const int2 au = *reinterpret_cast<const int2*>(&S.si[r][sxs[c]][0]);
+                    val[c] = VCV ? int_to_f64(min(au.x, bi[c])) : int_to_f64(au.y + uji[c] + abs(au.x - bi[c]));
                 }
             } else {
-                const double a0h = S.ahi[0][r], a0l = S.alo[0][r], a1h = S.ahi[1][r], a1l = S.alo[1][r];
-                const double u0 = S.uf[0][r], u1 = S.uf[1][r];
 #pragma unroll
                 for (int c = 0; c < ROW_CPT; ++c) {
-                    const double ah = side[c] ? a1h : a0h;
-                    const double al = side[c] ? a1l : a0l;
-                    const double u = side[c] ? u1 : u0;
+                    const double* sv = &S.sv[r][sxs[c]][0];
+                    const double ah = sv[0], al = sv[1];
                     if (VCV) {      // the shallower candidate; both lie on one root path
                         const bool rowmin = ah < bhi[c] || (ah == bhi[c] && al < blo[c]);
                         val[c] = rowmin ? ah : bhi[c];
                     } else {
+                        const double u = sv[2];
                         const double m = __dadd_rn(__dadd_rn(ah, -bhi[c]), __dadd_rn(al, -blo[c]));
                         val[c] = __dadd_rn(__dadd_rn(u, ujf[c]), fabs(m));
                     }
                 }
             }
             if (warp_has_in) {           // warp-uniform
+                if (!warp_multi) {
+                    const double x = s_ptab[r * nincap + in_e];
+                    if (pin0) val[0] = x;
+                    if (pin1) val[1] = x;
+                    if (pin2) val[2] = x;
+                    if (pin3) val[3] = x;
+                } else {
 #pragma unroll
-                for (int c = 0; c < ROW_CPT; ++c) {
-                    const unsigned e = (inpack >> (8 * c)) & 0xFFu;
-                    if (e) val[c] = s_ptab[r * nincap + e - 1];
+                    for (int c = 0; c < ROW_CPT; ++c) {
+                        const unsigned e = (inpack >> (8 * c)) & 0xFFu;
+                        if (e) val[c] = s_ptab[r * nincap + e - 1];
+                    }
                 }
             }
-#pragma unroll
-            for (int c = 0; c < ROW_CPT; c += 2) {
-                if (col[c] + 1 < n) store2<VEC2>(orow + col[c], val[c], val[c + 1]);
-                else if (col[c] < n) __stcs(orow + col[c], val[c]);
-            }
+            if (full0) store2<VEC2>(cp0 + ro, val[0], val[1]);
+            else if (half0) __stcs(cp0 + ro, val[0]);
+            if (full1) store2<VEC2>(cp1 + ro, val[2], val[3]);
+            else if (half1) __stcs(cp1 + ro, val[2]);
         }
 
         if (!staged) {   // rare: more in-block columns in this chunk than the staging table holds

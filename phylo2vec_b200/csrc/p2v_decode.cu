@@ -125,7 +125,13 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
         if (tid == 0 && status) status[tree] = 0;
 
         // ---- level 0: rank inside each batch of 32, stored sorted by rank ----------------------
-        for (int b = gw; b < nbat; b += NWT) {
+        // Whole-grid teams: warp-sized work is dealt round-robin over the CTAs, and never to warp 0 of a CTA
+        // (the master thread's warp runs shuffle-heavy code ~10x slower after a grid barrier, see
+        // p2v_cophenetic.cu blocks_kernel); gwr = -1 marks the idle warp, NWR the stride.
+        const int wq0 = (int)(threadIdx.x >> 5);
+        const int NWR = (CSIZE == 0) ? (THREADS / 32 - 1) * team_ctas<CSIZE>() : NWT;
+        const int gwr = (CSIZE == 0) ? (wq0 > 0 ? (wq0 - 1) * team_ctas<CSIZE>() + crank : NWR * 0 + 0x40000000) : gw;
+        for (int b = gwr; b < nbat; b += NWR) {
             const int t = b * 32 + lane;
             const bool act = t < k;
             const uint32_t x = wv[t];
@@ -156,7 +162,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
             const WT* ein = cur ? el1 : el0;
             WT* rout = cur ? rk0 : rk1;
             WT* eout = cur ? el0 : el1;
-            for (int i = tid; i < k; i += TT) {
+            for (int i = ((CSIZE == 0) ? (wq0 * team_ctas<CSIZE>() + crank) * 32 + lane : tid); i < k; i += TT) {
                 const int a = (i / (2 * S)) * (2 * S), m = a + S;
                 const uint32_t r = rin[i], e = ein[i];
                 if (m >= k) { rout[i] = (WT)r; eout[i] = (WT)e; continue; }      // lone block: copy through
@@ -186,7 +192,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
         const WT* time_at = cur ? el1 : el0;                  // element at slot s
 
         // ---- labels: nearest root (rank-0 insertion) at or left of every slot ------------------
-        for (int g = gw; g < nbat; g += NWT) {
+        for (int g = gwr; g < nbat; g += NWR) {
             const int s = g * 32 + lane;
             const bool act = s < k;
             const uint32_t t = act ? time_at[s] : 0u;
@@ -234,7 +240,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
         team_sync<CSIZE>();
         phase_stamp(3, CSIZE == 0 && tid == 0);
         IdxT* ot = out + tree * out_stride;
-        for (int g = gw; g < nbat; g += NWT) {
+        for (int g = gwr; g < nbat; g += NWR) {
             const int s = g * 32 + lane;
             const bool act = s < k;
             const uint32_t t = act ? time_at[s] : 0u;
@@ -270,7 +276,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
             uint4 ones; ones.x = ones.y = ones.z = ones.w = 0xFFFFFFFFu;
             for (int i = threadIdx.x * 8; i < TBL; i += THREADS * 8) *reinterpret_cast<uint4*>(s_tbl + i) = ones;
             team_sync<CSIZE>();                          // the labels of every slot are written (and the table is filled)
-            if (wq == 0) {
+            if (wq == 1) {            // not warp 0: see gwr above
                 for (int b = b0; b < b1; ++b) {
                     const int s = b * 32 + lane;
                     const bool act = s < k;
@@ -314,7 +320,7 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
                 for (int i = threadIdx.x * 8; i < TBL; i += THREADS * 8)
                     *reinterpret_cast<uint4*>(s_tbl + i) = *reinterpret_cast<const uint4*>(ptab16 + (size_t)w * TBL + i);
             __syncthreads();
-            if (wq == 0 && b0 < b1) {
+            if (wq == 1 && b0 < b1) {
                 uint32_t nlab = (b0 * 32 + lane < k) ? (uint32_t)wlab[b0 * 32 + lane] : 0u;
                 uint32_t nt = (b0 * 32 + lane < k) ? (uint32_t)time_at[b0 * 32 + lane] : 0u;
                 for (int b = b0; b < b1; ++b) {

@@ -51,27 +51,34 @@ t_dec = timeit(lambda: lib.p2v_to_ancestry_batch(v32.data_ptr(), 4, 1, k, anc.da
 print(f"n={n} decode(int32, to_ancestry) {t_dec * 1e3:.1f} us", flush=True)
 
 
-def phases(which, names):
+def phases(which, names, first=0, start=15):
     import ctypes
     import numpy as np
-    ts = np.zeros(64, dtype=np.uint64)
+    ts = np.zeros(256, dtype=np.uint64)
     lib.p2v_debug_phase_ns(which, ts.ctypes.data_as(ctypes.c_void_p))
-    t0 = int(ts[15])
+    t0 = int(ts[start])
     prev = t0
     parts = []
     for i, nm in enumerate(names):
-        parts.append(f"{nm}={(int(ts[i]) - prev) / 1e3:.1f}")
-        prev = int(ts[i])
+        parts.append(f"{nm}={(int(ts[first + i]) - prev) / 1e3:.1f}")
+        prev = int(ts[first + i])
+    if which == 1 and first == 38:
+        print("    per-CTA warp0 loop us:", " ".join(f"{int(ts[64 + c]) / 1e3:.0f}" for c in range(64)))
+        print("    block sizes:", " ".join(f"{(int(ts[128 + c]) & 0xFFFFFFFF) - (int(ts[128 + c]) >> 32)}" for c in range(64)))
+    if which == 1 and first == 38:
+        parts.append(f"maxloop={int(ts[40]) / 1e3:.1f}us at cta={int(ts[41]) >> 32} warp={(int(ts[41]) >> 16) & 0xFFFF} blocks={int(ts[41]) & 0xFFFF} nid={int(ts[42])}")
     return " ".join(parts) + f" | total={(prev - t0) / 1e3:.1f} us" + (f" rounds={int(ts[16])},{int(ts[17])}" if which else "")
 
 
-print("  decode phases (us):", phases(0, ["load", "level0", "merge", "labels-scan", "labels", "tab-init", "record", "combine", "sweep"]), flush=True)
+print("  decode phases (us):", phases(0, ["load", "level0", "merge", "labels-scan", "labels"]),
+      "then", phases(0, ["record+publish", "combine", "sweep"], first=6, start=4), flush=True)
 for name, weighted, blp in (("fp64", 1, bls.data_ptr()), ("topo", 0, 0)):
     t_prep = timeit(lambda: lib.p2v_cophenetic_prepare_batch(v.data_ptr(), 8, blp, 1, k, 0, None, ws.data_ptr(), need, s))
     print(f"  tables phases {name} (us):", phases(1, ["init", "jump", "rank", "positions"]), flush=True)
     for (r0, r1) in ((0, n // 8), (3 * n // 8, n // 2), (0, n)):
         out = torch.empty((1, r1 - r0, n), dtype=torch.float64, device=dev)
         t_rows = timeit(lambda: lib.p2v_cophenetic_rows_batch(ws.data_ptr(), need, 1, k, weighted, r0, r1, out.data_ptr(), s))
+        print("  blocks phases (us):", phases(1, ["count", "ids", "tiles", "minima", "columns"], first=33, start=32).replace(" rounds=", " tables-rounds="), flush=True)
         t_all = timeit(lambda: lib.p2v_cophenetic_batch(v.data_ptr(), 8, blp, 1, k, 0, r0, r1, out.data_ptr(), None,
                                                         ws.data_ptr(), need, s))
         gb = out.numel() * 8 / 1e9
