@@ -207,6 +207,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=device)
     lib = _capi.load()
     peaks, peak_src = measured_peaks()
+    # this rank's host thread (and the pinned buffers it allocates) next to its GPU's NUMA node
+    numa_cpus = int(lib.p2v_host_bind_thread())
 
     def barrier():
         if world > 1:
@@ -394,7 +396,7 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "trees/s", "h2d_bytes_per_step": Be * K * 8,
                     "d2h_bytes_per_step": Be * K * 4 + Be * 4, "batch_per_gpu": Be, "steps": e2e_steps,
                     "host_gbs": world * Be * e2e_steps * K * (8 + 4 + 24) / float(te.item()) / 1e9,
-                    "host_threads_per_rank": host_threads_per_rank(world),
+                    "host_threads_per_rank": host_threads_per_rank(world), "numa_bound_cpus": numa_cpus,
                     "pageable_buffers": e2e_pageable,
                     "result_bytes_per_step": Be * K * 24 + Be * 4,
                     "transport": "the int64 (k,3) result crosses PCIe as its two informative columns in 16 bits each (the "

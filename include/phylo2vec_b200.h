@@ -237,6 +237,12 @@ int p2v_from_newick_host(const char *newick, int64_t in_stride, int64_t B, int64
  * A thread that exits frees its cache.  p2v_host_release() frees the calling thread's cache now. */
 void p2v_host_release(void);
 int64_t p2v_host_cache_bytes(void);          /* bytes the calling thread currently keeps */
+/* The worker threads of the *_host entry points run on the CPUs next to the current device (its
+ * NUMA node, sysfs local_cpulist) when the machine has more than one node; P2V_HOST_NUMA=0
+ * disables that.  p2v_host_bind_thread() does the same for the CALLING thread (call it once per
+ * process before allocating pinned buffers, so that they land on that node); returns the number
+ * of CPUs it was bound to, 0 if it was left alone. */
+int p2v_host_bind_thread(void);
 void p2v_host_cache_limit(int64_t bytes);    /* process-wide limit per thread */
 
 /* profiling aid: nanosecond stamps at the phase boundaries of the last whole-grid

@@ -56,6 +56,7 @@ SIGNATURES = {
     "p2v_cophenetic_matrix_host": (_int, [_vp, _i64, _i64, _int, _i64, _i64, _vp, _vp]),
     "p2v_host_release": (None, []),
     "p2v_host_cache_bytes": (_i64, []),
+    "p2v_host_bind_thread": (_int, []),
     "p2v_host_cache_limit": (None, [_i64]),
     "p2v_debug_phase_ns": (_int, [_int, _vp]),
     "p2v_check_m_batch": (_int, [_vp, _i64, _i64, _vp, _vp]),

@@ -152,6 +152,7 @@ static cudaError_t host_ensure(HostCtx& H, size_t in_b, size_t out_b, size_t ws_
 
 static int host_thread_count();
 static bool is_pageable(const void* p);
+static bool bind_thread_near_gpu();
 
 // Pinned staging of the generic host path: a pageable buffer (a plain numpy array) would be staged
 // by the driver on one thread at ~10 GB/s; here worker threads copy it through pinned buffers of
@@ -211,6 +212,8 @@ static int host_chunked_staged(const void* in, size_t in_tree_bytes, void* out, 
     if (st_b > S.cap_stat) S.cap_stat = st_b;
 
     const int nthreads = host_thread_count();
+    int dev_of_call = 0;
+    cudaGetDevice(&dev_of_call);
     const int64_t nchunks = (B + chunk - 1) / chunk;
     std::mutex mu;
     std::condition_variable cv_job, cv_done;
@@ -220,7 +223,9 @@ static int host_chunked_staged(const void* in, size_t in_tree_bytes, void* out, 
     std::vector<std::thread> pool;
     pool.reserve(nthreads);
     for (int t = 0; t < nthreads; ++t) {
-        pool.emplace_back([&]() {
+        pool.emplace_back([&, dev_of_call]() {
+            cudaSetDevice(dev_of_call);
+            bind_thread_near_gpu();
             for (;;) {
                 CopyJob j;
                 {
@@ -411,6 +416,50 @@ static void host_trim() {
 }
 struct HostTrim { ~HostTrim() { host_trim(); } };
 
+// CPUs next to the current device: /sys/bus/pci/devices/<bus id>/local_cpulist (the cores of the GPU's NUMA
+// node) intersected with the process affinity.  Empty set = unknown (no sysfs, no NUMA): callers then leave
+// the affinity alone.  P2V_HOST_NUMA=0 switches the binding off.
+static bool gpu_local_cpus(cpu_set_t* out) {
+    CPU_ZERO(out);
+    const char* off = getenv("P2V_HOST_NUMA");
+    if (off && off[0] == '0') return false;
+    int dev = 0;
+    char bus[32] = {};
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, sizeof(bus), dev) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    for (char* c = bus; *c; ++c) if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+    std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return false;
+    char line[4096] = {};
+    const bool got = fgets(line, sizeof(line), f) != nullptr;
+    fclose(f);
+    if (!got) return false;
+    cpu_set_t have;
+    if (sched_getaffinity(0, sizeof(have), &have) != 0) return false;
+    int n = 0;
+    for (const char* q = line; *q;) {                 // "0-15,32-47"
+        while (*q == ',' || *q == ' ' || *q == '\n') ++q;
+        if (!*q) break;
+        char* end = nullptr;
+        long a = strtol(q, &end, 10), b = a;
+        if (end == q) break;
+        q = end;
+        if (*q == '-') { b = strtol(q + 1, &end, 10); q = end; }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c)
+            if (c >= 0 && CPU_ISSET((int)c, &have)) { CPU_SET((int)c, out); ++n; }
+    }
+    return n > 0 && n < CPU_COUNT(&have);            // every CPU local = nothing to bind
+}
+// binds the calling thread (workers call it when they start); false = left alone
+static bool bind_thread_near_gpu() {
+    cpu_set_t set;
+    if (!gpu_local_cpus(&set)) return false;
+    return sched_setaffinity(0, sizeof(set), &set) == 0;
+}
+
 static int host_thread_count() {
     const char* e = getenv("P2V_HOST_THREADS");
     if (e && atoi(e) > 0) return atoi(e);
@@ -523,6 +572,8 @@ static int ancestry_host_compact(const void* v, int64_t B, int64_t k, void* out,
 
     // widening workers
     const int nthreads = host_thread_count();
+    int dev_of_call = 0;
+    cudaGetDevice(&dev_of_call);
     std::mutex mu;
     std::condition_variable cv_job, cv_done;
     std::deque<WidenJob> jobs;
@@ -533,7 +584,9 @@ static int ancestry_host_compact(const void* v, int64_t B, int64_t k, void* out,
     std::vector<std::thread> pool;
     pool.reserve(nthreads);
     for (int t = 0; t < nthreads; ++t) {
-        pool.emplace_back([&]() {
+        pool.emplace_back([&, dev_of_call]() {
+            cudaSetDevice(dev_of_call);
+            bind_thread_near_gpu();
             for (;;) {
                 WidenJob j;
                 {
@@ -1237,6 +1290,12 @@ int p2v_cophenetic_matrix_host(const double* m, int64_t B, int64_t k, int unroot
 }
 
 void p2v_host_release(void) { g_host.release(); g_compact.release(); g_stage.release(); }
+int p2v_host_bind_thread(void) {
+    cpu_set_t set;
+    if (!gpu_local_cpus(&set)) return 0;
+    if (sched_setaffinity(0, sizeof(set), &set) != 0) return 0;
+    return CPU_COUNT(&set);
+}
 int64_t p2v_host_cache_bytes(void) { return (int64_t)(g_host.bytes() + g_stage.bytes() + g_compact.bytes()); }
 void p2v_host_cache_limit(int64_t bytes) { g_host_cache_limit.store(bytes, std::memory_order_relaxed); }
 
