@@ -170,6 +170,20 @@ size_t p2v_balance_workspace_bytes(int64_t B, int64_t k);
 int p2v_balance_batch(const void *v, int idx_bytes, int64_t B, int64_t k, double *out, int32_t *status,
                       void *workspace, size_t workspace_bytes, p2v_stream_t stream);
 
+/* ---- Robinson-Foulds distance (third "next" row, second half) ---------------------------------
+ * replaces vector::distance::robinson_foulds (phylo2vec/src/vector/distance.rs:41-162); PyO3
+ * robinson_foulds (py-phylo2vec/src/lib.rs:295-309); Python phylo2vec.stats.robinson_foulds
+ * (stats/treewise.py:10-58).  v1 (B1,k) and v2 (B2,k) with B1 == B2 (pair b = tree b of each batch)
+ * or one of them 1 (that tree against every tree of the other batch); out (max(B1,B2)) float64:
+ * the number of non-trivial bipartitions present in exactly one of the two (unrooted) trees,
+ * divided by the total number of bipartitions when normalize != 0.  k <= 65535. */
+size_t p2v_robinson_foulds_workspace_bytes(int64_t B1, int64_t B2, int64_t k);
+int p2v_robinson_foulds_batch(const void *v1, const void *v2, int idx_bytes, int64_t B1, int64_t B2, int64_t k,
+                              int normalize, double *out, int32_t *status, void *workspace,
+                              size_t workspace_bytes, p2v_stream_t stream);
+int p2v_robinson_foulds_host(const void *v1, const void *v2, int idx_bytes, int64_t B1, int64_t B2, int64_t k,
+                             int normalize, double *out, int32_t *status);
+
 /* ---- to_newick (second "next" row; vectors only) ------------------------------------------
  * replaces vector::convert::to_newick / build_newick (vector/convert.rs:341-397); PyO3 entry
  * point to_newick, vector arm (py-phylo2vec/src/lib.rs:90-96); Python phylo2vec.base.newick.

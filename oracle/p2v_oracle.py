@@ -376,3 +376,50 @@ def balance(v) -> np.ndarray:
     if rc:
         raise ValueError(f"oracle: balance failed ({rc})")
     return out
+
+
+def _bipartitions(v) -> set:
+    """vector/distance.rs:82-137 get_bipartitions: descendant leaf sets bottom-up through the ancestry (Python
+    ints as bit sets), trivial splits skipped, each split canonicalised (:142-153): the smaller side, the side
+    holding leaf 0 when the sides are equal."""
+    anc = to_ancestry(v)
+    k = anc.shape[0]
+    n = k + 1
+    desc = [1 << i for i in range(n)] + [0] * k
+    for c1, c2, p in anc.tolist():
+        desc[p] = desc[c1] | desc[c2]
+    full = (1 << n) - 1
+    splits = set()
+    for i in range(k):
+        d = desc[n + i]
+        size = bin(d).count("1")
+        if size <= 1 or size >= n - 1:
+            continue
+        comp = full ^ d
+        if size < n - size:
+            splits.add(d)
+        elif size > n - size:
+            splits.add(comp)
+        else:
+            splits.add(d if d & 1 else comp)
+    return splits
+
+
+def robinson_foulds(v1, v2, normalize: bool = False) -> float:
+    """vector/distance.rs:41-74 (PyO3 robinson_foulds, py-phylo2vec/src/lib.rs:295-309: a matrix is
+    reduced to its first column)."""
+    a, b = np.asarray(v1), np.asarray(v2)
+    if a.ndim == 2:
+        a = a[:, 0].astype(np.int64)
+    if b.ndim == 2:
+        b = b[:, 0].astype(np.int64)
+    if a.shape[0] != b.shape[0]:
+        raise AssertionError("Trees must have the same number of leaves")
+    if a.shape[0] + 1 <= 3:
+        return 0.0
+    s1, s2 = _bipartitions(a), _bipartitions(b)
+    diff = len(s1 - s2) + len(s2 - s1)
+    if normalize:
+        m = len(s1) + len(s2)
+        return 0.0 if m == 0 else diff / m
+    return float(diff)

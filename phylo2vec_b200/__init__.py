@@ -23,11 +23,13 @@ __all__ = [
     "to_ancestry_batch", "to_pairs_batch", "to_edges_batch", "from_ancestry_batch",
     "from_pairs_batch", "from_edges_batch", "cophenetic_distances_batch", "check_v_batch", "check_m_batch",
     "vcv_batch", "node_depths_batch", "to_newick_batch", "from_newick_batch", "balance_indices_batch",
+    "robinson_foulds_batch",
 ]
 
 _BATCH = {"to_ancestry_batch", "to_pairs_batch", "to_edges_batch", "from_ancestry_batch",
           "from_pairs_batch", "from_edges_batch", "cophenetic_distances_batch", "check_v_batch", "check_m_batch",
-          "vcv_batch", "node_depths_batch", "to_newick_batch", "from_newick_batch", "balance_indices_batch"}
+          "vcv_batch", "node_depths_batch", "to_newick_batch", "from_newick_batch", "balance_indices_batch",
+          "robinson_foulds_batch"}
 
 
 def __getattr__(name):

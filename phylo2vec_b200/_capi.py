@@ -46,6 +46,9 @@ SIGNATURES = {
     "p2v_newick_workspace_bytes": (_sz, [_i64, _i64]),
     "p2v_to_newick_batch": (_int, [_vp, _int, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "p2v_to_newick_host": (_int, [_vp, _int, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "p2v_robinson_foulds_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "p2v_robinson_foulds_batch": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _int, _vp, _vp, _vp, _sz, _vp]),
+    "p2v_robinson_foulds_host": (_int, [_vp, _vp, _int, _i64, _i64, _i64, _int, _vp, _vp]),
     "p2v_balance_workspace_bytes": (_sz, [_i64, _i64]),
     "p2v_balance_batch": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "p2v_balance_host": (_int, [_vp, _int, _i64, _i64, _vp, _vp]),

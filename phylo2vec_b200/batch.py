@@ -433,6 +433,37 @@ def from_newick_batch(newick, lengths=None, n_leaves: Optional[int] = None, dtyp
     return v
 
 
+def robinson_foulds_batch(V1, V2, normalize: bool = False, out=None, status=None, check: bool = True) -> torch.Tensor:
+    """Robinson-Foulds distances of tree pairs, float64 ``(P,)``: ``V1`` ``(B1,k)`` against ``V2`` ``(B2,k)`` with
+    ``B1 == B2`` (pair b = tree b of each batch) or one of them a single tree (against every tree of the other
+    batch).  Replaces vector::distance::robinson_foulds (phylo2vec/src/vector/distance.rs:41-162)."""
+    V1 = _idx_tensor(V1, 2, "robinson_foulds")
+    V2 = _idx_tensor(V2, 2, "robinson_foulds")
+    if V1.shape[1] != V2.shape[1]:
+        raise AssertionError("Trees must have the same number of leaves")
+    if V1.dtype != V2.dtype or V1.device != V2.device:
+        raise TypeError("robinson_foulds: both batches must share dtype and device")
+    B1, B2, k = V1.shape[0], V2.shape[0], V1.shape[1]
+    if B1 != B2 and B1 != 1 and B2 != 1:
+        raise ValueError("robinson_foulds: batches must have equal sizes, or one of them a single tree")
+    P = max(B1, B2)
+    lib = _capi.load()
+    out = _out_f64(out, (P,), V1.device)
+    status = _check_status(status, P, V1.device, "robinson_foulds")
+    need = int(lib.p2v_robinson_foulds_workspace_bytes(B1, B2, k))
+    with torch.cuda.device(V1.device):
+        ws = torch.empty(max(need, 16), dtype=torch.uint8, device=V1.device)
+        rc = lib.p2v_robinson_foulds_batch(V1.data_ptr(), V2.data_ptr(), V1.element_size(), B1, B2, k,
+                                           int(bool(normalize)), out.data_ptr(), status.data_ptr(), ws.data_ptr(), need,
+                                           _stream_ptr(V1.device))
+    _capi.check(rc, "robinson_foulds")
+    if check and bool(status.any()):
+        bad = int(torch.nonzero(status)[0, 0])
+        which = V1 if int(check_v_batch(V1[bad:bad + 1] if B1 > 1 else V1)[0]) != 0 else V2
+        raise_for_status(status[bad:bad + 1], which[bad:bad + 1] if which.shape[0] > 1 else which)
+    return out
+
+
 def balance_indices_batch(V, out=None, status=None, check: bool = True) -> torch.Tensor:
     """Sackin index, leaf-depth variance and B2 of every vector of a batch ``(B,k)``: float64 ``(B,3)``.
     Replaces vector::balance::{sackin, leaf_depth_variance, b2} (phylo2vec/src/vector/balance.rs:14-58)."""

@@ -1130,6 +1130,65 @@ int p2v_balance_host(const void* v, int idx_bytes, int64_t B, int64_t k, double*
         });
 }
 
+// ---- Robinson-Foulds (third "next" row, second half) -------------------------------------------
+size_t p2v_robinson_foulds_workspace_bytes(int64_t B1, int64_t B2, int64_t k) {
+    return robinson_foulds_workspace_bytes(B1, B2, k);
+}
+static int rf_check(const void* v1, const void* v2, const double* out, int idx_bytes, int64_t B1, int64_t B2, int64_t k) {
+    if (idx_bytes != 4 && idx_bytes != 8) return fail(P2V_ERR_INVALID_ARG, "idx_bytes must be 4 or 8");
+    if (B1 < 0 || B2 < 0 || k < 0) return fail(P2V_ERR_INVALID_ARG, "negative batch or length");
+    if (B1 != B2 && B1 != 1 && B2 != 1) return fail(P2V_ERR_INVALID_ARG, "batches must have equal sizes, or one of them one tree");
+    if (k > 65535) return fail(P2V_ERR_UNSUPPORTED, "robinson_foulds: more than 65536 leaves");
+    if (B1 > 0 && B2 > 0 && (!out || (k > 0 && (!v1 || !v2)))) return fail(P2V_ERR_INVALID_ARG, "null buffer");
+    return P2V_OK;
+}
+int p2v_robinson_foulds_batch(const void* v1, const void* v2, int idx_bytes, int64_t B1, int64_t B2, int64_t k,
+                              int normalize, double* out, int32_t* status, void* ws, size_t ws_bytes,
+                              p2v_stream_t stream) {
+    int rc = rf_check(v1, v2, out, idx_bytes, B1, B2, k);
+    if (rc) return rc;
+    if (B1 == 0 || B2 == 0) return P2V_OK;
+    if (ws_bytes < robinson_foulds_workspace_bytes(B1, B2, k) || (!ws && robinson_foulds_workspace_bytes(B1, B2, k) > 0))
+        return fail(P2V_ERR_WORKSPACE, "robinson_foulds workspace too small");
+    return from_cuda(launch_robinson_foulds(v1, v2, idx_bytes, B1, B2, k, normalize, out, status, ws, ws_bytes,
+                                            (cudaStream_t)stream), "robinson_foulds launch");
+}
+int p2v_robinson_foulds_host(const void* v1, const void* v2, int idx_bytes, int64_t B1, int64_t B2, int64_t k,
+                             int normalize, double* out, int32_t* status) {
+    int rc = rf_check(v1, v2, out, idx_bytes, B1, B2, k);
+    if (rc) return rc;
+    if (B1 == 0 || B2 == 0) return P2V_OK;
+    const int64_t P = B1 > B2 ? B1 : B2;
+    const size_t tree_b = (size_t)(k > 0 ? k : 1) * idx_bytes;
+    int64_t chunk = (int64_t)(((size_t)256 << 20) / tree_b);
+    if (chunk < 1) chunk = 1;
+    if (chunk > P) chunk = P;
+    const int64_t c1 = B1 == 1 ? 1 : chunk, c2 = B2 == 1 ? 1 : chunk;
+    const size_t wsb = robinson_foulds_workspace_bytes(c1, c2, k);
+    void *d1 = nullptr, *d2 = nullptr, *dws = nullptr;
+    double* dout = nullptr;
+    int32_t* dst = nullptr;
+    cudaError_t e = cudaMalloc(&d1, tree_b * c1);
+    if (e == cudaSuccess) e = cudaMalloc(&d2, tree_b * c2);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dout, sizeof(double) * chunk);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dst, sizeof(int32_t) * chunk);
+    if (e == cudaSuccess && wsb) e = cudaMalloc(&dws, wsb);
+    for (int64_t p0 = 0; p0 < P && e == cudaSuccess; p0 += chunk) {
+        const int64_t nb = (P - p0 < chunk) ? (P - p0) : chunk;
+        const int64_t n1 = B1 == 1 ? 1 : nb, n2 = B2 == 1 ? 1 : nb;
+        if (k > 0) {
+            e = cudaMemcpy(d1, (const char*)v1 + (B1 == 1 ? 0 : (size_t)p0 * tree_b), tree_b * n1, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess)
+                e = cudaMemcpy(d2, (const char*)v2 + (B2 == 1 ? 0 : (size_t)p0 * tree_b), tree_b * n2, cudaMemcpyHostToDevice);
+        }
+        if (e == cudaSuccess) e = launch_robinson_foulds(d1, d2, idx_bytes, n1, n2, k, normalize, dout, dst, dws, wsb, nullptr);
+        if (e == cudaSuccess) e = cudaMemcpy(out + p0, dout, sizeof(double) * nb, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && status) e = cudaMemcpy(status + p0, dst, sizeof(int32_t) * nb, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d1); cudaFree(d2); cudaFree(dout); cudaFree(dst); cudaFree(dws);
+    return from_cuda(e, "robinson_foulds host entry");
+}
+
 // ---- to_newick --------------------------------------------------------------------------
 size_t p2v_newick_max_bytes(int64_t k) { return newick_max_bytes(k); }
 size_t p2v_newick_workspace_bytes(int64_t B, int64_t k) { return newick_workspace_bytes(B, k); }

@@ -76,6 +76,11 @@ cudaError_t launch_to_newick(const void* v, int idx_bytes, int64_t B, int64_t k,
 size_t from_newick_workspace_bytes(int64_t B, int64_t k, int idx_bytes);
 cudaError_t launch_from_newick(const char* in, int64_t in_stride, const int64_t* lengths, int64_t B, int64_t k, void* v,
                                int idx_bytes, int32_t* status, void* ws, size_t ws_bytes, cudaStream_t stream);
+// Robinson-Foulds distance of tree pairs (vector/distance.rs:41-162): B1 == B2 pairs, or one tree against many
+size_t robinson_foulds_workspace_bytes(int64_t B1, int64_t B2, int64_t k);
+cudaError_t launch_robinson_foulds(const void* v1, const void* v2, int idx_bytes, int64_t B1, int64_t B2, int64_t k,
+                                   int normalize, double* out, int32_t* status, void* ws, size_t ws_bytes,
+                                   cudaStream_t stream);
 // int64 -> int32 index vectors (values that do not fit become -1 and fail check_v downstream)
 cudaError_t launch_narrow_v(const long long* v, int64_t count, int* out, cudaStream_t stream);
 

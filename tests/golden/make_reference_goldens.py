@@ -119,6 +119,21 @@ G = {
          "src": "phylo2vec/src/vector/convert.rs:767-779"},
     ],
     # ------------------------------------------------------------ validation
+    # Robinson-Foulds: the reference's own assertions (phylo2vec/src/vector/distance.rs:168-239).  "expected"
+    # is a number, or a property: "symmetric", "unit_interval" (normalised), "range_0_2".
+    # (The docstring example in py-phylo2vec/phylo2vec/stats/treewise.py:46-51 prints 2.0 for
+    # [0,1,2,3] vs [0,0,1,2]; the two 5-leaf trees share no bipartition, so the code -- and ete4, which the
+    # reference's tests compare with, tests/test_stats.py:283-310 -- give 2 (n - 3) = 4: not used as a golden.)
+    "robinson_foulds": [
+        {"v1": [0, 1, 2, 3], "v2": [0, 1, 2, 3], "normalize": False, "expected": 0.0, "src": "distance.rs:169-172"},
+        {"v1": [0, 1, 2, 3, 4, 5, 6], "v2": [0, 1, 2, 3, 4, 5, 6], "normalize": False, "expected": 0.0,
+         "src": "distance.rs:175-178"},
+        {"v1": [0, 1, 2, 3], "v2": [0, 0, 1, 2], "normalize": False, "expected": "symmetric", "src": "distance.rs:181-188"},
+        {"v1": [0, 1, 2, 3], "v2": [0, 0, 1, 2], "normalize": True, "expected": "unit_interval", "src": "distance.rs:191-196"},
+        {"v1": [0, 0], "v2": [0, 1], "normalize": False, "expected": 0.0, "src": "distance.rs:199-204"},
+        {"v1": [0, 0, 0], "v2": [0, 1, 0], "normalize": False, "expected": "range_0_2", "src": "distance.rs:207-217"},
+        {"v1": [0, 1, 2], "v2": [0, 1, 2], "normalize": False, "expected": 0.0, "src": "distance.rs:33-34 (doctest)"},
+    ],
     # test_check_m, phylo2vec/src/matrix/base.rs:131-170 (the empty-array case is a shape check)
     "check_m": {
         "ok": [

@@ -77,6 +77,47 @@ def test_check_m(goldens):
         O.check_m(np.zeros((1, 0)))
 
 
+def check_rf_golden(fn, g):
+    got = fn(g["v1"], g["v2"], g["normalize"])
+    exp = g["expected"]
+    if exp == "symmetric":
+        assert got == fn(g["v2"], g["v1"], g["normalize"]), g["src"]
+    elif exp == "unit_interval":
+        assert 0.0 <= got <= 1.0, g["src"]
+    elif exp == "range_0_2":
+        assert 0.0 <= got <= 2.0, g["src"]
+    else:
+        assert got == exp, g["src"]
+
+
+def test_robinson_foulds(goldens):
+    # phylo2vec/src/vector/distance.rs:41-162 and its test module :164-239
+    for g in goldens["robinson_foulds"]:
+        check_rf_golden(O.robinson_foulds, g)
+    with pytest.raises(AssertionError, match="same number of leaves"):      # distance.rs:220-225
+        O.robinson_foulds([0, 1, 2], [0, 1])
+    # the definition itself (what the reference checks against ete4): splits read off the tree by brute force
+    for n in (4, 5, 6, 9, 17):
+        rng = np.random.Generator(np.random.Philox(n))
+        for _ in range(5):
+            v1 = (rng.random(n - 1) * (2 * np.arange(n - 1) + 1)).astype(np.int64)
+            v2 = (rng.random(n - 1) * (2 * np.arange(n - 1) + 1)).astype(np.int64)
+
+            def splits(v):
+                anc = O.to_ancestry(v)
+                below = {i: frozenset([i]) for i in range(n)}
+                out = set()
+                for c1, c2, p in anc.tolist():
+                    below[p] = below[c1] | below[c2]
+                for p, s in below.items():
+                    if 2 <= len(s) <= n - 2:
+                        out.add(frozenset([s, frozenset(range(n)) - s]))
+                return out
+            s1, s2 = splits(v1), splits(v2)
+            assert O.robinson_foulds(v1, v2) == len(s1 ^ s2)
+            assert len(s1) == n - 3 and len(s2) == n - 3
+
+
 def test_check_v_message():
     # phylo2vec/src/vector/base.rs:60-67
     with pytest.raises(AssertionError) as e:
