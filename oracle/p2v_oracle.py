@@ -423,3 +423,153 @@ def robinson_foulds(v1, v2, normalize: bool = False) -> float:
         m = len(s1) + len(s2)
         return 0.0 if m == 0 else diff / m
     return float(diff)
+
+
+# ---- matrices <-> Newick with branch lengths (matrix/convert.rs, newick/mod.rs:161-255) ---------------
+def ryu_format(x: float) -> str:
+    """The Rust `ryu` crate's Buffer::format (what matrix/convert.rs:37-57 writes): the shortest round-trip
+    digits -- the same digits Python's repr finds -- laid out by ryu's rules: plain decimal for
+    1e-5 <= |x| < 1e16, otherwise d[.ddd]e[-]x without '+' or padding; a whole number ends in ".0"."""
+    import math
+    from decimal import Decimal
+    if math.isnan(x):
+        return "NaN"
+    if math.isinf(x):
+        return "-inf" if x < 0 else "inf"
+    sign = "-" if math.copysign(1.0, x) < 0 else ""
+    if x == 0:
+        return sign + "0.0"
+    t = Decimal(repr(abs(x))).as_tuple()
+    digits = "".join(map(str, t.digits)).lstrip("0")
+    k = t.exponent
+    stripped = digits.rstrip("0")
+    k += len(digits) - len(stripped)
+    digits = stripped
+    length = len(digits)
+    kk = length + k
+    if 0 <= k and kk <= 16:
+        return sign + digits + "0" * k + ".0"
+    if 0 < kk <= 16:
+        return sign + digits[:kk] + "." + digits[kk:]
+    if -5 < kk <= 0:
+        return sign + "0." + "0" * (-kk) + digits
+    e = kk - 1
+    return sign + digits[0] + ("." + digits[1:] if length > 1 else "") + "e" + str(e)
+
+
+def to_newick_matrix(m) -> str:
+    """matrix/convert.rs:26-57: check_m, parse_matrix, to_pairs, build_newick_with_bls."""
+    m = np.asarray(m, dtype=np.float64)
+    check_m(m)
+    v = m[:, 0].astype(np.int64)
+    pairs = to_pairs(v)
+    k = pairs.shape[0]
+    n = k + 1
+    cache = [str(i) for i in range(n)]
+    for c1, _c2 in pairs.tolist():               # prepare_cache, vector/convert.rs:341-359
+        cache[c1] = "(" + cache[c1]
+    for i, ((c1, c2), (bl1, bl2)) in enumerate(zip(pairs.tolist(), m[:, 1:3].tolist())):
+        s2 = cache[c2]
+        cache[c2] = ""
+        cache[c1] = cache[c1] + ":" + ryu_format(bl1) + "," + s2 + ":" + ryu_format(bl2) + ")" + str(n + i)
+    return cache[0] + ";"
+
+
+def _node_substr(s: str, start: int):
+    """newick/mod.rs:23-38"""
+    end = start
+    for i in range(start, len(s)):
+        if s[i] in ",);":
+            end = i
+            break
+    return s[start:end], end
+
+
+def parse_with_bls(newick: str):
+    """newick/mod.rs:161-255 (floats by Python's float(): correctly rounded, like Rust's parse::<f64>)."""
+    anc, bls, stack, bl_stack = [], [], [], []
+    i = 0
+    while i < len(newick):
+        c = newick[i]
+        if c == ")":
+            c2 = stack.pop()
+            c1 = stack.pop()
+            bl2 = bl_stack.pop()
+            bl1 = bl_stack.pop()
+            bls.append([bl1, bl2])
+            annotation, end = _node_substr(newick, i + 1)
+            i = end - 1
+            if ":" in annotation:
+                p, blp = annotation.split(":", 1)
+                if p == "":
+                    anc.append([c1, c2, max(c1, c2)])
+                    stack.append(min(c1, c2))
+                else:
+                    anc.append([c1, c2, int(p)])
+                    stack.append(int(p))
+                bl_stack.append(float(blp))
+            else:
+                if end == len(newick) - 1:
+                    anc.append([c1, c2, max(c1, c2)] if annotation == "" else [c1, c2, int(annotation)])
+                    break
+                raise ValueError("Missing annotation in the Newick string")
+        elif c.isdigit():
+            annotated, end = _node_substr(newick, i)
+            i = end - 1
+            node, bln = annotated.split(":", 1)
+            stack.append(int(node))
+            bl_stack.append(float(bln))
+        i += 1
+    return anc, bls
+
+
+def from_newick_matrix(newick: str) -> np.ndarray:
+    """matrix/convert.rs:84-122 with order_cherries / build_cherries (vector/convert.rs:398-477) and
+    order_cherries_no_parents (:534-573) including the rows whose two lengths swap."""
+    import re
+    if newick == "":
+        return np.zeros((0, 3))
+    cherries, bls = parse_with_bls(newick)
+    k = len(cherries)
+    has_parents = re.search(r"\)(\d+)", newick) is not None          # newick/mod.rs NewickPatterns.parents
+    swaps = []
+    if has_parents:
+        offset = max(c[2] for c in cherries) - 2 * k + 1
+        row_idxs = list(range(k))
+        new = [None] * k
+        for i, ch in enumerate(cherries):
+            idx = ch[2] - k - offset
+            new[idx] = list(ch)
+            row_idxs[idx] = i
+        min_desc = {}
+        for i, (c1, c2, p) in enumerate(new):
+            m1 = min_desc.get(c1, c1)
+            m2 = min_desc.get(c2, c2)
+            if m1 < m2:
+                lo, hi = m1, m2
+            else:
+                swaps.append(row_idxs[i])
+                lo, hi = m2, m1
+            min_desc[p] = lo
+            new[i] = [m1, m2, hi]
+        cherries = new
+    else:
+        to_sort, visited = [], {}
+        for c1, c2, cmax in cherries:
+            cmin = min(c1, c2)
+            sister = visited[cmin] if (cmin in visited and visited[cmin] < cmax) else cmax
+            to_sort.append(sister)
+            visited[cmin] = sister
+        row_idxs = sorted(range(k), key=lambda i: -to_sort[i])        # stable, descending
+        for i in row_idxs:
+            if cherries[i][0] > cherries[i][1]:
+                swaps.append(i)
+        cherries = [cherries[i] for i in row_idxs]
+    v = build_vector(np.array(cherries, dtype=np.int64))
+    for i in swaps:
+        bls[i] = [bls[i][1], bls[i][0]]
+    out = np.zeros((k, 3))
+    for i in range(k):
+        out[i, 0] = float(v[i])
+        out[i, 1], out[i, 2] = bls[row_idxs[i]]
+    return out

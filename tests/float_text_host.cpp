@@ -1,0 +1,15 @@
+// Host build of phylo2vec_b200/csrc/p2v_float_text.cuh for the CPU test suite (tests/test_float_text.py):
+// the same source the CUDA kernels compile, called through ctypes.
+#include "../phylo2vec_b200/csrc/p2v_float_text.cuh"
+
+extern "C" {
+int ft_format(double x, char* buf) { return p2v_ft::f64_to_shortest(x, buf); }
+int ft_parse(const char* s, int len, double* out) { return p2v_ft::parse_f64(s, len, out); }
+// batch forms so that millions of values are checked without ctypes call overhead
+void ft_format_many(const double* x, long n, char* buf /* n * 32 */, int* lens) {
+    for (long i = 0; i < n; ++i) lens[i] = p2v_ft::f64_to_shortest(x[i], buf + 32 * i);
+}
+void ft_parse_many(const char* buf /* n * stride */, const int* lens, long n, int stride, double* out, int* rc) {
+    for (long i = 0; i < n; ++i) rc[i] = p2v_ft::parse_f64(buf + (long)stride * i, lens[i], out + i);
+}
+}
