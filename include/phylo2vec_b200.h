@@ -189,8 +189,8 @@ int p2v_robinson_foulds_host(const void *v1, const void *v2, int idx_bytes, int6
  * point to_newick, vector arm (py-phylo2vec/src/lib.rs:90-96); Python phylo2vec.base.newick.
  * to_newick (base/newick.py:29-43).  Tree b's string is written NUL-terminated at
  * out + b * out_stride (out_stride >= p2v_newick_max_bytes(k)); lengths[b] (may be NULL) gets
- * its length without the NUL, 0 for an invalid vector.  k <= 2^19 (the matrix form with
- * branch lengths is not built).  The workspace holds the int32 ancestry of the batch, the
+ * its length without the NUL, 0 for an invalid vector.  k <= 2^19 (matrices with branch lengths:
+ * p2v_to_newick_matrix_batch below).  The workspace holds the int32 ancestry of the batch, the
  * decoder's scratch and, for trees too large for shared memory, per-CTA tables. */
 size_t p2v_newick_max_bytes(int64_t k);
 size_t p2v_newick_workspace_bytes(int64_t B, int64_t k);     /* the int32 ancestry of the batch */
@@ -212,6 +212,32 @@ size_t p2v_from_newick_workspace_bytes(int64_t B, int64_t k, int idx_bytes);
 int p2v_from_newick_batch(const char *newick, int64_t in_stride, const int64_t *lengths, int64_t B, int64_t k,
                           void *v, int idx_bytes, int32_t *status, void *workspace, size_t workspace_bytes,
                           p2v_stream_t stream);
+
+/* ---- matrices <-> Newick strings with branch lengths (second "next" row, matrix forms) ----------
+ * to_newick replaces matrix::convert::to_newick / build_newick_with_bls (phylo2vec/src/matrix/
+ * convert.rs:26-57; PyO3 to_newick, matrix arm, py-phylo2vec/src/lib.rs:90-96): matrix (B,k,3)
+ * float64 rows [v, bl1, bl2]; lengths are written as the shortest decimal that reads back to the
+ * same double, in the layout of the Rust ryu crate ("0.5", "3.0", "1e-7").  status: as check_m
+ * (the reference validates the matrix first).  out_stride >= p2v_newick_matrix_max_bytes(k).
+ * from_newick replaces matrix::convert::from_newick (:84-122) with newick::parse_with_bls
+ * (newick/mod.rs:161-255) and the branch-length bookkeeping of order_cherries /
+ * order_cherries_no_parents (vector/convert.rs:398-477, 534-573); PyO3 to_matrix (py-phylo2vec/src/
+ * lib.rs:103-106).  Strings with or without parent labels, every node but the root followed by
+ * ":length" (any literal Rust's str::parse::<f64> accepts; correctly rounded); every tree of the
+ * batch has k + 1 leaves labelled 0..k.  status[b]: 0 or P2V_TREE_MALFORMED. */
+size_t p2v_newick_matrix_max_bytes(int64_t k);
+size_t p2v_newick_matrix_workspace_bytes(int64_t B, int64_t k);
+int p2v_to_newick_matrix_batch(const double *matrix, int64_t B, int64_t k, char *out, int64_t out_stride,
+                               int64_t *lengths, int32_t *status, void *workspace, size_t workspace_bytes,
+                               p2v_stream_t stream);
+int p2v_to_newick_matrix_host(const double *matrix, int64_t B, int64_t k, char *out, int64_t out_stride,
+                              int64_t *lengths, int32_t *status);
+size_t p2v_from_newick_matrix_workspace_bytes(int64_t B, int64_t k);
+int p2v_from_newick_matrix_batch(const char *newick, int64_t in_stride, const int64_t *lengths, int64_t B, int64_t k,
+                                 double *matrix, int32_t *status, void *workspace, size_t workspace_bytes,
+                                 p2v_stream_t stream);
+int p2v_from_newick_matrix_host(const char *newick, int64_t in_stride, int64_t B, int64_t k, double *matrix,
+                                int32_t *status);
 
 /* ---- host-buffer entry points (H2D + kernels + D2H inside the call) ------ */
 int p2v_to_pairs_host(const void *v, int idx_bytes, int64_t B, int64_t k, void *pairs, int32_t *status);

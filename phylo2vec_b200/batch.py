@@ -355,32 +355,106 @@ def node_depths_batch(trees, out=None, bls=None, status=None, check: bool = True
 
 
 def to_newick_batch(V, status=None, check: bool = True, raw: bool = False):
-    """Newick strings of a batch of vectors ``(B,k)`` .  Returns a list of ``str``; with
-    ``raw=True`` the device buffers instead: a uint8 tensor ``(B, stride)`` of NUL-terminated strings
-    and an int64 tensor of their lengths.
-    Replaces vector::convert::to_newick (phylo2vec/src/vector/convert.rs:341-397)."""
-    V = _idx_tensor(V, 2, "to_newick")
-    B, k = V.shape
+    """Newick strings of a batch of vectors ``(B,k)`` or of matrices ``(B,k,3)`` float64 (branch lengths).  Returns
+    a list of ``str``; with ``raw=True`` the device buffers instead: a uint8 tensor ``(B, stride)`` of
+    NUL-terminated strings and an int64 tensor of their lengths.
+    Replaces vector::convert::to_newick (phylo2vec/src/vector/convert.rs:341-397) and matrix::convert::to_newick
+    (phylo2vec/src/matrix/convert.rs:26-57)."""
+    T = as_tensor(V)
     lib = _capi.load()
-    stride = (int(lib.p2v_newick_max_bytes(k)) + 15) & ~15
-    out = torch.empty((B, stride), dtype=torch.uint8, device=V.device)
-    lengths = torch.empty(B, dtype=torch.int64, device=V.device)
-    if status is None:
-        status = torch.empty(B, dtype=torch.int32, device=V.device)
-    need = int(lib.p2v_newick_workspace_bytes(B, k))
-    with torch.cuda.device(V.device):
-        ws = torch.empty(max(need, 16), dtype=torch.uint8, device=V.device)
-        rc = lib.p2v_to_newick_batch(V.data_ptr(), V.element_size(), B, k, out.data_ptr(), stride,
-                                     lengths.data_ptr(), status.data_ptr(), ws.data_ptr(), need,
-                                     _stream_ptr(V.device))
-    _capi.check(rc, "to_newick")
-    if check and bool(status.any()):
-        raise_for_status(status, V)
+    if T.dim() == 3:
+        if not T.is_cuda or T.dtype != torch.float64 or T.shape[2] != 3:
+            raise TypeError("to_newick: matrices must be a float64 CUDA tensor (B,k,3)")
+        M = T.contiguous()
+        B, k = M.shape[0], M.shape[1]
+        if k == 0:
+            raise AssertionError("Matrix should not be empty")
+        stride = (int(lib.p2v_newick_matrix_max_bytes(k)) + 15) & ~15
+        out = torch.empty((B, stride), dtype=torch.uint8, device=M.device)
+        lengths = torch.empty(B, dtype=torch.int64, device=M.device)
+        status = _check_status(status, B, M.device, "to_newick")
+        need = int(lib.p2v_newick_matrix_workspace_bytes(B, k))
+        with torch.cuda.device(M.device):
+            ws = torch.empty(max(need, 16), dtype=torch.uint8, device=M.device)
+            rc = lib.p2v_to_newick_matrix_batch(M.data_ptr(), B, k, out.data_ptr(), stride, lengths.data_ptr(),
+                                                status.data_ptr(), ws.data_ptr(), need, _stream_ptr(M.device))
+        _capi.check(rc, "to_newick")
+        if check and bool(status.any()):
+            raise_for_status(status, M[..., 0].to(torch.int64))
+        V = M
+    else:
+        V = _idx_tensor(V, 2, "to_newick")
+        B, k = V.shape
+        stride = (int(lib.p2v_newick_max_bytes(k)) + 15) & ~15
+        out = torch.empty((B, stride), dtype=torch.uint8, device=V.device)
+        lengths = torch.empty(B, dtype=torch.int64, device=V.device)
+        status = _check_status(status, B, V.device, "to_newick")
+        need = int(lib.p2v_newick_workspace_bytes(B, k))
+        with torch.cuda.device(V.device):
+            ws = torch.empty(max(need, 16), dtype=torch.uint8, device=V.device)
+            rc = lib.p2v_to_newick_batch(V.data_ptr(), V.element_size(), B, k, out.data_ptr(), stride,
+                                         lengths.data_ptr(), status.data_ptr(), ws.data_ptr(), need,
+                                         _stream_ptr(V.device))
+        _capi.check(rc, "to_newick")
+        if check and bool(status.any()):
+            raise_for_status(status, V)
     if raw:
         return out, lengths
-    host = out.cpu().numpy()
     ln = lengths.cpu().numpy()
+    width = int(ln.max()) if B else 0
+    host = out[:, :max(width, 1)].cpu().numpy()
     return [host[b, :ln[b]].tobytes().decode("ascii") for b in range(B)]
+
+
+def to_matrix_batch(newick, lengths=None, n_leaves: Optional[int] = None, status=None, check: bool = True,
+                    device=None) -> torch.Tensor:
+    """Matrices ``(B,k,3)`` float64 ``[v, bl1, bl2]`` of a batch of Newick strings with branch lengths (with or
+    without parent labels); every tree has the same number of leaves.  ``newick`` is a list of ``str`` or the raw
+    form :func:`to_newick_batch` returns.  Replaces matrix::convert::from_newick
+    (phylo2vec/src/matrix/convert.rs:84-122; PyO3 to_matrix, py-phylo2vec/src/lib.rs:103-106)."""
+    newick, lengths, n_leaves = _newick_buffers(newick, lengths, n_leaves, device, "to_matrix")
+    B, stride = newick.shape
+    k = int(n_leaves) - 1
+    lib = _capi.load()
+    m = torch.empty((B, k, 3), dtype=torch.float64, device=newick.device)
+    status = _check_status(status, B, newick.device, "to_matrix")
+    need = int(lib.p2v_from_newick_matrix_workspace_bytes(B, k))
+    with torch.cuda.device(newick.device):
+        ws = torch.empty(max(need, 16), dtype=torch.uint8, device=newick.device)
+        rc = lib.p2v_from_newick_matrix_batch(newick.data_ptr(), stride, 0 if lengths is None else lengths.data_ptr(), B, k,
+                                              m.data_ptr(), status.data_ptr(), ws.data_ptr(), need,
+                                              _stream_ptr(newick.device))
+    _capi.check(rc, "to_matrix")
+    if check:
+        st = status.cpu().numpy()
+        if st.any():
+            raise ValueError(f"malformed Newick string (tree {int(np.flatnonzero(st)[0])})")
+    return m
+
+
+def _newick_buffers(newick, lengths, n_leaves, device, what):
+    """list of str -> (uint8 (B, stride) CUDA tensor, int64 lengths, n_leaves); raw buffers pass through."""
+    if isinstance(newick, (list, tuple)):
+        if len(newick) == 0:
+            raise ValueError(f"{what}: empty batch")
+        enc = [s.encode("ascii") for s in newick]
+        if n_leaves is None:
+            n_leaves = enc[0].count(b",") + 1
+        stride = (max(len(e) for e in enc) + 1 + 15) & ~15
+        host = np.zeros((len(enc), stride), dtype=np.uint8)
+        for b, e in enumerate(enc):
+            host[b, :len(e)] = np.frombuffer(e, dtype=np.uint8)
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        newick = torch.from_numpy(host).to(dev)
+        lengths = torch.tensor([len(e) for e in enc], dtype=torch.int64, device=dev)
+    if not (isinstance(newick, torch.Tensor) and newick.dtype == torch.uint8 and newick.dim() == 2 and newick.is_cuda):
+        raise TypeError(f"{what}: expected a list of str or a uint8 CUDA tensor (B, stride)")
+    if n_leaves is None:
+        raise ValueError(f"{what}: n_leaves is required with a raw buffer")
+    newick = newick.contiguous()
+    if lengths is not None:
+        lengths = lengths.to(device=newick.device, dtype=torch.int64).contiguous()
+    return newick, lengths, n_leaves
 
 
 def from_newick_batch(newick, lengths=None, n_leaves: Optional[int] = None, dtype=torch.int64, status=None,

@@ -1294,6 +1294,88 @@ int p2v_from_newick_host(const char* newick, int64_t in_stride, int64_t B, int64
         });
 }
 
+// ---- matrices <-> Newick with branch lengths --------------------------------------------------
+size_t p2v_newick_matrix_max_bytes(int64_t k) { return newick_matrix_max_bytes(k); }
+size_t p2v_newick_matrix_workspace_bytes(int64_t B, int64_t k) { return newick_matrix_workspace_bytes(B, k); }
+size_t p2v_from_newick_matrix_workspace_bytes(int64_t B, int64_t k) { return from_newick_matrix_workspace_bytes(B, k); }
+static int nm_to_check(const double* m, const char* out, int64_t B, int64_t k, int64_t out_stride) {
+    if (B < 0 || k < 0) return fail(P2V_ERR_INVALID_ARG, "negative batch or length");
+    if (k == 0 && B > 0) return fail(P2V_ERR_INVALID_ARG, "Matrix should not be empty");
+    if (k > LARGE_K_MAX) return fail(P2V_ERR_UNSUPPORTED, "to_newick: k above 2^19");
+    if (B > 0 && (!out || !m)) return fail(P2V_ERR_INVALID_ARG, "null buffer");
+    if (out_stride < (int64_t)newick_matrix_max_bytes(k)) return fail(P2V_ERR_INVALID_ARG, "out_stride below p2v_newick_matrix_max_bytes(k)");
+    return P2V_OK;
+}
+int p2v_to_newick_matrix_batch(const double* matrix, int64_t B, int64_t k, char* out, int64_t out_stride, int64_t* lengths,
+                               int32_t* status, void* ws, size_t ws_bytes, p2v_stream_t stream) {
+    int rc = nm_to_check(matrix, out, B, k, out_stride);
+    if (rc) return rc;
+    if (B == 0) return P2V_OK;
+    if (!ws || ws_bytes < newick_matrix_workspace_bytes(B, k)) return fail(P2V_ERR_WORKSPACE, "to_newick workspace too small");
+    return from_cuda(launch_to_newick_matrix(matrix, B, k, out, out_stride, lengths, status, ws, ws_bytes,
+                                             (cudaStream_t)stream), "to_newick (matrix) launch");
+}
+int p2v_to_newick_matrix_host(const double* matrix, int64_t B, int64_t k, char* out, int64_t out_stride, int64_t* lengths,
+                              int32_t* status) {
+    HostTrim trim_on_return;
+    int rc = nm_to_check(matrix, out, B, k, out_stride);
+    if (rc) return rc;
+    if (B == 0) return P2V_OK;
+    int64_t done = 0;
+    int64_t* dlen[HOST_STREAMS] = {};
+    int64_t cap_chunk = 0;
+    int flip = 0;
+    int r = host_chunked(
+        matrix, (size_t)k * 3 * sizeof(double), out, (size_t)out_stride, status, B,
+        [&](int64_t nb) { if (nb > cap_chunk) cap_chunk = nb; return newick_matrix_workspace_bytes(nb, k); },
+        [&](void* din, void* dout, int32_t* dst, int64_t nb, void* ws, size_t wsb, cudaStream_t st) {
+            cudaError_t e = cudaSuccess;
+            const int s = flip; flip = (flip + 1) % HOST_STREAMS;
+            if (!dlen[s]) e = cudaMalloc((void**)&dlen[s], sizeof(int64_t) * (size_t)cap_chunk);
+            if (e != cudaSuccess) return e;
+            e = launch_to_newick_matrix((const double*)din, nb, k, (char*)dout, out_stride, dlen[s], dst, ws, wsb, st);
+            if (e == cudaSuccess && lengths)
+                e = cudaMemcpyAsync(lengths + done, dlen[s], sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, st);
+            done += nb;
+            return e;
+        });
+    cudaDeviceSynchronize();
+    for (int i = 0; i < HOST_STREAMS; ++i) if (dlen[i]) cudaFree(dlen[i]);
+    return r;
+}
+static int nm_from_check(const char* newick, int64_t in_stride, const double* m, int64_t B, int64_t k) {
+    if (B < 0 || k < 0) return fail(P2V_ERR_INVALID_ARG, "negative batch or length");
+    if (k > LARGE_K_MAX) return fail(P2V_ERR_UNSUPPORTED, "from_newick: k above 2^19");
+    if (B > 0 && (!newick || (k > 0 && !m))) return fail(P2V_ERR_INVALID_ARG, "null buffer");
+    if (in_stride < 1) return fail(P2V_ERR_INVALID_ARG, "in_stride must be positive");
+    return P2V_OK;
+}
+int p2v_from_newick_matrix_batch(const char* newick, int64_t in_stride, const int64_t* lengths, int64_t B, int64_t k,
+                                 double* matrix, int32_t* status, void* ws, size_t ws_bytes, p2v_stream_t stream) {
+    int rc = nm_from_check(newick, in_stride, matrix, B, k);
+    if (rc) return rc;
+    if (B == 0) return P2V_OK;
+    if (k == 0) {
+        if (status) return from_cuda(cudaMemsetAsync(status, 0, sizeof(int32_t) * B, (cudaStream_t)stream), "from_newick status");
+        return P2V_OK;
+    }
+    if (!ws || ws_bytes < from_newick_matrix_workspace_bytes(B, k)) return fail(P2V_ERR_WORKSPACE, "from_newick workspace too small");
+    return from_cuda(launch_from_newick_matrix(newick, in_stride, lengths, B, k, matrix, status, ws, ws_bytes,
+                                               (cudaStream_t)stream), "from_newick (matrix) launch");
+}
+int p2v_from_newick_matrix_host(const char* newick, int64_t in_stride, int64_t B, int64_t k, double* matrix, int32_t* status) {
+    HostTrim trim_on_return;
+    int rc = nm_from_check(newick, in_stride, matrix, B, k);
+    if (rc) return rc;
+    if (k == 0) { if (status && B > 0) memset(status, 0, sizeof(int32_t) * B); return P2V_OK; }
+    return host_chunked(
+        newick, (size_t)in_stride, matrix, (size_t)k * 3 * sizeof(double), status, B,
+        [&](int64_t nb) { return from_newick_matrix_workspace_bytes(nb, k); },
+        [&](void* din, void* dout, int32_t* dst, int64_t nb, void* ws, size_t wsb, cudaStream_t st) {
+            return launch_from_newick_matrix((const char*)din, in_stride, nullptr, nb, k, (double*)dout, dst, ws, wsb, st);
+        });
+}
+
 int p2v_to_pairs_host(const void* v, int idx_bytes, int64_t B, int64_t k, void* out, int32_t* status) {
     HostTrim trim_on_return;
     return decode_host(MODE_PAIRS, 2, v, idx_bytes, B, k, out, status);

@@ -242,6 +242,13 @@ cudaError_t launch_check_m(const double* m, const double* bl, int bl_stride, int
     return cudaGetLastError();
 }
 
+cudaError_t launch_matrix_v(const double* m, int64_t count, int* out, cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    matrix_v_kernel<<<sm_count() * 8, 256, 0, stream>>>(m, count, out);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // ---- k < 2 special cases (graph.rs:28-42) ---------------------------------------------
 __global__ void tiny_sum_kernel(const double* __restrict__ bl, int64_t bl_tree_stride, int64_t B,
                                 double* __restrict__ sums) {

@@ -29,7 +29,6 @@ constexpr int ENC_LARGE_WARPS = ENC_LARGE_THREADS / 32;
 
 // status codes written per tree
 constexpr int32_t TREE_OK = 0;
-constexpr int32_t TREE_MALFORMED = -2;
 
 // ---- generic per-tree body, parameterised on the storage type of the scratch
 //      arrays (uint16 in shared memory for k<=1024, uint32 in global above) ----

@@ -11,6 +11,7 @@ namespace p2v {
 enum DecodeMode { MODE_PAIRS = 0, MODE_ANCESTRY = 1, MODE_EDGES = 2, MODE_ANC2 = 3 };
 enum EncodeMode { FROM_PAIRS = 0, FROM_ANCESTRY = 1, FROM_EDGES = 2 };
 
+constexpr int32_t TREE_MALFORMED = -2;   // P2V_TREE_MALFORMED of the public header
 constexpr int SMALL_K_MAX = 2016;      // warp-per-tree decode in shared memory; the half2 rank scan needs K + 30 <= 2048
 constexpr int ENC_SMALL_K_MAX = 2047;  // warp-per-tree encode (rows exact in fp16)
 constexpr int LARGE_K_MAX = 1 << 19;   // CTA-per-tree kernels (bit mask + Fenwick in shared memory)
@@ -81,6 +82,16 @@ size_t robinson_foulds_workspace_bytes(int64_t B1, int64_t B2, int64_t k);
 cudaError_t launch_robinson_foulds(const void* v1, const void* v2, int idx_bytes, int64_t B1, int64_t B2, int64_t k,
                                    int normalize, double* out, int32_t* status, void* ws, size_t ws_bytes,
                                    cudaStream_t stream);
+// matrices <-> Newick strings with branch lengths (matrix/convert.rs:26-122)
+size_t newick_matrix_max_bytes(int64_t k);
+size_t newick_matrix_workspace_bytes(int64_t B, int64_t k);
+cudaError_t launch_to_newick_matrix(const double* m, int64_t B, int64_t k, char* out, int64_t out_stride, int64_t* lengths,
+                                    int32_t* status, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t from_newick_matrix_workspace_bytes(int64_t B, int64_t k);
+cudaError_t launch_from_newick_matrix(const char* in, int64_t in_stride, const int64_t* lengths, int64_t B, int64_t k,
+                                      double* m, int32_t* status, void* ws, size_t ws_bytes, cudaStream_t stream);
+// parse_matrix (matrix/base.rs:108-121): column 0 of (count,3) float64 rows as int32, saturating like `as usize`
+cudaError_t launch_matrix_v(const double* m, int64_t count, int* out, cudaStream_t stream);
 // int64 -> int32 index vectors (values that do not fit become -1 and fail check_v downstream)
 cudaError_t launch_narrow_v(const long long* v, int64_t count, int* out, cudaStream_t stream);
 

@@ -27,6 +27,7 @@
 
 #include "p2v_common.cuh"
 #include "p2v_internal.h"
+#include "p2v_tree_pass.cuh"
 
 namespace p2v {
 
@@ -46,46 +47,6 @@ __host__ __device__ inline uint32_t rf_hash_size(int64_t k) {
 }
 
 __device__ __forceinline__ uint32_t rf_slot(uint32_t key, uint32_t mask) { return (key * 2654435761u) >> 7 & mask; }
-
-// Bottom-up pass over rows [0,k): fire(r) runs once both children of row r are final.
-// Top-down pass: fire(r) runs once the parent row of r is final (the root row k-1 fires first).
-template <typename ST, typename Fire>
-__device__ __forceinline__ void rf_bottom_up(const ST* ch, int k, int lane, Fire fire) {
-    for (int base = 0; base < k; base += 32) {
-        const int r = base + lane;
-        const bool act = r < k;
-        int c1 = 0, c2 = 0;
-        if (act) { c1 = (int)ch[2 * r]; c2 = (int)ch[2 * r + 1]; }
-        // a child is a leaf (label <= k), a row of an earlier batch, or a row of this batch
-        const int w1 = (act && c1 > k && c1 - k - 1 >= base) ? c1 - k - 1 - base : -1;
-        const int w2 = (act && c2 > k && c2 - k - 1 >= base) ? c2 - k - 1 - base : -1;
-        unsigned done_mask = ~__ballot_sync(FULL, act);          // inactive lanes count as done
-        bool fired = !act;
-        while (done_mask != FULL) {
-            const bool ready = !fired && (w1 < 0 || ((done_mask >> w1) & 1u)) && (w2 < 0 || ((done_mask >> w2) & 1u));
-            if (ready) { fire(r, c1, c2); fired = true; }
-            __syncwarp();
-            done_mask |= __ballot_sync(FULL, ready);
-        }
-    }
-}
-template <typename ST, typename Fire>
-__device__ __forceinline__ void rf_top_down(const ST* par, int k, int lane, Fire fire) {
-    for (int base = ((k - 1) / 32) * 32; base >= 0; base -= 32) {
-        const int r = base + lane;
-        const bool act = r < k;
-        const int p = (act && r != k - 1) ? (int)par[r] : -1;        // parent row; the root has none
-        const int w = (p >= 0 && p < base + 32) ? p - base : -1;      // parent in this batch
-        unsigned done_mask = ~__ballot_sync(FULL, act);
-        bool fired = !act;
-        while (done_mask != FULL) {
-            const bool ready = !fired && (w < 0 || ((done_mask >> w) & 1u));
-            if (ready) { fire(r, p); fired = true; }
-            __syncwarp();
-            done_mask |= __ballot_sync(FULL, ready);
-        }
-    }
-}
 
 // anc: (k,2) int32 rows [child1, child2] of the two trees (the third column is k+1+row).
 template <typename ST>

@@ -134,6 +134,28 @@ G = {
         {"v1": [0, 0, 0], "v2": [0, 1, 0], "normalize": False, "expected": "range_0_2", "src": "distance.rs:207-217"},
         {"v1": [0, 1, 2], "v2": [0, 1, 2], "normalize": False, "expected": 0.0, "src": "distance.rs:33-34 (doctest)"},
     ],
+    # matrices <-> Newick with branch lengths: phylo2vec/src/matrix/convert.rs doctests and test tables
+    "to_newick_matrix": [
+        {"m": [[0.0, 0.5, 0.8], [1.0, 0.7, 0.6]], "newick": "(0:0.7,(1:0.5,2:0.8)3:0.6)4;", "src": "matrix/convert.rs:18-24"},
+        {"m": [[0.0, 0.9, 0.4], [0.0, 0.8, 3.12], [3.0, 0.4, 0.5]], "newick": "(((0:0.9,2:0.4)4:0.8,3:3.12)5:0.4,1:0.5)6;",
+         "src": "matrix/convert.rs:191-196"},
+        {"m": [[0.0, 0.1, 0.2]], "newick": "(0:0.1,1:0.2)2;", "src": "matrix/convert.rs:197"},
+        {"m": [[0.0, 1.0, 3.0], [0.0, 0.1, 0.2], [1.0, 0.5, 0.7]], "newick": "((0:0.1,2:0.2)5:0.5,(1:1.0,3:3.0)4:0.7)6;",
+         "src": "matrix/convert.rs:198-202"},
+    ],
+    "from_newick_matrix": [
+        {"newick": "(0:0.1,1:0.2)2;", "m": [[0.0, 0.1, 0.2]], "src": "matrix/convert.rs:73-78, 133"},
+        {"newick": "(1:0.2,0:0.1)2;", "m": [[0.0, 0.1, 0.2]], "src": "matrix/convert.rs:135 (bl_rows_to_swap)"},
+        {"newick": "(((0:0.9,2:0.4)4:0.8,3:3.0)5:0.4,1:0.5)6;", "m": [[0.0, 0.9, 0.4], [0.0, 0.8, 3.0], [3.0, 0.4, 0.5]],
+         "src": "matrix/convert.rs:136-140"},
+        {"newick": "(0:0.7,(1:0.5,2:0.8)3:0.6)4;", "m": [[0.0, 0.5, 0.8], [1.0, 0.7, 0.6]], "src": "matrix/convert.rs:141-144"},
+        {"newick": "((((0:0.30118185,3:0.69665915)5:0.69915295,4:0.059750594)6:0.0017238181,1:0.34410468)7:0.2021168,2:0.7084421)8;",
+         "m": [[0.0, 0.30118185, 0.69665915], [2.0, 0.69915295, 0.059750594], [0.0, 0.0017238181, 0.34410468],
+               [4.0, 0.2021168, 0.7084421]], "src": "matrix/convert.rs:145-150"},
+        {"newick": "(0:0.5,1:0.6);", "m": [[0.0, 0.5, 0.6]], "src": "matrix/convert.rs:160-162 (no parents)"},
+        {"newick": "((0:0.1,2:0.2):0.3,(1:0.5,3:0.7):0.4);", "m": [[0.0, 0.5, 0.7], [0.0, 0.1, 0.2], [1.0, 0.3, 0.4]],
+         "src": "matrix/convert.rs:163-167 (no parents)"},
+    ],
     # test_check_m, phylo2vec/src/matrix/base.rs:131-170 (the empty-array case is a shape check)
     "check_m": {
         "ok": [

@@ -118,6 +118,24 @@ def test_robinson_foulds(goldens):
             assert len(s1) == n - 3 and len(s2) == n - 3
 
 
+def test_matrix_newick(goldens):
+    # phylo2vec/src/matrix/convert.rs:26-122 with its doctests and tables (:18-24, :73-78, :131-205)
+    for g in goldens["to_newick_matrix"]:
+        assert O.to_newick_matrix(g["m"]) == g["newick"], g["src"]
+    for g in goldens["from_newick_matrix"]:
+        assert np.array_equal(O.from_newick_matrix(g["newick"]), np.array(g["m"])), g["src"]
+    assert O.from_newick_matrix("").shape == (0, 3)                       # :171-178
+    # test_newick (:207-222): matrix -> Newick -> matrix is the identity, bit for bit
+    from tests.helpers import sample_bls, sample_vectors, to_matrix_input
+    for n in (5, 10, 50, 100):
+        m = to_matrix_input(sample_vectors(1, n, seed=n)[0], sample_bls(1, n, seed=n)[0])
+        assert np.array_equal(O.from_newick_matrix(O.to_newick_matrix(m)), m)
+    # ryu's layout (matrix/convert.rs:37 `Buffer::format`): the strings the reference's tables hold
+    for x, sx in ((0.5, "0.5"), (3.0, "3.0"), (3.12, "3.12"), (0.059750594, "0.059750594"), (0.0017238181, "0.0017238181"),
+                  (1e-7, "1e-7"), (1e16, "1e16"), (1e15, "1000000000000000.0"), (1.5e-5, "0.000015"), (0.0, "0.0")):
+        assert O.ryu_format(x) == sx
+
+
 def test_check_v_message():
     # phylo2vec/src/vector/base.rs:60-67
     with pytest.raises(AssertionError) as e:
