@@ -36,8 +36,7 @@ def test_goldens_single_tree(p2v, goldens):
     assert to_newick([0]) == "(0,1)2;"
     with pytest.raises(AssertionError, match="out of bounds"):
         to_newick(np.array([0, 5, 1]))
-    with pytest.raises(NotImplementedError):
-        to_newick(np.zeros((3, 3)))
+    assert to_newick(np.array([[0.0, 0.5, 0.8], [1.0, 0.7, 0.6]])) == "(0:0.7,(1:0.5,2:0.8)3:0.6)4;"     # matrices: test_gpu_newick_matrix.py
 
 
 SIZES = [2, 3, 4, 5, 9, 10, 11, 33, 64, 65, 99, 100, 101, 129, 500, 999, 1000, 1001, 1023, 1024]
@@ -128,8 +127,7 @@ def test_from_newick_goldens(p2v, goldens):
         assert got.dtype == np.int64 and np.array_equal(got, np.array(g["v"])), g["src"]
     assert from_newick("0;").size == 0
     assert np.array_equal(from_newick("(0,1)2;"), [0])
-    with pytest.raises(NotImplementedError):
-        from_newick("((0:0.1,1:0.2)3:0.3,2:0.1)4;")
+    assert from_newick("((0:0.1,1:0.2)3:0.3,2:0.1)4;").shape == (2, 3)              # branch lengths: the matrix form
     assert np.array_equal(from_newick("(0,1)5,(2,3)4)6;"), [0, 2, 2])      # like the reference, "(" is not checked
     for bad in ("((0,1)5,(2,3)4)6", "((0,1)5,(2,3)4)9;", "((0,1)5,(2,x)4)6;", "((0,1)5,2,3)6;",
                 "((0,1)5,(2,2)4)6;", "((0,1)5,(2,3)5)6;", "((0,1)5;(2,3)4)6;"):
