@@ -239,6 +239,19 @@ int p2v_from_newick_matrix_batch(const char *newick, int64_t in_stride, const in
 int p2v_from_newick_matrix_host(const char *newick, int64_t in_stride, int64_t B, int64_t k, double *matrix,
                                 int32_t *status);
 
+/* ---- CSV text -> numbers (fourth "next" row: the file format either side of the batch API) -------
+ * the parsing inside phylo2vec.io.reader.load / read (py-phylo2vec/phylo2vec/io/reader.py:16-57,
+ * numpy.genfromtxt) for the files io/writer.py:13-50 writes ("%d" vectors, "%.18e" matrices) and
+ * for batches (one tree per line).  text: nbytes characters in DEVICE memory; fields are
+ * separated by `delimiter`, newlines or blanks.  kind 0: integers into `out` (idx_bytes 4/8;
+ * a malformed field becomes -1); kind 1: float64, correctly rounded.  At most `capacity` fields
+ * are written, in text order.  counts (device, 3 int64): fields found, rows (non-empty lines)
+ * found, error bits (1: a malformed field, 2: more fields than capacity). */
+size_t p2v_csv_workspace_bytes(int64_t nbytes);
+int p2v_csv_parse_batch(const char *text, int64_t nbytes, int delimiter, int kind, void *out, int idx_bytes,
+                        int64_t capacity, int64_t *counts, void *workspace, size_t workspace_bytes,
+                        p2v_stream_t stream);
+
 /* ---- host-buffer entry points (H2D + kernels + D2H inside the call) ------ */
 int p2v_to_pairs_host(const void *v, int idx_bytes, int64_t B, int64_t k, void *pairs, int32_t *status);
 int p2v_to_ancestry_host(const void *v, int idx_bytes, int64_t B, int64_t k, void *ancestry, int32_t *status);

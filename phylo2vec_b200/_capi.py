@@ -56,6 +56,8 @@ SIGNATURES = {
     "p2v_from_newick_matrix_workspace_bytes": (_sz, [_i64, _i64]),
     "p2v_from_newick_matrix_batch": (_int, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "p2v_from_newick_matrix_host": (_int, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    "p2v_csv_workspace_bytes": (_sz, [_i64]),
+    "p2v_csv_parse_batch": (_int, [_vp, _i64, _int, _int, _vp, _int, _i64, _vp, _vp, _sz, _vp]),
     "p2v_balance_workspace_bytes": (_sz, [_i64, _i64]),
     "p2v_balance_batch": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "p2v_balance_host": (_int, [_vp, _int, _i64, _i64, _vp, _vp]),

@@ -1376,6 +1376,19 @@ int p2v_from_newick_matrix_host(const char* newick, int64_t in_stride, int64_t B
         });
 }
 
+// ---- CSV text -> numbers (the load side of io/reader.py) ----------------------------------------
+size_t p2v_csv_workspace_bytes(int64_t nbytes) { return csv_workspace_bytes(nbytes); }
+int p2v_csv_parse_batch(const char* text, int64_t nbytes, int delimiter, int kind, void* out, int idx_bytes,
+                        int64_t capacity, int64_t* counts, void* ws, size_t ws_bytes, p2v_stream_t stream) {
+    if (nbytes < 0 || capacity < 0) return fail(P2V_ERR_INVALID_ARG, "negative size");
+    if (kind != 0 && kind != 1) return fail(P2V_ERR_INVALID_ARG, "kind must be 0 (integers) or 1 (float64)");
+    if (kind == 0 && idx_bytes != 4 && idx_bytes != 8) return fail(P2V_ERR_INVALID_ARG, "idx_bytes must be 4 or 8");
+    if (!counts || (nbytes > 0 && !text) || (capacity > 0 && !out)) return fail(P2V_ERR_INVALID_ARG, "null buffer");
+    if (!ws || ws_bytes < csv_workspace_bytes(nbytes)) return fail(P2V_ERR_WORKSPACE, "csv workspace too small");
+    return from_cuda(launch_csv_parse(text, nbytes, (char)delimiter, kind, out, idx_bytes, capacity,
+                                      reinterpret_cast<long long*>(counts), ws, ws_bytes, (cudaStream_t)stream), "csv parse");
+}
+
 int p2v_to_pairs_host(const void* v, int idx_bytes, int64_t B, int64_t k, void* out, int32_t* status) {
     HostTrim trim_on_return;
     return decode_host(MODE_PAIRS, 2, v, idx_bytes, B, k, out, status);

@@ -92,6 +92,11 @@ cudaError_t launch_from_newick_matrix(const char* in, int64_t in_stride, const i
                                       double* m, int32_t* status, void* ws, size_t ws_bytes, cudaStream_t stream);
 // parse_matrix (matrix/base.rs:108-121): column 0 of (count,3) float64 rows as int32, saturating like `as usize`
 cudaError_t launch_matrix_v(const double* m, int64_t count, int* out, cudaStream_t stream);
+// CSV text -> numbers (io/reader.py:16-57): kind 0 integers (idx_bytes 4/8), 1 float64; counts_out (device,
+// 3 int64) = fields found, rows found, error bits (1 malformed field, 2 more than `capacity` fields)
+size_t csv_workspace_bytes(int64_t nbytes);
+cudaError_t launch_csv_parse(const char* text, int64_t nbytes, char delim, int kind, void* out, int idx_bytes,
+                             int64_t capacity, long long* counts_out, void* ws, size_t ws_bytes, cudaStream_t stream);
 // int64 -> int32 index vectors (values that do not fit become -1 and fail check_v downstream)
 cudaError_t launch_narrow_v(const long long* v, int64_t count, int* out, cudaStream_t stream);
 
