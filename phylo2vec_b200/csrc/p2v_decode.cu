@@ -43,8 +43,8 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32)
 decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restrict__ out,
                     int64_t out_stride, int32_t* __restrict__ status, int K) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint8_t s_lut[2048];
-    nth_bit_lut_init(s_lut, threadIdx.x, blockDim.x);
+    __shared__ uint8_t s_lut[WPL > 2 ? 16 : 2048];       // the light form selects bits with ALU instructions
+    if (WPL <= 2) nth_bit_lut_init(s_lut, threadIdx.x, blockDim.x);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -604,10 +604,9 @@ static cudaError_t launch_decode_t(const void* v, int64_t B, int64_t k, void* ou
     const bool warp_per_tree = k <= SMALL_K_MAX || (k <= warp_k_max() && B * 4 > sm_count());
     if (warp_per_tree) {
         const int K = (int)((k + 31) & ~31);
-        const int narr = (MODE == MODE_PAIRS) ? 2 : 3;
         const int wpl = (k <= 1024) ? 1 : (k <= SMALL_K_MAX ? 2 : (k <= 4096 ? 4 : (k <= 8192 ? 8 : 16)));
         const int warps = (wpl <= 2) ? SMALL_WARPS : 1;
-        const size_t smem = (size_t)warps * ((size_t)narr * (K + 32) + 64 * wpl) * sizeof(uint16_t);
+        const size_t smem = (size_t)warps * decode_warp_scratch_u16(K, MODE, wpl) * sizeof(uint16_t);
         auto kern = decode_small_kernel<IdxT, MODE, 1>;
         if (wpl == 2) kern = decode_small_kernel<IdxT, MODE, 2>;
         else if (wpl == 4) kern = decode_small_kernel<IdxT, MODE, 4>;

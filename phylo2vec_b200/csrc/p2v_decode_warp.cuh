@@ -98,8 +98,28 @@ __device__ __forceinline__ void batch_rank_pair_int(const uint16_t* __restrict__
     R_hi = R1; R_lo = R0;
 }
 
-// uint16 entries of per-tree scratch the warp needs: sv, stime, (stbl), then the free-slot mask
+// The integer scan with the two batches' values handed in (the light form reads v from global memory).
+__device__ __forceinline__ void batch_rank_pair_vals(uint32_t x1, uint32_t x0, int b, int k, int lane,
+                                                     uint32_t& R_hi, uint32_t& R_lo) {
+    const int t1 = b * 32 + lane, t0 = t1 - 32;
+    const uint32_t i1 = (t1 < k) ? (x1 <= (uint32_t)t1 ? 0u : x1 - (uint32_t)t1) : BIG;
+    const uint32_t i0 = (t0 >= 0) ? (x0 <= (uint32_t)t0 ? 0u : x0 - (uint32_t)t0) : BIG;
+    uint32_t R1 = i1, R0 = i0;
+#pragma unroll
+    for (int d = 1; d < 32; ++d) {
+        rank_step(R1, i1, d);
+        rank_step(R0, i0, d);
+    }
+    R_hi = R1; R_lo = R0;
+}
+
+// uint16 entries of per-tree scratch the warp needs: sv, stime, (stbl), then the free-slot mask.
+// Mid-size trees (wpl > 2, the "light" form): only stbl and the mask live in shared memory -- v is read
+// from global memory batch by batch, and the (time, value) of every slot goes through the tree's own
+// output rows as a 32-bit scratch word -- so that three times as many trees fit an SM.
 __host__ __device__ inline size_t decode_warp_scratch_u16(int K, int mode, int wpl) {
+    if (wpl > 2) return (size_t)((mode == MODE_PAIRS) ? 0 : 1) * (K + 32) + 64 * wpl + 16 + 98 * 4;   // + a staged batch of rows
+
     return (size_t)((mode == MODE_PAIRS) ? 2 : 3) * (K + 32) + 64 * wpl;
 }
 
@@ -113,19 +133,30 @@ template <typename IdxT, typename OutT, int MODE, int WPL>
 __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int k, int K, OutT* ot,
                                                 uint16_t* base, int lane, const uint8_t* __restrict__ lut) {
     const int KA = K + 32;
-    const int narr = (MODE == MODE_PAIRS) ? 2 : 3;
-    uint16_t* sv = base;            // v[t]                                   (by time)
-    uint16_t* stime = sv + KA;      // element at slot s                      (by slot)
-    uint16_t* stbl = stime + KA;    // last row so far whose label is x       (by label)  [!PAIRS]
+    constexpr bool LIGHT = WPL > 2;                 // k <= 16384: time < 2^14 and v[t] < 2^15 share a 32-bit word
+    const int narr = LIGHT ? ((MODE == MODE_PAIRS) ? 0 : 1) : ((MODE == MODE_PAIRS) ? 2 : 3);
+    uint16_t* sv = base;            // v[t]                                   (by time)            [!LIGHT]
+    uint16_t* stime = sv + KA;      // element at slot s                      (by slot)            [!LIGHT]
+    uint16_t* stbl = LIGHT ? base : stime + KA;    // last row so far whose label is x (by label)  [!PAIRS]
     uint32_t* smask = reinterpret_cast<uint32_t*>(base + narr * KA);  // 32*WPL words of free-slot bits
     const int nb = K >> 5;
+    // light form: slot s parks (time | v[time] << 14) in the first four bytes of its own output row until the
+    // forward sweep reads it back (three batches ahead of the rows it writes)
+    // The words sit packed at the END of the tree's rows: row s is written after word s was read, and it only
+    // reaches words below s (its bytes start at R s, word j at R k - 4 k + 4 j, R >= 8 bytes per row).
+    constexpr int ROWE = (MODE == MODE_PAIRS || MODE == MODE_ANC2) ? 2 : (MODE == MODE_ANCESTRY ? 3 : 4);
+    uint32_t* const park_base = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(ot) + (size_t)ROWE * sizeof(OutT) * k - 4 * (size_t)k);
+    auto park = [&](int s) -> uint32_t* { return park_base + s; };
+    // light form, ancestry rows (24 / 12 bytes, three scalar stores at that stride each): a batch of rows is
+    // staged in shared memory and leaves as whole two-element vectors -- every 32-byte sector is written once
+    OutT* srow = reinterpret_cast<OutT*>((reinterpret_cast<uintptr_t>(smask + 32 * WPL) + 15) & ~(uintptr_t)15);
     // ---- A: load (8 loads in flight per lane), validate (check_v), narrow ----------
     if (MODE != MODE_PAIRS) {                   // "no row yet" for every label, 8 entries per store
         uint4 ones; ones.x = ones.y = ones.z = ones.w = 0xFFFFFFFFu;
         for (int i = lane * 8; i < KA; i += 256) *reinterpret_cast<uint4*>(stbl + i) = ones;
     }
     bool anybad = false;
-    for (int b0 = 0; b0 < nb; b0 += 8) {
+    for (int b0 = 0; b0 < (LIGHT ? 0 : nb); b0 += 8) {          // the light form validates in phase B
         long long xs[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -136,7 +167,7 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
         for (int j = 0; j < 8; ++j) {
             const int i = (b0 + j) * 32 + lane;
             anybad |= (unsigned long long)xs[j] > (unsigned long long)(2 * i);     // also catches negatives
-            if (b0 + j < nb) sv[i] = (uint16_t)xs[j];
+            if (!LIGHT && b0 + j < nb) sv[i] = (uint16_t)xs[j];
         }
     }
     if (__any_sync(FULL, anybad)) {             // rare: find the first offending index
@@ -162,9 +193,29 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
 
     // ---- B: slot assignment, walking time backwards, two batches per rank scan; the scan
     //         of the next pair is independent of the placement of the current one ------------
+    // light form: v of the batches straight from global memory, one pair of batches ahead of the scan that uses
+    // it (the loads have a whole pair of placements to land); check_v on the way -- an invalid entry counts as 0
+    // here and the smallest offending index is reported at the end (the rows of such a tree are garbage).
+    uint32_t xv_hi = 0, xv_lo = 0;                 // v[t] of the lane's element in the scanned batches
+    long long raw_hi = 0, raw_lo = 0;              // the pair of batches loaded ahead
+    int badmin = 0x7FFFFFFF;
+    auto issue_v = [&](int b) {                    // batches b (hi) and b - 1 (lo); b may be < 1 past the end
+        const int t1 = b * 32 + lane, t0 = t1 - 32;
+        raw_hi = (b >= 0 && t1 < k) ? (long long)__ldg(vt + t1) : 0;
+        raw_lo = (t0 >= 0) ? (long long)__ldg(vt + t0) : 0;
+    };
+    auto take_v = [&](int b) {
+        const int t1 = b * 32 + lane, t0 = t1 - 32;
+        const bool bad1 = (unsigned long long)raw_hi > (unsigned long long)(2 * (long long)t1);
+        const bool bad0 = t0 >= 0 && (unsigned long long)raw_lo > (unsigned long long)(2 * (long long)t0);
+        if (bad1 && t1 < k) badmin = min(badmin, t1);
+        if (bad0) badmin = min(badmin, t0);
+        xv_hi = bad1 ? 0u : (uint32_t)raw_hi;
+        xv_lo = bad0 ? 0u : (uint32_t)raw_lo;
+    };
     auto rank_pair = [&](int b, uint32_t& hi, uint32_t& lo) {      // batches b (hi) and b - 1 (lo)
         if (WPL <= 2) batch_rank_pair(sv, b, k, lane, hi, lo);
-        else batch_rank_pair_int(sv, b, k, lane, hi, lo);
+        else { take_v(b); issue_v(b - 2); batch_rank_pair_vals(xv_hi, xv_lo, b, k, lane, hi, lo); }
     };
     // The rank scan of the NEXT pair of batches is resumable (scan_begin / scan_step / scan_end) and
     // its 31 steps are issued between the dependent shuffles of the two placements of the CURRENT
@@ -212,7 +263,7 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
         if (i < 2) { scan_step(17 + 2 * i); scan_step(18 + 2 * i); }
         else scan_step(i + 19);
     };
-    auto place = [&](int b, uint32_t Rin, auto&& fill) {
+    auto place = [&](int b, uint32_t Rin, uint32_t xval, auto&& fill) {
             const int t = b * 32 + lane;
             const uint32_t R = (t < k) ? Rin : (uint32_t)t;
             // rank-select R among the free slots
@@ -270,8 +321,9 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
                 adv = adv && rr >= c;
                 if (adv) { rr -= c; wd = q.w; ++g; }
             }
-            const uint32_t pos = nth_set_bit_lut(wd, rr, lut);    // lut: nth_bit_lut_init, 2 KB per CTA
-            stime[g * 32 + pos] = (uint16_t)t;
+            const uint32_t pos = LIGHT ? nth_set_bit(wd, rr) : nth_set_bit_lut(wd, rr, lut);    // lut: nth_bit_lut_init, 2 KB per CTA
+            if (LIGHT) { if ((int)(g * 32 + pos) < k) *park((int)(g * 32 + pos)) = (uint32_t)t | (xval << 14); }
+            else stime[g * 32 + pos] = (uint16_t)t;
             if (WPL == 1 && P2V_DECODE_REDUX && K >= 512) {     // measured: +1.5 % at n = 512..1024, -3 % at n = 100
                 // The low ranks of a batch (its roots) all land in the first word that still has free
                 // slots, and same-word ATOMS serialise: those lanes are combined with one warp-wide
@@ -300,28 +352,39 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
     };
     int bp = nb - 1;
     uint32_t Rn_hi, Rn_lo;
+    if (LIGHT) issue_v(bp);
     if (nb & 1) {                                  // odd number of batches: the top one goes alone
-        rank_pair(bp, Rn_hi, Rn_lo);
-        place(bp, Rn_hi, fill_none);
+        if (LIGHT) {                               // (its "lower" batch bp - 1 is scanned again as the next pair's upper one)
+            take_v(bp); issue_v(bp - 1);
+            batch_rank_pair_vals(xv_hi, xv_lo, bp, k, lane, Rn_hi, Rn_lo);
+        } else rank_pair(bp, Rn_hi, Rn_lo);
+        place(bp, Rn_hi, xv_hi, fill_none);
         --bp;
     }
     if (bp >= 1) rank_pair(bp, Rn_hi, Rn_lo);
     for (; bp >= 3; bp -= 2) {                     // whole pairs (bp, bp - 1), the next pair's scan inside
         const uint32_t R1 = Rn_hi, R0 = Rn_lo;
+        const uint32_t X1 = xv_hi, X0 = xv_lo;
 #if P2V_DECODE_INTERLEAVE
         scan_begin(bp - 2);
-        place(bp, R1, fill_first);
-        place(bp - 1, R0, fill_second);
+        place(bp, R1, X1, fill_first);
+        place(bp - 1, R0, X0, fill_second);
         scan_end(Rn_hi, Rn_lo);
 #else
         rank_pair(bp - 2, Rn_hi, Rn_lo);
-        place(bp, R1, fill_none);
-        place(bp - 1, R0, fill_none);
+        place(bp, R1, X1, fill_none);
+        place(bp - 1, R0, X0, fill_none);
 #endif
     }
     if (bp >= 1) {                                 // last pair
-        place(bp, Rn_hi, fill_none);
-        place(bp - 1, Rn_lo, fill_none);
+        place(bp, Rn_hi, xv_hi, fill_none);
+        place(bp - 1, Rn_lo, xv_lo, fill_none);
+    }
+
+    if (LIGHT) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) badmin = min(badmin, __shfl_xor_sync(FULL, badmin, o));
+        if (badmin != 0x7FFFFFFF) return badmin;
     }
 
     // ---- D: forward sweep over the slots, 32 rows at a time -------------------------------
@@ -347,21 +410,35 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
         n_t = t; n_lab = lab;
         if (MODE != MODE_PAIRS) n_peers = __match_any_sync(FULL, act ? lab : (0x10000u + lane));
     };
-    uint32_t t1 = (lane < k) ? (uint32_t)stime[lane] : 0u;              // batch 0
-    uint32_t x1 = sv[t1];
-    label_stage(0, t1, x1);
-    t1 = (32 + lane < k) ? (uint32_t)stime[32 + lane] : 0u;             // batch 1 (stime has K + 32 entries)
-    x1 = sv[t1];
-    uint32_t t2 = (64 + lane < k) ? (uint32_t)stime[64 + lane] : 0u;    // batch 2
+    if (LIGHT) __syncwarp();                       // every lane's parked words are written
+    // light form: the parked word of a slot; the L2 copy is the one that is sure to hold the other lanes' stores
+    auto parked = [&](int s) -> uint32_t { return (s < k) ? __ldcg(park(s)) : 0u; };
+    uint32_t t1, x1, t2, w2 = 0;
+    if (LIGHT) {
+        const uint32_t w0 = parked(lane);
+        label_stage(0, w0 & 0x3FFFu, w0 >> 14);
+        const uint32_t w1 = parked(32 + lane);
+        t1 = w1 & 0x3FFFu; x1 = w1 >> 14;
+        w2 = parked(64 + lane);
+        t2 = 0;
+    } else {
+        t1 = (lane < k) ? (uint32_t)stime[lane] : 0u;              // batch 0
+        x1 = sv[t1];
+        label_stage(0, t1, x1);
+        t1 = (32 + lane < k) ? (uint32_t)stime[32 + lane] : 0u;             // batch 1 (stime has K + 32 entries)
+        x1 = sv[t1];
+        t2 = (64 + lane < k) ? (uint32_t)stime[64 + lane] : 0u;    // batch 2
+    }
     for (int b = 0; b < nb; ++b) {
         const int s = b * 32 + lane;
         const bool act = s < k;
         const uint32_t t = n_t, lab = n_lab, peers = n_peers;
         const bool root = n_root;
         // loads of the batches ahead
-        const uint32_t x2 = sv[t2];
         const int s3 = s + 96;
-        const uint32_t t3 = (s3 < k) ? (uint32_t)stime[s3] : 0u;
+        uint32_t x2, t3, w3 = 0;
+        if (LIGHT) { t2 = w2 & 0x3FFFu; x2 = w2 >> 14; w3 = parked(s3); t3 = 0; }
+        else { x2 = sv[t2]; t3 = (s3 < k) ? (uint32_t)stime[s3] : 0u; }
         if (MODE == MODE_PAIRS) {
             if (act) store_pair<OutT>(ot + 2 * (size_t)s, (OutT)lab, (OutT)(t + 1));
             label_stage(b + 1, t1, x1);
@@ -378,13 +455,35 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
             __syncwarp();
             if (act && (peers & lanes_gt(lane)) == 0) stbl[lab] = (uint16_t)s;
             __syncwarp();
-            if (act) {
+            if (LIGHT && MODE == MODE_ANCESTRY) {
+                const uint32_t q = act ? (uint32_t)stbl[t + 1] : NONE16;
+                const uint32_t c2p = (q != NONE16) ? (uint32_t)(k + 1) + q : t + 1;
+                // element parity of the batch's first element against a two-element (16 / 8 byte) boundary
+                OutT* const dst = ot + 96 * (size_t)b;
+                const int a = (int)((reinterpret_cast<uintptr_t>(dst) / sizeof(OutT)) & 1);
+                OutT* const st = srow + a;                 // the staged copy has the alignment of the destination
+                st[3 * lane] = (OutT)c1p; st[3 * lane + 1] = (OutT)c2p; st[3 * lane + 2] = (OutT)(k + 1 + s);
+                __syncwarp();
+                const int lim = 3 * min(32, k - b * 32);   // valid elements of this batch
+                // vectors (f, f + 1) with f + a even: f = 2 q - a
+#pragma unroll
+                for (int rep = 0; rep < 2; ++rep) {
+                    const int qv = lane + 32 * rep;
+                    const int f = 2 * qv - a;
+                    if (qv <= 48) {
+                        if (f >= 0 && f + 1 < lim) store_pair<OutT>(dst + f, st[f], st[f + 1]);
+                        else if (f + 1 >= 0 && f + 1 < lim && f < 0) dst[f + 1] = st[f + 1];     // the odd first element
+                        else if (f >= 0 && f < lim) dst[f] = st[f];                                // the odd last element
+                    }
+                }
+                __syncwarp();
+            } else if (act) {
                 const uint32_t q = stbl[t + 1];
                 const uint32_t c2p = (q != NONE16) ? (uint32_t)(k + 1) + q : t + 1;
                 store_row<OutT, MODE>(ot, s, (OutT)c1p, (OutT)c2p, (OutT)(k + 1 + s));
             }
         }
-        t1 = t2; x1 = x2; t2 = t3;
+        t1 = t2; x1 = x2; t2 = t3; w2 = w3;
     }
     __syncwarp();
     return -1;
