@@ -39,6 +39,7 @@ for n in sizes:
         b1 = min(B, b0 + step)
         V[b0:b1] = (torch.rand((b1 - b0, k), generator=g, device=dev, dtype=torch.float64) * hi).to(torch.int64)
     out = torch.empty((B, k, 3), dtype=torch.int64, device=dev)
+    p2v.to_ancestry_batch(V, out=out, check=False)
     t = timeit(lambda: p2v.to_ancestry_batch(V, out=out, check=False))
     v2 = torch.empty_like(V)
     t2 = timeit(lambda: p2v.from_ancestry_batch(out, out=v2, check=False))

@@ -138,6 +138,38 @@ def test_decode_parity_whole_grid(p2v, n_leaves):
     assert int(st[0]) == k // 2 + 1
 
 
+# Batches of big trees (16384 < k <= 65535, at least 38 of them) take the warp-per-tree kernel with the mask in
+# shared memory and the label table in the workspace (p2v_decode_warp_big.cuh); beyond 65535 the merge kernel.
+@pytest.mark.parametrize("n_leaves", [16386, 16400, 20000, 33000, 65535, 65536, 65537])
+def test_decode_parity_big_batches(p2v, n_leaves):
+    k = n_leaves - 1
+    B = 40
+    V = sample_vectors(B, n_leaves, seed=n_leaves)
+    V[1] = sample_vectors(1, n_leaves, seed=1, ordered=True)[0]
+    adv = list(adversarial_vectors(n_leaves).values())
+    V[2:2 + len(adv)] = np.stack(adv)
+    for dtype in (torch.int64, torch.int32):
+        Vd = dev(V, dtype)
+        for name, fn in (("to_ancestry", p2v.to_ancestry_batch), ("to_pairs", p2v.to_pairs_batch),
+                         ("to_edges", p2v.to_edges_batch)):
+            if dtype == torch.int32 and name == "to_edges":
+                continue
+            ref, st = O.batch(name, V, k)
+            assert not st.any()
+            got = fn(Vd)
+            assert np.array_equal(got.cpu().numpy().astype(np.int64), ref), (name, n_leaves, dtype)
+    bad = V.copy()
+    bad[7, k - 3] = 2 * (k - 3) + 1
+    bad[9, 5] = 11
+    bad[9, 100] = 999
+    st = torch.zeros(B, dtype=torch.int32, device="cuda")
+    p2v.to_ancestry_batch(dev(bad, torch.int64), status=st, check=False)
+    want = np.zeros(B, dtype=np.int32)
+    want[7] = k - 3 + 1
+    want[9] = 5 + 1
+    assert np.array_equal(st.cpu().numpy(), want)
+
+
 # Batches of mid-size trees stay on the warp-per-tree kernel (4 / 8 / 16 mask words per lane,
 # integer rank scan); a handful of such trees goes to the merge kernel (test_decode_parity above).
 MID_SIZES = [2017, 2049, 3000, 4096, 4097, 4098, 5000, 8192, 8193, 8194, 12289, 16384, 16385, 16386]
