@@ -804,8 +804,8 @@ def run_sweep(args):
     for n in sizes:
         k = n - 1
         rec = {"n_leaves": n}
-        # ---- decode / encode: B*k ~ 2.5e8 elements, at most 4M trees -------------------------
-        B = int(min(4_000_000, max(8, 250_000_000 // k)))
+        # ---- decode / encode: B*k ~ 1e9 elements (BASELINE.json configs[4]), at most 10M trees ------
+        B = int(min(10_000_000, max(8, 1_000_000_000 // k)))
         V = trees(B, n)
         need = lib.p2v_decode_workspace_bytes(B, k)
         ws = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
@@ -830,9 +830,9 @@ def run_sweep(args):
         rec["to_ancestry_cpu"] = {"sample": Bc, "trees_per_s": Bc / tc, "cores": nthreads,
                                   "matches_gpu": bool(np.array_equal(ref, anc[:Bc].cpu().numpy()))}
         del anc, back, ws, wse
-        # ---- distances: B * n^2 * 8 <= 8 GB -----------------------------------------------------
-        Bd = int(max(1, min(B, (8 << 30) // (n * n * 8))))
-        if n * n * 8 > (40 << 30):
+        # ---- distances: B * n^2 * 8 <= 64 GB per GPU (one tree at n = 100 000: 80 GB) ----------------
+        Bd = int(max(1, min(B, (64 << 30) // (n * n * 8))))
+        if n * n * 8 > (100 << 30):
             Bd = 0
         if Bd:
             Vd = V[:Bd].contiguous()
@@ -876,7 +876,7 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=0)
     ap.add_argument("--c3-trees", type=int, default=C3_TREES, help="trees of the C3 leg (whole job)")
     ap.add_argument("--sweep", action="store_true", help="per-size sweep instead of the bench line")
-    ap.add_argument("--sweep-out", default=os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_sweep.json"))
+    ap.add_argument("--sweep-out", default=os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_sweep.json"))
     ap.add_argument("--sweep-quick", action="store_true")
     args = ap.parse_args()
     if args.sweep:
