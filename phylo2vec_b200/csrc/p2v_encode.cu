@@ -16,14 +16,17 @@
 //    as the rows defining its internal children have fired.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "p2v_common.cuh"
 #include "p2v_internal.h"
+#include "p2v_encode_light.cuh"
 
 namespace p2v {
 
 constexpr int ENC_SMALL_WARPS = 4;
-constexpr int ENC_WARP_K_MAX = 4096;      // warp-per-tree encode for batches of trees up to here (above, two
-                                          // trees per SM are too few: measured 0.6x at n = 8192)
+constexpr int ENC_WARP_K_MAX = 4096;      // round-1 warp kernel with staged rows: only reachable with
+                                          // P2V_ENC_LIGHT_FROM above it (the light kernel takes 1024 < k <= 65535)
 constexpr int ENC_LARGE_THREADS = 256;
 constexpr int ENC_LARGE_WARPS = ENC_LARGE_THREADS / 32;
 
@@ -511,14 +514,70 @@ static int enc_large_grid(int64_t B) {
     return (int)(B < cap ? B : cap);
 }
 
+// ---- the light warp kernel (p2v_encode_light.cuh): shape of a launch, shared by the workspace query ----
+struct LightPlan { int warps, per_sm, K; bool gt; size_t smem, ws_words; };
+static int enc_light_from() {               // smallest k that takes the light kernel (P2V_ENC_LIGHT_FROM to experiment)
+    static const int v = [] { const char* e = getenv("P2V_ENC_LIGHT_FROM"); return e ? atoi(e) : 1025; }();
+    return v;
+}
+static int enc_env(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+static int enc_light_tsmem() { static const int v = enc_env("P2V_ENC_TSMEM", ENC_LIGHT_T_SMEM_K_MAX); return v; }
+static int enc_light_gt_per_sm() { static const int v = enc_env("P2V_ENC_GT_PERSM", 16); return v; }
+static bool enc_light(int64_t k) { return k >= enc_light_from() && k <= ENC_LIGHT_K_MAX; }
+static LightPlan enc_light_plan(int64_t k) {
+    LightPlan p;
+    p.K = (int)((k + 31) & ~31);
+    p.gt = k > enc_light_tsmem();
+    const size_t per_warp = enc_light_smem_words(p.K, !p.gt) * sizeof(uint32_t);
+    p.warps = per_warp <= 6144 ? 4 : (per_warp <= 12288 ? 2 : 1);
+    p.smem = per_warp * p.warps;
+    int per_sm = (int)((size_t)(227 * 1024) / (p.smem + 1024));
+    if (per_sm > 32) per_sm = 32;
+    if (per_sm * p.warps > 48) per_sm = 48 / p.warps;
+    if (p.gt && per_sm > enc_light_gt_per_sm()) per_sm = enc_light_gt_per_sm();       // tables in L2: more trees in flight only evict one another
+    if (per_sm < 1) per_sm = 1;
+    p.per_sm = per_sm;
+    p.ws_words = enc_light_ws_words(p.K, !p.gt);
+    return p;
+}
+
 size_t encode_workspace_bytes(int64_t B, int64_t k) {
-    if (k <= ENC_SMALL_K_MAX || B <= 0) return 0;
+    if (B <= 0) return 0;
+    if (enc_light(k)) {
+        const LightPlan p = enc_light_plan(k);
+        const int64_t want = (B + p.warps - 1) / p.warps, cap = (int64_t)sm_count() * p.per_sm;
+        return (size_t)(want < cap ? want : cap) * p.warps * p.ws_words * sizeof(uint32_t);
+    }
+    if (k <= ENC_SMALL_K_MAX) return 0;
     return (size_t)enc_large_grid(B) * enc_large_stride(k) * sizeof(uint32_t);
+}
+
+template <typename IdxT, int MODE, bool GT>
+static cudaError_t launch_encode_light(const void* in, int64_t B, int64_t k, void* v, int32_t* status, void* ws,
+                                       size_t ws_bytes, cudaStream_t stream) {
+    const LightPlan p = enc_light_plan(k);
+    auto kern = encode_light_kernel<IdxT, MODE, GT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, p.warps * 32, p.smem);
+    if (e != cudaSuccess) return e;
+    const int per_sm = occ < 1 ? 1 : (occ < p.per_sm ? occ : p.per_sm);
+    const int64_t want = (B + p.warps - 1) / p.warps, cap = (int64_t)sm_count() * per_sm;
+    const int grid = (int)(want < cap ? want : cap);
+    if (!ws || ws_bytes < (size_t)grid * p.warps * p.ws_words * sizeof(uint32_t)) return cudaErrorInvalidValue;
+    kern<<<grid, p.warps * 32, p.smem, stream>>>((const IdxT*)in, B, (int)k, (IdxT*)v, status, p.K, (uint32_t*)ws,
+                                                 p.ws_words);
+    count_launch();
+    return cudaGetLastError();
 }
 
 template <typename IdxT, int MODE>
 static cudaError_t launch_encode_t(const void* in, int64_t B, int64_t k, void* v, int32_t* status,
                                    void* ws, size_t ws_bytes, cudaStream_t stream) {
+    if (enc_light(k))
+        return k > enc_light_tsmem() ? launch_encode_light<IdxT, MODE, true>(in, B, k, v, status, ws, ws_bytes, stream)
+                                          : launch_encode_light<IdxT, MODE, false>(in, B, k, v, status, ws, ws_bytes, stream);
     // batches of mid-size trees stay on the warp-per-tree kernel (a fraction of the CTA kernel's work)
     if (k <= ENC_SMALL_K_MAX || (k <= ENC_WARP_K_MAX && B * 4 > sm_count())) {
         const int K = (int)((k + 31) & ~31);

@@ -226,6 +226,35 @@ def test_encode_parity_mid_batches(p2v, n_leaves, dtype):
     assert status[5].item() == -2 and int(status.count_nonzero()) == 1
 
 
+@pytest.mark.parametrize("n_leaves", [16385, 16386, 20000, 32768, 65535, 65536])
+def test_encode_parity_big_batches(p2v, n_leaves):
+    """Batches of big trees on the warp-per-tree encoder with its label table in the workspace."""
+    B = 150 if n_leaves <= 20000 else 40                  # more trees than SMs / 4 for the smaller sizes
+    V = sample_vectors(B, n_leaves, seed=17 * n_leaves)
+    adv = list(adversarial_vectors(n_leaves).values())
+    V[:len(adv)] = np.stack(adv)
+    k = n_leaves - 1
+    rng = np.random.default_rng(n_leaves)
+    perm = torch.from_numpy(rng.permutation(k)).cuda()
+    for dtype in (torch.int64, torch.int32):
+        Vd = dev(V, dtype)
+        anc = p2v.to_ancestry_batch(Vd)                    # checked against the oracle by the decode tests
+        assert torch.equal(p2v.from_ancestry_batch(anc), Vd), (n_leaves, dtype)
+        assert torch.equal(p2v.from_pairs_batch(p2v.to_pairs_batch(Vd)), Vd), (n_leaves, dtype)
+        edges = p2v.to_edges_batch(Vd)
+        assert torch.equal(p2v.from_edges_batch(edges), Vd), (n_leaves, dtype)
+        shuffled = edges.reshape(B, k, 2, 2)[:, perm].reshape(B, 2 * k, 2).contiguous()
+        assert torch.equal(p2v.from_edges_batch(shuffled), Vd), (n_leaves, dtype)
+    ref, st = O.batch("from_ancestry", anc[:3].cpu().numpy().astype(np.int64), k)
+    assert not st.any() and np.array_equal(ref, V[:3])
+    bad = anc.clone()
+    bad[2, 7, 2] = 1                                      # a leaf label as parent
+    bad[4, 9] = bad[4, 8]                                 # one parent label, two rows
+    status = torch.zeros(B, dtype=torch.int32, device="cuda")
+    p2v.from_ancestry_batch(bad, status=status, check=False)
+    assert status[2].item() == -2 and status[4].item() == -2 and int(status.count_nonzero()) == 2
+
+
 @pytest.mark.parametrize("n_leaves", SIZES)
 @pytest.mark.parametrize("dtype", [torch.int64, torch.int32])
 def test_encode_parity_and_round_trip(p2v, n_leaves, dtype):
