@@ -632,8 +632,10 @@ static cudaError_t launch_decode_t(const void* v, int64_t B, int64_t k, void* ou
     const bool warp_per_tree = k <= SMALL_K_MAX || (k <= warp_k_max() && B * 4 > sm_count());
     if (warp_per_tree) {
         const int K = (int)((k + 31) & ~31);
-        const int wpl = (k <= 1024) ? 1 : (k <= SMALL_K_MAX ? 2 : (k <= 4096 ? 4 : (k <= 8192 ? 8 : 16)));
-        const int warps = (wpl <= 2) ? SMALL_WARPS : 1;
+        static const int light_from = [] { const char* e = getenv("P2V_DECODE_LIGHT_FROM"); return e ? atoi(e) : SMALL_K_MAX + 1; }();
+        static const int light_warps = [] { const char* e = getenv("P2V_DECODE_LIGHT_WARPS"); return e ? atoi(e) : 2; }();
+        const int wpl = (k <= 1024) ? 1 : (k < light_from ? 2 : (k <= 4096 ? 4 : (k <= 8192 ? 8 : 16)));
+        const int warps = (wpl <= 2) ? SMALL_WARPS : (k <= 4096 ? light_warps : 1);
         const size_t smem = (size_t)warps * decode_warp_scratch_u16(K, MODE, wpl) * sizeof(uint16_t);
         auto kern = decode_small_kernel<IdxT, MODE, 1>;
         if (wpl == 2) kern = decode_small_kernel<IdxT, MODE, 2>;

@@ -113,6 +113,26 @@ __device__ __forceinline__ void batch_rank_pair_vals(uint32_t x1, uint32_t x0, i
     R_hi = R1; R_lo = R0;
 }
 
+// The same for k <= 16384 with ONE shuffle per step for both batches: the two 15-bit values share a word, and
+// field f of ((R | 0x8000 in both fields) - y) keeps its bit 15 iff y_f <= R_f; no borrow crosses the fields
+// (0x8000 + R_f - y_f >= 0) and no carry does either (R_f stays below 2^15 + 64).  SHFL.DOWN past lane 31
+// hands back the lane's own value, which always counts: those `lane` steps come last and are taken off.
+__device__ __forceinline__ void batch_rank_pair_vals15(uint32_t x1, uint32_t x0, int b, int k, int lane,
+                                                       uint32_t& R_hi, uint32_t& R_lo) {
+    const int t1 = b * 32 + lane, t0 = t1 - 32;
+    const uint32_t i1 = (t1 < k) ? (x1 <= (uint32_t)t1 ? 0u : x1 - (uint32_t)t1) : 0x7FFFu;
+    const uint32_t i0 = (t0 >= 0) ? (x0 <= (uint32_t)t0 ? 0u : x0 - (uint32_t)t0) : 0x7FFFu;
+    const uint32_t ins = i0 | (i1 << 16);
+    uint32_t R = ins;
+#pragma unroll
+    for (int d = 1; d < 32; ++d) {
+        const uint32_t y = __shfl_down_sync(FULL, ins, d);
+        R += (((R | 0x80008000u) - y) >> 15) & 0x00010001u;
+    }
+    R_lo = (R & 0xFFFFu) - (uint32_t)lane;                 // garbage for inactive lanes
+    R_hi = (R >> 16) - (uint32_t)lane;
+}
+
 // uint16 entries of per-tree scratch the warp needs: sv, stime, (stbl), then the free-slot mask.
 // Mid-size trees (wpl > 2, the "light" form): only stbl and the mask live in shared memory -- v is read
 // from global memory batch by batch, and the (time, value) of every slot goes through the tree's own
@@ -149,7 +169,7 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
     auto park = [&](int s) -> uint32_t* { return park_base + s; };
     // light form, ancestry rows (24 / 12 bytes, three scalar stores at that stride each): a batch of rows is
     // staged in shared memory and leaves as whole two-element vectors -- every 32-byte sector is written once
-    OutT* srow = reinterpret_cast<OutT*>((reinterpret_cast<uintptr_t>(smask + 32 * WPL) + 15) & ~(uintptr_t)15);
+    OutT* srow = reinterpret_cast<OutT*>(smask + 32 * WPL);       // 16-byte aligned: every piece before it is
     // ---- A: load (8 loads in flight per lane), validate (check_v), narrow ----------
     if (MODE != MODE_PAIRS) {                   // "no row yet" for every label, 8 entries per store
         uint4 ones; ones.x = ones.y = ones.z = ones.w = 0xFFFFFFFFu;
@@ -215,7 +235,7 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
     };
     auto rank_pair = [&](int b, uint32_t& hi, uint32_t& lo) {      // batches b (hi) and b - 1 (lo)
         if (WPL <= 2) batch_rank_pair(sv, b, k, lane, hi, lo);
-        else { take_v(b); issue_v(b - 2); batch_rank_pair_vals(xv_hi, xv_lo, b, k, lane, hi, lo); }
+        else { take_v(b); issue_v(b - 2); batch_rank_pair_vals15(xv_hi, xv_lo, b, k, lane, hi, lo); }
     };
     // The rank scan of the NEXT pair of batches is resumable (scan_begin / scan_step / scan_end) and
     // its 31 steps are issued between the dependent shuffles of the two placements of the CURRENT
@@ -356,7 +376,7 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
     if (nb & 1) {                                  // odd number of batches: the top one goes alone
         if (LIGHT) {                               // (its "lower" batch bp - 1 is scanned again as the next pair's upper one)
             take_v(bp); issue_v(bp - 1);
-            batch_rank_pair_vals(xv_hi, xv_lo, bp, k, lane, Rn_hi, Rn_lo);
+            batch_rank_pair_vals15(xv_hi, xv_lo, bp, k, lane, Rn_hi, Rn_lo);
         } else rank_pair(bp, Rn_hi, Rn_lo);
         place(bp, Rn_hi, xv_hi, fill_none);
         --bp;
@@ -413,13 +433,13 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
     if (LIGHT) __syncwarp();                       // every lane's parked words are written
     // light form: the parked word of a slot; the L2 copy is the one that is sure to hold the other lanes' stores
     auto parked = [&](int s) -> uint32_t { return (s < k) ? __ldcg(park(s)) : 0u; };
-    uint32_t t1, x1, t2, w2 = 0;
+    uint32_t t1, x1, t2, w2 = 0, w3 = 0, w4 = 0;   // parked words of the batches b + 2 .. b + 4 (they come from DRAM)
     if (LIGHT) {
         const uint32_t w0 = parked(lane);
         label_stage(0, w0 & 0x3FFFu, w0 >> 14);
         const uint32_t w1 = parked(32 + lane);
         t1 = w1 & 0x3FFFu; x1 = w1 >> 14;
-        w2 = parked(64 + lane);
+        w2 = parked(64 + lane); w3 = parked(96 + lane); w4 = parked(128 + lane);
         t2 = 0;
     } else {
         t1 = (lane < k) ? (uint32_t)stime[lane] : 0u;              // batch 0
@@ -436,8 +456,8 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
         const bool root = n_root;
         // loads of the batches ahead
         const int s3 = s + 96;
-        uint32_t x2, t3, w3 = 0;
-        if (LIGHT) { t2 = w2 & 0x3FFFu; x2 = w2 >> 14; w3 = parked(s3); t3 = 0; }
+        uint32_t x2, t3, w5 = 0;
+        if (LIGHT) { t2 = w2 & 0x3FFFu; x2 = w2 >> 14; w5 = parked(s + 160); t3 = 0; }
         else { x2 = sv[t2]; t3 = (s3 < k) ? (uint32_t)stime[s3] : 0u; }
         if (MODE == MODE_PAIRS) {
             if (act) store_pair<OutT>(ot + 2 * (size_t)s, (OutT)lab, (OutT)(t + 1));
@@ -483,7 +503,7 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
                 store_row<OutT, MODE>(ot, s, (OutT)c1p, (OutT)c2p, (OutT)(k + 1 + s));
             }
         }
-        t1 = t2; x1 = x2; t2 = t3; w2 = w3;
+        t1 = t2; x1 = x2; t2 = t3; w2 = w3; w3 = w4; w4 = w5;
     }
     __syncwarp();
     return -1;
