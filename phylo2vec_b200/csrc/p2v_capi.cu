@@ -1,6 +1,8 @@
 // C ABI of the library (declared in include/phylo2vec_b200.h).
 #include <emmintrin.h>
 #include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <condition_variable>
@@ -85,6 +87,11 @@ static int encode_entry(int mode, const void* in, int idx_bytes, int64_t B, int6
 // the H2D copy, the kernels and the D2H copy of neighbouring chunks overlap.  Streams and device
 // staging buffers are cached per host thread and grow on demand; p2v_host_release() frees them.
 constexpr int HOST_STREAMS = 3;
+// The thread-local caches below free their memory when a worker thread ends.  The main thread's destructors
+// only run while the process exits, when the CUDA driver may already be gone: nothing is called then (the
+// Python layer releases the main thread's cache from an atexit handler, which runs earlier; the OS has the rest).
+static bool at_process_exit() { return (long)syscall(SYS_gettid) == (long)getpid(); }
+
 struct HostCtx {
     int dev = -1;
     cudaStream_t st[HOST_STREAMS] = {};
@@ -107,8 +114,8 @@ struct HostCtx {
         dev = -1;
     }
     size_t bytes() const { return HOST_STREAMS * (cap_in + cap_out + cap_ws + cap_stat); }
-    // thread exit: give the memory back (errors such as cudaErrorCudartUnloading at process exit are ignored)
-    ~HostCtx() { release(); cudaGetLastError(); }
+    // thread exit: give the memory back (see at_process_exit)
+    ~HostCtx() { if (!at_process_exit()) { release(); cudaGetLastError(); } }
 };
 static thread_local HostCtx g_host;
 // Staging the *_host entry points may keep between calls, per host thread (device + pinned bytes).
@@ -164,7 +171,7 @@ struct StageCtx {
     cudaEvent_t ev[HOST_STREAMS] = {};
     size_t cap_in = 0, cap_out = 0, cap_stat = 0;
     size_t bytes() const { return HOST_STREAMS * (cap_in + cap_out + cap_stat); }
-    ~StageCtx() { release(); cudaGetLastError(); }
+    ~StageCtx() { if (!at_process_exit()) { release(); cudaGetLastError(); } }
     void release() {
         for (int i = 0; i < HOST_STREAMS; ++i) {
             if (hin[i]) cudaFreeHost(hin[i]);
@@ -390,7 +397,7 @@ struct CompactCtx {
     cudaEvent_t ev[HOST_STREAMS] = {};
     size_t cap_stage = 0, cap_v32 = 0, cap_hstat = 0, cap_vstage = 0;
     size_t bytes() const { return HOST_STREAMS * (cap_stage + cap_v32 + cap_hstat + cap_vstage); }
-    ~CompactCtx() { release(); cudaGetLastError(); }
+    ~CompactCtx() { if (!at_process_exit()) { release(); cudaGetLastError(); } }
     void release() {
         for (int i = 0; i < HOST_STREAMS; ++i) {
             if (stage[i]) cudaFreeHost(stage[i]);

@@ -1213,13 +1213,15 @@ __host__ __device__ inline SmallLayout small_layout(int k, bool topo) {
 
 // TILED: rows by tiles of 32 DFS positions with per-lane label-order columns in registers (pays off
 // from n ~ 150); otherwise one sparse-table query per element and a DFS-ordered row buffer.
-template <bool TOPO, bool VCV, bool VEC2, bool TILED>
+template <bool TOPO, bool VCV, bool VEC2, bool TILED, bool STAGED>
 __global__ void __launch_bounds__(CS_THREADS, 8)
 coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, int bl_stride, int64_t bl_tree_stride,
                   int64_t B, int k, int unrooted, int64_t row_begin, int64_t row_end, double* __restrict__ out,
-                  int32_t* __restrict__ status) {
+                  int32_t* __restrict__ status, int use_tma) {
+    constexpr bool stage_lengths = STAGED && !TOPO;
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ int s_bad[CS_TREES];
+    __shared__ __align__(8) uint64_t s_bar[2];    // [1]: mbarrier of the staged branch lengths
     __shared__ uint8_t s_lut[2048];
     nth_bit_lut_init(s_lut, threadIdx.x, CS_THREADS);
     const SmallLayout L = small_layout(k, TOPO);
@@ -1247,7 +1249,46 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
     const int stn = (n + 1 + 3) & ~3;             // entries per sparse-table level
 
     const int tpp = L.tpp;
+    // ---- staged branch lengths (TMA): while the rows of a tree are being written, the lengths of the NEXT tree
+    //      (its matrix rows, 24k bytes) arrive by one bulk copy (cp.async.bulk, completion on an mbarrier).
+    //      They land in the jumping buffers ja .. cnt, which are dead during the row phase (40k + 24 bytes >=
+    //      24k + 32), so staging costs no shared memory.  A copy takes the whole 16-byte pieces that cover the
+    //      source range; where those would reach outside the caller's array (an unaligned first or last
+    //      tree) the threads copy the range themselves.  Measured (profiles/r02_coph_small_tma.md): staging the
+    //      v rows the same way (4k bytes per tree, into the tree's ancestry slot) made the kernel 1 - 5 %
+    //      slower, so v is read straight from global memory; the staged lengths cost 2 - 4 % (the other CTAs
+    //      of the SM already hide these loads) and are a template flag, off for n <= 128.
+    const int bl_first = (bl_stride == 3) ? 1 : 0;        // matrix rows [v, bl1, bl2]: a tree's block starts one double earlier
+    const double* const bl_lo = TOPO ? nullptr : bl - bl_first;
+    double* const sbl_stage = reinterpret_cast<double*>(dyn + L.ja);
+    struct Piece { const char* a0; uint32_t bytes, lead; bool tma; };
+    auto piece = [use_tma](const char* g, size_t len, const char* lo, const char* hi) {
+        Piece q;
+        q.a0 = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(g) & ~(uintptr_t)15);
+        const char* e = reinterpret_cast<const char*>((reinterpret_cast<uintptr_t>(g) + len + 15) & ~(uintptr_t)15);
+        q.bytes = (uint32_t)(e - q.a0); q.lead = (uint32_t)(g - q.a0);
+        q.tma = use_tma && q.a0 >= lo && e <= hi;
+        return q;
+    };
+    auto bl_piece = [&](int64_t t) {
+        return piece(reinterpret_cast<const char*>(bl_lo + t * bl_tree_stride), (size_t)bl_tree_stride * 8,
+                     reinterpret_cast<const char*>(bl_lo), reinterpret_cast<const char*>(bl_lo + B * bl_tree_stride));
+    };
+    // every thread calls this at a point where the destination is dead
+    auto stage_bl = [&](int64_t t) {
+        if (TOPO || !stage_lengths || t >= B) return;
+        const Piece q = bl_piece(t);
+        if (q.tma) { if (tid == 0) { fence_proxy_async_smem(); bulk_load(sbl_stage, q.a0, q.bytes, &s_bar[1]); } }
+        else for (int i = tid; i < (int)bl_tree_stride; i += CS_THREADS) sbl_stage[q.lead / 8 + i] = __ldg(bl_lo + t * bl_tree_stride + i);
+    };
+    uint32_t par_bl = 0;
+    if (stage_lengths) {
+        if (tid == 0) { mbar_init(&s_bar[1], 1); fence_proxy_async_smem(); }
+        __syncthreads();
+        stage_bl((int64_t)blockIdx.x * tpp);
+    }
     for (int64_t base = (int64_t)blockIdx.x * tpp; base < B; base += (int64_t)gridDim.x * tpp) {
+        const int64_t base_next = base + (int64_t)gridDim.x * tpp;
         __syncthreads();                          // the previous pass's readers are done
         // ---- 1. decode: every warp its own tree ---------------------------------------------
         if (warp < tpp && base + warp < B) {
@@ -1259,29 +1300,53 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
         }
         __syncthreads();
         for (int sub = 0; sub < tpp && base + sub < B; ++sub) {
-        if (s_bad[sub] >= 0) continue;            // uniform
         const int64_t tree = base + sub;
+        const int64_t tree_next = (sub + 1 < tpp && tree + 1 < B) ? tree + 1 : base_next;
+        Piece qb; qb.lead = 0; qb.tma = false;
+        if (!TOPO && stage_lengths) {
+            qb = bl_piece(tree);
+            if (qb.tma) { mbar_wait(&s_bar[1], par_bl); par_bl ^= 1u; }
+        }
+        if (s_bad[sub] >= 0) {                    // uniform: skip the tree, keep the staging going
+            if (!TOPO && stage_lengths) { __syncthreads(); stage_bl(tree_next); __syncthreads(); }
+            continue;
+        }
         const int* anc = reinterpret_cast<const int*>(dyn + L.anc + sub * L.anc_stride);
         // ---- 2. parents, edge weights, first / last child pointers -----------------------------
-        const double* blt = bl ? bl + tree * bl_tree_stride : nullptr;
+        if (!TOPO && stage_lengths) {             // the staged lengths first: they sit where ja .. cnt are about to go
+            const double* blt = sbl_stage + qb.lead / 8 + bl_first;
+            for (int r = tid; r < k; r += CS_THREADS) {
+                const int c1 = anc[3 * r], c2 = anc[3 * r + 1];
+                double b1 = blt[(size_t)r * bl_stride], b2 = blt[(size_t)r * bl_stride + 1];
+                if (unrooted) {                   // graph.rs:46-50: the root edge to node 2k-1 has length 0
+                    if (c1 == 2 * k - 1) b1 = 0.0;
+                    if (c2 == 2 * k - 1) b2 = 0.0;
+                }
+                jh[c1] = b1; jh[c2] = b2; jl[c1] = 0.0; jl[c2] = 0.0;
+            }
+            if (tid == 0) { jh[root] = 0.0; jl[root] = 0.0; }
+            __syncthreads();
+        }
         for (int c = tid; c <= k; c += CS_THREADS) { dl[c] = (uint16_t)c; dr[c] = (uint16_t)c; }
+        const bool direct_bl = !TOPO && !stage_lengths;                 // lengths straight from global memory
+        const double* blg = direct_bl ? bl + tree * bl_tree_stride : nullptr;
         for (int r = tid; r < k; r += CS_THREADS) {
             const int c1 = anc[3 * r], c2 = anc[3 * r + 1], p = k + 1 + r;
             double b1 = 1.0, b2 = 1.0;
-            if (!TOPO) { b1 = blt[(size_t)r * bl_stride]; b2 = blt[(size_t)r * bl_stride + 1]; }
+            if (direct_bl) { b1 = blg[(size_t)r * bl_stride]; b2 = blg[(size_t)r * bl_stride + 1]; }
             int w1 = 1, w2 = 1;
-            if (unrooted) {                       // graph.rs:46-50: the root edge to node 2k-1 has length 0
+            if (unrooted) {
                 if (c1 == 2 * k - 1) { w1 = 0; b1 = 0.0; }
                 if (c2 == 2 * k - 1) { w2 = 0; b2 = 0.0; }
             }
             ja[c1] = (uint16_t)p; ja[c2] = (uint16_t)p;
             jd[c1] = (uint16_t)w1; jd[c2] = (uint16_t)w2;
             dl[p] = (uint16_t)c1; dr[p] = (uint16_t)c2;
-            if (!TOPO) { jh[c1] = b1; jh[c2] = b2; jl[c1] = 0.0; jl[c2] = 0.0; }
+            if (direct_bl) { jh[c1] = b1; jh[c2] = b2; jl[c1] = 0.0; jl[c2] = 0.0; }
         }
         if (tid == 0) {
             ja[root] = (uint16_t)CS_NONE; jd[root] = 0;
-            if (!TOPO) { jh[root] = 0.0; jl[root] = 0.0; }
+            if (!TOPO && !stage_lengths) { jh[root] = 0.0; jl[root] = 0.0; }
         }
         __syncthreads();
         // ---- pointer jumping (buffers 0 / 1): root-path sums upwards, leftmost / rightmost leaf
@@ -1359,6 +1424,7 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
             if (tid == 0) { st[0] = 0xFFFFFFFFu; st[n] = 0xFFFFFFFFu; }
         }
         __syncthreads();
+        stage_bl(tree_next);                      // the jumping buffers are dead from here on: the next lengths land in them
         for (int lev = 1; lev < L.levels; ++lev) {
             const int half = 1 << (lev - 1);
             for (int r = 1 + tid; r + (1 << lev) <= n; r += CS_THREADS)
@@ -1855,10 +1921,17 @@ static cudaError_t launch_cophenetic_small(const void* v_or_matrix, int idx_byte
     // measured: fp64 distance rows are bound by the double-double math either way, so only the
     // integer and vcv rows take the tiled path
     const bool tiled = (n > 160) && (topo || what != 0);
+    static const int use_tma = [] { const char* e = getenv("P2V_COPH_SMALL_TMA"); return e ? atoi(e) : 1; }();
+    // Branch lengths staged by TMA (see the kernel): measured against direct loads (profiles/r02_coph_small_tma.md)
+    // it costs 4 % at n = 100, 2 % at n = 128..320 and more below -- the other CTAs of the SM already hide
+    // those loads.  It is on for the one-tree-per-pass sizes, where it costs least; P2V_COPH_SMALL_STAGE_BL=0/1 forces it.
+    static const int stage_env = [] { const char* e = getenv("P2V_COPH_SMALL_STAGE_BL"); return e ? atoi(e) : -1; }();
+    const int stage_lengths = stage_env >= 0 ? stage_env : (n > 128);
     cudaError_t e = cudaSuccess;
 #define P2V_SMALL(T_, W_, V_)                                                                          \
     do {                                                                                               \
-        auto kern = tiled ? coph_small_kernel<T_, W_, V_, true> : coph_small_kernel<T_, W_, V_, false>; \
+        auto kern = tiled ? coph_small_kernel<T_, W_, V_, true, false> : coph_small_kernel<T_, W_, V_, false, false>; \
+        if (!T_ && stage_lengths) kern = tiled ? coph_small_kernel<T_, W_, V_, true, !T_> : coph_small_kernel<T_, W_, V_, false, !T_>; \
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
         if (e != cudaSuccess) return e;                                                                \
         int per_sm = 0;                                                                                \
@@ -1867,7 +1940,7 @@ static cudaError_t launch_cophenetic_small(const void* v_or_matrix, int idx_byte
         if (per_sm < 1) per_sm = 1;                                                                    \
         const int64_t cap = (int64_t)sm_count() * per_sm, want = (B + tpp - 1) / tpp;                  \
         kern<<<(int)(want < cap ? want : cap), CS_THREADS, smem, stream>>>(vin, bl, bl_stride, bl_tree_stride, B, (int)k, \
-                                                                     unrooted, row_begin, row_end, out, st);       \
+                                                                     unrooted, row_begin, row_end, out, st, use_tma); \
     } while (0)
 #define P2V_SMALL2(T_, W_) do { if (vec2) P2V_SMALL(T_, W_, true); else P2V_SMALL(T_, W_, false); } while (0)
     if (topo) { if (what) P2V_SMALL2(true, true); else P2V_SMALL2(true, false); }

@@ -564,7 +564,7 @@ static int large_teams(int64_t B) {
 
 constexpr int BIG_WARP_K_MAX = 65535;       // slots and labels fit 16 bits
 constexpr int BIG_WARP_CTAS_PER_SM = 16;    // resident trees per SM the workspace is sized for
-static bool big_warp_batch(int64_t B, int64_t k) { return k > WARP_K_MAX && k <= BIG_WARP_K_MAX && B * 4 > sm_count(); }
+static bool big_warp_batch(int64_t B, int64_t k) { return k > warp_k_max() && k <= BIG_WARP_K_MAX && B * 4 > sm_count(); }
 static size_t big_warp_table_stride(int64_t k) { return (((size_t)k + 31) & ~(size_t)31) + 32; }   // uint16 entries
 static int64_t big_warp_ctas(int64_t B) {
     const int64_t cap = (int64_t)sm_count() * BIG_WARP_CTAS_PER_SM;

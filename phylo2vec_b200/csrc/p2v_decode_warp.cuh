@@ -149,9 +149,11 @@ __host__ __device__ inline size_t decode_warp_scratch_u16(int K, int mode, int w
 // WPL = free-mask words per lane: 1 for k <= 1024, 2 for k <= 2016 (the half2 rank scan is exact
 // for integers up to 2048 and overshoots the true rank by at most 31 before the correction);
 // 4 / 8 / 16 for mid-size trees (k <= 4096 / 8192 / 16384) with the integer rank scan.
-template <typename IdxT, typename OutT, int MODE, int WPL>
+// VSTAGED: vt points into shared memory (a staged copy of the row), so plain loads instead of LDG.
+template <typename IdxT, typename OutT, int MODE, int WPL, bool VSTAGED = false>
 __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int k, int K, OutT* ot,
                                                 uint16_t* base, int lane, const uint8_t* __restrict__ lut) {
+    auto ldv = [&](int i) -> long long { return VSTAGED ? (long long)vt[i] : (long long)__ldg(vt + i); };
     const int KA = K + 32;
     constexpr bool LIGHT = WPL > 2;                 // k <= 16384: time < 2^14 and v[t] < 2^15 share a 32-bit word
     const int narr = LIGHT ? ((MODE == MODE_PAIRS) ? 0 : 1) : ((MODE == MODE_PAIRS) ? 2 : 3);
@@ -181,7 +183,7 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int i = (b0 + j) * 32 + lane;
-            xs[j] = (i < k) ? (long long)__ldg(vt + i) : 0;
+            xs[j] = (i < k) ? ldv(i) : 0;
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -193,7 +195,7 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
     if (__any_sync(FULL, anybad)) {             // rare: find the first offending index
         for (int b = 0; b < nb; ++b) {
             const int i = b * 32 + lane;
-            const bool ok = (i >= k) || (unsigned long long)(long long)__ldg(vt + i) <= (unsigned long long)(2 * i);
+            const bool ok = (i >= k) || (unsigned long long)ldv(i) <= (unsigned long long)(2 * i);
             const unsigned bm = __ballot_sync(FULL, !ok);
             if (bm) return b * 32 + __ffs(bm) - 1;
         }
@@ -221,8 +223,8 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
     int badmin = 0x7FFFFFFF;
     auto issue_v = [&](int b) {                    // batches b (hi) and b - 1 (lo); b may be < 1 past the end
         const int t1 = b * 32 + lane, t0 = t1 - 32;
-        raw_hi = (b >= 0 && t1 < k) ? (long long)__ldg(vt + t1) : 0;
-        raw_lo = (t0 >= 0) ? (long long)__ldg(vt + t0) : 0;
+        raw_hi = (b >= 0 && t1 < k) ? ldv(t1) : 0;
+        raw_lo = (t0 >= 0) ? ldv(t0) : 0;
     };
     auto take_v = [&](int b) {
         const int t1 = b * 32 + lane, t0 = t1 - 32;
