@@ -1838,10 +1838,11 @@ cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t
     // small matrices: one CTA walks all column chunks of its tile (row-side setup done once)
     // and bigger ones as many as still leave every SM a few CTAs: the per-tile set-up (row side,
     // minima over the blocks in between, sparse table of the block) is then paid once per group
+    static const int cta_factor = [] { const char* e = getenv("P2V_ROWS_CTA_FACTOR"); return e ? atoi(e) : 18; }();
     int chunks_per_cta = (chunks <= 4) ? chunks : 1;
     if (chunks > 4) {
         for (int c = 8; c > 1; c >>= 1)
-            if (B * tiles_bound * ((chunks + c - 1) / c) >= (int64_t)sm_count() * 18) { chunks_per_cta = c; break; }
+            if (B * tiles_bound * ((chunks + c - 1) / c) >= (int64_t)sm_count() * cta_factor) { chunks_per_cta = c; break; }
     }
     const int64_t work = B * tiles_bound * ((chunks + chunks_per_cta - 1) / chunks_per_cta);
     const size_t smem = rows_dyn_smem(call);

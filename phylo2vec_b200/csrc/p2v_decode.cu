@@ -58,18 +58,18 @@ decode_small_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
     }
 }
 
-// Batches of big trees (16384 < k <= 65535): one warp per tree, one tree per CTA (p2v_decode_warp_big.cuh);
+// Batches of big trees (16384 < k <= 262143): one warp per tree, one tree per CTA (p2v_decode_warp_big.cuh);
 // CTA c keeps its label table in slice c of the workspace.
-template <typename IdxT, int MODE>
+template <typename IdxT, int MODE, typename TblT>
 __global__ void __launch_bounds__(32)
 decode_big_warp_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restrict__ out, int64_t out_stride,
-                       int32_t* __restrict__ status, int K, uint16_t* __restrict__ tables, size_t table_stride) {
+                       int32_t* __restrict__ status, int K, TblT* __restrict__ tables, size_t table_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
-    uint16_t* gtbl = tables + (size_t)blockIdx.x * table_stride;
+    TblT* gtbl = tables + (size_t)blockIdx.x * table_stride;
     for (int64_t tree = blockIdx.x; tree < B; tree += gridDim.x) {
-        const int bad = decode_tree_warp_big<IdxT, IdxT, MODE>(v + tree * k, k, K, out + tree * out_stride,
-                                                               reinterpret_cast<uint16_t*>(smem_raw), gtbl, lane);
+        const int bad = decode_tree_warp_big<IdxT, IdxT, MODE, TblT>(v + tree * k, k, K, out + tree * out_stride,
+                                                                     reinterpret_cast<uint16_t*>(smem_raw), gtbl, lane);
         if (lane == 0 && status) status[tree] = bad + 1;
         __syncwarp();
     }
@@ -562,17 +562,18 @@ static int large_teams(int64_t B) {
     return (int)(B < cap ? B : cap);
 }
 
-constexpr int BIG_WARP_K_MAX = 65535;       // slots and labels fit 16 bits
+constexpr int BIG_WARP_K_MAX = 262143;      // 32 KB of free-slot mask per tree; label tables uint16 up to 65535 slots, uint32 above
 constexpr int BIG_WARP_CTAS_PER_SM = 16;    // resident trees per SM the workspace is sized for
 static bool big_warp_batch(int64_t B, int64_t k) { return k > warp_k_max() && k <= BIG_WARP_K_MAX && B * 4 > sm_count(); }
-static size_t big_warp_table_stride(int64_t k) { return (((size_t)k + 31) & ~(size_t)31) + 32; }   // uint16 entries
+static size_t big_warp_table_stride(int64_t k) { return (((size_t)k + 31) & ~(size_t)31) + 32; }   // entries
+static size_t big_warp_entry_bytes(int64_t k) { return k <= 65535 ? 2 : 4; }
 static int64_t big_warp_ctas(int64_t B) {
     const int64_t cap = (int64_t)sm_count() * BIG_WARP_CTAS_PER_SM;
     return B < cap ? B : cap;
 }
 
 size_t decode_workspace_bytes(int64_t B, int64_t k) {
-    if (B > 0 && big_warp_batch(B, k)) return (size_t)big_warp_ctas(B) * big_warp_table_stride(k) * sizeof(uint16_t);
+    if (B > 0 && big_warp_batch(B, k)) return (size_t)big_warp_ctas(B) * big_warp_table_stride(k) * big_warp_entry_bytes(k);
     if (k <= MID_K_MAX || B <= 0) return 0;
     return (size_t)large_teams(B) * large_ws_stride(B, k) * sizeof(uint32_t);
 }
@@ -658,19 +659,23 @@ static cudaError_t launch_decode_t(const void* v, int64_t B, int64_t k, void* ou
         const size_t smem = decode_big_scratch_u16(K) * sizeof(uint16_t);
         const size_t tstride = big_warp_table_stride(k);
         int64_t ctas = big_warp_ctas(B);
-        if (!ws || ws_bytes < (size_t)ctas * tstride * sizeof(uint16_t)) return cudaErrorInvalidValue;
-        auto kern = decode_big_warp_kernel<IdxT, MODE>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (!ws || ws_bytes < (size_t)ctas * tstride * big_warp_entry_bytes(k)) return cudaErrorInvalidValue;
+        auto go = [&](auto kern, auto* tables) -> cudaError_t {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            int per_sm = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem);
+            if (e != cudaSuccess) return e;
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm > BIG_WARP_CTAS_PER_SM) per_sm = BIG_WARP_CTAS_PER_SM;
+            const int64_t cap = (int64_t)sm_count() * per_sm;
+            if (ctas > cap) ctas = cap;
+            kern<<<(int)ctas, 32, smem, stream>>>((const IdxT*)v, B, (int)k, (IdxT*)out, out_stride, status, K, tables, tstride);
+            return cudaSuccess;
+        };
+        cudaError_t e = (k <= 65535) ? go(decode_big_warp_kernel<IdxT, MODE, uint16_t>, reinterpret_cast<uint16_t*>(ws))
+                                     : go(decode_big_warp_kernel<IdxT, MODE, uint32_t>, reinterpret_cast<uint32_t*>(ws));
         if (e != cudaSuccess) return e;
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm > BIG_WARP_CTAS_PER_SM) per_sm = BIG_WARP_CTAS_PER_SM;
-        const int64_t cap = (int64_t)sm_count() * per_sm;
-        if (ctas > cap) ctas = cap;
-        kern<<<(int)ctas, 32, smem, stream>>>((const IdxT*)v, B, (int)k, (IdxT*)out, out_stride, status, K,
-                                             reinterpret_cast<uint16_t*>(ws), tstride);
     } else if (k <= MID_K_MAX) {
         // mid-size trees: the same merge kernel with uint16 work arrays in shared memory
         const size_t smem = mid_smem_bytes(k);

@@ -1,4 +1,4 @@
-// Warp-per-tree decode for BATCHES of big trees (16384 < k <= 65535) -- the same backward slot assignment and
+// Warp-per-tree decode for BATCHES of big trees (16384 < k <= 262143) -- the same backward slot assignment and
 // forward relabel sweep as p2v_decode_warp.cuh, laid out so that dozens of such trees fit an SM:
 //   * shared memory holds the free-slot bit mask only (k / 8 bytes) plus one staged batch of rows;
 //   * lane l owns the mask words [l * wpl, (l + 1) * wpl) and keeps THE NUMBER of free slots among them in a
@@ -7,7 +7,8 @@
 //   * v is read from global memory a pair of batches ahead of the rank scan (and validated on the way);
 //   * the (time, value) of every slot is parked as a 64-bit word at the END of the tree's own output rows (row s is
 //     written after word s was read and only reaches words below s) and read back, coalesced, by the sweep;
-//   * "last row so far whose label is x" lives in global memory (uint16, one table per resident warp, L2).
+//   * "last row so far whose label is x" lives in global memory (one table per resident warp, L2; uint16 entries
+//     while slots fit 16 bits, uint32 above).
 // The merge kernel (decode_large_kernel) does O(k log^2 k) work per tree; this one O(32 k) like the small kernel.
 #pragma once
 #include "p2v_decode_warp.cuh"
@@ -19,15 +20,16 @@ __host__ __device__ inline int decode_big_wpl(int K) { return ((((K >> 5) + 31) 
 // uint16 entries of shared memory per warp: mask words (2 u16 each), per-lane placement counters, a staged batch
 __host__ __device__ inline size_t decode_big_scratch_u16(int K) { return (size_t)2 * 32 * decode_big_wpl(K) + 64 + 16 + 98 * 4; }
 
-template <typename IdxT, typename OutT, int MODE>
+template <typename IdxT, typename OutT, int MODE, typename TblT>
 __device__ __forceinline__ int decode_tree_warp_big(const IdxT* __restrict__ vt, int k, int K, OutT* ot, uint16_t* base,
-                                                    uint16_t* __restrict__ gtbl /* K + 32 entries, global */, int lane) {
+                                                    TblT* __restrict__ gtbl /* K + 32 entries, global */, int lane) {
+    constexpr uint32_t TNONE = (sizeof(TblT) == 2) ? 0xFFFFu : 0xFFFFFFFFu;
     const int KA = K + 32;
     const int W = K >> 5;                          // mask words in use
     const int wpl = decode_big_wpl(K);             // words per lane; words W .. 32 * wpl - 1 hold no free slot
     uint32_t* smask = reinterpret_cast<uint32_t*>(base);
     uint32_t* ldec = smask + 32 * wpl;             // 32 counters: placements that landed in lane l's words
-    OutT* srow = reinterpret_cast<OutT*>((reinterpret_cast<uintptr_t>(ldec + 32) + 15) & ~(uintptr_t)15);
+    OutT* srow = reinterpret_cast<OutT*>(ldec + 32);   // 16-byte aligned: 128 * wpl + 128 bytes into the warp's scratch
     const int nb = K >> 5;
     constexpr int ROWE = (MODE == MODE_PAIRS || MODE == MODE_ANC2) ? 2 : (MODE == MODE_ANCESTRY ? 3 : 4);
     // (rounded down to 8 bytes: 12-byte int32 ancestry rows of an odd k end on a 4-byte boundary; the words still
@@ -37,7 +39,8 @@ __device__ __forceinline__ int decode_tree_warp_big(const IdxT* __restrict__ vt,
 
     if (MODE != MODE_PAIRS) {                      // "no row yet" for every label
         uint4 ones; ones.x = ones.y = ones.z = ones.w = 0xFFFFFFFFu;
-        for (int i = lane * 8; i < KA; i += 256) __stcg(reinterpret_cast<uint4*>(gtbl + i), ones);
+        constexpr int PER = 16 / (int)sizeof(TblT);
+        for (int i = lane * PER; i < KA; i += 32 * PER) __stcg(reinterpret_cast<uint4*>(gtbl + i), ones);
     }
     for (int g = lane; g < 32 * wpl; g += 32) smask[g] = (g < W) ? 0xFFFFFFFFu : 0u;   // every slot below K is free (padding slots too)
     ldec[lane] = 0u;
@@ -164,19 +167,19 @@ __device__ __forceinline__ int decode_tree_warp_big(const IdxT* __restrict__ vt,
             label_stage(b + 1, (uint32_t)w1, (uint32_t)(w1 >> 32));
         } else {
             const uint32_t lower = peers & lanes_lt(lane);
-            uint32_t cand = NONE16;
+            uint32_t cand = TNONE;
             if (root && !lower) cand = __ldcg(gtbl + lab);
             label_stage(b + 1, (uint32_t)w1, (uint32_t)(w1 >> 32));          // overlaps the table lookup
             uint32_t c1p = (uint32_t)(k + s);
             if (root) {
                 if (lower) cand = (uint32_t)(b * 32 + 31 - __clz(lower));
-                c1p = (cand != NONE16) ? (uint32_t)(k + 1) + cand : lab;
+                c1p = (cand != TNONE) ? (uint32_t)(k + 1) + cand : lab;
             }
             __syncwarp();
-            if (act && (peers & lanes_gt(lane)) == 0) __stcg(gtbl + lab, (uint16_t)s);
+            if (act && (peers & lanes_gt(lane)) == 0) __stcg(gtbl + lab, (TblT)s);
             __syncwarp();
-            const uint32_t q = act ? (uint32_t)__ldcg(gtbl + t + 1) : NONE16;
-            const uint32_t c2p = (q != NONE16) ? (uint32_t)(k + 1) + q : t + 1;
+            const uint32_t q = act ? (uint32_t)__ldcg(gtbl + t + 1) : TNONE;
+            const uint32_t c2p = (q != TNONE) ? (uint32_t)(k + 1) + q : t + 1;
             if (MODE == MODE_ANCESTRY) {
                 OutT* const dst = ot + 96 * (size_t)b;
                 const int a = (int)((reinterpret_cast<uintptr_t>(dst) / sizeof(OutT)) & 1);

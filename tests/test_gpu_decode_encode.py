@@ -138,9 +138,10 @@ def test_decode_parity_whole_grid(p2v, n_leaves):
     assert int(st[0]) == k // 2 + 1
 
 
-# Batches of big trees (16384 < k <= 65535, at least 38 of them) take the warp-per-tree kernel with the mask in
-# shared memory and the label table in the workspace (p2v_decode_warp_big.cuh); beyond 65535 the merge kernel.
-@pytest.mark.parametrize("n_leaves", [16386, 16400, 20000, 33000, 65535, 65536, 65537])
+# Batches of big trees (16384 < k <= 262143, at least 38 of them) take the warp-per-tree kernel with the mask in
+# shared memory and the label table in the workspace (p2v_decode_warp_big.cuh; uint32 table entries above 65535
+# slots); beyond that the merge kernel.
+@pytest.mark.parametrize("n_leaves", [16386, 16400, 20000, 33000, 65535, 65536, 65537, 65570, 100000, 262144, 262145])
 def test_decode_parity_big_batches(p2v, n_leaves):
     k = n_leaves - 1
     B = 40
@@ -154,6 +155,8 @@ def test_decode_parity_big_batches(p2v, n_leaves):
                          ("to_edges", p2v.to_edges_batch)):
             if dtype == torch.int32 and name == "to_edges":
                 continue
+            if n_leaves > 70000 and (dtype, name) not in ((torch.int64, "to_ancestry"), (torch.int32, "to_pairs")):
+                continue                                   # the oracle takes seconds per call at these sizes
             ref, st = O.batch(name, V, k)
             assert not st.any()
             got = fn(Vd)
