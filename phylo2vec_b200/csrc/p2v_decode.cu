@@ -276,10 +276,10 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
         if (MODE == MODE_PAIRS) { team_sync<CSIZE>(); continue; }
 
         // ---- ancestry / edges, one huge tree on the whole grid, slots fit 16 bits: one worker per CTA with
-        //      its "last row with label x" table in SHARED memory.  1. warp 0 of every CTA records the last
+        //      its "last row with label x" table in SHARED memory.  1. warp 1 of every CTA records the last
         //      row of each label inside its slot range; 2. the tables are published (uint16) and an exclusive
         //      prefix over the workers -- eight labels per thread and step -- turns table w into "last row with
-        //      label x before range w"; 3. every CTA loads its prefix state back and warp 0 runs the ordinary
+        //      label x before range w"; 3. every CTA loads its prefix state back and warp 1 runs the ordinary
         //      sweep on its range.  All table traffic of the two sequential passes is shared-memory latency.
         if (CSIZE == 0 && SMEMTBL && !SMEMARR) {
             const int TBL = (int)tbl_entries;                                  // k + 2 rounded up to 8
