@@ -92,11 +92,12 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("P2V_B200_LIB") or LIB_PATH      # e.g. the -DP2V_DEBUG_BOUNDS build, libphylo2vec_b200_dbg.so
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m phylo2vec_b200.build` "
+            f"{path} is missing: build it with `python -m phylo2vec_b200.build` "
             "(needs nvcc; sm_100a). There is no CPU fallback.")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res

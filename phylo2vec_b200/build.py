@@ -1,6 +1,10 @@
 """Builds libphylo2vec_b200.so (CUDA kernels + C ABI) in-tree with nvcc for sm_100a.
 
-    python -m phylo2vec_b200.build [--force] [--verbose]
+    python -m phylo2vec_b200.build [--force] [--verbose] [--debug-bounds]
+
+--debug-bounds also builds lib/libphylo2vec_b200_dbg.so: the decode / encode kernels compiled with
+-DP2V_DEBUG_BOUNDS (every shared-memory table index asserted, see p2v_common.cuh), linked with the ordinary
+objects of the other sources; tests/test_gpu_debug_bounds.py runs the boundary sizes through it.
 
 The shared object stays inside the package (phylo2vec_b200/lib/), so it travels
 with the source tree to the GPU box; there is no JIT cache and no fallback.
@@ -17,6 +21,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libphylo2vec_b200.so")
+LIB_DBG = os.path.join(LIBDIR, "libphylo2vec_b200_dbg.so")
+DBG_SOURCES = ["p2v_decode.cu", "p2v_encode.cu"]      # the kernels with scattered shared-memory tables
 SOURCES = ["p2v_capi.cu", "p2v_decode.cu", "p2v_encode.cu", "p2v_cophenetic.cu", "p2v_newick.cu", "p2v_treewise.cu", "p2v_newick_matrix.cu", "p2v_csv.cu"]
 HEADERS = ["p2v_common.cuh", "p2v_internal.h", "p2v_decode_warp.cuh", "p2v_decode_warp_big.cuh", "p2v_encode_light.cuh", "p2v_tree_pass.cuh", "p2v_float_text.cuh", "p2v_float_tables.h", os.path.join("..", "..", "include", "phylo2vec_b200.h")]
 
@@ -87,5 +93,37 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_debug_bounds(force: bool = False) -> str:
+    """libphylo2vec_b200_dbg.so: DBG_SOURCES with -DP2V_DEBUG_BOUNDS, everything else from the ordinary objects."""
+    build(force=False)
+    objdir = os.path.join(HERE, "build")
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    if not force and os.path.exists(LIB_DBG) and all(os.path.getmtime(d) < os.path.getmtime(LIB_DBG) for d in deps):
+        return LIB_DBG
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = _nvcc()
+    compile_flags = [f for f in NVCC_FLAGS if f != "--shared"] + ["-DP2V_DEBUG_BOUNDS"]
+
+    def one(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".dbg.o")
+        return obj, subprocess.run([nvcc] + compile_flags + ["-c", "-o", obj, os.path.join(CSRC, src)],
+                                   capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=len(DBG_SOURCES)) as ex:
+        results = list(ex.map(one, DBG_SOURCES))
+    for _, r in results:
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed building libphylo2vec_b200_dbg.so")
+    objs = [o for o, _ in results] + [os.path.join(objdir, os.path.splitext(s)[0] + ".o") for s in SOURCES if s not in DBG_SOURCES]
+    r = subprocess.run([nvcc, "--shared", "-o", LIB_DBG] + objs + ["-lpthread"], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed linking libphylo2vec_b200_dbg.so")
+    return LIB_DBG
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--debug-bounds" in sys.argv:
+        print(build_debug_bounds(force="--force" in sys.argv))

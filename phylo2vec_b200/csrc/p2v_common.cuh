@@ -1,5 +1,6 @@
 // Shared device helpers for the phylo2vec B200 kernels (sm_100a).
 #pragma once
+#include <cstdio>
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -7,6 +8,22 @@
 namespace p2v {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
+// -DP2V_DEBUG_BOUNDS (python -m phylo2vec_b200.build --debug-bounds -> libphylo2vec_b200_dbg.so): every index into a
+// shared-memory table or a parked scratch word of the decode / encode kernels is checked; a bad one prints its
+// location and traps, which fails the launch (tests/test_gpu_debug_bounds.py runs the boundary sizes this way;
+// compute-sanitizer is closed on the GPU pool).
+#ifdef P2V_DEBUG_BOUNDS
+#define P2V_CHECK_INDEX(i, n)                                                                                   \
+    do {                                                                                                        \
+        if (!((unsigned long long)(long long)(i) < (unsigned long long)(long long)(n))) {                       \
+            printf("p2v bounds: %s:%d index %lld, limit %lld\n", __FILE__, __LINE__, (long long)(i), (long long)(n)); \
+            __trap();                                                                                           \
+        }                                                                                                       \
+    } while (0)
+#else
+#define P2V_CHECK_INDEX(i, n) do { } while (0)
+#endif
+
 constexpr uint32_t NONE16 = 0xFFFFu;
 constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 

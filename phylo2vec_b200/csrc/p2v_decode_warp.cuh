@@ -344,8 +344,9 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
                 if (adv) { rr -= c; wd = q.w; ++g; }
             }
             const uint32_t pos = LIGHT ? nth_set_bit(wd, rr) : nth_set_bit_lut(wd, rr, lut);    // lut: nth_bit_lut_init, 2 KB per CTA
+            P2V_CHECK_INDEX(g, 32 * WPL); P2V_CHECK_INDEX(pos, 32);
             if (LIGHT) { if ((int)(g * 32 + pos) < k) *park((int)(g * 32 + pos)) = (uint32_t)t | (xval << 14); }
-            else stime[g * 32 + pos] = (uint16_t)t;
+            else { P2V_CHECK_INDEX(g * 32 + pos, KA); stime[g * 32 + pos] = (uint16_t)t; }
             if (WPL == 1 && P2V_DECODE_REDUX && K >= 512) {     // measured: +1.5 % at n = 512..1024, -3 % at n = 100
                 // The low ranks of a batch (its roots) all land in the first word that still has free
                 // slots, and same-word ATOMS serialise: those lanes are combined with one warp-wide
@@ -460,14 +461,14 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
         const int s3 = s + 96;
         uint32_t x2, t3, w5 = 0;
         if (LIGHT) { t2 = w2 & 0x3FFFu; x2 = w2 >> 14; w5 = parked(s + 160); t3 = 0; }
-        else { x2 = sv[t2]; t3 = (s3 < k) ? (uint32_t)stime[s3] : 0u; }
+        else { P2V_CHECK_INDEX(t2, KA); x2 = sv[t2]; t3 = (s3 < k) ? (uint32_t)stime[s3] : 0u; }
         if (MODE == MODE_PAIRS) {
             if (act) store_pair<OutT>(ot + 2 * (size_t)s, (OutT)lab, (OutT)(t + 1));
             label_stage(b + 1, t1, x1);
         } else {
             const uint32_t lower = peers & lanes_lt(lane);
             uint32_t cand = NONE16;
-            if (root && !lower) cand = stbl[lab];
+            if (root && !lower) { P2V_CHECK_INDEX(lab, KA); cand = stbl[lab]; }
             label_stage(b + 1, t1, x1);                 // independent of the table: overlaps the lookup
             uint32_t c1p = (uint32_t)(k + s);            // non-root: the previous row's parent
             if (root) {
@@ -475,15 +476,17 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
                 c1p = (cand != NONE16) ? (uint32_t)(k + 1) + cand : lab;
             }
             __syncwarp();
-            if (act && (peers & lanes_gt(lane)) == 0) stbl[lab] = (uint16_t)s;
+            if (act && (peers & lanes_gt(lane)) == 0) { P2V_CHECK_INDEX(lab, KA); stbl[lab] = (uint16_t)s; }
             __syncwarp();
             if (LIGHT && MODE == MODE_ANCESTRY) {
+                if (act) P2V_CHECK_INDEX(t + 1, KA);
                 const uint32_t q = act ? (uint32_t)stbl[t + 1] : NONE16;
                 const uint32_t c2p = (q != NONE16) ? (uint32_t)(k + 1) + q : t + 1;
                 // element parity of the batch's first element against a two-element (16 / 8 byte) boundary
                 OutT* const dst = ot + 96 * (size_t)b;
                 const int a = (int)((reinterpret_cast<uintptr_t>(dst) / sizeof(OutT)) & 1);
                 OutT* const st = srow + a;                 // the staged copy has the alignment of the destination
+                P2V_CHECK_INDEX(a + 3 * lane + 2, 98);
                 st[3 * lane] = (OutT)c1p; st[3 * lane + 1] = (OutT)c2p; st[3 * lane + 2] = (OutT)(k + 1 + s);
                 __syncwarp();
                 const int lim = 3 * min(32, k - b * 32);   // valid elements of this batch
@@ -500,6 +503,7 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
                 }
                 __syncwarp();
             } else if (act) {
+                P2V_CHECK_INDEX(t + 1, KA);
                 const uint32_t q = stbl[t + 1];
                 const uint32_t c2p = (q != NONE16) ? (uint32_t)(k + 1) + q : t + 1;
                 store_row<OutT, MODE>(ot, s, (OutT)c1p, (OutT)c2p, (OutT)(k + 1 + s));

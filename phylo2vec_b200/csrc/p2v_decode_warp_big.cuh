@@ -103,6 +103,7 @@ __device__ __forceinline__ int decode_tree_warp_big(const IdxT* __restrict__ vt,
         }
         const uint32_t pos = nth_set_bit(wd, rr);
         const int slot = (int)(g * 32 + pos);
+        if (found) { P2V_CHECK_INDEX(g, 32 * wpl); P2V_CHECK_INDEX(pos, 32); }
         if (found && slot < k) __stcg(park + slot, (unsigned long long)(uint32_t)t | ((unsigned long long)xval << 32));
         __syncwarp();                                              // every lane has read the mask
         if (found) { atomicAnd(&smask[g], ~(1u << pos)); atomicAdd(&ldec[w], 1u); }
@@ -168,7 +169,7 @@ __device__ __forceinline__ int decode_tree_warp_big(const IdxT* __restrict__ vt,
         } else {
             const uint32_t lower = peers & lanes_lt(lane);
             uint32_t cand = TNONE;
-            if (root && !lower) cand = __ldcg(gtbl + lab);
+            if (root && !lower) { P2V_CHECK_INDEX(lab, KA); cand = __ldcg(gtbl + lab); }
             label_stage(b + 1, (uint32_t)w1, (uint32_t)(w1 >> 32));          // overlaps the table lookup
             uint32_t c1p = (uint32_t)(k + s);
             if (root) {
@@ -176,8 +177,9 @@ __device__ __forceinline__ int decode_tree_warp_big(const IdxT* __restrict__ vt,
                 c1p = (cand != TNONE) ? (uint32_t)(k + 1) + cand : lab;
             }
             __syncwarp();
-            if (act && (peers & lanes_gt(lane)) == 0) __stcg(gtbl + lab, (TblT)s);
+            if (act && (peers & lanes_gt(lane)) == 0) { P2V_CHECK_INDEX(lab, KA); __stcg(gtbl + lab, (TblT)s); }
             __syncwarp();
+            if (act) P2V_CHECK_INDEX(t + 1, KA);
             const uint32_t q = act ? (uint32_t)__ldcg(gtbl + t + 1) : TNONE;
             const uint32_t c2p = (q != TNONE) ? (uint32_t)(k + 1) + q : t + 1;
             if (MODE == MODE_ANCESTRY) {

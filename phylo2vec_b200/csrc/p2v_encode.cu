@@ -173,6 +173,7 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                         if (old & (1u << (idx & 31))) bad = true;      // two rows, one parent
                         dst = (int)idx;
                     }
+                    P2V_CHECK_INDEX(dst, KA);
                     sc1[dst] = (uint16_t)c1[j]; sc2[dst] = (uint16_t)c2[j]; spr[dst] = (uint16_t)pp[j];
                 }
             }
@@ -188,7 +189,7 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                 if (s < k) {
                     const uint32_t p = spr[s];
                     if (p < kint) bad = true;                 // a leaf label as parent: not a tree in this format
-                    else sdef[p - kint] = (uint16_t)s;
+                    else { P2V_CHECK_INDEX(p - kint, KA); sdef[p - kint] = (uint16_t)s; }
                 }
             }
             bad = __any_sync(FULL, bad);
@@ -202,8 +203,8 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                 uint32_t c1 = 0, c2 = 0, p = kint, d1 = NONE16, d2 = NONE16;
                 if (act) {
                     c1 = sc1[s]; c2 = sc2[s]; p = spr[s];
-                    if (c1 >= kint) d1 = sdef[c1 - kint];
-                    if (c2 >= kint) d2 = sdef[c2 - kint];
+                    if (c1 >= kint) { P2V_CHECK_INDEX(c1 - kint, KA); d1 = sdef[c1 - kint]; }
+                    if (c2 >= kint) { P2V_CHECK_INDEX(c2 - kint, KA); d2 = sdef[c2 - kint]; }
                     if (d1 != NONE16 && d1 >= (uint32_t)s) d1 = NONE16;  // defined later: a leaf, as in the reference
                     if (d2 != NONE16 && d2 >= (uint32_t)s) d2 = NONE16;
                 }
@@ -262,6 +263,7 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                     else {
                         const uint32_t bit = 1u << ((cm - 1) & 31);
                         if (atomicOr(&smask[(cm - 1) >> 5], bit) & bit) bad = true;
+                        P2V_CHECK_INDEX(cm, KA);
                         spr[cm] = (uint16_t)s;
                     }
                 }
@@ -326,6 +328,7 @@ encode_small_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                     }
                 }
                 if (act) {
+                    P2V_CHECK_INDEX(r, KA); P2V_CHECK_INDEX(g, 32 * WPL);
                     const uint32_t lo = min((uint32_t)sc1[r], (uint32_t)sc2[r]);
                     vo[c - 1] = (IdxT)(idx == 0 ? lo : (uint32_t)(c - 1) + idx);
                     atomicOr(&smask[g], 1u << (r & 31));

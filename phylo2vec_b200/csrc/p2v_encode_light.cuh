@@ -140,6 +140,7 @@ encode_light_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                     const long long idx = p[j] - k - offset;
                     if (a[j] < 0 || a[j] > top || c[j] < 0 || c[j] > top || p[j] < 0 || idx < 0 || idx >= k) { bad = true; continue; }
                     const uint32_t bit = 1u << (idx & 31);
+                    P2V_CHECK_INDEX(idx >> 5, 32 * wpl);
                     if (atomicOr(&mask[idx >> 5], bit) & bit) bad = true;               // two rows, one parent
                     __stcg(reinterpret_cast<uint2*>(E) + idx, make_uint2((uint32_t)a[j], (uint32_t)c[j]));
                 }
@@ -184,6 +185,7 @@ encode_light_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                     const uint32_t pi = p - kint;
                     const bool live = act && ok;
                     if (live) {
+                        P2V_CHECK_INDEX(pi, TN);
                         if (T.get(pi) != NONE) ok = false;         // the label already has a defining row
                         T.set(pi, NONE - 1 - lane);
                     }
@@ -193,11 +195,13 @@ encode_light_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                     int j1 = -1, j2 = -1;                          // lanes this row waits for
                     if (act) {
                         if (c1 >= kint) {
+                            P2V_CHECK_INDEX(c1 - kint, TN);
                             const uint32_t t = T.get(c1 - kint);
                             if (t >= PEND0) { if (t != NONE && (int)(NONE - 1 - t) < lane) j1 = (int)(NONE - 1 - t); }
                             else m1 = t;
                         }
                         if (c2 >= kint) {
+                            P2V_CHECK_INDEX(c2 - kint, TN);
                             const uint32_t t = T.get(c2 - kint);
                             if (t >= PEND0) { if (t != NONE && (int)(NONE - 1 - t) < lane) j2 = (int)(NONE - 1 - t); }
                             else m2 = t;
@@ -247,6 +251,7 @@ encode_light_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                     if (cm < 1 || cm > (uint32_t)k) bad = true;
                     else {
                         const uint32_t bit = 1u << ((cm - 1) & 31);
+                        P2V_CHECK_INDEX((cm - 1) >> 5, 32 * wpl);
                         if (atomicOr(&mask[(cm - 1) >> 5], bit) & bit) bad = true;      // c_max must be a permutation
                         __stcg(park + (cm - 1), (uint32_t)s | (lo << 16));
                     }
@@ -309,6 +314,7 @@ encode_light_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                 const uint32_t cnt = lcs[lane];
                 const uint32_t excl = warp_incl_scan(cnt, lane) - cnt;
                 const uint32_t g = r >> 5, src = g >> wsh;
+                P2V_CHECK_INDEX(g, 32 * wpl); P2V_CHECK_INDEX(src, 32);
                 uint32_t idx = __shfl_sync(FULL, excl, src) + (h ? inb_b : inb_a);
                 const uint4* q = reinterpret_cast<const uint4*>(mask + ((size_t)src << wsh));
                 const int nq = (int)(g - (src << wsh)) >> 2;
