@@ -20,12 +20,15 @@
 // sweep over that table.  Above T_SMEM_K_MAX the table T moves to the workspace as 32-bit entries.
 #pragma once
 
+#include <type_traits>
+
 #include "p2v_common.cuh"
 #include "p2v_internal.h"
 
 namespace p2v {
 
 constexpr int ENC_LIGHT_K_MAX = 65535;       // row and c_min share one parked 32-bit word
+constexpr int ENC_LIGHT_WIDE_K_MAX = 262143; // int64 output: a parked 64-bit word per value IS the output row; 32 KB of mask
 constexpr int ENC_LIGHT_T_SMEM_K_MAX = 32767;   // table in shared memory (uint16) up to here: 66 KB, three trees per SM
 
 __host__ __device__ inline int enc_light_wpl(int K) {   // mask words per lane: a power of two >= 4
@@ -67,7 +70,9 @@ template <> struct EncTable<true> {
 
 __device__ __forceinline__ uint32_t popc4(const uint4 q) { return __popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w); }
 
-template <typename IdxT, int MODE, bool GT>
+// WIDE (k > 65535, int64 output, table in the workspace): row and c_min take 32 bits each of a 64-bit parked word,
+// which sits exactly where v[c_max - 1] will go (the lane that reads it writes it).
+template <typename IdxT, int MODE, bool GT, bool WIDE = false>
 __global__ void __launch_bounds__(128)
 encode_light_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restrict__ vout,
                     int32_t* __restrict__ status, int K, uint32_t* __restrict__ ws, size_t ws_words) {
@@ -93,7 +98,8 @@ encode_light_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
     for (int64_t tree = (int64_t)blockIdx.x * nwarps + warp; tree < B; tree += (int64_t)gridDim.x * nwarps) {
         const IdxT* it = in + tree * ((int64_t)k * in_cols);
         IdxT* vo = vout + tree * k;
-        uint32_t* park = reinterpret_cast<uint32_t*>(vo) + (sizeof(IdxT) == 8 ? k : 0);
+        uint32_t* park = reinterpret_cast<uint32_t*>(vo) + ((sizeof(IdxT) == 8 && !WIDE) ? k : 0);
+        unsigned long long* park64 = reinterpret_cast<unsigned long long*>(vo);      // WIDE only
         bool bad = false;
         for (int j = 0; j < wpl; ++j) mask[lane * wpl + j] = 0;
         lcs[lane] = 0;
@@ -253,7 +259,8 @@ encode_light_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                         const uint32_t bit = 1u << ((cm - 1) & 31);
                         P2V_CHECK_INDEX((cm - 1) >> 5, 32 * wpl);
                         if (atomicOr(&mask[(cm - 1) >> 5], bit) & bit) bad = true;      // c_max must be a permutation
-                        __stcg(park + (cm - 1), (uint32_t)s | (lo << 16));
+                        if (WIDE) __stcg(park64 + (cm - 1), (unsigned long long)(uint32_t)s | ((unsigned long long)lo << 32));
+                        else __stcg(park + (cm - 1), (uint32_t)s | (lo << 16));
                     }
                 }
             }
@@ -266,24 +273,38 @@ encode_light_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
         __syncwarp();
 
         // ---- build_vector: values ascending, two batches per in-batch count -----------------------------
-        uint32_t wcur[2], wnxt[2];
-        auto fetch = [&](int bp, uint32_t (&w)[2]) {
+        using ParkT = typename std::conditional<WIDE, unsigned long long, uint32_t>::type;
+        ParkT wcur[2], wnxt[2];
+        auto fetch = [&](int bp, ParkT (&w)[2]) {
             const int ca = bp * 32 + lane + 1, cb = ca + 32;
-            w[0] = (ca <= k) ? __ldcg(park + (ca - 1)) : 0u;
-            w[1] = (cb <= k) ? __ldcg(park + (cb - 1)) : 0u;
+            if (WIDE) {
+                w[0] = (ca <= k) ? (ParkT)__ldcg(park64 + (ca - 1)) : (ParkT)0;
+                w[1] = (cb <= k) ? (ParkT)__ldcg(park64 + (cb - 1)) : (ParkT)0;
+            } else {
+                w[0] = (ca <= k) ? (ParkT)__ldcg(park + (ca - 1)) : (ParkT)0;
+                w[1] = (cb <= k) ? (ParkT)__ldcg(park + (cb - 1)) : (ParkT)0;
+            }
         };
         fetch(0, wcur);
         fetch(2, wnxt);
         for (int bp = 0; bp < nb; bp += 2) {
             const int ca = bp * 32 + lane + 1, cb = ca + 32;
             const bool act_a = ca <= k, act_b = cb <= k;
-            const uint32_t wa = wcur[0], wb = wcur[1];
+            const ParkT wa = wcur[0], wb = wcur[1];
             wcur[0] = wnxt[0]; wcur[1] = wnxt[1];
             fetch(bp + 4, wnxt);
-            const uint32_t ra = wa & 0xFFFFu, rb = wb & 0xFFFFu;
-            const uint32_t ka = act_a ? ra : 0xFFFFu, kb = act_b ? rb : 0xFFFFu;
+            const uint32_t ra = WIDE ? (uint32_t)wa : ((uint32_t)wa & 0xFFFFu), rb = WIDE ? (uint32_t)wb : ((uint32_t)wb & 0xFFFFu);
+            const uint32_t loa = WIDE ? (uint32_t)((unsigned long long)wa >> 32) : ((uint32_t)wa >> 16);
+            const uint32_t lob = WIDE ? (uint32_t)((unsigned long long)wb >> 32) : ((uint32_t)wb >> 16);
+            const uint32_t ka = act_a ? ra : (WIDE ? 0x7FFFFFFFu : 0xFFFFu), kb = act_b ? rb : (WIDE ? 0x7FFFFFFFu : 0xFFFFu);
             uint32_t inb_a = 0, inb_b = 0;
-            if (K <= 32768) {
+            if (WIDE) {                          // rows of 18 bits: one shuffle per batch and step
+#pragma unroll
+                for (int d = 1; d < 32; ++d) {
+                    count_smaller_step(inb_a, ka, d);
+                    count_smaller_step(inb_b, kb, d);
+                }
+            } else if (K <= 32768) {
                 // rows have 15 bits: both halves compared by ONE subtraction.  Field f of (M - y) keeps bit 15
                 // iff mine_f - 1 >= y_f (no borrow crosses a field: 0x8000 + mine_f - 1 - y_f >= 0).
                 const uint32_t ya = act_a ? ra : 0x7FFFu, yb = act_b ? rb : 0x7FFFu;
@@ -310,7 +331,7 @@ encode_light_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                 const int c = h ? cb : ca;
                 const bool act = h ? act_b : act_a;
                 const uint32_t r = h ? rb : ra;
-                const uint32_t lo = (h ? wb : wa) >> 16;
+                const uint32_t lo = h ? lob : loa;
                 const uint32_t cnt = lcs[lane];
                 const uint32_t excl = warp_incl_scan(cnt, lane) - cnt;
                 const uint32_t g = r >> 5, src = g >> wsh;

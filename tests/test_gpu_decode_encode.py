@@ -229,9 +229,10 @@ def test_encode_parity_mid_batches(p2v, n_leaves, dtype):
     assert status[5].item() == -2 and int(status.count_nonzero()) == 1
 
 
-@pytest.mark.parametrize("n_leaves", [16385, 16386, 20000, 32768, 65535, 65536])
+@pytest.mark.parametrize("n_leaves", [16385, 16386, 20000, 32768, 32769, 65535, 65536, 65537, 100000, 262144, 262145])
 def test_encode_parity_big_batches(p2v, n_leaves):
-    """Batches of big trees on the warp-per-tree encoder with its label table in the workspace."""
+    """Batches of big trees on the warp-per-tree encoder with its label table in the workspace (above 65536 leaves:
+    64-bit parked words for int64 rows, the CTA kernel for int32)."""
     B = 150 if n_leaves <= 20000 else 40                  # more trees than SMs / 4 for the smaller sizes
     V = sample_vectors(B, n_leaves, seed=17 * n_leaves)
     adv = list(adversarial_vectors(n_leaves).values())
