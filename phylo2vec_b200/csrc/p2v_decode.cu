@@ -563,17 +563,23 @@ static int large_teams(int64_t B) {
 }
 
 constexpr int BIG_WARP_K_MAX = 262143;      // 32 KB of free-slot mask per tree; label tables uint16 up to 65535 slots, uint32 above
-constexpr int BIG_WARP_CTAS_PER_SM = 16;    // resident trees per SM the workspace is sized for
+// Resident trees per SM the workspace is sized for.  The kernel is latency-bound (two dependent label-table
+// accesses per batch of rows), so more residents help until their tables fall out of the L2: measured 32 per SM
+// at n = 32768 (+13 % over 16), 16 above (P2V_DECODE_BIG_PER_SM forces a value).
+static int big_warp_ctas_per_sm(int64_t k) {
+    static const int v = [] { const char* e = getenv("P2V_DECODE_BIG_PER_SM"); return e ? atoi(e) : 0; }();
+    return v > 0 ? v : (k <= 32768 ? 32 : 16);
+}
 static bool big_warp_batch(int64_t B, int64_t k) { return k > warp_k_max() && k <= BIG_WARP_K_MAX && B * 4 > sm_count(); }
 static size_t big_warp_table_stride(int64_t k) { return (((size_t)k + 31) & ~(size_t)31) + 32; }   // entries
 static size_t big_warp_entry_bytes(int64_t k) { return k <= 65535 ? 2 : 4; }
-static int64_t big_warp_ctas(int64_t B) {
-    const int64_t cap = (int64_t)sm_count() * BIG_WARP_CTAS_PER_SM;
+static int64_t big_warp_ctas(int64_t B, int64_t k) {
+    const int64_t cap = (int64_t)sm_count() * big_warp_ctas_per_sm(k);
     return B < cap ? B : cap;
 }
 
 size_t decode_workspace_bytes(int64_t B, int64_t k) {
-    if (B > 0 && big_warp_batch(B, k)) return (size_t)big_warp_ctas(B) * big_warp_table_stride(k) * big_warp_entry_bytes(k);
+    if (B > 0 && big_warp_batch(B, k)) return (size_t)big_warp_ctas(B, k) * big_warp_table_stride(k) * big_warp_entry_bytes(k);
     if (k <= MID_K_MAX || B <= 0) return 0;
     return (size_t)large_teams(B) * large_ws_stride(B, k) * sizeof(uint32_t);
 }
@@ -658,7 +664,7 @@ static cudaError_t launch_decode_t(const void* v, int64_t B, int64_t k, void* ou
         const int K = (int)((k + 31) & ~31);
         const size_t smem = decode_big_scratch_u16(K) * sizeof(uint16_t);
         const size_t tstride = big_warp_table_stride(k);
-        int64_t ctas = big_warp_ctas(B);
+        int64_t ctas = big_warp_ctas(B, k);
         if (!ws || ws_bytes < (size_t)ctas * tstride * big_warp_entry_bytes(k)) return cudaErrorInvalidValue;
         auto go = [&](auto kern, auto* tables) -> cudaError_t {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -667,7 +673,7 @@ static cudaError_t launch_decode_t(const void* v, int64_t B, int64_t k, void* ou
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem);
             if (e != cudaSuccess) return e;
             if (per_sm < 1) per_sm = 1;
-            if (per_sm > BIG_WARP_CTAS_PER_SM) per_sm = BIG_WARP_CTAS_PER_SM;
+            if (per_sm > big_warp_ctas_per_sm(k)) per_sm = big_warp_ctas_per_sm(k);
             const int64_t cap = (int64_t)sm_count() * per_sm;
             if (ctas > cap) ctas = cap;
             kern<<<(int)ctas, 32, smem, stream>>>((const IdxT*)v, B, (int)k, (IdxT*)out, out_stride, status, K, tables, tstride);
