@@ -363,6 +363,12 @@ def run_b200(args):
             newick = bench_newick(torch, lib, device, peak)
         except Exception as exc:
             newick = ({"error": repr(exc)},) * 3
+    round2 = {}
+    if rank == 0:
+        try:
+            round2 = bench_round2_rows(torch, device)
+        except Exception as exc:
+            round2 = {"round2_rows_error": repr(exc)}
 
     if rank == 0:
         cb_rate, cb_cores, cb_dt = cpu_baseline(np, CPU_SAMPLE)
@@ -403,7 +409,7 @@ def run_b200(args):
                                  "third is k+1+row); host threads of the library widen them into the caller's int64 rows",
                     "api": "p2v_to_ancestry_host (C ABI, pinned host buffers)", "matches_device_path": e2e_ok},
             "gpu_launches": launches, "clocks": clocks, "parity_spot_check": parity,
-            "config_c2_other_functions": c2, "cophenetic_c4": coph, "c3": c3, "next_rows": {"to_newick": newick[0], "from_newick": newick[1], "balance_indices": newick[2]},
+            "config_c2_other_functions": c2, "cophenetic_c4": coph, "c3": c3, "next_rows": {"to_newick": newick[0], "from_newick": newick[1], "balance_indices": newick[2], **round2},
         }
         print(json.dumps(line))
     if world > 1:
@@ -511,6 +517,79 @@ def bench_newick(torch, lib, device, peak):
                              np.all(np.abs(gotb[:, 2] - refb[:, 2]) <= 1e-12 * np.abs(refb[:, 2])))}
         del V, ws3, bal
     return res, res2, res3
+
+
+def bench_round2_rows(torch, device):
+    """The rows added in round 2 (SURVEY 8f-2 matrices, 8f-3 Robinson-Foulds, 8f-4 CSV): throughput through the
+    package's batched API (CUDA events) with the oracle on a small sample beside it.  First versions: these
+    numbers say where they stand, not what bounds them."""
+    import io as _io
+    import numpy as np
+    import phylo2vec_b200 as p2v
+    from oracle import p2v_oracle as O
+    from phylo2vec_b200.io import reader
+    out = {}
+    stream = torch.cuda.current_stream(device)
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            r = fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3, r
+
+    for n, B in ((100, 200_000), (1000, 20_000)):
+        k = n - 1
+        g = torch.Generator(device=device).manual_seed(7 * n)
+        hi = (2 * torch.arange(k, device=device) + 1).to(torch.float64)
+        V1 = (torch.rand((B, k), generator=g, device=device, dtype=torch.float64) * hi).to(torch.int64)
+        V2 = (torch.rand((B, k), generator=g, device=device, dtype=torch.float64) * hi).to(torch.int64)
+        t, rf = timed(lambda: p2v.robinson_foulds_batch(V1, V2, check=False))
+        ns = 200 if n == 100 else 20
+        v1, v2 = V1[:ns].cpu().numpy(), V2[:ns].cpu().numpy()
+        t0 = time.perf_counter()
+        ref = np.array([O.robinson_foulds(v1[i], v2[i]) for i in range(ns)])
+        tc = time.perf_counter() - t0
+        out.setdefault("robinson_foulds", {})[f"n{n}"] = {
+            "pairs": B, "pairs_per_s": B / t, "cpu": {"sample": ns, "pairs_per_s": ns / tc, "cores": 1, "kind": "port (numpy / Python sets)"},
+            "matches_cpu": bool(np.array_equal(rf[:ns].cpu().numpy(), ref))}
+        # matrices with branch lengths -> Newick strings -> matrices
+        Bm = B // 4
+        M = torch.empty((Bm, k, 3), dtype=torch.float64, device=device)
+        M[..., 0] = V1[:Bm].to(torch.float64)
+        M[..., 1:] = torch.rand((Bm, k, 2), generator=g, device=device, dtype=torch.float64)
+        t1, (buf, ln) = timed(lambda: p2v.to_newick_batch(M, check=False, raw=True))
+        t2, M2 = timed(lambda: p2v.to_matrix_batch(buf, lengths=ln, n_leaves=n, check=False))
+        s0 = bytes(buf[0, :int(ln[0])].cpu().numpy()).decode()
+        out.setdefault("matrix_newick", {})[f"n{n}"] = {
+            "trees": Bm, "to_newick_trees_per_s": Bm / t1, "from_newick_trees_per_s": Bm / t2,
+            "string_bytes_per_tree": float(ln.double().mean()), "round_trip_bit_equal": bool(torch.equal(M2, M)),
+            "first_string_matches_cpu": s0 == O.to_newick_matrix(M[0].cpu().numpy())}
+    # CSV: a file of vectors, one per line, parsed on the GPU
+    n, B = 1000, 20_000
+    k = n - 1
+    rng = np.random.default_rng(3)
+    Vh = (rng.random((B, k)) * (2 * np.arange(k) + 1)).astype(np.int64)
+    sio = _io.StringIO()
+    np.savetxt(sio, Vh, fmt="%d", delimiter=",")
+    text = sio.getvalue().encode()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        Vd = reader.load_batch(_io.BytesIO(text), kind="vector", device=device, check=False)
+    torch.cuda.synchronize()
+    tw = (time.perf_counter() - t0) / 3
+    t0 = time.perf_counter()
+    head = b"\n".join(text.split(b"\n", B // 20)[: B // 20])           # the first twentieth of the lines
+    np.loadtxt(_io.BytesIO(head), delimiter=",", dtype=np.int64)
+    tnp = (time.perf_counter() - t0) * 20
+    out["csv_load_batch"] = {"trees": B, "n_leaves": n, "file_bytes": len(text), "seconds_wall_incl_h2d": tw,
+                             "file_gbs": len(text) / tw / 1e9, "numpy_loadtxt_seconds_extrapolated": tnp,
+                             "equal": bool(np.array_equal(Vd.cpu().numpy(), Vh))}
+    return out
 
 
 def _evt_ms(torch, stream, fn, reps):
