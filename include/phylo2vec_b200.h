@@ -83,9 +83,8 @@ int p2v_to_edges_batch(const void *v, int idx_bytes, int64_t B, int64_t k, void 
  * (:129-136, build_cherries :399-440), from_edges (:201-213, order_cherries
  * :449-477) and build_vector (:320-337, Fenwick :286-316); PyO3 entry points
  * from_pairs / from_ancestry / from_edges (py-phylo2vec/src/lib.rs:113-136).
- * k <= 1024 needs no workspace; larger trees need p2v_encode_workspace_bytes(B,k) bytes of
- * device scratch.  For k > 1024 the row v[tree] is also used as scratch while the tree is
- * encoded: a tree flagged P2V_TREE_MALFORMED leaves unspecified values there. */
+ * k < 800 needs no workspace; larger trees need p2v_encode_workspace_bytes(B,k) bytes of
+ * device scratch.  A tree flagged P2V_TREE_MALFORMED leaves unspecified values in its row of v. */
 size_t p2v_encode_workspace_bytes(int64_t B, int64_t k);
 int p2v_from_pairs_batch(const void *pairs, int idx_bytes, int64_t B, int64_t k, void *v,
                          int32_t *status, void *workspace, size_t workspace_bytes,

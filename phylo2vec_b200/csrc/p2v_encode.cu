@@ -519,17 +519,15 @@ static int enc_large_grid(int64_t B) {
 
 // ---- the light warp kernel (p2v_encode_light.cuh): shape of a launch, shared by the workspace query ----
 struct LightPlan { int warps, per_sm, K; bool gt; size_t smem, ws_words; };
-static int enc_light_from() {               // smallest k that takes the light kernel (P2V_ENC_LIGHT_FROM to experiment)
-    static const int v = [] { const char* e = getenv("P2V_ENC_LIGHT_FROM"); return e ? atoi(e) : 1025; }();
+static int enc_light_from() {               // smallest k that takes the light kernel: measured +7 % at k = 999, -3 % at 511
+                                            // against encode_small_kernel (P2V_ENC_LIGHT_FROM to experiment)
+    static const int v = [] { const char* e = getenv("P2V_ENC_LIGHT_FROM"); return e ? atoi(e) : 800; }();
     return v;
 }
 static int enc_env(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 static int enc_light_tsmem() { static const int v = enc_env("P2V_ENC_TSMEM", ENC_LIGHT_T_SMEM_K_MAX); return v; }
 static int enc_light_gt_per_sm() { static const int v = enc_env("P2V_ENC_GT_PERSM", 16); return v; }
-// idx_bytes = 0: any index width (the workspace query does not know it; the wide form's slices are the bigger ones)
-static bool enc_light(int64_t k, int idx_bytes = 0) {
-    return k >= enc_light_from() && (k <= ENC_LIGHT_K_MAX || (k <= ENC_LIGHT_WIDE_K_MAX && idx_bytes != 4));
-}
+static bool enc_light(int64_t k) { return k >= enc_light_from() && k <= ENC_LIGHT_WIDE_K_MAX; }
 static LightPlan enc_light_plan(int64_t k) {
     LightPlan p;
     p.K = (int)((k + 31) & ~31);
@@ -552,10 +550,7 @@ size_t encode_workspace_bytes(int64_t B, int64_t k) {
     if (enc_light(k)) {
         const LightPlan p = enc_light_plan(k);
         const int64_t want = (B + p.warps - 1) / p.warps, cap = (int64_t)sm_count() * p.per_sm;
-        const size_t light = (size_t)(want < cap ? want : cap) * p.warps * p.ws_words * sizeof(uint32_t);
-        if (k <= ENC_LIGHT_K_MAX) return light;
-        const size_t large = (size_t)enc_large_grid(B) * enc_large_stride(k) * sizeof(uint32_t);   // int32 input: CTA kernel
-        return light > large ? light : large;
+        return (size_t)(want < cap ? want : cap) * p.warps * p.ws_words * sizeof(uint32_t);
     }
     if (k <= ENC_SMALL_K_MAX) return 0;
     return (size_t)enc_large_grid(B) * enc_large_stride(k) * sizeof(uint32_t);
@@ -584,8 +579,8 @@ static cudaError_t launch_encode_light(const void* in, int64_t B, int64_t k, voi
 template <typename IdxT, int MODE>
 static cudaError_t launch_encode_t(const void* in, int64_t B, int64_t k, void* v, int32_t* status,
                                    void* ws, size_t ws_bytes, cudaStream_t stream) {
-    if (enc_light(k, (int)sizeof(IdxT))) {
-        if (k > ENC_LIGHT_K_MAX) return launch_encode_light<IdxT, MODE, true, sizeof(IdxT) == 8>(in, B, k, v, status, ws, ws_bytes, stream);
+    if (enc_light(k)) {
+        if (k > ENC_LIGHT_K_MAX) return launch_encode_light<IdxT, MODE, true, true>(in, B, k, v, status, ws, ws_bytes, stream);
         return k > enc_light_tsmem() ? launch_encode_light<IdxT, MODE, true>(in, B, k, v, status, ws, ws_bytes, stream)
                                      : launch_encode_light<IdxT, MODE, false>(in, B, k, v, status, ws, ws_bytes, stream);
     }

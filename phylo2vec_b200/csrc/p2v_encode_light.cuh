@@ -8,13 +8,15 @@
 //    while that row's batch is in flight, the label's smallest descendant leaf once the row has fired
 //    (round 1 kept the defining row and the smallest descendant in two tables, plus both relabelled
 //    children and the parent of every row: 10 bytes per leaf);
-//  * when a row fires, its cherry (c_min, c_max) is final: the permutation check on c_max happens there and
-//    the word  row | c_min << 16  is PARKED at index c_max - 1 in the tree's own output row -- build_vector
-//    walks the values upwards and reads exactly that, two batches ahead of the v entries it overwrites
-//    (int64 output: words k .. 2k of the row, the write pointer never passes the read pointer; int32 output:
-//    word c - 1 is read by the lane that then overwrites it);
-//  * the "rows seen" mask is k bits; every lane keeps the count of the mask words it owns, so the prefix
-//    count of a row is a warp scan, a walk over at most WPL words of the owner, and one partial word.
+//  * build_vector needs, for the cherry of every row, idx = #{earlier rows with a smaller c_max}.  Round 1 walked
+//    the VALUES upwards over a "rows seen" mask, which needs the rows sorted by c_max first (a table, or the
+//    (row, c_min) words a first version of this kernel parked in the output row and read back).  The same count
+//    taken in ROW order needs nothing of the kind: it is the number of c_max values already seen below this
+//    one -- a prefix count on a "values seen" mask -- plus the lower lanes of the batch with a smaller c_max.
+//    So a row's v entry is final when its cherry is: ONE pass over the rows, v[c_max - 1] stored from there
+//    (scattered; a tree's output row stays in L2 until complete), and the mask doubles as the permutation check;
+//  * the mask is k bits; every lane keeps the count of the mask words it owns, so the prefix count is a warp
+//    scan, a walk over at most WPL words of the owner, and one partial word.
 //
 // from_edges scatters (c1, c2) by parent first (order_cherries) into a workspace slice and then runs the same
 // sweep over that table.  Above T_SMEM_K_MAX the table T moves to the workspace as 32-bit entries.
@@ -27,8 +29,8 @@
 
 namespace p2v {
 
-constexpr int ENC_LIGHT_K_MAX = 65535;       // row and c_min share one parked 32-bit word
-constexpr int ENC_LIGHT_WIDE_K_MAX = 262143; // int64 output: a parked 64-bit word per value IS the output row; 32 KB of mask
+constexpr int ENC_LIGHT_K_MAX = 65535;       // c_max values of two batches share a shuffle (16-bit fields) up to here
+constexpr int ENC_LIGHT_WIDE_K_MAX = 262143; // above: a shuffle per batch (WIDE); 32 KB of mask per tree at the end
 constexpr int ENC_LIGHT_T_SMEM_K_MAX = 32767;   // table in shared memory (uint16) up to here: 66 KB, three trees per SM
 
 __host__ __device__ inline int enc_light_wpl(int K) {   // mask words per lane: a power of two >= 4
@@ -70,8 +72,7 @@ template <> struct EncTable<true> {
 
 __device__ __forceinline__ uint32_t popc4(const uint4 q) { return __popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w); }
 
-// WIDE (k > 65535, int64 output, table in the workspace): row and c_min take 32 bits each of a 64-bit parked word,
-// which sits exactly where v[c_max - 1] will go (the lane that reads it writes it).
+// WIDE (k > 65535, table in the workspace): the in-batch counts take one shuffle per batch and step.
 template <typename IdxT, int MODE, bool GT, bool WIDE = false>
 __global__ void __launch_bounds__(128)
 encode_light_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restrict__ vout,
@@ -98,8 +99,6 @@ encode_light_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
     for (int64_t tree = (int64_t)blockIdx.x * nwarps + warp; tree < B; tree += (int64_t)gridDim.x * nwarps) {
         const IdxT* it = in + tree * ((int64_t)k * in_cols);
         IdxT* vo = vout + tree * k;
-        uint32_t* park = reinterpret_cast<uint32_t*>(vo) + ((sizeof(IdxT) == 8 && !WIDE) ? k : 0);
-        unsigned long long* park64 = reinterpret_cast<unsigned long long*>(vo);      // WIDE only
         bool bad = false;
         for (int j = 0; j < wpl; ++j) mask[lane * wpl + j] = 0;
         lcs[lane] = 0;
@@ -157,7 +156,13 @@ encode_light_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
             __syncwarp();
         }
 
-        // ---- rows in order: relabel by smallest descendant (build_cherries), park (row, c_min) by c_max ----
+        // ---- ONE pass over the rows, in order, two batches at a time: relabel by smallest descendant
+        //      (build_cherries), then build_vector's index of the cherry right away --
+        //          idx = #{earlier rows with a smaller c_max}
+        //      = the c_max values already seen that lie below this one (prefix count on the "values seen" mask,
+        //      state before the batch) + the lower lanes of the batch with a smaller c_max; v[c_max - 1] is stored
+        //      from here (a scattered store: a tree's output row stays in L2 until it is complete).  The same
+        //      mask is the permutation check: a value seen twice is a malformed tree.
         if (!bad) {
             long long rcur[3], rnxt[3];
             auto issue = [&](int b, long long (&r)[3]) {
@@ -176,7 +181,8 @@ encode_light_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
             };
             issue(0, rcur);
             issue(1, rnxt);
-            for (int b = 0; b < nb; ++b) {
+            // one batch of rows through build_cherries: (c_max - 1, c_min) of the lane's row; false = malformed (uniform)
+            auto cherries = [&](int b, uint32_t& vmax, uint32_t& vmin) -> bool {
                 const int s = b * 32 + lane;
                 const bool act = s < k;
                 const long long a = rcur[0], c = rcur[1], pl = rcur[2];
@@ -197,7 +203,7 @@ encode_light_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                     }
                     __syncwarp();
                     if (live && T.get(pi) != NONE - 1 - (uint32_t)lane) ok = false;    // ... or another one in this batch
-                    if (!__all_sync(FULL, ok || !act)) { bad = true; break; }
+                    if (!__all_sync(FULL, ok || !act)) return false;
                     int j1 = -1, j2 = -1;                          // lanes this row waits for
                     if (act) {
                         if (c1 >= kint) {
@@ -251,113 +257,84 @@ encode_light_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                         __syncwarp();
                         done |= Rm;
                     }
-                } else if (!__all_sync(FULL, ok || !act)) { bad = true; break; }
-                if (act) {
-                    const uint32_t cm = max(m1, m2), lo = min(m1, m2);
-                    if (cm < 1 || cm > (uint32_t)k) bad = true;
-                    else {
-                        const uint32_t bit = 1u << ((cm - 1) & 31);
-                        P2V_CHECK_INDEX((cm - 1) >> 5, 32 * wpl);
-                        if (atomicOr(&mask[(cm - 1) >> 5], bit) & bit) bad = true;      // c_max must be a permutation
-                        if (WIDE) __stcg(park64 + (cm - 1), (unsigned long long)(uint32_t)s | ((unsigned long long)lo << 32));
-                        else __stcg(park + (cm - 1), (uint32_t)s | (lo << 16));
+                } else if (!__all_sync(FULL, ok || !act)) return false;
+                const uint32_t cm = max(m1, m2);
+                vmin = min(m1, m2);
+                vmax = cm - 1u;
+                return __all_sync(FULL, !act || (cm >= 1u && cm <= (uint32_t)k));
+            };
+            for (int bp = 0; bp < nb; bp += 2) {
+                uint32_t va = 0, la = 0, vb = 0, lb = 0;               // c_max - 1 and c_min of the lane's rows
+                if (!cherries(bp, va, la)) { bad = true; break; }
+                if (bp + 1 < nb && !cherries(bp + 1, vb, lb)) { bad = true; break; }
+                const bool act_a = bp * 32 + lane < k, act_b = (bp + 1) * 32 + lane < k;
+                uint32_t inb_a = 0, inb_b = 0;                           // lower lanes of the batch with a smaller c_max
+                if (WIDE) {                                              // values of up to 18 bits: a shuffle per batch and step
+                    const uint32_t ka = act_a ? va : 0x7FFFFFFFu, kb = act_b ? vb : 0x7FFFFFFFu;
+#pragma unroll
+                    for (int d = 1; d < 32; ++d) {
+                        count_smaller_step(inb_a, ka, d);
+                        count_smaller_step(inb_b, kb, d);
                     }
+                } else if (K <= 32768) {
+                    // 15-bit values: both batches compared by ONE subtraction per step.  Field f of (M - y) keeps bit 15
+                    // iff mine_f - 1 >= y_f (no borrow crosses a field: 0x8000 + mine_f - 1 - y_f >= 0).
+                    const uint32_t ya = act_a ? va : 0x7FFFu, yb = act_b ? vb : 0x7FFFu;
+                    const uint32_t packed = ya | (yb << 16);
+                    const uint32_t M = (ya + 0x7FFFu) | ((yb + 0x7FFFu) << 16);
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int d = 1; d < 32; ++d) {
+                        const uint32_t y = __shfl_up_sync(FULL, packed, d);    // below lane d: the lane's own value
+                        acc += ((M - y) >> 15) & 0x00010001u;
+                    }
+                    inb_a = acc & 0xFFFFu; inb_b = acc >> 16;
+                } else {
+                    const uint32_t ka = act_a ? va : 0xFFFFu, kb = act_b ? vb : 0xFFFFu;
+                    const uint32_t packed = ka | (kb << 16);
+#pragma unroll
+                    for (int d = 1; d < 32; ++d) {
+                        const uint32_t y = __shfl_up_sync(FULL, packed, d);
+                        inb_a += ((y & 0xFFFFu) < ka);
+                        inb_b += ((y >> 16) < kb);
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const bool act = h ? act_b : act_a;
+                    const uint32_t val = act ? (h ? vb : va) : 0u;
+                    const uint32_t lo = h ? lb : la;
+                    const uint32_t cnt = lcs[lane];
+                    const uint32_t excl = warp_incl_scan(cnt, lane) - cnt;
+                    const uint32_t g = val >> 5, src = g >> wsh;
+                    P2V_CHECK_INDEX(g, 32 * wpl); P2V_CHECK_INDEX(src, 32);
+                    uint32_t idx = __shfl_sync(FULL, excl, src) + (h ? inb_b : inb_a);
+                    const uint4* q = reinterpret_cast<const uint4*>(mask + ((size_t)src << wsh));
+                    const int nq = (int)(g - (src << wsh)) >> 2;
+                    for (int j = 0; j < nq; ++j) idx += popc4(q[j]);
+                    const uint32_t bit = 1u << (val & 31);
+                    {
+                        const uint4 t = q[nq];
+                        const uint32_t jj = g & 3u, low = bit - 1u;
+                        const uint32_t e0 = t.x, e1 = t.y, e2 = t.z, e3 = t.w;
+                        idx += jj == 0 ? __popc(e0 & low)
+                             : jj == 1 ? __popc(e0) + __popc(e1 & low)
+                             : jj == 2 ? __popc(e0) + __popc(e1) + __popc(e2 & low)
+                                       : __popc(e0) + __popc(e1) + __popc(e2) + __popc(e3 & low);
+                    }
+                    __syncwarp();                                        // every lane has read the mask
+                    if (act) {
+                        vo[val] = (IdxT)(idx == 0 ? lo : val + idx);
+                        if (atomicOr(&mask[g], bit) & bit) bad = true;   // c_max must be a permutation of 1 .. k
+                        atomicAdd(&lcs[src], 1u);
+                    }
+                    __syncwarp();
                 }
             }
         }
         bad = __any_sync(FULL, bad);
         __syncwarp();
         if (lane == 0 && status) status[tree] = bad ? TREE_MALFORMED : 0;
-        if (bad) continue;
-        for (int j = 0; j < wpl; ++j) mask[lane * wpl + j] = 0;
-        __syncwarp();
-
-        // ---- build_vector: values ascending, two batches per in-batch count -----------------------------
-        using ParkT = typename std::conditional<WIDE, unsigned long long, uint32_t>::type;
-        ParkT wcur[2], wnxt[2];
-        auto fetch = [&](int bp, ParkT (&w)[2]) {
-            const int ca = bp * 32 + lane + 1, cb = ca + 32;
-            if (WIDE) {
-                w[0] = (ca <= k) ? (ParkT)__ldcg(park64 + (ca - 1)) : (ParkT)0;
-                w[1] = (cb <= k) ? (ParkT)__ldcg(park64 + (cb - 1)) : (ParkT)0;
-            } else {
-                w[0] = (ca <= k) ? (ParkT)__ldcg(park + (ca - 1)) : (ParkT)0;
-                w[1] = (cb <= k) ? (ParkT)__ldcg(park + (cb - 1)) : (ParkT)0;
-            }
-        };
-        fetch(0, wcur);
-        fetch(2, wnxt);
-        for (int bp = 0; bp < nb; bp += 2) {
-            const int ca = bp * 32 + lane + 1, cb = ca + 32;
-            const bool act_a = ca <= k, act_b = cb <= k;
-            const ParkT wa = wcur[0], wb = wcur[1];
-            wcur[0] = wnxt[0]; wcur[1] = wnxt[1];
-            fetch(bp + 4, wnxt);
-            const uint32_t ra = WIDE ? (uint32_t)wa : ((uint32_t)wa & 0xFFFFu), rb = WIDE ? (uint32_t)wb : ((uint32_t)wb & 0xFFFFu);
-            const uint32_t loa = WIDE ? (uint32_t)((unsigned long long)wa >> 32) : ((uint32_t)wa >> 16);
-            const uint32_t lob = WIDE ? (uint32_t)((unsigned long long)wb >> 32) : ((uint32_t)wb >> 16);
-            const uint32_t ka = act_a ? ra : (WIDE ? 0x7FFFFFFFu : 0xFFFFu), kb = act_b ? rb : (WIDE ? 0x7FFFFFFFu : 0xFFFFu);
-            uint32_t inb_a = 0, inb_b = 0;
-            if (WIDE) {                          // rows of 18 bits: one shuffle per batch and step
-#pragma unroll
-                for (int d = 1; d < 32; ++d) {
-                    count_smaller_step(inb_a, ka, d);
-                    count_smaller_step(inb_b, kb, d);
-                }
-            } else if (K <= 32768) {
-                // rows have 15 bits: both halves compared by ONE subtraction.  Field f of (M - y) keeps bit 15
-                // iff mine_f - 1 >= y_f (no borrow crosses a field: 0x8000 + mine_f - 1 - y_f >= 0).
-                const uint32_t ya = act_a ? ra : 0x7FFFu, yb = act_b ? rb : 0x7FFFu;
-                const uint32_t packed = ya | (yb << 16);
-                const uint32_t M = (ya + 0x7FFFu) | ((yb + 0x7FFFu) << 16);
-                uint32_t acc = 0;
-#pragma unroll
-                for (int d = 1; d < 32; ++d) {
-                    const uint32_t y = __shfl_up_sync(FULL, packed, d);    // below lane d: the lane's own value
-                    acc += ((M - y) >> 15) & 0x00010001u;
-                }
-                inb_a = acc & 0xFFFFu; inb_b = acc >> 16;
-            } else {
-                const uint32_t packed = ka | (kb << 16);
-#pragma unroll
-                for (int d = 1; d < 32; ++d) {
-                    const uint32_t y = __shfl_up_sync(FULL, packed, d);
-                    inb_a += ((y & 0xFFFFu) < ka);
-                    inb_b += ((y >> 16) < kb);
-                }
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c = h ? cb : ca;
-                const bool act = h ? act_b : act_a;
-                const uint32_t r = h ? rb : ra;
-                const uint32_t lo = h ? lob : loa;
-                const uint32_t cnt = lcs[lane];
-                const uint32_t excl = warp_incl_scan(cnt, lane) - cnt;
-                const uint32_t g = r >> 5, src = g >> wsh;
-                P2V_CHECK_INDEX(g, 32 * wpl); P2V_CHECK_INDEX(src, 32);
-                uint32_t idx = __shfl_sync(FULL, excl, src) + (h ? inb_b : inb_a);
-                const uint4* q = reinterpret_cast<const uint4*>(mask + ((size_t)src << wsh));
-                const int nq = (int)(g - (src << wsh)) >> 2;
-                for (int j = 0; j < nq; ++j) idx += popc4(q[j]);
-                {
-                    const uint4 t = q[nq];
-                    const uint32_t jj = g & 3u, low = (1u << (r & 31)) - 1u;
-                    const uint32_t e0 = t.x, e1 = t.y, e2 = t.z, e3 = t.w;
-                    idx += jj == 0 ? __popc(e0 & low)
-                         : jj == 1 ? __popc(e0) + __popc(e1 & low)
-                         : jj == 2 ? __popc(e0) + __popc(e1) + __popc(e2 & low)
-                                   : __popc(e0) + __popc(e1) + __popc(e2) + __popc(e3 & low);
-                }
-                __syncwarp();
-                if (act) {
-                    vo[c - 1] = (IdxT)(idx == 0 ? lo : (uint32_t)(c - 1) + idx);
-                    atomicOr(&mask[g], 1u << (r & 31));
-                    atomicAdd(&lcs[src], 1u);
-                }
-                __syncwarp();
-            }
-        }
         __syncwarp();
     }
 }
