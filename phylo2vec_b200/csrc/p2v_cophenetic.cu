@@ -41,6 +41,7 @@
 #include <cooperative_groups.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "p2v_decode_warp.cuh"
 
@@ -1432,7 +1433,72 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
             __syncthreads();
         }
         if (!TILED) {
-        // ---- 4. rows ------------------------------------------------------------------------------
+        // ---- 4. rows: every lane owns pairs of columns in LABEL order, (j, j + 1) with j = 64 lc + 2 lane, keeps
+        //      their DFS positions (and, for n <= 128, their double-double depths) in registers for all the rows
+        //      of its warp, answers one sparse-table query per element and stores whole 16-byte pairs.  (Round 1
+        //      built each row in DFS order in shared memory and permuted it on the way out: 25 trips through
+        //      the shared-memory pipe per 32 elements -- the pipe ran at 87 % -- against 11 now.) -----------
+        auto rows_direct = [&](auto lc_tag, auto cache_tag) {
+            constexpr int LC = decltype(lc_tag)::value;
+            constexpr bool CACHE = decltype(cache_tag)::value;
+            uint32_t cpos[LC], cdi[LC];
+            double2 cd0[CACHE ? LC : 1], cd1[CACHE ? LC : 1];
+#pragma unroll
+            for (int lc = 0; lc < LC; ++lc) {
+                const int j = 64 * lc + 2 * lane;
+                cpos[lc] = 0; cdi[lc] = 0;
+                if (CACHE) { cd0[lc] = make_double2(0.0, 0.0); cd1[lc] = cd0[lc]; }
+                if (j < n) {
+                    const uint32_t pp = *reinterpret_cast<const uint32_t*>(pos + j);   // pos is padded to even n
+                    const uint32_t p0 = pp & 0xFFFFu, p1 = (j + 1 < n) ? (pp >> 16) : p0;
+                    cpos[lc] = p0 | (p1 << 16);
+                    cdi[lc] = (uint32_t)dipos[p0] | ((uint32_t)dipos[p1] << 16);
+                    if (!TOPO && CACHE) { cd0[lc] = ddpos[p0]; cd1[lc] = ddpos[p1]; }
+                }
+            }
+            double* orow = out + ((size_t)tree * rows + warp) * n;
+            const int i_end = (int)row_end;
+            for (int i = (int)row_begin + warp; i < i_end; i += NW, orow += (size_t)NW * n) {
+                const int q = pos[i];
+                const int di = dipos[q];
+                double2 dq = make_double2(0.0, 0.0);
+                if (!TOPO) dq = ddpos[q];
+                auto element = [&](int p, int dj_i, double2 dj) -> double {
+                    if (p == q) return VCV ? (TOPO ? int_to_f64(di) : dq.x) : 0.0;
+                    const int a = min(p, q) + 1, b = max(p, q);
+                    const int lev = 31 - __clz(b - a + 1);
+                    const uint32_t m = min(st[lev * stn + a], st[lev * stn + b - (1 << lev) + 1]);
+                    if (TOPO) {
+                        const int dlca = (int)(m >> 16);
+                        return VCV ? int_to_f64(dlca) : int_to_f64(di + dj_i - 2 * dlca);
+                    }
+                    const double2 sd = sepd[m & 0xFFFFu];
+                    if (VCV) return sd.x;
+                    return __dadd_rn(dd_sub_round(dq.x, dq.y, sd.x, sd.y), dd_sub_round(dj.x, dj.y, sd.x, sd.y));
+                };
+#pragma unroll
+                for (int lc = 0; lc < LC; ++lc) {
+                    const int j = 64 * lc + 2 * lane;
+                    if (j < n) {
+                        const int p0 = (int)(cpos[lc] & 0xFFFFu), p1 = (int)(cpos[lc] >> 16);
+                        double2 d0 = make_double2(0.0, 0.0), d1 = d0;
+                        if (!TOPO && !VCV) {
+                            if (CACHE) { d0 = cd0[lc]; d1 = cd1[lc]; }
+                            else { d0 = ddpos[p0]; d1 = ddpos[p1]; }
+                        }
+                        const double v0 = element(p0, (int)(cdi[lc] & 0xFFFFu), d0);
+                        const double v1 = element(p1, (int)(cdi[lc] >> 16), d1);
+                        if (j + 1 < n) store2<VEC2>(orow + j, v0, v1);
+                        else __stcs(orow + j, v0);
+                    }
+                }
+            }
+        };
+        if (n > 128) rows_direct(std::integral_constant<int, CS_MAXLC>{}, std::false_type{});
+        else if (n > 40) rows_direct(std::integral_constant<int, 2>{}, std::true_type{});
+        else {
+        // tiny trees (a pair of columns per lane leaves most lanes idle): the round-1 form, each row built in DFS
+        // order in shared memory, one position per lane, and permuted on the way out
         double* orow = out + ((size_t)tree * rows + warp) * n;
         const int i_end = (int)row_end;
         for (int i = (int)row_begin + warp; i < i_end; i += NW, orow += (size_t)NW * n) {
@@ -1477,6 +1543,7 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
                 for (int j = lane; j < n; j += 32) __stcs(orow + j, rowbuf[pos[j]]);
             }
             __syncwarp();
+        }
         }
         } else {
         // ---- 4. rows, a tile of 32 consecutive DFS positions per warp ---------------------------------
