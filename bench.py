@@ -286,12 +286,18 @@ def run_b200(args):
             del o
         anc_s = out[:Bs]
         vb = torch.empty((Bs, K), dtype=torch.int64, device=device)
-        ms = timed(lambda: lib.p2v_from_ancestry_batch(anc_s.data_ptr(), 8, Bs, K, vb.data_ptr(), status.data_ptr(), None, 0,
-                                                       stream.cuda_stream))
+        need_enc = int(lib.p2v_encode_workspace_bytes(Bs, K))
+        ws_enc = torch.empty(max(need_enc, 16), dtype=torch.uint8, device=device)
+
+        def enc_call():
+            rc = lib.p2v_from_ancestry_batch(anc_s.data_ptr(), 8, Bs, K, vb.data_ptr(), status.data_ptr(), ws_enc.data_ptr(),
+                                             need_enc, stream.cuda_stream)
+            assert rc == 0, lib.p2v_last_error()
+        ms = timed(enc_call)
         c2["from_ancestry"] = {"trees_per_s": Bs / (ms * 1e-3), "gbs": 4 * K * 8 * Bs / (ms * 1e-3) / 1e9,
                                "round_trip_equal": bool(torch.equal(vb, Vs))}
         c2["batch"] = Bs
-        del vb
+        del vb, ws_enc
 
     # ---- end to end: host buffers through the C ABI (H2D + kernels + D2H in the timed region) ----
     # The same per-GPU batch at every N, --steps timed steps; the staging of the host entry points is
