@@ -50,10 +50,21 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def _stale_dbg() -> bool:
+    if not os.path.exists(LIB_DBG):
+        return True
+    t = os.path.getmtime(LIB_DBG)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False, debug_bounds: bool = False) -> str:
     """Every source is compiled to its own object file (in parallel, only the stale ones) and the
-    objects are linked into the shared library."""
-    if not force and not _stale():
+    objects are linked into the shared library.  debug_bounds: also libphylo2vec_b200_dbg.so -- DBG_SOURCES
+    compiled once more with -DP2V_DEBUG_BOUNDS (in the same pool), linked with the ordinary objects of the rest."""
+    need_main = force or _stale()
+    need_dbg = debug_bounds and (force or need_main or _stale_dbg())
+    if not need_main and not need_dbg:
         return LIB
     from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIBDIR, exist_ok=True)
@@ -66,18 +77,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     compile_flags = [f for f in NVCC_FLAGS if f != "--shared"]
 
-    def one(src):
-        obj = os.path.join(objdir, os.path.splitext(src)[0] + (("." + tag) if tag else "") + ".o")
+    def one(job):
+        src, dbg = job
+        suffix = ".dbg" if dbg else ((("." + tag) if tag else ""))
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + suffix + ".o")
         path = os.path.join(CSRC, src)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(hdr_t, os.path.getmtime(path)):
             return obj, None
-        cmd = [nvcc] + compile_flags + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, path]
+        flags = compile_flags + (["-DP2V_DEBUG_BOUNDS"] if dbg else extra)
+        cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, path]
         if verbose:
             print(" ".join(cmd))
         return obj, subprocess.run(cmd, capture_output=True, text=True)
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        results = list(ex.map(one, SOURCES))
+    jobs = [(s, False) for s in SOURCES] + ([(s, True) for s in DBG_SOURCES] if need_dbg else [])
+    with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+        results = list(ex.map(one, jobs))
     for obj, r in results:
         if r is None:
             continue
@@ -85,45 +100,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(r.stdout + r.stderr)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed building libphylo2vec_b200.so")
-    r = subprocess.run([nvcc, "--shared", "-o", LIB] + [o for o, _ in results] + ["-lpthread"],
-                       capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed linking libphylo2vec_b200.so")
+    main_objs = [o for (o, _), (_, dbg) in zip(results, jobs) if not dbg]
+    if need_main:
+        r = subprocess.run([nvcc, "--shared", "-o", LIB] + main_objs + ["-lpthread"], capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed linking libphylo2vec_b200.so")
+    if need_dbg:
+        dbg_objs = [o for (o, _), (_, dbg) in zip(results, jobs) if dbg]
+        rest = [o for o, (s, dbg) in zip(main_objs, [j for j in jobs if not j[1]]) if s not in DBG_SOURCES]
+        r = subprocess.run([nvcc, "--shared", "-o", LIB_DBG] + dbg_objs + rest + ["-lpthread"], capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed linking libphylo2vec_b200_dbg.so")
     return LIB
 
 
 def build_debug_bounds(force: bool = False) -> str:
-    """libphylo2vec_b200_dbg.so: DBG_SOURCES with -DP2V_DEBUG_BOUNDS, everything else from the ordinary objects."""
-    build(force=False)
-    objdir = os.path.join(HERE, "build")
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    if not force and os.path.exists(LIB_DBG) and all(os.path.getmtime(d) < os.path.getmtime(LIB_DBG) for d in deps):
-        return LIB_DBG
-    from concurrent.futures import ThreadPoolExecutor
-    nvcc = _nvcc()
-    compile_flags = [f for f in NVCC_FLAGS if f != "--shared"] + ["-DP2V_DEBUG_BOUNDS"]
-
-    def one(src):
-        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".dbg.o")
-        return obj, subprocess.run([nvcc] + compile_flags + ["-c", "-o", obj, os.path.join(CSRC, src)],
-                                   capture_output=True, text=True)
-
-    with ThreadPoolExecutor(max_workers=len(DBG_SOURCES)) as ex:
-        results = list(ex.map(one, DBG_SOURCES))
-    for _, r in results:
-        if r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
-            raise RuntimeError("nvcc failed building libphylo2vec_b200_dbg.so")
-    objs = [o for o, _ in results] + [os.path.join(objdir, os.path.splitext(s)[0] + ".o") for s in SOURCES if s not in DBG_SOURCES]
-    r = subprocess.run([nvcc, "--shared", "-o", LIB_DBG] + objs + ["-lpthread"], capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed linking libphylo2vec_b200_dbg.so")
+    build(force=force, debug_bounds=True)
     return LIB_DBG
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
-    if "--debug-bounds" in sys.argv:
-        print(build_debug_bounds(force="--force" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, debug_bounds="--debug-bounds" in sys.argv))
