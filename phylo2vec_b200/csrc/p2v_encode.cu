@@ -569,7 +569,9 @@ static cudaError_t launch_encode_light(const void* in, int64_t B, int64_t k, voi
     const int per_sm = occ < 1 ? 1 : (occ < p.per_sm ? occ : p.per_sm);
     const int64_t want = (B + p.warps - 1) / p.warps, cap = (int64_t)sm_count() * per_sm;
     const int grid = (int)(want < cap ? want : cap);
-    if (!ws || ws_bytes < (size_t)grid * p.warps * p.ws_words * sizeof(uint32_t)) return cudaErrorInvalidValue;
+    // the workspace holds from_edges' (c1, c2) table and the label table when that is not in shared memory
+    const bool needs_ws = (MODE == FROM_EDGES) || GT;
+    if (needs_ws && (!ws || ws_bytes < (size_t)grid * p.warps * p.ws_words * sizeof(uint32_t))) return cudaErrorInvalidValue;
     kern<<<grid, p.warps * 32, p.smem, stream>>>((const IdxT*)in, B, (int)k, (IdxT*)v, status, p.K, (uint32_t*)ws,
                                                  p.ws_words);
     count_launch();
@@ -579,7 +581,9 @@ static cudaError_t launch_encode_light(const void* in, int64_t B, int64_t k, voi
 template <typename IdxT, int MODE>
 static cudaError_t launch_encode_t(const void* in, int64_t B, int64_t k, void* v, int32_t* status,
                                    void* ws, size_t ws_bytes, cudaStream_t stream) {
-    if (enc_light(k)) {
+    // below enc_light_from() the light kernel is still the faster one (+2 ... 14 %), but from_edges would need a
+    // workspace there, which the interface promises not to ask for: that mode stays on the round-1 kernel
+    if (enc_light(k) || (MODE != FROM_EDGES && k < enc_light_from())) {
         if (k > ENC_LIGHT_K_MAX) return launch_encode_light<IdxT, MODE, true, true>(in, B, k, v, status, ws, ws_bytes, stream);
         return k > enc_light_tsmem() ? launch_encode_light<IdxT, MODE, true>(in, B, k, v, status, ws, ws_bytes, stream)
                                      : launch_encode_light<IdxT, MODE, false>(in, B, k, v, status, ws, ws_bytes, stream);

@@ -263,6 +263,7 @@ encode_light_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                 vmax = cm - 1u;
                 return __all_sync(FULL, !act || (cm >= 1u && cm <= (uint32_t)k));
             };
+            uint32_t word1 = 0;                                        // K <= 1024: mask word `lane`
             for (int bp = 0; bp < nb; bp += 2) {
                 uint32_t va = 0, la = 0, vb = 0, lb = 0;               // c_max - 1 and c_min of the lane's rows
                 if (!cherries(bp, va, la)) { bad = true; break; }
@@ -304,15 +305,31 @@ encode_light_kernel(const IdxT* __restrict__ in, int64_t B, int k, IdxT* __restr
                     const bool act = h ? act_b : act_a;
                     const uint32_t val = act ? (h ? vb : va) : 0u;
                     const uint32_t lo = h ? lb : la;
+                    const uint32_t g = val >> 5;
+                    const uint32_t bit = 1u << (val & 31);
+                    uint32_t idx = h ? inb_b : inb_a;
+                    if (K <= 1024) {
+                        // at most 32 mask words: lane l keeps word l in a register -- its popcount is the lane's count, the
+                        // word a value falls into comes by one shuffle, and there is nothing to walk
+                        const uint32_t cnt = __popc(word1);
+                        const uint32_t excl = warp_incl_scan(cnt, lane) - cnt;
+                        idx += __shfl_sync(FULL, excl, g) + __popc(__shfl_sync(FULL, word1, g) & (bit - 1u));
+                        if (act) {
+                            vo[val] = (IdxT)(idx == 0 ? lo : val + idx);
+                            if (atomicOr(&mask[g], bit) & bit) bad = true;   // c_max must be a permutation of 1 .. k
+                        }
+                        __syncwarp();
+                        word1 = mask[lane];
+                        continue;
+                    }
                     const uint32_t cnt = lcs[lane];
                     const uint32_t excl = warp_incl_scan(cnt, lane) - cnt;
-                    const uint32_t g = val >> 5, src = g >> wsh;
+                    const uint32_t src = g >> wsh;
                     P2V_CHECK_INDEX(g, 32 * wpl); P2V_CHECK_INDEX(src, 32);
-                    uint32_t idx = __shfl_sync(FULL, excl, src) + (h ? inb_b : inb_a);
+                    idx += __shfl_sync(FULL, excl, src);
                     const uint4* q = reinterpret_cast<const uint4*>(mask + ((size_t)src << wsh));
                     const int nq = (int)(g - (src << wsh)) >> 2;
                     for (int j = 0; j < nq; ++j) idx += popc4(q[j]);
-                    const uint32_t bit = 1u << (val & 31);
                     {
                         const uint4 t = q[nq];
                         const uint32_t jj = g & 3u, low = bit - 1u;
