@@ -6,7 +6,12 @@
 //   vector::convert::from_edges      :201-213   + order_cherries :449-477
 //   vector::convert::build_vector    :320-337   + Fenwick :286-316
 //
-// Formulation (validated on the CPU by tests/parallel_model.py):
+// Three kernels: encode_light_kernel (p2v_encode_light.cuh, round 2: one pass over the rows, 2 bytes of shared
+// memory per leaf -- from_pairs / from_ancestry at every size up to k = 262143, from_edges from k = 800),
+// encode_small_kernel below (round 1; today only from_edges with k < 800, which must not need a workspace) and
+// encode_large_kernel (CTA per tree, k > 262143).
+//
+// Formulation of the two round-1 kernels (validated on the CPU by tests/parallel_model.py):
 //  * build_vector: for the cherry whose c_max is c, idx = number of EARLIER rows
 //    with a smaller c_max.  Walking the values c upwards in batches of 32, idx is
 //    a prefix-popcount on the "rows already seen" bit mask (state at batch
@@ -25,8 +30,8 @@
 namespace p2v {
 
 constexpr int ENC_SMALL_WARPS = 4;
-constexpr int ENC_WARP_K_MAX = 4096;      // round-1 warp kernel with staged rows: only reachable with
-                                          // P2V_ENC_LIGHT_FROM above it (the light kernel takes 1024 < k <= 65535)
+constexpr int ENC_WARP_K_MAX = 4096;      // round-1 warp kernel with staged rows: above k = 800 only reachable with
+                                          // P2V_ENC_LIGHT_FROM set higher (tuning / comparison runs)
 constexpr int ENC_LARGE_THREADS = 256;
 constexpr int ENC_LARGE_WARPS = ENC_LARGE_THREADS / 32;
 
