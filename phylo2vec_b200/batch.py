@@ -69,9 +69,9 @@ def raise_for_status(status: torch.Tensor, v: Optional[torch.Tensor] = None) -> 
 
     Invalid vectors: AssertionError with check_max's message
     (phylo2vec/src/vector/base.rs:60-67)."""
-    bad = torch.nonzero(status)
-    if bad.numel() == 0:
+    if not bool(status.any()):          # the usual case: one reduction and one word back, nothing allocated
         return
+    bad = torch.nonzero(status)
     b = int(bad[0, 0])
     code = int(status[b])
     if code > 0:
