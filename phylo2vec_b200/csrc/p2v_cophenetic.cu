@@ -1170,8 +1170,10 @@ struct SmallLayout {
     size_t dec, anc, ja, jd, dl, dr, nxt, cnt, pos, leaf_at, dipos, sepd, ddpos, jh, jl, st, rowbuf, colk, total;
     size_t dec_stride, anc_stride;
     int levels, tpp;                    // tpp: trees decoded side by side per pass (one per warp)
+    bool wt;                            // tiny trees: every warp takes its tree through ALL phases (own copy of the tables)
+    size_t wt_stride;                   // bytes between the warps' table copies
 };
-__host__ __device__ inline SmallLayout small_layout(int k, bool topo) {
+__host__ __device__ inline SmallLayout small_layout(int k, bool topo, bool wt) {
     SmallLayout L;
     const size_t n = (size_t)k + 1, N = 2 * (size_t)k + 1, K = ((size_t)k + 31) & ~(size_t)31;
     L.levels = 1;                                       // floor(log2(n - 1)) + 1
@@ -1207,14 +1209,17 @@ __host__ __device__ inline SmallLayout small_layout(int k, bool topo) {
     o = al16(o);
     L.rowbuf = o; o = al16(o + (size_t)(CS_THREADS / 32) * 8 * P32);
     L.colk = o; o = al16(o + (size_t)(CS_THREADS / 32) * 4 * P32);     // column candidates of a warp's tile
-    L.total = (o > a1 ? o : a1);
+    L.total = al16(o > a1 ? o : a1);
+    L.wt = wt;
+    L.wt_stride = L.total - L.ja;
+    if (L.wt) L.total = L.ja + (size_t)L.tpp * L.wt_stride;
     return L;
 }
 
 
 // TILED: rows by tiles of 32 DFS positions with per-lane label-order columns in registers (pays off
 // from n ~ 150); otherwise one sparse-table query per element and a DFS-ordered row buffer.
-template <bool TOPO, bool VCV, bool VEC2, bool TILED, bool STAGED>
+template <bool TOPO, bool VCV, bool VEC2, bool TILED, bool STAGED, bool WT>
 __global__ void __launch_bounds__(CS_THREADS, 8)
 coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, int bl_stride, int64_t bl_tree_stride,
                   int64_t B, int k, int unrooted, int64_t row_begin, int64_t row_end, double* __restrict__ out,
@@ -1225,27 +1230,34 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
     __shared__ __align__(8) uint64_t s_bar[2];    // [1]: mbarrier of the staged branch lengths
     __shared__ uint8_t s_lut[2048];
     nth_bit_lut_init(s_lut, threadIdx.x, CS_THREADS);
-    const SmallLayout L = small_layout(k, TOPO);
+    const SmallLayout L = small_layout(k, TOPO, WT);
     const int n = k + 1, N = 2 * k + 1, K = (k + 31) & ~31, root = 2 * k;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = CS_THREADS / 32;
-    uint16_t* ja = reinterpret_cast<uint16_t*>(dyn + L.ja);
-    uint16_t* jd = reinterpret_cast<uint16_t*>(dyn + L.jd);
-    uint16_t* dl = reinterpret_cast<uint16_t*>(dyn + L.dl);
-    uint16_t* dr = reinterpret_cast<uint16_t*>(dyn + L.dr);
-    uint16_t* nxt = reinterpret_cast<uint16_t*>(dyn + L.nxt);
-    uint16_t* cnt = reinterpret_cast<uint16_t*>(dyn + L.cnt);
-    uint16_t* pos = reinterpret_cast<uint16_t*>(dyn + L.pos);
-    uint16_t* leaf_at = reinterpret_cast<uint16_t*>(dyn + L.leaf_at);
-    uint16_t* dipos = reinterpret_cast<uint16_t*>(dyn + L.dipos);
-    double2* sepd = reinterpret_cast<double2*>(dyn + L.sepd);
-    double2* ddpos = reinterpret_cast<double2*>(dyn + L.ddpos);
-    double* jh = reinterpret_cast<double*>(dyn + L.jh);
-    double* jl = reinterpret_cast<double*>(dyn + L.jl);
-    uint32_t* st = reinterpret_cast<uint32_t*>(dyn + L.st);
+    // tiny trees (n <= 32, L.wt): a 31-node tree keeps one warp busy at best, so each of the CTA's warps takes its
+    // own tree through tables and rows, on its own copy of the tables, with warp-level barriers only
+    unsigned char* const tb = dyn + (WT ? (size_t)warp * L.wt_stride : 0);
+    const int t0 = WT ? lane : tid;                                       // the thread's index / count in its team
+    constexpr int ts = WT ? 32 : CS_THREADS;
+    auto bar = [&]() { if (WT) __syncwarp(); else __syncthreads(); };
+    auto bar_or = [&](int x) -> int { return WT ? __any_sync(FULL, x) : __syncthreads_or(x); };
+    uint16_t* ja = reinterpret_cast<uint16_t*>(tb + L.ja);
+    uint16_t* jd = reinterpret_cast<uint16_t*>(tb + L.jd);
+    uint16_t* dl = reinterpret_cast<uint16_t*>(tb + L.dl);
+    uint16_t* dr = reinterpret_cast<uint16_t*>(tb + L.dr);
+    uint16_t* nxt = reinterpret_cast<uint16_t*>(tb + L.nxt);
+    uint16_t* cnt = reinterpret_cast<uint16_t*>(tb + L.cnt);
+    uint16_t* pos = reinterpret_cast<uint16_t*>(tb + L.pos);
+    uint16_t* leaf_at = reinterpret_cast<uint16_t*>(tb + L.leaf_at);
+    uint16_t* dipos = reinterpret_cast<uint16_t*>(tb + L.dipos);
+    double2* sepd = reinterpret_cast<double2*>(tb + L.sepd);
+    double2* ddpos = reinterpret_cast<double2*>(tb + L.ddpos);
+    double* jh = reinterpret_cast<double*>(tb + L.jh);
+    double* jl = reinterpret_cast<double*>(tb + L.jl);
+    uint32_t* st = reinterpret_cast<uint32_t*>(tb + L.st);
     const int rb_stride = (n + 31) & ~31;
-    double* rowbuf = reinterpret_cast<double*>(dyn + L.rowbuf) + (size_t)warp * rb_stride;
-    uint32_t* colk = reinterpret_cast<uint32_t*>(dyn + L.colk) + (size_t)warp * rb_stride;
+    double* rowbuf = reinterpret_cast<double*>(tb + L.rowbuf) + (size_t)warp * rb_stride;
+    uint32_t* colk = reinterpret_cast<uint32_t*>(tb + L.colk) + (size_t)warp * rb_stride;
     const int64_t rows = row_end - row_begin;
     const int stn = (n + 1 + 3) & ~3;             // entries per sparse-table level
 
@@ -1300,7 +1312,8 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
             if (lane == 0) { s_bad[warp] = bad; status[tree] = bad + 1; }
         }
         __syncthreads();
-        for (int sub = 0; sub < tpp && base + sub < B; ++sub) {
+        // tiny trees (WT): every warp takes its own tree through all the phases, with warp-level barriers only
+        for (int sub = WT ? warp : 0; sub < (WT ? warp + 1 : tpp) && base + sub < B; ++sub) {
         const int64_t tree = base + sub;
         const int64_t tree_next = (sub + 1 < tpp && tree + 1 < B) ? tree + 1 : base_next;
         Piece qb; qb.lead = 0; qb.tma = false;
@@ -1309,14 +1322,14 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
             if (qb.tma) { mbar_wait(&s_bar[1], par_bl); par_bl ^= 1u; }
         }
         if (s_bad[sub] >= 0) {                    // uniform: skip the tree, keep the staging going
-            if (!TOPO && stage_lengths) { __syncthreads(); stage_bl(tree_next); __syncthreads(); }
+            if (!TOPO && stage_lengths) { bar(); stage_bl(tree_next); bar(); }
             continue;
         }
         const int* anc = reinterpret_cast<const int*>(dyn + L.anc + sub * L.anc_stride);
         // ---- 2. parents, edge weights, first / last child pointers -----------------------------
         if (!TOPO && stage_lengths) {             // the staged lengths first: they sit where ja .. cnt are about to go
             const double* blt = sbl_stage + qb.lead / 8 + bl_first;
-            for (int r = tid; r < k; r += CS_THREADS) {
+            for (int r = t0; r < k; r += ts) {
                 const int c1 = anc[3 * r], c2 = anc[3 * r + 1];
                 double b1 = blt[(size_t)r * bl_stride], b2 = blt[(size_t)r * bl_stride + 1];
                 if (unrooted) {                   // graph.rs:46-50: the root edge to node 2k-1 has length 0
@@ -1325,13 +1338,13 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
                 }
                 jh[c1] = b1; jh[c2] = b2; jl[c1] = 0.0; jl[c2] = 0.0;
             }
-            if (tid == 0) { jh[root] = 0.0; jl[root] = 0.0; }
-            __syncthreads();
+            if (t0 == 0) { jh[root] = 0.0; jl[root] = 0.0; }
+            bar();
         }
-        for (int c = tid; c <= k; c += CS_THREADS) { dl[c] = (uint16_t)c; dr[c] = (uint16_t)c; }
+        for (int c = t0; c <= k; c += ts) { dl[c] = (uint16_t)c; dr[c] = (uint16_t)c; }
         const bool direct_bl = !TOPO && !stage_lengths;                 // lengths straight from global memory
         const double* blg = direct_bl ? bl + tree * bl_tree_stride : nullptr;
-        for (int r = tid; r < k; r += CS_THREADS) {
+        for (int r = t0; r < k; r += ts) {
             const int c1 = anc[3 * r], c2 = anc[3 * r + 1], p = k + 1 + r;
             double b1 = 1.0, b2 = 1.0;
             if (direct_bl) { b1 = blg[(size_t)r * bl_stride]; b2 = blg[(size_t)r * bl_stride + 1]; }
@@ -1345,11 +1358,11 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
             dl[p] = (uint16_t)c1; dr[p] = (uint16_t)c2;
             if (direct_bl) { jh[c1] = b1; jh[c2] = b2; jl[c1] = 0.0; jl[c2] = 0.0; }
         }
-        if (tid == 0) {
+        if (t0 == 0) {
             ja[root] = (uint16_t)CS_NONE; jd[root] = 0;
             if (!TOPO && !stage_lengths) { jh[root] = 0.0; jl[root] = 0.0; }
         }
-        __syncthreads();
+        bar();
         // ---- pointer jumping (buffers 0 / 1): root-path sums upwards, leftmost / rightmost leaf
         //      downwards (leaves are fixed points) ---------------------------------------------------
         int cur = 0;
@@ -1361,7 +1374,7 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
             const double* h_in = jh + cur * N; double* h_out = jh + (cur ^ 1) * N;
             const double* w_in = jl + cur * N; double* w_out = jl + (cur ^ 1) * N;
             int live = 0;
-            for (int x = tid; x < N; x += CS_THREADS) {
+            for (int x = t0; x < N; x += ts) {
                 const unsigned a = a_in[x];
                 unsigned d = d_in[x], na = CS_NONE;
                 dd f = {0.0, 0.0};
@@ -1379,58 +1392,58 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
                 if (!TOPO) { h_out[x] = f.hi; w_out[x] = f.lo; }
             }
             cur ^= 1;
-            if (!__syncthreads_or(live)) break;
+            if (!bar_or(live)) break;
         }
         const uint16_t* dres = jd + cur * N;
         const uint16_t* lres = dl + cur * N;
         const uint16_t* rres = dr + cur * N;
         // ---- leaves as a linked list in DFS order: every internal node links the last leaf of its
         //      first child's subtree to the first leaf of its second child's; ranking by jumping -----
-        for (int r = tid; r < k; r += CS_THREADS) {
+        for (int r = t0; r < k; r += ts) {
             const int a = rres[anc[3 * r]], b = lres[anc[3 * r + 1]];
             nxt[a] = (uint16_t)b; cnt[a] = 1;
         }
-        if (tid == 0) { const int e = rres[root]; nxt[e] = (uint16_t)CS_NONE; cnt[e] = 0; }
-        __syncthreads();
+        if (t0 == 0) { const int e = rres[root]; nxt[e] = (uint16_t)CS_NONE; cnt[e] = 0; }
+        bar();
         int lc = 0;
         for (;;) {
             const uint16_t* n_in = nxt + lc * n; uint16_t* n_out = nxt + (lc ^ 1) * n;
             const uint16_t* c_in = cnt + lc * n; uint16_t* c_out = cnt + (lc ^ 1) * n;
             int live = 0;
-            for (int x = tid; x < n; x += CS_THREADS) {
+            for (int x = t0; x < n; x += ts) {
                 const unsigned a = n_in[x];
                 unsigned c = c_in[x], na = CS_NONE;
                 if (a != CS_NONE) { c += c_in[a]; na = n_in[a]; live |= (na != CS_NONE); }
                 n_out[x] = (uint16_t)na; c_out[x] = (uint16_t)c;
             }
             lc ^= 1;
-            if (!__syncthreads_or(live)) break;
+            if (!bar_or(live)) break;
         }
         // ---- 3. positions, separators, sparse table -------------------------------------------
         {
             const uint16_t* cres = cnt + lc * n;          // leaves after this one
             const double* hres = jh + cur * N;
             const double* wres = jl + cur * N;
-            for (int c = tid; c <= k; c += CS_THREADS) {
+            for (int c = t0; c <= k; c += ts) {
                 const int p = k - cres[c];
                 pos[c] = (uint16_t)p; leaf_at[p] = (uint16_t)c; dipos[p] = dres[c];
                 if (!TOPO) ddpos[p] = make_double2(hres[c], wres[c]);
             }
-            for (int r = tid; r < k; r += CS_THREADS) {
+            for (int r = t0; r < k; r += ts) {
                 const int u = k + 1 + r;
                 const int rp = k - cres[lres[anc[3 * r + 1]]];     // first position of the second child
                 st[rp] = ((uint32_t)dres[u] << 16) | (uint32_t)rp;
                 if (!TOPO) sepd[rp] = make_double2(hres[u], wres[u]);
             }
-            if (tid == 0) { st[0] = 0xFFFFFFFFu; st[n] = 0xFFFFFFFFu; }
+            if (t0 == 0) { st[0] = 0xFFFFFFFFu; st[n] = 0xFFFFFFFFu; }
         }
-        __syncthreads();
+        bar();
         stage_bl(tree_next);                      // the jumping buffers are dead from here on: the next lengths land in them
         for (int lev = 1; lev < L.levels; ++lev) {
             const int half = 1 << (lev - 1);
-            for (int r = 1 + tid; r + (1 << lev) <= n; r += CS_THREADS)
+            for (int r = 1 + t0; r + (1 << lev) <= n; r += ts)
                 st[lev * stn + r] = min(st[(lev - 1) * stn + r], st[(lev - 1) * stn + r + half]);
-            __syncthreads();
+            bar();
         }
         if (!TILED) {
         // ---- 4. rows: every lane owns pairs of columns in LABEL order, (j, j + 1) with j = 64 lc + 2 lane, keeps
@@ -1456,9 +1469,9 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
                     if (!TOPO && CACHE) { cd0[lc] = ddpos[p0]; cd1[lc] = ddpos[p1]; }
                 }
             }
-            double* orow = out + ((size_t)tree * rows + warp) * n;
+            double* orow = out + ((size_t)tree * rows + (WT ? 0 : warp)) * n;
             const int i_end = (int)row_end;
-            for (int i = (int)row_begin + warp; i < i_end; i += NW, orow += (size_t)NW * n) {
+            for (int i = (int)row_begin + (WT ? 0 : warp); i < i_end; i += (WT ? 1 : NW), orow += (size_t)(WT ? 1 : NW) * n) {
                 const int q = pos[i];
                 const int di = dipos[q];
                 double2 dq = make_double2(0.0, 0.0);
@@ -1499,9 +1512,9 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
         else {
         // tiny trees (a pair of columns per lane leaves most lanes idle): the round-1 form, each row built in DFS
         // order in shared memory, one position per lane, and permuted on the way out
-        double* orow = out + ((size_t)tree * rows + warp) * n;
+        double* orow = out + ((size_t)tree * rows + (WT ? 0 : warp)) * n;
         const int i_end = (int)row_end;
-        for (int i = (int)row_begin + warp; i < i_end; i += NW, orow += (size_t)NW * n) {
+        for (int i = (int)row_begin + (WT ? 0 : warp); i < i_end; i += (WT ? 1 : NW), orow += (size_t)(WT ? 1 : NW) * n) {
             const int q = pos[i];
             const int di = dipos[q];
             double2 dq = make_double2(0.0, 0.0);
@@ -1680,7 +1693,7 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
             }
         }
         }
-        __syncthreads();                          // rows done before the next tree's tables are built
+        bar();                          // rows done before the next tree's tables are built
         }  // sub
     }
 }
@@ -1982,7 +1995,10 @@ static cudaError_t launch_cophenetic_small(const void* v_or_matrix, int idx_byte
     }
     const bool topo = (bl == nullptr);
     const int64_t n = k + 1;
-    const SmallLayout SL = small_layout((int)k, topo);
+    static const int wt_max = [] { const char* e = getenv("P2V_COPH_SMALL_WT_MAX"); return e ? atoi(e) : 40; }();
+    // tiny trees: a warp per tree through all phases (measured: +35 % at n = 16, +15 % at 40, -8 % at 64)
+    const bool wt = n <= wt_max && n <= 128;
+    const SmallLayout SL = small_layout((int)k, topo, wt);
     const size_t smem = SL.total;
     const int tpp = SL.tpp;
     const bool vec2 = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
@@ -1998,8 +2014,9 @@ static cudaError_t launch_cophenetic_small(const void* v_or_matrix, int idx_byte
     cudaError_t e = cudaSuccess;
 #define P2V_SMALL(T_, W_, V_)                                                                          \
     do {                                                                                               \
-        auto kern = tiled ? coph_small_kernel<T_, W_, V_, true, false> : coph_small_kernel<T_, W_, V_, false, false>; \
-        if (!T_ && stage_lengths) kern = tiled ? coph_small_kernel<T_, W_, V_, true, !T_> : coph_small_kernel<T_, W_, V_, false, !T_>; \
+        auto kern = tiled ? coph_small_kernel<T_, W_, V_, true, false, false> : coph_small_kernel<T_, W_, V_, false, false, false>; \
+        if (!T_ && stage_lengths) kern = tiled ? coph_small_kernel<T_, W_, V_, true, !T_, false> : coph_small_kernel<T_, W_, V_, false, !T_, false>; \
+        if (wt) kern = coph_small_kernel<T_, W_, V_, false, false, true>;                                  \
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
         if (e != cudaSuccess) return e;                                                                \
         int per_sm = 0;                                                                                \

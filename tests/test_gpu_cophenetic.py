@@ -75,7 +75,8 @@ def test_type_dispatch(p2v):
         p2v.cophenetic_distances(np.array([0, 5, 1]))
 
 
-SIZES = [1, 2, 3, 4, 5, 8, 9, 33, 63, 64, 65, 66, 100, 129, 500, 1000, 1001, 1026, 1100]
+# 40 / 41: warp-per-tree small kernel below, CTA-per-tree above; 128 / 129 and 160 / 161 / 320 / 321: the small kernel's other shapes
+SIZES = [1, 2, 3, 4, 5, 8, 9, 16, 31, 32, 33, 40, 41, 48, 63, 64, 65, 66, 100, 128, 129, 160, 161, 320, 321, 500, 1000, 1001, 1026, 1100]
 
 
 @pytest.mark.parametrize("n_leaves", SIZES)
