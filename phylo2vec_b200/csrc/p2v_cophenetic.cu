@@ -1957,7 +1957,7 @@ cudaError_t launch_cophenetic_rows(void* ws, size_t ws_bytes, int64_t B, int64_t
 static int coph_small_n_max() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("P2V_COPH_SMALL_NMAX");       // tuning knob for benchmarks/sweep.py
+        const char* e = getenv("P2V_COPH_SMALL_NMAX");       // tuning knob (comparison runs)
         v = e ? atoi(e) : CS_N_DEFAULT;
         if (v > CS_N_MAX) v = CS_N_MAX;
         if (v < 0) v = 0;

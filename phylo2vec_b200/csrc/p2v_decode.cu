@@ -295,10 +295,14 @@ decode_large_kernel(const IdxT* __restrict__ v, int64_t B, int k, IdxT* __restri
             for (int i = threadIdx.x * 8; i < TBL; i += THREADS * 8) *reinterpret_cast<uint4*>(s_tbl + i) = ones;
             team_sync<CSIZE>();                          // the labels of every slot are written (and the table is filled)
             if (wq == 1) {            // not warp 0: see gwr above
+                // (the labels come from L2: the loads of the next two batches are in flight while one is recorded)
+                auto ldlab = [&](int b) -> uint32_t { const int s = b * 32 + lane; return (b < b1 && s < k) ? (uint32_t)wlab[s] : 0u; };
+                uint32_t l1 = ldlab(b0), l2 = ldlab(b0 + 1);
                 for (int b = b0; b < b1; ++b) {
                     const int s = b * 32 + lane;
                     const bool act = s < k;
-                    const uint32_t lab = act ? ((uint32_t)wlab[s] & (ROOTBIT - 1u)) : 0u;
+                    const uint32_t lab = l1 & (ROOTBIT - 1u);
+                    l1 = l2; l2 = ldlab(b + 2);
                     const uint32_t peers = __match_any_sync(FULL, act ? lab : (0x40000000u + lane));
                     if (act && (peers & lanes_gt(lane)) == 0) s_tbl[lab] = (uint16_t)s;
                     __syncwarp();
@@ -536,7 +540,7 @@ constexpr int WARP_K_MAX = 16384;          // warp-per-tree kernel for batches o
 static int warp_k_max() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("P2V_DECODE_WARP_KMAX");      // tuning knob for benchmarks/sweep.py
+        const char* e = getenv("P2V_DECODE_WARP_KMAX");      // tuning knob (comparison runs)
         v = e ? atoi(e) : WARP_K_MAX;
         if (v > WARP_K_MAX) v = WARP_K_MAX;
         if (v < SMALL_K_MAX) v = SMALL_K_MAX;
