@@ -75,6 +75,10 @@ constexpr int ROW_NINCAP = 64;             // in-block columns per chunk whose v
 // stretches.  (Cutting at 64 rows AND at 1.25x their mean span, as round 1 did, left tiles of 36 rows
 // on average: both lattices cut all the time.)  `bsz` bounds the positions in a block (capacity of
 // the in-block tables), `nidb` the number of block ids.
+static bool tables_smem_on() {            // P2V_TABLES_SMEM=0: the global-memory tables kernel for every size (comparison runs)
+    static const int v = [] { const char* e = getenv("P2V_TABLES_SMEM"); return e ? atoi(e) : 1; }();
+    return v != 0;
+}
 struct CophCall { int pcap, rcap, bsz, nidb, nincap; };
 inline CophCall coph_call(int64_t n, int64_t m) {
     CophCall c;
@@ -465,6 +469,150 @@ tables_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* 
         }
         team_sync<CSIZE>();
         phase_stamp(3, CSIZE == 0 && tid == 0);
+    }
+}
+
+// The same tables for BATCHES of mid-size trees (2k + 1 < 65536 nodes that fit shared memory), one CTA per tree with ALL
+// the jumping state in shared memory: node ids and topological depths as uint16, the leaf list as (next | count << 16).
+// tables_kernel<1> spends its time in dependent gathers from L2 (three per radix-4 round, about a dozen rounds);
+// here a round is shared-memory latency.  Writes exactly what the later kernels read: jDI / jDH / jDL by node,
+// pos, leaf_at, sepk / sephi / seplo by position.
+__host__ __device__ inline size_t tables_smem_bytes(int64_t k, bool weighted) {
+    const size_t N = 2 * (size_t)k + 1, NP = (N + 7) & ~(size_t)7;
+    return 8 * NP * sizeof(uint16_t) + (weighted ? 2 * N * sizeof(double2) : 0);
+}
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(TAB_THREADS)
+tables_smem_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const double* __restrict__ bl, int bl_stride,
+                   int64_t bl_tree_stride, int64_t B, int k, int unrooted, const int32_t* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char tsm[];
+    const CophLayout L = coph_layout(k);
+    const int n = L.n, N = L.N, root = 2 * k;
+    const int NP = (N + 7) & ~7;
+    const int tid = threadIdx.x, TT = blockDim.x;
+    constexpr unsigned NONE = 0xFFFFu;
+    uint16_t* const a16 = reinterpret_cast<uint16_t*>(tsm);      // [2][NP] ancestor
+    uint16_t* const dep = a16 + 2 * NP;                          // [2][NP] depth below that ancestor
+    uint16_t* const dl0 = dep + 2 * NP;                          // [2][NP] leftmost leaf
+    uint16_t* const dr0 = dl0 + 2 * NP;                          // [2][NP] rightmost leaf
+    double2* const dd2 = reinterpret_cast<double2*>(dr0 + 2 * NP);   // [2][N] double-double depth          [WEIGHTED]
+    uint32_t* const ln = reinterpret_cast<uint32_t*>(tsm);       // [2][n] leaf list, over a16 / dep once they are read
+    for (int64_t tree = blockIdx.x; tree < B; tree += gridDim.x) {
+        if (status && status[tree] != 0) continue;               // uniform per CTA
+        unsigned char* T = tab + (size_t)tree * tab_stride;
+        const int* anc = reinterpret_cast<const int*>(T + L.anc);
+        int* jDI = reinterpret_cast<int*>(T + L.jDI);
+        double* jDH = reinterpret_cast<double*>(T + L.jDH);
+        double* jDL = reinterpret_cast<double*>(T + L.jDL);
+        int* pos = reinterpret_cast<int*>(T + L.pos);
+        int* leaf_at = reinterpret_cast<int*>(T + L.leaf_at);
+        int* sepk = reinterpret_cast<int*>(T + L.sepk);
+        double* sephi = reinterpret_cast<double*>(T + L.sephi);
+        double* seplo = reinterpret_cast<double*>(T + L.seplo);
+        const double* blt = WEIGHTED ? bl + tree * bl_tree_stride : nullptr;
+        if (tid < TAB_FLAGS) reinterpret_cast<int*>(T + L.flags)[tid] = 0;     // as tables_kernel leaves them
+        __syncthreads();                                         // the previous tree's readers are done
+        for (int r = tid; r < k; r += TT) {
+            const int c1 = anc[3 * r], c2 = anc[3 * r + 1], p = k + 1 + r;
+            int w1 = 1, w2 = 1;
+            if (unrooted) {                                      // graph.rs:46-50: the root edge to node 2k-1 has length 0
+                if (c1 == 2 * k - 1) w1 = 0;
+                if (c2 == 2 * k - 1) w2 = 0;
+            }
+            a16[c1] = (uint16_t)p; a16[c2] = (uint16_t)p;
+            dep[c1] = (uint16_t)w1; dep[c2] = (uint16_t)w2;
+            if (WEIGHTED) {
+                dd2[c1] = make_double2(w1 ? blt[(size_t)r * bl_stride] : 0.0, 0.0);
+                dd2[c2] = make_double2(w2 ? blt[(size_t)r * bl_stride + 1] : 0.0, 0.0);
+            }
+            dl0[p] = (uint16_t)c1; dr0[p] = (uint16_t)c2;
+        }
+        for (int c = tid; c <= k; c += TT) { dl0[c] = (uint16_t)c; dr0[c] = (uint16_t)c; }
+        if (tid == 0) { a16[root] = (uint16_t)NONE; dep[root] = 0; if (WEIGHTED) dd2[root] = make_double2(0.0, 0.0); }
+        __syncthreads();
+        // root-path sums and leftmost / rightmost leaves by radix-4 pointer jumping
+        int cur = 0;
+        for (;;) {
+            const uint16_t* a_in = a16 + cur * NP; uint16_t* a_out = a16 + (cur ^ 1) * NP;
+            const uint16_t* p_in = dep + cur * NP; uint16_t* p_out = dep + (cur ^ 1) * NP;
+            const uint16_t* l_in = dl0 + cur * NP; uint16_t* l_out = dl0 + (cur ^ 1) * NP;
+            const uint16_t* r_in = dr0 + cur * NP; uint16_t* r_out = dr0 + (cur ^ 1) * NP;
+            const double2* d_in = dd2 + cur * N; double2* d_out = dd2 + (cur ^ 1) * N;
+            int live = 0;
+            for (int u = tid; u < N; u += TT) {
+                unsigned nl = l_in[u], nr = r_in[u];             // leaves are fixed points
+                unsigned a = a_in[u], dsum = p_in[u];
+                dd d = {0.0, 0.0};
+                if (WEIGHTED) { const double2 x = d_in[u]; d = dd{x.x, x.y}; }
+#pragma unroll
+                for (int hop = 0; hop < 3; ++hop) {
+                    nl = l_in[nl]; nr = r_in[nr];
+                    if (a != NONE) {
+                        if (WEIGHTED) { const double2 x = d_in[a]; d = dd_add(d, dd{x.x, x.y}); }
+                        dsum += p_in[a];
+                        a = a_in[a];
+                    }
+                }
+                live |= ((int)nl > k) | ((int)nr > k) | (a != NONE);
+                l_out[u] = (uint16_t)nl; r_out[u] = (uint16_t)nr;
+                a_out[u] = (uint16_t)a; p_out[u] = (uint16_t)dsum;
+                if (WEIGHTED) d_out[u] = make_double2(d.hi, d.lo);
+            }
+            cur ^= 1;
+            if (!__syncthreads_or(live)) break;
+        }
+        const uint16_t* dl = dl0 + cur * NP;
+        const uint16_t* dr = dr0 + cur * NP;
+        {   // depth of every node, where the other kernels read it
+            const uint16_t* p_res = dep + cur * NP;
+            const double2* d_res = dd2 + cur * N;
+            for (int u = tid; u < N; u += TT) {
+                jDI[u] = (int)p_res[u];
+                if (WEIGHTED) { const double2 x = d_res[u]; jDH[u] = x.x; jDL[u] = x.y; }
+            }
+        }
+        __syncthreads();                                         // a16 / dep are read: the leaf list takes their place
+        // the leaves as a linked list in DFS order (see tables_kernel), ranked by pointer jumping
+        for (int r = tid; r < k; r += TT) {
+            const unsigned a = dr[anc[3 * r]], b = dl[anc[3 * r + 1]];
+            ln[a] = b | (1u << 16);
+        }
+        if (tid == 0) ln[dr[root]] = NONE;                       // the last leaf: no successor, nothing after it
+        __syncthreads();
+        int lc = 0;
+        for (;;) {
+            const uint32_t* in = ln + lc * n; uint32_t* out = ln + (lc ^ 1) * n;
+            int live = 0;
+            for (int x = tid; x < n; x += TT) {
+                uint32_t s = in[x];
+                unsigned nx = s & 0xFFFFu, cnt = s >> 16;
+#pragma unroll
+                for (int hop = 0; hop < 3; ++hop) {
+                    if (nx != NONE) { const uint32_t t = in[nx]; nx = t & 0xFFFFu; cnt += t >> 16; }
+                }
+                live |= (nx != NONE);
+                out[x] = nx | (cnt << 16);
+            }
+            lc ^= 1;
+            if (!__syncthreads_or(live)) break;
+        }
+        const uint32_t* after = ln + lc * n;                     // >> 16 = number of leaves after this one
+        for (int c = tid; c <= k; c += TT) {
+            const int p = k - (int)(after[c] >> 16);
+            pos[c] = p;
+            leaf_at[p] = c;
+        }
+        if (tid == 0) {
+            sepk[0] = KEY_INF; sepk[n] = KEY_INF;
+            if (WEIGHTED) { sephi[0] = 0.0; seplo[0] = 0.0; sephi[n] = 0.0; seplo[n] = 0.0; }
+        }
+        for (int u = k + 1 + tid; u <= 2 * k; u += TT) {          // jDI / jDH / jDL: this CTA's own stores, two barriers ago
+            const int c1 = anc[3 * (u - k - 1) + 1];             // child 1: its first leaf opens the right part
+            const int r = k - (int)(after[dl[c1]] >> 16);
+            sepk[r] = jDI[u];
+            if (WEIGHTED) { sephi[r] = jDH[u]; seplo[r] = jDL[u]; }
+        }
     }
 }
 
@@ -1841,6 +1989,22 @@ cudaError_t launch_cophenetic_prepare(const void* v_or_matrix, int idx_bytes, co
                                                           unrooted, st, stream) ||
                        launch_tables_cluster<8>(tab, L.total, bl, bl_stride, bl_tree_stride, B, (int)k, unrooted,
                                                 st, stream);
+        }
+        if (!launched && 2 * k + 1 < 65535 && tables_smem_bytes(k, bl != nullptr) <= (size_t)220 * 1024 && tables_smem_on()) {
+            // batches of mid-size trees: the jumping state of a tree fits shared memory
+            const size_t smem = tables_smem_bytes(k, bl != nullptr);
+            auto kern = bl ? tables_smem_kernel<true> : tables_smem_kernel<false>;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            int per_sm = 0;
+            static const int th_env = [] { const char* e2 = getenv("P2V_TABLES_SMEM_THREADS"); return e2 ? atoi(e2) : TAB_THREADS; }();
+            const int th = th_env;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, th, smem);
+            if (e != cudaSuccess) return e;
+            const int64_t capt = (int64_t)sm_count() * (per_sm < 1 ? 1 : per_sm);
+            kern<<<(int)(B < capt ? B : capt), th, smem, stream>>>(tab, L.total, bl, bl_stride, bl_tree_stride, B,
+                                                                  (int)k, unrooted, st);
+            launched = true;
         }
         if (!launched) {
             const int grid = (int)(B < cap ? B : cap);
