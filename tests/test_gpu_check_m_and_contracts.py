@@ -151,6 +151,28 @@ def test_alignment_contract(p2v):
     assert np.array_equal(p2v.to_pairs_batch(V).cpu().numpy(), O.batch("to_pairs", V.cpu().numpy(), k)[0])
 
 
+@pytest.mark.parametrize("n_leaves", [130, 131, 200, 257, 320])
+def test_staged_branch_lengths_at_any_alignment(p2v, n_leaves):
+    """For 128 < n <= 320 the branch lengths of a tree reach the small-tree kernel by a TMA bulk copy of the 16-byte
+    pieces that cover its matrix rows.  Matrices that start 8 bytes off a 16-byte boundary (an odd k, a view into a
+    bigger buffer) shift every second tree's block: same distances, bit for bit, as from an aligned copy, including
+    the first and last tree, whose pieces would reach outside the array."""
+    B, k = 7, n_leaves - 1
+    V = sample_vectors(B, n_leaves, seed=3 * n_leaves)
+    M = np.stack([to_matrix_input(V[b], sample_bls(1, n_leaves, b)[0]) for b in range(B)])
+    want = p2v.cophenetic_distances_batch(torch.from_numpy(M).cuda())
+    for lead in (1, 2, 3):                                  # 8, 16, 24 bytes into a buffer
+        big = torch.zeros(B * k * 3 + 8, dtype=torch.float64, device="cuda")
+        view = big[lead:lead + B * k * 3].view(B, k, 3)
+        view.copy_(torch.from_numpy(M))
+        assert view.data_ptr() % 16 == (8 * lead) % 16
+        assert torch.equal(p2v.cophenetic_distances_batch(view), want), (n_leaves, lead)
+        assert torch.equal(p2v.vcv_batch(view), p2v.vcv_batch(torch.from_numpy(M).cuda())), (n_leaves, lead)
+    ref = O.cophenetic_distances(M[B - 1])
+    got = want[B - 1].cpu().numpy()
+    assert np.max(np.abs(got - ref) / np.maximum(ref, 1e-300)) <= 1e-12
+
+
 def test_status_tensor_is_validated(p2v):
     V = torch.from_numpy(sample_vectors(4, 30, seed=2)).cuda()
     for bad in (torch.zeros(4, dtype=torch.int64, device="cuda"), torch.zeros(3, dtype=torch.int32, device="cuda"),
