@@ -113,6 +113,12 @@ csv_parse_kernel(const char* __restrict__ s, int64_t nbytes, char delim, int64_t
                  const unsigned long long* __restrict__ bases, void* __restrict__ out_v, int64_t capacity,
                  int* __restrict__ err) {
     __shared__ int s_cnt[CSV_CPT][CSV_THREADS / 32];
+    // literals of more than 19 digits that the fast parser leaves undecided (about one in a thousand of those):
+    // queued, then decided exactly by one thread with the big-number scratch below (p2v_float_text.cuh)
+    constexpr int UNDQ = 32;
+    __shared__ int s_undn;
+    __shared__ long long s_und[UNDQ][3];
+    __shared__ uint32_t s_big[KIND == 1 ? 2 * p2v_ft::FT_BIG_LIMBS : 2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         bool start[CSV_CPT];
@@ -133,6 +139,7 @@ csv_parse_kernel(const char* __restrict__ s, int64_t nbytes, char delim, int64_t
 #pragma unroll
             for (int c = 0; c < CSV_CPT; ++c) s_cnt[c][warp] = __popc(ball[c]);
         }
+        if (threadIdx.x == 0) s_undn = 0;
         __syncthreads();
 #pragma unroll
         for (int c = 0; c < CSV_CPT; ++c) {
@@ -161,10 +168,28 @@ csv_parse_kernel(const char* __restrict__ s, int64_t nbytes, char delim, int64_t
                 reinterpret_cast<IdxT*>(out_v)[idx] = ok ? (IdxT)(neg ? -v : v) : (IdxT)-1;
             } else {
                 double x = 0.0;
-                ok = ok && p2v_ft::parse_f64(s + i0, (int)(i1 - i0), &x) == p2v_ft::PARSE_F64_OK;
+                if (ok) {
+                    const int rc = p2v_ft::parse_f64(s + i0, (int)(i1 - i0), &x);
+                    if (rc == p2v_ft::PARSE_F64_UNDECIDED) {
+                        const int slot = atomicAdd(&s_undn, 1);
+                        if (slot < UNDQ) { s_und[slot][0] = i0; s_und[slot][1] = i1; s_und[slot][2] = idx; }
+                        else ok = false;
+                    } else ok = rc == p2v_ft::PARSE_F64_OK;
+                }
                 reinterpret_cast<double*>(out_v)[idx] = x;
             }
             if (!ok) atomicOr(err, 1);
+        }
+        __syncthreads();
+        if (KIND == 1 && threadIdx.x == 0) {
+            const int nu = s_undn < UNDQ ? s_undn : UNDQ;
+            for (int u = 0; u < nu; ++u) {
+                double x = 0.0;
+                const int rc = p2v_ft::parse_f64_exact(s + s_und[u][0], (int)(s_und[u][1] - s_und[u][0]), s_big,
+                                                       s_big + p2v_ft::FT_BIG_LIMBS, &x);
+                if (rc != p2v_ft::PARSE_F64_OK) atomicOr(err, 1);
+                reinterpret_cast<double*>(out_v)[s_und[u][2]] = x;
+            }
         }
         __syncthreads();
     }

@@ -10,7 +10,8 @@
 //       Algorithm: Eisel-Lemire (Lemire, "Number parsing at a gigabyte per second", SP&E 2021; with the
 //       128-bit product it needs no fallback for up to 19 significant digits, Mushtak & Lemire 2023).
 //       Longer mantissas are cut to 19 digits and decided when the cut and the cut + 1 round to the same
-//       double (virtually always); otherwise PARSE_F64_UNDECIDED is returned -- the one documented gap.
+//       double (virtually always); otherwise PARSE_F64_UNDECIDED is returned and the caller takes the literal to
+//       parse_f64_exact (big-number comparison with the midpoint of the two candidates).
 //
 // Compiled as plain C++ too (tests/float_text_host.cpp checks both routines against Python's repr / float on
 // millions of values without a GPU).
@@ -348,6 +349,120 @@ P2V_HD int parse_f64(const char* s, int len, double* out) {
         }
     }
     *out = neg ? -v : v;
+    return PARSE_F64_OK;
+}
+
+// ------------------------------------------------------------------------- exact decision for long literals
+// parse_f64 leaves a literal of more than 19 significant digits undecided when its 19-digit cut and the cut + 1
+// round to different doubles (about one such literal in a thousand): the literal then lies within 1e-19 (relative)
+// of the midpoint of two adjacent doubles v < v1.  parse_f64_exact decides it exactly: all significant digits D
+// (up to FT_MAX_DIGITS; the midpoint of two doubles has at most 767) and the midpoint (2m + 1) 2^(e-1) are
+// brought to integers -- multiply by 5^|E10| on one side, shift by the powers of two -- and compared as big
+// numbers in caller-supplied scratch (2 x FT_BIG_LIMBS words; the callers keep one per warp or CTA, the slow
+// path is run by one thread at a time).  Ties go to the even mantissa, like Rust's str::parse::<f64>.
+constexpr int FT_MAX_DIGITS = 800;
+constexpr int FT_BIG_LIMBS = 96;              // 3072 bits: both sides stay below 2750 bits
+
+P2V_HD bool bn_mul_add(uint32_t* a, int& n, uint32_t mul, uint32_t add) {
+    uint64_t carry = add;
+    for (int i = 0; i < n; ++i) {
+        const uint64_t t = (uint64_t)a[i] * mul + carry;
+        a[i] = (uint32_t)t; carry = t >> 32;
+    }
+    if (carry) { if (n >= FT_BIG_LIMBS) return false; a[n++] = (uint32_t)carry; }
+    return true;
+}
+P2V_HD bool bn_mul_pow5(uint32_t* a, int& n, int64_t k) {
+    for (; k >= 13; k -= 13) if (!bn_mul_add(a, n, 1220703125u, 0u)) return false;      // 5^13
+    uint32_t r = 1;
+    for (; k > 0; --k) r *= 5u;
+    return r == 1u || bn_mul_add(a, n, r, 0u);
+}
+P2V_HD bool bn_shl(uint32_t* a, int& n, int64_t bits) {
+    if (n == 0 || bits <= 0) return true;
+    const int words = (int)(bits >> 5), sh = (int)(bits & 31);
+    if (n + words + 1 > FT_BIG_LIMBS) return false;
+    uint32_t top = 0;
+    if (sh) {
+        for (int i = 0; i < n; ++i) { const uint32_t x = a[i]; a[i] = (x << sh) | top; top = x >> (32 - sh); }
+        if (top) a[n++] = top;
+    }
+    if (words) {
+        for (int i = n - 1; i >= 0; --i) a[i + words] = a[i];
+        for (int i = 0; i < words; ++i) a[i] = 0;
+        n += words;
+    }
+    return true;
+}
+P2V_HD int bn_cmp(const uint32_t* a, int na, const uint32_t* b, int nb) {
+    if (na != nb) return na > nb ? 1 : -1;
+    for (int i = na - 1; i >= 0; --i) if (a[i] != b[i]) return a[i] > b[i] ? 1 : -1;
+    return 0;
+}
+
+// s[0 .. len): a literal parse_f64 returned PARSE_F64_UNDECIDED for (any valid literal works).  A, Bn: FT_BIG_LIMBS words each.
+P2V_HD int parse_f64_exact(const char* s, int len, uint32_t* A, uint32_t* Bn, double* out) {
+    int i = 0;
+    bool neg = false;
+    if (i < len && (s[i] == '+' || s[i] == '-')) { neg = s[i] == '-'; ++i; }
+    uint64_t w = 0;
+    int nd = 0, nbig = 0, na = 0;       // digits in w (<= 19), digits in A (<= FT_MAX_DIGITS), limbs of A
+    int64_t exp19 = 0, expbig = 0;      // decimal exponents that go with w and with A
+    bool any_digit = false, sticky = false;
+    auto take = [&](int dgt, bool frac) -> bool {
+        if (nd == 0 && dgt == 0) { if (frac) { --exp19; --expbig; } return true; }          // leading zeros
+        if (nd < 19) { w = w * 10 + (uint64_t)dgt; ++nd; if (frac) --exp19; } else if (!frac) ++exp19;
+        if (nbig < FT_MAX_DIGITS) { if (!bn_mul_add(A, na, 10u, (uint32_t)dgt)) return false; ++nbig; if (frac) --expbig; }
+        else { sticky |= dgt != 0; if (!frac) ++expbig; }
+        return true;
+    };
+    for (; i < len && s[i] >= '0' && s[i] <= '9'; ++i) { any_digit = true; if (!take(s[i] - '0', false)) return PARSE_F64_UNDECIDED; }
+    if (i < len && s[i] == '.') {
+        ++i;
+        for (; i < len && s[i] >= '0' && s[i] <= '9'; ++i) { any_digit = true; if (!take(s[i] - '0', true)) return PARSE_F64_UNDECIDED; }
+    }
+    if (!any_digit) return PARSE_F64_INVALID;
+    if (i < len && (s[i] == 'e' || s[i] == 'E')) {
+        ++i;
+        bool eneg = false;
+        if (i < len && (s[i] == '+' || s[i] == '-')) { eneg = s[i] == '-'; ++i; }
+        if (i >= len) return PARSE_F64_INVALID;
+        int64_t e = 0;
+        bool edig = false;
+        for (; i < len && s[i] >= '0' && s[i] <= '9'; ++i) { edig = true; if (e < 100000) e = e * 10 + (s[i] - '0'); }
+        if (!edig) return PARSE_F64_INVALID;
+        exp19 += eneg ? -e : e; expbig += eneg ? -e : e;
+    }
+    if (i != len) return PARSE_F64_INVALID;
+    if (w == 0) { *out = neg ? -0.0 : 0.0; return PARSE_F64_OK; }
+    const double v = el_compute(exp19, w), v1 = el_compute(exp19, w + 1);
+    double r = v;
+    if (f64_bits(v) != f64_bits(v1)) {
+        // v = m 2^e (m < 2^53), its successor v1 = (m + 1) 2^e: the midpoint is (2m + 1) 2^(e - 1)
+        const uint64_t bits = f64_bits(v);
+        const int ef = (int)((bits >> 52) & 0x7FF);
+        const uint64_t m = (bits & ((1ull << 52) - 1)) | (ef ? (1ull << 52) : 0ull);
+        const int64_t e2 = (ef ? ef - 1075 : -1074) - 1;
+        const uint64_t mid = 2 * m + 1;
+        int nb = 0;
+        Bn[nb++] = (uint32_t)mid;
+        if (mid >> 32) Bn[nb++] = (uint32_t)(mid >> 32);
+        // A 10^expbig  against  Bn 2^e2
+        bool fits = true;
+        if (expbig >= 0) {
+            fits = bn_mul_pow5(A, na, expbig);
+            const int64_t sh = e2 - expbig;                       // A 5^E  against  Bn 2^(e2 - E)
+            fits = fits && (sh >= 0 ? bn_shl(Bn, nb, sh) : bn_shl(A, na, -sh));
+        } else {
+            const int64_t F = -expbig, t = e2 + F;                // A  against  Bn 5^F 2^(e2 + F)
+            fits = bn_mul_pow5(Bn, nb, F);
+            fits = fits && (t >= 0 ? bn_shl(Bn, nb, t) : bn_shl(A, na, -t));
+        }
+        if (!fits) return PARSE_F64_UNDECIDED;
+        const int c = bn_cmp(A, na, Bn, nb);
+        if (c > 0 || (c == 0 && (sticky || (m & 1)))) r = v1;
+    }
+    *out = neg ? -r : r;
     return PARSE_F64_OK;
 }
 

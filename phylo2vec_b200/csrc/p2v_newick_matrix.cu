@@ -151,6 +151,8 @@ newick_matrix_parse_kernel(const char* __restrict__ in, int64_t in_stride, const
                            int maxlen, uint32_t* __restrict__ scratch, size_t scratch_words) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int N = 2 * k + 1;
+    // big-number scratch of the exact decision for long literals (p2v_float_text.cuh: parse_f64_exact), one per warp
+    __shared__ uint32_t s_big[NM_WARPS][2 * p2v_ft::FT_BIG_LIMBS];
     uint32_t* scr = scratch + ((size_t)blockIdx.x * nwarps + warp) * scratch_words;
     uint32_t* pos = scr;
     uint32_t* ks = pos + N;
@@ -220,7 +222,7 @@ newick_matrix_parse_kernel(const char* __restrict__ in, int64_t in_stride, const
         if (nnodes != N || nleaves != k + 1) bad = 1;
         __syncwarp();
         // ---- 2. every token: label, ":" and length ---------------------------------------------------
-        int any_lab = 0, any_nolab = 0;
+        int any_lab = 0, any_nolab = 0, und = 0;
         if (!bad) {
             for (int idx = lane; idx < N; idx += 32) {
                 const int start = (int)pos[idx];
@@ -236,7 +238,12 @@ newick_matrix_parse_kernel(const char* __restrict__ in, int64_t in_stride, const
                     const int f0 = i + 1;
                     int f1 = f0;
                     while (f1 < len && !nm_delim(s[f1])) ++f1;
-                    if (f1 - f0 > 400 || p2v_ft::parse_f64(s + f0, f1 - f0, &x) != p2v_ft::PARSE_F64_OK) bad = 1;
+                    if (f1 - f0 > 1200) bad = 1;
+                    else {
+                        const int rc = p2v_ft::parse_f64(s + f0, f1 - f0, &x);
+                        if (rc == p2v_ft::PARSE_F64_UNDECIDED) und = 1;                 // decided below, one lane at a time
+                        else if (rc != p2v_ft::PARSE_F64_OK) bad = 1;
+                    }
                     has_bl = true;
                     i = f1;
                 }
@@ -256,6 +263,37 @@ newick_matrix_parse_kernel(const char* __restrict__ in, int64_t in_stride, const
             if (lane == 0 && (ks[N - 1] & ~NM_INT) != 1u) bad = 1;
         }
         bad = __any_sync(FULL, bad) ? 1 : 0;
+        if (!bad && __any_sync(FULL, und)) {
+            // lengths of more than 19 digits that the fast parser left undecided (about one in a thousand of those):
+            // the lanes that saw one find it again and decide it exactly, one at a time on the warp's big-number scratch
+            for (int base = 0; base < N; base += 32) {
+                const int idx = base + lane;
+                int f0 = 0, f1 = 0;
+                bool need = false;
+                if (und && idx < N) {
+                    int i = (int)pos[idx] + ((ks[idx] & NM_INT) ? 1 : 0);
+                    while (i < len && s[i] >= '0' && s[i] <= '9') ++i;
+                    if (i < len && s[i] == ':') {
+                        f0 = i + 1; f1 = f0;
+                        while (f1 < len && !nm_delim(s[f1])) ++f1;
+                        double tmp;
+                        need = p2v_ft::parse_f64(s + f0, f1 - f0, &tmp) == p2v_ft::PARSE_F64_UNDECIDED;
+                    }
+                }
+                unsigned m = __ballot_sync(FULL, need);
+                while (m) {
+                    const int turn = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (lane == turn) {
+                        double x = 0.0;
+                        if (p2v_ft::parse_f64_exact(s + f0, f1 - f0, s_big[warp], s_big[warp] + p2v_ft::FT_BIG_LIMBS, &x) != p2v_ft::PARSE_F64_OK) bad = 1;
+                        bl[idx] = x;
+                    }
+                    __syncwarp();
+                }
+            }
+            bad = __any_sync(FULL, bad) ? 1 : 0;
+        }
         any_lab = __any_sync(FULL, any_lab); any_nolab = __any_sync(FULL, any_nolab);
         if (any_lab && any_nolab) bad = 1;                                       // parent labels on some ")" only
         const bool labelled = any_lab != 0;

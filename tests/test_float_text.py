@@ -143,7 +143,78 @@ def test_parse_grammar_and_long_mantissas(lib):
             undecided += 1
         else:
             assert r == 0 and v == float(s), s
-    assert undecided <= len(strings) // 400           # about 2^-10 of such literals: the documented gap
+    assert undecided <= len(strings) // 400           # about 2^-10 of such literals go on to parse_f64_exact (below)
     # the classic hard case sits exactly on a boundary: reported, never mis-rounded
     _, rc = parse_many(lib, ["9007199254740993.0000000000000000000000001"])
     assert rc[0] in (0, 2)
+
+
+def parse_full_many(lib, strings, exact_only=False):
+    """parse_f64, then parse_f64_exact for what it left undecided -- what the kernels do."""
+    stride = max(len(s) for s in strings) + 1
+    buf = np.zeros((len(strings), stride), dtype=np.uint8)
+    lens = np.array([len(s) for s in strings], dtype=np.int32)
+    for i, s in enumerate(strings):
+        buf[i, :len(s)] = np.frombuffer(s.encode(), dtype=np.uint8)
+    out = np.zeros(len(strings))
+    rc = np.zeros(len(strings), dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)       # noqa: E731
+    und = ctypes.c_long(0)
+    if exact_only:
+        lib.ft_parse_exact_many(p(buf), p(lens), ctypes.c_long(len(strings)), stride, p(out), p(rc))
+    else:
+        lib.ft_parse_full_many(p(buf), p(lens), ctypes.c_long(len(strings)), stride, p(out), p(rc), ctypes.byref(und))
+    return out, rc, und.value
+
+
+def hard_long_literals(rng, n_doubles, n_random):
+    """Literals of more than 19 digits: the exact midpoints of neighbouring doubles written out in full (ties go to
+    the even mantissa), the same one unit above and below in a far digit, and random long digit strings."""
+    from decimal import Decimal, getcontext
+    getcontext().prec = 1200
+    out = []
+    xs = rng.integers(0, 1 << 63, n_doubles, dtype=np.uint64).view(np.float64)
+    xs = np.concatenate([xs[np.isfinite(xs) & (xs != 0)], [5e-324, 2.2250738585072014e-308, 2.225073858507201e-308,
+                                                          1.0, 0.1, 9007199254740992.0, 1e23, 8.98846567431158e307]])
+    for d in xs.tolist():
+        d2 = float(np.nextafter(d, np.inf))
+        if not np.isfinite(d2):
+            continue
+        m = (Decimal(d) + Decimal(d2)) / 2
+        s = format(m, "f") if 1e-5 < abs(m) < 1e20 else format(m, "e").replace("e+", "e")
+        mant, _, ex = s.partition("e")
+        tail = "e" + ex if ex else ""
+        out.append(s)                                         # the tie itself
+        out.append(mant + "1" + tail)                         # just above
+        md = list(mant)
+        j = len(md) - 1
+        while j >= 0 and md[j] in ".0":
+            j -= 1
+        if j >= 0 and md[j].isdigit():
+            md[j] = str(int(md[j]) - 1)
+            out.append("".join(md) + "99999" + tail)          # just below
+    for _ in range(n_random):
+        nd = int(rng.integers(20, 60))
+        digs = ("".join(map(str, rng.integers(0, 10, nd)))).lstrip("0") or "1"
+        cut = int(rng.integers(0, len(digs) + 1))
+        e = int(rng.integers(-340, 311))
+        out.append(digs[:cut] + "." + digs[cut:] + (f"e{e}" if rng.random() < 0.7 else ""))
+    return out
+
+
+def test_long_literals_are_decided_exactly(lib):
+    rng = np.random.Generator(np.random.Philox(5))
+    strings = hard_long_literals(rng, 3000, 40_000)
+    want = np.array([float(s) for s in strings])
+    out, rc, undecided = parse_full_many(lib, strings)
+    assert undecided > 2000                               # the ties and their neighbours do take the slow path
+    assert not rc.any()
+    assert np.array_equal(out, want) and np.array_equal(np.signbit(out), np.signbit(want))
+    # the exact routine alone agrees with the fast one wherever that decides
+    out2, rc2, _ = parse_full_many(lib, strings, exact_only=True)
+    assert not rc2.any() and np.array_equal(out2, want)
+    # 800 significant digits are kept; anything beyond only matters as "not zero"
+    one = "1." + "0" * 900 + "1"
+    tie = format(__import__("decimal").Decimal(1.0) + __import__("decimal").Decimal(2.0) ** -53, "f")
+    out3, rc3, _ = parse_full_many(lib, [one, tie, tie + "0" * 900 + "1", tie[:-1] + "4" + "9" * 900])
+    assert not rc3.any() and out3.tolist() == [1.0, 1.0, float(np.nextafter(1.0, 2.0)), 1.0]

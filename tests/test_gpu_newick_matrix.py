@@ -134,6 +134,38 @@ def test_to_matrix_batch_against_oracle(p2v, n_leaves):
             p2v.to_matrix_batch(mixed)
 
 
+@pytest.mark.parametrize("n_leaves", [5, 40, 300])
+def test_long_literals_are_read_exactly(p2v, n_leaves, tmp_path):
+    """Branch lengths of more than 19 significant digits, many of them exactly half way between two doubles or a
+    hair beside it: the fast parser leaves those undecided and parse_f64_exact settles them -- the matrix is the one
+    Python's (and Rust's) correctly rounded float() gives, bit for bit.  The same through the CSV reader."""
+    from tests.test_float_text import hard_long_literals
+    B = 6
+    M = matrices(B, n_leaves, seed=77 + n_leaves)
+    rng = np.random.Generator(np.random.Philox(n_leaves))
+    lits = [x for x in hard_long_literals(rng, 400, 300) if not x.startswith("-") and len(x) < 900]
+    strings = []
+    for b in range(B):
+        it = iter(rng.permutation(len(lits)).tolist())
+        strings.append(re.sub(r":([0-9.e+-]+)", lambda mm: ":" + lits[next(it)], O.to_newick_matrix(M[b])))
+    want = np.stack([O.from_newick_matrix(s) for s in strings])              # Python float(): correctly rounded
+    got = p2v.to_matrix_batch(strings).cpu().numpy()
+    assert np.array_equal(got, want)
+    # CSV: one flattened matrix per line, lengths written as the same long literals
+    k = n_leaves - 1
+    lines = []
+    lits = [x for x in lits if len(x) < 500]                                # the CSV reader's fields are shorter than 512 bytes
+    for b in range(B):
+        it = iter(rng.permutation(len(lits)).tolist())
+        lines.append(",".join(f"{int(want[b, r, 0])},{lits[next(it)]},{lits[next(it)]}" for r in range(k)))
+    path = tmp_path / "long.csv"
+    path.write_text("\n".join(lines) + "\n")
+    from phylo2vec_b200.io import reader
+    got_csv = reader.load_batch(str(path), kind="matrix", check=False).cpu().numpy()
+    want_csv = np.array([[float(x) for x in ln.split(",")] for ln in lines]).reshape(B, k, 3)
+    assert np.array_equal(got_csv, want_csv)
+
+
 def test_host_entry_points(p2v):
     from phylo2vec_b200 import _capi
     lib = _capi.load()
