@@ -133,6 +133,27 @@ __device__ __forceinline__ void batch_rank_pair_vals15(uint32_t x1, uint32_t x0,
     R_hi = (R >> 16) - (uint32_t)lane;
 }
 
+// The same shuffles, but the two fields are taken apart before the compare: two independent chains of
+// (ISETP, predicated IADD) per step instead of one chain of five dependent operations.  One more instruction per
+// step, half the dependent latency: for the trees that leave few warps on an SM (k > 8192) latency is what counts.
+__device__ __forceinline__ void batch_rank_pair_vals15s(uint32_t x1, uint32_t x0, int b, int k, int lane,
+                                                        uint32_t& R_hi, uint32_t& R_lo) {
+    const int t1 = b * 32 + lane, t0 = t1 - 32;
+    const uint32_t i1 = (t1 < k) ? (x1 <= (uint32_t)t1 ? 0u : x1 - (uint32_t)t1) : 0x7FFFu;
+    const uint32_t i0 = (t0 >= 0) ? (x0 <= (uint32_t)t0 ? 0u : x0 - (uint32_t)t0) : 0x7FFFu;
+    const uint32_t ins = i0 | (i1 << 16);
+    uint32_t R0 = i0, R1 = i1;
+#pragma unroll
+    for (int d = 1; d < 32; ++d) {
+        const uint32_t y = __shfl_down_sync(FULL, ins, d);
+        const uint32_t y0 = y & 0xFFFFu, y1 = y >> 16;
+        if (y0 <= R0) ++R0;
+        if (y1 <= R1) ++R1;
+    }
+    R_lo = R0 - (uint32_t)lane;                            // the `lane` wrapped steps always count
+    R_hi = R1 - (uint32_t)lane;
+}
+
 // uint16 entries of per-tree scratch the warp needs: sv, stime, (stbl), then the free-slot mask.
 // Mid-size trees (wpl > 2, the "light" form): only stbl and the mask live in shared memory -- v is read
 // from global memory batch by batch, and the (time, value) of every slot goes through the tree's own
@@ -237,7 +258,11 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
     };
     auto rank_pair = [&](int b, uint32_t& hi, uint32_t& lo) {      // batches b (hi) and b - 1 (lo)
         if (WPL <= 2) batch_rank_pair(sv, b, k, lane, hi, lo);
-        else { take_v(b); issue_v(b - 2); batch_rank_pair_vals15(xv_hi, xv_lo, b, k, lane, hi, lo); }
+        else {
+            take_v(b); issue_v(b - 2);
+            if (WPL >= 16) batch_rank_pair_vals15s(xv_hi, xv_lo, b, k, lane, hi, lo);
+            else batch_rank_pair_vals15(xv_hi, xv_lo, b, k, lane, hi, lo);
+        }
     };
     // The rank scan of the NEXT pair of batches is resumable (scan_begin / scan_step / scan_end) and
     // its 31 steps are issued between the dependent shuffles of the two placements of the CURRENT
@@ -379,7 +404,8 @@ __device__ __forceinline__ int decode_tree_warp(const IdxT* __restrict__ vt, int
     if (nb & 1) {                                  // odd number of batches: the top one goes alone
         if (LIGHT) {                               // (its "lower" batch bp - 1 is scanned again as the next pair's upper one)
             take_v(bp); issue_v(bp - 1);
-            batch_rank_pair_vals15(xv_hi, xv_lo, bp, k, lane, Rn_hi, Rn_lo);
+            if (WPL >= 16) batch_rank_pair_vals15s(xv_hi, xv_lo, bp, k, lane, Rn_hi, Rn_lo);
+            else batch_rank_pair_vals15(xv_hi, xv_lo, bp, k, lane, Rn_hi, Rn_lo);
         } else rank_pair(bp, Rn_hi, Rn_lo);
         place(bp, Rn_hi, xv_hi, fill_none);
         --bp;
