@@ -22,7 +22,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libphylo2vec_b200.so")
 LIB_DBG = os.path.join(LIBDIR, "libphylo2vec_b200_dbg.so")
-DBG_SOURCES = ["p2v_decode.cu", "p2v_encode.cu"]      # the kernels with scattered shared-memory tables
+DBG_SOURCES = ["p2v_decode.cu", "p2v_encode.cu", "p2v_cophenetic.cu"]      # the kernels with scattered shared-memory tables
 SOURCES = ["p2v_capi.cu", "p2v_decode.cu", "p2v_encode.cu", "p2v_cophenetic.cu", "p2v_newick.cu", "p2v_treewise.cu", "p2v_newick_matrix.cu", "p2v_csv.cu"]
 HEADERS = ["p2v_common.cuh", "p2v_internal.h", "p2v_decode_warp.cuh", "p2v_decode_warp_big.cuh", "p2v_encode_light.cuh", "p2v_tree_pass.cuh", "p2v_float_text.cuh", "p2v_float_tables.h", os.path.join("..", "..", "include", "phylo2vec_b200.h")]
 

@@ -520,6 +520,7 @@ tables_smem_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const dou
                 if (c1 == 2 * k - 1) w1 = 0;
                 if (c2 == 2 * k - 1) w2 = 0;
             }
+            P2V_CHECK_INDEX(c1, N); P2V_CHECK_INDEX(c2, N); P2V_CHECK_INDEX(p, N);
             a16[c1] = (uint16_t)p; a16[c2] = (uint16_t)p;
             dep[c1] = (uint16_t)w1; dep[c2] = (uint16_t)w2;
             if (WEIGHTED) {
@@ -547,8 +548,10 @@ tables_smem_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const dou
                 if (WEIGHTED) { const double2 x = d_in[u]; d = dd{x.x, x.y}; }
 #pragma unroll
                 for (int hop = 0; hop < 3; ++hop) {
+                    P2V_CHECK_INDEX(nl, N); P2V_CHECK_INDEX(nr, N);
                     nl = l_in[nl]; nr = r_in[nr];
                     if (a != NONE) {
+                        P2V_CHECK_INDEX(a, N);
                         if (WEIGHTED) { const double2 x = d_in[a]; d = dd_add(d, dd{x.x, x.y}); }
                         dsum += p_in[a];
                         a = a_in[a];
@@ -576,6 +579,7 @@ tables_smem_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const dou
         // the leaves as a linked list in DFS order (see tables_kernel), ranked by pointer jumping
         for (int r = tid; r < k; r += TT) {
             const unsigned a = dr[anc[3 * r]], b = dl[anc[3 * r + 1]];
+            P2V_CHECK_INDEX(a, n); P2V_CHECK_INDEX(b, n);
             ln[a] = b | (1u << 16);
         }
         if (tid == 0) ln[dr[root]] = NONE;                       // the last leaf: no successor, nothing after it
@@ -600,6 +604,7 @@ tables_smem_kernel(unsigned char* __restrict__ tab, size_t tab_stride, const dou
         const uint32_t* after = ln + lc * n;                     // >> 16 = number of leaves after this one
         for (int c = tid; c <= k; c += TT) {
             const int p = k - (int)(after[c] >> 16);
+            P2V_CHECK_INDEX(p, n);
             pos[c] = p;
             leaf_at[p] = c;
         }
@@ -1501,6 +1506,7 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
                 if (c1 == 2 * k - 1) { w1 = 0; b1 = 0.0; }
                 if (c2 == 2 * k - 1) { w2 = 0; b2 = 0.0; }
             }
+            P2V_CHECK_INDEX(c1, N); P2V_CHECK_INDEX(c2, N); P2V_CHECK_INDEX(p, N);
             ja[c1] = (uint16_t)p; ja[c2] = (uint16_t)p;
             jd[c1] = (uint16_t)w1; jd[c2] = (uint16_t)w2;
             dl[p] = (uint16_t)c1; dr[p] = (uint16_t)c2;
@@ -1549,6 +1555,7 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
         //      first child's subtree to the first leaf of its second child's; ranking by jumping -----
         for (int r = t0; r < k; r += ts) {
             const int a = rres[anc[3 * r]], b = lres[anc[3 * r + 1]];
+            P2V_CHECK_INDEX(a, n); P2V_CHECK_INDEX(b, n);
             nxt[a] = (uint16_t)b; cnt[a] = 1;
         }
         if (t0 == 0) { const int e = rres[root]; nxt[e] = (uint16_t)CS_NONE; cnt[e] = 0; }
@@ -1574,12 +1581,14 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
             const double* wres = jl + cur * N;
             for (int c = t0; c <= k; c += ts) {
                 const int p = k - cres[c];
+                P2V_CHECK_INDEX(p, n);
                 pos[c] = (uint16_t)p; leaf_at[p] = (uint16_t)c; dipos[p] = dres[c];
                 if (!TOPO) ddpos[p] = make_double2(hres[c], wres[c]);
             }
             for (int r = t0; r < k; r += ts) {
                 const int u = k + 1 + r;
                 const int rp = k - cres[lres[anc[3 * r + 1]]];     // first position of the second child
+                P2V_CHECK_INDEX(rp, n + 1);
                 st[rp] = ((uint32_t)dres[u] << 16) | (uint32_t)rp;
                 if (!TOPO) sepd[rp] = make_double2(hres[u], wres[u]);
             }
@@ -1628,11 +1637,13 @@ coph_small_kernel(const int* __restrict__ v32, const double* __restrict__ bl, in
                     if (p == q) return VCV ? (TOPO ? int_to_f64(di) : dq.x) : 0.0;
                     const int a = min(p, q) + 1, b = max(p, q);
                     const int lev = 31 - __clz(b - a + 1);
+                    P2V_CHECK_INDEX(lev, L.levels); P2V_CHECK_INDEX(a, stn); P2V_CHECK_INDEX(b - (1 << lev) + 1, stn);
                     const uint32_t m = min(st[lev * stn + a], st[lev * stn + b - (1 << lev) + 1]);
                     if (TOPO) {
                         const int dlca = (int)(m >> 16);
                         return VCV ? int_to_f64(dlca) : int_to_f64(di + dj_i - 2 * dlca);
                     }
+                    P2V_CHECK_INDEX(m & 0xFFFFu, n + 1);
                     const double2 sd = sepd[m & 0xFFFFu];
                     if (VCV) return sd.x;
                     return __dadd_rn(dd_sub_round(dq.x, dq.y, sd.x, sd.y), dd_sub_round(dj.x, dj.y, sd.x, sd.y));

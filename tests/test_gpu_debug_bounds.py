@@ -1,4 +1,4 @@
-"""The decode / encode kernels once more through the -DP2V_DEBUG_BOUNDS build (libphylo2vec_b200_dbg.so): every index
+"""The decode / encode / distance kernels once more through the -DP2V_DEBUG_BOUNDS build (libphylo2vec_b200_dbg.so): every index
 into a shared-memory table is asserted on the device, a bad one traps and fails the launch.  compute-sanitizer is
 closed on the GPU pool; this is the memory check that runs instead, over the sizes where the kernels change shape."""
 
@@ -38,6 +38,22 @@ for n in sizes:
         assert torch.equal(p2v.from_edges_batch(p2v.to_edges_batch(Vd)), Vd), n
     one = torch.from_numpy(V[:2]).cuda()                       # a few trees: the CTA / cluster / whole-grid kernels
     assert torch.equal(p2v.from_ancestry_batch(p2v.to_ancestry_batch(one)), one), n
+    torch.cuda.synchronize()
+# the distance kernels with shared-memory tables: the fused small-tree kernel in all its shapes, the shared-memory
+# tables kernel of mid-size batches
+from oracle import p2v_oracle as O
+from tests.helpers import sample_bls, to_matrix_input
+for n in [3, 4, 16, 32, 33, 40, 41, 64, 100, 128, 129, 161, 200, 320, 321, 700, 2000]:
+    B = 5
+    V = sample_vectors(B, n, seed=7 * n)
+    M = np.stack([to_matrix_input(V[b], sample_bls(1, n, b)[0]) for b in range(B)])
+    Dt = p2v.cophenetic_distances_batch(torch.from_numpy(V).cuda()).cpu().numpy()
+    Df = p2v.cophenetic_distances_batch(torch.from_numpy(M).cuda()).cpu().numpy()
+    Cv = p2v.vcv_batch(torch.from_numpy(M).cuda()).cpu().numpy()
+    assert np.isfinite(Cv).all()
+    if n <= 700:
+        ref = O.cophenetic_distances(V[0]); assert np.array_equal(Dt[0], ref), n
+        ref = O.cophenetic_distances(M[1]); assert np.max(np.abs(Df[1] - ref) / np.maximum(ref, 1e-300)) <= 1e-12, n
     torch.cuda.synchronize()
 print("bounds ok", len(sizes))
 """
