@@ -173,6 +173,29 @@ def test_staged_branch_lengths_at_any_alignment(p2v, n_leaves):
     assert np.max(np.abs(got - ref) / np.maximum(ref, 1e-300)) <= 1e-12
 
 
+@pytest.mark.parametrize("n_leaves", [130, 200, 320])
+def test_invalid_trees_between_staged_ones(p2v, n_leaves):
+    """A batch for the small-tree kernel's staged (TMA) path with invalid vectors at the start, in the middle, twice in a
+    row and at the end: the skipped trees keep the copy / barrier sequence going, their neighbours get the distances
+    of a clean batch, and the statuses name the bad entries."""
+    B, k = 11, n_leaves - 1
+    V = sample_vectors(B, n_leaves, seed=5 * n_leaves)
+    M = np.stack([to_matrix_input(V[b], sample_bls(1, n_leaves, b)[0]) for b in range(B)])
+    clean = p2v.cophenetic_distances_batch(torch.from_numpy(M).cuda()).cpu().numpy()
+    bad = M.copy()
+    for b in (0, 4, 5, 10):
+        bad[b, 7, 0] = 2 * 7 + 1                      # v[7] out of range
+    st = torch.zeros(B, dtype=torch.int32, device="cuda")
+    got = p2v.cophenetic_distances_batch(torch.from_numpy(bad).cuda(), status=st, check=False).cpu().numpy()
+    torch.cuda.synchronize()
+    want_st = np.zeros(B, dtype=np.int32)
+    want_st[[0, 4, 5, 10]] = 8
+    assert np.array_equal(st.cpu().numpy(), want_st)
+    for b in range(B):
+        if want_st[b] == 0:
+            assert np.array_equal(got[b], clean[b]), b
+
+
 def test_status_tensor_is_validated(p2v):
     V = torch.from_numpy(sample_vectors(4, 30, seed=2)).cuda()
     for bad in (torch.zeros(4, dtype=torch.int64, device="cuda"), torch.zeros(3, dtype=torch.int32, device="cuda"),
