@@ -127,6 +127,29 @@ def build_vector_model(cherries):
     return v
 
 
+def build_vector_rows_model(cherries):
+    """The round-2 form (p2v_encode_light.cuh): the same index taken in ROW order, 32 rows at a time --
+    idx(row) = #{earlier rows with a smaller c_max} = the c_max values already seen below this one (prefix count
+    on a "values seen" mask, state before the batch) + the lower lanes of the batch with a smaller c_max.  No
+    table of rows by value; the mask doubles as the permutation check."""
+    ch = np.asarray(cherries, dtype=np.int64).reshape(-1, 3)
+    k = len(ch)
+    seen = np.zeros(k + 1, dtype=bool)                           # by value
+    v = np.zeros(k, dtype=np.int64)
+    for a in range(0, k, W):
+        e = min(k, a + W)
+        cm = ch[a:e, 2]
+        assert ((cm >= 1) & (cm <= k)).all() and not seen[cm].any() and len(set(cm.tolist())) == len(cm), "not a permutation"
+        idx = np.array([seen[:c].sum() for c in cm])             # prefix count on the mask
+        for lane in range(e - a):                                 # in-batch: lower lanes with a smaller value
+            idx[lane] += sum(1 for l2 in range(lane) if cm[l2] < cm[lane])
+        for lane in range(e - a):
+            r = a + lane
+            v[cm[lane] - 1] = min(ch[r, 0], ch[r, 1]) if idx[lane] == 0 else cm[lane] - 1 + idx[lane]
+        seen[cm] = True
+    return v
+
+
 def min_desc_cherries_model(anc):
     """build_cherries (convert.rs:399-440): sequential semantics."""
     anc = np.asarray(anc, dtype=np.int64).reshape(-1, 3)
@@ -473,3 +496,57 @@ def ancestry_forward_model(v):
             q = tbl[t[l] + 1]
             anc[a + l] = (c1[l], k + 1 + q if q >= 0 else t[l] + 1, k + 1 + a + l)
     return anc
+
+
+# --------------------------------------------------------------------------
+# Robinson-Foulds by Day's algorithm (p2v_treewise.cu; reference: vector/distance.rs:41-162)
+# --------------------------------------------------------------------------
+def robinson_foulds_day_model(v1, v2):
+    """Leaves renumbered by their DFS rank in tree 1, rotated so that leaf 0 has rank 0; a split of tree 1 is the
+    interval of ranks on the side WITHOUT leaf 0; tree 2 supplies (min, max, count) of the ranks below every node and of
+    everything outside it; a contiguous side without leaf 0 is looked up.  RF = |S1| + |S2| - 2 shared."""
+    from oracle import p2v_oracle as O
+    n = len(v1) + 1
+    if n < 4:
+        return 0.0
+    k = n - 1
+
+    def children(v):
+        anc = O.to_ancestry(np.asarray(v))
+        ch = {}
+        for c1, c2, p in anc.tolist():
+            ch[p] = (c1, c2)
+        return ch, 2 * k
+
+    def below(ch, root):                                          # leaves below every node, iteratively
+        leaves = {x: [x] for x in range(n)}
+        for p in sorted(ch):                                      # parents are created after their children
+            leaves[p] = leaves[ch[p][0]] + leaves[ch[p][1]]
+        return leaves
+
+    ch1, root1 = children(v1)
+    order = below(ch1, root1)[root1]                              # DFS order of tree 1
+    at0 = order.index(0)
+    rank = {leaf: (i - at0) % n for i, leaf in enumerate(order)}
+
+    def splits(ch, root, contiguous_only):
+        out = set()
+        for p, leaves in below(ch, root).items():
+            if p == root:
+                continue
+            r = sorted(rank[x] for x in leaves)
+            side = r if 0 not in r else sorted(set(range(n)) - set(r))      # the side without leaf 0
+            if len(side) <= 1 or len(side) >= n - 1:
+                continue                                          # trivial split
+            if side[-1] - side[0] + 1 == len(side):
+                out.add(("interval", side[0], side[-1]))
+            elif not contiguous_only:
+                out.add(("set",) + tuple(side))
+        return out
+
+    s1 = splits(ch1, root1, False)
+    assert all(t[0] == "interval" for t in s1)                   # in tree 1's own order every split is an interval
+    ch2, root2 = children(v2)
+    s2_all = splits(ch2, root2, False)
+    shared = len(s1 & s2_all)
+    return float(len(s1) + len(s2_all) - 2 * shared)

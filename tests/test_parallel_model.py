@@ -28,6 +28,8 @@ def test_encode_model(n_leaves):
         ch = np.concatenate([pairs, pairs.max(axis=1, keepdims=True)], axis=1)
         assert np.array_equal(M.build_vector_model(ch), v)
         assert np.array_equal(M.build_vector_model(M.min_desc_cherries_model(O.to_ancestry(v))), v)
+        assert np.array_equal(M.build_vector_rows_model(ch), v)                     # the one-pass form of round 2
+        assert np.array_equal(M.build_vector_rows_model(M.min_desc_cherries_model(O.to_ancestry(v))), v)
 
 
 @pytest.mark.parametrize("n_leaves", [3, 4, 5, 8, 9, 17, 40, 70])
@@ -65,3 +67,11 @@ def test_merge_slot_assignment_and_forward_sweep(n_leaves):
         ref, _ = M.slot_assignment(v)
         assert np.array_equal(M.slot_assignment_merge(v), ref)
         assert np.array_equal(M.ancestry_forward_model(v), O.to_ancestry(v))
+
+
+@pytest.mark.parametrize("n_leaves", [2, 3, 4, 5, 8, 33, 64, 100])
+def test_robinson_foulds_day_model(n_leaves):
+    vs = list(sample_vectors(5, n_leaves, seed=3 * n_leaves)) + list(adversarial_vectors(n_leaves).values())
+    for a in range(len(vs)):
+        for b in (a, (a + 1) % len(vs), (a + 3) % len(vs)):
+            assert M.robinson_foulds_day_model(vs[a], vs[b]) == O.robinson_foulds(vs[a], vs[b])
